@@ -1,0 +1,265 @@
+/*
+ * svtb200.h -- C ABI of libsvtvp9_b200.so: the B200 (sm_100a) implementation of SVT-VP9's
+ * per-block encode hot path (motion estimation, forward/inverse transform + quantisation,
+ * in-loop deblocking).
+ *
+ * Plain C: pointers, sizes and POD structs only.  Every entry point returns 0 on success and a
+ * negative SVTB200_E* code on failure (the reference-side shim then falls back to the reference's
+ * own CPU kernel for that unit of work: results are identical by construction).
+ *
+ * Reference interfaces replaced (all paths relative to the reference tree):
+ *   S1  motion_estimate_sb()            Source/Lib/Codec/EbMotionEstimation.c:4524
+ *         -> svtb200_picture_upload() + svtb200_me_picture()       (one call per picture, all SBs)
+ *   S2  eb_vp9_loop_filter_frame()      Source/Lib/VPX/vp9_loopfilter.c:1521
+ *         -> svtb200_deblock_picture()                             (one call per picture)
+ *   S3  RTCD kernels bound in setup_rtcd_internal()  Source/Lib/VPX/vpx_dsp_rtcd.h:1123,
+ *       setup_rtcd_internal_vp9() Source/Lib/VPX/vp9_rtcd.h:138, used by perform_coding_loop()
+ *       Source/Lib/Codec/EbEncDecProcess.c:365 and perform_inv_trans_add() :589
+ *         -> svtb200_fwd_txfm_batch / svtb200_quantize_batch / svtb200_inv_txfm_add_batch
+ *            (batched twins of eb_vp9_fdct* / fht*, eb_vp9_quantize_b[_32x32], eb_vp9_idct*_add/iht*_add)
+ *         -> svtb200_txq_batch (fused residual -> transform -> quantise -> [inverse + recon])
+ *
+ * "Host" entry points take HOST pointers (pinned or pageable) and perform the host<->device copies
+ * themselves; the "_dev" twins take device pointers already resident in HBM.
+ */
+#ifndef SVTB200_H
+#define SVTB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVTB200_OK 0
+#define SVTB200_ENODEV (-1)   /* no CUDA device / CUDA runtime failure at create */
+#define SVTB200_EINVAL (-2)   /* bad parameter */
+#define SVTB200_ENOMEM (-3)   /* device or pinned allocation failed */
+#define SVTB200_ECUDA (-4)    /* a launch or copy failed; see svtb200_last_error() */
+#define SVTB200_ENOENT (-5)   /* unknown picture id */
+
+typedef struct SvtB200Ctx SvtB200Ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int         svtb200_create(int device, SvtB200Ctx **out);
+void        svtb200_destroy(SvtB200Ctx *ctx);
+const char *svtb200_last_error(const SvtB200Ctx *ctx);
+int         svtb200_sync(SvtB200Ctx *ctx);
+/* number of kernel launches issued by this context since creation (bench "gpu_launches") */
+uint64_t    svtb200_launch_count(const SvtB200Ctx *ctx);
+/* raw cudaStream_t the context launches on (for CUDA-event timing by the caller) */
+void       *svtb200_stream(SvtB200Ctx *ctx);
+
+/* ---- pinned host memory (the "pinned async copies" of the staging path) ------------------- */
+void *svtb200_host_alloc(size_t bytes);
+void  svtb200_host_free(void *p);
+/* device memory helpers for the *_dev entry points (tests / bench) */
+void *svtb200_dev_alloc(SvtB200Ctx *ctx, size_t bytes);
+void  svtb200_dev_free(SvtB200Ctx *ctx, void *p);
+int   svtb200_memcpy_h2d(SvtB200Ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int   svtb200_memcpy_d2h(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+
+/* =============================================================================================
+ * S1  Motion estimation
+ * ============================================================================================= */
+
+/* One 8-bit plane with its padding, as in EbPictureBufferDesc (Source/Lib/Codec/EbPictureBufferDesc.h:27):
+ * buf points at the first byte of the PADDED buffer; the picture's (0,0) sample is at
+ * buf[origin_y * stride + origin_x]. */
+typedef struct SvtB200Plane {
+    const uint8_t *buf;
+    int32_t        stride;
+    int32_t        origin_x, origin_y; /* padding on the left / top */
+    int32_t        width, height;      /* without padding */
+    int32_t        padded_height;      /* rows in buf (height + top + bottom padding) */
+} SvtB200Plane;
+
+/* The three planes of an EbPaReferenceObject (Source/Lib/Codec/EbReferenceObject.h:37): padded
+ * source luma, its 1/4 (2:1 x 2:1) and 1/16 (4:1 x 4:1) point decimations.  quarter may have
+ * buf == NULL when HME level 1 is disabled. */
+int svtb200_picture_upload(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane *full,
+                           const SvtB200Plane *quarter, const SvtB200Plane *sixteenth);
+/* Upload only the full-resolution padded luma; the 1/4 and 1/16 decimations (+ their padding)
+ * are produced on the device exactly as eb_vp9_decimation_2d + eb_vp9_generate_padding would
+ * (Source/Lib/Codec/EbPictureAnalysisProcess.c:102, :5025). quarter_pad/sixteenth_pad are the
+ * origin_x(=origin_y) of the decimated planes (reference: 32+... see DESIGN.md). */
+int svtb200_picture_upload_luma(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane *full,
+                                int32_t quarter_pad, int32_t sixteenth_pad, int make_quarter);
+int svtb200_picture_release(SvtB200Ctx *ctx, uint64_t pic_id);
+
+/* Everything motion_estimate_sb() reads from MeContext / PictureParentControlSet /
+ * SequenceControlSet (EbMotionEstimationContext.h:275, EbPictureControlSet.h:229). */
+typedef struct SvtB200MeParams {
+    /* picture */
+    int32_t luma_width, luma_height;        /* SequenceControlSet::luma_width/height */
+    int32_t num_lists;                      /* 1: P picture (list 0), 2: B picture (lists 0,1) */
+    int32_t temporal_layer_index;
+    int32_t hierarchical_levels;
+    uint64_t ref_poc[2];                    /* pcs->ref_pic_poc_array */
+    /* HME */
+    int32_t enable_hme_flag, enable_hme_level0, enable_hme_level1, enable_hme_level2;
+    int32_t single_hme_quadrant;
+    int32_t number_hme_search_region_in_width, number_hme_search_region_in_height;
+    int32_t hme_level0_total_search_area_width, hme_level0_total_search_area_height;
+    int32_t hme_level0_search_area_in_width[2], hme_level0_search_area_in_height[2];
+    int32_t hme_level1_search_area_in_width[2], hme_level1_search_area_in_height[2];
+    int32_t hme_level2_search_area_in_width[2], hme_level2_search_area_in_height[2];
+    int32_t hme_l0_multiplier_x, hme_l0_multiplier_y; /* hme_level_0_search_area_multiplier_x/y[hier][tl], percent */
+    /* full-pel */
+    int32_t search_area_width, search_area_height;
+    /* sub-pel */
+    int32_t fractional_search_method; /* 0 SUB_SAD_SEARCH, 1 FULL_SAD_SEARCH, 2 SSD_SEARCH (EbDefinitions.h:664-666) */
+    int32_t fractional_search_model;  /* 0 all on, 1 su_pel_enable(), 2 all off */
+    int32_t fractional_search64x64;
+    int32_t cu8x8_mode, cu16x16_mode; /* pcs->cu8x8_mode / cu16x16_mode */
+    int32_t rate_control_mode;        /* != 0 -> rcme_distortion is produced */
+} SvtB200MeParams;
+
+/* Same 40-byte layout as MeCuResults (Source/Lib/Codec/EbMotionEstimationLcuResults.h:36-56). */
+typedef struct SvtB200MeCuResult {
+    int16_t x_mv_l0, y_mv_l0, x_mv_l1, y_mv_l1; /* quarter-pel units */
+    struct {
+        uint32_t distortion;
+        uint32_t direction; /* 0 uni L0, 1 uni L1, 2 bi */
+    } cand[3];
+    uint8_t total_me_candidate_index;
+    uint8_t pad_[7];
+} SvtB200MeCuResult;
+
+#define SVTB200_ME_PUS_PER_SB 85
+
+/* Motion-estimate every 64x64 super-block of picture cur_id against ref_id[0..num_lists-1].
+ * out_results: HOST buffer of n_sb * 85 entries (raster SB order, reference PU order);
+ * out_rcme_distortion: HOST buffer of n_sb uint32 or NULL.  Blocks until the results are in
+ * host memory. */
+int svtb200_me_picture(SvtB200Ctx *ctx, const SvtB200MeParams *params, uint64_t cur_id,
+                       const uint64_t ref_id[2], SvtB200MeCuResult *out_results,
+                       uint32_t *out_rcme_distortion);
+/* Device-resident variant: results stay in HBM (out_results_dev from svtb200_dev_alloc);
+ * asynchronous on the context stream. */
+int svtb200_me_picture_dev(SvtB200Ctx *ctx, const SvtB200MeParams *params, uint64_t cur_id,
+                           const uint64_t ref_id[2], SvtB200MeCuResult *out_results_dev,
+                           uint32_t *out_rcme_distortion_dev);
+
+/* =============================================================================================
+ * S3  Transform / quantisation (batched)
+ * ============================================================================================= */
+
+enum { SVTB200_TX_4X4 = 0, SVTB200_TX_8X8 = 1, SVTB200_TX_16X16 = 2, SVTB200_TX_32X32 = 3 };
+enum { SVTB200_DCT_DCT = 0, SVTB200_ADST_DCT = 1, SVTB200_DCT_ADST = 2, SVTB200_ADST_ADST = 3 };
+
+/* The five 2-entry (DC, AC) rows quantize_b reads (Source/Lib/VPX/quantize.c:112):
+ * zbin, round, quant, quant_shift, dequant -- produced by eb_vp9_init_quantizer
+ * (Source/Lib/VPX/vp9_quantize.c:206) on the reference host. */
+typedef struct SvtB200QuantRow {
+    int16_t zbin[2], round[2], quant[2], quant_shift[2], dequant[2];
+} SvtB200QuantRow;
+
+/* Scan order tables (VP9 bitstream constants; Source/Lib/VPX/vp9_scan.c): scan[i] = raster
+ * position of the i-th coefficient, iscan = inverse.  One pair per (tx_size, tx_type);
+ * 32x32 uses tx_type 0 only.  Must be registered before any quantize / txq call. */
+int svtb200_set_scan(SvtB200Ctx *ctx, int tx_size, int tx_type, const int16_t *scan,
+                     const int16_t *iscan);
+
+/* Batched eb_vp9_fdct{4x4,8x8,16x16,32x32} / eb_vp9_fht{4x4,8x8,16x16} /
+ * eb_vpx_partial_fdct32x32 (partial32 != 0).  in: n blocks of N*N int16 residuals, contiguous
+ * (stride N); out: n blocks of N*N int16 coefficients.  tx_type applies to the whole batch.
+ * For partial32 only the top-left 16x16 of each output block is written; the rest is zeroed
+ * (the reference caller memsets: EbEncDecProcess.c:403-406). */
+int svtb200_fwd_txfm_batch(SvtB200Ctx *ctx, int tx_size, int tx_type, int partial32, int n,
+                           const int16_t *in, int16_t *out);
+int svtb200_fwd_txfm_batch_dev(SvtB200Ctx *ctx, int tx_size, int tx_type, int partial32, int n,
+                               const int16_t *in_dev, int16_t *out_dev);
+
+/* Batched eb_vp9_quantize_b (4..16) / eb_vp9_quantize_b_32x32: coeff -> qcoeff, dqcoeff, eob.
+ * qrow_index[i] selects the quantiser row of block i (NULL -> row 0 for all). */
+int svtb200_quantize_batch(SvtB200Ctx *ctx, int tx_size, int tx_type, int n, const int16_t *coeff,
+                           const SvtB200QuantRow *qrows, int n_qrows, const uint16_t *qrow_index,
+                           int16_t *qcoeff, int16_t *dqcoeff, uint16_t *eob);
+int svtb200_quantize_batch_dev(SvtB200Ctx *ctx, int tx_size, int tx_type, int n,
+                               const int16_t *coeff_dev, const SvtB200QuantRow *qrows_dev,
+                               int n_qrows, const uint16_t *qrow_index_dev, int16_t *qcoeff_dev,
+                               int16_t *dqcoeff_dev, uint16_t *eob_dev);
+
+/* Batched eb_vp9_idct{4x4,8x8,16x16,32x32}_add / eb_vp9_iht*_add (Source/Lib/VPX/vp9_idct.c:111-190):
+ * dest (n blocks of N*N uint8, contiguous, stride N) += inverse(dqcoeff), clipped. eob[i]
+ * selects the reference's partial variant (results are identical to the full transform). */
+int svtb200_inv_txfm_add_batch(SvtB200Ctx *ctx, int tx_size, int tx_type, int n,
+                               const int16_t *dqcoeff, const uint16_t *eob, uint8_t *dest);
+int svtb200_inv_txfm_add_batch_dev(SvtB200Ctx *ctx, int tx_size, int tx_type, int n,
+                                   const int16_t *dqcoeff_dev, const uint16_t *eob_dev,
+                                   uint8_t *dest_dev);
+
+/* Fused perform_coding_loop (EbEncDecProcess.c:365-587) for n transform blocks of one size:
+ * residual = src - pred; forward transform (tx_type per job); quantise; and, when do_recon,
+ * recon = clip(pred + inverse(dqcoeff)).  src/pred/recon are planes addressed by per-job byte
+ * offsets; coefficient outputs are contiguous per job (N*N each). */
+typedef struct SvtB200TxJob {
+    uint32_t src_offset;   /* byte offset of the block's top-left sample in src   */
+    uint32_t pred_offset;  /* ... in pred  */
+    uint32_t recon_offset; /* ... in recon (used when flags & SVTB200_TXJ_RECON) */
+    uint16_t qrow;         /* index into qrows */
+    uint8_t  tx_type;      /* SVTB200_DCT_DCT .. ADST_ADST (32x32: DCT only) */
+    uint8_t  flags;        /* SVTB200_TXJ_* */
+} SvtB200TxJob;
+#define SVTB200_TXJ_RECON 1u     /* do inverse transform + reconstruction */
+#define SVTB200_TXJ_PARTIAL32 2u /* 32x32 only: eb_vpx_partial_fdct32x32 (pf_md_level path) */
+
+typedef struct SvtB200TxPlanes {
+    const uint8_t *src;   int32_t src_stride;   size_t src_bytes;
+    const uint8_t *pred;  int32_t pred_stride;  size_t pred_bytes;
+    uint8_t       *recon; int32_t recon_stride; size_t recon_bytes;
+} SvtB200TxPlanes;
+
+int svtb200_txq_batch(SvtB200Ctx *ctx, int tx_size, int n, const SvtB200TxJob *jobs,
+                      const SvtB200TxPlanes *planes, const SvtB200QuantRow *qrows, int n_qrows,
+                      int16_t *coeff /* may be NULL */, int16_t *qcoeff, int16_t *dqcoeff,
+                      uint16_t *eob);
+int svtb200_txq_batch_dev(SvtB200Ctx *ctx, int tx_size, int n, const SvtB200TxJob *jobs_dev,
+                          const SvtB200TxPlanes *planes_dev, const SvtB200QuantRow *qrows_dev,
+                          int n_qrows, int16_t *coeff_dev, int16_t *qcoeff_dev,
+                          int16_t *dqcoeff_dev, uint16_t *eob_dev);
+
+/* =============================================================================================
+ * S2  Deblocking loop filter
+ * ============================================================================================= */
+
+/* Same layout as LOOP_FILTER_MASK (Source/Lib/VPX/vp9_loopfilter.h:62-70), one per 64x64 SB in
+ * raster order, as built by eb_vp9_build_mask_frame (vp9_loopfilter.c:1548). */
+typedef struct SvtB200LfMask {
+    uint64_t left_y[4];  /* per TX_SIZES */
+    uint64_t above_y[4];
+    uint64_t int_4x4_y;
+    uint16_t left_uv[4];
+    uint16_t above_uv[4];
+    uint16_t int_4x4_uv;
+    uint8_t  lfl_y[64];
+} SvtB200LfMask;
+
+/* loop_filter_thresh (vp9_loopfilter.h:42-46): one per filter level 0..63; only the first byte
+ * of each 16-byte SIMD lane array is meaningful. */
+typedef struct SvtB200LfThresh {
+    uint8_t mblim, lim, hev_thr;
+} SvtB200LfThresh;
+
+typedef struct SvtB200LfParams {
+    int32_t width, height;         /* luma, in samples (multiple of 8) */
+    int32_t mi_rows, mi_cols;      /* cm->mi_rows / mi_cols (8x8 units) */
+    int32_t y_only;                /* filter luma only */
+    int32_t filter_level;          /* lf->filter_level; 0 -> no-op */
+} SvtB200LfParams;
+
+/* In-place eb_vp9_loop_filter_frame on HOST planes y/u/v (pointers at picture origin). */
+int svtb200_deblock_picture(SvtB200Ctx *ctx, const SvtB200LfParams *p, uint8_t *y, int32_t y_stride,
+                            uint8_t *u, uint8_t *v, int32_t uv_stride, const SvtB200LfMask *lfm,
+                            int32_t lfm_stride /* SBs per row */, const SvtB200LfThresh thr[64]);
+int svtb200_deblock_picture_dev(SvtB200Ctx *ctx, const SvtB200LfParams *p, uint8_t *y_dev,
+                                int32_t y_stride, uint8_t *u_dev, uint8_t *v_dev, int32_t uv_stride,
+                                const SvtB200LfMask *lfm_dev, int32_t lfm_stride,
+                                const SvtB200LfThresh *thr_dev);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVTB200_H */

@@ -1,0 +1,52 @@
+#!/bin/bash
+# TEST INFRASTRUCTURE ONLY.  Compiles the UNMODIFIED reference sources where they lie
+# (/root/reference, read-only) into oracle/_ref/ (git-ignored).  No reference source is
+# copied into this repository: gcc reads the .c files in place and only object files,
+# a generated version header and the asm shim object end up under oracle/_ref/.
+#
+# The reference's own build (cmake + NASM) is not usable here (no yasm/nasm); the six
+# .asm files export 59 symbols, none on the hot path; oracle/ref_asm_shim.c forwards
+# each to its plain-C twin that already lives in the reference objects.
+set -e
+REF=${SVT_REF:-/root/reference}
+HERE=$(cd "$(dirname "$0")" && pwd)
+OUT=$HERE/_ref
+if [ ! -d "$REF/Source/Lib/Codec" ]; then
+  echo "build_ref: $REF not present; keeping prebuilt oracle/_ref (if any)"; exit 0
+fi
+mkdir -p $OUT/obj $OUT/inc
+sed 's/@SVT_VP9_VERSION_MAJOR@/0/;s/@SVT_VP9_VERSION_MINOR@/3/;s/@SVT_VP9_VERSION_PATCHLEVEL@/1/' \
+    $REF/Source/API/EbApiVersion.h.in > $OUT/inc/EbApiVersion.h
+L=$REF/Source/Lib
+INC="-I$OUT/inc -I$REF/Source/API -I$L/VPX -I$L/Codec -I$L/C_DEFAULT -I$L/ASM_SSE2 -I$L/ASM_SSSE3 -I$L/ASM_SSE4_1 -I$L/ASM_AVX2"
+CF="-std=gnu99 -O2 -fPIC -w -g"
+echo "$INC" > $OUT/inc_flags.txt
+cc_one() { # src flags prefix
+  local o=$OUT/obj/$3_$(basename $1 .c).o
+  if [ ! -f $o ] || [ $1 -nt $o ]; then gcc $CF $2 $INC -c $1 -o $o; fi
+}
+export -f cc_one; export OUT CF INC
+J=$(nproc)
+ls $L/VPX/*.c       | xargs -P $J -I{} bash -c 'cc_one {} "" VPX'
+ls $L/Codec/*.c     | xargs -P $J -I{} bash -c 'cc_one {} "" Codec'
+ls $L/C_DEFAULT/*.c | xargs -P $J -I{} bash -c 'cc_one {} "" C'
+ls $L/ASM_SSE2/*.c  | xargs -P $J -I{} bash -c 'cc_one {} "-msse2" SSE2'
+ls $L/ASM_SSSE3/*.c | xargs -P $J -I{} bash -c 'cc_one {} "-mssse3" SSSE3'
+ls $L/ASM_SSE4_1/*.c| xargs -P $J -I{} bash -c 'cc_one {} "-msse4.1" SSE41'
+ls $L/ASM_AVX2/*.c  | xargs -P $J -I{} bash -c 'cc_one {} "-mavx2" AVX2'
+gcc $CF $INC -c $HERE/ref_asm_shim.c -o $OUT/obj/shim.o
+# every symbol stays visible (no version script): the tests call internal _c kernels by name
+gcc -shared -o $OUT/libSvtVp9Enc_ref.so $OUT/obj/*.o -lpthread -lm -Wl,--no-undefined
+gcc -std=gnu99 -O2 -w -I$OUT/inc -I$REF/Source/API $REF/Source/App/*.c -o $OUT/SvtVp9EncApp_ref \
+    -L$OUT -lSvtVp9Enc_ref -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN'
+echo "build_ref: ok -> $OUT"
+
+# ---- seam-check flavour: same reference objects + a --wrap interposer that runs the oracle port
+# next to the reference's motion_estimate_sb (pins oracle/me_port.c against the reference)
+gcc $CF $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/ref_seam_check.c -o $OUT/seam_check.o
+gcc -std=gnu99 -O2 -fPIC -I$HERE/../include -c $HERE/me_port.c -o $OUT/me_port.o
+gcc -shared -o $OUT/libSvtVp9Enc_seam.so $OUT/obj/*.o $OUT/seam_check.o $OUT/me_port.o -lpthread -lm \
+    -Wl,--no-undefined -Wl,--wrap=motion_estimate_sb
+gcc -std=gnu99 -O2 -w -I$OUT/inc -I$REF/Source/API $REF/Source/App/*.c -o $OUT/SvtVp9EncApp_seam \
+    -L$OUT -lSvtVp9Enc_seam -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN'
+echo "build_ref: seam-check flavour ok"

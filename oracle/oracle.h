@@ -1,0 +1,31 @@
+/* TEST INFRASTRUCTURE ONLY -- declarations of the CPU oracle ("port").  See the individual .c
+ * files for the reference functions each restatement follows.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may use these. */
+#ifndef SVTB200_ORACLE_H
+#define SVTB200_ORACLE_H
+#include <stdint.h>
+#include "../include/svtb200.h"
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* intermediate values of one super-block, for stage-by-stage comparison with the CUDA path */
+typedef struct SvtB200OracleSbTrace {
+    int16_t  hme_center_x[2], hme_center_y[2]; /* search centre after HME, before the (0,0) test */
+    int16_t  sa_ox[2], sa_oy[2], sa_w[2], sa_h[2];
+    uint32_t fullpel_sad[2][85], fullpel_mv[2][85]; /* internal (z-order) PU indexing */
+    uint8_t  subpel_enable[2];                      /* bit0 32x32, bit1 16x16, bit2 8x8, bit3 quarter */
+} SvtB200OracleSbTrace;
+
+/* cur/ref0/ref1: arrays of 3 planes {full, quarter, sixteenth}; ref1 may be NULL for P pictures */
+void svtb200_oracle_me_sb(const SvtB200MeParams *P, const SvtB200Plane cur[3], const SvtB200Plane ref0[3],
+                          const SvtB200Plane ref1[3], int sb_x, int sb_y, SvtB200MeCuResult out[85],
+                          uint32_t *rcme_distortion, SvtB200OracleSbTrace *trace);
+void svtb200_oracle_me_picture(const SvtB200MeParams *P, const SvtB200Plane cur[3], const SvtB200Plane ref0[3],
+                               const SvtB200Plane ref1[3], SvtB200MeCuResult *out, uint32_t *rcme, int sb_begin,
+                               int sb_end);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

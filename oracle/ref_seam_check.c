@@ -1,0 +1,179 @@
+/*
+ * TEST INFRASTRUCTURE ONLY.  Link-time interposer on the UNMODIFIED reference objects
+ * (-Wl,--wrap=motion_estimate_sb): every call first runs the reference's own
+ * motion_estimate_sb() and then, depending on SVTB200_SEAM_MODE,
+ *   check : runs the CPU oracle (oracle/me_port.c) on the same inputs and counts mismatches
+ *           (this is how the oracle restatement is pinned against the reference);
+ *   dump  : writes the picture's planes, the translated parameters and the reference's results
+ *           to $SVTB200_SEAM_DIR (golden fixtures for tests/golden, see oracle/make_golden.py).
+ * The summary goes to $SVTB200_SEAM_DIR/summary.txt (the app closes stderr before exit).
+ */
+#define _GNU_SOURCE
+#include <pthread.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "svtb200_ref_glue.h"
+#include "../oracle/oracle.h"
+
+EbErrorType __real_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_index, uint32_t sb_origin_x,
+                                      uint32_t sb_origin_y, MeContext *me, EbPictureBufferDesc *input);
+
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static int   g_mode = -1; /* 0 off, 1 check, 2 dump */
+static char  g_dir[512];
+static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed;
+static int   g_max_dump_pics = 4, g_dump_from = 0;
+
+#define MAX_TRACKED 64
+typedef struct {
+    uint64_t pic; int used; int n_sb, done; FILE *f; SvtB200MeCuResult *res;
+} DumpPic;
+static DumpPic g_dp[MAX_TRACKED];
+static int g_dumped;
+
+static void write_summary(void) {
+    char path[600];
+    snprintf(path, sizeof(path), "%s/summary.txt", g_dir);
+    FILE *f = fopen(path, "w");
+    if (!f) return;
+    fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped);
+    fclose(f);
+}
+
+static void init_once(void) {
+    if (g_mode >= 0) return;
+    const char *m = getenv("SVTB200_SEAM_MODE"), *d = getenv("SVTB200_SEAM_DIR");
+    g_mode = 0;
+    if (m && !strcmp(m, "check")) g_mode = 1;
+    if (m && !strcmp(m, "dump")) g_mode = 2;
+    snprintf(g_dir, sizeof(g_dir), "%s", d ? d : "/tmp");
+    if (getenv("SVTB200_SEAM_MAXPICS")) g_max_dump_pics = atoi(getenv("SVTB200_SEAM_MAXPICS"));
+    if (getenv("SVTB200_SEAM_FROM")) g_dump_from = atoi(getenv("SVTB200_SEAM_FROM"));
+    if (g_mode) atexit(write_summary);
+}
+
+static void ref_to_abi(const MeCuResults *r, SvtB200MeCuResult *o, int nl) {
+    memset(o, 0, sizeof(*o));
+    o->x_mv_l0 = r->x_mv_l0; o->y_mv_l0 = r->y_mv_l0;
+    if (nl == 2) { o->x_mv_l1 = r->x_mv_l1; o->y_mv_l1 = r->y_mv_l1; } /* P pictures: stale scratch, ignored */
+    o->total_me_candidate_index = r->total_me_candidate_index;
+    for (int i = 0; i < r->total_me_candidate_index && i < 3; i++) {
+        o->cand[i].distortion = r->distortion_direction[i].distortion;
+        o->cand[i].direction  = r->distortion_direction[i].direction;
+    }
+}
+
+static void write_plane(FILE *f, const SvtB200Plane *p) {
+    int32_t hdr[6] = {p->stride, p->origin_x, p->origin_y, p->width, p->height, p->padded_height};
+    fwrite(hdr, sizeof(hdr), 1, f);
+    if (p->buf && p->padded_height > 0) fwrite(p->buf, 1, (size_t)p->stride * p->padded_height, f);
+}
+
+EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_index, uint32_t sb_origin_x,
+                                      uint32_t sb_origin_y, MeContext *me, EbPictureBufferDesc *input) {
+    EbErrorType rc = __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input);
+    pthread_mutex_lock(&g_mu);
+    init_once();
+    int mode = g_mode;
+    pthread_mutex_unlock(&g_mu);
+    if (!mode) return rc;
+
+    SvtB200MeParams P;
+    svtb200_glue_me_params(pcs, me, &P);
+    SvtB200Plane cur[3], r0[3], r1[3];
+    svtb200_glue_pa_planes((EbPaReferenceObject *)pcs->pareference_picture_wrapper_ptr->object_ptr, cur);
+    svtb200_glue_pa_planes((EbPaReferenceObject *)pcs->ref_pa_pic_ptr_array[0]->object_ptr, r0);
+    if (P.num_lists == 2) svtb200_glue_pa_planes((EbPaReferenceObject *)pcs->ref_pa_pic_ptr_array[1]->object_ptr, r1);
+    /* the source SB is read through the PA reference object's padded plane (aliases enhanced_picture) */
+    SvtB200MeCuResult refres[85];
+    for (int i = 0; i < 85; i++) ref_to_abi(&pcs->me_results[sb_index][i], &refres[i], P.num_lists);
+
+    if (mode == 1) {
+        SvtB200MeCuResult mine[85];
+        uint32_t rcme = 0;
+        SvtB200OracleSbTrace tr; memset(&tr, 0, sizeof(tr));
+        svtb200_oracle_me_sb(&P, cur, r0, P.num_lists == 2 ? r1 : NULL, sb_origin_x / 64, sb_origin_y / 64, mine, &rcme, &tr);
+        int bad = 0;
+        for (int i = 0; i < 85; i++) if (memcmp(&mine[i], &refres[i], sizeof(mine[i]))) bad++;
+        if (P.rate_control_mode && rcme != pcs->rcme_distortion[sb_index]) bad++;
+        pthread_mutex_lock(&g_mu);
+        g_sb_total++;
+        if (bad) {
+            g_sb_bad++; g_pu_bad += bad;
+            if (g_printed < 20) {
+                g_printed++;
+                char path[600]; snprintf(path, sizeof(path), "%s/mismatch.txt", g_dir);
+                FILE *f = fopen(path, "a");
+                if (f) {
+                    fprintf(f, "pic %llu sb %u (%u,%u) nl %d tl %d bad %d\n", (unsigned long long)pcs->picture_number, sb_index,
+                            sb_origin_x, sb_origin_y, P.num_lists, P.temporal_layer_index, bad);
+                    for (int l = 0; l < P.num_lists; l++)
+                        fprintf(f, "  list %d: ref sa_org (%d,%d) | port hme (%d,%d) sa_org (%d,%d) %dx%d subpel %x\n", l,
+                                me->x_search_area_origin[l][0], me->y_search_area_origin[l][0], tr.hme_center_x[l], tr.hme_center_y[l],
+                                tr.sa_ox[l], tr.sa_oy[l], tr.sa_w[l], tr.sa_h[l], tr.subpel_enable[l]);
+                    {   /* direct 64x64 sub-sampled SAD at the reference's list-0 MV (if full-pel) */
+                        int mx = refres[0].x_mv_l0, my = refres[0].y_mv_l0;
+                        const uint8_t *sp = cur[0].buf + (cur[0].origin_y + sb_origin_y) * cur[0].stride + cur[0].origin_x + sb_origin_x;
+                        const uint8_t *rp = r0[0].buf + (r0[0].origin_y + (int)sb_origin_y + (my >> 2)) * r0[0].stride + r0[0].origin_x + (int)sb_origin_x + (mx >> 2);
+                        unsigned sad = 0;
+                        for (int y = 0; y < 64; y += 2) for (int x = 0; x < 64; x++) sad += abs(sp[y * cur[0].stride + x] - rp[y * r0[0].stride + x]);
+                        for (int dx = -3; dx <= 6; dx++) {
+                            unsigned s2 = 0;
+                            for (int y = 0; y < 64; y += 2) for (int x = 0; x < 64; x++) s2 += abs(sp[y * cur[0].stride + x] - rp[y * r0[0].stride + x + dx]);
+                            fprintf(f, "   dx %d -> %u\n", dx, 2 * s2);
+                        }
+                        fprintf(f, "  planes: cur stride %d ox %d w %d | ref stride %d ox %d w %d h %d ph %d\n", cur[0].stride, cur[0].origin_x, cur[0].width, r0[0].stride, r0[0].origin_x, r0[0].width, r0[0].height, r0[0].padded_height);
+                        fprintf(f, "  direct sad@ref mv0 (%d,%d) = %u ; fullpel port sad[0]=%u mv=(%d,%d)\n", mx, my, 2 * sad, tr.fullpel_sad[0][0],
+                                (int16_t)(tr.fullpel_mv[0][0] & 0xffff), (int16_t)(tr.fullpel_mv[0][0] >> 16));
+                    }
+                    for (int i = 0; i < 85; i++)
+                        if (memcmp(&mine[i], &refres[i], sizeof(mine[i])))
+                            fprintf(f, "  pu %d ref mv0(%d,%d) mv1(%d,%d) n%d d[%u:%u %u:%u %u:%u] | port mv0(%d,%d) mv1(%d,%d) n%d d[%u:%u %u:%u %u:%u]\n", i,
+                                    refres[i].x_mv_l0, refres[i].y_mv_l0, refres[i].x_mv_l1, refres[i].y_mv_l1, refres[i].total_me_candidate_index,
+                                    refres[i].cand[0].distortion, refres[i].cand[0].direction, refres[i].cand[1].distortion, refres[i].cand[1].direction,
+                                    refres[i].cand[2].distortion, refres[i].cand[2].direction,
+                                    mine[i].x_mv_l0, mine[i].y_mv_l0, mine[i].x_mv_l1, mine[i].y_mv_l1, mine[i].total_me_candidate_index,
+                                    mine[i].cand[0].distortion, mine[i].cand[0].direction, mine[i].cand[1].distortion, mine[i].cand[1].direction,
+                                    mine[i].cand[2].distortion, mine[i].cand[2].direction);
+                    fclose(f);
+                }
+            }
+        }
+        pthread_mutex_unlock(&g_mu);
+        return rc;
+    }
+
+    /* dump mode: one file per picture, written when its last SB arrives */
+    if ((int)pcs->picture_number < g_dump_from) return rc;
+    pthread_mutex_lock(&g_mu);
+    DumpPic *dp = NULL;
+    for (int i = 0; i < MAX_TRACKED; i++) if (g_dp[i].used && g_dp[i].pic == pcs->picture_number) dp = &g_dp[i];
+    if (!dp && g_dumped < g_max_dump_pics) {
+        for (int i = 0; i < MAX_TRACKED && !dp; i++) if (!g_dp[i].used) dp = &g_dp[i];
+        if (dp) {
+            memset(dp, 0, sizeof(*dp));
+            dp->used = 1; dp->pic = pcs->picture_number; g_dumped++;
+            dp->n_sb = ((P.luma_width + 63) / 64) * ((P.luma_height + 63) / 64);
+            dp->res  = (SvtB200MeCuResult *)calloc((size_t)dp->n_sb * 85, sizeof(SvtB200MeCuResult));
+            char path[600]; snprintf(path, sizeof(path), "%s/me_pic%04llu.bin", g_dir, (unsigned long long)pcs->picture_number);
+            dp->f = fopen(path, "wb");
+            uint32_t magic[4] = {0x42305653u /* 'SV0B' */, 1, (uint32_t)sizeof(P), (uint32_t)dp->n_sb};
+            fwrite(magic, sizeof(magic), 1, dp->f);
+            fwrite(&P, sizeof(P), 1, dp->f);
+            for (int i = 0; i < 3; i++) write_plane(dp->f, &cur[i]);
+            for (int i = 0; i < 3; i++) write_plane(dp->f, &r0[i]);
+            if (P.num_lists == 2) for (int i = 0; i < 3; i++) write_plane(dp->f, &r1[i]);
+        }
+    }
+    if (dp && dp->f) {
+        memcpy(dp->res + (size_t)sb_index * 85, refres, sizeof(refres));
+        if (++dp->done == dp->n_sb) {
+            fwrite(dp->res, sizeof(SvtB200MeCuResult), (size_t)dp->n_sb * 85, dp->f);
+            fclose(dp->f); dp->f = NULL; free(dp->res); dp->res = NULL;
+        }
+    }
+    pthread_mutex_unlock(&g_mu);
+    return rc;
+}
