@@ -1,0 +1,43 @@
+"""Regenerates tests/golden/me_*.bin.gz from the UNMODIFIED reference (oracle/_ref, seam-dump flavour).
+
+Run in the container that has /root/reference (after oracle/build_ref.sh).  The dumps are written by
+oracle/ref_seam_check.c in dump mode: per picture the translated SvtB200MeParams, the padded
+full / quarter / sixteenth planes of the current and reference pictures, and the reference's own
+me_results for every super-block.  Test infrastructure only.
+"""
+import glob
+import gzip
+import importlib
+import os
+import shutil
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+synth = importlib.import_module("svt-vp9_b200.synth")
+
+SELECT = {(8, 1): [3, 8, 16, 17], (3, 1): [2, 16, 18], (5, 0): [1, 4, 16]}
+
+
+def main():
+    w, h, n = 192, 128, 20
+    yuv = "/tmp/svtb200_golden.yuv"
+    synth.write_yuv(yuv, synth.make_clip(w, h, n, seed=9, k=3, g=3, a=5, b=3, m=32, noise=2))
+    for (mode, tune), pics in SELECT.items():
+        d = "/tmp/svtb200_gold_%d_%d" % (mode, tune)
+        shutil.rmtree(d, ignore_errors=True)
+        os.makedirs(d)
+        env = dict(os.environ, SVTB200_SEAM_MODE="dump", SVTB200_SEAM_DIR=d, SVTB200_SEAM_MAXPICS="32")
+        subprocess.run(["./SvtVp9EncApp_seam", "-i", yuv, "-w", str(w), "-h", str(h), "-n", str(n), "-enc-mode", str(mode),
+                        "-tune", str(tune), "-b", "/tmp/svtb200_golden.ivf"], cwd=os.path.join(ROOT, "oracle", "_ref"), env=env,
+                       check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for p in pics:
+            dst = os.path.join(ROOT, "tests", "golden", "me_%dx%d_m%dt%d_pic%02d.bin.gz" % (w, h, mode, tune, p))
+            with open(os.path.join(d, "me_pic%04d.bin" % p), "rb") as f, gzip.open(dst, "wb", 9) as g:
+                shutil.copyfileobj(f, g)
+            print("wrote", dst)
+
+
+if __name__ == "__main__":
+    main()

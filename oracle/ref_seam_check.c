@@ -100,6 +100,7 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
         if (P.rate_control_mode && rcme != pcs->rcme_distortion[sb_index]) bad++;
         pthread_mutex_lock(&g_mu);
         g_sb_total++;
+        if ((g_sb_total & 1023) == 0) write_summary(); /* the 4K reference aborts in deinit: atexit never runs */
         if (bad) {
             g_sb_bad++; g_pu_bad += bad;
             if (g_printed < 20) {

@@ -1,0 +1,179 @@
+"""ctypes mirror of include/svtb200.h -- the host-side entry points the tests and bench call.
+
+The CUDA library is the only implementation behind these calls: there is no CPU fallback, and
+loading fails loudly when libsvtvp9_b200.so has not been built (see svt-vp9_b200/build.py).
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvtvp9_b200.so")
+
+
+class Plane(C.Structure):
+    _fields_ = [("buf", C.c_void_p), ("stride", C.c_int32), ("origin_x", C.c_int32), ("origin_y", C.c_int32),
+                ("width", C.c_int32), ("height", C.c_int32), ("padded_height", C.c_int32)]
+
+
+class MeParams(C.Structure):
+    _fields_ = [("luma_width", C.c_int32), ("luma_height", C.c_int32), ("num_lists", C.c_int32),
+                ("temporal_layer_index", C.c_int32), ("hierarchical_levels", C.c_int32),
+                ("ref_poc", C.c_uint64 * 2),
+                ("enable_hme_flag", C.c_int32), ("enable_hme_level0", C.c_int32), ("enable_hme_level1", C.c_int32),
+                ("enable_hme_level2", C.c_int32), ("single_hme_quadrant", C.c_int32),
+                ("number_hme_search_region_in_width", C.c_int32), ("number_hme_search_region_in_height", C.c_int32),
+                ("hme_level0_total_search_area_width", C.c_int32), ("hme_level0_total_search_area_height", C.c_int32),
+                ("hme_level0_search_area_in_width", C.c_int32 * 2), ("hme_level0_search_area_in_height", C.c_int32 * 2),
+                ("hme_level1_search_area_in_width", C.c_int32 * 2), ("hme_level1_search_area_in_height", C.c_int32 * 2),
+                ("hme_level2_search_area_in_width", C.c_int32 * 2), ("hme_level2_search_area_in_height", C.c_int32 * 2),
+                ("hme_l0_multiplier_x", C.c_int32), ("hme_l0_multiplier_y", C.c_int32),
+                ("search_area_width", C.c_int32), ("search_area_height", C.c_int32),
+                ("fractional_search_method", C.c_int32), ("fractional_search_model", C.c_int32),
+                ("fractional_search64x64", C.c_int32), ("cu8x8_mode", C.c_int32), ("cu16x16_mode", C.c_int32),
+                ("rate_control_mode", C.c_int32)]
+
+
+ME_RESULT_DTYPE = np.dtype([("x_mv_l0", "<i2"), ("y_mv_l0", "<i2"), ("x_mv_l1", "<i2"), ("y_mv_l1", "<i2"),
+                            ("cand", [("distortion", "<u4"), ("direction", "<u4")], 3),
+                            ("total", "u1"), ("pad", "u1", 7)])
+assert ME_RESULT_DTYPE.itemsize == 40
+
+ME_TRACE_DTYPE = np.dtype([("hme_center_x", "<i2", 2), ("hme_center_y", "<i2", 2), ("sa_ox", "<i2", 2), ("sa_oy", "<i2", 2),
+                           ("sa_w", "<i2", 2), ("sa_h", "<i2", 2), ("fullpel_sad", "<u4", (2, 85)),
+                           ("fullpel_mv", "<u4", (2, 85)), ("subpel_enable", "u1", 2), ("pad", "u1", 2)])
+assert ME_TRACE_DTYPE.itemsize == 1388
+
+
+class QuantRow(C.Structure):
+    _fields_ = [("zbin", C.c_int16 * 2), ("round", C.c_int16 * 2), ("quant", C.c_int16 * 2),
+                ("quant_shift", C.c_int16 * 2), ("dequant", C.c_int16 * 2)]
+
+
+QUANT_ROW_DTYPE = np.dtype([("zbin", "<i2", 2), ("round", "<i2", 2), ("quant", "<i2", 2), ("quant_shift", "<i2", 2),
+                            ("dequant", "<i2", 2)])
+
+TX_JOB_DTYPE = np.dtype([("src_offset", "<u4"), ("pred_offset", "<u4"), ("recon_offset", "<u4"), ("qrow", "<u2"),
+                         ("tx_type", "u1"), ("flags", "u1")])
+assert TX_JOB_DTYPE.itemsize == 16
+
+
+class TxPlanes(C.Structure):
+    _fields_ = [("src", C.c_void_p), ("src_stride", C.c_int32), ("src_bytes", C.c_size_t),
+                ("pred", C.c_void_p), ("pred_stride", C.c_int32), ("pred_bytes", C.c_size_t),
+                ("recon", C.c_void_p), ("recon_stride", C.c_int32), ("recon_bytes", C.c_size_t)]
+
+
+LF_MASK_DTYPE = np.dtype([("left_y", "<u8", 4), ("above_y", "<u8", 4), ("int_4x4_y", "<u8"), ("left_uv", "<u2", 4),
+                          ("above_uv", "<u2", 4), ("int_4x4_uv", "<u2"), ("lfl_y", "u1", 64), ("pad", "u1", 6)])
+assert LF_MASK_DTYPE.itemsize == 160
+LF_THRESH_DTYPE = np.dtype([("mblim", "u1"), ("lim", "u1"), ("hev_thr", "u1")])
+
+
+class LfParams(C.Structure):
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("mi_rows", C.c_int32), ("mi_cols", C.c_int32),
+                ("y_only", C.c_int32), ("filter_level", C.c_int32)]
+
+
+def plane_of(arr, origin_x, origin_y, width, height):
+    """Describe a padded 2-D uint8 numpy array (C-contiguous) as an SvtB200Plane."""
+    assert arr.dtype == np.uint8 and arr.flags["C_CONTIGUOUS"] and arr.ndim == 2
+    p = Plane()
+    p.buf = arr.ctypes.data
+    p.stride = arr.shape[1]
+    p.origin_x, p.origin_y, p.width, p.height, p.padded_height = origin_x, origin_y, width, height, arr.shape[0]
+    return p
+
+
+_lib = None
+
+
+def lib():
+    """Load libsvtvp9_b200.so; raises if it is missing (no fallback path exists)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("CUDA extension %s is not built; run python -c 'import __graft_entry__ as g; g.build()'" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        L.svtb200_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.svtb200_destroy.argtypes = [C.c_void_p]
+        L.svtb200_last_error.argtypes = [C.c_void_p]
+        L.svtb200_last_error.restype = C.c_char_p
+        L.svtb200_sync.argtypes = [C.c_void_p]
+        L.svtb200_launch_count.argtypes = [C.c_void_p]
+        L.svtb200_launch_count.restype = C.c_uint64
+        L.svtb200_stream.argtypes = [C.c_void_p]
+        L.svtb200_stream.restype = C.c_void_p
+        L.svtb200_host_alloc.argtypes = [C.c_size_t]
+        L.svtb200_host_alloc.restype = C.c_void_p
+        L.svtb200_host_free.argtypes = [C.c_void_p]
+        L.svtb200_dev_alloc.argtypes = [C.c_void_p, C.c_size_t]
+        L.svtb200_dev_alloc.restype = C.c_void_p
+        L.svtb200_dev_free.argtypes = [C.c_void_p, C.c_void_p]
+        L.svtb200_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.svtb200_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.svtb200_picture_upload.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane)]
+        L.svtb200_picture_release.argtypes = [C.c_void_p, C.c_uint64]
+        L.svtb200_me_picture.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
+        L.svtb200_me_picture_dev.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
+        L.svtb200_me_enable_trace.argtypes = [C.c_void_p, C.c_int]
+        L.svtb200_me_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        _lib = L
+    return _lib
+
+
+class Context:
+    """One SvtB200Ctx (one CUDA device + stream)."""
+
+    def __init__(self, device=0):
+        self.L = lib()
+        h = C.c_void_p()
+        rc = self.L.svtb200_create(device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("svtb200_create(device=%d) failed: %d" % (device, rc))
+        self.h = h
+
+    def close(self):
+        if self.h:
+            self.L.svtb200_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError("%s failed: %d (%s)" % (what, rc, self.L.svtb200_last_error(self.h).decode()))
+
+    def sync(self):
+        self.check(self.L.svtb200_sync(self.h), "sync")
+
+    def launches(self):
+        return int(self.L.svtb200_launch_count(self.h))
+
+    # ---- S1
+    def picture_upload(self, pic_id, full, quarter, sixteenth):
+        q = C.byref(quarter) if quarter is not None else None
+        s = C.byref(sixteenth) if sixteenth is not None else None
+        self.check(self.L.svtb200_picture_upload(self.h, pic_id, C.byref(full), q, s), "picture_upload")
+
+    def picture_release(self, pic_id):
+        self.L.svtb200_picture_release(self.h, pic_id)
+
+    def me_picture(self, params, cur_id, ref_ids, want_rcme=False):
+        n_sb = ((params.luma_width + 63) // 64) * ((params.luma_height + 63) // 64)
+        out = np.zeros(n_sb * 85, dtype=ME_RESULT_DTYPE)
+        rcme = np.zeros(n_sb, dtype=np.uint32)
+        ids = (C.c_uint64 * 2)(ref_ids[0], ref_ids[1] if len(ref_ids) > 1 else ref_ids[0])
+        self.check(self.L.svtb200_me_picture(self.h, C.byref(params), cur_id, ids, out.ctypes.data,
+                                             rcme.ctypes.data if want_rcme else None), "me_picture")
+        return (out, rcme) if want_rcme else out
+
+    def me_trace(self, n_sb):
+        tr = np.zeros(n_sb, dtype=ME_TRACE_DTYPE)
+        self.check(self.L.svtb200_me_read_trace(self.h, tr.ctypes.data, tr.nbytes), "me_read_trace")
+        return tr

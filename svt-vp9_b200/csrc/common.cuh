@@ -1,0 +1,77 @@
+/* common.cuh -- context object and error plumbing shared by the C-ABI translation units. */
+#ifndef SVTB200_COMMON_CUH
+#define SVTB200_COMMON_CUH
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <map>
+#include <mutex>
+#include <string>
+#include <vector>
+#include "../../include/svtb200.h"
+
+struct DevPlane {
+    uint8_t *buf = nullptr;
+    int32_t  stride = 0, ox = 0, oy = 0, w = 0, h = 0, rows = 0;
+};
+struct DevPicture {
+    DevPlane pl[3]; /* full, quarter, sixteenth */
+};
+
+struct ScanTable {
+    int16_t *scan = nullptr, *iscan = nullptr;
+    int      n = 0;
+};
+
+struct SvtB200Ctx {
+    int          device = 0;
+    cudaStream_t stream = nullptr;
+    std::mutex   mu;
+    std::string  err;
+    uint64_t     launches = 0;
+    int          smem_optin = 0, sm_count = 0;
+    std::map<uint64_t, DevPicture> pics;
+    /* ME scratch, grown on demand */
+    uint8_t *interp_scratch = nullptr; size_t interp_scratch_bytes = 0;
+    void    *me_out = nullptr;  size_t me_out_bytes = 0;
+    uint32_t *me_rcme = nullptr; size_t me_rcme_bytes = 0;
+    void    *me_trace = nullptr; size_t me_trace_bytes = 0; int me_trace_enabled = 0;
+    /* pinned staging */
+    uint8_t *pin = nullptr; size_t pin_bytes = 0;
+    /* transform / quant */
+    ScanTable scans[4][4];
+    /* generic device scratch for the host-pointer entry points */
+    uint8_t *scratch = nullptr; size_t scratch_bytes = 0;
+};
+
+#define SVTB200_CUDA_CHECK(ctx, call)                                                                 \
+    do {                                                                                              \
+        cudaError_t e_ = (call);                                                                      \
+        if (e_ != cudaSuccess) {                                                                      \
+            char b_[512];                                                                             \
+            snprintf(b_, sizeof(b_), "%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e_)); \
+            (ctx)->err = b_;                                                                          \
+            return SVTB200_ECUDA;                                                                     \
+        }                                                                                             \
+    } while (0)
+
+static inline int svtb200_grow(SvtB200Ctx *ctx, void **p, size_t *cap, size_t need) {
+    if (*cap >= need) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    size_t n = need + need / 4 + 256;
+    if (cudaMalloc(p, n) != cudaSuccess) { ctx->err = "cudaMalloc failed"; cudaGetLastError(); return SVTB200_ENOMEM; }
+    *cap = n;
+    return 0;
+}
+static inline int svtb200_grow_pinned(SvtB200Ctx *ctx, size_t need) {
+    if (ctx->pin_bytes >= need) return 0;
+    if (ctx->pin) cudaFreeHost(ctx->pin);
+    ctx->pin = nullptr; ctx->pin_bytes = 0;
+    size_t n = need + need / 4 + 256;
+    if (cudaMallocHost((void **)&ctx->pin, n) != cudaSuccess) { ctx->err = "cudaMallocHost failed"; cudaGetLastError(); return SVTB200_ENOMEM; }
+    ctx->pin_bytes = n;
+    return 0;
+}
+#endif

@@ -1,0 +1,118 @@
+/* me.cu -- host side of S1: svtb200_me_picture[_dev] (see include/svtb200.h). */
+#include "common.cuh"
+#include "me_kernel.cuh"
+
+static void to_dev(const DevPlane &d, MePlaneDev *o) { o->buf = d.buf; o->stride = d.stride; o->ox = d.ox; o->oy = d.oy; o->w = d.w; o->h = d.h; }
+
+/* worst-case staging-window size over HME levels and the full-pel search */
+static int me_window_bytes(const SvtB200MeParams &P) {
+    auto win = [](int saw, int sah, int w, int h) { int pitch = ((saw + w - 1 + 4) + 3) & ~3; return pitch * (sah + 2 * (h - 1) + 1); };
+    int best = 0;
+    if (P.enable_hme_flag) {
+        if (P.enable_hme_level0) {
+            int tw = (P.hme_level0_total_search_area_width * P.hme_l0_multiplier_x) / 100, th = (P.hme_level0_total_search_area_height * P.hme_l0_multiplier_y) / 100;
+            for (int i = 0; i < 2; i++) {
+                tw = std::max(tw, (P.hme_level0_search_area_in_width[i] * P.hme_l0_multiplier_x) / 100);
+                th = std::max(th, (P.hme_level0_search_area_in_height[i] * P.hme_l0_multiplier_y) / 100);
+            }
+            best = std::max(best, win(tw, th, 16, 8));
+        }
+        if (P.enable_hme_level1)
+            for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++)
+                best = std::max(best, win(std::max(8, 2 * P.hme_level1_search_area_in_width[i]), P.hme_level1_search_area_in_height[j], 32, 16));
+        if (P.enable_hme_level2)
+            for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++)
+                best = std::max(best, win(std::max(8, 2 * P.hme_level2_search_area_in_width[i]), P.hme_level2_search_area_in_height[j], 64, 32));
+    }
+    const int saw = std::min(P.search_area_width, 127), sah = std::min(P.search_area_height, 127);
+    best = std::max(best, (((saw + 63 + 16 + 4) + 3) & ~3) * (sah + 63 + 1));
+    return best + 16;
+}
+
+static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, const uint64_t ref_id[2],
+                     SvtB200MeCuResult *out_dev, uint32_t *rcme_dev) {
+    if (!c || !P || !ref_id || !out_dev) return SVTB200_EINVAL;
+    if (P->num_lists < 1 || P->num_lists > 2 || P->luma_width <= 0 || P->luma_height <= 0) return SVTB200_EINVAL;
+    if (P->number_hme_search_region_in_width > 2 || P->number_hme_search_region_in_height > 2) return SVTB200_EINVAL;
+    MeKernelArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *P;
+    auto itc = c->pics.find(cur_id);
+    if (itc == c->pics.end()) { c->err = "unknown current picture id"; return SVTB200_ENOENT; }
+    for (int i = 0; i < 3; i++) to_dev(itc->second.pl[i], &A.cur[i]);
+    for (int l = 0; l < P->num_lists; l++) {
+        auto itr = c->pics.find(ref_id[l]);
+        if (itr == c->pics.end()) { c->err = "unknown reference picture id"; return SVTB200_ENOENT; }
+        for (int i = 0; i < 3; i++) to_dev(itr->second.pl[i], &A.ref[l][i]);
+    }
+    if (P->num_lists == 1) for (int i = 0; i < 3; i++) A.ref[1][i] = A.ref[0][i];
+    if (P->enable_hme_flag && ((P->enable_hme_level0 && !A.cur[2].buf) || (P->enable_hme_level1 && !A.cur[1].buf))) {
+        c->err = "HME level enabled but its decimated plane was not uploaded"; return SVTB200_EINVAL;
+    }
+    A.sbs_w = (P->luma_width + ME_SB - 1) / ME_SB;
+    A.n_sb  = A.sbs_w * ((P->luma_height + ME_SB - 1) / ME_SB);
+    A.out = out_dev; A.rcme = rcme_dev;
+    A.win_bytes = me_window_bytes(*P);
+    const int saw = std::min(P->search_area_width, 127), sah = std::min(P->search_area_height, 127);
+    const int is = ((saw + 63 + 2) + 7) & ~7;
+    A.interp_plane_bytes = is * (sah + 63 + 4);
+    A.interp_in_smem = 1;
+    MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 1);
+    if (L.total > c->smem_optin) {
+        A.interp_in_smem = 0;
+        L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 0);
+        if (L.total > c->smem_optin) { c->err = "search window does not fit in shared memory"; return SVTB200_EINVAL; }
+        const size_t need = (size_t)A.n_sb * 2 * 3 * me_align16(A.interp_plane_bytes);
+        int rc = svtb200_grow(c, (void **)&c->interp_scratch, &c->interp_scratch_bytes, need);
+        if (rc) return rc;
+        A.interp_scratch = c->interp_scratch;
+    }
+    if (c->me_trace_enabled) {
+        int rc = svtb200_grow(c, &c->me_trace, &c->me_trace_bytes, (size_t)A.n_sb * sizeof(MeTraceDev));
+        if (rc) return rc;
+        A.trace = (MeTraceDev *)c->me_trace;
+    }
+    SVTB200_CUDA_CHECK(c, cudaFuncSetAttribute(me_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    me_sb_kernel<<<A.n_sb, ME_THREADS, L.total, c->stream>>>(A);
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
+extern "C" {
+
+int svtb200_me_picture_dev(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, const uint64_t ref_id[2],
+                           SvtB200MeCuResult *out_dev, uint32_t *rcme_dev) {
+    if (!c) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    return me_launch(c, P, cur_id, ref_id, out_dev, rcme_dev);
+}
+
+int svtb200_me_picture(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, const uint64_t ref_id[2],
+                       SvtB200MeCuResult *out, uint32_t *out_rcme) {
+    if (!c || !P || !out) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    const int n_sb = ((P->luma_width + ME_SB - 1) / ME_SB) * ((P->luma_height + ME_SB - 1) / ME_SB);
+    const size_t bytes = (size_t)n_sb * 85 * sizeof(SvtB200MeCuResult);
+    int rc = svtb200_grow(c, &c->me_out, &c->me_out_bytes, bytes);
+    if (rc) return rc;
+    rc = svtb200_grow(c, (void **)&c->me_rcme, &c->me_rcme_bytes, (size_t)n_sb * 4);
+    if (rc) return rc;
+    rc = me_launch(c, P, cur_id, ref_id, (SvtB200MeCuResult *)c->me_out, c->me_rcme);
+    if (rc) return rc;
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(out, c->me_out, bytes, cudaMemcpyDeviceToHost, c->stream));
+    if (out_rcme) SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(out_rcme, c->me_rcme, (size_t)n_sb * 4, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SVTB200_OK;
+}
+
+/* debugging aid for the parity tests: per-SB stage outputs of the next me_picture calls */
+int svtb200_me_enable_trace(SvtB200Ctx *c, int on) { if (!c) return SVTB200_EINVAL; c->me_trace_enabled = on; return SVTB200_OK; }
+int svtb200_me_read_trace(SvtB200Ctx *c, void *host, size_t bytes) {
+    if (!c || !c->me_trace || bytes > c->me_trace_bytes) return SVTB200_EINVAL;
+    return svtb200_memcpy_d2h(c, host, c->me_trace, bytes);
+}
+
+} /* extern "C" */
