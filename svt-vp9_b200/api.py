@@ -177,3 +177,86 @@ class Context:
         tr = np.zeros(n_sb, dtype=ME_TRACE_DTYPE)
         self.check(self.L.svtb200_me_read_trace(self.h, tr.ctypes.data, tr.nbytes), "me_read_trace")
         return tr
+
+
+# ---- S3: transform / quantisation -------------------------------------------------------------------------------
+def _bind_txq(L):
+    if getattr(L, "_txq_bound", False):
+        return
+    vp = C.c_void_p
+    L.svtb200_set_scan.argtypes = [vp, C.c_int, C.c_int, vp, vp]
+    L.svtb200_fwd_txfm_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.svtb200_fwd_txfm_batch_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp]
+    L.svtb200_quantize_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.svtb200_quantize_batch_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, C.c_int, vp, vp, vp, vp]
+    L.svtb200_inv_txfm_add_batch.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.svtb200_inv_txfm_add_batch_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
+    L.svtb200_txq_batch.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(TxPlanes), vp, C.c_int, vp, vp, vp, vp]
+    L.svtb200_txq_batch_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(TxPlanes), vp, C.c_int, vp, vp, vp, vp]
+    L._txq_bound = True
+
+
+def _ctx_register_scans(self, tables):
+    """tables: mapping with scan_<ts>_<tt> / iscan_<ts>_<tt> int16 arrays (svt-vp9_b200/data/vp9_tables.npz)."""
+    _bind_txq(self.L)
+    for ts in range(4):
+        for tt in range(4):
+            s = np.ascontiguousarray(tables["scan_%d_%d" % (ts, tt)], dtype=np.int16)
+            i = np.ascontiguousarray(tables["iscan_%d_%d" % (ts, tt)], dtype=np.int16)
+            self.check(self.L.svtb200_set_scan(self.h, ts, tt, s.ctypes.data, i.ctypes.data), "set_scan")
+
+
+def _ctx_fwd_txfm(self, tx_size, tx_type, resid, partial32=0):
+    _bind_txq(self.L)
+    resid = np.ascontiguousarray(resid, dtype=np.int16)
+    out = np.zeros_like(resid)
+    self.check(self.L.svtb200_fwd_txfm_batch(self.h, tx_size, tx_type, partial32, resid.shape[0], resid.ctypes.data, out.ctypes.data), "fwd_txfm_batch")
+    return out
+
+
+def _ctx_quantize(self, tx_size, tx_type, coeff, rows, row_idx=None):
+    _bind_txq(self.L)
+    coeff = np.ascontiguousarray(coeff, dtype=np.int16)
+    n = coeff.shape[0]
+    q, dq, eob = np.zeros_like(coeff), np.zeros_like(coeff), np.zeros(n, dtype=np.uint16)
+    rows = np.ascontiguousarray(rows)
+    idx = None if row_idx is None else np.ascontiguousarray(row_idx, dtype=np.uint16)
+    self.check(self.L.svtb200_quantize_batch(self.h, tx_size, tx_type, n, coeff.ctypes.data, rows.ctypes.data, len(rows),
+                                             None if idx is None else idx.ctypes.data, q.ctypes.data, dq.ctypes.data, eob.ctypes.data), "quantize_batch")
+    return q, dq, eob
+
+
+def _ctx_inv_add(self, tx_size, tx_type, dq, eob, dest):
+    _bind_txq(self.L)
+    dq = np.ascontiguousarray(dq, dtype=np.int16)
+    out = np.ascontiguousarray(dest.copy(), dtype=np.uint8)
+    eob = np.ascontiguousarray(eob, dtype=np.uint16)
+    self.check(self.L.svtb200_inv_txfm_add_batch(self.h, tx_size, tx_type, dq.shape[0], dq.ctypes.data, eob.ctypes.data, out.ctypes.data), "inv_txfm_add_batch")
+    return out
+
+
+def _ctx_txq(self, tx_size, jobs, src, pred, recon, rows, want_coeff=True):
+    """jobs: TX_JOB_DTYPE array; src/pred/recon: 2-D uint8 planes (recon may be None). Returns coeff, q, dq, eob, recon."""
+    _bind_txq(self.L)
+    n, N = len(jobs), 4 << tx_size
+    jobs = np.ascontiguousarray(jobs)
+    src, pred = np.ascontiguousarray(src), np.ascontiguousarray(pred)
+    rec = None if recon is None else np.ascontiguousarray(recon.copy())
+    pl = TxPlanes()
+    pl.src, pl.src_stride, pl.src_bytes = src.ctypes.data, src.shape[1], src.nbytes
+    pl.pred, pl.pred_stride, pl.pred_bytes = pred.ctypes.data, pred.shape[1], pred.nbytes
+    if rec is not None:
+        pl.recon, pl.recon_stride, pl.recon_bytes = rec.ctypes.data, rec.shape[1], rec.nbytes
+    coeff = np.zeros((n, N, N), dtype=np.int16)
+    q, dq, eob = np.zeros_like(coeff), np.zeros_like(coeff), np.zeros(n, dtype=np.uint16)
+    rows = np.ascontiguousarray(rows)
+    self.check(self.L.svtb200_txq_batch(self.h, tx_size, n, jobs.ctypes.data, C.byref(pl), rows.ctypes.data, len(rows),
+                                        coeff.ctypes.data if want_coeff else None, q.ctypes.data, dq.ctypes.data, eob.ctypes.data), "txq_batch")
+    return coeff, q, dq, eob, rec
+
+
+Context.register_scans = _ctx_register_scans
+Context.fwd_txfm = _ctx_fwd_txfm
+Context.quantize = _ctx_quantize
+Context.inv_txfm_add = _ctx_inv_add
+Context.txq = _ctx_txq

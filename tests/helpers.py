@@ -140,3 +140,160 @@ def emu_me_picture(pic, sb_begin=0, sb_end=None, win_bytes=65536, force_global_i
     emu().me_emu_run(C.byref(pic.params), cur, r0, r1, out.ctypes.data, rcme.ctypes.data, tr.ctypes.data, sb_begin, sb_end,
                      win_bytes, force_global_interp)
     return out, rcme, tr
+
+
+# ---------------------------------------------------------------------------------------------
+# transform / quantisation helpers
+# ---------------------------------------------------------------------------------------------
+_tables = None
+
+
+def vp9_tables():
+    global _tables
+    if _tables is None:
+        _tables = np.load(os.path.join(ROOT, "svt-vp9_b200", "data", "vp9_tables.npz"))
+    return _tables
+
+
+def scan_of(tx_size, tx_type):
+    t = vp9_tables()
+    return t["scan_%d_%d" % (tx_size, tx_type)], t["iscan_%d_%d" % (tx_size, tx_type)]
+
+
+_oracle_tx_ready = False
+
+
+def oracle_tx():
+    global _oracle_tx_ready
+    L = oracle()
+    if not _oracle_tx_ready:
+        L.svtb200_oracle_fwd_txfm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.svtb200_oracle_quantize.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.svtb200_oracle_quant_row.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p]
+        L.svtb200_oracle_inv_txfm_add.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+        _oracle_tx_ready = True
+    return L
+
+
+def oracle_fwd(tx_size, tx_type, partial32, resid):
+    """resid: (n, N, N) int16 -> (n, N, N) int16"""
+    L = oracle_tx()
+    n, N = resid.shape[0], resid.shape[1]
+    resid = np.ascontiguousarray(resid)
+    out = np.zeros_like(resid)
+    for i in range(n):
+        L.svtb200_oracle_fwd_txfm(tx_size, tx_type, partial32, resid[i].ctypes.data, N, out[i].ctypes.data)
+    return out
+
+
+def quant_rows(qindices):
+    t = vp9_tables()
+    rows = np.zeros(len(qindices), dtype=api.QUANT_ROW_DTYPE)
+    L = oracle_tx()
+    for i, q in enumerate(qindices):
+        L.svtb200_oracle_quant_row(int(q), int(t["dc_q"][q]), int(t["ac_q"][q]), rows[i:].ctypes.data)
+    return rows
+
+
+def oracle_quant(tx_size, tx_type, coeff, rows, row_idx):
+    L = oracle_tx()
+    scan, _ = scan_of(tx_size, tx_type)
+    scan = np.ascontiguousarray(scan)
+    n = coeff.shape[0]
+    coeff = np.ascontiguousarray(coeff)
+    q, dq, eob = np.zeros_like(coeff), np.zeros_like(coeff), np.zeros(n, dtype=np.uint16)
+    for i in range(n):
+        L.svtb200_oracle_quantize(tx_size, coeff[i].ctypes.data, rows[int(row_idx[i]):].ctypes.data, scan.ctypes.data,
+                                  q[i].ctypes.data, dq[i].ctypes.data, eob[i:].ctypes.data)
+    return q, dq, eob
+
+
+def oracle_inv_add(tx_size, tx_type, dq, eob, dest):
+    L = oracle_tx()
+    N = dq.shape[1]
+    dq = np.ascontiguousarray(dq)
+    out = np.ascontiguousarray(dest.copy())
+    for i in range(dq.shape[0]):
+        L.svtb200_oracle_inv_txfm_add(tx_size, tx_type, dq[i].ctypes.data, int(eob[i]), out[i].ctypes.data, N)
+    return out
+
+
+# ---- the unmodified reference's own C kernels (oracle/_ref), for pinning the oracle
+_ref = None
+
+
+def ref_lib():
+    global _ref
+    if _ref is None:
+        _ref = C.CDLL(os.path.join(REF_DIR, "libSvtVp9Enc_ref.so"))
+    return _ref
+
+
+def ref_fwd(tx_size, tx_type, partial32, resid):
+    R = ref_lib()
+    n, N = resid.shape[0], resid.shape[1]
+    resid = np.ascontiguousarray(resid)
+    out = np.zeros_like(resid)
+    for i in range(n):
+        src, dst = C.c_void_p(resid[i].ctypes.data), C.c_void_p(out[i].ctypes.data)
+        if tx_size == 3:
+            (R.eb_vpx_partial_fdct32x32_c if partial32 else R.eb_vp9_fdct32x32_c)(src, dst, N)
+        else:
+            [R.eb_vp9_fht4x4_c, R.eb_vp9_fht8x8_c, R.eb_vp9_fht16x16_c][tx_size](src, dst, N, tx_type)
+    return out
+
+
+def ref_quant(tx_size, tx_type, coeff, rows, row_idx):
+    R = ref_lib()
+    scan, iscan = scan_of(tx_size, tx_type)
+    scan, iscan = np.ascontiguousarray(scan), np.ascontiguousarray(iscan)
+    n, nn = coeff.shape[0], coeff.shape[1] * coeff.shape[2]
+    coeff = np.ascontiguousarray(coeff)
+    q, dq, eob = np.zeros_like(coeff), np.zeros_like(coeff), np.zeros(n, dtype=np.uint16)
+    f = R.eb_vp9_quantize_b_32x32_c if tx_size == 3 else R.eb_vp9_quantize_b_c
+    f.argtypes = [C.c_void_p, C.c_ssize_t, C.c_int] + [C.c_void_p] * 10
+    for i in range(n):
+        r = rows[int(row_idx[i]):int(row_idx[i]) + 1]
+        f(coeff[i].ctypes.data, nn, 0, r["zbin"].ctypes.data, r["round"].ctypes.data, r["quant"].ctypes.data,
+          r["quant_shift"].ctypes.data, q[i].ctypes.data, dq[i].ctypes.data, r["dequant"].ctypes.data, eob[i:].ctypes.data,
+          scan.ctypes.data, iscan.ctypes.data)
+    return q, dq, eob
+
+
+def ref_inv_add(tx_size, tx_type, dq, eob, dest):
+    """Dispatch by eob exactly as eb_vp9_idct*_add / eb_vp9_iht*_add (vp9_idct.c:111-190), calling the _c kernels."""
+    R = ref_lib()
+    N = dq.shape[1]
+    dq = np.ascontiguousarray(dq)
+    out = np.ascontiguousarray(dest.copy())
+    for i in range(dq.shape[0]):
+        e, a, d = int(eob[i]), C.c_void_p(dq[i].ctypes.data), C.c_void_p(out[i].ctypes.data)
+        if tx_type != 0 and tx_size < 3:
+            [R.eb_vp9_iht4x4_16_add_c, R.eb_vp9_iht8x8_64_add_c, R.eb_vp9_iht16x16_256_add_c][tx_size](a, d, N, tx_type)
+        elif tx_size == 0:
+            (R.eb_vp9_idct4x4_16_add_c if e > 1 else R.eb_vp9_idct4x4_1_add_c)(a, d, N)
+        elif tx_size == 1:
+            (R.eb_vp9_idct8x8_1_add_c if e == 1 else R.eb_vp9_idct8x8_12_add_c if e <= 12 else R.eb_vp9_idct8x8_64_add_c)(a, d, N)
+        elif tx_size == 2:
+            (R.eb_vp9_idct16x16_1_add_c if e == 1 else R.eb_vp9_idct16x16_10_add_c if e <= 10 else
+             R.eb_vp9_idct16x16_38_add_c if e <= 38 else R.eb_vp9_idct16x16_256_add_c)(a, d, N)
+        else:
+            (R.eb_vp9_idct32x32_1_add_c if e == 1 else R.eb_vp9_idct32x32_34_add_c if e <= 34 else
+             R.eb_vp9_idct32x32_135_add_c if e <= 135 else R.eb_vp9_idct32x32_1024_add_c)(a, d, N)
+    return out
+
+
+def residual_blocks(rng, n, N, kind):
+    """Test residuals: 'uniform' in [-255,255], 'smooth' (low-pass, small eob after quantisation), 'extreme' (+-255 patterns)."""
+    if kind == "uniform":
+        return rng.integers(-255, 256, size=(n, N, N), dtype=np.int16)
+    if kind == "extreme":
+        b = rng.choice(np.array([-255, 255, 0], dtype=np.int16), size=(n, N, N))
+        b[0] = 255
+        b[1 % n] = -255
+        return b
+    x = rng.normal(0, 1, size=(n, N, N))
+    for _ in range(3):
+        x = (x + np.roll(x, 1, 1) + np.roll(x, 1, 2) + np.roll(x, -1, 1) + np.roll(x, -1, 2)) / 5
+    x = x / (np.abs(x).max() + 1e-9) * rng.integers(4, 200, size=(n, 1, 1))
+    return np.clip(np.rint(x), -255, 255).astype(np.int16)
