@@ -41,3 +41,24 @@ def main():
 
 if __name__ == "__main__":
     main()
+    make_lf_golden()
+
+
+def make_lf_golden():
+    """tests/golden/lf_*.bin.gz: loop-filtered pictures (inputs, masks, thresholds and the reference's output) of a smooth
+    192x128 clip at enc-mode 3, q 50 -- the textured clip above barely triggers the filter."""
+    w, h, n = 192, 128, 20
+    yuv = "/tmp/svtb200_golden_smooth.yuv"
+    synth.write_yuv(yuv, synth.make_clip(w, h, n, seed=21, k=10, g=2.0, a=2, b=1, m=32, noise=0))
+    d = "/tmp/svtb200_gold_lf"
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    env = dict(os.environ, SVTB200_SEAM_MODE="dump", SVTB200_SEAM_DIR=d, SVTB200_SEAM_MAXPICS="12")
+    subprocess.run(["./SvtVp9EncApp_seam", "-i", yuv, "-w", str(w), "-h", str(h), "-n", str(n), "-enc-mode", "3", "-tune", "1",
+                    "-q", "50", "-b", "/tmp/svtb200_golden.ivf"], cwd=os.path.join(ROOT, "oracle", "_ref"), env=env, check=True,
+                   stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+    for p in (0, 2, 9):
+        dst = os.path.join(ROOT, "tests", "golden", "lf_%dx%d_smooth_m3_%02d.bin.gz" % (w, h, p))
+        with open(os.path.join(d, "lf_pic%04d.bin" % p), "rb") as f, gzip.open(dst, "wb", 9) as g:
+            shutil.copyfileobj(f, g)
+        print("wrote", dst)

@@ -178,3 +178,92 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
     pthread_mutex_unlock(&g_mu);
     return rc;
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------
+ * S2: eb_vp9_loop_filter_frame -- run the oracle port (oracle/lf_port.c) on a copy and compare the planes
+ * ------------------------------------------------------------------------------------------------------------- */
+void __real_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_filter_level, int y_only, int partial_frame);
+void svtb200_oracle_deblock_picture(const SvtB200LfParams *p, uint8_t *y, int y_stride, uint8_t *u, uint8_t *v, int uv_stride,
+                                    SvtB200LfMask *lfm, int lfm_stride, const SvtB200LfThresh thr[64]);
+static long g_lf_total, g_lf_bad, g_lf_dumped;
+
+static void write_lf_summary(void) {
+    char path[600];
+    snprintf(path, sizeof(path), "%s/summary_lf.txt", g_dir);
+    FILE *f = fopen(path, "w");
+    if (!f) return;
+    fprintf(f, "lf_pictures %ld\nlf_bad %ld\nlf_dumped %ld\n", g_lf_total, g_lf_bad, g_lf_dumped);
+    fclose(f);
+}
+
+void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_filter_level, int y_only, int partial_frame) {
+    pthread_mutex_lock(&g_mu);
+    init_once();
+    int mode = g_mode;
+    pthread_mutex_unlock(&g_mu);
+    if (!mode || !frame_filter_level || partial_frame || sizeof(LOOP_FILTER_MASK) != sizeof(SvtB200LfMask)) {
+        __real_eb_vp9_loop_filter_frame(cm, xd, frame_filter_level, y_only, partial_frame);
+        return;
+    }
+    SvtB200LfParams P; SvtB200LfThresh thr[64];
+    svtb200_glue_lf(cm, frame_filter_level, y_only, &P, thr);
+    const int W = P.width, H = P.height, ys = xd->plane[0].dst.stride, cs = xd->plane[1].dst.stride;
+    /* the reference advances xd->plane[].dst.buf while filtering: remember the picture origins */
+    uint8_t *const ry = xd->plane[0].dst.buf, *const ru = xd->plane[1].dst.buf, *const rv = xd->plane[2].dst.buf;
+    const int sb_rows = (cm->mi_rows + 7) >> 3, n_lfm = cm->lf.lfm_stride * sb_rows;
+    uint8_t *cy = malloc((size_t)W * H), *cu = malloc((size_t)W * H / 4), *cv = malloc((size_t)W * H / 4);
+    SvtB200LfMask *lfm = malloc(sizeof(SvtB200LfMask) * n_lfm);
+    memcpy(lfm, cm->lf.lfm, sizeof(SvtB200LfMask) * n_lfm);
+    for (int r = 0; r < H; r++) memcpy(cy + (size_t)r * W, ry + (size_t)r * ys, W);
+    for (int r = 0; r < H / 2; r++) { memcpy(cu + (size_t)r * (W / 2), ru + (size_t)r * cs, W / 2); memcpy(cv + (size_t)r * (W / 2), rv + (size_t)r * cs, W / 2); }
+    FILE *df = NULL;
+    if (mode == 2) {
+        pthread_mutex_lock(&g_mu);
+        if (g_lf_dumped < g_max_dump_pics) {
+            char path[600]; snprintf(path, sizeof(path), "%s/lf_pic%04ld.bin", g_dir, g_lf_dumped++);
+            df = fopen(path, "wb");
+        }
+        pthread_mutex_unlock(&g_mu);
+        if (df) { /* inputs: params, thresholds, masks (before adjustment), planes */
+            uint32_t hdr[4] = {0x4c305653u, 1, (uint32_t)cm->lf.lfm_stride, (uint32_t)n_lfm};
+            fwrite(hdr, sizeof(hdr), 1, df); fwrite(&P, sizeof(P), 1, df); fwrite(thr, sizeof(thr), 1, df);
+            fwrite(lfm, sizeof(SvtB200LfMask), n_lfm, df);
+            fwrite(cy, 1, (size_t)W * H, df); fwrite(cu, 1, (size_t)W * H / 4, df); fwrite(cv, 1, (size_t)W * H / 4, df);
+        }
+    }
+    __real_eb_vp9_loop_filter_frame(cm, xd, frame_filter_level, y_only, partial_frame);
+    svtb200_oracle_deblock_picture(&P, cy, W, cu, cv, W / 2, lfm, cm->lf.lfm_stride, thr);
+    long bad = 0;
+    for (int r = 0; r < H; r++) bad += memcmp(cy + (size_t)r * W, ry + (size_t)r * ys, W) != 0;
+    if (!y_only)
+        for (int r = 0; r < H / 2; r++) {
+            bad += memcmp(cu + (size_t)r * (W / 2), ru + (size_t)r * cs, W / 2) != 0;
+            bad += memcmp(cv + (size_t)r * (W / 2), rv + (size_t)r * cs, W / 2) != 0;
+        }
+    if (bad && g_printed < 40) {
+        char path[600]; snprintf(path, sizeof(path), "%s/mismatch_lf.txt", g_dir);
+        FILE *f = fopen(path, "a");
+        if (f) {
+            int shown = 0;
+            fprintf(f, "lf picture %ld level %d y_only %d mi %dx%d bad rows %ld\n", g_lf_total, frame_filter_level, y_only, cm->mi_cols, cm->mi_rows, bad);
+            for (int r = 0; r < H && shown < 12; r++) for (int x = 0; x < W && shown < 12; x++)
+                if (cy[(size_t)r * W + x] != ry[(size_t)r * ys + x]) { fprintf(f, "  Y (%d,%d) ref %d port %d\n", x, r, ry[(size_t)r * ys + x], cy[(size_t)r * W + x]); shown++; }
+            shown = 0;
+            for (int r = 0; r < H / 2 && shown < 8; r++) for (int x = 0; x < W / 2 && shown < 8; x++)
+                if (cu[(size_t)r * (W / 2) + x] != ru[(size_t)r * cs + x]) { fprintf(f, "  U (%d,%d) ref %d port %d\n", x, r, ru[(size_t)r * cs + x], cu[(size_t)r * (W / 2) + x]); shown++; }
+            fclose(f); g_printed++;
+        }
+    }
+    if (df) { /* expected outputs = the reference's own filtered planes */
+        for (int r = 0; r < H; r++) fwrite(ry + (size_t)r * ys, 1, W, df);
+        for (int r = 0; r < H / 2; r++) fwrite(ru + (size_t)r * cs, 1, W / 2, df);
+        for (int r = 0; r < H / 2; r++) fwrite(rv + (size_t)r * cs, 1, W / 2, df);
+        fclose(df);
+    }
+    pthread_mutex_lock(&g_mu);
+    g_lf_total++; if (bad) g_lf_bad++;
+    write_lf_summary();
+    pthread_mutex_unlock(&g_mu);
+    free(cy); free(cu); free(cv); free(lfm);
+}

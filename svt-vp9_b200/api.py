@@ -260,3 +260,23 @@ Context.fwd_txfm = _ctx_fwd_txfm
 Context.quantize = _ctx_quantize
 Context.inv_txfm_add = _ctx_inv_add
 Context.txq = _ctx_txq
+
+
+# ---- S2: deblocking -------------------------------------------------------------------------------------------------
+def _ctx_deblock(self, params, y, u, v, lfm, lfm_stride, thr):
+    """In-place eb_vp9_loop_filter_frame on host planes (2-D uint8 arrays at picture origin). Returns (y, u, v) copies."""
+    L = self.L
+    if not getattr(L, "_lf_bound", False):
+        vp = C.c_void_p
+        L.svtb200_deblock_picture.argtypes = [vp, C.POINTER(LfParams), vp, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, vp]
+        L.svtb200_deblock_picture_dev.argtypes = [vp, C.POINTER(LfParams), vp, C.c_int32, vp, vp, C.c_int32, vp, C.c_int32, vp]
+        L._lf_bound = True
+    y, u, v = np.ascontiguousarray(y.copy()), np.ascontiguousarray(u.copy()), np.ascontiguousarray(v.copy())
+    lfm = np.ascontiguousarray(lfm)
+    thr = np.ascontiguousarray(thr)
+    self.check(L.svtb200_deblock_picture(self.h, C.byref(params), y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data, u.shape[1],
+                                         lfm.ctypes.data, lfm_stride, thr.ctypes.data), "deblock_picture")
+    return y, u, v
+
+
+Context.deblock = _ctx_deblock

@@ -16,6 +16,10 @@
 #include "EbReferenceObject.h"
 #include "EbPictureBufferDesc.h"
 
+#include "vp9_onyxc_int.h"
+#include "vp9_blockd.h"
+#include "vp9_loopfilter.h"
+
 #include "svtb200.h"
 
 static inline void svtb200_glue_plane(const EbPictureBufferDesc *d, SvtB200Plane *p) {
@@ -72,6 +76,21 @@ static inline void svtb200_glue_me_params(PictureParentControlSet *pcs, const Me
     P->cu8x8_mode               = pcs->cu8x8_mode;
     P->cu16x16_mode             = pcs->cu16x16_mode;
     P->rate_control_mode        = scs->static_config.rate_control_mode;
+}
+
+
+/* Arguments of eb_vp9_loop_filter_frame() (Source/Lib/VPX/vp9_loopfilter.c:1521) as plain data: picture geometry,
+ * the per-SB LOOP_FILTER_MASK array (same layout as SvtB200LfMask) and the 64 threshold triples. */
+static inline void svtb200_glue_lf(VP9_COMMON *cm, int filter_level, int y_only, SvtB200LfParams *P, SvtB200LfThresh thr[64]) {
+    memset(P, 0, sizeof(*P));
+    P->mi_rows = cm->mi_rows; P->mi_cols = cm->mi_cols;
+    P->width = cm->mi_cols * 8; P->height = cm->mi_rows * 8;
+    P->y_only = y_only; P->filter_level = filter_level;
+    for (int l = 0; l < 64; l++) {
+        thr[l].mblim = cm->lf_info.lfthr[l].mblim[0];
+        thr[l].lim = cm->lf_info.lfthr[l].lim[0];
+        thr[l].hev_thr = cm->lf_info.lfthr[l].hev_thr[0];
+    }
 }
 
 #endif

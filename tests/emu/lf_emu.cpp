@@ -1,0 +1,17 @@
+// CPU execution of the deblocking kernel source under csrc/emu/cuda_emu.h (test infrastructure only).
+#define SVTB200_CPU_EMU 1
+#include "../../svt-vp9_b200/csrc/emu/cuda_emu.h"
+#include "../../svt-vp9_b200/csrc/deblock_kernel.cuh"
+
+extern "C" int lf_emu_run(const SvtB200LfParams *p, uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs, const SvtB200LfMask *lfm,
+                          int lfm_stride, const SvtB200LfThresh *thr) {
+    LfKernelArgs A;
+    memset(&A, 0, sizeof(A));
+    A.P = *p; A.y = y; A.u = u; A.v = v; A.y_stride = ys; A.uv_stride = cs; A.lfm = lfm; A.lfm_stride = lfm_stride; A.thr = thr;
+    A.sbs_w = (p->mi_cols + 7) >> 3; A.sbs_h = (p->mi_rows + 7) >> 3;
+    std::vector<int32_t> done((size_t)A.sbs_w * A.sbs_h, 0);
+    int32_t ticket = 0;
+    A.ticket = &ticket; A.done = done.data(); A.gen = 1;
+    emu_launch(dim3(A.sbs_w * A.sbs_h), dim3(LF_THREADS), 0, [&] { lf_sb_kernel(A); });
+    return 0;
+}

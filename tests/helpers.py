@@ -297,3 +297,120 @@ def residual_blocks(rng, n, N, kind):
         x = (x + np.roll(x, 1, 1) + np.roll(x, 1, 2) + np.roll(x, -1, 1) + np.roll(x, -1, 2)) / 5
     x = x / (np.abs(x).max() + 1e-9) * rng.integers(4, 200, size=(n, 1, 1))
     return np.clip(np.rint(x), -255, 255).astype(np.int16)
+
+
+# ---------------------------------------------------------------------------------------------
+# deblocking helpers
+# ---------------------------------------------------------------------------------------------
+class LfPicture:
+    """One loop-filtered picture dumped from the reference (oracle/ref_seam_check.c, dump mode): inputs + the
+    reference's filtered planes."""
+
+    def __init__(self, path):
+        import gzip
+        with (gzip.open(path, "rb") if path.endswith(".gz") else open(path, "rb")) as f:
+            data = f.read()
+        magic, ver, self.lfm_stride, n_lfm = struct.unpack_from("<4I", data, 0)
+        assert magic == 0x4c305653 and ver == 1
+        off = 16
+        self.params = api.LfParams.from_buffer_copy(data[off:off + C.sizeof(api.LfParams)])
+        off += C.sizeof(api.LfParams)
+        self.thr = np.frombuffer(data, dtype=api.LF_THRESH_DTYPE, count=64, offset=off).copy()
+        off += 64 * 3
+        self.lfm = np.frombuffer(data, dtype=api.LF_MASK_DTYPE, count=n_lfm, offset=off).copy()
+        off += 160 * n_lfm
+        W, Hh = self.params.width, self.params.height
+        planes = []
+        for n, shape in [(W * Hh, (Hh, W)), (W * Hh // 4, (Hh // 2, W // 2)), (W * Hh // 4, (Hh // 2, W // 2))] * 2:
+            planes.append(np.frombuffer(data, dtype=np.uint8, count=n, offset=off).reshape(shape).copy())
+            off += n
+        self.y, self.u, self.v, self.ey, self.eu, self.ev = planes
+
+
+def oracle_deblock(params, y, u, v, lfm, lfm_stride, thr):
+    L = oracle()
+    L.svtb200_oracle_deblock_picture.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    y, u, v, m = y.copy(), u.copy(), v.copy(), lfm.copy()
+    L.svtb200_oracle_deblock_picture(C.byref(params), y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data, u.shape[1],
+                                     m.ctypes.data, lfm_stride, np.ascontiguousarray(thr).ctypes.data)
+    return y, u, v
+
+
+def emu_deblock(params, y, u, v, lfm, lfm_stride, thr):
+    L = emu()
+    L.lf_emu_run.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+    y, u, v = y.copy(), u.copy(), v.copy()
+    L.lf_emu_run(C.byref(params), y.ctypes.data, y.shape[1], u.ctypes.data, v.ctypes.data, u.shape[1],
+                 np.ascontiguousarray(lfm).ctypes.data, lfm_stride, np.ascontiguousarray(thr).ctypes.data)
+    return y, u, v
+
+
+def lf_thresholds(sharpness=0):
+    """update_sharpness + eb_vp9_loop_filter_init (vp9_loopfilter.c:221-262) for the 64 levels."""
+    thr = np.zeros(64, dtype=api.LF_THRESH_DTYPE)
+    for lvl in range(64):
+        lim = lvl >> ((sharpness > 0) + (sharpness > 4))
+        if sharpness > 0:
+            lim = min(lim, 9 - sharpness)
+        lim = max(lim, 1)
+        thr[lvl] = (2 * (lvl + 2) + lim, lim, lvl >> 4)
+    return thr
+
+
+def synthetic_lf_case(rng, width, height, level):
+    """A picture with a random but self-consistent transform-block structure: per 64x64 SB a random mix of 32x32, 16x16,
+    8x8 and 4x4 transform blocks (chroma one size down), edge masks set the way eb_vp9_build_mask does (before
+    eb_vp9_adjust_mask), some blocks left unfiltered (skip)."""
+    mi_cols, mi_rows = width // 8, height // 8
+    sbs_w, sbs_h = (mi_cols + 7) // 8, (mi_rows + 7) // 8
+    lfm = np.zeros(sbs_w * sbs_h, dtype=api.LF_MASK_DTYPE)
+    for sb in range(sbs_w * sbs_h):
+        m = lfm[sb]
+        m["lfl_y"][:] = level
+        ly, ay, lu, au = [0] * 4, [0] * 4, [0] * 4, [0] * 4
+        i4y = i4u = 0
+        for q in range(4):  # 32x32 quadrants
+            qr, qc = (q >> 1) * 4, (q & 1) * 4
+            kind = rng.integers(0, 4)  # 0: one 32x32, 1: 16x16s, 2: 8x8s, 3: 4x4s
+            if rng.random() < 0.15:
+                continue  # skipped inter block: no edges at all
+            size = [4, 2, 1, 1][kind]
+            tx = [3, 2, 1, 0][kind]
+            for br in range(qr, qr + 4, size):
+                for bc in range(qc, qc + 4, size):
+                    for k in range(size):
+                        ly[tx] |= 1 << ((br + k) * 8 + bc)
+                        ay[tx] |= 1 << (br * 8 + bc + k)
+            if kind == 3:
+                for br in range(qr, qr + 4):
+                    for bc in range(qc, qc + 4):
+                        i4y |= 1 << (br * 8 + bc)
+            # chroma: 16x16 chroma region of this quadrant = 2x2 chroma blocks; transform one size down
+            ctx_ = max(tx - 1, 0)
+            csize = {3: 2, 2: 2, 1: 1, 0: 1}[tx]
+            cr0, cc0 = qr // 2, qc // 2
+            for br in range(cr0, cr0 + 2, csize):
+                for bc in range(cc0, cc0 + 2, csize):
+                    for k in range(csize):
+                        lu[ctx_] |= 1 << ((br + k) * 4 + bc)
+                        au[ctx_] |= 1 << (br * 4 + bc + k)
+            if tx <= 1 and kind == 3:
+                for br in range(cr0, cr0 + 2):
+                    for bc in range(cc0, cc0 + 2):
+                        i4u |= 1 << (br * 4 + bc)
+        for k in range(4):
+            m["left_y"][k], m["above_y"][k], m["left_uv"][k], m["above_uv"][k] = ly[k], ay[k], lu[k], au[k]
+        m["int_4x4_y"], m["int_4x4_uv"] = i4y, i4u
+    # blocky content so that all filter flavours trigger: smooth areas with small steps + textured areas
+    base = rng.integers(0, 256, size=(height // 8 + 1, width // 8 + 1)).astype(np.float32)
+    yimg = np.kron(base, np.ones((8, 8), np.float32))[:height, :width]
+    yimg = yimg * 0.15 + 100 + rng.integers(-2, 3, size=yimg.shape) * (rng.random(yimg.shape) < 0.5)
+    tex = rng.integers(0, 256, size=yimg.shape)
+    sel = np.kron(rng.random((height // 32 + 1, width // 32 + 1)) < 0.3, np.ones((32, 32), bool))[:height, :width]
+    yimg = np.where(sel, tex, yimg)
+    y = np.clip(np.rint(yimg), 0, 255).astype(np.uint8)
+    u = np.ascontiguousarray(y[::2, ::2] // 2 + 60).astype(np.uint8)
+    v = np.ascontiguousarray(255 - u)
+    P = api.LfParams()
+    P.width, P.height, P.mi_rows, P.mi_cols, P.y_only, P.filter_level = width, height, mi_rows, mi_cols, 0, level
+    return P, y, u, v, lfm, sbs_w
