@@ -87,6 +87,10 @@ int svtb200_picture_upload(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane 
 int svtb200_picture_upload_luma(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane *full,
                                 int32_t quarter_pad, int32_t sixteenth_pad, int make_quarter);
 int svtb200_picture_release(SvtB200Ctx *ctx, uint64_t pic_id);
+/* Device-side descriptor of an uploaded plane (which: 0 full, 1 quarter, 2 sixteenth): buf is a DEVICE pointer with the
+ * same stride / origin as the uploaded host plane -- for chaining svtb200_txq_batch_dev / svtb200_deblock_picture_dev
+ * on planes that are already resident. */
+int svtb200_picture_plane_dev(SvtB200Ctx *ctx, uint64_t pic_id, int which, SvtB200Plane *out);
 
 /* Everything motion_estimate_sb() reads from MeContext / PictureParentControlSet /
  * SequenceControlSet (EbMotionEstimationContext.h:275, EbPictureControlSet.h:229). */

@@ -51,3 +51,8 @@ gcc -shared -o $OUT/libSvtVp9Enc_seam.so $OUT/obj/*.o $OUT/seam_check.o $OUT/me_
 gcc -std=gnu99 -O2 -w -I$OUT/inc -I$REF/Source/API $REF/Source/App/*.c -o $OUT/SvtVp9EncApp_seam \
     -L$OUT -lSvtVp9Enc_seam -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN'
 echo "build_ref: seam-check flavour ok"
+
+# ---- path driver: the reference's own hot-path functions callable from plain data (bench reference arm + tests)
+gcc $CF -fcommon $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/ref_path_driver.c -o $OUT/ref_path_driver.o
+gcc -shared -o $OUT/libSvtVp9Enc_refdrv.so $OUT/obj/*.o $OUT/ref_path_driver.o -lpthread -lm -Wl,--no-undefined
+echo "build_ref: path driver ok"

@@ -1,0 +1,231 @@
+/*
+ * TEST INFRASTRUCTURE / CPU BASELINE ONLY.  Drives the UNMODIFIED reference's own hot-path functions from plain
+ * data, so that (a) bench.py's reference arm times the reference's real implementation (C or AVX2 dispatch, as the
+ * encoder itself would select) on the host cores, and (b) the tests can compare the CUDA path with the reference
+ * on arbitrary inputs, not only on dumped encodes.  Compiled by oracle/build_ref.sh against the reference's headers
+ * and linked with the reference objects into oracle/_ref/libSvtVp9Enc_refdrv.so.  Nothing here is product code.
+ *
+ *   refdrv_init(asm)            eb_vp9_ASM_TYPES + setup_rtcd_internal / setup_rtcd_internal_vp9 (EbEncHandle.c:800-807)
+ *   refdrv_me_range(...)        motion_estimate_sb (EbMotionEstimation.c:4524) for a range of SBs, with the per-SB
+ *                               buffer set-up of eb_vp9_motion_estimation_kernel (EbMotionEstimationProcess.c:978-1035)
+ *   refdrv_txq(...)             the kernel sequence of perform_coding_loop (EbEncDecProcess.c:365-587)
+ *   refdrv_deblock(...)         eb_vp9_loop_filter_frame (vp9_loopfilter.c:1521)
+ */
+#define RTCD_C /* the two headers then provide the static setup_rtcd_internal*; built with -fcommon so that the
+                  function-pointer variables merge with the definitions in the reference objects */
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "svtb200_ref_glue.h"
+#include "vpx_dsp_rtcd.h"
+#include "vp9_rtcd.h"
+#include "vp9_idct.h"
+#include "vp9_scan.h"
+#include "EbMotionEstimation.h"
+#include "EbPictureOperators.h"
+
+uint32_t get_cpu_asm_type(void);
+EbErrorType eb_vp9_me_context_ctor(MeContext **object_dbl_ptr);
+
+static int g_init;
+
+int refdrv_init(int use_simd) {
+    if (g_init) return 0;
+    /* the constructors register their allocations in the encoder's global memory map */
+    static uint32_t idx;
+    static uint64_t total;
+    memory_map       = (EbMemoryMapEntry *)calloc(MAX_NUM_PTR, sizeof(EbMemoryMapEntry));
+    memory_map_index = &idx;
+    total_lib_memory = &total;
+    eb_vp9_ASM_TYPES = use_simd ? get_cpu_asm_type() : 0;
+    setup_rtcd_internal(eb_vp9_ASM_TYPES);
+    setup_rtcd_internal_vp9(eb_vp9_ASM_TYPES);
+    g_init = 1;
+    return (int)eb_vp9_ASM_TYPES;
+}
+
+/* ------------------------------------------------------------------------------------------------ ME */
+typedef struct {
+    MeContext               *me;
+    PictureParentControlSet *pcs;
+    SequenceControlSet      *scs;
+    EbObjectWrapper          scs_w, ref_w[2];
+    EbPaReferenceObject      pa_cur, pa_ref[2];
+    EbPictureBufferDesc      d_cur[3], d_ref[2][3];
+    MeCuResults             *res; /* one SB */
+    MeCuResults             *res_ptr[1];
+} RefMe;
+
+void *refdrv_me_new(void) {
+    RefMe *r = (RefMe *)calloc(1, sizeof(RefMe));
+    if (eb_vp9_me_context_ctor(&r->me) != EB_ErrorNone) return NULL;
+    r->pcs = (PictureParentControlSet *)calloc(1, sizeof(PictureParentControlSet));
+    r->scs = (SequenceControlSet *)calloc(1, sizeof(SequenceControlSet));
+    r->res = (MeCuResults *)calloc(85, sizeof(MeCuResults));
+    return r;
+}
+
+static void desc_of(const SvtB200Plane *p, EbPictureBufferDesc *d) {
+    memset(d, 0, sizeof(*d));
+    d->buffer_y = (EbByte)p->buf; d->stride_y = (uint16_t)p->stride;
+    d->origin_x = (uint16_t)p->origin_x; d->origin_y = (uint16_t)p->origin_y;
+    d->width = (uint16_t)p->width; d->height = (uint16_t)p->height;
+    d->luma_size = (uint32_t)p->stride * (uint32_t)p->padded_height;
+}
+
+int refdrv_me_range(void *h, const SvtB200MeParams *P, const SvtB200Plane cur[3], const SvtB200Plane ref0[3],
+                    const SvtB200Plane ref1[3], int sb_begin, int sb_end, SvtB200MeCuResult *out) {
+    RefMe *r = (RefMe *)h;
+    MeContext *me = r->me;
+    PictureParentControlSet *pcs = r->pcs;
+    for (int i = 0; i < 3; i++) { desc_of(&cur[i], &r->d_cur[i]); desc_of(&ref0[i], &r->d_ref[0][i]); desc_of(ref1 ? &ref1[i] : &ref0[i], &r->d_ref[1][i]); }
+    for (int l = 0; l < 2; l++) {
+        r->pa_ref[l].input_padded_picture_ptr = &r->d_ref[l][0];
+        r->pa_ref[l].quarter_decimated_picture_ptr = &r->d_ref[l][1];
+        r->pa_ref[l].sixteenth_decimated_picture_ptr = &r->d_ref[l][2];
+        r->ref_w[l].object_ptr = &r->pa_ref[l];
+        pcs->ref_pa_pic_ptr_array[l] = &r->ref_w[l];
+        pcs->ref_pic_poc_array[l] = P->ref_poc[l];
+    }
+    r->scs->luma_width = (uint16_t)P->luma_width; r->scs->luma_height = (uint16_t)P->luma_height;
+    r->scs->static_config.rate_control_mode = 0;
+    r->scs_w.object_ptr = r->scs;
+    pcs->sequence_control_set_wrapper_ptr = &r->scs_w;
+    pcs->slice_type = P->num_lists == 1 ? P_SLICE : B_SLICE;
+    pcs->temporal_layer_index = (uint8_t)P->temporal_layer_index;
+    pcs->hierarchical_levels = (uint8_t)P->hierarchical_levels;
+    pcs->enable_hme_flag = (EB_BOOL)P->enable_hme_flag;
+    pcs->enable_hme_level_0_flag = (EB_BOOL)P->enable_hme_level0;
+    pcs->enable_hme_level_1_flag = (EB_BOOL)P->enable_hme_level1;
+    pcs->enable_hme_level_2_flag = (EB_BOOL)P->enable_hme_level2;
+    pcs->cu8x8_mode = P->cu8x8_mode; pcs->cu16x16_mode = P->cu16x16_mode;
+    pcs->max_number_of_pus_per_sb = 85;
+    pcs->me_results = r->res_ptr; r->res_ptr[0] = r->res;
+    me->single_hme_quadrant = (EB_BOOL)P->single_hme_quadrant;
+    me->number_hme_search_region_in_width = (uint16_t)P->number_hme_search_region_in_width;
+    me->number_hme_search_region_in_height = (uint16_t)P->number_hme_search_region_in_height;
+    me->hme_level0_total_search_area_width = (uint16_t)P->hme_level0_total_search_area_width;
+    me->hme_level0_total_search_area_height = (uint16_t)P->hme_level0_total_search_area_height;
+    for (int i = 0; i < 2; i++) {
+        me->hme_level0_search_area_in_width_array[i] = (uint16_t)P->hme_level0_search_area_in_width[i];
+        me->hme_level0_search_area_in_height_array[i] = (uint16_t)P->hme_level0_search_area_in_height[i];
+        me->hme_level1_search_area_in_width_array[i] = (uint16_t)P->hme_level1_search_area_in_width[i];
+        me->hme_level1_search_area_in_height_array[i] = (uint16_t)P->hme_level1_search_area_in_height[i];
+        me->hme_level2_search_area_in_width_array[i] = (uint16_t)P->hme_level2_search_area_in_width[i];
+        me->hme_level2_search_area_in_height_array[i] = (uint16_t)P->hme_level2_search_area_in_height[i];
+    }
+    me->search_area_width = (uint8_t)P->search_area_width; me->search_area_height = (uint8_t)P->search_area_height;
+    me->fractional_search_method = (uint8_t)P->fractional_search_method;
+    me->fractional_search_model = (uint8_t)P->fractional_search_model;
+    me->fractional_search64x64 = (EB_BOOL)P->fractional_search64x64;
+
+    const EbPictureBufferDesc *in = &r->d_cur[0], *q = &r->d_cur[1], *s = &r->d_cur[2];
+    const int sbs_w = (P->luma_width + 63) / 64;
+    for (int sb = sb_begin; sb < sb_end; sb++) {
+        const uint32_t ox = (uint32_t)(sb % sbs_w) * 64, oy = (uint32_t)(sb / sbs_w) * 64;
+        const uint32_t sbw = (uint32_t)(P->luma_width - (int)ox < 64 ? P->luma_width - (int)ox : 64);
+        const uint32_t sbh = (uint32_t)(P->luma_height - (int)oy < 64 ? P->luma_height - (int)oy : 64);
+        uint32_t bi = (in->origin_y + oy) * in->stride_y + in->origin_x + ox;
+        me->hme_search_type = HME_RECTANGULAR;
+        for (uint32_t row = 0; row < 64; row++) memcpy(&me->sb_buffer[row * 64], &in->buffer_y[bi + row * in->stride_y], 64);
+        me->sb_src_ptr = &in->buffer_y[bi]; me->sb_src_stride = in->stride_y;
+        if (P->enable_hme_level1) {
+            bi = (q->origin_y + (oy >> 1)) * q->stride_y + q->origin_x + (ox >> 1);
+            for (uint32_t row = 0; row < (sbh >> 1); row++)
+                memcpy(&me->quarter_sb_buffer[row * me->quarter_sb_buffer_stride], &q->buffer_y[bi + row * q->stride_y], sbw >> 1);
+        }
+        if (P->enable_hme_level0) {
+            bi = (s->origin_y + (oy >> 2)) * s->stride_y + s->origin_x + (ox >> 2);
+            uint8_t *fp = &s->buffer_y[bi], *lp = me->sixteenth_sb_buffer;
+            for (uint32_t row = 0; row < (sbh >> 2); row += 2) { memcpy(lp, fp, sbw >> 2); lp += 16; fp += s->stride_y << 1; }
+        }
+        motion_estimate_sb(pcs, 0, ox, oy, me, (EbPictureBufferDesc *)in);
+        for (int i = 0; i < 85; i++) {
+            SvtB200MeCuResult *o = &out[(size_t)sb * 85 + i];
+            const MeCuResults *m = &r->res[i];
+            memset(o, 0, sizeof(*o));
+            o->x_mv_l0 = m->x_mv_l0; o->y_mv_l0 = m->y_mv_l0;
+            if (P->num_lists == 2) { o->x_mv_l1 = m->x_mv_l1; o->y_mv_l1 = m->y_mv_l1; }
+            o->total_me_candidate_index = m->total_me_candidate_index;
+            for (int k = 0; k < m->total_me_candidate_index && k < 3; k++) { o->cand[k].distortion = m->distortion_direction[k].distortion; o->cand[k].direction = m->distortion_direction[k].direction; }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ transform / quant */
+int refdrv_txq(int tx_size, int n_begin, int n_end, const SvtB200TxJob *jobs, const SvtB200TxPlanes *pl, const SvtB200QuantRow *qrows,
+               int16_t *coeff, int16_t *qcoeff, int16_t *dqcoeff, uint16_t *eob) {
+    const int N = 4 << tx_size, nn = N * N;
+    const int asm_i = (eb_vp9_ASM_TYPES & PREAVX2_MASK) && 1;
+    int16_t resid[32 * 32] __attribute__((aligned(64)));
+    int16_t tmp[32 * 32] __attribute__((aligned(64)));
+    for (int i = n_begin; i < n_end; i++) {
+        const SvtB200TxJob *j = &jobs[i];
+        /* the SIMD quantisers load 8-entry, 16-byte aligned rows (QUANTS in vp9_quantize.h: [q][8], entries 1..7 = AC) */
+        struct { int16_t zbin[8], round[8], quant[8], quant_shift[8], dequant[8]; } qa __attribute__((aligned(32)));
+        for (int k = 0; k < 8; k++) {
+            qa.zbin[k] = qrows[j->qrow].zbin[k != 0]; qa.round[k] = qrows[j->qrow].round[k != 0]; qa.quant[k] = qrows[j->qrow].quant[k != 0];
+            qa.quant_shift[k] = qrows[j->qrow].quant_shift[k != 0]; qa.dequant[k] = qrows[j->qrow].dequant[k != 0];
+        }
+        const typeof(qa) *q = &qa;
+        const uint8_t *s = pl->src + j->src_offset, *p = pl->pred + j->pred_offset;
+        int16_t *c = coeff ? coeff + (size_t)i * nn : tmp;
+        const int tt = tx_size == 3 ? 0 : j->tx_type;
+        const scan_order *so = tx_size == 3 ? &eb_vp9_default_scan_orders[TX_32X32] : &eb_vp9_scan_orders[tx_size][tt];
+        eb_vp9_residual_kernel_func_ptr_array[asm_i][N >> 3]((uint8_t *)s, pl->src_stride, (uint8_t *)p, pl->pred_stride, resid, N, N, N);
+        switch (tx_size) {
+        case 3:
+            if (j->flags & SVTB200_TXJ_PARTIAL32) { memset(c, 0, 1024 * sizeof(int16_t)); eb_vpx_partial_fdct32x32(resid, c, N); }
+            else eb_vp9_fdct32x32(resid, c, N);
+            eb_vp9_quantize_b_32x32(c, 1024, 0, q->zbin, q->round, q->quant, q->quant_shift, qcoeff + (size_t)i * nn, dqcoeff + (size_t)i * nn,
+                                    q->dequant, &eob[i], so->scan, so->iscan);
+            break;
+        case 2: eb_vp9_fht16x16(resid, c, N, tt); break;
+        case 1: eb_vp9_fht8x8(resid, c, N, tt); break;
+        default: eb_vp9_fht4x4(resid, c, N, tt); break;
+        }
+        if (tx_size < 3)
+            eb_vp9_quantize_b(c, nn, 0, q->zbin, q->round, q->quant, q->quant_shift, qcoeff + (size_t)i * nn, dqcoeff + (size_t)i * nn,
+                              q->dequant, &eob[i], so->scan, so->iscan);
+        if ((j->flags & SVTB200_TXJ_RECON) && pl->recon) {
+            uint8_t *r = pl->recon + j->recon_offset;
+            for (int y = 0; y < N; y++) memcpy(r + (size_t)y * pl->recon_stride, p + (size_t)y * pl->pred_stride, N);
+            if (eob[i]) {
+                const int16_t *d = dqcoeff + (size_t)i * nn;
+                switch (tx_size) {
+                case 3: eb_vp9_idct32x32_add(d, r, pl->recon_stride, eob[i]); break;
+                case 2: eb_vp9_iht16x16_add(tt, d, r, pl->recon_stride, eob[i]); break;
+                case 1: eb_vp9_iht8x8_add(tt, d, r, pl->recon_stride, eob[i]); break;
+                default: eb_vp9_iht4x4_add(tt, d, r, pl->recon_stride, eob[i]); break;
+                }
+            }
+        }
+    }
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ deblocking */
+int refdrv_deblock(const SvtB200LfParams *P, uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs, const SvtB200LfMask *lfm,
+                   int lfm_stride, const SvtB200LfThresh *thr) {
+    VP9_COMMON  *cm = (VP9_COMMON *)calloc(1, sizeof(VP9_COMMON));
+    MACROBLOCKD *xd = (MACROBLOCKD *)calloc(1, sizeof(MACROBLOCKD));
+    const int sbs_h = (P->mi_rows + 7) >> 3;
+    cm->mi_rows = P->mi_rows; cm->mi_cols = P->mi_cols;
+    cm->lf.lfm_stride = lfm_stride;
+    cm->lf.lfm = (LOOP_FILTER_MASK *)malloc(sizeof(LOOP_FILTER_MASK) * (size_t)lfm_stride * sbs_h);
+    memcpy(cm->lf.lfm, lfm, sizeof(LOOP_FILTER_MASK) * (size_t)lfm_stride * sbs_h);
+    cm->lf.filter_level = P->filter_level;
+    for (int l = 0; l < 64; l++) {
+        memset(cm->lf_info.lfthr[l].mblim, thr[l].mblim, SIMD_WIDTH);
+        memset(cm->lf_info.lfthr[l].lim, thr[l].lim, SIMD_WIDTH);
+        memset(cm->lf_info.lfthr[l].hev_thr, thr[l].hev_thr, SIMD_WIDTH);
+    }
+    xd->plane[0].dst.buf = y; xd->plane[0].dst.stride = ys;
+    xd->plane[1].dst.buf = u; xd->plane[1].dst.stride = cs; xd->plane[1].subsampling_x = xd->plane[1].subsampling_y = 1;
+    xd->plane[2].dst.buf = v; xd->plane[2].dst.stride = cs; xd->plane[2].subsampling_x = xd->plane[2].subsampling_y = 1;
+    eb_vp9_loop_filter_frame(cm, xd, P->filter_level, P->y_only, 0);
+    free(cm->lf.lfm); free(cm); free(xd);
+    return 0;
+}

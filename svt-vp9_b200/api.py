@@ -115,6 +115,7 @@ def lib():
         L.svtb200_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.svtb200_picture_upload.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane)]
         L.svtb200_picture_release.argtypes = [C.c_void_p, C.c_uint64]
+        L.svtb200_picture_plane_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Plane)]
         L.svtb200_me_picture.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
         L.svtb200_me_picture_dev.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
         L.svtb200_me_enable_trace.argtypes = [C.c_void_p, C.c_int]

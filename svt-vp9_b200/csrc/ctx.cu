@@ -103,6 +103,17 @@ int svtb200_picture_upload(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *f
     return SVTB200_OK;
 }
 
+int svtb200_picture_plane_dev(SvtB200Ctx *c, uint64_t pic_id, int which, SvtB200Plane *out) {
+    if (!c || !out || which < 0 || which > 2) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->pics.find(pic_id);
+    if (it == c->pics.end() || !it->second.pl[which].buf) return SVTB200_ENOENT;
+    const DevPlane &d = it->second.pl[which];
+    out->buf = d.buf; out->stride = d.stride; out->origin_x = d.ox; out->origin_y = d.oy; out->width = d.w; out->height = d.h;
+    out->padded_height = d.rows;
+    return SVTB200_OK;
+}
+
 int svtb200_picture_release(SvtB200Ctx *c, uint64_t pic_id) {
     if (!c) return SVTB200_EINVAL;
     std::lock_guard<std::mutex> g(c->mu);

@@ -414,3 +414,78 @@ def synthetic_lf_case(rng, width, height, level):
     P = api.LfParams()
     P.width, P.height, P.mi_rows, P.mi_cols, P.y_only, P.filter_level = width, height, mi_rows, mi_cols, 0, level
     return P, y, u, v, lfm, sbs_w
+
+
+# ---------------------------------------------------------------------------------------------
+# the reference's own hot-path functions (oracle/_ref/libSvtVp9Enc_refdrv.so, oracle/ref_path_driver.c)
+# ---------------------------------------------------------------------------------------------
+_refdrv = None
+
+
+def have_refdrv():
+    return os.path.exists(os.path.join(REF_DIR, "libSvtVp9Enc_refdrv.so"))
+
+
+def refdrv(use_simd=1):
+    global _refdrv
+    if _refdrv is None:
+        L = C.CDLL(os.path.join(REF_DIR, "libSvtVp9Enc_refdrv.so"))
+        L.refdrv_init.argtypes = [C.c_int]
+        L.refdrv_me_new.restype = C.c_void_p
+        L.refdrv_me_range.argtypes = [C.c_void_p, C.POINTER(api.MeParams), C.POINTER(api.Plane), C.POINTER(api.Plane), C.POINTER(api.Plane),
+                                      C.c_int, C.c_int, C.c_void_p]
+        L.refdrv_txq.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(api.TxPlanes), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refdrv_deblock.argtypes = [C.POINTER(api.LfParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.refdrv_init(use_simd)
+        _refdrv = L
+    return _refdrv
+
+
+def refdrv_me_picture(P, cur, r0, r1, n_sb, threads=1):
+    """The reference's motion_estimate_sb over a whole picture; cur/r0/r1 = (api.Plane * 3)."""
+    from concurrent.futures import ThreadPoolExecutor
+    L = refdrv()
+    out = np.zeros(n_sb * 85, dtype=api.ME_RESULT_DTYPE)
+    chunk = max(1, (n_sb + threads * 4 - 1) // (threads * 4))
+    ranges = [(s, min(n_sb, s + chunk)) for s in range(0, n_sb, chunk)]
+
+    def work(rg):
+        h = L.refdrv_me_new()
+        L.refdrv_me_range(h, C.byref(P), cur, r0, r1, rg[0], rg[1], out.ctypes.data)
+
+    if threads == 1:
+        for rg in ranges:
+            work(rg)
+    else:
+        with ThreadPoolExecutor(threads) as ex:
+            list(ex.map(work, ranges))
+    return out
+
+
+def refdrv_txq(tx_size, jobs, src, pred, recon, rows):
+    L = refdrv()
+    n, N = len(jobs), 4 << tx_size
+    jobs = np.ascontiguousarray(jobs)
+    rec = None if recon is None else np.ascontiguousarray(recon.copy())
+    pl = api.TxPlanes()
+    pl.src, pl.src_stride, pl.src_bytes = src.ctypes.data, src.shape[1], src.nbytes
+    pl.pred, pl.pred_stride, pl.pred_bytes = pred.ctypes.data, pred.shape[1], pred.nbytes
+    if rec is not None:
+        pl.recon, pl.recon_stride, pl.recon_bytes = rec.ctypes.data, rec.shape[1], rec.nbytes
+    coeff = np.zeros((n, N, N), dtype=np.int16)
+    q, dq, eob = np.zeros_like(coeff), np.zeros_like(coeff), np.zeros(n, dtype=np.uint16)
+    rows = np.ascontiguousarray(rows)
+    L.refdrv_txq(tx_size, 0, n, jobs.ctypes.data, C.byref(pl), rows.ctypes.data, coeff.ctypes.data, q.ctypes.data, dq.ctypes.data, eob.ctypes.data)
+    return coeff, q, dq, eob, rec
+
+
+def refdrv_deblock(P, y, u, v, lfm, lfm_stride, thr, pad=16):
+    """Runs the reference filter on padded copies (it also filters the half block row/column below/right of odd-sized
+    pictures, inside its padding)."""
+    L = refdrv()
+    yy = np.ascontiguousarray(np.pad(y, ((0, pad), (0, pad)), mode="edge"))
+    uu = np.ascontiguousarray(np.pad(u, ((0, pad), (0, pad)), mode="edge"))
+    vv = np.ascontiguousarray(np.pad(v, ((0, pad), (0, pad)), mode="edge"))
+    L.refdrv_deblock(C.byref(P), yy.ctypes.data, yy.shape[1], uu.ctypes.data, vv.ctypes.data, uu.shape[1],
+                     np.ascontiguousarray(lfm).ctypes.data, lfm_stride, np.ascontiguousarray(thr).ctypes.data)
+    return yy[:y.shape[0], :y.shape[1]], uu[:u.shape[0], :u.shape[1]], vv[:v.shape[0], :v.shape[1]]
