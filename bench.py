@@ -37,6 +37,7 @@ api = importlib.import_module("svt-vp9_b200.api")
 frames = importlib.import_module("svt-vp9_b200.frames")
 presets = importlib.import_module("svt-vp9_b200.presets")
 synth = importlib.import_module("svt-vp9_b200.synth")
+sharding = importlib.import_module("svt-vp9_b200.sharding")
 
 W4K, H4K = 3840, 2160
 N_SB = 60 * 34
@@ -458,12 +459,11 @@ def main():
     ms_e2e = (time.perf_counter() - t0) * 1000.0
     sampler.stop()
 
-    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_res, ms_e2e = float(t[0]), float(t[1])
-    value = world * args.steps / (ms_res / 1000.0)
-    e2e = world * args.steps / (ms_e2e / 1000.0)
+    # every rank processed its own pictures (svt-vp9_b200/sharding.py): time = max over ranks, units = sum over ranks
+    ms_res, units = sharding.agree_step(ms_res, args.steps, device="cuda")
+    ms_e2e, _ = sharding.agree_step(ms_e2e, args.steps, device="cuda")
+    value = units / (ms_res / 1000.0)
+    e2e = units / (ms_e2e / 1000.0)
     h2d = pics[0]["full"].nbytes + pics[0]["sixteenth"].nbytes + 2 * csize
     d2h = N_SB * 85 * 40 + N_TU_Y * 2050 + 2 * N_TU_C * 514 + (W4K * H4K * 3 // 2) // 16  # filtered planes on 1 of 16 pictures
 

@@ -114,6 +114,7 @@ def lib():
         L.svtb200_memcpy_h2d.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.svtb200_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.svtb200_picture_upload.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane)]
+        L.svtb200_picture_upload_luma.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Plane), C.c_int32, C.c_int32, C.c_int]
         L.svtb200_picture_release.argtypes = [C.c_void_p, C.c_uint64]
         L.svtb200_picture_plane_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Plane)]
         L.svtb200_me_picture.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
@@ -161,6 +162,19 @@ class Context:
         q = C.byref(quarter) if quarter is not None else None
         s = C.byref(sixteenth) if sixteenth is not None else None
         self.check(self.L.svtb200_picture_upload(self.h, pic_id, C.byref(full), q, s), "picture_upload")
+
+    def picture_upload_luma(self, pic_id, full, quarter_pad=32, sixteenth_pad=16, make_quarter=True):
+        """Only the picture area of the padded luma crosses PCIe; padding and both decimations are made on the device."""
+        self.check(self.L.svtb200_picture_upload_luma(self.h, pic_id, C.byref(full), quarter_pad, sixteenth_pad, int(make_quarter)),
+                   "picture_upload_luma")
+
+    def picture_plane(self, pic_id, which):
+        """Download one resident plane (0 full, 1 quarter, 2 sixteenth) -> (array (rows, stride), Plane descriptor)."""
+        d = Plane()
+        self.check(self.L.svtb200_picture_plane_dev(self.h, pic_id, which, C.byref(d)), "picture_plane_dev")
+        out = np.zeros((d.padded_height, d.stride), dtype=np.uint8)
+        self.check(self.L.svtb200_memcpy_d2h(self.h, out.ctypes.data, d.buf, out.nbytes), "memcpy_d2h")
+        return out, d
 
     def picture_release(self, pic_id):
         self.L.svtb200_picture_release(self.h, pic_id)

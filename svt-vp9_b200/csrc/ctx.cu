@@ -103,6 +103,77 @@ int svtb200_picture_upload(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *f
     return SVTB200_OK;
 }
 
+/* Edge replication of the padded source plane (eb_vp9_generate_padding, EbPictureOperators.c) and the point decimations
+ * of eb_vp9_decimation_2d (EbPictureAnalysisProcess.c:102) with their own padding, one thread per 4 output bytes. */
+__global__ void pa_pad_full_kernel(uint8_t *buf, int stride, int ox, int oy, int w, int h, int rows) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= stride || y >= rows) return;
+    const int sy = min(max(y - oy, 0), h - 1);
+    if (y >= oy && y < oy + h && x4 >= ox && x4 + 4 <= ox + w) return; /* interior word */
+    const uint8_t *row = buf + (size_t)(oy + sy) * stride + ox;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) v |= (uint32_t)row[min(max(x4 + k - ox, 0), w - 1)] << (8 * k);
+    if (x4 + 4 <= stride) *(uint32_t *)(buf + (size_t)y * stride + x4) = v;
+    else for (int k = 0; x4 + k < stride; k++) buf[(size_t)y * stride + x4 + k] = (uint8_t)(v >> (8 * k));
+}
+__global__ void pa_decimate_kernel(const uint8_t *full, int fstride, int fox, int foy, uint8_t *dst, int stride, int ox, int oy,
+                                   int w, int h, int rows, int step) {
+    const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x4 >= stride || y >= rows) return;
+    const uint8_t *row = full + (size_t)(foy + min(max(y - oy, 0), h - 1) * step) * fstride + fox;
+    uint32_t v = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) v |= (uint32_t)row[min(max(x4 + k - ox, 0), w - 1) * step] << (8 * k);
+    if (x4 + 4 <= stride) *(uint32_t *)(dst + (size_t)y * stride + x4) = v;
+    else for (int k = 0; x4 + k < stride; k++) dst[(size_t)y * stride + x4 + k] = (uint8_t)(v >> (8 * k));
+}
+
+static int alloc_plane(SvtB200Ctx *c, DevPlane *dst, int stride, int rows) {
+    const size_t bytes = (size_t)stride * rows;
+    if (!dst->buf || (size_t)dst->stride * dst->rows < bytes) {
+        if (dst->buf) cudaFree(dst->buf);
+        dst->buf = nullptr;
+        if (cudaMalloc((void **)&dst->buf, bytes + 256) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(plane) failed"; return SVTB200_ENOMEM; }
+        cudaMemsetAsync(dst->buf + bytes, 0, 256, c->stream);
+    }
+    dst->stride = stride; dst->rows = rows;
+    return 0;
+}
+
+int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *full, int32_t quarter_pad, int32_t sixteenth_pad,
+                                int make_quarter) {
+    if (!c || !full || !full->buf || full->stride <= 0 || full->padded_height <= 0 || quarter_pad < 0 || sixteenth_pad < 0) return SVTB200_EINVAL;
+    if ((full->stride & 3) || full->width <= 0 || full->height <= 0) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    DevPicture &p = c->pics[pic_id];
+    int rc;
+    DevPlane *f = &p.pl[0];
+    if ((rc = alloc_plane(c, f, full->stride, full->padded_height))) return rc;
+    f->ox = full->origin_x; f->oy = full->origin_y; f->w = full->width; f->h = full->height;
+    /* only the picture area crosses PCIe; the padding is regenerated on the device */
+    const size_t off = (size_t)f->oy * f->stride + f->ox;
+    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(f->buf + off, f->stride, full->buf + off, full->stride, f->w, f->h, cudaMemcpyHostToDevice, c->stream));
+    dim3 blk(128);
+    pa_pad_full_kernel<<<dim3((f->stride / 4 + 127) / 128, f->rows), blk, 0, c->stream>>>(f->buf, f->stride, f->ox, f->oy, f->w, f->h, f->rows);
+    c->launches++;
+    for (int lvl = 1; lvl <= 2; lvl++) {
+        DevPlane *d = &p.pl[lvl];
+        if (lvl == 1 && !make_quarter) { if (d->buf) cudaFree(d->buf); *d = DevPlane(); continue; }
+        const int step = lvl == 1 ? 2 : 4, pad = lvl == 1 ? quarter_pad : sixteenth_pad;
+        const int w = (f->w + step - 1) / step, h = (f->h + step - 1) / step;
+        const int stride = (w + 2 * pad + 3) & ~3; /* multiple of 4 for the word stores; the reference's strides are */
+        if ((rc = alloc_plane(c, d, stride, h + 2 * pad))) return rc;
+        d->ox = pad; d->oy = pad; d->w = w; d->h = h;
+        pa_decimate_kernel<<<dim3((stride / 4 + 127) / 128, d->rows), blk, 0, c->stream>>>(f->buf, f->stride, f->ox, f->oy, d->buf, stride, pad, pad, w, h,
+                                                                                     d->rows, step);
+        c->launches++;
+    }
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
 int svtb200_picture_plane_dev(SvtB200Ctx *c, uint64_t pic_id, int which, SvtB200Plane *out) {
     if (!c || !out || which < 0 || which > 2) return SVTB200_EINVAL;
     std::lock_guard<std::mutex> g(c->mu);

@@ -462,18 +462,34 @@ def refdrv_me_picture(P, cur, r0, r1, n_sb, threads=1):
     return out
 
 
+def aligned_zeros(shape, dtype, align=64):
+    """The reference's SIMD kernels use aligned loads/stores on coefficient buffers and block rows."""
+    dt = np.dtype(dtype)
+    n = int(np.prod(shape)) * dt.itemsize
+    raw = np.zeros(n + align, dtype=np.uint8)
+    off = (-raw.ctypes.data) % align
+    return raw[off:off + n].view(dt).reshape(shape)
+
+
+def aligned_copy(a, align=64):
+    out = aligned_zeros(a.shape, a.dtype, align)
+    out[...] = a
+    return out
+
+
 def refdrv_txq(tx_size, jobs, src, pred, recon, rows):
     L = refdrv()
     n, N = len(jobs), 4 << tx_size
     jobs = np.ascontiguousarray(jobs)
-    rec = None if recon is None else np.ascontiguousarray(recon.copy())
+    src, pred = aligned_copy(src), aligned_copy(pred)
+    rec = None if recon is None else aligned_copy(recon)
     pl = api.TxPlanes()
     pl.src, pl.src_stride, pl.src_bytes = src.ctypes.data, src.shape[1], src.nbytes
     pl.pred, pl.pred_stride, pl.pred_bytes = pred.ctypes.data, pred.shape[1], pred.nbytes
     if rec is not None:
         pl.recon, pl.recon_stride, pl.recon_bytes = rec.ctypes.data, rec.shape[1], rec.nbytes
-    coeff = np.zeros((n, N, N), dtype=np.int16)
-    q, dq, eob = np.zeros_like(coeff), np.zeros_like(coeff), np.zeros(n, dtype=np.uint16)
+    coeff, q, dq = (aligned_zeros((n, N, N), np.int16) for _ in range(3))
+    eob = np.zeros(n, dtype=np.uint16)
     rows = np.ascontiguousarray(rows)
     L.refdrv_txq(tx_size, 0, n, jobs.ctypes.data, C.byref(pl), rows.ctypes.data, coeff.ctypes.data, q.ctypes.data, dq.ctypes.data, eob.ctypes.data)
     return coeff, q, dq, eob, rec

@@ -1,0 +1,67 @@
+"""The C-ABI shared library: it loads without a GPU, exports every entry point include/svtb200.h declares, and its
+structs have the sizes the header (and the reference's own structs, via the seam check) fix."""
+import ctypes as C
+import importlib
+import os
+import re
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+api = H.api
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "svtb200.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(svtb200_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_library_exports_every_declared_symbol():
+    L = C.CDLL(os.path.join(ROOT, "svt-vp9_b200", "libsvtvp9_b200.so"))
+    names = declared_symbols()
+    assert len(names) >= 25
+    missing = [n for n in names if not hasattr(L, n)]
+    assert not missing, missing
+
+
+def test_struct_sizes_match_header():
+    assert api.ME_RESULT_DTYPE.itemsize == 40          # MeCuResults, EbMotionEstimationLcuResults.h:36-56
+    assert api.LF_MASK_DTYPE.itemsize == 160           # LOOP_FILTER_MASK, vp9_loopfilter.h
+    assert api.TX_JOB_DTYPE.itemsize == 16
+    assert C.sizeof(api.Plane) == 32
+
+
+def test_create_fails_loudly_without_a_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(RuntimeError):
+        api.Context(0)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,hme1", [(640, 384, True), (200, 136, True), (456, 248, False)])
+def test_device_decimation_and_padding_match_host_front_end(w, h, hme1):
+    frames = importlib.import_module("svt-vp9_b200.frames")
+    rng = np.random.default_rng(w)
+    luma = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    pl = frames.pa_planes(luma)
+    st = frames.plane_structs(pl)
+    poisoned = pl["full"].copy()
+    poisoned[:frames.FULL_PAD] = 0x55            # the padding must be regenerated on the device, not copied
+    poisoned[:, :frames.FULL_PAD] = 0xAA
+    st_p = frames.plane_structs({**pl, "full": poisoned})
+    ctx = api.Context(0)
+    ctx.picture_upload_luma(7, st_p[0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, hme1)
+    for which, key in ((0, "full"), (1, "quarter"), (2, "sixteenth")):
+        if which == 1 and not hme1:
+            continue
+        got, d = ctx.picture_plane(7, which)
+        want = pl[key]
+        assert (d.origin_x, d.origin_y, d.width, d.height) == (st[which].origin_x, st[which].origin_y, st[which].width, st[which].height)
+        assert (got[:, :want.shape[1]] == want).all(), key
+    ctx.close()
