@@ -4,31 +4,6 @@
 
 static void to_dev(const DevPlane &d, MePlaneDev *o) { o->buf = d.buf; o->stride = d.stride; o->ox = d.ox; o->oy = d.oy; o->w = d.w; o->h = d.h; }
 
-/* worst-case staging-window size over HME levels and the full-pel search */
-static int me_window_bytes(const SvtB200MeParams &P) {
-    auto win = [](int saw, int sah, int w, int h) { int pitch = ((saw + w - 1 + 4) + 3) & ~3; return pitch * (sah + 2 * (h - 1) + 1); };
-    int best = 0;
-    if (P.enable_hme_flag) {
-        if (P.enable_hme_level0) {
-            int tw = (P.hme_level0_total_search_area_width * P.hme_l0_multiplier_x) / 100, th = (P.hme_level0_total_search_area_height * P.hme_l0_multiplier_y) / 100;
-            for (int i = 0; i < 2; i++) {
-                tw = std::max(tw, (P.hme_level0_search_area_in_width[i] * P.hme_l0_multiplier_x) / 100);
-                th = std::max(th, (P.hme_level0_search_area_in_height[i] * P.hme_l0_multiplier_y) / 100);
-            }
-            best = std::max(best, win(tw, th, 16, 8));
-        }
-        if (P.enable_hme_level1)
-            for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++)
-                best = std::max(best, win(std::max(8, 2 * P.hme_level1_search_area_in_width[i]), P.hme_level1_search_area_in_height[j], 32, 16));
-        if (P.enable_hme_level2)
-            for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++)
-                best = std::max(best, win(std::max(8, 2 * P.hme_level2_search_area_in_width[i]), P.hme_level2_search_area_in_height[j], 64, 32));
-    }
-    const int saw = std::min(P.search_area_width, 127), sah = std::min(P.search_area_height, 127);
-    best = std::max(best, (((saw + 63 + 16 + 4) + 3) & ~3) * (sah + 63 + 1));
-    return best + 16;
-}
-
 static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, const uint64_t ref_id[2],
                      SvtB200MeCuResult *out_dev, uint32_t *rcme_dev) {
     if (!c || !P || !ref_id || !out_dev) return SVTB200_EINVAL;
@@ -53,9 +28,7 @@ static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, c
     A.n_sb  = A.sbs_w * ((P->luma_height + ME_SB - 1) / ME_SB);
     A.out = out_dev; A.rcme = rcme_dev;
     A.win_bytes = me_window_bytes(*P);
-    const int saw = std::min(P->search_area_width, 127), sah = std::min(P->search_area_height, 127);
-    const int is = ((saw + 63 + 2) + 7) & ~7;
-    A.interp_plane_bytes = is * (sah + 63 + 4);
+    A.interp_plane_bytes = me_interp_plane_bytes(*P);
     A.interp_in_smem = 1;
     MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 1);
     if (L.total > c->smem_optin) {

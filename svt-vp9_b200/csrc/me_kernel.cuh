@@ -7,12 +7,19 @@
  *
  * B200 mapping (not a translation of the AVX2 code):
  *   - the source SB lives in shared memory for the whole chain; every search window is staged
- *     once into shared memory with 128-bit-friendly pitch and consumed from there;
- *   - block matching works on packed 4-byte words: funnel-shift re-alignment + VABSDIFF4.U8.ACC
- *     (4 absolute differences and the accumulate in one instruction);
- *   - "first minimum in raster order" is a single 64-bit atomicMin on (sad << 32 | raster index);
+ *     once into shared memory, re-aligned to 32-bit words on the way in, and consumed from there
+ *     (block matching, the three half-pel filters and the integer samples of the quarter-pel
+ *     averages all read the same staged copy);
+ *   - everything that touches samples works on packed 4-byte words: funnel-shift re-alignment,
+ *     VABSDIFF4.U8.ACC (4 absolute differences + accumulate), byte averages, DP4A for the
+ *     horizontal 4-tap filter and 2x16-bit lane arithmetic for the vertical one;
+ *   - exhaustive searches evaluate 4 horizontally adjacent candidates per thread from one set of
+ *     window words; "first minimum in raster order" is a single 64-bit atomicMin on
+ *     (sad << 32 | raster index);
  *   - the 8x8 -> 16x16 -> 32x32 -> 64x64 SAD pyramid is built once per search position in shared
  *     memory, all 85 partitions reduce in parallel;
+ *   - sub-pel refinement of all enabled partition sizes runs as ONE pass over equally sized work
+ *     units (16 words each) for the half-pel ring and one for the quarter-pel ring;
  *   - the three half-pel planes of both reference lists stay in shared memory (global scratch only
  *     for search areas too large to fit) so that quarter-pel and bi-prediction never re-filter.
  *
@@ -27,7 +34,10 @@
 #define ME_THREADS 256
 #define ME_SB 64
 #define ME_MAX_SAD (64 * 64 * 255)
-#define ME_CHUNK 32 /* search positions whose SAD pyramid is resident at once */
+#define ME_CHUNK 32       /* search positions whose SAD pyramid is resident at once */
+#define ME_HALO_X 4       /* staged full-pel window: columns left of the search-area origin (word aligned) */
+#define ME_HALO_Y 2       /* rows above / below (the 4-tap filters reach 2 rows up, 1+1 down) */
+#define ME_HME_STRIPE 32  /* HME candidate rows staged at once (bounds the window for wide HME areas) */
 
 struct MePlaneDev {
     const uint8_t *buf;
@@ -81,9 +91,10 @@ struct MeSbState { /* scalar control state of one SB, written by thread 0 */
     /* current windowed search */
     int32_t  s_w, s_h, s_pitch;     /* source block (bytes per row, rows, pitch) */
     int32_t  w_x, w_y;              /* window origin relative to the picture (0,0) of its plane */
-    int32_t  w_saw, w_sah, w_pitch, w_rows;
+    int32_t  w_saw, w_sah, w_pitch;
+    int32_t  fp_pitch;              /* pitch of the staged full-pel window */
     unsigned long long best_key;
-    uint32_t red[9];
+    uint32_t red[8 * 5];
 };
 
 __device__ __forceinline__ const uint8_t *me_pix(const MePlaneDev &p, int x, int y) {
@@ -92,6 +103,10 @@ __device__ __forceinline__ const uint8_t *me_pix(const MePlaneDev &p, int x, int
 __device__ __forceinline__ int16_t me_mvx(uint32_t mv) { return (int16_t)(mv & 0xffff); }
 __device__ __forceinline__ int16_t me_mvy(uint32_t mv) { return (int16_t)(mv >> 16); }
 __device__ __forceinline__ uint32_t me_mkmv(int x, int y) { return ((uint32_t)(uint16_t)y << 16) | (uint16_t)x; }
+
+/* ---------------------------------------------------------------------------------------------
+ * packed-byte primitives
+ * ------------------------------------------------------------------------------------------- */
 __device__ __forceinline__ uint32_t me_absdiff_acc(uint32_t a, uint32_t b, uint32_t acc) {
 #if defined(__CUDA_ARCH__)
     uint32_t r;
@@ -101,17 +116,89 @@ __device__ __forceinline__ uint32_t me_absdiff_acc(uint32_t a, uint32_t b, uint3
     return __vsadu4(a, b) + acc;
 #endif
 }
+/* sum_i a.byte[i] (unsigned) * b.byte[i] (signed) + c */
+__device__ __forceinline__ int me_dp4a_us(uint32_t a, uint32_t b, int c) {
+#if defined(__CUDA_ARCH__)
+    int r;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 0xff) * (int)(int8_t)((b >> (8 * i)) & 0xff);
+    return c;
+#endif
+}
+/* sum_i a.byte[i] * b.byte[i] (both unsigned) + c */
+__device__ __forceinline__ uint32_t me_dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+#if defined(__CUDA_ARCH__)
+    uint32_t r;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+#else
+    for (int i = 0; i < 4; i++) c += ((a >> (8 * i)) & 0xff) * ((b >> (8 * i)) & 0xff);
+    return c;
+#endif
+}
+/* per-lane max / min of two unsigned 16-bit lanes */
+__device__ __forceinline__ uint32_t me_max_u16x2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __vimax3_u16x2(a, b, b);
+#else
+    const uint32_t al = a & 0xffff, bl = b & 0xffff, ah = a >> 16, bh = b >> 16;
+    return (al > bl ? al : bl) | ((ah > bh ? ah : bh) << 16);
+#endif
+}
+__device__ __forceinline__ uint32_t me_min_u16x2(uint32_t a, uint32_t b) {
+#if defined(__CUDA_ARCH__)
+    return __vimin3_u16x2(a, b, b);
+#else
+    const uint32_t al = a & 0xffff, bl = b & 0xffff, ah = a >> 16, bh = b >> 16;
+    return (al < bl ? al : bl) | ((ah < bh ? ah : bh) << 16);
+#endif
+}
+/* 4 bytes at any byte address (shared or global): the two enclosing aligned words, re-aligned.
+ * Reads up to 4 bytes past p + 3; every buffer this is used on carries that much slack. */
+__device__ __forceinline__ uint32_t me_ld4(const uint8_t *p) {
+    const uintptr_t a = (uintptr_t)p;
+    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+    return __funnelshift_r(w[0], w[1], (uint32_t)(a & 3) * 8);
+}
+/* a row of consecutive words starting at any byte address, one new aligned load per word */
+struct MeStream {
+    const uint32_t *w;
+    uint32_t        lo, sh;
+    __device__ __forceinline__ void open(const uint8_t *p) {
+        const uintptr_t a = (uintptr_t)p;
+        w = (const uint32_t *)(a & ~(uintptr_t)3); sh = (uint32_t)(a & 3) * 8; lo = *w++;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        const uint32_t hi = *w++, v = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        return v;
+    }
+};
 
-/* sum over the CTA; every thread gets the total */
-__device__ __forceinline__ uint32_t me_block_sum(uint32_t v, uint32_t *red) {
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+/* sum over the CTA of n (<= 5) values per thread; every thread gets the totals */
+template <int N>
+__device__ __forceinline__ void me_block_sum_n(uint32_t (&v)[N], int n, uint32_t *red) {
     const int warp = threadIdx.x >> 5;
     __syncthreads(); /* protect red[] from the previous use */
-    if ((threadIdx.x & 31) == 0) red[warp] = v;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        if (c < n) {
+            uint32_t x = v[c];
+            for (int o = 16; o > 0; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
+            if ((threadIdx.x & 31) == 0) red[c * 8 + warp] = x;
+        }
+    }
     __syncthreads();
-    uint32_t t = 0;
-    for (int i = 0; i < ME_THREADS / 32; i++) t += red[i];
-    return t;
+#pragma unroll
+    for (int c = 0; c < N; c++) {
+        if (c < n) {
+            uint32_t s = 0;
+            for (int i = 0; i < ME_THREADS / 32; i++) s += red[c * 8 + i];
+            v[c] = s;
+        }
+    }
 }
 
 /* window clipping exactly as the reference's "Correct the ... edge" statements (the left/top
@@ -136,29 +223,69 @@ __device__ __forceinline__ int16_t me_widen8(int16_t w) {
     return (int16_t)((w < 8) ? 8 : (w & 7) ? w + (w - ((w >> 3) << 3)) : w);
 }
 
-/* SAD of the source SB (every other row) against the reference at displacement (dx,dy):
- * sbw x sbh/2 samples, times two.  All threads must call; all get the result. */
-__device__ static uint32_t me_sb_sad_at(const uint8_t *src, const MeSbState *st, const MePlaneDev &rp, int dx, int dy,
-                                        uint32_t *red) {
-    const uint8_t *r = me_pix(rp, st->ox + dx, st->oy + dy);
-    const int n = (st->sbh >> 1) * st->sbw;
-    uint32_t acc = 0;
-    for (int i = threadIdx.x; i < n; i += ME_THREADS) {
-        const int y = i / st->sbw, x = i - y * st->sbw;
-        const int a = src[(2 * y) * ME_SB + x], b = __ldg(r + (ptrdiff_t)(2 * y) * rp.stride + x);
-        acc += (uint32_t)(a > b ? a - b : b - a);
+/* SADs of the source SB (every other row) against the reference at n (<= 5) displacements:
+ * sbw x sbh/2 samples, times two.  All threads must call; all get the results in out[]. */
+__device__ static void me_sb_sad_multi(const uint8_t *src, const MeSbState *st, const MePlaneDev &rp, int n, const int16_t *dx,
+                                       const int16_t *dy, uint32_t (&out)[5], uint32_t *red) {
+    const int sbw = st->sbw, rows = st->sbh >> 1;
+    uint32_t acc[5] = {0, 0, 0, 0, 0};
+    if (((sbw | rp.stride) & 3) == 0 && ((uintptr_t)rp.buf & 3) == 0 && (sbw & 7) == 0) {
+        /* one 8-sample segment per thread */
+        const int nseg = sbw >> 3, seg = threadIdx.x;
+        const int y = (nseg == 8) ? seg >> 3 : seg / nseg, x = (seg - y * nseg) * 8;
+        if (y < rows) {
+            const uint32_t *sp = (const uint32_t *)(src + (2 * y) * ME_SB + x);
+            const uint32_t s0 = sp[0], s1 = sp[1];
+#pragma unroll
+            for (int c = 0; c < 5; c++) {
+                if (c < n) {
+                    const uint8_t *r = me_pix(rp, st->ox + dx[c] + x, st->oy + dy[c] + 2 * y);
+                    const uintptr_t a = (uintptr_t)r;
+                    const uint32_t *w = (const uint32_t *)(a & ~(uintptr_t)3);
+                    const uint32_t sh = (uint32_t)(a & 3) * 8, w0 = __ldg(w), w1 = __ldg(w + 1), w2 = __ldg(w + 2);
+                    acc[c] = me_absdiff_acc(__funnelshift_r(w0, w1, sh), s0, acc[c]);
+                    acc[c] = me_absdiff_acc(__funnelshift_r(w1, w2, sh), s1, acc[c]);
+                }
+            }
+        }
+    } else {
+        const int cnt = rows * sbw;
+        for (int c = 0; c < n; c++) {
+            const uint8_t *r = me_pix(rp, st->ox + dx[c], st->oy + dy[c]);
+            for (int i = threadIdx.x; i < cnt; i += ME_THREADS) {
+                const int y = i / sbw, x = i - y * sbw;
+                const int a = src[(2 * y) * ME_SB + x], b = __ldg(r + (ptrdiff_t)(2 * y) * rp.stride + x);
+                acc[c] += (uint32_t)(a > b ? a - b : b - a);
+            }
+        }
     }
-    return me_block_sum(acc, red) << 1;
+    me_block_sum_n(acc, n, red);
+    for (int c = 0; c < 5; c++) out[c] = c < n ? acc[c] << 1 : 0;
 }
 
-/* Stage a rows x cols byte window of plane pl starting at picture coordinates (x0,y0) into
- * shared memory with the given pitch (pitch >= cols + 4, multiple of 4). */
+/* Stage a rows x cols byte window of plane pl starting at picture coordinates (x0,y0) into shared
+ * memory: byte x of row y of the staged copy is R(x0 + x, y0 + y), rows are word aligned (the
+ * re-alignment happens here, once).  pitch is a multiple of 4 and >= cols + 8. */
 __device__ static void me_stage_window(uint8_t *win, int pitch, const MePlaneDev &pl, int x0, int y0, int cols, int rows) {
     const uint8_t *g = me_pix(pl, x0, y0);
-    const int cw = cols + 4; /* one spare word for the funnel shift */
-    for (int i = threadIdx.x; i < rows * cw; i += ME_THREADS) {
-        const int y = i / cw, x = i - y * cw;
-        win[y * pitch + x] = __ldg(g + (ptrdiff_t)y * pl.stride + x);
+    if ((pl.stride & 3) == 0 && ((uintptr_t)pl.buf & 3) == 0) {
+        const uint32_t sh = (uint32_t)((uintptr_t)g & 3) * 8;
+        const uint8_t *ga = g - (sh >> 3);
+        const int nw = ((cols + 3) >> 2) + 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+        for (int y = warp; y < rows; y += ME_THREADS / 32) {
+            const uint32_t *gr = (const uint32_t *)(ga + (ptrdiff_t)y * pl.stride);
+            uint32_t *wr = (uint32_t *)(win + y * pitch);
+            for (int x = lane; x < nw; x += 32) {
+                const uint32_t lo = __ldg(gr + x), hi = sh ? __ldg(gr + x + 1) : 0u;
+                wr[x] = __funnelshift_r(lo, hi, sh);
+            }
+        }
+    } else {
+        const int cw = cols + 4;
+        for (int i = threadIdx.x; i < rows * cw; i += ME_THREADS) {
+            const int y = i / cw, x = i - y * cw;
+            win[y * pitch + x] = __ldg(g + (ptrdiff_t)y * pl.stride + x);
+        }
     }
 }
 
@@ -175,34 +302,79 @@ __device__ __forceinline__ uint32_t me_row_sad(const uint32_t *srow, const uint8
     return acc;
 }
 
-/* Exhaustive window search (eb_vp9_sad_loop_kernel semantics): source block s_w x s_h in sblk
- * (pitch s_pitch, rows already sub-sampled), candidate (xs,ys) uses window rows ys + 2r.
- * Result: st->best_key = (sad << 32 | ys * saw + xs) of the first minimum, or ~0 if none. */
-__device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win, MeSbState *st, uint32_t *posacc /* >= 256 */) {
-    const int saw = st->w_saw, sah = st->w_sah, npos = saw * sah, w = st->s_w, h = st->s_h;
+/* Exhaustive search of one stripe of a window (eb_vp9_sad_loop_kernel semantics): source block
+ * s_w x s_h in sblk (pitch s_pitch, rows already sub-sampled); the stripe holds candidate rows
+ * [y0, y0 + nrows) of the w_saw-wide area, candidate (xs,ys) uses staged rows (ys - y0) + 2r.
+ * Folds (sad << 32 | ys * saw + xs) of the first minimum into st->best_key. */
+template <int WWORDS>
+__device__ __forceinline__ void me_search4(const uint32_t *sblk, int sp32, const uint32_t *wrow0, int wp32, int h, uint32_t (&acc)[4]) {
+    for (int r = 0; r < h; r++) {
+        const uint32_t *wrow = wrow0 + (2 * r) * wp32, *srow = sblk + r * sp32;
+        uint32_t lo = wrow[0];
+#pragma unroll
+        for (int k = 0; k < WWORDS; k++) {
+            const uint32_t hi = wrow[k + 1], s = srow[k];
+            acc[0] = me_absdiff_acc(lo, s, acc[0]);
+            acc[1] = me_absdiff_acc(__funnelshift_r(lo, hi, 8), s, acc[1]);
+            acc[2] = me_absdiff_acc(__funnelshift_r(lo, hi, 16), s, acc[2]);
+            acc[3] = me_absdiff_acc(__funnelshift_r(lo, hi, 24), s, acc[3]);
+            lo = hi;
+        }
+    }
+}
+__device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win, MeSbState *st, uint32_t *posacc /* >= 256 */, int y0,
+                                        int nrows) {
+    const int saw = st->w_saw, npos = saw * nrows, w = st->s_w, h = st->s_h;
     const int wwords = w >> 2;
-    if (threadIdx.x == 0) st->best_key = ~0ull;
-    __syncthreads();
     if (npos <= 0) return;
-    if (npos >= ME_THREADS || (w & 3)) {
+    if (w & 3) {
         unsigned long long best = ~0ull;
         for (int pos = threadIdx.x; pos < npos; pos += ME_THREADS) {
             const int ys = pos / saw, xs = pos - ys * saw;
             uint32_t acc = 0;
-            if (w & 3) {
-                for (int r = 0; r < h; r++)
-                    for (int x = 0; x < w; x++) {
-                        const int a = sblk[r * st->s_pitch + x], b = win[(ys + 2 * r) * st->w_pitch + xs + x];
-                        acc += (uint32_t)(a > b ? a - b : b - a);
-                    }
-            } else {
-                for (int r = 0; r < h; r++)
-                    acc = me_row_sad((const uint32_t *)(sblk + r * st->s_pitch), win + (ys + 2 * r) * st->w_pitch, xs, wwords, acc);
-            }
+            for (int r = 0; r < h; r++)
+                for (int x = 0; x < w; x++) {
+                    const int a = sblk[r * st->s_pitch + x], b = win[(ys + 2 * r) * st->w_pitch + xs + x];
+                    acc += (uint32_t)(a > b ? a - b : b - a);
+                }
             if (acc < 0xffffffu) {
-                const unsigned long long key = ((unsigned long long)acc << 32) | (uint32_t)pos;
+                const unsigned long long key = ((unsigned long long)acc << 32) | (uint32_t)(pos + y0 * saw);
                 if (key < best) best = key;
             }
+        }
+        if (best != ~0ull) atomicMin(&st->best_key, best);
+    } else if (npos >= ME_THREADS) {
+        /* 4 horizontally adjacent candidates per thread share every window word */
+        const int ngx = (saw + 3) >> 2, ngroups = ngx * nrows, sp32 = st->s_pitch >> 2, wp32 = st->w_pitch >> 2;
+        unsigned long long best = ~0ull;
+        for (int g = threadIdx.x; g < ngroups; g += ME_THREADS) {
+            const int ys = g / ngx, gx = g - ys * ngx;
+            const uint32_t *wrow0 = (const uint32_t *)win + ys * wp32 + gx;
+            uint32_t acc[4] = {0, 0, 0, 0};
+            if (wwords == 4) me_search4<4>((const uint32_t *)sblk, sp32, wrow0, wp32, h, acc);
+            else if (wwords == 8) me_search4<8>((const uint32_t *)sblk, sp32, wrow0, wp32, h, acc);
+            else if (wwords == 16) me_search4<16>((const uint32_t *)sblk, sp32, wrow0, wp32, h, acc);
+            else {
+                for (int r = 0; r < h; r++) {
+                    const uint32_t *wrow = wrow0 + (2 * r) * wp32, *srow = (const uint32_t *)sblk + r * sp32;
+                    uint32_t lo = wrow[0];
+                    for (int k = 0; k < wwords; k++) {
+                        const uint32_t hi = wrow[k + 1], s = srow[k];
+                        acc[0] = me_absdiff_acc(lo, s, acc[0]);
+                        acc[1] = me_absdiff_acc(__funnelshift_r(lo, hi, 8), s, acc[1]);
+                        acc[2] = me_absdiff_acc(__funnelshift_r(lo, hi, 16), s, acc[2]);
+                        acc[3] = me_absdiff_acc(__funnelshift_r(lo, hi, 24), s, acc[3]);
+                        lo = hi;
+                    }
+                }
+            }
+            const uint32_t pos0 = (uint32_t)((y0 + ys) * saw + 4 * gx);
+#pragma unroll
+            for (int j = 0; j < 4; j++)
+                if (4 * gx + j < saw && acc[j] < 0xffffffu) {
+                    const unsigned long long key = ((unsigned long long)acc[j] << 32) | (pos0 + j);
+                    if (key < best) best = key;
+                }
         }
         if (best != ~0ull) atomicMin(&st->best_key, best);
     } else {
@@ -222,12 +394,11 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
         }
         __syncthreads();
         if (threadIdx.x < (unsigned)npos && posacc[threadIdx.x] < 0xffffffu)
-            atomicMin(&st->best_key, ((unsigned long long)posacc[threadIdx.x] << 32) | threadIdx.x);
+            atomicMin(&st->best_key, ((unsigned long long)posacc[threadIdx.x] << 32) | (uint32_t)(threadIdx.x + y0 * saw));
     }
-    __syncthreads();
 }
 
-/* one HME level: thread 0 prepared st->s_*, st->w_*; all threads stage and search.
+/* one HME level: thread 0 prepared st->s_*, st->w_*; all threads stage and search, stripe by stripe.
  * level 0/1 read the source block from the decimated planes of the current picture, level 2
  * from the shared-memory SB. */
 __device__ static void me_hme_search(const MeKernelArgs &A, int list, int level, MeSbState *st, const uint8_t *src,
@@ -248,29 +419,37 @@ __device__ static void me_hme_search(const MeKernelArgs &A, int list, int level,
             hsrc[y * st->s_pitch + x] = __ldg(g + (ptrdiff_t)(2 * y) * cp.stride + x);
         }
     }
+    if (threadIdx.x == 0) st->best_key = ~0ull;
     const MePlaneDev &rp = A.ref[list][level == 0 ? 2 : level == 1 ? 1 : 0];
-    me_stage_window(win, st->w_pitch, rp, st->w_x, st->w_y, st->w_saw + w - 1, st->w_rows);
-    __syncthreads();
-    me_window_search(hsrc, win, st, posacc);
+    const int extra = 2 * (h - 1), sah = st->w_sah;
+    int stripe = A.win_bytes / st->w_pitch - extra - 1; /* candidate rows the buffer can hold */
+    if (stripe < 1) stripe = 1;
+    for (int y0 = 0; y0 < sah; y0 += stripe) {
+        const int n = min(stripe, sah - y0);
+        me_stage_window(win, st->w_pitch, rp, st->w_x, st->w_y + y0, st->w_saw + w - 1, n + extra);
+        __syncthreads();
+        me_window_search(hsrc, win, st, posacc, y0, n);
+        __syncthreads();
+    }
 }
 
 /* prepare the window geometry for a search of saw x sah candidates (thread 0) */
 __device__ __forceinline__ void me_set_window(MeSbState *st, int w, int h, int wx, int wy, int saw, int sah) {
     st->s_w = w; st->s_h = h; st->s_pitch = (w + 3) & ~3;
     st->w_x = wx; st->w_y = wy; st->w_saw = saw; st->w_sah = sah;
-    st->w_pitch = ((saw + w - 1 + 4) + 3) & ~3;
-    st->w_rows  = sah + 2 * (h - 1);
+    st->w_pitch = (saw + w + 8 + 3) & ~3;
 }
 
 
 /* ---------------------------------------------------------------------------------------------
  * Full-pel search over the 85 partitions.
- * win holds the reference region starting at R(0,0) = top-left of the clipped search area
- * (cols saw+63(+16 for the tail quirk), rows sah+63).  Search positions are processed in chunks
- * of ME_CHUNK; per chunk the 64 sub-sampled 8x8 SADs of every position are written to shared
- * memory and summed up the pyramid; every partition keeps (2*sad << 32 | raster index) minima.
+ * rb points at R(0,0) = top-left of the clipped search area inside the staged window (pitch
+ * wpitch; the window also holds ME_HALO_X / ME_HALO_Y samples around it and the +16 columns of
+ * the tail quirk).  Search positions are processed in chunks of ME_CHUNK; per chunk the 64
+ * sub-sampled 8x8 SADs of every position are written to shared memory and summed up the
+ * pyramid; every partition keeps (2*sad << 32 | raster index) minima.
  * ------------------------------------------------------------------------------------------- */
-__device__ static void me_fullpel(const uint8_t *src, const uint8_t *win, int wpitch, MeSbState *st, int list,
+__device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpitch, MeSbState *st, int list,
                                   unsigned long long *pu_key /* [85] smem */, uint16_t *s8 /* [CHUNK][64] */,
                                   uint16_t *s16 /* [CHUNK][16] */, uint32_t *s32 /* [CHUNK][4] */) {
     const int saw = st->saw[list], sah = st->sah[list], npos = saw * sah;
@@ -288,17 +467,28 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *win, int wp
             const int b16 = (z16 & 1) | ((z16 & 4) >> 1) | ((z16 & 2) << 1) | (z16 & 8);
             const int bx = (b16 & 3) * 16 + (k & 1) * 8, by = (b16 >> 2) * 16 + (k >> 1) * 8;
             const uint32_t *sp = (const uint32_t *)(src + by * ME_SB + bx);
+            const uint32_t s0 = sp[0], s1 = sp[1], s2 = sp[32], s3 = sp[33], s4 = sp[64], s5 = sp[65], s6 = sp[96], s7 = sp[97];
+            int pos = c0 + lane, ys = pos / saw, xs = pos - ys * saw;
             for (int pp = lane; pp < cn; pp += 4) {
-                const int pos = c0 + pp, ys = pos / saw, xs = pos - ys * saw;
                 /* the reference's single-position routine matches 16x16 blocks 12 and 13 sixteen
                  * samples further right (EbMotionEstimation.c:855-856); reproduced */
                 const int skew = (xs >= tail_from && (z16 == 12 || z16 == 13)) ? 16 : 0;
-                const uint8_t *wr = win + (ys + by) * wpitch;
                 const int xo = xs + bx + skew;
+                const uint32_t *wp = (const uint32_t *)(rb + (ys + by) * wpitch + (xo & ~3));
+                const uint32_t sh = (uint32_t)(xo & 3) * 8;
+                const int p2 = wpitch >> 1; /* two rows, in words */
                 uint32_t acc = 0;
-#pragma unroll
-                for (int r = 0; r < 4; r++) acc = me_row_sad(sp + r * (2 * ME_SB / 4), wr + (2 * r) * wpitch, xo, 2, acc);
+                acc = me_absdiff_acc(__funnelshift_r(wp[0], wp[1], sh), s0, acc);
+                acc = me_absdiff_acc(__funnelshift_r(wp[1], wp[2], sh), s1, acc);
+                acc = me_absdiff_acc(__funnelshift_r(wp[p2], wp[p2 + 1], sh), s2, acc);
+                acc = me_absdiff_acc(__funnelshift_r(wp[p2 + 1], wp[p2 + 2], sh), s3, acc);
+                acc = me_absdiff_acc(__funnelshift_r(wp[2 * p2], wp[2 * p2 + 1], sh), s4, acc);
+                acc = me_absdiff_acc(__funnelshift_r(wp[2 * p2 + 1], wp[2 * p2 + 2], sh), s5, acc);
+                acc = me_absdiff_acc(__funnelshift_r(wp[3 * p2], wp[3 * p2 + 1], sh), s6, acc);
+                acc = me_absdiff_acc(__funnelshift_r(wp[3 * p2 + 1], wp[3 * p2 + 2], sh), s7, acc);
                 s8[pp * 64 + z8] = (uint16_t)acc;
+                xs += 4;
+                while (xs >= saw) { xs -= saw; ys++; }
             }
         }
         __syncthreads();
@@ -379,92 +569,122 @@ __device__ static void me_su_pel_enable(const uint32_t *bs, const uint32_t *bm, 
  *   pb[x + y*is] = H(R(x-2..x+1, y-2))       x < wasm, y < H+4
  *   ph[x + y*is] = V(R(x-1, y-2..y+1))       x < wasm, y < H+1
  *   pj[x + y*is] = V(pb[x + (y..y+3)*is])    x < wasm, y < H+1
- * taps {-2,18,18,-2}, +16 >> 5, clipped (two rounded 8-bit passes for j).
+ * taps {-2,18,18,-2}, +16 >> 5, clipped (two rounded 8-bit passes for j).  R is read from the
+ * staged full-pel window (rb = R(0,0), pitch rp); four output samples per step.
  * ------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ uint8_t me_tap4(int a, int b, int c, int d) {
-    int v = (-2 * a + 18 * b + 18 * c - 2 * d + 16) >> 5;
-    return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v);
+__device__ __forceinline__ uint32_t me_clip8(int v) { return (uint32_t)min(max(v, 0), 255); }
+/* horizontal: outputs x..x+3 from the words holding R(x-4..x-1), R(x..x+3), R(x+4..x+7) */
+__device__ __forceinline__ uint32_t me_hfilt4(uint32_t wm, uint32_t w0, uint32_t wp) {
+    const uint32_t K = 0xFE1212FEu; /* -2, 18, 18, -2 */
+    const uint32_t v0 = me_clip8(me_dp4a_us(__funnelshift_r(wm, w0, 16), K, 16) >> 5);
+    const uint32_t v1 = me_clip8(me_dp4a_us(__funnelshift_r(wm, w0, 24), K, 16) >> 5);
+    const uint32_t v2 = me_clip8(me_dp4a_us(w0, K, 16) >> 5);
+    const uint32_t v3 = me_clip8(me_dp4a_us(__funnelshift_r(w0, wp, 8), K, 16) >> 5);
+    return v0 | (v1 << 8) | (v2 << 16) | (v3 << 24);
 }
-__device__ static void me_interp(const MePlaneDev &rp, const MeSbState *st, int list, uint8_t *pb, uint8_t *ph, uint8_t *pj) {
+/* vertical: the same four columns on rows a,b,c,d; even and odd bytes as two 16-bit lanes each.
+ * lane value = 18*(b+c) - 2*(a+d) + 16 + 1024 stays in [20, 10220]: no borrow between lanes;
+ * (v + 1024) >> 5 == (v >> 5) + 32 also for negative v. */
+__device__ __forceinline__ uint32_t me_vfilt4(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    const uint32_t M = 0x00ff00ffu;
+    const uint32_t se = (b & M) + (c & M), so = ((b >> 8) & M) + ((c >> 8) & M);
+    const uint32_t te = (a & M) + (d & M), to = ((a >> 8) & M) + ((d >> 8) & M);
+    uint32_t ve = ((se * 18u + 0x04100410u - 2u * te) >> 5) & 0x07ff07ffu;
+    uint32_t vo = ((so * 18u + 0x04100410u - 2u * to) >> 5) & 0x07ff07ffu;
+    ve = me_min_u16x2(me_max_u16x2(ve, 0x00200020u), 0x011f011fu) - 0x00200020u;
+    vo = me_min_u16x2(me_max_u16x2(vo, 0x00200020u), 0x011f011fu) - 0x00200020u;
+    return ve | (vo << 8);
+}
+__device__ static void me_interp(const uint8_t *rb, int rp, const MeSbState *st, int list, uint8_t *pb, uint8_t *ph, uint8_t *pj) {
     const int W = st->saw[list] + ME_SB - 1, H = st->sah[list] + ME_SB - 1;
     const int wasm = (W + 2 + 7) & ~7, is = st->istride[list];
-    const uint8_t *R = me_pix(rp, st->ox + st->sa_ox[list], st->oy + st->sa_oy[list]);
-    const int rs = rp.stride;
-    for (int i = threadIdx.x; i < wasm * (H + 4); i += ME_THREADS) {
-        const int y = i / wasm, x = i - y * wasm;
-        const uint8_t *p = R + (ptrdiff_t)(y - 2) * rs + (x - 2);
-        pb[x + y * is] = me_tap4(__ldg(p), __ldg(p + 1), __ldg(p + 2), __ldg(p + 3));
+    const int nw = wasm >> 2, is32 = is >> 2;
+    /* b: one word of four outputs per step */
+    for (int it = threadIdx.x; it < nw * (H + 4); it += ME_THREADS) {
+        const int y = it / nw, i = it - y * nw;
+        const uint32_t *r = (const uint32_t *)(rb + (y - 2) * rp) + i;
+        ((uint32_t *)pb)[y * is32 + i] = me_hfilt4(r[-1], r[0], r[1]);
     }
-    for (int i = threadIdx.x; i < wasm * (H + 1); i += ME_THREADS) {
-        const int y = i / wasm, x = i - y * wasm;
-        const uint8_t *p = R + (ptrdiff_t)(y - 2) * rs + (x - 1);
-        ph[x + y * is] = me_tap4(__ldg(p), __ldg(p + rs), __ldg(p + 2 * rs), __ldg(p + 3 * rs));
-    }
-    __syncthreads();
-    for (int i = threadIdx.x; i < wasm * (H + 1); i += ME_THREADS) {
-        const int y = i / wasm, x = i - y * wasm;
-        const uint8_t *q = pb + x + y * is;
-        pj[x + y * is] = me_tap4(q[0], q[is], q[2 * is], q[3 * is]);
-    }
-    __syncthreads();
-}
-
-/* generic distortion between the source PU (shared memory, pitch 64) and up to two prediction
- * sources averaged on the fly; rows [r0, r0+nr) with the given row step; method as the reference */
-struct MePred { const uint8_t *p1, *p2; int s1, s2; }; /* p2 == nullptr: single source */
-
-__device__ __forceinline__ uint32_t me_pred_dist(const uint8_t *s, const MePred &pr, int w, int y, int sq) {
-    const uint8_t *a = pr.p1 + (ptrdiff_t)y * pr.s1;
-    const uint8_t *sr = s + y * ME_SB;
-    uint32_t acc = 0;
-    if (pr.p2) {
-        const uint8_t *b = pr.p2 + (ptrdiff_t)y * pr.s2;
-        for (int x = 0; x < w; x++) {
-            const int d = (int)sr[x] - ((a[x] + b[x] + 1) >> 1);
-            acc += sq ? (uint32_t)(d * d) : (uint32_t)(d < 0 ? -d : d);
-        }
-    } else {
-        for (int x = 0; x < w; x++) {
-            const int d = (int)sr[x] - (int)a[x];
-            acc += sq ? (uint32_t)(d * d) : (uint32_t)(d < 0 ? -d : d);
-        }
-    }
-    return acc;
-}
-
-/* Evaluate ntask (PU, candidate) tasks in parallel: task i covers PU geometry geo[i] and
- * prediction preds[i]; result dist[i] (metric per 'method'; for SSD also sad[i] = full SAD). */
-struct MeTask { MePred pr; int16_t px, py, w, h; int32_t valid; };
-
-__device__ static void me_run_tasks(const uint8_t *src, const MeTask *tasks, int ntask, int method, uint32_t *dist,
-                                    uint32_t *sad /* may be null unless method==SSD */) {
-    for (int i = threadIdx.x; i < ntask; i += ME_THREADS) { dist[i] = 0; if (sad) sad[i] = 0; }
-    __syncthreads();
-    /* rows of all tasks are dealt round-robin to the threads */
-    int T = 1;
-    while (T * 2 * ntask <= ME_THREADS && T < 32) T *= 2;
-    for (int base = 0; base < ntask * T; base += ME_THREADS) {
-        const int id = base + threadIdx.x;
-        if (id < ntask * T) {
-            const int ti = id / T, part = id - ti * T;
-            const MeTask &tk = tasks[ti];
-            if (tk.valid) {
-                const uint8_t *s = src + tk.py * ME_SB + tk.px;
-                uint32_t d = 0, a = 0;
-                if (method == 0) { /* SUB_SAD: even rows, doubled */
-                    for (int y = 2 * part; y < tk.h; y += 2 * T) d += me_pred_dist(s, tk.pr, tk.w, y, 0);
-                    d <<= 1;
-                } else if (method == 1) {
-                    for (int y = part; y < tk.h; y += T) d += me_pred_dist(s, tk.pr, tk.w, y, 0);
-                } else {
-                    for (int y = part; y < tk.h; y += T) { d += me_pred_dist(s, tk.pr, tk.w, y, 1); a += me_pred_dist(s, tk.pr, tk.w, y, 0); }
-                }
-                atomicAdd(&dist[ti], d);
-                if (sad && method == 2) atomicAdd(&sad[ti], a);
+    /* h: a thread walks down a word column with a rolling window of four rows */
+    const int nseg = nw >= ME_THREADS ? 1 : ME_THREADS / nw, per = (H + 1 + nseg - 1) / nseg;
+    for (int it = threadIdx.x; it < nw * nseg; it += ME_THREADS) {
+        const int seg = it / nw, i = it - seg * nw;
+        const int ya = seg * per, yb = min(H + 1, ya + per);
+        if (ya < yb) {
+            const uint8_t *r = rb + (ya - 2) * rp + 4 * i - 1;
+            uint32_t a = me_ld4(r), b = me_ld4(r + rp), c = me_ld4(r + 2 * rp);
+            r += 3 * rp;
+            for (int y = ya; y < yb; y++, r += rp) {
+                const uint32_t d = me_ld4(r);
+                ((uint32_t *)ph)[y * is32 + i] = me_vfilt4(a, b, c, d);
+                a = b; b = c; c = d;
             }
         }
     }
     __syncthreads();
+    for (int it = threadIdx.x; it < nw * nseg; it += ME_THREADS) {
+        const int seg = it / nw, i = it - seg * nw;
+        const int ya = seg * per, yb = min(H + 1, ya + per);
+        if (ya < yb) {
+            const uint32_t *q = (const uint32_t *)pb + ya * is32 + i;
+            uint32_t a = q[0], b = q[is32], c = q[2 * is32];
+            q += 3 * is32;
+            for (int y = ya; y < yb; y++, q += is32) {
+                const uint32_t d = *q;
+                ((uint32_t *)pj)[y * is32 + i] = me_vfilt4(a, b, c, d);
+                a = b; b = c; c = d;
+            }
+        }
+    }
+    __syncthreads();
+}
+
+/* ---------------------------------------------------------------------------------------------
+ * Sub-pel refinement.  A prediction is one plane or the rounded average of two (MePred); the
+ * distortion of a PU against it is computed by T threads, each taking every T-th (sub-sampled)
+ * row, then reduced with shuffles inside the aligned lane group.
+ * ------------------------------------------------------------------------------------------- */
+struct MePred { const uint8_t *p1, *p2; int s1, s2; }; /* p2 == nullptr: single source */
+
+/* SAD (sq == 0) or SSD (sq == 1) of one row of wwords words; srow is word aligned */
+__device__ __forceinline__ uint32_t me_pred_row(const uint32_t *srow, const MePred &pr, int y, int wwords, int sq) {
+    MeStream a, b;
+    a.open(pr.p1 + (ptrdiff_t)y * pr.s1);
+    uint32_t acc = 0;
+    if (pr.p2) {
+        b.open(pr.p2 + (ptrdiff_t)y * pr.s2);
+        for (int k = 0; k < wwords; k++) {
+            const uint32_t v = __vavgu4(a.next(), b.next());
+            if (sq) { const uint32_t d = __vabsdiffu4(v, srow[k]); acc = me_dp4a_uu(d, d, acc); }
+            else acc = me_absdiff_acc(v, srow[k], acc);
+        }
+    } else {
+        for (int k = 0; k < wwords; k++) {
+            const uint32_t v = a.next();
+            if (sq) { const uint32_t d = __vabsdiffu4(v, srow[k]); acc = me_dp4a_uu(d, d, acc); }
+            else acc = me_absdiff_acc(v, srow[k], acc);
+        }
+    }
+    return acc;
+}
+/* distortion share of thread 'part' of T for the w x w PU at s (pitch ME_SB); method as the reference:
+ * 0 SUB_SAD (even rows, doubled), 1 full SAD, 2 SSD (+ the full SAD in *sad) */
+__device__ __forceinline__ uint32_t me_pred_part(const uint8_t *s, const MePred &pr, int w, int part, int T, int method, uint32_t *sad) {
+    const int wwords = w >> 2;
+    uint32_t d = 0, a = 0;
+    if (method == 0) {
+        for (int y = 2 * part; y < w; y += 2 * T) d += me_pred_row((const uint32_t *)(s + y * ME_SB), pr, y, wwords, 0);
+        d <<= 1;
+    } else if (method == 1) {
+        for (int y = part; y < w; y += T) d += me_pred_row((const uint32_t *)(s + y * ME_SB), pr, y, wwords, 0);
+    } else {
+        for (int y = part; y < w; y += T) {
+            d += me_pred_row((const uint32_t *)(s + y * ME_SB), pr, y, wwords, 1);
+            a += me_pred_row((const uint32_t *)(s + y * ME_SB), pr, y, wwords, 0);
+        }
+    }
+    *sad = a;
+    return d;
 }
 
 /* quarter-pel source table: kind 0 = integer plane, 1 = b, 2 = h, 3 = j; offsets in samples.
@@ -481,19 +701,23 @@ __device__ static const MeQSrc me_qtab[4][8][2] = {
      {{2, -1, 0}, {1, 0, -1}}, {{1, 0, -1}, {2, 0, 0}}, {{1, 0, 0}, {2, 0, 0}}, {{2, -1, 0}, {1, 0, 0}}},
 };
 
-struct MeInterp { uint8_t *pb, *ph, *pj; }; /* plane bases as written by me_interp */
+/* sample sources of one reference list: the staged integer window and the three half-pel planes */
+struct MeInterp {
+    uint8_t       *pb, *ph, *pj; /* plane bases as written by me_interp */
+    const uint8_t *rb;           /* R(0,0) of the list's search area: staged window, or the plane itself when the
+                                    other list's window has replaced it */
+    int            rp;           /* pitch of rb */
+};
 
 /* pointer conventions of the reference's half_pel_search_sb arguments */
 __device__ __forceinline__ const uint8_t *me_PB(const MeInterp &ip, int is) { return ip.pb + 2 * is; }
 __device__ __forceinline__ const uint8_t *me_PH(const MeInterp &ip) { return ip.ph + 1; }
 __device__ __forceinline__ const uint8_t *me_PJ(const MeInterp &ip) { return ip.pj; }
 
-__device__ __forceinline__ const uint8_t *me_qsrc_ptr(const MePlaneDev &rp, const MeSbState *st, int list, const MeInterp &ip,
-                                                      MeQSrc q, int x, int y, int *stride) {
-    const int is = st->istride[list];
+__device__ __forceinline__ const uint8_t *me_qsrc_ptr(int is, const MeInterp &ip, MeQSrc q, int x, int y, int *stride) {
     x += q.ox; y += q.oy;
     switch (q.kind) {
-    case 0: *stride = rp.stride; return me_pix(rp, st->ox + st->sa_ox[list] + x, st->oy + st->sa_oy[list] + y);
+    case 0: *stride = ip.rp; return ip.rb + x + y * ip.rp;
     case 1: *stride = is; return me_PB(ip, is) + x + y * is;
     case 2: *stride = is; return me_PH(ip) + x + y * is;
     default: *stride = is; return me_PJ(ip) + x + y * is;
@@ -510,49 +734,63 @@ __device__ __forceinline__ void me_pu_geom(int idx, int *px, int *py, int *w) {
     } else { const int b = me_itab8[idx - 21]; *px = (b & 7) * 8; *py = (b >> 3) * 8; *w = 8; }
 }
 
-/* Half-pel then quarter-pel refinement of the PUs idx0..idx1-1 (one size class), all at once. */
-__device__ static void me_subpel_class(const MeKernelArgs &A, const uint8_t *src, MeSbState *st, int list, const MeInterp &ip,
-                                       int idx0, int idx1, int do_quarter, int quarter_w_override, uint32_t *bsad, uint32_t *bmv,
-                                       uint32_t *bssd, uint8_t *dir, MeTask *tasks, uint32_t *dist, uint32_t *sad) {
-    const MePlaneDev &rp = A.ref[list][0];
+/* work units of the four size classes: class c has npu = 4^c PUs from index idx0, T = 32 >> ... threads per
+ * (PU, candidate) task so that every unit is 16 words (8 for the 8x8 class) */
+__device__ __forceinline__ int me_cls_idx0(int c) { return c == 0 ? 0 : c == 1 ? 1 : c == 2 ? 5 : 21; }
+__device__ __forceinline__ int me_cls_npu(int c) { return 1 << (2 * c); }
+__device__ __forceinline__ int me_cls_tlog(int c) { return c == 0 ? 5 : c == 1 ? 3 : c == 2 ? 1 : 0; }
+
+/* sum over the aligned group of 2^tlog lanes (all 32 lanes call) */
+__device__ __forceinline__ uint32_t me_group_sum(uint32_t v, int tlog) {
+    for (int o = 0; o < tlog; o++) v += __shfl_xor_sync(0xffffffffu, v, 1 << o); /* tlog is warp-uniform */
+    return v;
+}
+
+/* Half-pel then quarter-pel refinement of every enabled size class (cmask bit c), all at once.
+ * dist/sadv: [85 * 9] indexed idx * 9 + candidate. */
+__device__ static void me_subpel(const MeKernelArgs &A, const uint8_t *src, MeSbState *st, int list, const MeInterp &ip, int cmask,
+                                 int qmask /* classes that also run quarter-pel */, uint32_t *bsad, uint32_t *bmv, uint32_t *bssd,
+                                 uint8_t *dir, uint32_t *dist, uint32_t *sadv) {
     const int method = A.P.fractional_search_method, is = st->istride[list];
-    const int npu = idx1 - idx0;
-    /* ---- half-pel: 8 candidates per PU (+ the full-pel SSD when the metric is SSD) ---- */
-    for (int i = threadIdx.x; i < npu * 9; i += ME_THREADS) {
-        const int pu = i / 9, k = i - pu * 9, idx = idx0 + pu;
-        int px, py, w;
-        me_pu_geom(idx, &px, &py, &w);
-        const int16_t x_mv = me_mvx(bmv[idx]), y_mv = me_mvy(bmv[idx]);
-        const int xs = (x_mv >> 2) - st->sa_ox[list], ys = (y_mv >> 2) - st->sa_oy[list];
-        MeTask tk;
-        tk.px = (int16_t)px; tk.py = (int16_t)py; tk.w = (int16_t)w; tk.h = (int16_t)w; tk.valid = 1;
-        tk.pr.p2 = 0; tk.pr.s2 = 0;
-        const int base = xs + px + (ys + py) * is;
-        if (k == 8) { /* integer position (only needed for SSD) */
-            tk.pr.p1 = me_pix(rp, st->ox + st->sa_ox[list] + xs + px, st->oy + st->sa_oy[list] + ys + py);
-            tk.pr.s1 = rp.stride; tk.valid = (method == 2);
-        } else {
-            const uint8_t *pb = me_PB(ip, is), *ph = me_PH(ip), *pj = me_PJ(ip);
-            const uint8_t *c;
-            switch (k) { /* L, R, T, B, TL, TR, BR, BL */
-            case 0: c = pb + base; break;
-            case 1: c = pb + base + 1; break;
-            case 2: c = ph + base; break;
-            case 3: c = ph + base + is; break;
-            case 4: c = pj + base; break;
-            case 5: c = pj + base + 1; break;
-            case 6: c = pj + base + 1 + is; break;
-            default: c = pj + base + is; break;
+    const int sa_ox = st->sa_ox[list], sa_oy = st->sa_oy[list];
+    const int ncand = (method == 2) ? 9 : 8;
+    /* ---- half-pel: 8 candidates per PU (+ the full-pel position when the metric is SSD) ---- */
+    for (int c = 0; c < 4; c++) {
+        if (!(cmask & (1 << c))) continue;
+        const int tlog = me_cls_tlog(c), T = 1 << tlog, idx0 = me_cls_idx0(c), nunits = me_cls_npu(c) * ncand * T;
+        for (int u = threadIdx.x; u < nunits; u += ME_THREADS) {
+            const int task = u >> tlog, part = u & (T - 1);
+            const int pu = (ncand == 8) ? task >> 3 : task / 9, k = task - pu * ncand, idx = idx0 + pu;
+            int px, py, w;
+            me_pu_geom(idx, &px, &py, &w);
+            const uint32_t mv = bmv[idx];
+            const int xs = (me_mvx(mv) >> 2) - sa_ox, ys = (me_mvy(mv) >> 2) - sa_oy;
+            const int base = xs + px + (ys + py) * is;
+            MePred pr;
+            pr.p2 = 0; pr.s2 = 0; pr.s1 = is;
+            switch (k) { /* L, R, T, B, TL, TR, BR, BL, integer */
+            case 0: pr.p1 = me_PB(ip, is) + base; break;
+            case 1: pr.p1 = me_PB(ip, is) + base + 1; break;
+            case 2: pr.p1 = me_PH(ip) + base; break;
+            case 3: pr.p1 = me_PH(ip) + base + is; break;
+            case 4: pr.p1 = me_PJ(ip) + base; break;
+            case 5: pr.p1 = me_PJ(ip) + base + 1; break;
+            case 6: pr.p1 = me_PJ(ip) + base + 1 + is; break;
+            case 7: pr.p1 = me_PJ(ip) + base + is; break;
+            default: pr.p1 = ip.rb + xs + px + (ys + py) * ip.rp; pr.s1 = ip.rp; break;
             }
-            tk.pr.p1 = c; tk.pr.s1 = is;
+            uint32_t a = 0;
+            uint32_t d = me_pred_part(src + py * ME_SB + px, pr, w, part, T, method, &a);
+            d = me_group_sum(d, tlog);
+            if (method == 2) a = me_group_sum(a, tlog);
+            if (part == 0) { dist[idx * 9 + k] = d; if (method == 2) sadv[idx * 9 + k] = a; }
         }
-        tasks[i] = tk;
     }
     __syncthreads();
-    me_run_tasks(src, tasks, npu * 9, method, dist, sad);
-    for (int pu = threadIdx.x; pu < npu; pu += ME_THREADS) {
-        const int idx = idx0 + pu;
-        const uint32_t *d = dist + pu * 9;
+    for (int idx = threadIdx.x; idx < 85; idx += ME_THREADS) {
+        const int c = idx == 0 ? 0 : idx < 5 ? 1 : idx < 21 ? 2 : 3;
+        if (!(cmask & (1 << c))) continue;
+        const uint32_t *d = dist + idx * 9;
         const int16_t x_mv = me_mvx(bmv[idx]), y_mv = me_mvy(bmv[idx]);
         const int dx[8] = {-2, 2, 0, 0, -2, 2, 2, -2}, dy[8] = {0, 0, -2, 2, -2, -2, 2, 2};
         uint32_t best = (method == 2) ? d[8] : bsad[idx];
@@ -560,7 +798,7 @@ __device__ static void me_subpel_class(const MeKernelArgs &A, const uint8_t *src
         for (int k = 0; k < 8; k++) if (d[k] < best) { best = d[k]; win = k; }
         if (method == 2) bssd[idx] = best;
         if (win >= 0) {
-            bsad[idx] = (method == 2) ? sad[pu * 9 + win] : best;
+            bsad[idx] = (method == 2) ? sadv[idx * 9 + win] : best;
             bmv[idx]  = me_mkmv(x_mv + dx[win], y_mv + dy[win]);
         }
         /* direction of the smallest half-pel distortion, tie order L,R,T,B,TL,TR,BL,BR;
@@ -572,40 +810,55 @@ __device__ static void me_subpel_class(const MeKernelArgs &A, const uint8_t *src
         for (int t = 0; t < 8; t++) if (d[order[t]] == m) { dir[idx] = (uint8_t)code[order[t]]; break; }
     }
     __syncthreads();
-    if (!do_quarter) return;
+    cmask &= qmask;
+    if (!cmask) return;
     /* ---- quarter-pel: the three positions next to the winning half-pel direction ---- */
-    for (int i = threadIdx.x; i < npu * 8; i += ME_THREADS) {
-        const int pu = i >> 3, k = i & 7, idx = idx0 + pu;
-        int px, py, w;
-        me_pu_geom(idx, &px, &py, &w);
-        if (quarter_w_override) w = quarter_w_override;
-        const int16_t x_mv = me_mvx(bmv[idx]), y_mv = me_mvy(bmv[idx]);
-        const int xs = ((x_mv + 2) >> 2) - st->sa_ox[list], ys = ((y_mv + 2) >> 2) - st->sa_oy[list];
-        const int phase = (y_mv & 2) + ((x_mv & 2) >> 1);
-        const int d = phase ? (dir[idx] + 4) & 7 : dir[idx];
-        const int ring[8] = {7, 3, 1, 5, 0, 2, 4, 6};
-        const int diff = (ring[k] - d) & 7;
-        MeTask tk;
-        tk.px = (int16_t)px; tk.py = (int16_t)py; tk.w = (int16_t)w; tk.h = (int16_t)w;
-        tk.valid = (diff == 0 || diff == 1 || diff == 7);
-        int s1 = 0, s2 = 0;
-        tk.pr.p1 = me_qsrc_ptr(rp, st, list, ip, me_qtab[phase][k][0], xs + px, ys + py, &s1);
-        tk.pr.p2 = me_qsrc_ptr(rp, st, list, ip, me_qtab[phase][k][1], xs + px, ys + py, &s2);
-        tk.pr.s1 = s1; tk.pr.s2 = s2;
-        tasks[i] = tk;
+    for (int c = 0; c < 4; c++) {
+        if (!(cmask & (1 << c))) continue;
+        /* the 64x64 PU is refined on its top-left 32x32 only (the reference passes 32 as the size) */
+        const int tlog = (c == 0) ? 3 : me_cls_tlog(c), T = 1 << tlog, idx0 = me_cls_idx0(c);
+        const int nunits = me_cls_npu(c) * 3 * T, nround = (nunits + 31) & ~31;
+        for (int u = threadIdx.x; u < nround; u += ME_THREADS) {
+            const int active = u < nunits;
+            const int task = active ? u >> tlog : 0, part = u & (T - 1);
+            const int pu = task / 3, j = task - pu * 3, idx = idx0 + pu;
+            int px, py, w;
+            me_pu_geom(idx, &px, &py, &w);
+            if (c == 0) w = 32;
+            const uint32_t mv = bmv[idx];
+            const int16_t x_mv = me_mvx(mv), y_mv = me_mvy(mv);
+            const int xs = ((x_mv + 2) >> 2) - sa_ox, ys = ((y_mv + 2) >> 2) - sa_oy;
+            const int phase = (y_mv & 2) + ((x_mv & 2) >> 1);
+            const int d0 = phase ? (dir[idx] + 4) & 7 : dir[idx];
+            const int inv[8] = {4, 2, 5, 1, 6, 3, 7, 0}; /* ring code -> candidate L,R,T,B,TL,TR,BR,BL */
+            const int k = inv[(d0 + j - 1) & 7];
+            MePred pr;
+            pr.p1 = me_qsrc_ptr(is, ip, me_qtab[phase][k][0], xs + px, ys + py, &pr.s1);
+            pr.p2 = me_qsrc_ptr(is, ip, me_qtab[phase][k][1], xs + px, ys + py, &pr.s2);
+            uint32_t a = 0, d = 0;
+            if (active) d = me_pred_part(src + py * ME_SB + px, pr, w, part, T, method, &a);
+            d = me_group_sum(d, tlog);
+            if (method == 2) a = me_group_sum(a, tlog);
+            if (active && part == 0) { dist[idx * 9 + k] = d; if (method == 2) sadv[idx * 9 + k] = a; }
+        }
     }
     __syncthreads();
-    me_run_tasks(src, tasks, npu * 8, method, dist, sad);
-    for (int pu = threadIdx.x; pu < npu; pu += ME_THREADS) {
-        const int idx = idx0 + pu;
+    for (int idx = threadIdx.x; idx < 85; idx += ME_THREADS) {
+        const int c = idx == 0 ? 0 : idx < 5 ? 1 : idx < 21 ? 2 : 3;
+        if (!(cmask & (1 << c))) continue;
         const int16_t x_mv = me_mvx(bmv[idx]), y_mv = me_mvy(bmv[idx]);
         const int dx[8] = {-1, 1, 0, 0, -1, 1, 1, -1}, dy[8] = {0, 0, -1, 1, -1, -1, 1, 1};
+        const int ring[8] = {7, 3, 1, 5, 0, 2, 4, 6};
+        const int phase = (y_mv & 2) + ((x_mv & 2) >> 1);
+        const int d0 = phase ? (dir[idx] + 4) & 7 : dir[idx];
         uint32_t best = (method == 2) ? bssd[idx] : bsad[idx];
         int win = -1;
-        for (int k = 0; k < 8; k++)
-            if (tasks[pu * 8 + k].valid && dist[pu * 8 + k] < best) { best = dist[pu * 8 + k]; win = k; }
+        for (int k = 0; k < 8; k++) {
+            const int diff = (ring[k] - d0) & 7;
+            if ((diff == 0 || diff == 1 || diff == 7) && dist[idx * 9 + k] < best) { best = dist[idx * 9 + k]; win = k; }
+        }
         if (win >= 0) {
-            if (method == 2) { bssd[idx] = best; bsad[idx] = sad[pu * 8 + win]; }
+            if (method == 2) { bssd[idx] = best; bsad[idx] = sadv[idx * 9 + win]; }
             else bsad[idx] = best;
             bmv[idx] = me_mkmv(x_mv + dx[win], y_mv + dy[win]);
         }
@@ -613,16 +866,14 @@ __device__ static void me_subpel_class(const MeKernelArgs &A, const uint8_t *src
     __syncthreads();
 }
 
-/* prediction of list 'list' at quarter-pel mv for the PU at (px,py): at most two planes to average
+/* prediction of one list at quarter-pel mv for the PU at (px,py): at most two planes to average
  * (select_buffer / quarter_pel_compensation) */
-__device__ static void me_bipred_pred(const MePlaneDev &rp, const MeSbState *st, int list, const MeInterp &ip, uint32_t mv,
-                                      int px, int py, MePred *out) {
-    const int is = st->istride[list];
+__device__ static void me_bipred_pred(int sa_ox, int sa_oy, int is, const MeInterp &ip, uint32_t mv, int px, int py, MePred *out) {
     const int16_t x = me_mvx(mv), y = me_mvy(mv);
-    const int xs = (x >> 2) - st->sa_ox[list], ys = (y >> 2) - st->sa_oy[list];
+    const int xs = (x >> 2) - sa_ox, ys = (y >> 2) - sa_oy;
     const int frac = (x & 3) + ((y & 3) << 2);
-    const uint8_t *Ap = me_pix(rp, st->ox + st->sa_ox[list] + xs + px, st->oy + st->sa_oy[list] + ys + py);
-    const int as = rp.stride;
+    const int as = ip.rp;
+    const uint8_t *Ap = ip.rb + (xs + px) + (ys + py) * as;
     /* b RIGHT of the integer sample, h BELOW it, j down-right */
     const uint8_t *b = ip.pb + (xs + 1 + px) + (ys + 2 + py) * is;
     const uint8_t *h = ip.ph + (xs + 1 + px) + (ys + 1 + py) * is;
@@ -648,21 +899,20 @@ __device__ static void me_bipred_pred(const MePlaneDev &rp, const MeSbState *st,
     }
     *out = p;
 }
-
-__device__ __forceinline__ uint32_t me_pred_px(const MePred &p, int x, int y) {
-    const uint32_t a = p.p1[(ptrdiff_t)y * p.s1 + x];
+/* one word of a prediction row */
+__device__ __forceinline__ uint32_t me_pred_word(const MePred &p, int y, int k) {
+    const uint32_t a = me_ld4(p.p1 + (ptrdiff_t)y * p.s1 + 4 * k);
     if (!p.p2) return a;
-    return (a + p.p2[(ptrdiff_t)y * p.s2 + x] + 1) >> 1;
+    return __vavgu4(a, me_ld4(p.p2 + (ptrdiff_t)y * p.s2 + 4 * k));
 }
 
 
 /* ---------------------------------------------------------------------------------------------
- * shared-memory layout of one CTA
+ * shared-memory layout of one CTA and the launch plan (shared by the host code and the emulation)
  * ------------------------------------------------------------------------------------------- */
 struct MeSmemLayout {
-    int src, hsrc, win, interp, s8, s16, s32, pu_key, bsad, bmv, bssd, bip, dir, posacc, tasks, dist, sad, preds, state, total;
+    int src, hsrc, win, interp, s8, s16, s32, pu_key, bsad, bmv, bssd, bip, dir, posacc, dist, sad, preds, state, total;
 };
-#define ME_MAX_TASKS 576
 __host__ __device__ static inline int me_align16(int v) { return (v + 15) & ~15; }
 __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int interp_plane_bytes, int interp_in_smem) {
     MeSmemLayout L;
@@ -681,13 +931,47 @@ __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int
     L.bip = o; o += me_align16(85 * 4);
     L.dir = o; o += me_align16(85);
     L.posacc = o; o += 256 * 4;
-    L.tasks = o; o += me_align16(ME_MAX_TASKS * (int)sizeof(MeTask));
-    L.dist = o; o += ME_MAX_TASKS * 4;
-    L.sad = o; o += ME_MAX_TASKS * 4;
-    L.preds = o; o += me_align16(85 * 2 * (int)sizeof(MePred));
+    L.dist = o; o += me_align16(85 * 9 * 4);
+    L.sad = o; o += me_align16(85 * 9 * 4);
+    L.preds = o; o += me_align16(85 * 2 * 24);
     L.state = o; o += me_align16((int)sizeof(MeSbState));
     L.total = o;
     return L;
+}
+/* pitch / rows of the staged full-pel window of a saw x sah search area */
+__host__ __device__ static inline int me_fp_pitch(int saw) { return (saw + ME_SB - 1 + 16 + ME_HALO_X + 8 + 3) & ~3; }
+__host__ __device__ static inline int me_fp_rows(int sah) { return sah + ME_SB - 1 + 2 * ME_HALO_Y; }
+/* capacity of the window buffer: the full-pel window, and the largest HME stripe */
+static inline int me_window_bytes(const SvtB200MeParams &P) {
+    auto hme = [](int saw, int sah, int w, int h) {
+        const int pitch = (saw + w + 8 + 3) & ~3, rows = (sah < ME_HME_STRIPE ? sah : ME_HME_STRIPE) + 2 * (h - 1) + 2;
+        return pitch * rows;
+    };
+    auto mx = [](int a, int b) { return a > b ? a : b; };
+    int best = 0;
+    if (P.enable_hme_flag) {
+        if (P.enable_hme_level0) {
+            int tw = (P.hme_level0_total_search_area_width * P.hme_l0_multiplier_x) / 100, th = (P.hme_level0_total_search_area_height * P.hme_l0_multiplier_y) / 100;
+            for (int i = 0; i < 2; i++) {
+                tw = mx(tw, (P.hme_level0_search_area_in_width[i] * P.hme_l0_multiplier_x) / 100);
+                th = mx(th, (P.hme_level0_search_area_in_height[i] * P.hme_l0_multiplier_y) / 100);
+            }
+            best = mx(best, hme(tw, th, 16, 8));
+        }
+        if (P.enable_hme_level1)
+            for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++)
+                best = mx(best, hme(mx(8, 2 * P.hme_level1_search_area_in_width[i]), P.hme_level1_search_area_in_height[j], 32, 16));
+        if (P.enable_hme_level2)
+            for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++)
+                best = mx(best, hme(mx(8, 2 * P.hme_level2_search_area_in_width[i]), P.hme_level2_search_area_in_height[j], 64, 32));
+    }
+    const int saw = P.search_area_width < 127 ? P.search_area_width : 127, sah = P.search_area_height < 127 ? P.search_area_height : 127;
+    best = mx(best, me_fp_pitch(saw) * (me_fp_rows(sah) + 1));
+    return best + 16;
+}
+static inline int me_interp_plane_bytes(const SvtB200MeParams &P) {
+    const int saw = P.search_area_width < 127 ? P.search_area_width : 127, sah = P.search_area_height < 127 ? P.search_area_height : 127;
+    return (((saw + ME_SB - 1 + 2) + 7) & ~7) * (sah + ME_SB - 1 + 4);
 }
 
 #ifdef SVTB200_CPU_EMU
@@ -772,11 +1056,10 @@ __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, 
             __syncthreads();
         }
 }
-
 /* ---------------------------------------------------------------------------------------------
  * the kernel: one CTA per super-block
  * ------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant__ MeKernelArgs A) {
+__global__ void __launch_bounds__(ME_THREADS, 3) me_sb_kernel(const __grid_constant__ MeKernelArgs A) {
     ME_DYN_SMEM(smem);
     const SvtB200MeParams &P = A.P;
     const MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, A.interp_in_smem);
@@ -787,7 +1070,6 @@ __global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant
     uint32_t *bsad = (uint32_t *)(smem + L.bsad), *bmv = (uint32_t *)(smem + L.bmv), *bssd = (uint32_t *)(smem + L.bssd);
     uint32_t *bip = (uint32_t *)(smem + L.bip), *posacc = (uint32_t *)(smem + L.posacc);
     uint8_t  *dir = smem + L.dir;
-    MeTask   *tasks = (MeTask *)(smem + L.tasks);
     uint32_t *dist = (uint32_t *)(smem + L.dist), *sadv = (uint32_t *)(smem + L.sad);
     MePred   *preds = (MePred *)(smem + L.preds);
     MeSbState *st = (MeSbState *)(smem + L.state);
@@ -798,6 +1080,7 @@ __global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant
         uint8_t *base = A.interp_in_smem ? smem + L.interp + (size_t)l * 3 * ipb
                                          : A.interp_scratch + ((size_t)sb * 2 + l) * 3 * ipb;
         ip[l].pb = base; ip[l].ph = base + ipb; ip[l].pj = base + 2 * ipb;
+        ip[l].rb = 0; ip[l].rp = 0;
     }
 
     if (t == 0) {
@@ -813,15 +1096,8 @@ __global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant
     for (int i = t; i < 2 * 85; i += ME_THREADS) { bsad[i] = ME_MAX_SAD; bmv[i] = 0; bssd[i] = 0; }
     for (int i = t; i < 85; i += ME_THREADS) { bip[i] = 0; dir[i] = 0; }
     __syncthreads();
-    { /* source SB: all 64 rows from the padded plane */
-        const uint8_t *g = me_pix(A.cur[0], st->ox, st->oy);
-        for (int i = t; i < ME_SB * ME_SB / 4; i += ME_THREADS) {
-            const int y = i >> 4, x = (i & 15) * 4;
-            const uint8_t *p = g + (ptrdiff_t)y * A.cur[0].stride + x;
-            src[y * ME_SB + x] = __ldg(p); src[y * ME_SB + x + 1] = __ldg(p + 1);
-            src[y * ME_SB + x + 2] = __ldg(p + 2); src[y * ME_SB + x + 3] = __ldg(p + 3);
-        }
-    }
+    /* source SB: all 64 rows from the padded plane */
+    me_stage_window(src, ME_SB, A.cur[0], st->ox, st->oy, ME_SB - 4, ME_SB);
     __syncthreads();
 
     for (int list = 0; list < nl; list++) {
@@ -829,19 +1105,28 @@ __global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant
         uint32_t *ls = bsad + list * 85, *lm = bmv + list * 85, *lq = bssd + list * 85;
         if (t == 0) { st->xsc = 0; st->ysc = 0; }
         __syncthreads();
+        uint32_t sad_zero = 0;
+        int have_zero = 0;
         if (P.temporal_layer_index > 0 || list == 0) {
             /* ---- test_search_area_bounds: O, (A == O), B, C, D and, for list 1, the mirrored list-0 MV */
             const int pad = ME_SB - 1, W0 = P.hme_level0_total_search_area_width, H0 = P.hme_level0_total_search_area_height;
-            const uint32_t c_o = me_sb_sad_at(src, st, rp, 0, 0, st->red);
-            const uint32_t c_b = me_sb_sad_at(src, st, rp, me_clip_center(st->ox, (int16_t)W0, pad, rp.w), me_clip_center(st->oy, 0, pad, rp.h), st->red);
-            const uint32_t c_c = me_sb_sad_at(src, st, rp, me_clip_center(st->ox, 0, pad, rp.w), me_clip_center(st->oy, (int16_t)(0 - H0), pad, rp.h), st->red);
-            const uint32_t c_d = me_sb_sad_at(src, st, rp, me_clip_center(st->ox, 0, pad, rp.w), me_clip_center(st->oy, (int16_t)H0, pad, rp.h), st->red);
-            uint64_t c_dir = 0xFFFFFFFFFFFFFull;
+            int16_t cdx[5], cdy[5];
+            cdx[0] = 0; cdy[0] = 0;
+            cdx[1] = me_clip_center(st->ox, (int16_t)W0, pad, rp.w); cdy[1] = me_clip_center(st->oy, 0, pad, rp.h);
+            cdx[2] = me_clip_center(st->ox, 0, pad, rp.w); cdy[2] = me_clip_center(st->oy, (int16_t)(0 - H0), pad, rp.h);
+            cdx[3] = me_clip_center(st->ox, 0, pad, rp.w); cdy[3] = me_clip_center(st->oy, (int16_t)H0, pad, rp.h);
             int16_t dirx = 0, diry = 0;
+            int nc = 4;
             if (list == 1) {
                 dirx = (int16_t)(0 - (me_mvx(bmv[0]) >> 2)); diry = (int16_t)(0 - (me_mvy(bmv[0]) >> 2));
-                c_dir = me_sb_sad_at(src, st, rp, me_clip_center(st->ox, dirx, pad, rp.w), me_clip_center(st->oy, diry, pad, rp.h), st->red);
-            }
+                cdx[4] = me_clip_center(st->ox, dirx, pad, rp.w); cdy[4] = me_clip_center(st->oy, diry, pad, rp.h);
+                nc = 5;
+            } else { cdx[4] = 0; cdy[4] = 0; }
+            uint32_t cs[5];
+            me_sb_sad_multi(src, st, rp, nc, cdx, cdy, cs, st->red);
+            const uint32_t c_o = cs[0], c_b = cs[1], c_c = cs[2], c_d = cs[3];
+            const uint64_t c_dir = (list == 1) ? (uint64_t)cs[4] : 0xFFFFFFFFFFFFFull;
+            sad_zero = c_o; have_zero = 1;
             if (t == 0) {
                 uint64_t best = c_o;
                 if (c_b < best) best = c_b;
@@ -910,9 +1195,12 @@ __global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant
         if (A.trace && t == 0) { A.trace[sb].hme_center_x[list] = st->xsc; A.trace[sb].hme_center_y[list] = st->ysc; }
         /* ---- (0,0) versus the HME centre */
         if (st->xsc != 0 || st->ysc != 0) {
+            int16_t cdx[5] = {0, 0, 0, 0, 0}, cdy[5] = {0, 0, 0, 0, 0};
             const int16_t cx = me_clip_center(st->ox, st->xsc, ME_SB - 1, rp.w), cy = me_clip_center(st->oy, st->ysc, ME_SB - 1, rp.h);
-            const uint32_t zero = me_sb_sad_at(src, st, rp, 0, 0, st->red);
-            const uint32_t hme  = me_sb_sad_at(src, st, rp, cx, cy, st->red);
+            cdx[0] = cx; cdy[0] = cy;
+            uint32_t cs[5];
+            me_sb_sad_multi(src, st, rp, have_zero ? 1 : 2, cdx, cdy, cs, st->red); /* candidate 1 = (0,0) when not yet known */
+            const uint32_t hme = cs[0], zero = have_zero ? sad_zero : cs[1];
             __syncthreads();
             if (t == 0) { if (zero <= hme) { st->xsc = 0; st->ysc = 0; } else { st->xsc = cx; st->ysc = cy; } }
             __syncthreads();
@@ -923,14 +1211,17 @@ __global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant
             me_clip_window(st->ox, &xo, &saw, ME_SB - 1, P.luma_width);
             me_clip_window(st->oy, &yo, &sah, ME_SB - 1, P.luma_height);
             st->sa_ox[list] = xo; st->sa_oy[list] = yo; st->saw[list] = saw; st->sah[list] = sah;
-            st->w_pitch = ((saw + 63 + 16 + 4) + 3) & ~3;
+            st->fp_pitch = me_fp_pitch(saw);
             if (A.trace) { A.trace[sb].sa_ox[list] = xo; A.trace[sb].sa_oy[list] = yo; A.trace[sb].sa_w[list] = saw; A.trace[sb].sa_h[list] = sah; }
         }
         __syncthreads();
-        /* ---- full-pel search */
-        me_stage_window(win, st->w_pitch, rp, st->ox + st->sa_ox[list], st->oy + st->sa_oy[list], st->saw[list] + 63 + 16, st->sah[list] + 63);
+        /* ---- full-pel search: the window (with the halo the half-pel filters need) is staged once */
+        const int fpp = st->fp_pitch;
+        const uint8_t *rb = win + ME_HALO_Y * fpp + ME_HALO_X;
+        me_stage_window(win, fpp, rp, st->ox + st->sa_ox[list] - ME_HALO_X, st->oy + st->sa_oy[list] - ME_HALO_Y,
+                        st->saw[list] + ME_SB - 1 + 16 + ME_HALO_X, me_fp_rows(st->sah[list]));
         __syncthreads();
-        me_fullpel(src, win, st->w_pitch, st, list, pu_key, s8, s16, s32);
+        me_fullpel(src, rb, fpp, st, list, pu_key, s8, s16, s32);
         if (t < 85) {
             const unsigned long long k = pu_key[t];
             const uint32_t pos = (uint32_t)(k & 0xffffffffu);
@@ -953,14 +1244,16 @@ __global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant
             if (A.trace) A.trace[sb].subpel_enable[list] = (uint8_t)(e32 | (e16 << 1) | (e8 << 2) | (eq << 3));
         }
         __syncthreads();
+        ip[list].rb = rb; ip[list].rp = fpp;
         if (st->e32 || st->e16 || st->e8 || st->eq) {
-            me_interp(rp, st, list, ip[list].pb, ip[list].ph, ip[list].pj);
+            me_interp(rb, fpp, st, list, ip[list].pb, ip[list].ph, ip[list].pj);
             if (t == 0) st->interp_ok[list] = 1;
-            const int e16 = st->e16 && P.cu16x16_mode == 0, e8 = st->e8 && P.cu8x8_mode != 1, eq = st->eq;
-            if (P.fractional_search64x64) me_subpel_class(A, src, st, list, ip[list], 0, 1, 1, 32, ls, lm, lq, dir, tasks, dist, sadv);
-            if (st->e32) me_subpel_class(A, src, st, list, ip[list], 1, 5, eq, 0, ls, lm, lq, dir, tasks, dist, sadv);
-            if (e16) me_subpel_class(A, src, st, list, ip[list], 5, 21, eq, 0, ls, lm, lq, dir, tasks, dist, sadv);
-            if (e8) me_subpel_class(A, src, st, list, ip[list], 21, 85, eq, 0, ls, lm, lq, dir, tasks, dist, sadv);
+            int cmask = 0;
+            if (P.fractional_search64x64) cmask |= 1;
+            if (st->e32) cmask |= 2;
+            if (st->e16 && P.cu16x16_mode == 0) cmask |= 4;
+            if (st->e8 && P.cu8x8_mode != 1) cmask |= 8;
+            if (cmask) me_subpel(A, src, st, list, ip[list], cmask, st->eq ? 15 : 1, ls, lm, lq, dir, dist, sadv);
         }
         __syncthreads();
     }
@@ -968,33 +1261,34 @@ __global__ void __launch_bounds__(ME_THREADS) me_sb_kernel(const __grid_constant
     /* ---- bi-prediction: SAD(src, avg(pred L0, pred L1)) at the two uni-pred winners */
     if (nl == 2) {
         const int sub = (P.fractional_search_method == 0);
+        /* list 1's integer samples are still staged; list 0's window has been overwritten: read the plane */
+        ip[0].rb = me_pix(A.ref[0][0], st->ox + st->sa_ox[0], st->oy + st->sa_oy[0]); ip[0].rp = A.ref[0][0].stride;
         for (int i = t; i < 85 * 2; i += ME_THREADS) {
             const int idx = i >> 1, l = i & 1;
             int px, py, w;
             me_pu_geom(idx, &px, &py, &w);
-            me_bipred_pred(A.ref[l][0], st, l, ip[l], bmv[l * 85 + idx], px, py, &preds[i]);
+            me_bipred_pred(st->sa_ox[l], st->sa_oy[l], st->istride[l], ip[l], bmv[l * 85 + idx], px, py, &preds[i]);
         }
         __syncthreads();
+        /* one (sub-sampled) row of one PU per unit: 64x64 -> 32 lanes, 32x32 -> 16, 16x16 -> 8, 8x8 -> 4 */
         for (int cls = 0; cls < 4; cls++) {
             if (cls == 3 && P.cu8x8_mode != 0) continue;
             if (cls >= 2 && P.cu16x16_mode != 0) continue;
-            for (int seg = t; seg < 512; seg += ME_THREADS) {
-                const int y = seg >> 3, x8 = (seg & 7) * 8;
-                if (sub && (y & 1)) continue;
-                int idx;
-                if (cls == 0) idx = 0;
-                else if (cls == 1) idx = 1 + (x8 >> 5) + 2 * (y >> 5);
-                else if (cls == 2) idx = 5 + me_tab16[(x8 >> 4) + 4 * (y >> 4)];
-                else idx = 21 + me_tab8[(x8 >> 3) + 8 * (y >> 3)];
+            const int tlog = 5 - cls, T = 1 << tlog, idx0 = me_cls_idx0(cls), nunits = me_cls_npu(cls) * T;
+            for (int u = t; u < nunits; u += ME_THREADS) {
+                const int idx = idx0 + (u >> tlog), part = u & (T - 1);
                 int px, py, w;
                 me_pu_geom(idx, &px, &py, &w);
                 const MePred &p0 = preds[idx * 2], &p1 = preds[idx * 2 + 1];
+                const int wwords = w >> 2;
                 uint32_t acc = 0;
-                for (int x = 0; x < 8; x++) {
-                    const int d = (int)src[y * ME_SB + x8 + x] - (int)((me_pred_px(p0, x8 + x - px, y - py) + me_pred_px(p1, x8 + x - px, y - py) + 1) >> 1);
-                    acc += (uint32_t)(d < 0 ? -d : d);
+                for (int y = sub ? 2 * part : part; y < w; y += sub ? 2 * T : T) {
+                    const uint32_t *srow = (const uint32_t *)(src + (py + y) * ME_SB + px);
+                    for (int k = 0; k < wwords; k++)
+                        acc = me_absdiff_acc(__vavgu4(me_pred_word(p0, y, k), me_pred_word(p1, y, k)), srow[k], acc);
                 }
-                atomicAdd(&bip[idx], sub ? acc << 1 : acc);
+                acc = me_group_sum(acc, tlog);
+                if (part == 0) bip[idx] = sub ? acc << 1 : acc;
             }
         }
         __syncthreads();

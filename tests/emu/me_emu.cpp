@@ -17,9 +17,8 @@ extern "C" int me_emu_run(const SvtB200MeParams *P, const SvtB200Plane cur[3], c
     A.sbs_w = (P->luma_width + 63) / 64;
     A.n_sb  = A.sbs_w * ((P->luma_height + 63) / 64);
     A.out = out; A.rcme = rcme; A.trace = trace;
-    A.win_bytes = win_bytes;
-    const int saw = P->search_area_width < 127 ? P->search_area_width : 127, sah = P->search_area_height < 127 ? P->search_area_height : 127;
-    A.interp_plane_bytes = (((saw + 63 + 2) + 7) & ~7) * (sah + 63 + 4);
+    A.win_bytes = win_bytes > 0 ? win_bytes : me_window_bytes(*P); /* 0: the size the host code would choose */
+    A.interp_plane_bytes = me_interp_plane_bytes(*P);
     A.interp_in_smem = !force_global_interp;
     std::vector<uint8_t> scratch;
     if (force_global_interp) { scratch.resize((size_t)A.n_sb * 6 * me_align16(A.interp_plane_bytes)); A.interp_scratch = scratch.data(); }

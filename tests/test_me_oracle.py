@@ -32,14 +32,17 @@ def test_emulated_kernel_tables():
     assert H.emu().me_emu_check_tables() == 0
 
 
-EMU_CASES = [("me_192x128_m8t1_pic16", [0, 2, 5]), ("me_192x128_m8t1_pic17", [1, 4]), ("me_192x128_m5t0_pic01", [3]),
-             ("me_192x128_m3t1_pic18", [2])]
+# (fixture, SBs, window-buffer bytes: 0 = the size the host code plans, 8400 = just above the full-pel window of the
+#  16x9 search area so that the HME areas are searched in several stripes, 98304 = everything in one stripe; global interp)
+EMU_CASES = [("me_192x128_m8t1_pic16", [0, 2, 5], 98304, 0), ("me_192x128_m8t1_pic16", [1, 4], 8400, 0),
+             ("me_192x128_m8t1_pic17", [1, 4], 0, 0), ("me_192x128_m8t1_pic08", [3], 8400, 1),
+             ("me_192x128_m5t0_pic01", [3], 0, 0), ("me_192x128_m3t1_pic18", [2], 0, 0), ("me_192x128_m3t1_pic02", [5], 0, 1)]
 
 
-@pytest.mark.parametrize("name,sbs", EMU_CASES, ids=[c[0] for c in EMU_CASES])
-def test_emulated_kernel_matches_reference_dump(name, sbs):
+@pytest.mark.parametrize("name,sbs,win,gl", EMU_CASES, ids=["%s-w%d-g%d" % (c[0], c[2], c[3]) for c in EMU_CASES])
+def test_emulated_kernel_matches_reference_dump(name, sbs, win, gl):
     pic = H.MePicture(os.path.join(H.GOLDEN, name + ".bin.gz"))
     for sb in sbs:
-        out, _, _ = H.emu_me_picture(pic, sb, sb + 1, win_bytes=98304)
+        out, _, _ = H.emu_me_picture(pic, sb, sb + 1, win_bytes=win, force_global_interp=gl)
         ok = H.me_equal(out[sb * 85:(sb + 1) * 85], pic.expected[sb * 85:(sb + 1) * 85], pic.params.num_lists)
         assert ok.all(), "emulated kernel differs on SB %d (%d PUs)" % (sb, (~ok).sum())
