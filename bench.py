@@ -352,18 +352,21 @@ def main():
     d_jobs_y, d_jobs_c = to_dev(jobs_y), to_dev(jobs_c)
     d_rows = to_dev(H.quant_rows([QINDEX]))
     d_lfm, d_thr = to_dev(lf_masks_32x32()), to_dev(H.lf_thresholds())
-    d_rec = [L.svtb200_dev_alloc(h, W4K * H4K), L.svtb200_dev_alloc(h, csize), L.svtb200_dev_alloc(h, csize)]
-    d_me = L.svtb200_dev_alloc(h, N_SB * 85 * 40)
-    d_q = {32: L.svtb200_dev_alloc(h, N_TU_Y * 2048), 16: [L.svtb200_dev_alloc(h, N_TU_C * 512) for _ in range(2)]}
+    # result buffers exist NSLOT times: the end-to-end leg downloads slot s while the kernels of the next pictures fill the others
+    NSLOT = 3
+    d_rec = [[L.svtb200_dev_alloc(h, W4K * H4K), L.svtb200_dev_alloc(h, csize), L.svtb200_dev_alloc(h, csize)] for _ in range(NSLOT)]
+    d_me = [L.svtb200_dev_alloc(h, N_SB * 85 * 40) for _ in range(NSLOT)]
+    d_q = [{32: L.svtb200_dev_alloc(h, N_TU_Y * 2048), 16: [L.svtb200_dev_alloc(h, N_TU_C * 512) for _ in range(2)]} for _ in range(NSLOT)]
     d_dq = {32: L.svtb200_dev_alloc(h, N_TU_Y * 2048), 16: [L.svtb200_dev_alloc(h, N_TU_C * 512) for _ in range(2)]}
-    d_eob = {32: L.svtb200_dev_alloc(h, N_TU_Y * 2), 16: [L.svtb200_dev_alloc(h, N_TU_C * 2) for _ in range(2)]}
+    d_eob = [{32: L.svtb200_dev_alloc(h, N_TU_Y * 2), 16: [L.svtb200_dev_alloc(h, N_TU_C * 2) for _ in range(2)]} for _ in range(NSLOT)]
     LfP = api.LfParams()
     LfP.width, LfP.height, LfP.mi_rows, LfP.mi_cols, LfP.y_only, LfP.filter_level = W4K, H4K, H4K // 8, W4K // 8, 0, LF_LEVEL
     # pinned host result buffers for the e2e leg
-    h_me = torch.empty(N_SB * 85 * 40, dtype=torch.uint8).pin_memory()
-    h_q = {32: torch.empty(N_TU_Y * 2048, dtype=torch.uint8).pin_memory(), 16: [torch.empty(N_TU_C * 512, dtype=torch.uint8).pin_memory() for _ in range(2)]}
-    h_eob = {32: torch.empty(N_TU_Y * 2, dtype=torch.uint8).pin_memory(), 16: [torch.empty(N_TU_C * 2, dtype=torch.uint8).pin_memory() for _ in range(2)]}
-    h_rec = [torch.empty(W4K * H4K, dtype=torch.uint8).pin_memory(), torch.empty(csize, dtype=torch.uint8).pin_memory(), torch.empty(csize, dtype=torch.uint8).pin_memory()]
+    pinned = lambda n: torch.empty(n, dtype=torch.uint8).pin_memory()
+    h_me = [pinned(N_SB * 85 * 40) for _ in range(NSLOT)]
+    h_q = [{32: pinned(N_TU_Y * 2048), 16: [pinned(N_TU_C * 512) for _ in range(2)]} for _ in range(NSLOT)]
+    h_eob = [{32: pinned(N_TU_Y * 2), 16: [pinned(N_TU_C * 2) for _ in range(2)]} for _ in range(NSLOT)]
+    h_rec = [[pinned(W4K * H4K), pinned(csize), pinned(csize)] for _ in range(NSLOT)]
 
     def txq_planes(src, sstride, sbytes, pred, rec, rstride, rbytes):
         pl = api.TxPlanes()
@@ -377,47 +380,73 @@ def main():
     alg = {"me_sb_kernel": 0, "txq_kernel": 0, "lf_sb_kernel": 0}
     marks = []
 
-    def kernels(i, timed):
+    def kernels(i, timed, slot=0):
         n = ENCODE_ORDER[i % 16]
         P, (r0, r1) = me_params(n)
         ids = (C.c_uint64 * 2)(r0, r1)
         e = [ev() for _ in range(4)] if timed else None
         if timed:
             e[0].record(stream)
-        ctx.check(L.svtb200_me_picture_dev(h, C.byref(P), n, ids, d_me, None), "me_picture_dev")
+        ctx.check(L.svtb200_me_picture_dev(h, C.byref(P), n, ids, d_me[slot], None), "me_picture_dev")
         if timed:
             e[1].record(stream)
         ybytes = sy * dplane[n].padded_height
-        pl = txq_planes(dplane[n].buf, sy, ybytes, dplane[r0].buf, d_rec[0], W4K, W4K * H4K)
-        ctx.check(L.svtb200_txq_batch_dev(h, 3, N_TU_Y, d_jobs_y, C.byref(pl), d_rows, 1, None, d_q[32], d_dq[32], d_eob[32]), "txq y")
+        rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
+        pl = txq_planes(dplane[n].buf, sy, ybytes, dplane[r0].buf, rec[0], W4K, W4K * H4K)
+        ctx.check(L.svtb200_txq_batch_dev(h, 3, N_TU_Y, d_jobs_y, C.byref(pl), d_rows, 1, None, q[32], d_dq[32], eob[32]), "txq y")
         for k, (dc, pc) in enumerate(((d_u, d_u), (d_v, d_v))):
-            pl = txq_planes(dc[n], W4K // 2, csize, pc[r0], d_rec[1 + k], W4K // 2, csize)
-            ctx.check(L.svtb200_txq_batch_dev(h, 2, N_TU_C, d_jobs_c, C.byref(pl), d_rows, 1, None, d_q[16][k], d_dq[16][k], d_eob[16][k]), "txq c")
+            pl = txq_planes(dc[n], W4K // 2, csize, pc[r0], rec[1 + k], W4K // 2, csize)
+            ctx.check(L.svtb200_txq_batch_dev(h, 2, N_TU_C, d_jobs_c, C.byref(pl), d_rows, 1, None, q[16][k], d_dq[16][k], eob[16][k]), "txq c")
         if timed:
             e[2].record(stream)
         if n == 16:
-            ctx.check(L.svtb200_deblock_picture_dev(h, C.byref(LfP), d_rec[0], W4K, d_rec[1], d_rec[2], W4K // 2, d_lfm, 60, d_thr), "deblock")
+            ctx.check(L.svtb200_deblock_picture_dev(h, C.byref(LfP), rec[0], W4K, rec[1], rec[2], W4K // 2, d_lfm, 60, d_thr), "deblock")
         if timed:
             e[3].record(stream)
             marks.append((e, P, n))
-        return n
+        return n, r0
+
+    # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI's three queues.  Picture i+1 uploads and
+    # picture i-1 downloads while picture i computes; the host collects picture i-3's results (the previous user of the slot)
+    # before it queues picture i, i.e. three pictures are in flight (upload / kernels / download).
+    downloaded = [0] * NSLOT   # marker after the last download out of each result slot
+    chroma_used = {}      # marker after the last kernel that read the chroma buffers of a picture
+
+    skip = os.environ.get("SVTB200_E2E_SKIP", "").split(",")  # diagnosis only: "h2d", "d2h", "kernels"
 
     def step_e2e(i):
         n = ENCODE_ORDER[i % 16]
-        ctx.picture_upload(n, PS[n][0], None, PS[n][2])                       # H2D luma + 1/16 plane (pinned)
-        L.svtb200_memcpy_h2d(h, d_u[n], pu[n].data_ptr(), csize)               # H2D chroma
-        L.svtb200_memcpy_h2d(h, d_v[n], pv[n].data_ptr(), csize)
-        kernels(i, False)
-        L.svtb200_memcpy_d2h(h, h_me.data_ptr(), d_me, N_SB * 85 * 40)         # D2H ME results
-        L.svtb200_memcpy_d2h(h, h_q[32].data_ptr(), d_q[32], N_TU_Y * 2048)    # D2H quantised coefficients + eob
-        L.svtb200_memcpy_d2h(h, h_eob[32].data_ptr(), d_eob[32], N_TU_Y * 2)
+        slot = i % NSLOT
+        if downloaded[slot]:
+            ctx.wait(downloaded[slot])                                          # picture i-NSLOT is complete in host memory; its slot is free
+        if "h2d" not in skip:
+            ctx.picture_upload_luma(n, PS[n][0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, False)   # H2D luma picture area; padding + 1/16 on the device
+            if n in chroma_used:
+                ctx.stream_wait(api.UPLOAD, chroma_used[n])
+            ctx.check(L.svtb200_memcpy_h2d_async(h, d_u[n], pu[n].data_ptr(), csize), "h2d u")     # H2D chroma
+            ctx.check(L.svtb200_memcpy_h2d_async(h, d_v[n], pv[n].data_ptr(), csize), "h2d v")
+            ctx.fence(api.UPLOAD, api.COMPUTE)
+        if "kernels" in skip:
+            r0 = n
+        else:
+            _, r0 = kernels(i, False, slot)
+        L.svtb200_picture_touch(h, n)
+        L.svtb200_picture_touch(h, r0)
+        chroma_used[n] = chroma_used[r0] = ctx.marker(api.COMPUTE)
+        ctx.stream_wait(api.DOWNLOAD, chroma_used[n])
+        rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
+        d2h = lambda hb, db, nb: ("d2h" in skip) or ctx.check(L.svtb200_memcpy_d2h_async(h, hb.data_ptr(), db, nb), "d2h")
+        d2h(h_me[slot], d_me[slot], N_SB * 85 * 40)                             # D2H ME results
+        d2h(h_q[slot][32], q[32], N_TU_Y * 2048)                                # D2H quantised coefficients + eob
+        d2h(h_eob[slot][32], eob[32], N_TU_Y * 2)
         for k in range(2):
-            L.svtb200_memcpy_d2h(h, h_q[16][k].data_ptr(), d_q[16][k], N_TU_C * 512)
-            L.svtb200_memcpy_d2h(h, h_eob[16][k].data_ptr(), d_eob[16][k], N_TU_C * 2)
+            d2h(h_q[slot][16][k], q[16][k], N_TU_C * 512)
+            d2h(h_eob[slot][16][k], eob[16][k], N_TU_C * 2)
         if n == 16:                                                            # D2H filtered reference picture
-            L.svtb200_memcpy_d2h(h, h_rec[0].data_ptr(), d_rec[0], W4K * H4K)
-            L.svtb200_memcpy_d2h(h, h_rec[1].data_ptr(), d_rec[1], csize)
-            L.svtb200_memcpy_d2h(h, h_rec[2].data_ptr(), d_rec[2], csize)
+            d2h(h_rec[slot][0], rec[0], W4K * H4K)
+            d2h(h_rec[slot][1], rec[1], csize)
+            d2h(h_rec[slot][2], rec[2], csize)
+        downloaded[slot] = ctx.marker(api.DOWNLOAD)
 
     def barrier():
         if world > 1:
@@ -452,9 +481,14 @@ def main():
         step_e2e(i)
     barrier()
     t0 = time.perf_counter()
+    t_issue = 0.0
     for i in range(args.steps):
+        ti = time.perf_counter()
         step_e2e(args.warmup + i)
+        t_issue += time.perf_counter() - ti
     ctx.sync()
+    if os.environ.get("SVTB200_BENCH_DEBUG"):
+        sys.stderr.write("e2e host time in step_e2e (issue + waits): %.3f ms/step\n" % (1000.0 * t_issue / args.steps))
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1000.0
     sampler.stop()
@@ -464,7 +498,7 @@ def main():
     ms_e2e, _ = sharding.agree_step(ms_e2e, args.steps, device="cuda")
     value = units / (ms_res / 1000.0)
     e2e = units / (ms_e2e / 1000.0)
-    h2d = pics[0]["full"].nbytes + pics[0]["sixteenth"].nbytes + 2 * csize
+    h2d = W4K * H4K + 2 * csize  # the picture area of the three planes (padding and the 1/16 plane are made on the device)
     d2h = N_SB * 85 * 40 + N_TU_Y * 2050 + 2 * N_TU_C * 514 + (W4K * H4K * 3 // 2) // 16  # filtered planes on 1 of 16 pictures
 
     try:

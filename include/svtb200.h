@@ -60,6 +60,26 @@ void  svtb200_dev_free(SvtB200Ctx *ctx, void *p);
 int   svtb200_memcpy_h2d(SvtB200Ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int   svtb200_memcpy_d2h(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 
+/* A context owns three in-order queues: COMPUTE (every kernel, and the synchronous copies above), UPLOAD (picture
+ * uploads and svtb200_memcpy_h2d_async) and DOWNLOAD (svtb200_memcpy_d2h_async), so that the PCIe traffic of the
+ * previous / next picture overlaps the kernels of the current one -- the role the reference's picture-level pipeline
+ * (EbEncHandle.c: one process per stage, several pictures in flight) plays on the CPU.  Picture uploads are ordered
+ * against the kernels that read them by the library; everything else is ordered by the caller with markers:
+ *   svtb200_marker(q, &t)        t = "everything queued on q so far"
+ *   svtb200_stream_wait(q, t)    queue q does not start later work before t is reached
+ *   svtb200_fence(from, to)      = marker(from) + stream_wait(to)
+ *   svtb200_wait(t)              the calling host thread blocks until t is reached
+ * Host buffers of the async copies must be page-locked (svtb200_host_alloc). */
+#define SVTB200_STREAM_COMPUTE  0
+#define SVTB200_STREAM_UPLOAD   1
+#define SVTB200_STREAM_DOWNLOAD 2
+int svtb200_memcpy_h2d_async(SvtB200Ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+int svtb200_memcpy_d2h_async(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
+int svtb200_marker(SvtB200Ctx *ctx, int stream, uint64_t *ticket);
+int svtb200_stream_wait(SvtB200Ctx *ctx, int stream, uint64_t ticket);
+int svtb200_fence(SvtB200Ctx *ctx, int from_stream, int to_stream);
+int svtb200_wait(SvtB200Ctx *ctx, uint64_t ticket);
+
 /* =============================================================================================
  * S1  Motion estimation
  * ============================================================================================= */
@@ -91,6 +111,9 @@ int svtb200_picture_release(SvtB200Ctx *ctx, uint64_t pic_id);
  * same stride / origin as the uploaded host plane -- for chaining svtb200_txq_batch_dev / svtb200_deblock_picture_dev
  * on planes that are already resident. */
 int svtb200_picture_plane_dev(SvtB200Ctx *ctx, uint64_t pic_id, int which, SvtB200Plane *out);
+/* Tell the library that kernels the CALLER queued on the compute queue (through the *_dev entry points, on planes obtained
+ * from svtb200_picture_plane_dev) read picture pic_id: a later re-upload of that id waits for them. */
+int svtb200_picture_touch(SvtB200Ctx *ctx, uint64_t pic_id);
 
 /* Everything motion_estimate_sb() reads from MeContext / PictureParentControlSet /
  * SequenceControlSet (EbMotionEstimationContext.h:275, EbPictureControlSet.h:229). */

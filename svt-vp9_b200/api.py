@@ -116,6 +116,13 @@ def lib():
         L.svtb200_picture_upload.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane)]
         L.svtb200_picture_upload_luma.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Plane), C.c_int32, C.c_int32, C.c_int]
         L.svtb200_picture_release.argtypes = [C.c_void_p, C.c_uint64]
+        L.svtb200_picture_touch.argtypes = [C.c_void_p, C.c_uint64]
+        L.svtb200_memcpy_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.svtb200_memcpy_d2h_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.svtb200_marker.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
+        L.svtb200_stream_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+        L.svtb200_fence.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.svtb200_wait.argtypes = [C.c_void_p, C.c_uint64]
         L.svtb200_picture_plane_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Plane)]
         L.svtb200_me_picture.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
         L.svtb200_me_picture_dev.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
@@ -123,6 +130,9 @@ def lib():
         L.svtb200_me_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib = L
     return _lib
+
+
+COMPUTE, UPLOAD, DOWNLOAD = 0, 1, 2
 
 
 class Context:
@@ -175,6 +185,21 @@ class Context:
         out = np.zeros((d.padded_height, d.stride), dtype=np.uint8)
         self.check(self.L.svtb200_memcpy_d2h(self.h, out.ctypes.data, d.buf, out.nbytes), "memcpy_d2h")
         return out, d
+
+    # ---- the three queues of a context (include/svtb200.h): ordering between them
+    def marker(self, stream):
+        t = C.c_uint64()
+        self.check(self.L.svtb200_marker(self.h, stream, C.byref(t)), "marker")
+        return t.value
+
+    def stream_wait(self, stream, ticket):
+        self.check(self.L.svtb200_stream_wait(self.h, stream, ticket), "stream_wait")
+
+    def fence(self, src, dst):
+        self.check(self.L.svtb200_fence(self.h, src, dst), "fence")
+
+    def wait(self, ticket):
+        self.check(self.L.svtb200_wait(self.h, ticket), "wait")
 
     def picture_release(self, pic_id):
         self.L.svtb200_picture_release(self.h, pic_id)

@@ -11,12 +11,16 @@
 #include <vector>
 #include "../../include/svtb200.h"
 
+#define SVTB200_MARKER_RING 256
+
 struct DevPlane {
     uint8_t *buf = nullptr;
     int32_t  stride = 0, ox = 0, oy = 0, w = 0, h = 0, rows = 0;
 };
 struct DevPicture {
-    DevPlane pl[3]; /* full, quarter, sixteenth */
+    DevPlane    pl[3];            /* full, quarter, sixteenth */
+    cudaEvent_t ready = nullptr;  /* recorded on the upload stream after the picture's copies / front-end kernels */
+    cudaEvent_t used = nullptr;   /* recorded on the compute stream after the last kernel that reads the picture */
 };
 
 struct ScanTable {
@@ -26,7 +30,10 @@ struct ScanTable {
 
 struct SvtB200Ctx {
     int          device = 0;
-    cudaStream_t stream = nullptr;
+    cudaStream_t stream = nullptr;              /* compute */
+    cudaStream_t up = nullptr, down = nullptr;  /* host->device and device->host copy streams */
+    cudaEvent_t  markers[SVTB200_MARKER_RING] = {};
+    uint64_t     next_ticket = 1;
     std::mutex   mu;
     std::string  err;
     uint64_t     launches = 0;
@@ -73,5 +80,14 @@ static inline int svtb200_grow_pinned(SvtB200Ctx *ctx, size_t need) {
     if (cudaMallocHost((void **)&ctx->pin, n) != cudaSuccess) { ctx->err = "cudaMallocHost failed"; cudaGetLastError(); return SVTB200_ENOMEM; }
     ctx->pin_bytes = n;
     return 0;
+}
+static inline cudaStream_t svtb200_pick_stream(SvtB200Ctx *c, int which) {
+    return which == SVTB200_STREAM_UPLOAD ? c->up : which == SVTB200_STREAM_DOWNLOAD ? c->down : c->stream;
+}
+/* a kernel about to read picture p on the compute stream: wait for its upload; afterwards note the use */
+static inline void svtb200_pic_acquire(SvtB200Ctx *c, DevPicture &p) { if (p.ready) cudaStreamWaitEvent(c->stream, p.ready, 0); }
+static inline void svtb200_pic_release(SvtB200Ctx *c, DevPicture &p) {
+    if (!p.used) cudaEventCreateWithFlags(&p.used, cudaEventDisableTiming);
+    cudaEventRecord(p.used, c->stream);
 }
 #endif

@@ -11,7 +11,12 @@ int svtb200_create(int device, SvtB200Ctx **out) {
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return SVTB200_ENODEV; }
     SvtB200Ctx *c = new SvtB200Ctx();
     c->device = device;
-    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; cudaGetLastError(); return SVTB200_ENODEV; }
+    /* the upload queue also runs the (tiny) padding / decimation kernels: give it priority over the picture-sized compute kernels */
+    int prio_lo = 0, prio_hi = 0;
+    cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->up, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->down, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete c; cudaGetLastError(); return SVTB200_ENODEV; }
     cudaDeviceGetAttribute(&c->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
     *out = c;
@@ -21,8 +26,13 @@ int svtb200_create(int device, SvtB200Ctx **out) {
 void svtb200_destroy(SvtB200Ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
-    for (auto &kv : c->pics) for (int i = 0; i < 3; i++) if (kv.second.pl[i].buf) cudaFree(kv.second.pl[i].buf);
+    cudaStreamSynchronize(c->up); cudaStreamSynchronize(c->stream); cudaStreamSynchronize(c->down);
+    for (auto &kv : c->pics) {
+        for (int i = 0; i < 3; i++) if (kv.second.pl[i].buf) cudaFree(kv.second.pl[i].buf);
+        if (kv.second.ready) cudaEventDestroy(kv.second.ready);
+        if (kv.second.used) cudaEventDestroy(kv.second.used);
+    }
+    for (int i = 0; i < SVTB200_MARKER_RING; i++) if (c->markers[i]) cudaEventDestroy(c->markers[i]);
     if (c->interp_scratch) cudaFree(c->interp_scratch);
     if (c->me_out) cudaFree(c->me_out);
     if (c->me_rcme) cudaFree(c->me_rcme);
@@ -30,7 +40,7 @@ void svtb200_destroy(SvtB200Ctx *c) {
     if (c->scratch) cudaFree(c->scratch);
     if (c->pin) cudaFreeHost(c->pin);
     for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { if (c->scans[a][b].scan) cudaFree(c->scans[a][b].scan); if (c->scans[a][b].iscan) cudaFree(c->scans[a][b].iscan); }
-    cudaStreamDestroy(c->stream);
+    cudaStreamDestroy(c->stream); cudaStreamDestroy(c->up); cudaStreamDestroy(c->down);
     delete c;
 }
 
@@ -40,7 +50,62 @@ void *svtb200_stream(SvtB200Ctx *c) { return c ? (void *)c->stream : nullptr; }
 
 int svtb200_sync(SvtB200Ctx *c) {
     if (!c) return SVTB200_EINVAL;
+    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->up));
     SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->down));
+    return SVTB200_OK;
+}
+
+/* ---- the three in-order queues of a context and the markers that order work between them ---- */
+int svtb200_memcpy_h2d_async(SvtB200Ctx *c, void *d, const void *h, size_t n) {
+    if (!c) return SVTB200_EINVAL;
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->up));
+    return SVTB200_OK;
+}
+int svtb200_memcpy_d2h_async(SvtB200Ctx *c, void *h, const void *d, size_t n) {
+    if (!c) return SVTB200_EINVAL;
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->down));
+    return SVTB200_OK;
+}
+int svtb200_marker(SvtB200Ctx *c, int stream, uint64_t *ticket) {
+    if (!c || !ticket || stream < 0 || stream > 2) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    const uint64_t t = c->next_ticket++;
+    cudaEvent_t &e = c->markers[t % SVTB200_MARKER_RING];
+    if (!e) SVTB200_CUDA_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    SVTB200_CUDA_CHECK(c, cudaEventRecord(e, svtb200_pick_stream(c, stream)));
+    *ticket = t;
+    return SVTB200_OK;
+}
+static int marker_event(SvtB200Ctx *c, uint64_t ticket, cudaEvent_t *e) {
+    if (ticket == 0 || ticket >= c->next_ticket) return SVTB200_EINVAL;
+    if (c->next_ticket - ticket > SVTB200_MARKER_RING) { *e = nullptr; return SVTB200_OK; } /* recycled: long since reached */
+    *e = c->markers[ticket % SVTB200_MARKER_RING];
+    return SVTB200_OK;
+}
+int svtb200_stream_wait(SvtB200Ctx *c, int stream, uint64_t ticket) {
+    if (!c || stream < 0 || stream > 2) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaEvent_t e;
+    int rc = marker_event(c, ticket, &e);
+    if (rc) return rc;
+    if (e) SVTB200_CUDA_CHECK(c, cudaStreamWaitEvent(svtb200_pick_stream(c, stream), e, 0));
+    return SVTB200_OK;
+}
+int svtb200_fence(SvtB200Ctx *c, int from, int to) {
+    uint64_t t;
+    int rc = svtb200_marker(c, from, &t);
+    return rc ? rc : svtb200_stream_wait(c, to, t);
+}
+int svtb200_wait(SvtB200Ctx *c, uint64_t ticket) {
+    if (!c) return SVTB200_EINVAL;
+    cudaEvent_t e;
+    {
+        std::lock_guard<std::mutex> g(c->mu);
+        int rc = marker_event(c, ticket, &e);
+        if (rc) return rc;
+    }
+    if (e) SVTB200_CUDA_CHECK(c, cudaEventSynchronize(e));
     return SVTB200_OK;
 }
 
@@ -82,12 +147,20 @@ static int upload_plane(SvtB200Ctx *c, const SvtB200Plane *src, DevPlane *dst) {
         dst->buf = nullptr;
         /* slack: window staging may read a few bytes past the last padded row */
         if (cudaMalloc((void **)&dst->buf, bytes + 256) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(plane) failed"; return SVTB200_ENOMEM; }
-        cudaMemsetAsync(dst->buf + bytes, 0, 256, c->stream);
+        cudaMemsetAsync(dst->buf + bytes, 0, 256, c->up);
     }
     dst->stride = src->stride; dst->ox = src->origin_x; dst->oy = src->origin_y; dst->w = src->width; dst->h = src->height;
     dst->rows = src->padded_height;
-    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(dst->buf, src->buf, bytes, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(dst->buf, src->buf, bytes, cudaMemcpyHostToDevice, c->up));
     return 0;
+}
+/* uploads run on the upload queue: after every kernel that still reads the picture's previous contents, and
+ * followed by the event the compute queue waits on before it touches the new contents */
+static void upload_begin(SvtB200Ctx *c, DevPicture &p) { if (p.used) cudaStreamWaitEvent(c->up, p.used, 0); }
+static int upload_end(SvtB200Ctx *c, DevPicture &p) {
+    if (!p.ready) SVTB200_CUDA_CHECK(c, cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
+    SVTB200_CUDA_CHECK(c, cudaEventRecord(p.ready, c->up));
+    return SVTB200_OK;
 }
 
 int svtb200_picture_upload(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *full, const SvtB200Plane *quarter,
@@ -97,10 +170,11 @@ int svtb200_picture_upload(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *f
     cudaSetDevice(c->device);
     DevPicture &p = c->pics[pic_id];
     int rc;
+    upload_begin(c, p);
     if ((rc = upload_plane(c, full, &p.pl[0]))) return rc;
     if ((rc = upload_plane(c, quarter, &p.pl[1]))) return rc;
     if ((rc = upload_plane(c, sixteenth, &p.pl[2]))) return rc;
-    return SVTB200_OK;
+    return upload_end(c, p);
 }
 
 /* Edge replication of the padded source plane (eb_vp9_generate_padding, EbPictureOperators.c) and the point decimations
@@ -135,7 +209,7 @@ static int alloc_plane(SvtB200Ctx *c, DevPlane *dst, int stride, int rows) {
         if (dst->buf) cudaFree(dst->buf);
         dst->buf = nullptr;
         if (cudaMalloc((void **)&dst->buf, bytes + 256) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc(plane) failed"; return SVTB200_ENOMEM; }
-        cudaMemsetAsync(dst->buf + bytes, 0, 256, c->stream);
+        cudaMemsetAsync(dst->buf + bytes, 0, 256, c->up);
     }
     dst->stride = stride; dst->rows = rows;
     return 0;
@@ -149,14 +223,15 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
     cudaSetDevice(c->device);
     DevPicture &p = c->pics[pic_id];
     int rc;
+    upload_begin(c, p);
     DevPlane *f = &p.pl[0];
     if ((rc = alloc_plane(c, f, full->stride, full->padded_height))) return rc;
     f->ox = full->origin_x; f->oy = full->origin_y; f->w = full->width; f->h = full->height;
     /* only the picture area crosses PCIe; the padding is regenerated on the device */
     const size_t off = (size_t)f->oy * f->stride + f->ox;
-    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(f->buf + off, f->stride, full->buf + off, full->stride, f->w, f->h, cudaMemcpyHostToDevice, c->stream));
+    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(f->buf + off, f->stride, full->buf + off, full->stride, f->w, f->h, cudaMemcpyHostToDevice, c->up));
     dim3 blk(128);
-    pa_pad_full_kernel<<<dim3((f->stride / 4 + 127) / 128, f->rows), blk, 0, c->stream>>>(f->buf, f->stride, f->ox, f->oy, f->w, f->h, f->rows);
+    pa_pad_full_kernel<<<dim3((f->stride / 4 + 127) / 128, f->rows), blk, 0, c->up>>>(f->buf, f->stride, f->ox, f->oy, f->w, f->h, f->rows);
     c->launches++;
     for (int lvl = 1; lvl <= 2; lvl++) {
         DevPlane *d = &p.pl[lvl];
@@ -166,12 +241,12 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
         const int stride = (w + 2 * pad + 3) & ~3; /* multiple of 4 for the word stores; the reference's strides are */
         if ((rc = alloc_plane(c, d, stride, h + 2 * pad))) return rc;
         d->ox = pad; d->oy = pad; d->w = w; d->h = h;
-        pa_decimate_kernel<<<dim3((stride / 4 + 127) / 128, d->rows), blk, 0, c->stream>>>(f->buf, f->stride, f->ox, f->oy, d->buf, stride, pad, pad, w, h,
+        pa_decimate_kernel<<<dim3((stride / 4 + 127) / 128, d->rows), blk, 0, c->up>>>(f->buf, f->stride, f->ox, f->oy, d->buf, stride, pad, pad, w, h,
                                                                                      d->rows, step);
         c->launches++;
     }
     SVTB200_CUDA_CHECK(c, cudaGetLastError());
-    return SVTB200_OK;
+    return upload_end(c, p);
 }
 
 int svtb200_picture_plane_dev(SvtB200Ctx *c, uint64_t pic_id, int which, SvtB200Plane *out) {
@@ -179,9 +254,20 @@ int svtb200_picture_plane_dev(SvtB200Ctx *c, uint64_t pic_id, int which, SvtB200
     std::lock_guard<std::mutex> g(c->mu);
     auto it = c->pics.find(pic_id);
     if (it == c->pics.end() || !it->second.pl[which].buf) return SVTB200_ENOENT;
+    svtb200_pic_acquire(c, it->second); /* work queued on the compute stream after this call sees the uploaded contents */
     const DevPlane &d = it->second.pl[which];
     out->buf = d.buf; out->stride = d.stride; out->origin_x = d.ox; out->origin_y = d.oy; out->width = d.w; out->height = d.h;
     out->padded_height = d.rows;
+    return SVTB200_OK;
+}
+
+int svtb200_picture_touch(SvtB200Ctx *c, uint64_t pic_id) {
+    if (!c) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    auto it = c->pics.find(pic_id);
+    if (it == c->pics.end()) return SVTB200_ENOENT;
+    cudaSetDevice(c->device);
+    svtb200_pic_release(c, it->second);
     return SVTB200_OK;
 }
 
@@ -191,8 +277,10 @@ int svtb200_picture_release(SvtB200Ctx *c, uint64_t pic_id) {
     auto it = c->pics.find(pic_id);
     if (it == c->pics.end()) return SVTB200_ENOENT;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    cudaStreamSynchronize(c->up); cudaStreamSynchronize(c->stream);
     for (int i = 0; i < 3; i++) if (it->second.pl[i].buf) cudaFree(it->second.pl[i].buf);
+    if (it->second.ready) cudaEventDestroy(it->second.ready);
+    if (it->second.used) cudaEventDestroy(it->second.used);
     c->pics.erase(it);
     return SVTB200_OK;
 }

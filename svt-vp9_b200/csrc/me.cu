@@ -46,7 +46,11 @@ static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, c
         A.trace = (MeTraceDev *)c->me_trace;
     }
     SVTB200_CUDA_CHECK(c, cudaFuncSetAttribute(me_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    svtb200_pic_acquire(c, itc->second);
+    for (int l = 0; l < P->num_lists; l++) svtb200_pic_acquire(c, c->pics.find(ref_id[l])->second);
     me_sb_kernel<<<A.n_sb, ME_THREADS, L.total, c->stream>>>(A);
+    svtb200_pic_release(c, itc->second);
+    for (int l = 0; l < P->num_lists; l++) svtb200_pic_release(c, c->pics.find(ref_id[l])->second);
     c->launches++;
     SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return SVTB200_OK;
