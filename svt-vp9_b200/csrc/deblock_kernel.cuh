@@ -6,11 +6,13 @@
  * VP9 fixes the filtering order: super-blocks in raster order, and inside each the vertical edges of a plane
  * before its horizontal edges.  Filters reach 8 samples across super-block borders, so SB (r,c) depends on
  * (r,c-1) and (r-1,c+1): a wavefront.  One CTA per SB takes its SB index from an atomic ticket (so a CTA only
- * ever waits for CTAs that already hold a ticket, i.e. are running or done -- no deadlock), polls the two
- * dependency flags, stages the 72x72 luma and two 40x40 chroma tiles (SB + 8 samples of left/top context) in
- * shared memory with L1-bypassing loads, filters all three planes concurrently (one thread per sample row for
- * the vertical edges, one per sample column for the horizontal edges, edges sequential along the thread's line),
- * writes the tile back and publishes its flag after a device-scope fence.
+ * ever waits for CTAs that already hold a ticket, i.e. are running or done -- no deadlock).  The SB's own samples
+ * are untouched until its turn, so they are fetched into the shared-memory tiles (72x72 luma, two 40x40 chroma:
+ * SB + 8 samples of left/top context) BEFORE the CTA polls its two dependency flags; after the flags only the
+ * 8-sample left and top strips remain to be read (8-byte L1-bypassing loads).  All three planes are filtered
+ * concurrently (one thread per sample row for the vertical edges, one per sample column for the horizontal edges,
+ * edges sequential along the thread's line); the tile is written back with 8-byte stores and the flag published
+ * after a device-scope fence.
  *
  * The file also compiles as plain C++ under csrc/emu/cuda_emu.h for the CPU-side logic tests.
  */
@@ -37,15 +39,19 @@ struct LfKernelArgs {
 };
 
 #ifdef SVTB200_CPU_EMU
+#define LF_SHARED16 alignas(16) static
 static inline uint8_t lf_ldcg(const uint8_t *p) { return *p; }
+static inline uint2 lf_ldcg8(const uint8_t *p) { uint2 v; memcpy(&v, p, 8); return v; }
 static inline void lf_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void lf_sleep() {}
 static inline int lf_flag_load(const int32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void lf_flag_store(int32_t *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #else
+#define LF_SHARED16 __shared__ __align__(16)
 __device__ __forceinline__ uint8_t lf_ldcg(const uint8_t *p) { return __ldcg(p); }
+__device__ __forceinline__ uint2 lf_ldcg8(const uint8_t *p) { return __ldcg((const uint2 *)p); }
 __device__ __forceinline__ void lf_fence() { __threadfence(); }
-__device__ __forceinline__ void lf_sleep() { __nanosleep(64); }
+__device__ __forceinline__ void lf_sleep() { __nanosleep(20); }
 __device__ __forceinline__ int lf_flag_load(const int32_t *p) { return *(const volatile int32_t *)p; }
 __device__ __forceinline__ void lf_flag_store(int32_t *p, int v) { *(volatile int32_t *)p = v; }
 #endif
@@ -186,8 +192,52 @@ __device__ static void lf_horizontal_col(uint8_t *t, int col, int pitch, const L
     }
 }
 
+/* Copy the samples [x_lo, x_hi) x [y_lo, y_hi) (SB-relative; the tile keeps SB sample (0,0) at (8,8)) between the
+ * picture plane and the shared-memory tile.  vec: x bounds, plane pointer and stride are multiples of 8 -> 8-byte
+ * global accesses (the tile pitch is only 4-byte aligned: two words on the shared side). */
+template <int PITCH>
+__device__ __forceinline__ void lf_tile_load(uint8_t *tile, const uint8_t *g, int gstride, int x_lo, int x_hi, int y_lo, int y_hi, bool vec) {
+    if (x_hi <= x_lo || y_hi <= y_lo) return;
+    if (vec) {
+        const int nx = (x_hi - x_lo) >> 3, n = nx * (y_hi - y_lo);
+        for (int i = threadIdx.x; i < n; i += LF_THREADS) {
+            const int ry = i / nx, yy = y_lo + ry, xx = x_lo + (i - ry * nx) * 8;
+            const uint2 v = lf_ldcg8(g + (ptrdiff_t)yy * gstride + xx);
+            uint32_t *d = (uint32_t *)(tile + (yy + 8) * PITCH + xx + 8);
+            d[0] = v.x; d[1] = v.y;
+        }
+    } else {
+        const int nx = x_hi - x_lo, n = nx * (y_hi - y_lo);
+        for (int i = threadIdx.x; i < n; i += LF_THREADS) {
+            const int ry = i / nx, yy = y_lo + ry, xx = x_lo + (i - ry * nx);
+            tile[(yy + 8) * PITCH + xx + 8] = lf_ldcg(g + (ptrdiff_t)yy * gstride + xx);
+        }
+    }
+}
+template <int PITCH>
+__device__ __forceinline__ void lf_tile_store(const uint8_t *tile, uint8_t *g, int gstride, int x_lo, int x_hi, int y_lo, int y_hi, bool vec) {
+    if (x_hi <= x_lo || y_hi <= y_lo) return;
+    if (vec) {
+        const int nx = (x_hi - x_lo) >> 3, n = nx * (y_hi - y_lo);
+        for (int i = threadIdx.x; i < n; i += LF_THREADS) {
+            const int ry = i / nx, yy = y_lo + ry, xx = x_lo + (i - ry * nx) * 8;
+            const uint32_t *sp = (const uint32_t *)(tile + (yy + 8) * PITCH + xx + 8);
+            uint2 v; v.x = sp[0]; v.y = sp[1];
+            *(uint2 *)(g + (ptrdiff_t)yy * gstride + xx) = v;
+        }
+    } else {
+        const int nx = x_hi - x_lo, n = nx * (y_hi - y_lo);
+        for (int i = threadIdx.x; i < n; i += LF_THREADS) {
+            const int ry = i / nx, yy = y_lo + ry, xx = x_lo + (i - ry * nx);
+            g[(ptrdiff_t)yy * gstride + xx] = tile[(yy + 8) * PITCH + xx + 8];
+        }
+    }
+}
+
 __global__ void __launch_bounds__(LF_THREADS) lf_sb_kernel(const __grid_constant__ LfKernelArgs A) {
-    __shared__ uint8_t ty[72 * LF_YP], tu[40 * LF_CP], tv[40 * LF_CP];
+    LF_SHARED16 uint8_t ty[72 * LF_YP];
+    LF_SHARED16 uint8_t tu[40 * LF_CP];
+    LF_SHARED16 uint8_t tv[40 * LF_CP];
     __shared__ SvtB200LfMask m;
     __shared__ SvtB200LfThresh thr[64];
     __shared__ uint8_t lfl_uv[16];
@@ -199,6 +249,20 @@ __global__ void __launch_bounds__(LF_THREADS) lf_sb_kernel(const __grid_constant
     const int sb = sb_s;
     if (sb >= A.sbs_w * A.sbs_h) return;
     const int r = sb / A.sbs_w, c = sb - r * A.sbs_w, mi_row = r * 8, mi_col = c * 8;
+    const int rows = A.P.mi_rows - mi_row < 8 ? A.P.mi_rows - mi_row : 8;
+    const int cols = A.P.mi_cols - mi_col < 8 ? A.P.mi_cols - mi_col : 8;
+    const int x0 = mi_col * 8, y0 = mi_row * 8, cx0 = mi_col * 4, cy0 = mi_row * 4;
+    const int lw = cols * 8, lh = rows * 8, cw = cols * 4, ch = rows * 4;
+    const int lpx = x0 >= 8 ? 8 : 0, lpy = y0 >= 8 ? 8 : 0; /* context available left / above */
+    uint8_t *gy = A.y + (size_t)y0 * A.y_stride + x0, *gu = A.u + (size_t)cy0 * A.uv_stride + cx0, *gv = A.v + (size_t)cy0 * A.uv_stride + cx0;
+    const bool vy = (((uintptr_t)A.y | (uintptr_t)A.y_stride) & 7) == 0;
+    const bool vc = !A.P.y_only && ((((uintptr_t)A.u | (uintptr_t)A.v | (uintptr_t)A.uv_stride) & 7) == 0) && (cw & 7) == 0;
+    /* ---- the SB's own samples: nobody has modified them yet, fetch them while the dependencies finish */
+    lf_tile_load<LF_YP>(ty, gy, A.y_stride, 0, lw, 0, lh, vy);
+    if (!A.P.y_only) {
+        lf_tile_load<LF_CP>(tu, gu, A.uv_stride, 0, cw, 0, ch, vc);
+        lf_tile_load<LF_CP>(tv, gv, A.uv_stride, 0, cw, 0, ch, vc);
+    }
     if (t == 0) {
         m = A.lfm[c + r * A.lfm_stride];
         lf_adjust_mask(A.P.mi_rows, A.P.mi_cols, mi_row, mi_col, &m);
@@ -209,23 +273,14 @@ __global__ void __launch_bounds__(LF_THREADS) lf_sb_kernel(const __grid_constant
         lf_fence();
     }
     __syncthreads();
-    const int rows = A.P.mi_rows - mi_row < 8 ? A.P.mi_rows - mi_row : 8;
-    const int cols = A.P.mi_cols - mi_col < 8 ? A.P.mi_cols - mi_col : 8;
-    const int x0 = mi_col * 8, y0 = mi_row * 8, cx0 = mi_col * 4, cy0 = mi_row * 4;
-    const int lw = cols * 8, lh = rows * 8, cw = cols * 4, ch = rows * 4;
-    const int lpx = x0 >= 8 ? 8 : 0, lpy = y0 >= 8 ? 8 : 0; /* context available left / above */
-    /* ---- stage the tiles (SB + 8 samples of left / top context), bypassing L1 */
-    for (int i = t; i < (lh + lpy) * (lw + lpx); i += LF_THREADS) {
-        const int yy = i / (lw + lpx) - lpy, xx = i - (yy + lpy) * (lw + lpx) - lpx;
-        ty[(yy + 8) * LF_YP + xx + 8] = lf_ldcg(A.y + (size_t)(y0 + yy) * A.y_stride + x0 + xx);
-    }
+    /* ---- the 8-sample strips the neighbours have just finished: left of the SB, and above it (with the corner) */
+    lf_tile_load<LF_YP>(ty, gy, A.y_stride, -lpx, 0, 0, lh, vy);
+    lf_tile_load<LF_YP>(ty, gy, A.y_stride, -lpx, lw, -lpy, 0, vy);
     if (!A.P.y_only) {
-        for (int i = t; i < (ch + lpy) * (cw + lpx); i += LF_THREADS) {
-            const int yy = i / (cw + lpx) - lpy, xx = i - (yy + lpy) * (cw + lpx) - lpx;
-            const size_t g = (size_t)(cy0 + yy) * A.uv_stride + cx0 + xx;
-            tu[(yy + 8) * LF_CP + xx + 8] = lf_ldcg(A.u + g);
-            tv[(yy + 8) * LF_CP + xx + 8] = lf_ldcg(A.v + g);
-        }
+        lf_tile_load<LF_CP>(tu, gu, A.uv_stride, -lpx, 0, 0, ch, vc);
+        lf_tile_load<LF_CP>(tu, gu, A.uv_stride, -lpx, cw, -lpy, 0, vc);
+        lf_tile_load<LF_CP>(tv, gv, A.uv_stride, -lpx, 0, 0, ch, vc);
+        lf_tile_load<LF_CP>(tv, gv, A.uv_stride, -lpx, cw, -lpy, 0, vc);
     }
     __syncthreads();
     LfPlaneMasks MY, MC;
@@ -244,20 +299,15 @@ __global__ void __launch_bounds__(LF_THREADS) lf_sb_kernel(const __grid_constant
     if (t < 64) { if (t < lw) lf_horizontal_col(ty + 8 * LF_YP + 8 + t, t, LF_YP, MY, thr); }
     else if (!A.P.y_only) { const int q = (t - 64) & 31; if (q < cw) lf_horizontal_col((t < 96 ? tu : tv) + 8 * LF_CP + 8 + q, q, LF_CP, MC, thr); }
     __syncthreads();
-    /* ---- write back everything this SB may have changed (its own samples + the 8-sample left / top strips) */
-    for (int i = t; i < (lh + lpy) * (lw + lpx); i += LF_THREADS) {
-        const int yy = i / (lw + lpx) - lpy, xx = i - (yy + lpy) * (lw + lpx) - lpx;
-        if (yy < 0 && xx < 0) continue;
-        A.y[(size_t)(y0 + yy) * A.y_stride + x0 + xx] = ty[(yy + 8) * LF_YP + xx + 8];
-    }
+    /* ---- write back everything this SB may have changed (its own samples + the 8-sample left / top strips; the
+     * corner is never modified) */
+    lf_tile_store<LF_YP>(ty, gy, A.y_stride, -lpx, lw, 0, lh, vy);
+    lf_tile_store<LF_YP>(ty, gy, A.y_stride, 0, lw, -lpy, 0, vy);
     if (!A.P.y_only) {
-        for (int i = t; i < (ch + lpy) * (cw + lpx); i += LF_THREADS) {
-            const int yy = i / (cw + lpx) - lpy, xx = i - (yy + lpy) * (cw + lpx) - lpx;
-            if (yy < 0 && xx < 0) continue;
-            const size_t g = (size_t)(cy0 + yy) * A.uv_stride + cx0 + xx;
-            A.u[g] = tu[(yy + 8) * LF_CP + xx + 8];
-            A.v[g] = tv[(yy + 8) * LF_CP + xx + 8];
-        }
+        lf_tile_store<LF_CP>(tu, gu, A.uv_stride, -lpx, cw, 0, ch, vc);
+        lf_tile_store<LF_CP>(tu, gu, A.uv_stride, 0, cw, -lpy, 0, vc);
+        lf_tile_store<LF_CP>(tv, gv, A.uv_stride, -lpx, cw, 0, ch, vc);
+        lf_tile_store<LF_CP>(tv, gv, A.uv_stride, 0, cw, -lpy, 0, vc);
     }
     lf_fence();
     __syncthreads();

@@ -20,6 +20,7 @@
 #include <thread>
 #include <vector>
 
+struct uint2 { unsigned x, y; };
 struct uint3_emu { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 extern thread_local uint3_emu threadIdx, blockIdx;
