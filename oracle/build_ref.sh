@@ -56,3 +56,14 @@ echo "build_ref: seam-check flavour ok"
 gcc $CF -fcommon $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/ref_path_driver.c -o $OUT/ref_path_driver.o
 gcc -shared -o $OUT/libSvtVp9Enc_refdrv.so $OUT/obj/*.o $OUT/ref_path_driver.o -lpthread -lm -Wl,--no-undefined
 echo "build_ref: path driver ok"
+
+# ---- drop-in flavour: the same reference objects with the two seam functions bound to libsvtvp9_b200.so
+# (svt-vp9_b200/shim/svtb200_wrap.c); used by the encoder-level parity test on the GPU box
+if [ -f $HERE/../svt-vp9_b200/libsvtvp9_b200.so ]; then
+  gcc $CF $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/../svt-vp9_b200/shim/svtb200_wrap.c -o $OUT/svtb200_wrap.o
+  gcc -shared -o $OUT/libSvtVp9Enc_b200.so $OUT/obj/*.o $OUT/svtb200_wrap.o -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm \
+      -Wl,--wrap=motion_estimate_sb -Wl,--wrap=eb_vp9_loop_filter_frame -Wl,-rpath,'$ORIGIN/../../svt-vp9_b200'
+  gcc -std=gnu99 -O2 -w -I$OUT/inc -I$REF/Source/API $REF/Source/App/*.c -o $OUT/SvtVp9EncApp_b200 \
+      -L$OUT -lSvtVp9Enc_b200 -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../svt-vp9_b200'
+  echo "build_ref: drop-in flavour ok"
+fi

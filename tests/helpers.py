@@ -505,3 +505,17 @@ def refdrv_deblock(P, y, u, v, lfm, lfm_stride, thr, pad=16):
     L.refdrv_deblock(C.byref(P), yy.ctypes.data, yy.shape[1], uu.ctypes.data, vv.ctypes.data, uu.shape[1],
                      np.ascontiguousarray(lfm).ctypes.data, lfm_stride, np.ascontiguousarray(thr).ctypes.data)
     return yy[:y.shape[0], :y.shape[1]], uu[:u.shape[0], :u.shape[1]], vv[:v.shape[0], :v.shape[1]]
+
+
+def cudart_path():
+    """libcudart.so.12 that libsvtvp9_b200.so resolves to in this image (for child processes that are not python)."""
+    import glob
+    for pat in ("/usr/local/cuda/lib64/libcudart.so.12*", os.path.join(os.path.dirname(os.__file__), "site-packages", "nvidia", "cuda_runtime", "lib", "libcudart.so.12*")):
+        hits = sorted(glob.glob(pat))
+        if hits:
+            return hits[0]
+    try:
+        import nvidia.cuda_runtime as m
+        return os.path.join(os.path.dirname(m.__file__), "lib", "libcudart.so.12")
+    except Exception:
+        return ""

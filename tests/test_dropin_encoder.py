@@ -1,0 +1,64 @@
+"""Encoder-level drop-in check: the UNMODIFIED reference encoder objects with motion_estimate_sb() and
+eb_vp9_loop_filter_frame() bound to libsvtvp9_b200.so (svt-vp9_b200/shim/svtb200_wrap.c, linked with -Wl,--wrap by
+oracle/build_ref.sh into oracle/_ref/SvtVp9EncApp_b200) must write the same bitstream, byte for byte, as the reference
+application built from the same objects (oracle/_ref/SvtVp9EncApp_ref).  Both binaries are built where /root/reference
+exists and travel to the GPU box; the test is skipped where they are absent."""
+import hashlib
+import os
+import subprocess
+import tempfile
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+REF_DIR = os.path.join(H.ROOT, "oracle", "_ref")
+APP_REF, APP_B200 = os.path.join(REF_DIR, "SvtVp9EncApp_ref"), os.path.join(REF_DIR, "SvtVp9EncApp_b200")
+pytestmark = pytest.mark.skipif(not (os.path.exists(APP_REF) and os.path.exists(APP_B200)), reason="oracle/_ref applications not built")
+
+
+def _write_yuv(path, w, h, n, seed):
+    clip = H.synth.make_clip(w, h, n, seed=seed, k=3, g=4, a=5, b=3, m=32, noise=2)
+    with open(path, "wb") as f:
+        for y, u, v in clip:
+            f.write(y.tobytes()); f.write(u.tobytes()); f.write(v.tobytes())
+
+
+def _encode(app, yuv, out, w, h, n, mode, extra_env=None, extra_args=()):
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = ":".join(p for p in (os.path.dirname(H.cudart_path()), env.get("LD_LIBRARY_PATH", "")) if p)
+    env.update(extra_env or {})
+    cmd = [app, "-i", yuv, "-w", str(w), "-h", str(h), "-n", str(n), "-enc-mode", str(mode), "-tune", "1", "-q", "45", "-b", out] + list(extra_args)
+    r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=900)
+    assert os.path.exists(out) and os.path.getsize(out) > 0, r.stdout.decode(errors="replace")[-2000:]
+    return hashlib.md5(open(out, "rb").read()).hexdigest()
+
+
+def _report(path):
+    return dict((l.split()[0], int(l.split()[1])) for l in open(path) if len(l.split()) == 2)
+
+
+def test_wrapper_falls_back_to_reference_kernels_without_a_gpu():
+    """SVT_VP9_GPU=off: every call goes to __real_*; the bitstream must equal the reference application's."""
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "clip.yuv")
+        _write_yuv(yuv, 192, 128, 10, 7)
+        a = _encode(APP_REF, yuv, os.path.join(d, "ref.ivf"), 192, 128, 10, 8)
+        b = _encode(APP_B200, yuv, os.path.join(d, "b200.ivf"), 192, 128, 10, 8, {"SVT_VP9_GPU": "off", "SVT_VP9_GPU_REPORT": os.path.join(d, "rep.txt")})
+        assert a == b
+        assert _report(os.path.join(d, "rep.txt"))["me_pictures"] == 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,mode", [(640, 384, 34, 8), (448, 256, 20, 3), (1920, 1088, 18, 8)], ids=["640x384-m8", "448x256-m3", "1920x1088-m8"])
+def test_encoder_with_gpu_hot_path_writes_the_reference_bitstream(w, h, n, mode):
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "clip.yuv")
+        _write_yuv(yuv, w, h, n, 11 + mode)
+        a = _encode(APP_REF, yuv, os.path.join(d, "ref.ivf"), w, h, n, mode)
+        rep = os.path.join(d, "rep.txt")
+        b = _encode(APP_B200, yuv, os.path.join(d, "b200.ivf"), w, h, n, mode, {"SVT_VP9_GPU": "0", "SVT_VP9_GPU_REPORT": rep, "SVT_VP9_GPU_VERBOSE": "1"})
+        r = _report(rep)
+        assert r["state"] == 1 and r["me_pictures"] >= n - 2 and r["fallbacks"] == 0 and r["launches"] > 0, r   # the GPU did the work
+        assert a == b, "bitstreams differ (%s)" % r
