@@ -271,14 +271,13 @@ __device__ static void me_stage_window(uint8_t *win, int pitch, const MePlaneDev
     if ((pl.stride & 3) == 0 && ((uintptr_t)pl.buf & 3) == 0) {
         const uint32_t sh = (uint32_t)((uintptr_t)g & 3) * 8;
         const uint8_t *ga = g - (sh >> 3);
-        const int nw = ((cols + 3) >> 2) + 1, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-        for (int y = warp; y < rows; y += ME_THREADS / 32) {
-            const uint32_t *gr = (const uint32_t *)(ga + (ptrdiff_t)y * pl.stride);
-            uint32_t *wr = (uint32_t *)(win + y * pitch);
-            for (int x = lane; x < nw; x += 32) {
-                const uint32_t lo = __ldg(gr + x), hi = sh ? __ldg(gr + x + 1) : 0u;
-                wr[x] = __funnelshift_r(lo, hi, sh);
-            }
+        const int nw = ((cols + 3) >> 2) + 1, total = nw * rows;
+        const uint32_t rcp = 0xffffffffu / (uint32_t)nw + 1u; /* ceil(2^32 / nw): __umulhi(i, rcp) == i / nw while i * nw < 2^32 */
+        for (int i = threadIdx.x; i < total; i += ME_THREADS) {
+            const int y = (int)__umulhi((uint32_t)i, rcp), x = i - y * nw;
+            const uint32_t *gr = (const uint32_t *)(ga + (ptrdiff_t)y * pl.stride) + x;
+            const uint32_t lo = __ldg(gr), hi = sh ? __ldg(gr + 1) : 0u;
+            ((uint32_t *)(win + y * pitch))[x] = __funnelshift_r(lo, hi, sh);
         }
     } else {
         const int cw = cols + 4;
@@ -346,9 +345,10 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
     } else if (npos >= ME_THREADS) {
         /* 4 horizontally adjacent candidates per thread share every window word */
         const int ngx = (saw + 3) >> 2, ngroups = ngx * nrows, sp32 = st->s_pitch >> 2, wp32 = st->w_pitch >> 2;
+        const uint32_t rcp = 0xffffffffu / (uint32_t)ngx + 1u; /* __umulhi(g, rcp) == g / ngx */
         unsigned long long best = ~0ull;
         for (int g = threadIdx.x; g < ngroups; g += ME_THREADS) {
-            const int ys = g / ngx, gx = g - ys * ngx;
+            const int ys = (int)__umulhi((uint32_t)g, rcp), gx = g - ys * ngx;
             const uint32_t *wrow0 = (const uint32_t *)win + ys * wp32 + gx;
             uint32_t acc[4] = {0, 0, 0, 0};
             if (wwords == 4) me_search4<4>((const uint32_t *)sblk, sp32, wrow0, wp32, h, acc);
@@ -451,44 +451,46 @@ __device__ __forceinline__ void me_set_window(MeSbState *st, int w, int h, int w
  * ------------------------------------------------------------------------------------------- */
 __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpitch, MeSbState *st, int list,
                                   unsigned long long *pu_key /* [85] smem */, uint16_t *s8 /* [CHUNK][64] */,
-                                  uint16_t *s16 /* [CHUNK][16] */, uint32_t *s32 /* [CHUNK][4] */) {
-    const int saw = st->saw[list], sah = st->sah[list], npos = saw * sah;
+                                  uint16_t *s16 /* [CHUNK][16] */, uint32_t *s32 /* [CHUNK][4] */, uint32_t *spos /* [CHUNK] */) {
+    const int saw = st->saw[list], sah = st->sah[list];
     const int tail_from = saw & ~7; /* columns handled by the reference's one-position routine */
+    /* candidates are taken four at a time along x (one group shares every window word); a chunk is ME_CHUNK/4 groups */
+    const int ngx = (saw + 3) >> 2, ngroups = ngx * sah;
     for (int i = threadIdx.x; i < 85; i += ME_THREADS) pu_key[i] = ((unsigned long long)ME_MAX_SAD << 32) | 0xffffffffu;
     __syncthreads();
     const int t = threadIdx.x;
-    for (int c0 = 0; c0 < npos; c0 += ME_CHUNK) {
-        const int cn = min(ME_CHUNK, npos - c0);
+    for (int g0 = 0; g0 < ngroups; g0 += ME_CHUNK / 4) {
+        const int gn = min(ME_CHUNK / 4, ngroups - g0), cn = gn * 4;
         /* phase 1: 8x8 SADs (rows 0,2,4,6), z-ordered so that 4 consecutive entries form a 16x16 */
         {
-            const int z8 = t & 63, lane = t >> 6;
-            const int z16 = z8 >> 2, k = z8 & 3;
+            const int z8 = t & 63, z16 = z8 >> 2, k = z8 & 3;
             /* raster position of the 16x16 block with internal index z16 */
             const int b16 = (z16 & 1) | ((z16 & 4) >> 1) | ((z16 & 2) << 1) | (z16 & 8);
             const int bx = (b16 & 3) * 16 + (k & 1) * 8, by = (b16 >> 2) * 16 + (k >> 1) * 8;
             const uint32_t *sp = (const uint32_t *)(src + by * ME_SB + bx);
-            const uint32_t s0 = sp[0], s1 = sp[1], s2 = sp[32], s3 = sp[33], s4 = sp[64], s5 = sp[65], s6 = sp[96], s7 = sp[97];
-            int pos = c0 + lane, ys = pos / saw, xs = pos - ys * saw;
-            for (int pp = lane; pp < cn; pp += 4) {
+            const int p2 = wpitch >> 1; /* two rows, in words */
+            for (int gl = t >> 6; gl < gn; gl += 4) {
+                const int g = g0 + gl, ys = g / ngx, gx = g - ys * ngx;
                 /* the reference's single-position routine matches 16x16 blocks 12 and 13 sixteen
                  * samples further right (EbMotionEstimation.c:855-856); reproduced */
-                const int skew = (xs >= tail_from && (z16 == 12 || z16 == 13)) ? 16 : 0;
-                const int xo = xs + bx + skew;
-                const uint32_t *wp = (const uint32_t *)(rb + (ys + by) * wpitch + (xo & ~3));
-                const uint32_t sh = (uint32_t)(xo & 3) * 8;
-                const int p2 = wpitch >> 1; /* two rows, in words */
-                uint32_t acc = 0;
-                acc = me_absdiff_acc(__funnelshift_r(wp[0], wp[1], sh), s0, acc);
-                acc = me_absdiff_acc(__funnelshift_r(wp[1], wp[2], sh), s1, acc);
-                acc = me_absdiff_acc(__funnelshift_r(wp[p2], wp[p2 + 1], sh), s2, acc);
-                acc = me_absdiff_acc(__funnelshift_r(wp[p2 + 1], wp[p2 + 2], sh), s3, acc);
-                acc = me_absdiff_acc(__funnelshift_r(wp[2 * p2], wp[2 * p2 + 1], sh), s4, acc);
-                acc = me_absdiff_acc(__funnelshift_r(wp[2 * p2 + 1], wp[2 * p2 + 2], sh), s5, acc);
-                acc = me_absdiff_acc(__funnelshift_r(wp[3 * p2], wp[3 * p2 + 1], sh), s6, acc);
-                acc = me_absdiff_acc(__funnelshift_r(wp[3 * p2 + 1], wp[3 * p2 + 2], sh), s7, acc);
-                s8[pp * 64 + z8] = (uint16_t)acc;
-                xs += 4;
-                while (xs >= saw) { xs -= saw; ys++; }
+                const int skew = (4 * gx >= tail_from && (z16 == 12 || z16 == 13)) ? 16 : 0;
+                const uint32_t *wp = (const uint32_t *)(rb + (ys + by) * wpitch + 4 * gx + bx + skew);
+                uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const uint32_t w0 = wp[r * p2], w1 = wp[r * p2 + 1], w2 = wp[r * p2 + 2];
+                    const uint32_t s0 = sp[r * 32], s1 = sp[r * 32 + 1];
+                    a0 = me_absdiff_acc(w0, s0, a0); a0 = me_absdiff_acc(w1, s1, a0);
+                    a1 = me_absdiff_acc(__funnelshift_r(w0, w1, 8), s0, a1); a1 = me_absdiff_acc(__funnelshift_r(w1, w2, 8), s1, a1);
+                    a2 = me_absdiff_acc(__funnelshift_r(w0, w1, 16), s0, a2); a2 = me_absdiff_acc(__funnelshift_r(w1, w2, 16), s1, a2);
+                    a3 = me_absdiff_acc(__funnelshift_r(w0, w1, 24), s0, a3); a3 = me_absdiff_acc(__funnelshift_r(w1, w2, 24), s1, a3);
+                }
+                uint16_t *o = s8 + (gl * 4) * 64 + z8;
+                o[0] = (uint16_t)a0; o[64] = (uint16_t)a1; o[128] = (uint16_t)a2; o[192] = (uint16_t)a3;
+            }
+            if (t < cn) { /* raster index of every slot of the chunk (invalid beyond the right edge of the area) */
+                const int g = g0 + (t >> 2), ys = g / ngx, xs = 4 * (g - ys * ngx) + (t & 3);
+                spos[t] = xs < saw ? (uint32_t)(ys * saw + xs) : 0xffffffffu;
             }
         }
         __syncthreads();
@@ -497,18 +499,18 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
             const int z8 = t & 63, lane = t >> 6;
             unsigned long long best = ~0ull;
             for (int pp = lane; pp < cn; pp += 4) {
-                const uint32_t v = 2u * s8[pp * 64 + z8];
-                if (v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | (uint32_t)(c0 + pp); if (key < best) best = key; }
+                const uint32_t v = 2u * s8[pp * 64 + z8], pos = spos[pp];
+                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best) best = key; }
             }
             if (best != ~0ull) atomicMin(&pu_key[21 + z8], best);
             const int z16 = t & 15, l16 = t >> 4;
             best = ~0ull;
             for (int pp = l16; pp < cn; pp += 16) {
                 const uint16_t *q = s8 + pp * 64 + z16 * 4;
-                const uint32_t sum = (uint32_t)q[0] + q[1] + q[2] + q[3];
+                const uint32_t sum = (uint32_t)q[0] + q[1] + q[2] + q[3], pos = spos[pp];
                 s16[pp * 16 + z16] = (uint16_t)sum;
                 const uint32_t v = 2u * sum;
-                if (v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | (uint32_t)(c0 + pp); if (key < best) best = key; }
+                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best) best = key; }
             }
             if (best != ~0ull) atomicMin(&pu_key[5 + z16], best);
         }
@@ -519,19 +521,19 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
             unsigned long long best = ~0ull;
             for (int pp = l32; pp < cn; pp += 64) {
                 const uint16_t *q = s16 + pp * 16 + q32 * 4;
-                const uint32_t sum = (uint32_t)q[0] + q[1] + q[2] + q[3];
+                const uint32_t sum = (uint32_t)q[0] + q[1] + q[2] + q[3], pos = spos[pp];
                 s32[pp * 4 + q32] = sum;
                 const uint32_t v = 2u * sum;
-                if (v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | (uint32_t)(c0 + pp); if (key < best) best = key; }
+                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best) best = key; }
             }
             if (best != ~0ull) atomicMin(&pu_key[1 + q32], best);
         }
         __syncthreads();
         /* phase 4: 64x64 */
-        if (t < cn) {
+        if (t < cn && spos[t] != 0xffffffffu) {
             const uint32_t *q = s32 + t * 4;
             const uint32_t v = 2u * (q[0] + q[1] + q[2] + q[3]);
-            if (v < ME_MAX_SAD) atomicMin(&pu_key[0], ((unsigned long long)v << 32) | (uint32_t)(c0 + t));
+            if (v < ME_MAX_SAD) atomicMin(&pu_key[0], ((unsigned long long)v << 32) | spos[t]);
         }
         __syncthreads();
     }
@@ -599,16 +601,17 @@ __device__ static void me_interp(const uint8_t *rb, int rp, const MeSbState *st,
     const int W = st->saw[list] + ME_SB - 1, H = st->sah[list] + ME_SB - 1;
     const int wasm = (W + 2 + 7) & ~7, is = st->istride[list];
     const int nw = wasm >> 2, is32 = is >> 2;
+    const uint32_t rcp = 0xffffffffu / (uint32_t)nw + 1u; /* __umulhi(i, rcp) == i / nw */
     /* b: one word of four outputs per step */
     for (int it = threadIdx.x; it < nw * (H + 4); it += ME_THREADS) {
-        const int y = it / nw, i = it - y * nw;
+        const int y = (int)__umulhi((uint32_t)it, rcp), i = it - y * nw;
         const uint32_t *r = (const uint32_t *)(rb + (y - 2) * rp) + i;
         ((uint32_t *)pb)[y * is32 + i] = me_hfilt4(r[-1], r[0], r[1]);
     }
     /* h: a thread walks down a word column with a rolling window of four rows */
     const int nseg = nw >= ME_THREADS ? 1 : ME_THREADS / nw, per = (H + 1 + nseg - 1) / nseg;
     for (int it = threadIdx.x; it < nw * nseg; it += ME_THREADS) {
-        const int seg = it / nw, i = it - seg * nw;
+        const int seg = (int)__umulhi((uint32_t)it, rcp), i = it - seg * nw;
         const int ya = seg * per, yb = min(H + 1, ya + per);
         if (ya < yb) {
             const uint8_t *r = rb + (ya - 2) * rp + 4 * i - 1;
@@ -623,7 +626,7 @@ __device__ static void me_interp(const uint8_t *rb, int rp, const MeSbState *st,
     }
     __syncthreads();
     for (int it = threadIdx.x; it < nw * nseg; it += ME_THREADS) {
-        const int seg = it / nw, i = it - seg * nw;
+        const int seg = (int)__umulhi((uint32_t)it, rcp), i = it - seg * nw;
         const int ya = seg * per, yb = min(H + 1, ya + per);
         if (ya < yb) {
             const uint32_t *q = (const uint32_t *)pb + ya * is32 + i;
@@ -1221,7 +1224,7 @@ __global__ void __launch_bounds__(ME_THREADS, 3) me_sb_kernel(const __grid_const
         me_stage_window(win, fpp, rp, st->ox + st->sa_ox[list] - ME_HALO_X, st->oy + st->sa_oy[list] - ME_HALO_Y,
                         st->saw[list] + ME_SB - 1 + 16 + ME_HALO_X, me_fp_rows(st->sah[list]));
         __syncthreads();
-        me_fullpel(src, rb, fpp, st, list, pu_key, s8, s16, s32);
+        me_fullpel(src, rb, fpp, st, list, pu_key, s8, s16, s32, posacc);
         if (t < 85) {
             const unsigned long long k = pu_key[t];
             const uint32_t pos = (uint32_t)(k & 0xffffffffu);
