@@ -376,8 +376,8 @@ def main():
         return pl
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_ms = {"me_sb_kernel": 0.0, "txq_kernel": 0.0, "lf_sb_kernel": 0.0}
-    alg = {"me_sb_kernel": 0, "txq_kernel": 0, "lf_sb_kernel": 0}
+    stage_ms = {"me_sb_kernel": 0.0, "txq_kernel": 0.0, "lf_row_kernel": 0.0}
+    alg = {"me_sb_kernel": 0, "txq_kernel": 0, "lf_row_kernel": 0}
     marks = []
 
     def kernels(i, timed, slot=0):
@@ -476,7 +476,7 @@ def main():
         stage_ms["me_sb_kernel"] += e[0].elapsed_time(e[1]); alg["me_sb_kernel"] += me_bytes(P); n_me += 1
         stage_ms["txq_kernel"] += e[1].elapsed_time(e[2]); alg["txq_kernel"] += txq_bytes()
         if n == 16:
-            stage_ms["lf_sb_kernel"] += e[2].elapsed_time(e[3]); alg["lf_sb_kernel"] += lf_bytes()
+            stage_ms["lf_row_kernel"] += e[2].elapsed_time(e[3]); alg["lf_row_kernel"] += lf_bytes()
     for i in range(min(args.warmup, 4)):
         step_e2e(i)
     barrier()

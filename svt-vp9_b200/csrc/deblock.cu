@@ -14,7 +14,8 @@ static int lf_launch(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int ys
     memset(&A, 0, sizeof(A));
     A.P = *p; A.y = y; A.u = u; A.v = v; A.y_stride = ys; A.uv_stride = cs; A.lfm = lfm; A.lfm_stride = lfm_stride; A.thr = thr;
     A.sbs_w = (p->mi_cols + 7) >> 3; A.sbs_h = (p->mi_rows + 7) >> 3;
-    const size_t n = (size_t)A.sbs_w * A.sbs_h;
+    if (A.sbs_w > 1023) return SVTB200_EINVAL;
+    const size_t n = (size_t)A.sbs_h; /* one progress word per super-block row */
     LfScratch *S;
     { std::lock_guard<std::mutex> g(g_lf_mu); S = &g_lf[c]; }
     if (S->done_n < n) {
@@ -27,7 +28,9 @@ static int lf_launch(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int ys
     S->gen++;
     A.ticket = S->ticket; A.done = S->done; A.gen = S->gen;
     SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->ticket, 0, 4, c->stream));
-    lf_sb_kernel<<<(unsigned)n, LF_THREADS, 0, c->stream>>>(A);
+    const size_t dyn = (size_t)A.sbs_w * (sizeof(SvtB200LfMask) + 16);
+    if (dyn > 48 * 1024) SVTB200_CUDA_CHECK(c, cudaFuncSetAttribute(lf_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    lf_row_kernel<<<(unsigned)n, LF_THREADS, dyn, c->stream>>>(A);
     c->launches++;
     SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return SVTB200_OK;

@@ -5,14 +5,16 @@
  *
  * VP9 fixes the filtering order: super-blocks in raster order, and inside each the vertical edges of a plane
  * before its horizontal edges.  Filters reach 8 samples across super-block borders, so SB (r,c) depends on
- * (r,c-1) and (r-1,c+1): a wavefront.  One CTA per SB takes its SB index from an atomic ticket (so a CTA only
- * ever waits for CTAs that already hold a ticket, i.e. are running or done -- no deadlock).  The SB's own samples
- * are untouched until its turn, so they are fetched into the shared-memory tiles (72x72 luma, two 40x40 chroma:
- * SB + 8 samples of left/top context) BEFORE the CTA polls its two dependency flags; after the flags only the
- * 8-sample left and top strips remain to be read (8-byte L1-bypassing loads).  All three planes are filtered
- * concurrently (one thread per sample row for the vertical edges, one per sample column for the horizontal edges,
- * edges sequential along the thread's line); the tile is written back with 8-byte stores and the flag published
- * after a device-scope fence.
+ * (r,c-1) and (r-1,c+1): a wavefront of sbs_w + 2*(sbs_h-1) dependent steps, i.e. a latency chain.
+ *
+ * One persistent CTA (256 threads) per super-block ROW walks its row left to right, so the left dependency never
+ * leaves shared memory: the right 8 columns of tile c become the left context of tile c+1 by a shared-memory copy.
+ * Warps 0-3 filter (one thread per sample row for the vertical edges, one per sample column for the horizontal
+ * edges of luma / U / V, edges sequential along the thread's line); warps 4-7 move data: while tile c is filtered
+ * they write tile c-1 back (8-byte stores), publish the row's progress after a device-scope fence, and fetch tile
+ * c+1 (its own samples, which nobody has modified yet, and the 8-sample strip above it once the row above has
+ * progressed far enough) with 8-byte L1-bypassing loads into the other tile buffer.  Rows take their index from an
+ * atomic ticket, so a CTA only ever waits for CTAs that already run -- no deadlock.  Two CTA barriers per SB.
  *
  * The file also compiles as plain C++ under csrc/emu/cuda_emu.h for the CPU-side logic tests.
  */
@@ -21,7 +23,8 @@
 #include <stdint.h>
 #include "../../include/svtb200.h"
 
-#define LF_THREADS 128
+#define LF_THREADS 256       /* 128 filtering + 128 data-moving threads */
+#define LF_HALF 128
 #define LF_YP 76 /* luma tile pitch (odd number of words: conflict-free column access) */
 #define LF_CP 44 /* chroma tile pitch */
 
@@ -33,25 +36,29 @@ struct LfKernelArgs {
     int32_t  lfm_stride;
     const SvtB200LfThresh *thr; /* [64] */
     int32_t *ticket;            /* zeroed before the launch */
-    int32_t *done;              /* one flag per SB; a SB is finished when its flag == gen */
+    int32_t *done;              /* one word per SB row: (gen << 10) | number of SBs of the row that are final in memory */
     int32_t  gen;
     int32_t  sbs_w, sbs_h;
 };
 
 #ifdef SVTB200_CPU_EMU
 #define LF_SHARED16 alignas(16) static
+#define LF_DYN_SMEM(name) uint8_t *name = emu_dyn_smem
 static inline uint8_t lf_ldcg(const uint8_t *p) { return *p; }
 static inline uint2 lf_ldcg8(const uint8_t *p) { uint2 v; memcpy(&v, p, 8); return v; }
 static inline void lf_fence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 static inline void lf_sleep() {}
+static inline void lf_sync_movers() { emu_sync_upper_half(); }
 static inline int lf_flag_load(const int32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void lf_flag_store(int32_t *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #else
 #define LF_SHARED16 __shared__ __align__(16)
+#define LF_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 __device__ __forceinline__ uint8_t lf_ldcg(const uint8_t *p) { return __ldcg(p); }
 __device__ __forceinline__ uint2 lf_ldcg8(const uint8_t *p) { return __ldcg((const uint2 *)p); }
 __device__ __forceinline__ void lf_fence() { __threadfence(); }
 __device__ __forceinline__ void lf_sleep() { __nanosleep(20); }
+__device__ __forceinline__ void lf_sync_movers() { asm volatile("bar.sync 1, 128;" ::: "memory"); } /* threads 128..255 */
 __device__ __forceinline__ int lf_flag_load(const int32_t *p) { return *(const volatile int32_t *)p; }
 __device__ __forceinline__ void lf_flag_store(int32_t *p, int v) { *(volatile int32_t *)p = v; }
 #endif
@@ -196,11 +203,12 @@ __device__ static void lf_horizontal_col(uint8_t *t, int col, int pitch, const L
  * picture plane and the shared-memory tile.  vec: x bounds, plane pointer and stride are multiples of 8 -> 8-byte
  * global accesses (the tile pitch is only 4-byte aligned: two words on the shared side). */
 template <int PITCH>
-__device__ __forceinline__ void lf_tile_load(uint8_t *tile, const uint8_t *g, int gstride, int x_lo, int x_hi, int y_lo, int y_hi, bool vec) {
+__device__ __forceinline__ void lf_tile_load(uint8_t *tile, const uint8_t *g, int gstride, int x_lo, int x_hi, int y_lo, int y_hi, bool vec, int tid,
+                                             int nthr) {
     if (x_hi <= x_lo || y_hi <= y_lo) return;
     if (vec) {
         const int nx = (x_hi - x_lo) >> 3, n = nx * (y_hi - y_lo);
-        for (int i = threadIdx.x; i < n; i += LF_THREADS) {
+        for (int i = tid; i < n; i += nthr) {
             const int ry = i / nx, yy = y_lo + ry, xx = x_lo + (i - ry * nx) * 8;
             const uint2 v = lf_ldcg8(g + (ptrdiff_t)yy * gstride + xx);
             uint32_t *d = (uint32_t *)(tile + (yy + 8) * PITCH + xx + 8);
@@ -208,18 +216,19 @@ __device__ __forceinline__ void lf_tile_load(uint8_t *tile, const uint8_t *g, in
         }
     } else {
         const int nx = x_hi - x_lo, n = nx * (y_hi - y_lo);
-        for (int i = threadIdx.x; i < n; i += LF_THREADS) {
+        for (int i = tid; i < n; i += nthr) {
             const int ry = i / nx, yy = y_lo + ry, xx = x_lo + (i - ry * nx);
             tile[(yy + 8) * PITCH + xx + 8] = lf_ldcg(g + (ptrdiff_t)yy * gstride + xx);
         }
     }
 }
-template <int PITCH>
-__device__ __forceinline__ void lf_tile_store(const uint8_t *tile, uint8_t *g, int gstride, int x_lo, int x_hi, int y_lo, int y_hi, bool vec) {
+template <int PITCH, int NX = 0 /* (x_hi - x_lo) / 8 when known at compile time */>
+__device__ __forceinline__ void lf_tile_store(const uint8_t *tile, uint8_t *g, int gstride, int x_lo, int x_hi, int y_lo, int y_hi, bool vec, int tid,
+                                              int nthr) {
     if (x_hi <= x_lo || y_hi <= y_lo) return;
     if (vec) {
-        const int nx = (x_hi - x_lo) >> 3, n = nx * (y_hi - y_lo);
-        for (int i = threadIdx.x; i < n; i += LF_THREADS) {
+        const int nx = NX ? NX : (x_hi - x_lo) >> 3, n = nx * (y_hi - y_lo);
+        for (int i = tid; i < n; i += nthr) {
             const int ry = i / nx, yy = y_lo + ry, xx = x_lo + (i - ry * nx) * 8;
             const uint32_t *sp = (const uint32_t *)(tile + (yy + 8) * PITCH + xx + 8);
             uint2 v; v.x = sp[0]; v.y = sp[1];
@@ -227,90 +236,229 @@ __device__ __forceinline__ void lf_tile_store(const uint8_t *tile, uint8_t *g, i
         }
     } else {
         const int nx = x_hi - x_lo, n = nx * (y_hi - y_lo);
-        for (int i = threadIdx.x; i < n; i += LF_THREADS) {
+        for (int i = tid; i < n; i += nthr) {
             const int ry = i / nx, yy = y_lo + ry, xx = x_lo + (i - ry * nx);
             g[(ptrdiff_t)yy * gstride + xx] = tile[(yy + 8) * PITCH + xx + 8];
         }
     }
 }
 
-__global__ void __launch_bounds__(LF_THREADS) lf_sb_kernel(const __grid_constant__ LfKernelArgs A) {
-    LF_SHARED16 uint8_t ty[72 * LF_YP];
-    LF_SHARED16 uint8_t tu[40 * LF_CP];
-    LF_SHARED16 uint8_t tv[40 * LF_CP];
-    __shared__ SvtB200LfMask m;
+struct LfTile { uint8_t *y, *u, *v; };
+
+/* geometry of super-block c of row r */
+struct LfSbGeom { int mi_col, cols, lw, cw; };
+__device__ __forceinline__ LfSbGeom lf_geom(const LfKernelArgs &A, int c) {
+    LfSbGeom g;
+    g.mi_col = c * 8;
+    g.cols = A.P.mi_cols - g.mi_col < 8 ? A.P.mi_cols - g.mi_col : 8;
+    g.lw = g.cols * 8; g.cw = g.cols * 4;
+    return g;
+}
+
+__global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constant__ LfKernelArgs A) {
+    LF_SHARED16 uint8_t ty[2][72 * LF_YP];
+    LF_SHARED16 uint8_t tu[2][40 * LF_CP];
+    LF_SHARED16 uint8_t tv[2][40 * LF_CP];
+    LF_DYN_SMEM(dyn); /* sbs_w adjusted masks (160 B each), then sbs_w x 16 chroma filter levels */
+    SvtB200LfMask *msk = (SvtB200LfMask *)dyn;
+    uint8_t (*lfl_uv)[16] = (uint8_t (*)[16])(dyn + (size_t)A.sbs_w * sizeof(SvtB200LfMask));
     __shared__ SvtB200LfThresh thr[64];
-    __shared__ uint8_t lfl_uv[16];
-    __shared__ int sb_s;
+    __shared__ int row_s;
     const int t = threadIdx.x;
-    if (t == 0) sb_s = atomicAdd(A.ticket, 1);
+    const bool mover = t >= LF_HALF;
+    const int mt = t - LF_HALF;
+    if (t == 0) row_s = atomicAdd(A.ticket, 1);
     if (t < 64) thr[t] = A.thr[t];
     __syncthreads();
-    const int sb = sb_s;
-    if (sb >= A.sbs_w * A.sbs_h) return;
-    const int r = sb / A.sbs_w, c = sb - r * A.sbs_w, mi_row = r * 8, mi_col = c * 8;
+    const int r = row_s;
+    if (r >= A.sbs_h) return;
+    const int mi_row = r * 8;
     const int rows = A.P.mi_rows - mi_row < 8 ? A.P.mi_rows - mi_row : 8;
-    const int cols = A.P.mi_cols - mi_col < 8 ? A.P.mi_cols - mi_col : 8;
-    const int x0 = mi_col * 8, y0 = mi_row * 8, cx0 = mi_col * 4, cy0 = mi_row * 4;
-    const int lw = cols * 8, lh = rows * 8, cw = cols * 4, ch = rows * 4;
-    const int lpx = x0 >= 8 ? 8 : 0, lpy = y0 >= 8 ? 8 : 0; /* context available left / above */
-    uint8_t *gy = A.y + (size_t)y0 * A.y_stride + x0, *gu = A.u + (size_t)cy0 * A.uv_stride + cx0, *gv = A.v + (size_t)cy0 * A.uv_stride + cx0;
+    const int y0 = mi_row * 8, cy0 = mi_row * 4, lh = rows * 8, ch = rows * 4, lpy = r > 0 ? 8 : 0;
     const bool vy = (((uintptr_t)A.y | (uintptr_t)A.y_stride) & 7) == 0;
-    const bool vc = !A.P.y_only && ((((uintptr_t)A.u | (uintptr_t)A.v | (uintptr_t)A.uv_stride) & 7) == 0) && (cw & 7) == 0;
-    /* ---- the SB's own samples: nobody has modified them yet, fetch them while the dependencies finish */
-    lf_tile_load<LF_YP>(ty, gy, A.y_stride, 0, lw, 0, lh, vy);
-    if (!A.P.y_only) {
-        lf_tile_load<LF_CP>(tu, gu, A.uv_stride, 0, cw, 0, ch, vc);
-        lf_tile_load<LF_CP>(tv, gv, A.uv_stride, 0, cw, 0, ch, vc);
-    }
-    if (t == 0) {
-        m = A.lfm[c + r * A.lfm_stride];
-        lf_adjust_mask(A.P.mi_rows, A.P.mi_cols, mi_row, mi_col, &m);
-        for (int rr = 0; rr < 4; rr++) for (int cc = 0; cc < 4; cc++) lfl_uv[rr * 4 + cc] = m.lfl_y[(rr * 2) * 8 + cc * 2];
-        /* wavefront: left neighbour and upper-right neighbour (upper neighbour in the last column) */
-        if (c > 0) while (lf_flag_load(&A.done[sb - 1]) != A.gen) lf_sleep();
-        if (r > 0) { const int dep = (r - 1) * A.sbs_w + (c + 1 < A.sbs_w ? c + 1 : c); while (lf_flag_load(&A.done[dep]) != A.gen) lf_sleep(); }
+    const bool vc0 = !A.P.y_only && ((((uintptr_t)A.u | (uintptr_t)A.v | (uintptr_t)A.uv_stride) & 7) == 0);
+    const bool chroma = !A.P.y_only;
+    const int32_t *above = r > 0 ? A.done + (r - 1) : nullptr;
+    int32_t *mine = A.done + r;
+
+    /* the row above must have finished 'need' super-blocks (their right 8 columns included) */
+    auto wait_above = [&](int need) {
+        if (!above) return;
+        if (need > A.sbs_w) need = A.sbs_w;
+        for (;;) {
+            const int f = lf_flag_load(above);
+            if ((f >> 10) == A.gen && (f & 1023) >= need) break;
+            lf_sleep();
+        }
         lf_fence();
+    };
+    /* fetch into buffer b the samples of tile c nobody has modified yet (its own), or (strip) the 8 rows above it with the
+     * top-left corner, final once the row above has published c + 1; the strip left of the tile comes from the previous
+     * tile through shared memory */
+    auto fetch = [&](int c, int b, bool strip, int tid, int nthr) {
+        const LfSbGeom g = lf_geom(A, c);
+        const int lpx = c > 0 ? 8 : 0;
+        const bool vc = vc0 && (g.cw & 7) == 0;
+        uint8_t *gy = A.y + (size_t)y0 * A.y_stride + c * 64;
+        uint8_t *gu = chroma ? A.u + (size_t)cy0 * A.uv_stride + c * 32 : nullptr, *gv = chroma ? A.v + (size_t)cy0 * A.uv_stride + c * 32 : nullptr;
+        if (nthr == LF_HALF && g.cols == 8 && rows == 8 && lpx && vy && (vc || !chroma)) {
+            /* whole interior tile, 128 threads: independent 8-byte loads issued together, then stored */
+            if (!strip) {
+                uint2 v[6];
+#pragma unroll
+                for (int k = 0; k < 4; k++) { const int i = tid + 128 * k; v[k] = lf_ldcg8(gy + (ptrdiff_t)(i >> 3) * A.y_stride + (i & 7) * 8); }
+                if (chroma) {
+                    v[4] = lf_ldcg8(gu + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
+                    v[5] = lf_ldcg8(gv + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int i = tid + 128 * k;
+                    uint32_t *d = (uint32_t *)(ty[b] + ((i >> 3) + 8) * LF_YP + (i & 7) * 8 + 8);
+                    d[0] = v[k].x; d[1] = v[k].y;
+                }
+                if (chroma) {
+                    uint32_t *d = (uint32_t *)(tu[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
+                    d[0] = v[4].x; d[1] = v[4].y;
+                    d = (uint32_t *)(tv[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
+                    d[0] = v[5].x; d[1] = v[5].y;
+                }
+            } else if (lpy) {
+                /* luma: 8 rows x 9 words-of-8; chroma: 2 planes x 8 rows x 5 */
+                const int ty_y = tid / 9, ty_x = tid - ty_y * 9;
+                const int tc_p = tid >> 6, tc_i = tid & 63, tc_y = tc_i / 5, tc_x = tc_i - tc_y * 5;
+                uint2 a, q;
+                a.x = a.y = q.x = q.y = 0;
+                if (tid < 72) a = lf_ldcg8(gy + (ptrdiff_t)(ty_y - 8) * A.y_stride + (ty_x - 1) * 8);
+                if (chroma && tc_i < 40) q = lf_ldcg8((tc_p ? gv : gu) + (ptrdiff_t)(tc_y - 8) * A.uv_stride + (tc_x - 1) * 8);
+                if (tid < 72) { uint32_t *d = (uint32_t *)(ty[b] + ty_y * LF_YP + ty_x * 8); d[0] = a.x; d[1] = a.y; }
+                if (chroma && tc_i < 40) { uint32_t *d = (uint32_t *)((tc_p ? tv[b] : tu[b]) + tc_y * LF_CP + tc_x * 8); d[0] = q.x; d[1] = q.y; }
+            }
+            return;
+        }
+        if (!strip) {
+            lf_tile_load<LF_YP>(ty[b], gy, A.y_stride, 0, g.lw, 0, lh, vy, tid, nthr);
+            if (chroma) {
+                lf_tile_load<LF_CP>(tu[b], gu, A.uv_stride, 0, g.cw, 0, ch, vc, tid, nthr);
+                lf_tile_load<LF_CP>(tv[b], gv, A.uv_stride, 0, g.cw, 0, ch, vc, tid, nthr);
+            }
+        } else {
+            lf_tile_load<LF_YP>(ty[b], gy, A.y_stride, -lpx, g.lw, -lpy, 0, vy, tid, nthr);
+            if (chroma) {
+                lf_tile_load<LF_CP>(tu[b], gu, A.uv_stride, -lpx, g.cw, -lpy, 0, vc, tid, nthr);
+                lf_tile_load<LF_CP>(tv[b], gv, A.uv_stride, -lpx, g.cw, -lpy, 0, vc, tid, nthr);
+            }
+        }
+    };
+    /* write back a whole-width tile c-1 but for its right 8 columns, and the strip above it (the common case with
+     * compile-time extents); or arbitrary extents */
+    auto put = [&](int c, int b, int x_lo, int x_hi, int y_lo, int y_hi, int cx_lo, int cx_hi, int cy_lo, int cy_hi, int tid, int nthr) {
+        const LfSbGeom g = lf_geom(A, c);
+        const bool vc = vc0 && (g.cw & 7) == 0;
+        uint8_t *gy = A.y + (size_t)y0 * A.y_stride + c * 64;
+        lf_tile_store<LF_YP>(ty[b], gy, A.y_stride, x_lo, x_hi, y_lo, y_hi, vy, tid, nthr);
+        if (chroma) {
+            uint8_t *gu = A.u + (size_t)cy0 * A.uv_stride + c * 32, *gv = A.v + (size_t)cy0 * A.uv_stride + c * 32;
+            lf_tile_store<LF_CP>(tu[b], gu, A.uv_stride, cx_lo, cx_hi, cy_lo, cy_hi, vc, tid, nthr);
+            lf_tile_store<LF_CP>(tv[b], gv, A.uv_stride, cx_lo, cx_hi, cy_lo, cy_hi, vc, tid, nthr);
+        }
+    };
+    auto put_body = [&](int c, int b, int tid, int nthr) { /* tile c is 64 luma samples wide */
+        uint8_t *gy = A.y + (size_t)y0 * A.y_stride + c * 64;
+        lf_tile_store<LF_YP, 7>(ty[b], gy, A.y_stride, 0, 56, 0, lh, vy, tid, nthr);
+        lf_tile_store<LF_YP, 8>(ty[b], gy, A.y_stride, 0, 64, -lpy, 0, vy, tid, nthr);
+        if (chroma) {
+            uint8_t *gu = A.u + (size_t)cy0 * A.uv_stride + c * 32, *gv = A.v + (size_t)cy0 * A.uv_stride + c * 32;
+            lf_tile_store<LF_CP, 3>(tu[b], gu, A.uv_stride, 0, 24, 0, ch, vc0, tid, nthr);
+            lf_tile_store<LF_CP, 4>(tu[b], gu, A.uv_stride, 0, 32, -lpy, 0, vc0, tid, nthr);
+            lf_tile_store<LF_CP, 3>(tv[b], gv, A.uv_stride, 0, 24, 0, ch, vc0, tid, nthr);
+            lf_tile_store<LF_CP, 4>(tv[b], gv, A.uv_stride, 0, 32, -lpy, 0, vc0, tid, nthr);
+        }
+    };
+    auto put_left = [&](int c, int b, int tid, int nthr) { /* the left context of tile c = the right 8 columns of tile c-1 */
+        uint8_t *gy = A.y + (size_t)y0 * A.y_stride + c * 64;
+        lf_tile_store<LF_YP, 1>(ty[b], gy, A.y_stride, -8, 0, 0, lh, vy, tid, nthr);
+        if (chroma) {
+            uint8_t *gu = A.u + (size_t)cy0 * A.uv_stride + c * 32, *gv = A.v + (size_t)cy0 * A.uv_stride + c * 32;
+            lf_tile_store<LF_CP, 1>(tu[b], gu, A.uv_stride, -8, 0, 0, ch, vc0, tid, nthr);
+            lf_tile_store<LF_CP, 1>(tv[b], gv, A.uv_stride, -8, 0, 0, ch, vc0, tid, nthr);
+        }
+    };
+
+    /* ---- prologue: tile 0 */
+    for (int c = t; c < A.sbs_w; c += LF_THREADS) { /* every mask of the row, border-adjusted, once */
+        msk[c] = A.lfm[c + r * A.lfm_stride];
+        lf_adjust_mask(A.P.mi_rows, A.P.mi_cols, mi_row, c * 8, &msk[c]);
+        for (int rr = 0; rr < 4; rr++) for (int cc = 0; cc < 4; cc++) lfl_uv[c][rr * 4 + cc] = msk[c].lfl_y[(rr * 2) * 8 + cc * 2];
     }
     __syncthreads();
-    /* ---- the 8-sample strips the neighbours have just finished: left of the SB, and above it (with the corner) */
-    lf_tile_load<LF_YP>(ty, gy, A.y_stride, -lpx, 0, 0, lh, vy);
-    lf_tile_load<LF_YP>(ty, gy, A.y_stride, -lpx, lw, -lpy, 0, vy);
-    if (!A.P.y_only) {
-        lf_tile_load<LF_CP>(tu, gu, A.uv_stride, -lpx, 0, 0, ch, vc);
-        lf_tile_load<LF_CP>(tu, gu, A.uv_stride, -lpx, cw, -lpy, 0, vc);
-        lf_tile_load<LF_CP>(tv, gv, A.uv_stride, -lpx, 0, 0, ch, vc);
-        lf_tile_load<LF_CP>(tv, gv, A.uv_stride, -lpx, cw, -lpy, 0, vc);
+    fetch(0, 0, false, t, LF_THREADS);
+
+    for (int c = 0; c < A.sbs_w; c++) {
+        const int cur = c & 1, oth = cur ^ 1;
+        const LfSbGeom G = lf_geom(A, c);
+        __syncthreads(); /* tile c (but for the strip above it) is in buffer cur; tile c-1 (filtered) is in buffer oth */
+        LfPlaneMasks MY, MC;
+        if (!mover) {
+            const SvtB200LfMask &m = msk[c];
+            MY.l16 = m.left_y[2]; MY.l8 = m.left_y[1]; MY.l4 = m.left_y[0]; MY.a16 = m.above_y[2]; MY.a8 = m.above_y[1]; MY.a4 = m.above_y[0];
+            MY.i4v = m.int_4x4_y; MY.i4h = m.int_4x4_y; MY.lfl = m.lfl_y; MY.bw = 8; MY.rows = rows; MY.px_rows = lh; MY.top = mi_row == 0;
+            MC.l16 = m.left_uv[2]; MC.l8 = m.left_uv[1]; MC.l4 = m.left_uv[0]; MC.a16 = m.above_uv[2]; MC.a8 = m.above_uv[1]; MC.a4 = m.above_uv[0];
+            MC.i4v = m.int_4x4_uv; MC.i4h = m.int_4x4_uv;
+            /* the internal 4x4 edge of the picture's last (half) chroma block row is not filtered horizontally */
+            for (int rr = 0; rr < 8; rr += 2) if (mi_row + rr == A.P.mi_rows - 1) MC.i4h &= ~((uint64_t)0xf << ((rr >> 1) * 4));
+            MC.lfl = lfl_uv[c]; MC.bw = 4; MC.rows = (rows + 1) >> 1; MC.px_rows = ch; MC.top = mi_row == 0;
+            /* ---- vertical edges: one thread per sample row; the thread first pulls its row of the left context
+             * (the previous tile's right 8 columns, final but for this SB's left edge) out of the other buffer */
+            if (t < 64) {
+                if (c > 0 && t < lh) {
+                    const uint32_t *s = (const uint32_t *)(ty[oth] + (t + 8) * LF_YP + 8 + 56);
+                    uint32_t *d = (uint32_t *)(ty[cur] + (t + 8) * LF_YP);
+                    d[0] = s[0]; d[1] = s[1];
+                }
+                lf_vertical_row(ty[cur] + (t + 8) * LF_YP + 8, t, MY, thr);
+            } else if (chroma) {
+                const int q = (t - 64) & 31;
+                uint8_t *tc = t < 96 ? tu[cur] : tv[cur];
+                if (c > 0 && q < ch) {
+                    const uint32_t *s = (const uint32_t *)((t < 96 ? tu[oth] : tv[oth]) + (q + 8) * LF_CP + 8 + 24);
+                    uint32_t *d = (uint32_t *)(tc + (q + 8) * LF_CP);
+                    d[0] = s[0]; d[1] = s[1];
+                }
+                lf_vertical_row(tc + (q + 8) * LF_CP + 8, q, MC, thr);
+            }
+        } else {
+            /* ---- movers, first half of the step: the strip above tile c (only the horizontal edges need it) as soon as
+             * the row above has published SB c; tile c-1 but for its right 8 columns (still the left context of tile c) */
+            if (mt == 0) wait_above(c + 1);
+            lf_sync_movers();
+            fetch(c, cur, true, mt, LF_HALF);
+            if (c > 0) put_body(c - 1, oth, mt, LF_HALF);
+        }
+        __syncthreads(); /* vertical edges done; buffer oth is free */
+        if (!mover) {
+            /* ---- horizontal edges: one thread per sample column */
+            if (t < 64) { if (t < G.lw) lf_horizontal_col(ty[cur] + 8 * LF_YP + 8 + t, t, LF_YP, MY, thr); }
+            else if (chroma) { const int q = (t - 64) & 31; if (q < G.cw) lf_horizontal_col((t < 96 ? tu[cur] : tv[cur]) + 8 * LF_CP + 8 + q, q, LF_CP, MC, thr); }
+        } else {
+            /* ---- movers, second half: the own samples of tile c+1 into the freed buffer; the left context of tile c is
+             * final now (horizontal edges do not reach it): with it tile c-1 is complete in memory -> publish */
+            if (c + 1 < A.sbs_w) fetch(c + 1, oth, false, mt, LF_HALF);
+            if (c > 0) put_left(c, cur, mt, LF_HALF);
+            lf_fence();
+            lf_sync_movers();
+            if (mt == 0 && c > 0) lf_flag_store(mine, (A.gen << 10) | c); /* SBs 0..c-1 are final in memory */
+        }
     }
     __syncthreads();
-    LfPlaneMasks MY, MC;
-    MY.l16 = m.left_y[2]; MY.l8 = m.left_y[1]; MY.l4 = m.left_y[0]; MY.a16 = m.above_y[2]; MY.a8 = m.above_y[1]; MY.a4 = m.above_y[0];
-    MY.i4v = m.int_4x4_y; MY.i4h = m.int_4x4_y; MY.lfl = m.lfl_y; MY.bw = 8; MY.rows = rows; MY.px_rows = lh; MY.top = mi_row == 0;
-    MC.l16 = m.left_uv[2]; MC.l8 = m.left_uv[1]; MC.l4 = m.left_uv[0]; MC.a16 = m.above_uv[2]; MC.a8 = m.above_uv[1]; MC.a4 = m.above_uv[0];
-    MC.i4v = m.int_4x4_uv; MC.i4h = m.int_4x4_uv;
-    /* the internal 4x4 edge of the picture's last (half) chroma block row is not filtered horizontally */
-    for (int rr = 0; rr < 8; rr += 2) if (mi_row + rr == A.P.mi_rows - 1) MC.i4h &= ~((uint64_t)0xf << ((rr >> 1) * 4));
-    MC.lfl = lfl_uv; MC.bw = 4; MC.rows = (rows + 1) >> 1; MC.px_rows = ch; MC.top = mi_row == 0;
-    /* ---- vertical edges: one thread per sample row */
-    if (t < 64) lf_vertical_row(ty + (t + 8) * LF_YP + 8, t, MY, thr);
-    else if (!A.P.y_only) { const int q = (t - 64) & 31; lf_vertical_row((t < 96 ? tu : tv) + (q + 8) * LF_CP + 8, q, MC, thr); }
-    __syncthreads();
-    /* ---- horizontal edges: one thread per sample column */
-    if (t < 64) { if (t < lw) lf_horizontal_col(ty + 8 * LF_YP + 8 + t, t, LF_YP, MY, thr); }
-    else if (!A.P.y_only) { const int q = (t - 64) & 31; if (q < cw) lf_horizontal_col((t < 96 ? tu : tv) + 8 * LF_CP + 8 + q, q, LF_CP, MC, thr); }
-    __syncthreads();
-    /* ---- write back everything this SB may have changed (its own samples + the 8-sample left / top strips; the
-     * corner is never modified) */
-    lf_tile_store<LF_YP>(ty, gy, A.y_stride, -lpx, lw, 0, lh, vy);
-    lf_tile_store<LF_YP>(ty, gy, A.y_stride, 0, lw, -lpy, 0, vy);
-    if (!A.P.y_only) {
-        lf_tile_store<LF_CP>(tu, gu, A.uv_stride, -lpx, cw, 0, ch, vc);
-        lf_tile_store<LF_CP>(tu, gu, A.uv_stride, 0, cw, -lpy, 0, vc);
-        lf_tile_store<LF_CP>(tv, gv, A.uv_stride, -lpx, cw, 0, ch, vc);
-        lf_tile_store<LF_CP>(tv, gv, A.uv_stride, 0, cw, -lpy, 0, vc);
+    /* ---- epilogue: the last tile, right columns included */
+    {
+        const LfSbGeom g = lf_geom(A, A.sbs_w - 1);
+        put(A.sbs_w - 1, (A.sbs_w - 1) & 1, 0, g.lw, 0, lh, 0, g.cw, 0, ch, t, LF_THREADS);
+        put(A.sbs_w - 1, (A.sbs_w - 1) & 1, 0, g.lw, -lpy, 0, 0, g.cw, -lpy, 0, t, LF_THREADS);
     }
     lf_fence();
     __syncthreads();
-    if (t == 0) lf_flag_store(&A.done[sb], A.gen);
+    if (t == 0) lf_flag_store(mine, (A.gen << 10) | A.sbs_w);
 }
 #endif

@@ -26,7 +26,7 @@ struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c 
 extern thread_local uint3_emu threadIdx, blockIdx;
 extern thread_local dim3 blockDim, gridDim;
 extern thread_local uint8_t *emu_dyn_smem;
-extern thread_local std::barrier<> *emu_block_barrier, *emu_warp_barrier;
+extern thread_local std::barrier<> *emu_block_barrier, *emu_warp_barrier, *emu_upper_half_barrier;
 extern thread_local uint64_t *emu_warp_xchg; /* 32 slots per warp */
 
 #define __global__
@@ -40,6 +40,8 @@ extern thread_local uint64_t *emu_warp_xchg; /* 32 slots per warp */
 
 static inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
 static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier->arrive_and_wait(); }
+/* named barrier over the upper half of the CTA's threads (bar.sync 1, blockDim/2 on the device) */
+static inline void emu_sync_upper_half() { emu_upper_half_barrier->arrive_and_wait(); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
 
 static inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t s) {
@@ -105,6 +107,7 @@ template <class F> static void emu_launch(dim3 grid, dim3 block, size_t smem_byt
     std::vector<uint64_t> xchg((size_t)nwarps * 32);
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
         std::barrier<> bar(nthreads);
+        std::barrier<> upper(nthreads >= 2 ? nthreads - nthreads / 2 : 1);
         std::vector<std::unique_ptr<std::barrier<>>> wbars;
         for (unsigned w = 0; w < nwarps; w++) wbars.emplace_back(new std::barrier<>(std::min(32u, nthreads - w * 32)));
         std::vector<std::thread> ts;
@@ -113,7 +116,7 @@ template <class F> static void emu_launch(dim3 grid, dim3 block, size_t smem_byt
                 threadIdx = {t % block.x, (t / block.x) % block.y, t / (block.x * block.y)};
                 blockIdx = {bx, by, bz}; blockDim = block; gridDim = grid;
                 emu_dyn_smem = (uint8_t *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
-                emu_block_barrier = &bar; emu_warp_barrier = wbars[t / 32].get(); emu_warp_xchg = xchg.data() + (size_t)(t / 32) * 32;
+                emu_block_barrier = &bar; emu_upper_half_barrier = &upper; emu_warp_barrier = wbars[t / 32].get(); emu_warp_xchg = xchg.data() + (size_t)(t / 32) * 32;
                 body();
             });
         for (auto &th : ts) th.join();
@@ -121,6 +124,6 @@ template <class F> static void emu_launch(dim3 grid, dim3 block, size_t smem_byt
 }
 #define SVTB200_EMU_DEFINE_STATE                                              \
     thread_local uint3_emu threadIdx, blockIdx; thread_local dim3 blockDim, gridDim; \
-    thread_local uint8_t *emu_dyn_smem; thread_local std::barrier<> *emu_block_barrier, *emu_warp_barrier; \
+    thread_local uint8_t *emu_dyn_smem; thread_local std::barrier<> *emu_block_barrier, *emu_warp_barrier, *emu_upper_half_barrier; \
     thread_local uint64_t *emu_warp_xchg;
 #endif
