@@ -176,6 +176,18 @@ int svtb200_me_picture_dev(SvtB200Ctx *ctx, const SvtB200MeParams *params, uint6
 enum { SVTB200_TX_4X4 = 0, SVTB200_TX_8X8 = 1, SVTB200_TX_16X16 = 2, SVTB200_TX_32X32 = 3 };
 enum { SVTB200_DCT_DCT = 0, SVTB200_ADST_DCT = 1, SVTB200_DCT_ADST = 2, SVTB200_ADST_ADST = 3 };
 
+/* compute_zz_sad() (Source/Lib/Codec/EbMotionEstimationProcess.c:431; called per picture with look-ahead, :1079-1096):
+ * for every COMPLETE 64x64 super-block the 16x16 SAD between the current picture's 1/16 plane and a 4:1 point decimation
+ * (eb_vp9_decimation_2d, step 4) of the PREVIOUS picture's full-resolution plane at the same position, and the non-moving
+ * score it maps to: 0 / 10 / 20 / 30 for sad < 512 >> s, < 1024 >> s, < 2048 >> s, else, with
+ * s = non_moving_th_shift[input_resolution] = {4, 2, 0, 0} (:353).  Incomplete (edge) super-blocks: sad 0xffffffff,
+ * score 30.  The score array is what the reference stores in previous_pcs->non_moving_index_array.
+ * scores: n_sb bytes; sads: n_sb uint32 or NULL.  Both pictures must be resident (svtb200_picture_upload*). */
+int svtb200_zz_sad_picture(SvtB200Ctx *ctx, uint64_t cur_id, uint64_t prev_id, int32_t luma_width, int32_t luma_height,
+                           int32_t th_shift, uint8_t *scores_host, uint32_t *sads_host);
+int svtb200_zz_sad_picture_dev(SvtB200Ctx *ctx, uint64_t cur_id, uint64_t prev_id, int32_t luma_width, int32_t luma_height,
+                               int32_t th_shift, uint8_t *scores_dev, uint32_t *sads_dev);
+
 /* The five 2-entry (DC, AC) rows quantize_b reads (Source/Lib/VPX/quantize.c:112):
  * zbin, round, quant, quant_shift, dequant -- produced by eb_vp9_init_quantizer
  * (Source/Lib/VPX/vp9_quantize.c:206) on the reference host. */

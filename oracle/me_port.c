@@ -733,3 +733,30 @@ void svtb200_oracle_me_picture(const SvtB200MeParams *P, const SvtB200Plane cur[
     for (int sb = sb_begin; sb < sb_end; sb++)
         svtb200_oracle_me_sb(P, cur, ref0, ref1, sb % sbs_w, sb / sbs_w, out + (size_t)sb * 85, rcme ? rcme + sb : 0, 0);
 }
+
+/* compute_zz_sad (Source/Lib/Codec/EbMotionEstimationProcess.c:431-527, the ADAPTIVE_QP_INDEX_GEN branch): 16x16 SAD of the
+ * current 1/16 plane against eb_vp9_decimation_2d(previous full plane, step 4) per complete SB, mapped to the non-moving
+ * scores with thresholds (block_width * block_height * {2,4,8}) >> non_moving_th_shift[input_resolution] (:353, :503-515). */
+void svtb200_oracle_zz_sad_picture(const SvtB200Plane *cur16, const SvtB200Plane *prev_full, int w, int h, int th_shift,
+                                   uint8_t *scores, uint32_t *sads) {
+    const int sbs_w = (w + SB - 1) / SB, sbs_h = (h + SB - 1) / SB;
+    for (int sy = 0; sy < sbs_h; sy++)
+        for (int sx = 0; sx < sbs_w; sx++) {
+            const int ox = sx * SB, oy = sy * SB, sb = sx + sy * sbs_w;
+            const int bw = (w - ox < SB ? w - ox : SB) >> 2, bh = (h - oy < SB ? h - oy : SB) >> 2;
+            uint32_t sad = 0xffffffffu;
+            if (w - ox >= SB && h - oy >= SB) {
+                uint8_t dec[16 * 16];
+                const uint8_t *p = prev_full->buf + (size_t)(prev_full->origin_y + oy) * prev_full->stride + prev_full->origin_x + ox;
+                for (int y = 0; y < SB; y += 4)
+                    for (int x = 0; x < SB; x += 4) dec[(y >> 2) * 16 + (x >> 2)] = p[(size_t)y * prev_full->stride + x];
+                const uint8_t *c = cur16->buf + (size_t)(cur16->origin_y + (oy >> 2)) * cur16->stride + cur16->origin_x + (ox >> 2);
+                sad = 0;
+                for (int y = 0; y < 16; y++)
+                    for (int x = 0; x < 16; x++) { const int d = (int)c[(size_t)y * cur16->stride + x] - (int)dec[y * 16 + x]; sad += (uint32_t)(d < 0 ? -d : d); }
+            }
+            const uint32_t area = (uint32_t)(bw * bh);
+            scores[sb] = sad < ((area * 2) >> th_shift) ? 0 : sad < ((area * 4) >> th_shift) ? 10 : sad < ((area * 8) >> th_shift) ? 20 : 30;
+            if (sads) sads[sb] = sad;
+        }
+}

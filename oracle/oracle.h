@@ -25,6 +25,9 @@ void svtb200_oracle_me_picture(const SvtB200MeParams *P, const SvtB200Plane cur[
                                const SvtB200Plane ref1[3], SvtB200MeCuResult *out, uint32_t *rcme, int sb_begin,
                                int sb_end);
 
+void svtb200_oracle_zz_sad_picture(const SvtB200Plane *cur16, const SvtB200Plane *prev_full, int w, int h, int th_shift,
+                                   uint8_t *scores, uint32_t *sads);
+
 #ifdef __cplusplus
 }
 #endif

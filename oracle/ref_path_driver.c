@@ -206,6 +206,45 @@ int refdrv_txq(int tx_size, int n_begin, int n_end, const SvtB200TxJob *jobs, co
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------ zz sad */
+#include "EbMotionEstimationProcess.h"
+EbErrorType compute_zz_sad(MotionEstimationContext *context_ptr, SequenceControlSet *sequence_control_set_ptr,
+                           PictureParentControlSet *picture_control_set_ptr, EbPictureBufferDesc *sixteenth_decimated_picture_ptr,
+                           uint32_t x_sb_start_index, uint32_t x_sb_end_index, uint32_t y_sb_start_index, uint32_t y_sb_end_index);
+
+/* the reference's compute_zz_sad over a whole picture; input_resolution 0..3 selects non_moving_th_shift */
+int refdrv_zz_sad(void *h, const SvtB200Plane *cur16, const SvtB200Plane *prev_full, int w, int hgt, int input_resolution, uint8_t *scores) {
+    RefMe *r = (RefMe *)h;
+    const int sbs_w = (w + 63) / 64, sbs_h = (hgt + 63) / 64, n_sb = sbs_w * sbs_h;
+    MotionEstimationContext mec;
+    memset(&mec, 0, sizeof(mec));
+    mec.me_context_ptr = r->me;
+    SequenceControlSet *scs = (SequenceControlSet *)calloc(1, sizeof(SequenceControlSet));
+    scs->picture_width_in_sb = (uint8_t)sbs_w; scs->input_resolution = (uint8_t)input_resolution;
+    scs->luma_width = (uint16_t)w; scs->luma_height = (uint16_t)hgt;
+    scs->sb_params_array = (SbParams *)calloc((size_t)n_sb, sizeof(SbParams));
+    for (int i = 0; i < n_sb; i++) {
+        SbParams *p = &scs->sb_params_array[i];
+        p->origin_x = (uint16_t)((i % sbs_w) * 64); p->origin_y = (uint16_t)((i / sbs_w) * 64);
+        p->width = (uint8_t)(w - p->origin_x < 64 ? w - p->origin_x : 64); p->height = (uint8_t)(hgt - p->origin_y < 64 ? hgt - p->origin_y : 64);
+        p->is_complete_sb = (uint8_t)(p->width == 64 && p->height == 64);
+    }
+    PictureParentControlSet *cur = (PictureParentControlSet *)calloc(1, sizeof(PictureParentControlSet));
+    PictureParentControlSet *prev = (PictureParentControlSet *)calloc(1, sizeof(PictureParentControlSet));
+    EbObjectWrapper prev_w;
+    memset(&prev_w, 0, sizeof(prev_w));
+    EbPictureBufferDesc d_prev, d_cur16;
+    desc_of(prev_full, &d_prev); desc_of(cur16, &d_cur16);
+    prev->enhanced_picture_ptr = &d_prev;
+    prev->non_moving_index_array = (uint8_t *)calloc((size_t)n_sb, 1);
+    prev_w.object_ptr = prev;
+    cur->previous_picture_control_set_wrapper_ptr = &prev_w;
+    compute_zz_sad(&mec, scs, cur, &d_cur16, 0, (uint32_t)sbs_w, 0, (uint32_t)sbs_h);
+    memcpy(scores, prev->non_moving_index_array, (size_t)n_sb);
+    free(prev->non_moving_index_array); free(prev); free(cur); free(scs->sb_params_array); free(scs);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------ deblocking */
 int refdrv_deblock(const SvtB200LfParams *P, uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs, const SvtB200LfMask *lfm,
                    int lfm_stride, const SvtB200LfThresh *thr) {

@@ -126,6 +126,8 @@ def lib():
         L.svtb200_picture_plane_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_int, C.POINTER(Plane)]
         L.svtb200_me_picture.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
         L.svtb200_me_picture_dev.argtypes = [C.c_void_p, C.POINTER(MeParams), C.c_uint64, C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
+        L.svtb200_zz_sad_picture.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        L.svtb200_zz_sad_picture_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.svtb200_me_enable_trace.argtypes = [C.c_void_p, C.c_int]
         L.svtb200_me_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         _lib = L
@@ -212,6 +214,13 @@ class Context:
         self.check(self.L.svtb200_me_picture(self.h, C.byref(params), cur_id, ids, out.ctypes.data,
                                              rcme.ctypes.data if want_rcme else None), "me_picture")
         return (out, rcme) if want_rcme else out
+
+    def zz_sad_picture(self, cur_id, prev_id, width, height, th_shift):
+        """compute_zz_sad for a whole picture -> (scores u8[n_sb], sads u32[n_sb])."""
+        n_sb = ((width + 63) // 64) * ((height + 63) // 64)
+        scores, sads = np.zeros(n_sb, dtype=np.uint8), np.zeros(n_sb, dtype=np.uint32)
+        self.check(self.L.svtb200_zz_sad_picture(self.h, cur_id, prev_id, width, height, th_shift, scores.ctypes.data, sads.ctypes.data), "zz_sad_picture")
+        return scores, sads
 
     def me_trace(self, n_sb):
         tr = np.zeros(n_sb, dtype=ME_TRACE_DTYPE)

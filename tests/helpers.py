@@ -32,6 +32,7 @@ def oracle():
         L = C.CDLL(build.build_oracle())
         L.svtb200_oracle_me_sb.argtypes = [C.POINTER(api.MeParams), C.POINTER(api.Plane), C.POINTER(api.Plane),
                                            C.POINTER(api.Plane), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.svtb200_oracle_zz_sad_picture.argtypes = [C.POINTER(api.Plane), C.POINTER(api.Plane), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.svtb200_oracle_me_picture.argtypes = [C.POINTER(api.MeParams), C.POINTER(api.Plane), C.POINTER(api.Plane),
                                                 C.POINTER(api.Plane), C.c_void_p, C.c_void_p, C.c_int, C.c_int]
         _oracle = L
@@ -435,6 +436,7 @@ def refdrv(use_simd=1):
         L.refdrv_me_range.argtypes = [C.c_void_p, C.POINTER(api.MeParams), C.POINTER(api.Plane), C.POINTER(api.Plane), C.POINTER(api.Plane),
                                       C.c_int, C.c_int, C.c_void_p]
         L.refdrv_txq.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(api.TxPlanes), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.refdrv_zz_sad.argtypes = [C.c_void_p, C.POINTER(api.Plane), C.POINTER(api.Plane), C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.refdrv_deblock.argtypes = [C.POINTER(api.LfParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
         L.refdrv_init(use_simd)
         _refdrv = L
@@ -519,3 +521,19 @@ def cudart_path():
         return os.path.join(os.path.dirname(m.__file__), "lib", "libcudart.so.12")
     except Exception:
         return ""
+
+
+def oracle_zz_sad(cur_structs, prev_structs, w, h, th_shift):
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    scores, sads = np.zeros(n_sb, dtype=np.uint8), np.zeros(n_sb, dtype=np.uint32)
+    oracle().svtb200_oracle_zz_sad_picture(C.byref(cur_structs[2]), C.byref(prev_structs[0]), w, h, th_shift, scores.ctypes.data, sads.ctypes.data)
+    return scores, sads
+
+
+def refdrv_zz_sad(cur_structs, prev_structs, w, h, input_resolution):
+    """The reference's compute_zz_sad; input_resolution 0..3 -> non_moving_th_shift {4, 2, 0, 0}."""
+    L = refdrv()
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    scores = np.zeros(n_sb, dtype=np.uint8)
+    L.refdrv_zz_sad(L.refdrv_me_new(), C.byref(cur_structs[2]), C.byref(prev_structs[0]), w, h, input_resolution, scores.ctypes.data)
+    return scores

@@ -26,7 +26,8 @@ for name in ("SvtVp9EncApp_ref", "SvtVp9EncApp_b200", "SvtVp9EncApp_b200"):
     dt = time.time() - t0
     txt = r.stdout.decode(errors="replace")
     m = re.search(r"Average Speed:\s*([0-9.]+)\s*fps", txt)
-    line = {"app": name, "w": w, "h": h, "frames": n, "enc_mode": mode, "wall_s": round(dt, 2), "app_fps": float(m.group(1)) if m else None,
+    m2 = re.search(r"Total Encoding Time:\s*([0-9.]+)\s*ms", txt)
+    line = {"app": name, "rc": r.returncode, "enc_ms": float(m2.group(1)) if m2 else None, "tail": None if m else txt[-200:], "w": w, "h": h, "frames": n, "enc_mode": mode, "wall_s": round(dt, 2), "app_fps": float(m.group(1)) if m else None,
             "md5": hashlib.md5(open(out, "rb").read()).hexdigest() if os.path.exists(out) else None}
     if "b200" in name and os.path.exists(rep):
         line["gpu"] = dict((l.split()[0], int(l.split()[1])) for l in open(rep) if len(l.split()) == 2)
