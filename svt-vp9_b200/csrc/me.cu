@@ -30,10 +30,10 @@ static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, c
     A.win_bytes = me_window_bytes(*P);
     A.interp_plane_bytes = me_interp_plane_bytes(*P);
     A.interp_in_smem = 1;
-    MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 1);
+    MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 1, me_bip0_bytes(*P));
     if (L.total > c->smem_optin) {
         A.interp_in_smem = 0;
-        L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 0);
+        L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 0, me_bip0_bytes(*P));
         if (L.total > c->smem_optin) { c->err = "search window does not fit in shared memory"; return SVTB200_EINVAL; }
         const size_t need = (size_t)A.n_sb * 2 * 3 * me_align16(A.interp_plane_bytes);
         int rc = svtb200_grow(c, (void **)&c->interp_scratch, &c->interp_scratch_bytes, need);

@@ -201,6 +201,26 @@ __device__ __forceinline__ void me_block_sum_n(uint32_t (&v)[N], int n, uint32_t
     }
 }
 
+/* minimum of 64-bit keys over lanes whose index differs in the bits of 'mask' (xor butterfly) */
+__device__ __forceinline__ unsigned long long me_shfl_min64(unsigned long long v, int mask) {
+    for (int o = 1; o < 32; o <<= 1)
+        if (mask & o) {
+            const unsigned long long x = __shfl_xor_sync(0xffffffffu, v, o);
+            v = x < v ? x : v;
+        }
+    return v;
+}
+/* minimum over the CTA; red64: 8 words of shared memory; every thread gets the result */
+__device__ __forceinline__ unsigned long long me_block_min64(unsigned long long v, unsigned long long *red64) {
+    v = me_shfl_min64(v, 31);
+    __syncthreads(); /* protect red64[] from the previous use */
+    if ((threadIdx.x & 31) == 0) red64[threadIdx.x >> 5] = v;
+    __syncthreads();
+    unsigned long long m = red64[0];
+    for (int i = 1; i < ME_THREADS / 32; i++) m = red64[i] < m ? red64[i] : m;
+    return m;
+}
+
 /* window clipping exactly as the reference's "Correct the ... edge" statements (the left/top
  * branch never shrinks the size because the origin is moved first) */
 __device__ __forceinline__ void me_clip_window(int origin, int16_t *org, int16_t *size, int pad, int pic_dim) {
@@ -326,8 +346,8 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
     const int saw = st->w_saw, npos = saw * nrows, w = st->s_w, h = st->s_h;
     const int wwords = w >> 2;
     if (npos <= 0) return;
+    unsigned long long best = ~0ull;
     if (w & 3) {
-        unsigned long long best = ~0ull;
         for (int pos = threadIdx.x; pos < npos; pos += ME_THREADS) {
             const int ys = pos / saw, xs = pos - ys * saw;
             uint32_t acc = 0;
@@ -341,12 +361,10 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
                 if (key < best) best = key;
             }
         }
-        if (best != ~0ull) atomicMin(&st->best_key, best);
     } else if (npos >= ME_THREADS) {
         /* 4 horizontally adjacent candidates per thread share every window word */
         const int ngx = (saw + 3) >> 2, ngroups = ngx * nrows, sp32 = st->s_pitch >> 2, wp32 = st->w_pitch >> 2;
         const uint32_t rcp = 0xffffffffu / (uint32_t)ngx + 1u; /* __umulhi(g, rcp) == g / ngx */
-        unsigned long long best = ~0ull;
         for (int g = threadIdx.x; g < ngroups; g += ME_THREADS) {
             const int ys = (int)__umulhi((uint32_t)g, rcp), gx = g - ys * ngx;
             const uint32_t *wrow0 = (const uint32_t *)win + ys * wp32 + gx;
@@ -376,7 +394,6 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
                     if (key < best) best = key;
                 }
         }
-        if (best != ~0ull) atomicMin(&st->best_key, best);
     } else {
         /* few positions: split every candidate's rows over P threads */
         int P = 1;
@@ -394,8 +411,11 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
         }
         __syncthreads();
         if (threadIdx.x < (unsigned)npos && posacc[threadIdx.x] < 0xffffffu)
-            atomicMin(&st->best_key, ((unsigned long long)posacc[threadIdx.x] << 32) | (uint32_t)(threadIdx.x + y0 * saw));
+            best = ((unsigned long long)posacc[threadIdx.x] << 32) | (uint32_t)(threadIdx.x + y0 * saw);
     }
+    /* first minimum in raster order over the CTA (the key carries the raster index); posacc doubles as scratch */
+    const unsigned long long m = me_block_min64(best, (unsigned long long *)posacc + 64);
+    if (threadIdx.x == 0 && m < st->best_key) st->best_key = m;
 }
 
 /* one HME level: thread 0 prepared st->s_*, st->w_*; all threads stage and search, stripe by stripe.
@@ -456,9 +476,9 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
     const int tail_from = saw & ~7; /* columns handled by the reference's one-position routine */
     /* candidates are taken four at a time along x (one group shares every window word); a chunk is ME_CHUNK/4 groups */
     const int ngx = (saw + 3) >> 2, ngroups = ngx * sah;
-    for (int i = threadIdx.x; i < 85; i += ME_THREADS) pu_key[i] = ((unsigned long long)ME_MAX_SAD << 32) | 0xffffffffu;
-    __syncthreads();
     const int t = threadIdx.x;
+    /* every thread keeps the running minima of "its" partitions over all chunks; one reduction at the end */
+    unsigned long long best8 = ~0ull, best16 = ~0ull, best32 = ~0ull, best64 = ~0ull;
     for (int g0 = 0; g0 < ngroups; g0 += ME_CHUNK / 4) {
         const int gn = min(ME_CHUNK / 4, ngroups - g0), cn = gn * 4;
         /* phase 1: 8x8 SADs (rows 0,2,4,6), z-ordered so that 4 consecutive entries form a 16x16 */
@@ -487,6 +507,14 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
                 }
                 uint16_t *o = s8 + (gl * 4) * 64 + z8;
                 o[0] = (uint16_t)a0; o[64] = (uint16_t)a1; o[128] = (uint16_t)a2; o[192] = (uint16_t)a3;
+                /* this thread's own four candidates of its 8x8 partition */
+                const uint32_t pos0 = (uint32_t)(ys * saw + 4 * gx);
+                const uint32_t av[4] = {a0, a1, a2, a3};
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const uint32_t v = 2u * av[j];
+                    if (4 * gx + j < saw && v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | (pos0 + j); if (key < best8) best8 = key; }
+                }
             }
             if (t < cn) { /* raster index of every slot of the chunk (invalid beyond the right edge of the area) */
                 const int g = g0 + (t >> 2), ys = g / ngx, xs = 4 * (g - ys * ngx) + (t & 3);
@@ -494,49 +522,63 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
             }
         }
         __syncthreads();
-        /* phase 2: 8x8 minima and 16x16 sums */
+        /* phase 2: 16x16 sums */
         {
-            const int z8 = t & 63, lane = t >> 6;
-            unsigned long long best = ~0ull;
-            for (int pp = lane; pp < cn; pp += 4) {
-                const uint32_t v = 2u * s8[pp * 64 + z8], pos = spos[pp];
-                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best) best = key; }
-            }
-            if (best != ~0ull) atomicMin(&pu_key[21 + z8], best);
             const int z16 = t & 15, l16 = t >> 4;
-            best = ~0ull;
             for (int pp = l16; pp < cn; pp += 16) {
                 const uint16_t *q = s8 + pp * 64 + z16 * 4;
                 const uint32_t sum = (uint32_t)q[0] + q[1] + q[2] + q[3], pos = spos[pp];
                 s16[pp * 16 + z16] = (uint16_t)sum;
                 const uint32_t v = 2u * sum;
-                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best) best = key; }
+                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best16) best16 = key; }
             }
-            if (best != ~0ull) atomicMin(&pu_key[5 + z16], best);
         }
         __syncthreads();
         /* phase 3: 32x32 */
         {
             const int q32 = t & 3, l32 = t >> 2;
-            unsigned long long best = ~0ull;
             for (int pp = l32; pp < cn; pp += 64) {
                 const uint16_t *q = s16 + pp * 16 + q32 * 4;
                 const uint32_t sum = (uint32_t)q[0] + q[1] + q[2] + q[3], pos = spos[pp];
                 s32[pp * 4 + q32] = sum;
                 const uint32_t v = 2u * sum;
-                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best) best = key; }
+                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best32) best32 = key; }
             }
-            if (best != ~0ull) atomicMin(&pu_key[1 + q32], best);
         }
         __syncthreads();
         /* phase 4: 64x64 */
         if (t < cn && spos[t] != 0xffffffffu) {
             const uint32_t *q = s32 + t * 4;
             const uint32_t v = 2u * (q[0] + q[1] + q[2] + q[3]);
-            if (v < ME_MAX_SAD) atomicMin(&pu_key[0], ((unsigned long long)v << 32) | spos[t]);
+            if (v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | spos[t]; if (key < best64) best64 = key; }
         }
         __syncthreads();
     }
+    /* ---- reduce: 8x8 partitions live on threads z8 + 64*{0..3}; 16x16 on lanes z16, z16+16 of every warp; 32x32 on the
+     * lanes = q32 (mod 4) of every warp; 64x64 on warp 0.  s8 (free now) is the exchange buffer. */
+    unsigned long long *x8 = (unsigned long long *)s8, *x16 = x8 + 256, *x32 = x16 + 128;
+    const unsigned long long none = ((unsigned long long)ME_MAX_SAD << 32) | 0xffffffffu;
+    x8[t] = best8;
+    best16 = me_shfl_min64(best16, 16);
+    best32 = me_shfl_min64(best32, 4 | 8 | 16);
+    if ((t & 31) < 16) x16[(t >> 5) * 16 + (t & 15)] = best16;
+    if ((t & 31) < 4) x32[(t >> 5) * 4 + (t & 3)] = best32;
+    if (t < 32) { best64 = me_shfl_min64(best64, 31); if (t == 0) pu_key[0] = best64 != ~0ull ? best64 : none; }
+    __syncthreads();
+    if (t < 64) {
+        unsigned long long m = x8[t];
+        for (int i = 1; i < 4; i++) m = x8[t + 64 * i] < m ? x8[t + 64 * i] : m;
+        pu_key[21 + t] = m != ~0ull ? m : none;
+    } else if (t < 80) {
+        unsigned long long m = ~0ull;
+        for (int i = 0; i < 8; i++) m = x16[i * 16 + (t - 64)] < m ? x16[i * 16 + (t - 64)] : m;
+        pu_key[5 + (t - 64)] = m != ~0ull ? m : none;
+    } else if (t < 84) {
+        unsigned long long m = ~0ull;
+        for (int i = 0; i < 8; i++) m = x32[i * 4 + (t - 80)] < m ? x32[i * 4 + (t - 80)] : m;
+        pu_key[1 + (t - 80)] = m != ~0ull ? m : none;
+    }
+    __syncthreads();
 }
 
 /* ---------------------------------------------------------------------------------------------
@@ -914,16 +956,17 @@ __device__ __forceinline__ uint32_t me_pred_word(const MePred &p, int y, int k) 
  * shared-memory layout of one CTA and the launch plan (shared by the host code and the emulation)
  * ------------------------------------------------------------------------------------------- */
 struct MeSmemLayout {
-    int src, hsrc, win, interp, s8, s16, s32, pu_key, bsad, bmv, bssd, bip, dir, posacc, dist, sad, preds, state, total;
+    int src, hsrc, win, interp, bip0, s8, s16, s32, pu_key, bsad, bmv, bssd, bip, dir, posacc, dist, sad, state, total;
 };
 __host__ __device__ static inline int me_align16(int v) { return (v + 15) & ~15; }
-__host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int interp_plane_bytes, int interp_in_smem) {
+__host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int interp_plane_bytes, int interp_in_smem, int bip0_bytes) {
     MeSmemLayout L;
     int o = 0;
     L.src = o; o += ME_SB * ME_SB;
     L.hsrc = o; o += 64 * 32;
     L.win = o; o += me_align16(win_bytes);
-    L.interp = o; o += interp_in_smem ? 6 * me_align16(interp_plane_bytes) : 0;
+    L.interp = o; o += interp_in_smem ? 3 * me_align16(interp_plane_bytes) : 0; /* the planes of the list being searched */
+    L.bip0 = o; o += me_align16(bip0_bytes);                                  /* list-0 predictions kept for bi-prediction */
     L.s8 = o; o += ME_CHUNK * 64 * 2;
     L.s16 = o; o += ME_CHUNK * 16 * 2;
     L.s32 = o; o += ME_CHUNK * 4 * 4;
@@ -936,7 +979,6 @@ __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int
     L.posacc = o; o += 256 * 4;
     L.dist = o; o += me_align16(85 * 9 * 4);
     L.sad = o; o += me_align16(85 * 9 * 4);
-    L.preds = o; o += me_align16(85 * 2 * 24);
     L.state = o; o += me_align16((int)sizeof(MeSbState));
     L.total = o;
     return L;
@@ -946,12 +988,18 @@ __host__ __device__ static inline int me_fp_pitch(int saw) { return (saw + ME_SB
 __host__ __device__ static inline int me_fp_rows(int sah) { return sah + ME_SB - 1 + 2 * ME_HALO_Y; }
 /* capacity of the window buffer: the full-pel window, and the largest HME stripe */
 static inline int me_window_bytes(const SvtB200MeParams &P) {
-    auto hme = [](int saw, int sah, int w, int h) {
-        const int pitch = (saw + w + 8 + 3) & ~3, rows = (sah < ME_HME_STRIPE ? sah : ME_HME_STRIPE) + 2 * (h - 1) + 2;
-        return pitch * rows;
+    const int saw = P.search_area_width < 127 ? P.search_area_width : 127, sah = P.search_area_height < 127 ? P.search_area_height : 127;
+    const int fp = me_fp_pitch(saw) * (me_fp_rows(sah) + 1);
+    /* an HME area is searched in stripes of candidate rows; shorter stripes while that keeps the buffer at the size the
+     * full-pel window needs anyway (more CTAs per SM), never below 8 rows */
+    auto hme = [fp](int hsaw, int hsah, int w, int h) {
+        const int pitch = (hsaw + w + 8 + 3) & ~3;
+        int stripe = hsah < ME_HME_STRIPE ? hsah : ME_HME_STRIPE;
+        while (stripe > 8 && pitch * (stripe + 2 * (h - 1) + 2) > fp) stripe -= 8;
+        return pitch * (stripe + 2 * (h - 1) + 2);
     };
     auto mx = [](int a, int b) { return a > b ? a : b; };
-    int best = 0;
+    int best = fp;
     if (P.enable_hme_flag) {
         if (P.enable_hme_level0) {
             int tw = (P.hme_level0_total_search_area_width * P.hme_l0_multiplier_x) / 100, th = (P.hme_level0_total_search_area_height * P.hme_l0_multiplier_y) / 100;
@@ -968,9 +1016,14 @@ static inline int me_window_bytes(const SvtB200MeParams &P) {
             for (int i = 0; i < 2; i++) for (int j = 0; j < 2; j++)
                 best = mx(best, hme(mx(8, 2 * P.hme_level2_search_area_in_width[i]), P.hme_level2_search_area_in_height[j], 64, 32));
     }
-    const int saw = P.search_area_width < 127 ? P.search_area_width : 127, sah = P.search_area_height < 127 ? P.search_area_height : 127;
-    best = mx(best, me_fp_pitch(saw) * (me_fp_rows(sah) + 1));
     return best + 16;
+}
+/* list-0 predictions of the partitions bi-prediction evaluates: one 64-wide image per size class, sub-sampled rows when
+ * the metric is the sub-sampled SAD */
+__host__ __device__ static inline int me_bip0_bytes(const SvtB200MeParams &P) {
+    if (P.num_lists < 2) return 0;
+    const int ncls = 2 + (P.cu16x16_mode == 0 ? 1 : 0) + ((P.cu16x16_mode == 0 && P.cu8x8_mode == 0) ? 1 : 0);
+    return ncls * ME_SB * (P.fractional_search_method == 0 ? ME_SB / 2 : ME_SB);
 }
 static inline int me_interp_plane_bytes(const SvtB200MeParams &P) {
     const int saw = P.search_area_width < 127 ? P.search_area_width : 127, sah = P.search_area_height < 127 ? P.search_area_height : 127;
@@ -1062,10 +1115,10 @@ __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, 
 /* ---------------------------------------------------------------------------------------------
  * the kernel: one CTA per super-block
  * ------------------------------------------------------------------------------------------- */
-__global__ void __launch_bounds__(ME_THREADS, 3) me_sb_kernel(const __grid_constant__ MeKernelArgs A) {
+__global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_constant__ MeKernelArgs A) {
     ME_DYN_SMEM(smem);
     const SvtB200MeParams &P = A.P;
-    const MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, A.interp_in_smem);
+    const MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, A.interp_in_smem, me_bip0_bytes(A.P));
     uint8_t  *src = smem + L.src, *hsrc = smem + L.hsrc, *win = smem + L.win;
     uint16_t *s8 = (uint16_t *)(smem + L.s8), *s16 = (uint16_t *)(smem + L.s16);
     uint32_t *s32 = (uint32_t *)(smem + L.s32);
@@ -1074,13 +1127,13 @@ __global__ void __launch_bounds__(ME_THREADS, 3) me_sb_kernel(const __grid_const
     uint32_t *bip = (uint32_t *)(smem + L.bip), *posacc = (uint32_t *)(smem + L.posacc);
     uint8_t  *dir = smem + L.dir;
     uint32_t *dist = (uint32_t *)(smem + L.dist), *sadv = (uint32_t *)(smem + L.sad);
-    MePred   *preds = (MePred *)(smem + L.preds);
+    uint8_t  *bip0 = smem + L.bip0;
     MeSbState *st = (MeSbState *)(smem + L.state);
     const int sb = blockIdx.x + A.sb_first, t = threadIdx.x, nl = P.num_lists;
     const int ipb = me_align16(A.interp_plane_bytes);
     MeInterp ip[2];
     for (int l = 0; l < 2; l++) {
-        uint8_t *base = A.interp_in_smem ? smem + L.interp + (size_t)l * 3 * ipb
+        uint8_t *base = A.interp_in_smem ? smem + L.interp /* one set, reused by list 1 */
                                          : A.interp_scratch + ((size_t)sb * 2 + l) * 3 * ipb;
         ip[l].pb = base; ip[l].ph = base + ipb; ip[l].pj = base + 2 * ipb;
         ip[l].rb = 0; ip[l].rp = 0;
@@ -1259,36 +1312,54 @@ __global__ void __launch_bounds__(ME_THREADS, 3) me_sb_kernel(const __grid_const
             if (cmask) me_subpel(A, src, st, list, ip[list], cmask, st->eq ? 15 : 1, ls, lm, lq, dir, dist, sadv);
         }
         __syncthreads();
+        if (list == 0 && nl == 2) {
+            /* the list-0 prediction of every partition bi-prediction will evaluate, at the final list-0 vectors: one 64-wide
+             * image per size class (even rows only for the sub-sampled metric) */
+            const int sub = (P.fractional_search_method == 0), rsh = sub ? 1 : 0;
+            for (int cls = 0; cls < 4; cls++) {
+                if (cls == 3 && P.cu8x8_mode != 0) continue;
+                if (cls >= 2 && P.cu16x16_mode != 0) continue;
+                const int tlog = 5 - cls, T = 1 << tlog, idx0 = me_cls_idx0(cls), nunits = me_cls_npu(cls) * T;
+                uint8_t *img = bip0 + cls * (ME_SB * (ME_SB >> rsh));
+                for (int u = t; u < nunits; u += ME_THREADS) {
+                    const int idx = idx0 + (u >> tlog), part = u & (T - 1);
+                    int px, py, w;
+                    me_pu_geom(idx, &px, &py, &w);
+                    MePred p0;
+                    me_bipred_pred(st->sa_ox[0], st->sa_oy[0], st->istride[0], ip[0], bmv[idx], px, py, &p0);
+                    const int wwords = w >> 2;
+                    for (int y = sub ? 2 * part : part; y < w; y += sub ? 2 * T : T) {
+                        uint32_t *d = (uint32_t *)(img + ((py + y) >> rsh) * ME_SB + px);
+                        for (int k = 0; k < wwords; k++) d[k] = me_pred_word(p0, y, k);
+                    }
+                }
+            }
+            __syncthreads();
+        }
     }
 
-    /* ---- bi-prediction: SAD(src, avg(pred L0, pred L1)) at the two uni-pred winners */
+    /* ---- bi-prediction: SAD(src, avg(pred L0, pred L1)) at the two uni-pred winners; the list-0 predictions were put
+     * aside (bip0) before list 1 took over the half-pel planes */
     if (nl == 2) {
-        const int sub = (P.fractional_search_method == 0);
-        /* list 1's integer samples are still staged; list 0's window has been overwritten: read the plane */
-        ip[0].rb = me_pix(A.ref[0][0], st->ox + st->sa_ox[0], st->oy + st->sa_oy[0]); ip[0].rp = A.ref[0][0].stride;
-        for (int i = t; i < 85 * 2; i += ME_THREADS) {
-            const int idx = i >> 1, l = i & 1;
-            int px, py, w;
-            me_pu_geom(idx, &px, &py, &w);
-            me_bipred_pred(st->sa_ox[l], st->sa_oy[l], st->istride[l], ip[l], bmv[l * 85 + idx], px, py, &preds[i]);
-        }
-        __syncthreads();
+        const int sub = (P.fractional_search_method == 0), rsh = sub ? 1 : 0;
         /* one (sub-sampled) row of one PU per unit: 64x64 -> 32 lanes, 32x32 -> 16, 16x16 -> 8, 8x8 -> 4 */
         for (int cls = 0; cls < 4; cls++) {
             if (cls == 3 && P.cu8x8_mode != 0) continue;
             if (cls >= 2 && P.cu16x16_mode != 0) continue;
             const int tlog = 5 - cls, T = 1 << tlog, idx0 = me_cls_idx0(cls), nunits = me_cls_npu(cls) * T;
+            const uint8_t *img = bip0 + cls * (ME_SB * (ME_SB >> rsh));
             for (int u = t; u < nunits; u += ME_THREADS) {
                 const int idx = idx0 + (u >> tlog), part = u & (T - 1);
                 int px, py, w;
                 me_pu_geom(idx, &px, &py, &w);
-                const MePred &p0 = preds[idx * 2], &p1 = preds[idx * 2 + 1];
+                MePred p1;
+                me_bipred_pred(st->sa_ox[1], st->sa_oy[1], st->istride[1], ip[1], bmv[85 + idx], px, py, &p1);
                 const int wwords = w >> 2;
                 uint32_t acc = 0;
                 for (int y = sub ? 2 * part : part; y < w; y += sub ? 2 * T : T) {
                     const uint32_t *srow = (const uint32_t *)(src + (py + y) * ME_SB + px);
-                    for (int k = 0; k < wwords; k++)
-                        acc = me_absdiff_acc(__vavgu4(me_pred_word(p0, y, k), me_pred_word(p1, y, k)), srow[k], acc);
+                    const uint32_t *p0 = (const uint32_t *)(img + ((py + y) >> rsh) * ME_SB + px);
+                    for (int k = 0; k < wwords; k++) acc = me_absdiff_acc(__vavgu4(p0[k], me_pred_word(p1, y, k)), srow[k], acc);
                 }
                 acc = me_group_sum(acc, tlog);
                 if (part == 0) bip[idx] = sub ? acc << 1 : acc;

@@ -23,7 +23,7 @@ extern "C" int me_emu_run(const SvtB200MeParams *P, const SvtB200Plane cur[3], c
     std::vector<uint8_t> scratch;
     if (force_global_interp) { scratch.resize((size_t)A.n_sb * 6 * me_align16(A.interp_plane_bytes)); A.interp_scratch = scratch.data(); }
     A.sb_first = sb_begin;
-    MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, A.interp_in_smem);
+    MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, A.interp_in_smem, me_bip0_bytes(*P));
     emu_launch(dim3(sb_end - sb_begin), dim3(ME_THREADS), L.total, [&] { me_sb_kernel(A); });
     return L.total;
 }
