@@ -188,7 +188,7 @@ __device__ __forceinline__ int quant_row(const int (&c)[N], int (&dq)[N], const 
 
 /* MODE 0 fused from planes, 1 forward only, 2 quantise only, 3 inverse + add only */
 template <int N, int MODE>
-__global__ void __launch_bounds__(TXQ_THREADS) txq_kernel(const __grid_constant__ TxqArgs A) {
+__global__ void __launch_bounds__(TXQ_THREADS, 4) txq_kernel(const __grid_constant__ TxqArgs A) {
     constexpr int G = TXQ_THREADS / N; /* blocks per CTA pass */
     constexpr int SHIFT = TxCfg<N>::SHIFT, TS = TxCfg<N>::TS;
     __shared__ int tiles[G * N * (N + 1)];
