@@ -147,18 +147,22 @@ template <int N>
 __device__ __forceinline__ int quant_row(const int (&c)[N], int (&dq)[N], const SvtB200QuantRow &qr, const int16_t *iscan, int lane,
                                          int16_t *q_dst, int16_t *dq_dst, bool live) {
     constexpr int TS = TxCfg<N>::TS;
-    const int16_t *isc = iscan + lane * N;
-    const int zb_dc = TS == 3 ? (qr.zbin[0] + 1) >> 1 : qr.zbin[0], zb_ac = TS == 3 ? (qr.zbin[1] + 1) >> 1 : qr.zbin[1];
-    const int rd_dc = TS == 3 ? (qr.round[0] + 1) >> 1 : qr.round[0], rd_ac = TS == 3 ? (qr.round[1] + 1) >> 1 : qr.round[1];
-    const int qu_dc = qr.quant[0], qu_ac = qr.quant[1], qs_dc = qr.quant_shift[0], qs_ac = qr.quant_shift[1];
-    const int dq_dc = qr.dequant[0], dq_ac = qr.dequant[1];
+    /* this lane's row of the inverse scan, fetched with vector loads */
+    int isc[N];
+    load_row16<N>(iscan + lane * N, isc);
+    /* AC constants; the DC entry differs only for coefficient (0,0), i.e. lane 0, k 0 */
+    const int zb_ac = TS == 3 ? (qr.zbin[1] + 1) >> 1 : qr.zbin[1], rd_ac = TS == 3 ? (qr.round[1] + 1) >> 1 : qr.round[1];
+    const int qu_ac = qr.quant[1], qs_ac = qr.quant_shift[1], dq_ac = qr.dequant[1];
+    const bool dc = lane == 0;
+    const int zb_0 = dc ? (TS == 3 ? (qr.zbin[0] + 1) >> 1 : qr.zbin[0]) : zb_ac, rd_0 = dc ? (TS == 3 ? (qr.round[0] + 1) >> 1 : qr.round[0]) : rd_ac;
+    const int qu_0 = dc ? qr.quant[0] : qu_ac, qs_0 = dc ? qr.quant_shift[0] : qs_ac, dq_0 = dc ? qr.dequant[0] : dq_ac;
     int nzc = N * N;
     if (TS < 3) { /* trailing coefficients (scan order) inside the dead zone are dropped */
         int last = -1;
 #pragma unroll
         for (int k = 0; k < N; k++) {
-            const int zb = (lane | k) ? zb_ac : zb_dc;
-            if (!(c[k] < zb && c[k] > -zb)) last = max(last, (int)__ldg(isc + k));
+            const int zb = k ? zb_ac : zb_0;
+            if (!(c[k] < zb && c[k] > -zb)) last = max(last, isc[k]);
         }
         nzc = group_max<N>(last) + 1;
     }
@@ -166,21 +170,17 @@ __device__ __forceinline__ int quant_row(const int (&c)[N], int (&dq)[N], const 
     int q[N];
 #pragma unroll
     for (int k = 0; k < N; k++) {
-        const bool ac = (lane | k) != 0;
-        const int zb = ac ? zb_ac : zb_dc;
+        const int zb = k ? zb_ac : zb_0, rd = k ? rd_ac : rd_0, qu = k ? qu_ac : qu_0, qs = k ? qs_ac : qs_0, dv = k ? dq_ac : dq_0;
         const int sign = c[k] >> 31, a = (c[k] ^ sign) - sign;
-        q[k] = 0; dq[k] = 0;
-        if (a >= zb) {
-            const int si = __ldg(isc + k);
-            if (si < nzc) {
-                int t = a + (ac ? rd_ac : rd_dc);
-                t = min(max(t, -32768), 32767);
-                t = ((((t * (ac ? qu_ac : qu_dc)) >> 16) + t) * (ac ? qs_ac : qs_dc)) >> (TS == 3 ? 15 : 16);
-                q[k]  = w16((t ^ sign) - sign);
-                dq[k] = TS == 3 ? w16(q[k] * (ac ? dq_ac : dq_dc) / 2) : w16(q[k] * (ac ? dq_ac : dq_dc));
-                if (t) eob = max(eob, si);
-            }
-        }
+        /* branch-free: quantise every coefficient, keep the result only outside the dead zone and before the cut-off */
+        int t = min(a + rd, 32767);
+        t = ((((t * qu) >> 16) + t) * qs) >> (TS == 3 ? 15 : 16);
+        const bool keep = a >= zb && isc[k] < nzc;
+        t = keep ? t : 0;
+        const int qv = w16((t ^ sign) - sign);
+        q[k]  = qv;
+        dq[k] = TS == 3 ? w16(qv * dv / 2) : w16(qv * dv);
+        eob = t ? max(eob, isc[k]) : eob;
     }
     if (live) { store_row16<N>(q_dst, q); store_row16<N>(dq_dst, dq); }
     return group_max<N>(eob) + 1;
