@@ -5,6 +5,8 @@
 struct LfScratch { int32_t *ticket = nullptr, *done = nullptr; size_t done_n = 0; int32_t gen = 0; };
 static std::map<SvtB200Ctx *, LfScratch> g_lf;
 static std::mutex g_lf_mu;
+static unsigned long long *g_lf_trace; /* tools only */
+extern "C" void svtb200_lf_set_trace(void *dev) { g_lf_trace = (unsigned long long *)dev; }
 
 static int lf_launch(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs,
                      const SvtB200LfMask *lfm, int lfm_stride, const SvtB200LfThresh *thr) {
@@ -26,7 +28,7 @@ static int lf_launch(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int ys
         SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->done, 0, n * 4, c->stream));
     }
     S->gen++;
-    A.ticket = S->ticket; A.done = S->done; A.gen = S->gen;
+    A.ticket = S->ticket; A.done = S->done; A.gen = S->gen; A.trace = g_lf_trace;
     SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->ticket, 0, 4, c->stream));
     const size_t dyn = (size_t)A.sbs_w * (sizeof(SvtB200LfMask) + 16);
     if (dyn > 48 * 1024) SVTB200_CUDA_CHECK(c, cudaFuncSetAttribute(lf_row_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));

@@ -39,9 +39,11 @@ struct LfKernelArgs {
     int32_t *done;              /* one word per SB row: (gen << 10) | number of SBs of the row that are final in memory */
     int32_t  gen;
     int32_t  sbs_w, sbs_h;
+    unsigned long long *trace;  /* optional (tools/lf_trace.py): [row][sb][8] SM clock stamps */
 };
 
 #ifdef SVTB200_CPU_EMU
+static inline unsigned long long lf_clock() { return 0; }
 #define LF_SHARED16 alignas(16) static
 #define LF_DYN_SMEM(name) uint8_t *name = emu_dyn_smem
 static inline uint8_t lf_ldcg(const uint8_t *p) { return *p; }
@@ -52,6 +54,7 @@ static inline void lf_sync_movers() { emu_sync_upper_half(); }
 static inline int lf_flag_load(const int32_t *p) { return __atomic_load_n(p, __ATOMIC_ACQUIRE); }
 static inline void lf_flag_store(int32_t *p, int v) { __atomic_store_n(p, v, __ATOMIC_RELEASE); }
 #else
+__device__ __forceinline__ unsigned long long lf_clock() { return (unsigned long long)clock64(); }
 #define LF_SHARED16 __shared__ __align__(16)
 #define LF_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
 __device__ __forceinline__ uint8_t lf_ldcg(const uint8_t *p) { return __ldcg(p); }
@@ -350,6 +353,35 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
             }
         }
     };
+    /* the own samples of an interior tile as two steps: the loads are issued half a step before the buffer they go to is free */
+    auto own_fast = [&](int c) {
+        const LfSbGeom g = lf_geom(A, c);
+        return g.cols == 8 && rows == 8 && c > 0 && vy && (!chroma || vc0);
+    };
+    auto own_issue = [&](int c, uint2 (&v)[6], int tid) {
+        const uint8_t *gy = A.y + (size_t)y0 * A.y_stride + c * 64;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { const int i = tid + 128 * k; v[k] = lf_ldcg8(gy + (ptrdiff_t)(i >> 3) * A.y_stride + (i & 7) * 8); }
+        if (chroma) {
+            const uint8_t *gu = A.u + (size_t)cy0 * A.uv_stride + c * 32, *gv = A.v + (size_t)cy0 * A.uv_stride + c * 32;
+            v[4] = lf_ldcg8(gu + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
+            v[5] = lf_ldcg8(gv + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
+        }
+    };
+    auto own_commit = [&](int b, const uint2 (&v)[6], int tid) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = tid + 128 * k;
+            uint32_t *d = (uint32_t *)(ty[b] + ((i >> 3) + 8) * LF_YP + (i & 7) * 8 + 8);
+            d[0] = v[k].x; d[1] = v[k].y;
+        }
+        if (chroma) {
+            uint32_t *d = (uint32_t *)(tu[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
+            d[0] = v[4].x; d[1] = v[4].y;
+            d = (uint32_t *)(tv[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
+            d[0] = v[5].x; d[1] = v[5].y;
+        }
+    };
     /* write back a whole-width tile c-1 but for its right 8 columns, and the strip above it (the common case with
      * compile-time extents); or arbitrary extents */
     auto put = [&](int c, int b, int x_lo, int x_hi, int y_lo, int y_hi, int cx_lo, int cx_hi, int cy_lo, int cy_hi, int tid, int nthr) {
@@ -398,7 +430,11 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
         const int cur = c & 1, oth = cur ^ 1;
         const LfSbGeom G = lf_geom(A, c);
         __syncthreads(); /* tile c (but for the strip above it) is in buffer cur; tile c-1 (filtered) is in buffer oth */
+        unsigned long long *tr = A.trace ? A.trace + ((size_t)r * A.sbs_w + c) * 8 : nullptr;
+        if (tr && t == 0) tr[0] = lf_clock();
         LfPlaneMasks MY, MC;
+        uint2 pre[6];
+        bool pre_valid = false;
         if (!mover) {
             const SvtB200LfMask &m = msk[c];
             MY.l16 = m.left_y[2]; MY.l8 = m.left_y[1]; MY.l4 = m.left_y[0]; MY.a16 = m.above_y[2]; MY.a8 = m.above_y[1]; MY.a4 = m.above_y[0];
@@ -428,26 +464,39 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
                 lf_vertical_row(tc + (q + 8) * LF_CP + 8, q, MC, thr);
             }
         } else {
-            /* ---- movers, first half of the step: the strip above tile c (only the horizontal edges need it) as soon as
-             * the row above has published SB c; tile c-1 but for its right 8 columns (still the left context of tile c) */
+            /* ---- movers, first half of the step: issue the loads of tile c+1's own samples (they land in registers); write
+             * tile c-1 back but for its right 8 columns (still the left context of tile c); then the strip above tile c
+             * (only the horizontal edges need it), as late as possible so that the row above has time to publish SB c */
+            if (c + 1 < A.sbs_w && own_fast(c + 1)) { own_issue(c + 1, pre, mt); pre_valid = true; }
+            if (c > 0) put_body(c - 1, oth, mt, LF_HALF);
+            if (tr && mt == 0) tr[4] = lf_clock();
             if (mt == 0) wait_above(c + 1);
+            if (tr && mt == 0) tr[5] = lf_clock();
             lf_sync_movers();
             fetch(c, cur, true, mt, LF_HALF);
-            if (c > 0) put_body(c - 1, oth, mt, LF_HALF);
+            if (tr && mt == 0) tr[6] = lf_clock();
         }
+        if (tr && t == 0) tr[1] = lf_clock();
         __syncthreads(); /* vertical edges done; buffer oth is free */
+        if (tr && t == 0) tr[2] = lf_clock();
         if (!mover) {
             /* ---- horizontal edges: one thread per sample column */
             if (t < 64) { if (t < G.lw) lf_horizontal_col(ty[cur] + 8 * LF_YP + 8 + t, t, LF_YP, MY, thr); }
             else if (chroma) { const int q = (t - 64) & 31; if (q < G.cw) lf_horizontal_col((t < 96 ? tu[cur] : tv[cur]) + 8 * LF_CP + 8 + q, q, LF_CP, MC, thr); }
+            if (tr && t == 0) tr[3] = lf_clock();
         } else {
-            /* ---- movers, second half: the own samples of tile c+1 into the freed buffer; the left context of tile c is
-             * final now (horizontal edges do not reach it): with it tile c-1 is complete in memory -> publish */
-            if (c + 1 < A.sbs_w) fetch(c + 1, oth, false, mt, LF_HALF);
+            /* ---- movers, second half: the left context of tile c is final as soon as the vertical pass is over (horizontal
+             * edges do not reach it): with it tile c-1 is complete in memory -> fence, publish at once; then tile c+1's own
+             * samples go from the registers into the freed buffer */
             if (c > 0) put_left(c, cur, mt, LF_HALF);
             lf_fence();
             lf_sync_movers();
             if (mt == 0 && c > 0) lf_flag_store(mine, (A.gen << 10) | c); /* SBs 0..c-1 are final in memory */
+            if (tr && mt == 0) tr[7] = lf_clock();
+            if (c + 1 < A.sbs_w) {
+                if (pre_valid) own_commit(oth, pre, mt);
+                else fetch(c + 1, oth, false, mt, LF_HALF);
+            }
         }
     }
     __syncthreads();

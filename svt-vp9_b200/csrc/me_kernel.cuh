@@ -34,7 +34,6 @@
 #define ME_THREADS 256
 #define ME_SB 64
 #define ME_MAX_SAD (64 * 64 * 255)
-#define ME_CHUNK 32       /* search positions whose SAD pyramid is resident at once */
 #define ME_HALO_X 4       /* staged full-pel window: columns left of the search-area origin (word aligned) */
 #define ME_HALO_Y 2       /* rows above / below (the 4-tap filters reach 2 rows up, 1+1 down) */
 #define ME_HME_STRIPE 32  /* HME candidate rows staged at once (bounds the window for wide HME areas) */
@@ -465,118 +464,86 @@ __device__ __forceinline__ void me_set_window(MeSbState *st, int w, int h, int w
  * Full-pel search over the 85 partitions.
  * rb points at R(0,0) = top-left of the clipped search area inside the staged window (pitch
  * wpitch; the window also holds ME_HALO_X / ME_HALO_Y samples around it and the +16 columns of
- * the tail quirk).  Search positions are processed in chunks of ME_CHUNK; per chunk the 64
- * sub-sampled 8x8 SADs of every position are written to shared memory and summed up the
- * pyramid; every partition keeps (2*sad << 32 | raster index) minima.
+ * the tail quirk).  Work item = (group of 4 horizontally adjacent candidates, one 16x16 block):
+ * the thread accumulates the four 8x8 quadrants of its block for the four candidates from one
+ * set of window words (every other row), sums them to the 16x16 SAD in registers, and the
+ * 32x32 / 64x64 SADs come from shuffles over the 4 / 16 lanes that hold the other blocks of the
+ * same candidates -- no shared-memory pyramid, no barrier inside the search.  Every thread keeps
+ * running minima (2*sad << 32 | raster index) of "its" partitions; warps merge with shuffles,
+ * the CTA with one atomicMin per warp and partition.
  * ------------------------------------------------------------------------------------------- */
+__device__ __forceinline__ void me_key_min(unsigned long long &best, uint32_t sad, uint32_t pos, bool valid) {
+    const uint32_t v = 2u * sad;
+    if (valid && v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best) best = key; }
+}
 __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpitch, MeSbState *st, int list,
-                                  unsigned long long *pu_key /* [85] smem */, uint16_t *s8 /* [CHUNK][64] */,
-                                  uint16_t *s16 /* [CHUNK][16] */, uint32_t *s32 /* [CHUNK][4] */, uint32_t *spos /* [CHUNK] */) {
+                                  unsigned long long *pu_key /* [85] smem */) {
     const int saw = st->saw[list], sah = st->sah[list];
     const int tail_from = saw & ~7; /* columns handled by the reference's one-position routine */
-    /* candidates are taken four at a time along x (one group shares every window word); a chunk is ME_CHUNK/4 groups */
     const int ngx = (saw + 3) >> 2, ngroups = ngx * sah;
     const int t = threadIdx.x;
-    /* every thread keeps the running minima of "its" partitions over all chunks; one reduction at the end */
-    unsigned long long best8 = ~0ull, best16 = ~0ull, best32 = ~0ull, best64 = ~0ull;
-    for (int g0 = 0; g0 < ngroups; g0 += ME_CHUNK / 4) {
-        const int gn = min(ME_CHUNK / 4, ngroups - g0), cn = gn * 4;
-        /* phase 1: 8x8 SADs (rows 0,2,4,6), z-ordered so that 4 consecutive entries form a 16x16 */
-        {
-            const int z8 = t & 63, z16 = z8 >> 2, k = z8 & 3;
-            /* raster position of the 16x16 block with internal index z16 */
-            const int b16 = (z16 & 1) | ((z16 & 4) >> 1) | ((z16 & 2) << 1) | (z16 & 8);
-            const int bx = (b16 & 3) * 16 + (k & 1) * 8, by = (b16 >> 2) * 16 + (k >> 1) * 8;
-            const uint32_t *sp = (const uint32_t *)(src + by * ME_SB + bx);
-            const int p2 = wpitch >> 1; /* two rows, in words */
-            for (int gl = t >> 6; gl < gn; gl += 4) {
-                const int g = g0 + gl, ys = g / ngx, gx = g - ys * ngx;
-                /* the reference's single-position routine matches 16x16 blocks 12 and 13 sixteen
-                 * samples further right (EbMotionEstimation.c:855-856); reproduced */
-                const int skew = (4 * gx >= tail_from && (z16 == 12 || z16 == 13)) ? 16 : 0;
-                const uint32_t *wp = (const uint32_t *)(rb + (ys + by) * wpitch + 4 * gx + bx + skew);
-                uint32_t a0 = 0, a1 = 0, a2 = 0, a3 = 0;
+    for (int i = t; i < 85; i += ME_THREADS) pu_key[i] = ((unsigned long long)ME_MAX_SAD << 32) | 0xffffffffu;
+    const int z16 = t & 15, gl = t >> 4;
+    /* raster position of the 16x16 block with internal index z16 */
+    const int b16 = (z16 & 1) | ((z16 & 4) >> 1) | ((z16 & 2) << 1) | (z16 & 8);
+    const int bx = (b16 & 3) * 16, by = (b16 >> 2) * 16;
+    const uint32_t *sp = (const uint32_t *)(src + by * ME_SB + bx);
+    const int p2 = wpitch >> 1; /* two rows, in words */
+    const bool skewed = (z16 == 12 || z16 == 13);
+    unsigned long long b8[4] = {~0ull, ~0ull, ~0ull, ~0ull}, b16k = ~0ull, b32k = ~0ull, b64k = ~0ull;
+    for (int g0 = 0; g0 < ngroups; g0 += ME_THREADS / 16) {
+        const int g = g0 + gl;
+        const bool active = g < ngroups;
+        const int ga = active ? g : 0, ys = ga / ngx, gx = ga - ys * ngx;
+        /* the reference's single-position routine matches 16x16 blocks 12 and 13 sixteen samples further right
+         * (EbMotionEstimation.c:855-856); reproduced */
+        const int skew = (skewed && 4 * gx >= tail_from) ? 16 : 0;
+        const uint32_t *wp = (const uint32_t *)(rb + (ys + by) * wpitch + 4 * gx + bx + skew);
+        uint32_t acc[4][4]; /* [candidate][quadrant: 0 TL, 1 TR, 2 BL, 3 BR] */
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const uint32_t w0 = wp[r * p2], w1 = wp[r * p2 + 1], w2 = wp[r * p2 + 2];
-                    const uint32_t s0 = sp[r * 32], s1 = sp[r * 32 + 1];
-                    a0 = me_absdiff_acc(w0, s0, a0); a0 = me_absdiff_acc(w1, s1, a0);
-                    a1 = me_absdiff_acc(__funnelshift_r(w0, w1, 8), s0, a1); a1 = me_absdiff_acc(__funnelshift_r(w1, w2, 8), s1, a1);
-                    a2 = me_absdiff_acc(__funnelshift_r(w0, w1, 16), s0, a2); a2 = me_absdiff_acc(__funnelshift_r(w1, w2, 16), s1, a2);
-                    a3 = me_absdiff_acc(__funnelshift_r(w0, w1, 24), s0, a3); a3 = me_absdiff_acc(__funnelshift_r(w1, w2, 24), s1, a3);
-                }
-                uint16_t *o = s8 + (gl * 4) * 64 + z8;
-                o[0] = (uint16_t)a0; o[64] = (uint16_t)a1; o[128] = (uint16_t)a2; o[192] = (uint16_t)a3;
-                /* this thread's own four candidates of its 8x8 partition */
-                const uint32_t pos0 = (uint32_t)(ys * saw + 4 * gx);
-                const uint32_t av[4] = {a0, a1, a2, a3};
+        for (int j = 0; j < 4; j++) acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0;
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const uint32_t v = 2u * av[j];
-                    if (4 * gx + j < saw && v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | (pos0 + j); if (key < best8) best8 = key; }
-                }
-            }
-            if (t < cn) { /* raster index of every slot of the chunk (invalid beyond the right edge of the area) */
-                const int g = g0 + (t >> 2), ys = g / ngx, xs = 4 * (g - ys * ngx) + (t & 3);
-                spos[t] = xs < saw ? (uint32_t)(ys * saw + xs) : 0xffffffffu;
-            }
-        }
-        __syncthreads();
-        /* phase 2: 16x16 sums */
-        {
-            const int z16 = t & 15, l16 = t >> 4;
-            for (int pp = l16; pp < cn; pp += 16) {
-                const uint16_t *q = s8 + pp * 64 + z16 * 4;
-                const uint32_t sum = (uint32_t)q[0] + q[1] + q[2] + q[3], pos = spos[pp];
-                s16[pp * 16 + z16] = (uint16_t)sum;
-                const uint32_t v = 2u * sum;
-                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best16) best16 = key; }
+        for (int r = 0; r < 8; r++) {
+            const uint32_t *w = wp + r * p2;
+            const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
+            const uint32_t s0 = sp[r * 32], s1 = sp[r * 32 + 1], s2 = sp[r * 32 + 2], s3 = sp[r * 32 + 3];
+            const int q = r < 4 ? 0 : 2;
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const uint32_t sh = 8 * j;
+                acc[j][q] = me_absdiff_acc(j ? __funnelshift_r(w0, w1, sh) : w0, s0, acc[j][q]);
+                acc[j][q] = me_absdiff_acc(j ? __funnelshift_r(w1, w2, sh) : w1, s1, acc[j][q]);
+                acc[j][q + 1] = me_absdiff_acc(j ? __funnelshift_r(w2, w3, sh) : w2, s2, acc[j][q + 1]);
+                acc[j][q + 1] = me_absdiff_acc(j ? __funnelshift_r(w3, w4, sh) : w3, s3, acc[j][q + 1]);
             }
         }
-        __syncthreads();
-        /* phase 3: 32x32 */
-        {
-            const int q32 = t & 3, l32 = t >> 2;
-            for (int pp = l32; pp < cn; pp += 64) {
-                const uint16_t *q = s16 + pp * 16 + q32 * 4;
-                const uint32_t sum = (uint32_t)q[0] + q[1] + q[2] + q[3], pos = spos[pp];
-                s32[pp * 4 + q32] = sum;
-                const uint32_t v = 2u * sum;
-                if (v < ME_MAX_SAD && pos != 0xffffffffu) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best32) best32 = key; }
-            }
+        const uint32_t pos0 = (uint32_t)(ys * saw + 4 * gx);
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const bool valid = active && 4 * gx + j < saw;
+            const uint32_t s16 = acc[j][0] + acc[j][1] + acc[j][2] + acc[j][3];
+            uint32_t s32 = s16 + __shfl_xor_sync(0xffffffffu, s16, 1);
+            s32 += __shfl_xor_sync(0xffffffffu, s32, 2);
+            uint32_t s64 = s32 + __shfl_xor_sync(0xffffffffu, s32, 4);
+            s64 += __shfl_xor_sync(0xffffffffu, s64, 8);
+#pragma unroll
+            for (int q = 0; q < 4; q++) me_key_min(b8[q], acc[j][q], pos0 + j, valid);
+            me_key_min(b16k, s16, pos0 + j, valid);
+            me_key_min(b32k, s32, pos0 + j, valid);
+            me_key_min(b64k, s64, pos0 + j, valid);
         }
-        __syncthreads();
-        /* phase 4: 64x64 */
-        if (t < cn && spos[t] != 0xffffffffu) {
-            const uint32_t *q = s32 + t * 4;
-            const uint32_t v = 2u * (q[0] + q[1] + q[2] + q[3]);
-            if (v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | spos[t]; if (key < best64) best64 = key; }
-        }
-        __syncthreads();
     }
-    /* ---- reduce: 8x8 partitions live on threads z8 + 64*{0..3}; 16x16 on lanes z16, z16+16 of every warp; 32x32 on the
-     * lanes = q32 (mod 4) of every warp; 64x64 on warp 0.  s8 (free now) is the exchange buffer. */
-    unsigned long long *x8 = (unsigned long long *)s8, *x16 = x8 + 256, *x32 = x16 + 128;
-    const unsigned long long none = ((unsigned long long)ME_MAX_SAD << 32) | 0xffffffffu;
-    x8[t] = best8;
-    best16 = me_shfl_min64(best16, 16);
-    best32 = me_shfl_min64(best32, 4 | 8 | 16);
-    if ((t & 31) < 16) x16[(t >> 5) * 16 + (t & 15)] = best16;
-    if ((t & 31) < 4) x32[(t >> 5) * 4 + (t & 3)] = best32;
-    if (t < 32) { best64 = me_shfl_min64(best64, 31); if (t == 0) pu_key[0] = best64 != ~0ull ? best64 : none; }
-    __syncthreads();
-    if (t < 64) {
-        unsigned long long m = x8[t];
-        for (int i = 1; i < 4; i++) m = x8[t + 64 * i] < m ? x8[t + 64 * i] : m;
-        pu_key[21 + t] = m != ~0ull ? m : none;
-    } else if (t < 80) {
-        unsigned long long m = ~0ull;
-        for (int i = 0; i < 8; i++) m = x16[i * 16 + (t - 64)] < m ? x16[i * 16 + (t - 64)] : m;
-        pu_key[5 + (t - 64)] = m != ~0ull ? m : none;
-    } else if (t < 84) {
-        unsigned long long m = ~0ull;
-        for (int i = 0; i < 8; i++) m = x32[i * 4 + (t - 80)] < m ? x32[i * 4 + (t - 80)] : m;
-        pu_key[1 + (t - 80)] = m != ~0ull ? m : none;
+    /* the two half-warps hold different candidate groups of the same blocks */
+#pragma unroll
+    for (int q = 0; q < 4; q++) b8[q] = me_shfl_min64(b8[q], 16);
+    b16k = me_shfl_min64(b16k, 16); b32k = me_shfl_min64(b32k, 16); b64k = me_shfl_min64(b64k, 16);
+    __syncthreads(); /* pu_key initialised */
+    if ((t & 31) < 16) {
+#pragma unroll
+        for (int q = 0; q < 4; q++) if (b8[q] != ~0ull) atomicMin(&pu_key[21 + z16 * 4 + q], b8[q]);
+        if (b16k != ~0ull) atomicMin(&pu_key[5 + z16], b16k);
+        if ((z16 & 3) == 0 && b32k != ~0ull) atomicMin(&pu_key[1 + (z16 >> 2)], b32k);
+        if (z16 == 0 && b64k != ~0ull) atomicMin(&pu_key[0], b64k);
     }
     __syncthreads();
 }
@@ -956,7 +923,7 @@ __device__ __forceinline__ uint32_t me_pred_word(const MePred &p, int y, int k) 
  * shared-memory layout of one CTA and the launch plan (shared by the host code and the emulation)
  * ------------------------------------------------------------------------------------------- */
 struct MeSmemLayout {
-    int src, hsrc, win, interp, bip0, s8, s16, s32, pu_key, bsad, bmv, bssd, bip, dir, posacc, dist, sad, state, total;
+    int src, hsrc, win, interp, bip0, pu_key, bsad, bmv, bssd, bip, dir, posacc, dist, sad, state, total;
 };
 __host__ __device__ static inline int me_align16(int v) { return (v + 15) & ~15; }
 __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int interp_plane_bytes, int interp_in_smem, int bip0_bytes) {
@@ -967,9 +934,6 @@ __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int
     L.win = o; o += me_align16(win_bytes);
     L.interp = o; o += interp_in_smem ? 3 * me_align16(interp_plane_bytes) : 0; /* the planes of the list being searched */
     L.bip0 = o; o += me_align16(bip0_bytes);                                  /* list-0 predictions kept for bi-prediction */
-    L.s8 = o; o += ME_CHUNK * 64 * 2;
-    L.s16 = o; o += ME_CHUNK * 16 * 2;
-    L.s32 = o; o += ME_CHUNK * 4 * 4;
     L.pu_key = o; o += me_align16(85 * 8);
     L.bsad = o; o += me_align16(2 * 85 * 4);
     L.bmv = o; o += me_align16(2 * 85 * 4);
@@ -1120,8 +1084,6 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
     const SvtB200MeParams &P = A.P;
     const MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, A.interp_in_smem, me_bip0_bytes(A.P));
     uint8_t  *src = smem + L.src, *hsrc = smem + L.hsrc, *win = smem + L.win;
-    uint16_t *s8 = (uint16_t *)(smem + L.s8), *s16 = (uint16_t *)(smem + L.s16);
-    uint32_t *s32 = (uint32_t *)(smem + L.s32);
     unsigned long long *pu_key = (unsigned long long *)(smem + L.pu_key);
     uint32_t *bsad = (uint32_t *)(smem + L.bsad), *bmv = (uint32_t *)(smem + L.bmv), *bssd = (uint32_t *)(smem + L.bssd);
     uint32_t *bip = (uint32_t *)(smem + L.bip), *posacc = (uint32_t *)(smem + L.posacc);
@@ -1277,7 +1239,7 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
         me_stage_window(win, fpp, rp, st->ox + st->sa_ox[list] - ME_HALO_X, st->oy + st->sa_oy[list] - ME_HALO_Y,
                         st->saw[list] + ME_SB - 1 + 16 + ME_HALO_X, me_fp_rows(st->sah[list]));
         __syncthreads();
-        me_fullpel(src, rb, fpp, st, list, pu_key, s8, s16, s32, posacc);
+        me_fullpel(src, rb, fpp, st, list, pu_key);
         if (t < 85) {
             const unsigned long long k = pu_key[t];
             const uint32_t pos = (uint32_t)(k & 0xffffffffu);
