@@ -276,6 +276,8 @@ def main():
                           "transform/quantise/reconstruct pass over every TU (luma 32x32, chroma 16x16, q 45) + deblocking on the "
                           "base-layer picture; 16-picture hierarchical mini-GOP in encode order",
               "pictures_per_step": 1,
+              "queues": "motion estimation on the context's first compute queue, transform pass + deblocking on its second (they belong to different "
+                        "pictures in the encoder); value = CUDA events around the K steps with both queues joined inside the timed region",
               "l2": "17 distinct pictures (165 MB of luma planes + 105 MB chroma) cycled: working set larger than the 126 MB L2",
               "parallelism": "pictures sharded across GPUs (independent mini-GOP streams per rank), no collective on the data path"}
 
@@ -380,16 +382,27 @@ def main():
     alg = {"me_sb_kernel": 0, "txq_kernel": 0, "lf_row_kernel": 0}
     marks = []
 
-    def kernels(i, timed, slot=0):
+    # The transform pass and the deblocking of a picture go to the context's second compute queue: in the encoder they belong to
+    # a different (earlier) picture than the one being motion-estimated, and their CTAs fill the tail of the ME grid.
+    ctx.select_compute(api.COMPUTE2)
+    stream2 = torch.cuda.ExternalStream(L.svtb200_stream(h), device=torch.device("cuda", local_rank))
+    ctx.select_compute(api.COMPUTE)
+
+    def kernels(i, timed, slot=0, overlap=True, sink=None):
         n = ENCODE_ORDER[i % 16]
+        s2 = stream2 if overlap else stream
         P, (r0, r1) = me_params(n)
         ids = (C.c_uint64 * 2)(r0, r1)
-        e = [ev() for _ in range(4)] if timed else None
+        e = [ev() for _ in range(6)] if timed else None
         if timed:
             e[0].record(stream)
         ctx.check(L.svtb200_me_picture_dev(h, C.byref(P), n, ids, d_me[slot], None), "me_picture_dev")
         if timed:
             e[1].record(stream)
+        if overlap:
+            ctx.select_compute(api.COMPUTE2)
+        if timed:
+            e[2].record(s2)
         ybytes = sy * dplane[n].padded_height
         rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
         pl = txq_planes(dplane[n].buf, sy, ybytes, dplane[r0].buf, rec[0], W4K, W4K * H4K)
@@ -398,12 +411,15 @@ def main():
             pl = txq_planes(dc[n], W4K // 2, csize, pc[r0], rec[1 + k], W4K // 2, csize)
             ctx.check(L.svtb200_txq_batch_dev(h, 2, N_TU_C, d_jobs_c, C.byref(pl), d_rows, 1, None, q[16][k], d_dq[16][k], eob[16][k]), "txq c")
         if timed:
-            e[2].record(stream)
+            e[3].record(s2)
         if n == 16:
             ctx.check(L.svtb200_deblock_picture_dev(h, C.byref(LfP), rec[0], W4K, rec[1], rec[2], W4K // 2, d_lfm, 60, d_thr), "deblock")
         if timed:
-            e[3].record(stream)
-            marks.append((e, P, n))
+            e[4].record(s2)
+            (marks if sink is None else sink).append((e, P, n))
+        L.svtb200_picture_touch(h, n)      # the transform kernels read the planes of pictures n and r0 on this queue
+        L.svtb200_picture_touch(h, r0)
+        ctx.select_compute(api.COMPUTE)
         return n, r0
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI's three queues.  Picture i+1 uploads and
@@ -426,14 +442,14 @@ def main():
             ctx.check(L.svtb200_memcpy_h2d_async(h, d_u[n], pu[n].data_ptr(), csize), "h2d u")     # H2D chroma
             ctx.check(L.svtb200_memcpy_h2d_async(h, d_v[n], pv[n].data_ptr(), csize), "h2d v")
             ctx.fence(api.UPLOAD, api.COMPUTE)
+            ctx.fence(api.UPLOAD, api.COMPUTE2)
         if "kernels" in skip:
             r0 = n
         else:
             _, r0 = kernels(i, False, slot)
-        L.svtb200_picture_touch(h, n)
-        L.svtb200_picture_touch(h, r0)
-        chroma_used[n] = chroma_used[r0] = ctx.marker(api.COMPUTE)
+        chroma_used[n] = chroma_used[r0] = ctx.marker(api.COMPUTE2)
         ctx.stream_wait(api.DOWNLOAD, chroma_used[n])
+        ctx.fence(api.COMPUTE, api.DOWNLOAD)
         rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
         d2h = lambda hb, db, nb: ("d2h" in skip) or ctx.check(L.svtb200_memcpy_d2h_async(h, hb.data_ptr(), db, nb), "d2h")
         d2h(h_me[slot], d_me[slot], N_SB * 85 * 40)                             # D2H ME results
@@ -464,8 +480,10 @@ def main():
     e0, e1 = ev(), ev()
     launches0 = ctx.launches()
     e0.record(stream)
+    ctx.fence(api.COMPUTE, api.COMPUTE2)   # the second queue starts inside the timed region ...
     for i in range(args.steps):
         kernels(args.warmup + i, True)
+    ctx.fence(api.COMPUTE2, api.COMPUTE)   # ... and ends inside it
     e1.record(stream)
     ctx.sync()
     barrier()
@@ -474,9 +492,20 @@ def main():
     n_me = 0
     for e, P, n in marks:
         stage_ms["me_sb_kernel"] += e[0].elapsed_time(e[1]); alg["me_sb_kernel"] += me_bytes(P); n_me += 1
-        stage_ms["txq_kernel"] += e[1].elapsed_time(e[2]); alg["txq_kernel"] += txq_bytes()
+        stage_ms["txq_kernel"] += e[2].elapsed_time(e[3]); alg["txq_kernel"] += txq_bytes()
         if n == 16:
-            stage_ms["lf_row_kernel"] += e[2].elapsed_time(e[3]); alg["lf_row_kernel"] += lf_bytes()
+            stage_ms["lf_row_kernel"] += e[3].elapsed_time(e[4]); alg["lf_row_kernel"] += lf_bytes()
+    # the same kernels one at a time (single queue): durations without the other queue's interference
+    iso_marks, iso_ms = [], {"me_sb_kernel": 0.0, "txq_kernel": 0.0, "lf_row_kernel": 0.0}
+    iso_n = {"me_sb_kernel": 0, "txq_kernel": 0, "lf_row_kernel": 0}
+    for i in range(16):
+        kernels(i, True, 0, overlap=False, sink=iso_marks)
+    ctx.sync()
+    for e, P, n in iso_marks:
+        iso_ms["me_sb_kernel"] += e[0].elapsed_time(e[1]); iso_n["me_sb_kernel"] += 1
+        iso_ms["txq_kernel"] += e[2].elapsed_time(e[3]); iso_n["txq_kernel"] += 1
+        if n == 16:
+            iso_ms["lf_row_kernel"] += e[3].elapsed_time(e[4]); iso_n["lf_row_kernel"] += 1
     for i in range(min(args.warmup, 4)):
         step_e2e(i)
     barrier()
@@ -516,8 +545,11 @@ def main():
     for k in stage_ms:
         if stage_ms[k] > 0:
             a = alg[k] / (stage_ms[k] / 1000.0) / 1e9
+            per_pic = alg[k] / {"me_sb_kernel": n_me, "txq_kernel": n_me, "lf_row_kernel": max(1, sum(1 for m in marks if m[2] == 16))}[k]
+            iso = iso_ms[k] / max(1, iso_n[k])
             per_kernel[k] = {"ms_total": stage_ms[k], "share": stage_ms[k] / sum(stage_ms.values()), "achieved_gbs": a, "frac": a / peak,
-                             "traffic": traffic.get(k)}
+                             "traffic": traffic.get(k), "ms_per_picture_alone": iso, "achieved_gbs_alone": per_pic / (iso / 1000.0) / 1e9 if iso else None,
+                             "frac_alone": per_pic / (iso / 1000.0) / 1e9 / peak if iso else None}
     launches_dom = n_me if dom == "me_sb_kernel" else (3 * n_me if dom == "txq_kernel" else max(1, args.steps // 16))
     roof = {"bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"],
             "traffic": traffic.get(dom), "kernel": dom, "alg_bytes_per_launch": alg[dom] / launches_dom,

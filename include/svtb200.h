@@ -73,6 +73,10 @@ int   svtb200_memcpy_d2h(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, s
 #define SVTB200_STREAM_COMPUTE  0
 #define SVTB200_STREAM_UPLOAD   1
 #define SVTB200_STREAM_DOWNLOAD 2
+#define SVTB200_STREAM_COMPUTE2 3 /* second compute queue: work of a DIFFERENT picture (e.g. the deblocking of picture n beside the
+                                    motion estimation of picture n+1) fills the tail of the other queue's kernels */
+/* kernels of the following *_dev / host-pointer calls go to compute queue 'which' (COMPUTE or COMPUTE2); not thread safe */
+int svtb200_select_compute(SvtB200Ctx *ctx, int which);
 int svtb200_memcpy_h2d_async(SvtB200Ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int svtb200_memcpy_d2h_async(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 int svtb200_marker(SvtB200Ctx *ctx, int stream, uint64_t *ticket);

@@ -119,6 +119,7 @@ def lib():
         L.svtb200_picture_touch.argtypes = [C.c_void_p, C.c_uint64]
         L.svtb200_memcpy_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.svtb200_memcpy_d2h_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.svtb200_select_compute.argtypes = [C.c_void_p, C.c_int]
         L.svtb200_marker.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
         L.svtb200_stream_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
         L.svtb200_fence.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -134,7 +135,7 @@ def lib():
     return _lib
 
 
-COMPUTE, UPLOAD, DOWNLOAD = 0, 1, 2
+COMPUTE, UPLOAD, DOWNLOAD, COMPUTE2 = 0, 1, 2, 3
 
 
 class Context:
@@ -196,6 +197,9 @@ class Context:
 
     def stream_wait(self, stream, ticket):
         self.check(self.L.svtb200_stream_wait(self.h, stream, ticket), "stream_wait")
+
+    def select_compute(self, which):
+        self.check(self.L.svtb200_select_compute(self.h, which), "select_compute")
 
     def fence(self, src, dst):
         self.check(self.L.svtb200_fence(self.h, src, dst), "fence")
