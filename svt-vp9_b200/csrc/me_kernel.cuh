@@ -364,6 +364,7 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
         /* 4 horizontally adjacent candidates per thread share every window word */
         const int ngx = (saw + 3) >> 2, ngroups = ngx * nrows, sp32 = st->s_pitch >> 2, wp32 = st->w_pitch >> 2;
         const uint32_t rcp = 0xffffffffu / (uint32_t)ngx + 1u; /* __umulhi(g, rcp) == g / ngx */
+        uint32_t bv = 0xffffffu, bp = 0;
         for (int g = threadIdx.x; g < ngroups; g += ME_THREADS) {
             const int ys = (int)__umulhi((uint32_t)g, rcp), gx = g - ys * ngx;
             const uint32_t *wrow0 = (const uint32_t *)win + ys * wp32 + gx;
@@ -387,12 +388,10 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
             }
             const uint32_t pos0 = (uint32_t)((y0 + ys) * saw + 4 * gx);
 #pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (4 * gx + j < saw && acc[j] < 0xffffffu) {
-                    const unsigned long long key = ((unsigned long long)acc[j] << 32) | (pos0 + j);
-                    if (key < best) best = key;
-                }
+            for (int j = 0; j < 4; j++) /* raster order is increasing along a thread's groups: strict < keeps the first minimum */
+                if (4 * gx + j < saw && acc[j] < bv) { bv = acc[j]; bp = pos0 + j; }
         }
+        if (bv < 0xffffffu) best = ((unsigned long long)bv << 32) | bp;
     } else {
         /* few positions: split every candidate's rows over P threads */
         int P = 1;
@@ -472,9 +471,15 @@ __device__ __forceinline__ void me_set_window(MeSbState *st, int w, int h, int w
  * running minima (2*sad << 32 | raster index) of "its" partitions; warps merge with shuffles,
  * the CTA with one atomicMin per warp and partition.
  * ------------------------------------------------------------------------------------------- */
-__device__ __forceinline__ void me_key_min(unsigned long long &best, uint32_t sad, uint32_t pos, bool valid) {
+/* a thread visits its candidates in increasing raster order, so "first minimum" is a strict < on the SAD alone; the
+ * 64-bit (sad, index) key is only built when threads merge */
+struct MeBest { uint32_t v, pos; };
+__device__ __forceinline__ void me_best_upd(MeBest &b, uint32_t sad, uint32_t pos, bool valid) {
     const uint32_t v = 2u * sad;
-    if (valid && v < ME_MAX_SAD) { const unsigned long long key = ((unsigned long long)v << 32) | pos; if (key < best) best = key; }
+    if (valid && v < b.v) { b.v = v; b.pos = pos; }
+}
+__device__ __forceinline__ unsigned long long me_best_key(const MeBest &b) {
+    return b.v < ME_MAX_SAD ? ((unsigned long long)b.v << 32) | b.pos : ~0ull;
 }
 __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpitch, MeSbState *st, int list,
                                   unsigned long long *pu_key /* [85] smem */) {
@@ -490,7 +495,8 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
     const uint32_t *sp = (const uint32_t *)(src + by * ME_SB + bx);
     const int p2 = wpitch >> 1; /* two rows, in words */
     const bool skewed = (z16 == 12 || z16 == 13);
-    unsigned long long b8[4] = {~0ull, ~0ull, ~0ull, ~0ull}, b16k = ~0ull, b32k = ~0ull, b64k = ~0ull;
+    const MeBest none = {ME_MAX_SAD, 0xffffffffu};
+    MeBest r8[4] = {none, none, none, none}, r16 = none, r32 = none, r64 = none;
     for (int g0 = 0; g0 < ngroups; g0 += ME_THREADS / 16) {
         const int g = g0 + gl;
         const bool active = g < ngroups;
@@ -527,16 +533,17 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
             uint32_t s64 = s32 + __shfl_xor_sync(0xffffffffu, s32, 4);
             s64 += __shfl_xor_sync(0xffffffffu, s64, 8);
 #pragma unroll
-            for (int q = 0; q < 4; q++) me_key_min(b8[q], acc[j][q], pos0 + j, valid);
-            me_key_min(b16k, s16, pos0 + j, valid);
-            me_key_min(b32k, s32, pos0 + j, valid);
-            me_key_min(b64k, s64, pos0 + j, valid);
+            for (int q = 0; q < 4; q++) me_best_upd(r8[q], acc[j][q], pos0 + j, valid);
+            me_best_upd(r16, s16, pos0 + j, valid);
+            me_best_upd(r32, s32, pos0 + j, valid);
+            me_best_upd(r64, s64, pos0 + j, valid);
         }
     }
     /* the two half-warps hold different candidate groups of the same blocks */
+    unsigned long long b8[4], b16k, b32k, b64k;
 #pragma unroll
-    for (int q = 0; q < 4; q++) b8[q] = me_shfl_min64(b8[q], 16);
-    b16k = me_shfl_min64(b16k, 16); b32k = me_shfl_min64(b32k, 16); b64k = me_shfl_min64(b64k, 16);
+    for (int q = 0; q < 4; q++) b8[q] = me_shfl_min64(me_best_key(r8[q]), 16);
+    b16k = me_shfl_min64(me_best_key(r16), 16); b32k = me_shfl_min64(me_best_key(r32), 16); b64k = me_shfl_min64(me_best_key(r64), 16);
     __syncthreads(); /* pu_key initialised */
     if ((t & 31) < 16) {
 #pragma unroll
