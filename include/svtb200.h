@@ -293,6 +293,22 @@ typedef struct SvtB200LfParams {
     int32_t filter_level;          /* lf->filter_level; 0 -> no-op */
 } SvtB200LfParams;
 
+/* What eb_vp9_setup_mask() (Source/Lib/VPX/vp9_loopfilter.c:901) reads of one ModeInfo (vp9_blockd.h:70-95), per 8x8
+ * mode-info unit: the block size enum (BLOCK_4X4 = 0 ... BLOCK_64X64 = 12), the luma transform size (TX_4X4 = 0 ... TX_32X32 = 3),
+ * mi->skip && is_inter_block(mi), and get_filter_level(&cm->lf_info, mi) (:242).  Every unit of a block carries the block's values
+ * (as mi_grid_visible points every unit at its block). */
+typedef struct SvtB200LfModeInfo {
+    uint8_t sb_type, tx_size, skip_inter, filter_level;
+} SvtB200LfModeInfo;
+
+/* eb_vp9_build_mask_frame() (vp9_loopfilter.c:1548) for a whole picture: one SvtB200LfMask (= LOOP_FILTER_MASK) per 64x64
+ * super-block at lfm[r * lfm_stride + c], BEFORE eb_vp9_adjust_mask (svtb200_deblock_picture applies that itself).
+ * mi: mi_rows x mi_stride units.  The _dev variant leaves the masks on the device for svtb200_deblock_picture_dev. */
+int svtb200_build_masks(SvtB200Ctx *ctx, int32_t mi_rows, int32_t mi_cols, const SvtB200LfModeInfo *mi, int32_t mi_stride,
+                        SvtB200LfMask *lfm, int32_t lfm_stride);
+int svtb200_build_masks_dev(SvtB200Ctx *ctx, int32_t mi_rows, int32_t mi_cols, const SvtB200LfModeInfo *mi_dev, int32_t mi_stride,
+                            SvtB200LfMask *lfm_dev, int32_t lfm_stride);
+
 /* In-place eb_vp9_loop_filter_frame on HOST planes y/u/v (pointers at picture origin). */
 int svtb200_deblock_picture(SvtB200Ctx *ctx, const SvtB200LfParams *p, uint8_t *y, int32_t y_stride,
                             uint8_t *u, uint8_t *v, int32_t uv_stride, const SvtB200LfMask *lfm,

@@ -200,3 +200,88 @@ void svtb200_oracle_deblock_picture(const SvtB200LfParams *p, uint8_t *y, int y_
             }
         }
 }
+
+
+/* ---------------------------------------------------------------------------------------------------------------------
+ * Edge-mask construction: eb_vp9_build_mask_frame (Source/Lib/VPX/vp9_loopfilter.c:1548) -> eb_vp9_setup_mask (:901-1018)
+ * -> build_masks (:677-748) / build_y_mask (:753-784), with the lookup tables the reference keeps at :36-200 restated as
+ * explicit literals in the reference's own index order (BLOCK_SIZE 0..12, TX_SIZE 0..3).
+ * ------------------------------------------------------------------------------------------------------------------- */
+static const uint64_t o_left_pred[13] = {0x1ull, 0x1ull, 0x1ull, 0x1ull, 0x0101ull, 0x1ull, 0x0101ull, 0x01010101ull, 0x0101ull,
+                                         0x01010101ull, 0x0101010101010101ull, 0x01010101ull, 0x0101010101010101ull};
+static const uint64_t o_above_pred[13] = {0x1ull, 0x1ull, 0x1ull, 0x1ull, 0x1ull, 0x3ull, 0x3ull, 0x3ull, 0xfull, 0xfull, 0xfull, 0xffull, 0xffull};
+static const uint64_t o_size_mask[13] = {0x1ull, 0x1ull, 0x1ull, 0x1ull, 0x0101ull, 0x3ull, 0x0303ull, 0x03030303ull, 0x0f0full, 0x0f0f0f0full,
+                                         0x0f0f0f0f0f0f0f0full, 0xffffffffull, 0xffffffffffffffffull};
+static const uint16_t o_left_pred_uv[13] = {0x1, 0x1, 0x1, 0x1, 0x1, 0x1, 0x1, 0x11, 0x1, 0x11, 0x1111, 0x11, 0x1111};
+static const uint16_t o_above_pred_uv[13] = {0x1, 0x1, 0x1, 0x1, 0x1, 0x1, 0x1, 0x1, 0x3, 0x3, 0x3, 0xf, 0xf};
+static const uint16_t o_size_mask_uv[13] = {0x1, 0x1, 0x1, 0x1, 0x1, 0x1, 0x1, 0x11, 0x3, 0x33, 0x3333, 0xff, 0xffff};
+static const uint64_t o_left_tx[4] = {0xffffffffffffffffull, 0xffffffffffffffffull, 0x5555555555555555ull, 0x1111111111111111ull};
+static const uint64_t o_above_tx[4] = {0xffffffffffffffffull, 0xffffffffffffffffull, 0x00ff00ff00ff00ffull, 0x000000ff000000ffull};
+static const uint16_t o_left_tx_uv[4] = {0xffff, 0xffff, 0x5555, 0x1111};
+static const uint16_t o_above_tx_uv[4] = {0xffff, 0xffff, 0x0f0f, 0x000f};
+static const uint8_t o_w8[13] = {1, 1, 1, 1, 1, 2, 2, 2, 4, 4, 4, 8, 8}, o_h8[13] = {1, 1, 1, 1, 2, 1, 2, 4, 2, 4, 8, 4, 8};
+/* eb_vp9_uv_txsize_lookup[bs][tx][1][1] (4:2:0) */
+static const uint8_t o_uv_tx[13][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 0, 0, 0}, {0, 1, 1, 1},
+                                       {0, 1, 1, 1}, {0, 1, 1, 1}, {0, 1, 2, 2}, {0, 1, 2, 2}, {0, 1, 2, 2}, {0, 1, 2, 3}};
+
+static void o_build(const SvtB200LfModeInfo *mi, int sy, int su, int uv, SvtB200LfMask *m) {
+    const int bs = mi->sb_type, tx = mi->tx_size, txu = o_uv_tx[bs][tx];
+    if (!mi->filter_level) return;
+    for (int i = 0; i < o_h8[bs]; i++) memset(&m->lfl_y[sy + 8 * i], mi->filter_level, o_w8[bs]);
+    m->above_y[tx] |= o_above_pred[bs] << sy; m->left_y[tx] |= o_left_pred[bs] << sy;
+    if (uv) { m->above_uv[txu] |= (uint16_t)(o_above_pred_uv[bs] << su); m->left_uv[txu] |= (uint16_t)(o_left_pred_uv[bs] << su); }
+    if (mi->skip_inter) return;
+    m->above_y[tx] |= (o_size_mask[bs] & o_above_tx[tx]) << sy; m->left_y[tx] |= (o_size_mask[bs] & o_left_tx[tx]) << sy;
+    if (uv) {
+        m->above_uv[txu] |= (uint16_t)((o_size_mask_uv[bs] & o_above_tx_uv[txu]) << su);
+        m->left_uv[txu] |= (uint16_t)((o_size_mask_uv[bs] & o_left_tx_uv[txu]) << su);
+    }
+    if (tx == 0) m->int_4x4_y |= o_size_mask[bs] << sy;
+    if (uv && txu == 0) m->int_4x4_uv |= (uint16_t)((o_size_mask_uv[bs] & 0xffff) << su);
+}
+
+void svtb200_oracle_build_masks(int mi_rows, int mi_cols, const SvtB200LfModeInfo *mi, int stride, SvtB200LfMask *lfm, int lfm_stride) {
+    static const int s32y[4] = {0, 4, 32, 36}, s16y[4] = {0, 2, 16, 18}, s8y[4] = {0, 1, 8, 9}, s32u[4] = {0, 2, 8, 10}, s16u[4] = {0, 1, 4, 5};
+    for (int mr = 0; mr < mi_rows; mr += 8)
+        for (int mc = 0; mc < mi_cols; mc += 8) {
+            SvtB200LfMask *m = &lfm[(mr >> 3) * lfm_stride + (mc >> 3)];
+            const SvtB200LfModeInfo *p = mi + (size_t)mr * stride + mc;
+            const int max_rows = mr + 8 > mi_rows ? mi_rows - mr : 8, max_cols = mc + 8 > mi_cols ? mi_cols - mc : 8;
+            memset(m, 0, sizeof(*m));
+            switch (p->sb_type) {
+            case 12: o_build(p, 0, 0, 1, m); break;
+            case 11: o_build(p, 0, 0, 1, m); if (4 < max_rows) o_build(p + 4 * stride, 32, 8, 1, m); break;
+            case 10: o_build(p, 0, 0, 1, m); if (4 < max_cols) o_build(p + 4, 4, 2, 1, m); break;
+            default:
+                for (int a = 0; a < 4; a++) {
+                    const int c32 = (a & 1) << 2, r32 = (a >> 1) << 2;
+                    const SvtB200LfModeInfo *q = p + r32 * stride + c32;
+                    if (c32 >= max_cols || r32 >= max_rows) continue;
+                    switch (q->sb_type) {
+                    case 9: o_build(q, s32y[a], s32u[a], 1, m); break;
+                    case 8: o_build(q, s32y[a], s32u[a], 1, m); if (r32 + 2 < max_rows) o_build(q + 2 * stride, s32y[a] + 16, s32u[a] + 4, 1, m); break;
+                    case 7: o_build(q, s32y[a], s32u[a], 1, m); if (c32 + 2 < max_cols) o_build(q + 2, s32y[a] + 2, s32u[a] + 1, 1, m); break;
+                    default:
+                        for (int b = 0; b < 4; b++) {
+                            const int c16 = c32 + ((b & 1) << 1), r16 = r32 + ((b >> 1) << 1);
+                            const SvtB200LfModeInfo *t = p + r16 * stride + c16;
+                            const int sy = s32y[a] + s16y[b], su = s32u[a] + s16u[b];
+                            if (c16 >= max_cols || r16 >= max_rows) continue;
+                            switch (t->sb_type) {
+                            case 6: o_build(t, sy, su, 1, m); break;
+                            case 5: o_build(t, sy, su, 1, m); if (r16 + 1 < max_rows) o_build(t + stride, sy + 8, 0, 0, m); break;
+                            case 4: o_build(t, sy, su, 1, m); if (c16 + 1 < max_cols) o_build(t + 1, sy + 1, 0, 0, m); break;
+                            default:
+                                o_build(t, sy + s8y[0], su, 1, m);
+                                for (int e = 1; e < 4; e++) {
+                                    const int c8 = c16 + (e & 1), r8 = r16 + (e >> 1);
+                                    if (c8 >= max_cols || r8 >= max_rows) continue;
+                                    o_build(p + r8 * stride + c8, sy + s8y[e], 0, 0, m);
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+}

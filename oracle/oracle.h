@@ -28,6 +28,8 @@ void svtb200_oracle_me_picture(const SvtB200MeParams *P, const SvtB200Plane cur[
 void svtb200_oracle_zz_sad_picture(const SvtB200Plane *cur16, const SvtB200Plane *prev_full, int w, int h, int th_shift,
                                    uint8_t *scores, uint32_t *sads);
 
+void svtb200_oracle_build_masks(int mi_rows, int mi_cols, const SvtB200LfModeInfo *mi, int stride, SvtB200LfMask *lfm, int lfm_stride);
+
 #ifdef __cplusplus
 }
 #endif

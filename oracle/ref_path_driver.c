@@ -245,6 +245,32 @@ int refdrv_zz_sad(void *h, const SvtB200Plane *cur16, const SvtB200Plane *prev_f
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------ edge masks */
+/* the reference's eb_vp9_setup_mask over a picture described by plain per-unit data: sb_type, tx_size, skip, ref_frame[0]
+ * (0 = intra) and which of the two mode classes of mode_lf_lut the block's mode falls in; levels[ref * 2 + cls] plays
+ * lf_info.lvl[0][ref][cls] (what eb_vp9_loop_filter_frame_init derives from the deltas) */
+typedef struct { uint8_t sb_type, tx_size, skip, ref, cls; } RefdrvMi;
+void eb_vp9_setup_mask(VP9_COMMON *const cm, const int mi_row, const int mi_col, ModeInfo **mi, const int mode_info_stride, LOOP_FILTER_MASK *lfm);
+
+int refdrv_build_masks(int mi_rows, int mi_cols, const RefdrvMi *g, int stride, const uint8_t levels[8], SvtB200LfMask *out, int lfm_stride) {
+    VP9_COMMON *cm = (VP9_COMMON *)calloc(1, sizeof(VP9_COMMON));
+    ModeInfo *mis = (ModeInfo *)calloc((size_t)mi_rows * stride, sizeof(ModeInfo));
+    ModeInfo **grid = (ModeInfo **)calloc((size_t)(mi_rows + 8) * stride + 8, sizeof(ModeInfo *));
+    cm->mi_rows = mi_rows; cm->mi_cols = mi_cols; cm->mi_stride = stride;
+    for (int ref = 0; ref < 4; ref++) for (int c = 0; c < 2; c++) cm->lf_info.lvl[0][ref][c] = levels[ref * 2 + c];
+    for (int i = 0; i < mi_rows * stride; i++) {
+        mis[i].sb_type = (BLOCK_SIZE)g[i].sb_type; mis[i].tx_size = (TX_SIZE)g[i].tx_size; mis[i].skip = (int8_t)g[i].skip;
+        mis[i].ref_frame[0] = (MV_REFERENCE_FRAME)g[i].ref; mis[i].ref_frame[1] = (MV_REFERENCE_FRAME)-1;
+        mis[i].mode = g[i].ref == 0 ? DC_PRED : (g[i].cls ? NEARESTMV : ZEROMV);
+        grid[i] = &mis[i];
+    }
+    for (int r = 0; r < mi_rows; r += 8)
+        for (int c = 0; c < mi_cols; c += 8)
+            eb_vp9_setup_mask(cm, r, c, grid + (size_t)r * stride + c, stride, (LOOP_FILTER_MASK *)&out[(r >> 3) * lfm_stride + (c >> 3)]);
+    free(grid); free(mis); free(cm);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------ deblocking */
 int refdrv_deblock(const SvtB200LfParams *P, uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs, const SvtB200LfMask *lfm,
                    int lfm_stride, const SvtB200LfThresh *thr) {

@@ -68,6 +68,7 @@ class TxPlanes(C.Structure):
 LF_MASK_DTYPE = np.dtype([("left_y", "<u8", 4), ("above_y", "<u8", 4), ("int_4x4_y", "<u8"), ("left_uv", "<u2", 4),
                           ("above_uv", "<u2", 4), ("int_4x4_uv", "<u2"), ("lfl_y", "u1", 64), ("pad", "u1", 6)])
 assert LF_MASK_DTYPE.itemsize == 160
+LF_MODE_INFO_DTYPE = np.dtype([("sb_type", "u1"), ("tx_size", "u1"), ("skip_inter", "u1"), ("filter_level", "u1")])
 LF_THRESH_DTYPE = np.dtype([("mblim", "u1"), ("lim", "u1"), ("hev_thr", "u1")])
 
 
@@ -316,6 +317,21 @@ Context.txq = _ctx_txq
 
 
 # ---- S2: deblocking -------------------------------------------------------------------------------------------------
+def _ctx_build_masks(self, mi, lfm_stride=None):
+    """mi: (mi_rows, mi_cols) array of LF_MODE_INFO_DTYPE -> (sbs_h * lfm_stride) LF_MASK_DTYPE (before eb_vp9_adjust_mask)."""
+    mi = np.ascontiguousarray(mi)
+    rows, cols = mi.shape
+    sbs_w, sbs_h = (cols + 7) // 8, (rows + 7) // 8
+    stride = lfm_stride or sbs_w
+    out = np.zeros(sbs_h * stride, dtype=LF_MASK_DTYPE)
+    self.L.svtb200_build_masks.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32]
+    self.check(self.L.svtb200_build_masks(self.h, rows, cols, mi.ctypes.data, cols, out.ctypes.data, stride), "build_masks")
+    return out
+
+
+Context.build_masks = _ctx_build_masks
+
+
 def _ctx_deblock(self, params, y, u, v, lfm, lfm_stride, thr):
     """In-place eb_vp9_loop_filter_frame on host planes (2-D uint8 arrays at picture origin). Returns (y, u, v) copies."""
     L = self.L
