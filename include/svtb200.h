@@ -293,6 +293,11 @@ typedef struct SvtB200LfParams {
     int32_t filter_level;          /* lf->filter_level; 0 -> no-op */
 } SvtB200LfParams;
 
+/* eb_vp9_pick_filter_level(cpi, LPF_PICK_FROM_Q) (Source/Lib/VPX/vp9_picklpf.c:37-85, 8-bit): the frame's filter level from
+ * ac_q = eb_vp9_ac_quant(base_qindex, 0, VPX_BITS_8): clamp(ROUND_POWER_OF_TWO(ac_q * 20723 + 1015158, 18) - (key frame ? 4 : 0),
+ * 0, 63); sharpness stays 0.  A scalar per picture: plain host arithmetic, no device work. */
+int svtb200_pick_filter_level(int32_t ac_q, int32_t is_key_frame);
+
 /* What eb_vp9_setup_mask() (Source/Lib/VPX/vp9_loopfilter.c:901) reads of one ModeInfo (vp9_blockd.h:70-95), per 8x8
  * mode-info unit: the block size enum (BLOCK_4X4 = 0 ... BLOCK_64X64 = 12), the luma transform size (TX_4X4 = 0 ... TX_32X32 = 3),
  * mi->skip && is_inter_block(mi), and get_filter_level(&cm->lf_info, mi) (:242).  Every unit of a block carries the block's values

@@ -271,6 +271,21 @@ int refdrv_build_masks(int mi_rows, int mi_cols, const RefdrvMi *g, int stride, 
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------ filter level */
+#include "vp9_encoder.h"
+#include "vp9_picklpf.h"
+int refdrv_pick_filter_level(int base_qindex, int key_frame) {
+    VP9_COMP *cpi = (VP9_COMP *)calloc(1, sizeof(VP9_COMP));
+    cpi->common.base_qindex = base_qindex; cpi->common.bit_depth = VPX_BITS_8;
+    cpi->common.frame_type = key_frame ? KEY_FRAME : INTER_FRAME;
+    cpi->common.lf.filter_level = 1;
+    eb_vp9_pick_filter_level(cpi, LPF_PICK_FROM_Q);
+    const int lvl = cpi->common.lf.filter_level * 256 + cpi->common.lf.sharpness_level;
+    free(cpi);
+    return lvl;
+}
+int refdrv_ac_quant(int qindex) { return eb_vp9_ac_quant(qindex, 0, VPX_BITS_8); }
+
 /* ------------------------------------------------------------------------------------------------ deblocking */
 int refdrv_deblock(const SvtB200LfParams *P, uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs, const SvtB200LfMask *lfm,
                    int lfm_stride, const SvtB200LfThresh *thr) {

@@ -16,6 +16,12 @@ static int lfm_launch(SvtB200Ctx *c, int mi_rows, int mi_cols, const SvtB200LfMo
 
 extern "C" {
 
+int svtb200_pick_filter_level(int32_t ac_q, int32_t is_key_frame) {
+    int guess = (ac_q * 20723 + 1015158 + (1 << 17)) >> 18;
+    if (is_key_frame) guess -= 4;
+    return guess < 0 ? 0 : guess > 63 ? 63 : guess;
+}
+
 int svtb200_build_masks_dev(SvtB200Ctx *c, int32_t mi_rows, int32_t mi_cols, const SvtB200LfModeInfo *mi, int32_t mi_stride,
                             SvtB200LfMask *lfm, int32_t lfm_stride) {
     if (!c) return SVTB200_EINVAL;

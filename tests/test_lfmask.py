@@ -130,3 +130,16 @@ def test_device_built_masks_drive_the_deblocking_kernel():
     for a, b in zip(got, want):
         assert (a == b).all()
     assert (want[0] != y).any()
+
+
+@pytest.mark.skipif(not H.have_refdrv(), reason="oracle/_ref path driver not built")
+def test_pick_filter_level_matches_reference_for_every_qindex():
+    """row d1: svtb200_pick_filter_level vs eb_vp9_pick_filter_level(LPF_PICK_FROM_Q); loads the product library without a GPU"""
+    P = C.CDLL(H.os.path.join(H.ROOT, "svt-vp9_b200", "libsvtvp9_b200.so"))
+    R = H.refdrv()
+    tab = H.vp9_tables()["ac_q"]
+    for q in range(256):
+        ac = R.refdrv_ac_quant(q)
+        assert ac == int(tab[q])
+        for key in (0, 1):
+            assert P.svtb200_pick_filter_level(ac, key) * 256 == R.refdrv_pick_filter_level(q, key), (q, key)
