@@ -57,6 +57,29 @@ def test_cuda_me_matches_reference_functions(name, w, h, mk):
     assert ok.all(), "%d PUs differ from the reference" % (~ok).sum()
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("tl,nl,poc", [(0, 2, (0, 0)), (1, 2, (0, 16)), (4, 2, (0, 2)), (3, 1, (4, 0))], ids=["tl0", "tl1", "tl4", "P"])
+def test_cuda_me_full_4k_picture_matches_reference_functions(tl, nl, poc):
+    """BASELINE config C at full size: every one of the 2040 super-blocks against the reference's motion_estimate_sb
+    (run on all host cores through the path driver)."""
+    import os
+    w, h = 3840, 2160
+    P = presets.me_params_4k_m8(w, h, tl, nl, poc)
+    clip = H.synth.make_clip(w, h, 3, seed=31 + tl, k=3, g=4, a=7, b=5, m=48, noise=2)
+    pl = [frames.pa_planes(f[0]) for f in clip]
+    st = [frames.plane_structs(p) for p in pl]
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    threads = max(1, min(64, len(os.sched_getaffinity(0))))
+    ref = H.refdrv_me_picture(P, st[1], st[0], st[2] if nl == 2 else None, n_sb, threads=threads)
+    ctx = api.Context(0)
+    for i, s_ in enumerate(st):
+        ctx.picture_upload(i, s_[0], s_[1], s_[2])
+    out = ctx.me_picture(P, 1, [0, 2] if nl == 2 else [0])
+    ctx.close()
+    ok = H.me_equal(out, ref, nl)
+    assert ok.all(), "%d of %d PUs differ from the reference" % ((~ok).sum(), ok.size)
+
+
 def _txq_case(ts, seed):
     rng = np.random.default_rng(seed)
     N, Hh, W = 4 << ts, 256, 384
