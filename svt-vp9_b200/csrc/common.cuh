@@ -82,6 +82,8 @@ static inline int svtb200_grow_pinned(SvtB200Ctx *ctx, size_t need) {
     ctx->pin_bytes = n;
     return 0;
 }
+void svtb200_lf_release(SvtB200Ctx *c); /* deblock.cu: per-context wavefront scratch */
+
 static inline cudaStream_t svtb200_pick_stream(SvtB200Ctx *c, int which) {
     return which == SVTB200_STREAM_UPLOAD ? c->up : which == SVTB200_STREAM_DOWNLOAD ? c->down : which == SVTB200_STREAM_COMPUTE2 ? c->compute[1] : c->compute[0];
 }

@@ -34,6 +34,7 @@ void svtb200_destroy(SvtB200Ctx *c) {
         if (kv.second.used) cudaEventDestroy(kv.second.used);
     }
     for (int i = 0; i < SVTB200_MARKER_RING; i++) if (c->markers[i]) cudaEventDestroy(c->markers[i]);
+    svtb200_lf_release(c);
     if (c->interp_scratch) cudaFree(c->interp_scratch);
     if (c->me_out) cudaFree(c->me_out);
     if (c->me_rcme) cudaFree(c->me_rcme);

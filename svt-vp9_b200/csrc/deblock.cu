@@ -8,6 +8,16 @@ static std::mutex g_lf_mu;
 static unsigned long long *g_lf_trace; /* tools only */
 extern "C" void svtb200_lf_set_trace(void *dev) { g_lf_trace = (unsigned long long *)dev; }
 
+/* called by svtb200_destroy */
+void svtb200_lf_release(SvtB200Ctx *c) {
+    std::lock_guard<std::mutex> g(g_lf_mu);
+    auto it = g_lf.find(c);
+    if (it == g_lf.end()) return;
+    if (it->second.ticket) cudaFree(it->second.ticket);
+    if (it->second.done) cudaFree(it->second.done);
+    g_lf.erase(it);
+}
+
 static int lf_launch(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int ys, uint8_t *u, uint8_t *v, int cs,
                      const SvtB200LfMask *lfm, int lfm_stride, const SvtB200LfThresh *thr) {
     if (!p || !y || !lfm || !thr || p->mi_rows <= 0 || p->mi_cols <= 0 || (!p->y_only && (!u || !v))) return SVTB200_EINVAL;
