@@ -831,13 +831,21 @@ __device__ static void me_subpel(const MeKernelArgs &A, const uint8_t *src, MeSb
     __syncthreads();
     cmask &= qmask;
     if (!cmask) return;
-    /* ---- quarter-pel: the three positions next to the winning half-pel direction ---- */
-    for (int c = 0; c < 4; c++) {
-        if (!(cmask & (1 << c))) continue;
-        /* the 64x64 PU is refined on its top-left 32x32 only (the reference passes 32 as the size) */
-        const int tlog = (c == 0) ? 3 : me_cls_tlog(c), T = 1 << tlog, idx0 = me_cls_idx0(c);
-        const int nunits = me_cls_npu(c) * 3 * T, nround = (nunits + 31) & ~31;
-        for (int u = threadIdx.x; u < nround; u += ME_THREADS) {
+    /* ---- quarter-pel: the three positions next to the winning half-pel direction.  The units of all enabled classes form
+     * one index space (each class padded to whole warps) so that they run side by side instead of class after class ---- */
+    {
+        int off[5];
+        off[0] = 0;
+        for (int c = 0; c < 4; c++) {
+            /* the 64x64 PU is refined on its top-left 32x32 only (the reference passes 32 as the size) */
+            const int tl = (c == 0) ? 3 : me_cls_tlog(c);
+            off[c + 1] = off[c] + ((cmask & (1 << c)) ? ((me_cls_npu(c) * 3 << tl) + 31) & ~31 : 0);
+        }
+        for (int g = threadIdx.x; g < off[4]; g += ME_THREADS) {
+            const int c = g < off[1] ? 0 : g < off[2] ? 1 : g < off[3] ? 2 : 3;
+            const int u = g - off[c];
+            const int tlog = (c == 0) ? 3 : me_cls_tlog(c), T = 1 << tlog, idx0 = me_cls_idx0(c);
+            const int nunits = me_cls_npu(c) * 3 * T;
             const int active = u < nunits;
             const int task = active ? u >> tlog : 0, part = u & (T - 1);
             const int pu = task / 3, j = task - pu * 3, idx = idx0 + pu;
