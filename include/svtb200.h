@@ -50,6 +50,11 @@ int         svtb200_sync(SvtB200Ctx *ctx);
 uint64_t    svtb200_launch_count(const SvtB200Ctx *ctx);
 /* raw cudaStream_t the context launches on (for CUDA-event timing by the caller) */
 void       *svtb200_stream(SvtB200Ctx *ctx);
+/* Page-lock a buffer the CALLER owns (e.g. the reference's picture buffers, allocated once per pool entry) so that copies
+ * from / to it are asynchronous DMA transfers instead of staged pageable copies.  Returns SVTB200_OK also when the range is
+ * already registered. */
+int   svtb200_host_register(void *ptr, size_t bytes);
+int   svtb200_host_unregister(void *ptr);
 
 /* ---- pinned host memory (the "pinned async copies" of the staging path) ------------------- */
 void *svtb200_host_alloc(size_t bytes);

@@ -124,6 +124,18 @@ void *svtb200_host_alloc(size_t bytes) {
     return p;
 }
 void svtb200_host_free(void *p) { if (p) cudaFreeHost(p); }
+int svtb200_host_register(void *p, size_t bytes) {
+    if (!p || !bytes) return SVTB200_EINVAL;
+    const cudaError_t e = cudaHostRegister(p, bytes, cudaHostRegisterPortable);
+    if (e == cudaSuccess) return SVTB200_OK;
+    cudaGetLastError();
+    return e == cudaErrorHostMemoryAlreadyRegistered ? SVTB200_OK : SVTB200_ECUDA;
+}
+int svtb200_host_unregister(void *p) {
+    if (!p) return SVTB200_EINVAL;
+    if (cudaHostUnregister(p) != cudaSuccess) { cudaGetLastError(); return SVTB200_ECUDA; }
+    return SVTB200_OK;
+}
 
 void *svtb200_dev_alloc(SvtB200Ctx *c, size_t bytes) {
     if (!c) return nullptr;

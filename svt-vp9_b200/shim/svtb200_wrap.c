@@ -54,6 +54,19 @@ static int ctx_ready(void) {
     return g_state == 1;
 }
 
+/* The CUDA context (~0.5 s) is created while the encoder allocates its own pools, not inside the first picture. */
+static void *warm_up(void *arg) {
+    (void)arg;
+    pthread_mutex_lock(&g_mu);
+    ctx_ready();
+    pthread_mutex_unlock(&g_mu);
+    return NULL;
+}
+__attribute__((constructor)) static void svtb200_wrap_init(void) {
+    pthread_t th;
+    if (pthread_create(&th, NULL, warm_up, NULL) == 0) pthread_detach(th);
+}
+
 /* ------------------------------------------------------------------------------------------------------------ S1 */
 #define MAX_IN_FLIGHT 64
 typedef struct {
@@ -84,6 +97,9 @@ static int ensure_resident(const EbPaReferenceObject *o, uint64_t poc, int want_
     if (free_i < 0) return SVTB200_ENOMEM;
     SvtB200Plane pl[3];
     svtb200_glue_pa_planes(o, pl);
+    if (!g_res[free_i].valid || g_res[free_i].obj != (const void *)o) /* a buffer of the reference's pool, first time seen: page-lock it */
+        for (int k = 0; k < 3; k++)
+            if (pl[k].buf && pl[k].stride > 0 && pl[k].padded_height > 0) svtb200_host_register((void *)pl[k].buf, (size_t)pl[k].stride * pl[k].padded_height);
     int rc = svtb200_picture_upload(g_ctx, (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
     if (rc != SVTB200_OK) return rc;
     g_res[free_i].obj = o; g_res[free_i].poc = poc; g_res[free_i].valid = 1;
@@ -184,6 +200,22 @@ void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_
     SvtB200LfParams P;
     SvtB200LfThresh thr[64];
     svtb200_glue_lf(cm, frame_filter_level, y_only, &P, thr);
+    {   /* the reconstruction buffers come from a small pool: page-lock each plane the first time it is filtered */
+        static const void *seen[64];
+        static int n_seen;
+        pthread_mutex_lock(&g_mu);
+        int known = 0;
+        for (int i = 0; i < n_seen; i++) known |= seen[i] == (const void *)xd->plane[0].dst.buf;
+        if (!known && n_seen < 64) {
+            seen[n_seen++] = xd->plane[0].dst.buf;
+            svtb200_host_register(xd->plane[0].dst.buf, (size_t)xd->plane[0].dst.stride * (P.height - 1) + P.width);
+            if (!y_only) {
+                svtb200_host_register(xd->plane[1].dst.buf, (size_t)xd->plane[1].dst.stride * (P.height / 2 - 1) + P.width / 2);
+                svtb200_host_register(xd->plane[2].dst.buf, (size_t)xd->plane[2].dst.stride * (P.height / 2 - 1) + P.width / 2);
+            }
+        }
+        pthread_mutex_unlock(&g_mu);
+    }
     const int rc = svtb200_deblock_picture(g_ctx, &P, xd->plane[0].dst.buf, xd->plane[0].dst.stride, xd->plane[1].dst.buf, xd->plane[2].dst.buf,
                                            xd->plane[1].dst.stride, (const SvtB200LfMask *)cm->lf.lfm, cm->lf.lfm_stride, thr);
     pthread_mutex_lock(&g_mu);
