@@ -559,14 +559,18 @@ def main():
         cpu_line = None
         if world == 1:
             cpu = CpuPath(clip, ncores)
-            t0 = time.perf_counter()
             sample = [16, 8, 4, 2, 1, 3]
-            for n in sample:
+            for n in sample[:2]:          # thread pool / page-fault warm-up, untimed
                 cpu.step(n)
+            t0 = time.perf_counter()
+            reps = 3
+            for _ in range(reps):
+                for n in sample:
+                    cpu.step(n)
             dt = time.perf_counter() - t0
-            cpu_line = {"value": len(sample) / dt, "unit": "fps", "cores": ncores, "kind": cpu.kind,
-                        "sample": "%d whole 4K pictures (temporal layers 0,1,2,3,4,4) through ME + transform/quant/recon (+ deblock on the "
-                                  "base-layer picture), %d host threads, %.1f s" % (len(sample), ncores, dt)}
+            cpu_line = {"value": reps * len(sample) / dt, "unit": "fps", "cores": ncores, "kind": cpu.kind,
+                        "sample": "%d whole 4K pictures (3 x temporal layers 0,1,2,3,4,4) through ME + transform/quant/recon (+ deblock on the "
+                                  "base-layer picture), %d host threads, %.1f s" % (reps * len(sample), ncores, dt)}
         print(json.dumps({"metric": METRIC, "value": value, "unit": "fps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "u8", "data": "synthetic", "config": config, "clocks": sampler.summary(),
