@@ -120,6 +120,11 @@ int svtb200_picture_release(SvtB200Ctx *ctx, uint64_t pic_id);
  * same stride / origin as the uploaded host plane -- for chaining svtb200_txq_batch_dev / svtb200_deblock_picture_dev
  * on planes that are already resident. */
 int svtb200_picture_plane_dev(SvtB200Ctx *ctx, uint64_t pic_id, int which, SvtB200Plane *out);
+/* eb_vp9_generate_padding() (Source/Lib/Codec/EbMcp.c:17; pad_ref_and_set_flags, EbEncDecProcess.c:4822) on a device-resident
+ * plane: buf points at the first byte of the PADDED plane (pitch 'stride'), the width x height picture area starts at
+ * (pad_x, pad_y); every sample of the (width + 2 pad_x) x (height + 2 pad_y) rectangle outside the picture area becomes a
+ * copy of the nearest picture sample.  stride, buf and width + 2 pad_x must be multiples of 4.  Runs on the current compute queue. */
+int svtb200_pad_plane_dev(SvtB200Ctx *ctx, uint8_t *buf_dev, int32_t stride, int32_t width, int32_t height, int32_t pad_x, int32_t pad_y);
 /* Tell the library that kernels the CALLER queued on the compute queue (through the *_dev entry points, on planes obtained
  * from svtb200_picture_plane_dev) read picture pic_id: a later re-upload of that id waits for them. */
 int svtb200_picture_touch(SvtB200Ctx *ctx, uint64_t pic_id);

@@ -200,17 +200,17 @@ int svtb200_picture_upload(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *f
 
 /* Edge replication of the padded source plane (eb_vp9_generate_padding, EbPictureOperators.c) and the point decimations
  * of eb_vp9_decimation_2d (EbPictureAnalysisProcess.c:102) with their own padding, one thread per 4 output bytes. */
-__global__ void pa_pad_full_kernel(uint8_t *buf, int stride, int ox, int oy, int w, int h, int rows) {
+__global__ void pa_pad_full_kernel(uint8_t *buf, int pitch, int ox, int oy, int w, int h, int rows, int cols /* bytes of a row to write */) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
-    if (x4 >= stride || y >= rows) return;
+    if (x4 >= cols || y >= rows) return;
     const int sy = min(max(y - oy, 0), h - 1);
     if (y >= oy && y < oy + h && x4 >= ox && x4 + 4 <= ox + w) return; /* interior word */
-    const uint8_t *row = buf + (size_t)(oy + sy) * stride + ox;
+    const uint8_t *row = buf + (size_t)(oy + sy) * pitch + ox;
     uint32_t v = 0;
 #pragma unroll
     for (int k = 0; k < 4; k++) v |= (uint32_t)row[min(max(x4 + k - ox, 0), w - 1)] << (8 * k);
-    if (x4 + 4 <= stride) *(uint32_t *)(buf + (size_t)y * stride + x4) = v;
-    else for (int k = 0; x4 + k < stride; k++) buf[(size_t)y * stride + x4 + k] = (uint8_t)(v >> (8 * k));
+    if (x4 + 4 <= cols) *(uint32_t *)(buf + (size_t)y * pitch + x4) = v;
+    else for (int k = 0; x4 + k < cols; k++) buf[(size_t)y * pitch + x4 + k] = (uint8_t)(v >> (8 * k));
 }
 __global__ void pa_decimate_kernel(const uint8_t *full, int fstride, int fox, int foy, uint8_t *dst, int stride, int ox, int oy,
                                    int w, int h, int rows, int step) {
@@ -252,7 +252,7 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
     const size_t off = (size_t)f->oy * f->stride + f->ox;
     SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(f->buf + off, f->stride, full->buf + off, full->stride, f->w, f->h, cudaMemcpyHostToDevice, c->up));
     dim3 blk(128);
-    pa_pad_full_kernel<<<dim3((f->stride / 4 + 127) / 128, f->rows), blk, 0, c->up>>>(f->buf, f->stride, f->ox, f->oy, f->w, f->h, f->rows);
+    pa_pad_full_kernel<<<dim3((f->stride / 4 + 127) / 128, f->rows), blk, 0, c->up>>>(f->buf, f->stride, f->ox, f->oy, f->w, f->h, f->rows, f->stride);
     c->launches++;
     for (int lvl = 1; lvl <= 2; lvl++) {
         DevPlane *d = &p.pl[lvl];
@@ -279,6 +279,20 @@ int svtb200_picture_plane_dev(SvtB200Ctx *c, uint64_t pic_id, int which, SvtB200
     const DevPlane &d = it->second.pl[which];
     out->buf = d.buf; out->stride = d.stride; out->origin_x = d.ox; out->origin_y = d.oy; out->width = d.w; out->height = d.h;
     out->padded_height = d.rows;
+    return SVTB200_OK;
+}
+
+/* eb_vp9_generate_padding (Source/Lib/Codec/EbMcp.c:17) on a device plane: horizontal then vertical edge replication */
+int svtb200_pad_plane_dev(SvtB200Ctx *c, uint8_t *buf, int32_t stride, int32_t width, int32_t height, int32_t pad_x, int32_t pad_y) {
+    if (!c || !buf || stride <= 0 || width <= 0 || height <= 0 || pad_x < 0 || pad_y < 0 || width + 2 * pad_x > stride) return SVTB200_EINVAL;
+    if ((stride & 3) || ((uintptr_t)buf & 3) || ((width + 2 * pad_x) & 3)) { c->err = "pad_plane: stride, base and padded width must be multiples of 4"; return SVTB200_EINVAL; }
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    const int cols = width + 2 * pad_x, rows = height + 2 * pad_y;
+    /* the kernel treats 'cols' as the row length to write and 'stride' as the pitch */
+    pa_pad_full_kernel<<<dim3((cols / 4 + 127) / 128, rows), dim3(128), 0, c->stream>>>(buf, stride, pad_x, pad_y, width, height, rows, cols);
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return SVTB200_OK;
 }
 

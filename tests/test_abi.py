@@ -65,3 +65,29 @@ def test_device_decimation_and_padding_match_host_front_end(w, h, hme1):
         assert (d.origin_x, d.origin_y, d.width, d.height) == (st[which].origin_x, st[which].origin_y, st[which].width, st[which].height)
         assert (got[:, :want.shape[1]] == want).all(), key
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,px,py", [(640, 384, 68, 68), (200, 136, 32, 32), (96, 40, 16, 4)])
+def test_device_padding_matches_reference_generate_padding(w, h, px, py):
+    """eb_vp9_generate_padding (EbMcp.c:17) from the reference library vs svtb200_pad_plane_dev on the same buffer"""
+    if not H.have_ref():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(w + px)
+    stride = w + 2 * px
+    buf = rng.integers(0, 256, size=(h + 2 * py, stride), dtype=np.uint8)
+    want = buf.copy()
+    R = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libSvtVp9Enc_ref.so"))
+    R.eb_vp9_generate_padding.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32]
+    R.eb_vp9_generate_padding(want.ctypes.data, stride, w, h, px, py)
+    ctx = api.Context(0)
+    L = ctx.L
+    L.svtb200_pad_plane_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
+    d = L.svtb200_dev_alloc(ctx.h, buf.nbytes)
+    L.svtb200_memcpy_h2d(ctx.h, d, buf.ctypes.data, buf.nbytes)
+    ctx.check(L.svtb200_pad_plane_dev(ctx.h, d, stride, w, h, px, py), "pad_plane_dev")
+    got = np.zeros_like(buf)
+    L.svtb200_memcpy_d2h(ctx.h, got.ctypes.data, d, buf.nbytes)
+    ctx.close()
+    assert (got == want).all()
+    assert (np.pad(buf[py:py + h, px:px + w], ((py, py), (px, px)), mode="edge") == got).all()
