@@ -190,6 +190,17 @@ int svtb200_me_picture_dev(SvtB200Ctx *ctx, const SvtB200MeParams *params, uint6
 enum { SVTB200_TX_4X4 = 0, SVTB200_TX_8X8 = 1, SVTB200_TX_16X16 = 2, SVTB200_TX_32X32 = 3 };
 enum { SVTB200_DCT_DCT = 0, SVTB200_ADST_DCT = 1, SVTB200_DCT_ADST = 2, SVTB200_ADST_ADST = 3 };
 
+/* compute_block_mean_compute_variance() (Source/Lib/Codec/EbPictureAnalysisProcess.c:2115-3356, per SB from
+ * compute_picture_spatial_statistics :4784): for every 64x64 super-block the means and variances of its 85 square blocks in the
+ * reference's ME_TIER_ZERO_PU order (64x64, 4 32x32, 16 16x16, 64 8x8; raster inside a size).  8x8 level: rows 0,2,4,6 only,
+ * mean = sum << 3 (8.8 fixed point), mean of squares = sum of squares << 11 (16.16); each larger size = (sum of its four
+ * quadrants) >> 2; y_mean = mean >> 8, variance = (uint16)((mean of squares - mean * mean) >> 16).  Incomplete super-blocks read
+ * the plane's padding exactly as the reference does.  y_mean: n_sb x 85 bytes, variance: n_sb x 85 uint16. */
+int svtb200_block_stats_picture(SvtB200Ctx *ctx, uint64_t pic_id, int32_t luma_width, int32_t luma_height, uint8_t *y_mean_host,
+                                uint16_t *variance_host);
+int svtb200_block_stats_picture_dev(SvtB200Ctx *ctx, uint64_t pic_id, int32_t luma_width, int32_t luma_height, uint8_t *y_mean_dev,
+                                    uint16_t *variance_dev);
+
 /* compute_zz_sad() (Source/Lib/Codec/EbMotionEstimationProcess.c:431; called per picture with look-ahead, :1079-1096):
  * for every COMPLETE 64x64 super-block the 16x16 SAD between the current picture's 1/16 plane and a 4:1 point decimation
  * (eb_vp9_decimation_2d, step 4) of the PREVIOUS picture's full-resolution plane at the same position, and the non-moving

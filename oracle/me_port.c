@@ -760,3 +760,33 @@ void svtb200_oracle_zz_sad_picture(const SvtB200Plane *cur16, const SvtB200Plane
             if (sads) sads[sb] = sad;
         }
 }
+
+
+/* compute_block_mean_compute_variance (Source/Lib/Codec/EbPictureAnalysisProcess.c:2115-3356): 8x8 means from rows 0,2,4,6
+ * (eb_vp9_compute_sub_mean8x8_sse2_intrin: sum << 3; eb_vp9_compute_subd_mean_of_squared_values8x8_sse2_intrin: sum of squares
+ * << 11, ASM_SSE2/EbComputeMean_Intrinsic_SSE2.c:10-53), quadrant averages (>> 2) up to 64x64 (:2732-2960), outputs
+ * y_mean = mean >> MEAN_PRECISION(8) and variance = (mean_sq - mean^2) >> VARIANCE_PRECISION(16) (:2962-3350). */
+void svtb200_oracle_block_stats_picture(const SvtB200Plane *full, int w, int h, uint8_t *y_mean, uint16_t *variance) {
+    const int sbs_w = (w + SB - 1) / SB, sbs_h = (h + SB - 1) / SB;
+    for (int sb = 0; sb < sbs_w * sbs_h; sb++) {
+        const int ox = (sb % sbs_w) * SB, oy = (sb / sbs_w) * SB;
+        uint64_t m[85], q[85];
+        for (int b = 0; b < 64; b++) {
+            const uint8_t *p = full->buf + (size_t)(full->origin_y + oy + (b >> 3) * 8) * full->stride + full->origin_x + ox + (b & 7) * 8;
+            uint64_t s = 0, s2 = 0;
+            for (int r = 0; r < 8; r += 2)
+                for (int x = 0; x < 8; x++) { const uint64_t v = p[(size_t)r * full->stride + x]; s += v; s2 += v * v; }
+            m[21 + b] = s << 3; q[21 + b] = s2 << 11;
+        }
+        for (int i = 0; i < 16; i++) {
+            const int a = 21 + (2 * (i >> 2)) * 8 + 2 * (i & 3);
+            m[5 + i] = (m[a] + m[a + 1] + m[a + 8] + m[a + 9]) >> 2; q[5 + i] = (q[a] + q[a + 1] + q[a + 8] + q[a + 9]) >> 2;
+        }
+        for (int i = 0; i < 4; i++) {
+            const int a = 5 + (2 * (i >> 1)) * 4 + 2 * (i & 1);
+            m[1 + i] = (m[a] + m[a + 1] + m[a + 4] + m[a + 5]) >> 2; q[1 + i] = (q[a] + q[a + 1] + q[a + 4] + q[a + 5]) >> 2;
+        }
+        m[0] = (m[1] + m[2] + m[3] + m[4]) >> 2; q[0] = (q[1] + q[2] + q[3] + q[4]) >> 2;
+        for (int i = 0; i < 85; i++) { y_mean[(size_t)sb * 85 + i] = (uint8_t)(m[i] >> 8); variance[(size_t)sb * 85 + i] = (uint16_t)((q[i] - m[i] * m[i]) >> 16); }
+    }
+}

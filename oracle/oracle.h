@@ -30,6 +30,8 @@ void svtb200_oracle_zz_sad_picture(const SvtB200Plane *cur16, const SvtB200Plane
 
 void svtb200_oracle_build_masks(int mi_rows, int mi_cols, const SvtB200LfModeInfo *mi, int stride, SvtB200LfMask *lfm, int lfm_stride);
 
+void svtb200_oracle_block_stats_picture(const SvtB200Plane *full, int w, int h, uint8_t *y_mean, uint16_t *variance);
+
 #ifdef __cplusplus
 }
 #endif

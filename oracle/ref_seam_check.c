@@ -23,7 +23,7 @@ EbErrorType __real_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static int   g_mode = -1; /* 0 off, 1 check, 2 dump */
 static char  g_dir[512];
-static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed;
+static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed, g_stats_bad;
 static int   g_max_dump_pics = 4, g_dump_from = 0;
 
 #define MAX_TRACKED 64
@@ -38,7 +38,7 @@ static void write_summary(void) {
     snprintf(path, sizeof(path), "%s/summary.txt", g_dir);
     FILE *f = fopen(path, "w");
     if (!f) return;
-    fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped);
+    fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\nstats_bad %ld\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped, g_stats_bad);
     fclose(f);
 }
 
@@ -97,6 +97,15 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
         svtb200_oracle_me_sb(&P, cur, r0, P.num_lists == 2 ? r1 : NULL, sb_origin_x / 64, sb_origin_y / 64, mine, &rcme, &tr);
         int bad = 0;
         for (int i = 0; i < 85; i++) if (memcmp(&mine[i], &refres[i], sizeof(mine[i]))) bad++;
+        {   /* the picture-analysis statistics of this SB (compute_block_mean_compute_variance) against the oracle restatement */
+            SvtB200Plane one = cur[0];
+            uint8_t ym[85]; uint16_t var[85];
+            one.origin_x += (int32_t)sb_origin_x; one.origin_y += (int32_t)sb_origin_y;
+            svtb200_oracle_block_stats_picture(&one, 64, 64, ym, var);
+            int sbad = 0;
+            for (int i = 0; i < 85; i++) if (ym[i] != pcs->y_mean[sb_index][i] || var[i] != pcs->variance[sb_index][i]) sbad++;
+            if (sbad) { pthread_mutex_lock(&g_mu); g_stats_bad += sbad; pthread_mutex_unlock(&g_mu); }
+        }
         if (P.rate_control_mode && rcme != pcs->rcme_distortion[sb_index]) bad++;
         pthread_mutex_lock(&g_mu);
         g_sb_total++;

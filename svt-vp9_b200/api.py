@@ -227,6 +227,14 @@ class Context:
         self.check(self.L.svtb200_zz_sad_picture(self.h, cur_id, prev_id, width, height, th_shift, scores.ctypes.data, sads.ctypes.data), "zz_sad_picture")
         return scores, sads
 
+    def block_stats_picture(self, pic_id, width, height):
+        """compute_block_mean_compute_variance for every SB -> (y_mean u8[n_sb, 85], variance u16[n_sb, 85])."""
+        n_sb = ((width + 63) // 64) * ((height + 63) // 64)
+        ym, var = np.zeros((n_sb, 85), dtype=np.uint8), np.zeros((n_sb, 85), dtype=np.uint16)
+        self.L.svtb200_block_stats_picture.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+        self.check(self.L.svtb200_block_stats_picture(self.h, pic_id, width, height, ym.ctypes.data, var.ctypes.data), "block_stats_picture")
+        return ym, var
+
     def me_trace(self, n_sb):
         tr = np.zeros(n_sb, dtype=ME_TRACE_DTYPE)
         self.check(self.L.svtb200_me_read_trace(self.h, tr.ctypes.data, tr.nbytes), "me_read_trace")

@@ -1,4 +1,5 @@
-/* zz.cu -- compute_zz_sad (EbMotionEstimationProcess.c:431) for a whole picture: one warp per super-block. */
+/* zz.cu -- picture-analysis side kernels, one warp per super-block: compute_zz_sad (EbMotionEstimationProcess.c:431) and
+ * compute_block_mean_compute_variance (EbPictureAnalysisProcess.c:2115). */
 #include "common.cuh"
 
 struct ZzArgs {
@@ -35,6 +36,72 @@ __global__ void __launch_bounds__(256) zz_sad_kernel(const ZzArgs A) {
     }
 }
 
+/* ---- block statistics: one warp per super-block, two 8x8 blocks per lane ---- */
+struct StatArgs {
+    const uint8_t *full; int32_t stride, ox, oy;
+    int32_t sbs_w, n_sb;
+    uint8_t *y_mean; uint16_t *variance;
+};
+__device__ __forceinline__ uint32_t st_dp4a_uu(uint32_t a, uint32_t b, uint32_t c) {
+    uint32_t r;
+    asm("dp4a.u32.u32 %0, %1, %2, %3;" : "=r"(r) : "r"(a), "r"(b), "r"(c));
+    return r;
+}
+__global__ void __launch_bounds__(256) block_stats_kernel(const StatArgs A) {
+    __shared__ unsigned long long m_s[8][85], q_s[8][85]; /* per warp: means (8.8) and means of squares (16.16), ME_TIER_ZERO_PU order */
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31, sb = blockIdx.x * 8 + w;
+    if (sb >= A.n_sb) return;
+    const int sx = (sb % A.sbs_w) * 64, sy = (sb / A.sbs_w) * 64;
+    unsigned long long *m = m_s[w], *q = q_s[w];
+    for (int h = 0; h < 2; h++) {
+        const int b = lane + 32 * h, bx = (b & 7) * 8, by = (b >> 3) * 8;
+        const uint8_t *p = A.full + (size_t)(A.oy + sy + by) * A.stride + A.ox + sx + bx;
+        uint32_t sum = 0, sq = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r += 2) { /* the reference sub-samples: rows 0, 2, 4, 6 */
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const uint32_t v = __ldg(p + (size_t)r * A.stride + k); sum += v; sq += v * v; }
+        }
+        m[21 + b] = (unsigned long long)sum << 3;
+        q[21 + b] = (unsigned long long)sq << 11;
+    }
+    __syncwarp();
+    if (lane < 16) { /* 16x16: raster index lane, its four 8x8 */
+        const int r = lane >> 2, c = lane & 3, a = 21 + (2 * r) * 8 + 2 * c;
+        m[5 + lane] = (m[a] + m[a + 1] + m[a + 8] + m[a + 9]) >> 2;
+        q[5 + lane] = (q[a] + q[a + 1] + q[a + 8] + q[a + 9]) >> 2;
+    }
+    __syncwarp();
+    if (lane < 4) {
+        const int r = lane >> 1, c = lane & 1, a = 5 + (2 * r) * 4 + 2 * c;
+        m[1 + lane] = (m[a] + m[a + 1] + m[a + 4] + m[a + 5]) >> 2;
+        q[1 + lane] = (q[a] + q[a + 1] + q[a + 4] + q[a + 5]) >> 2;
+    }
+    __syncwarp();
+    if (lane == 0) { m[0] = (m[1] + m[2] + m[3] + m[4]) >> 2; q[0] = (q[1] + q[2] + q[3] + q[4]) >> 2; }
+    __syncwarp();
+    for (int i = lane; i < 85; i += 32) {
+        A.y_mean[(size_t)sb * 85 + i] = (uint8_t)(m[i] >> 8);
+        A.variance[(size_t)sb * 85 + i] = (uint16_t)((q[i] - m[i] * m[i]) >> 16);
+    }
+}
+
+static int stats_launch(SvtB200Ctx *c, uint64_t pic_id, int w, int h, uint8_t *y_mean, uint16_t *variance) {
+    if (!y_mean || !variance || w <= 0 || h <= 0) return SVTB200_EINVAL;
+    auto it = c->pics.find(pic_id);
+    if (it == c->pics.end() || !it->second.pl[0].buf) { c->err = "block_stats: picture not resident"; return SVTB200_ENOENT; }
+    const DevPlane &f = it->second.pl[0];
+    StatArgs A;
+    A.full = f.buf; A.stride = f.stride; A.ox = f.ox; A.oy = f.oy;
+    A.sbs_w = (w + 63) / 64; A.n_sb = A.sbs_w * ((h + 63) / 64); A.y_mean = y_mean; A.variance = variance;
+    svtb200_pic_acquire(c, it->second);
+    block_stats_kernel<<<(A.n_sb + 7) / 8, 256, 0, c->stream>>>(A);
+    svtb200_pic_release(c, it->second);
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
 static int zz_launch(SvtB200Ctx *c, uint64_t cur_id, uint64_t prev_id, int w, int h, int th_shift, uint8_t *scores, uint32_t *sads) {
     if (!scores || w <= 0 || h <= 0 || th_shift < 0 || th_shift > 11) return SVTB200_EINVAL;
     auto ic = c->pics.find(cur_id), ip = c->pics.find(prev_id);
@@ -54,6 +121,30 @@ static int zz_launch(SvtB200Ctx *c, uint64_t cur_id, uint64_t prev_id, int w, in
 }
 
 extern "C" {
+
+int svtb200_block_stats_picture_dev(SvtB200Ctx *c, uint64_t pic_id, int32_t w, int32_t h, uint8_t *y_mean, uint16_t *variance) {
+    if (!c) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    return stats_launch(c, pic_id, w, h, y_mean, variance);
+}
+
+int svtb200_block_stats_picture(SvtB200Ctx *c, uint64_t pic_id, int32_t w, int32_t h, uint8_t *y_mean, uint16_t *variance) {
+    if (!c || !y_mean || !variance || w <= 0 || h <= 0) return SVTB200_EINVAL;
+    std::lock_guard<std::mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    const size_t n = (size_t)((w + 63) / 64) * ((h + 63) / 64) * 85;
+    int rc = svtb200_grow(c, (void **)&c->scratch, &c->scratch_bytes, n * 3 + 512);
+    if (rc) return rc;
+    uint16_t *d_v = (uint16_t *)c->scratch;
+    uint8_t *d_m = c->scratch + ((n * 2 + 255) & ~(size_t)255);
+    rc = stats_launch(c, pic_id, w, h, d_m, d_v);
+    if (rc) return rc;
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(y_mean, d_m, n, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(variance, d_v, n * 2, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SVTB200_OK;
+}
 
 int svtb200_zz_sad_picture_dev(SvtB200Ctx *c, uint64_t cur_id, uint64_t prev_id, int32_t w, int32_t h, int32_t th_shift, uint8_t *scores, uint32_t *sads) {
     if (!c) return SVTB200_EINVAL;

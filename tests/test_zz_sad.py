@@ -1,4 +1,5 @@
 """compute_zz_sad: the oracle restatement against the reference's own function, the CUDA path against both."""
+import ctypes as C
 import importlib
 
 import numpy as np
@@ -51,3 +52,49 @@ def test_cuda_zz_sad_matches_oracle_and_reference(w, h, res, noise):
     assert len(set(exp.tolist())) >= 2
     if H.have_refdrv():
         assert (got == H.refdrv_zz_sad(st[1], st[0], w, h, res)).all()
+
+
+def _oracle_stats(st, w, h):
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    ym, var = np.zeros((n_sb, 85), dtype=np.uint8), np.zeros((n_sb, 85), dtype=np.uint16)
+    L = H.oracle()
+    L.svtb200_oracle_block_stats_picture.argtypes = [C.POINTER(api.Plane), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    L.svtb200_oracle_block_stats_picture(C.byref(st[0]), w, h, ym.ctypes.data, var.ctypes.data)
+    return ym, var
+
+
+@pytest.mark.skipif(not H.have_ref(), reason="oracle/_ref not built")
+def test_oracle_block_stats_8x8_level_matches_reference_intrinsics():
+    """the 8x8 entries (21..84) against the reference's own eb_vp9_compute_sub_mean8x8_sse2_intrin /
+    eb_vp9_compute_subd_mean_of_squared_values8x8_sse2_intrin; the whole function is pinned inside real encodes by the seam check
+    (oracle/ref_seam_check.c: stats_bad 0)"""
+    import os
+    R = C.CDLL(os.path.join(H.ROOT, "oracle", "_ref", "libSvtVp9Enc_ref.so"))
+    for f in (R.eb_vp9_compute_sub_mean8x8_sse2_intrin, R.eb_vp9_compute_subd_mean_of_squared_values8x8_sse2_intrin):
+        f.argtypes, f.restype = [C.c_void_p, C.c_uint16], C.c_uint64
+    w, h = 200, 136
+    pl, st = _pair(w, h, 6, 3)
+    ym, var = _oracle_stats(st[1], w, h)
+    full = pl[1]["full"]
+    sbs_w = (w + 63) // 64
+    for sb in range(ym.shape[0]):
+        ox, oy = (sb % sbs_w) * 64, (sb // sbs_w) * 64
+        for b in range(64):
+            p = full[frames.FULL_PAD + oy + (b >> 3) * 8:, frames.FULL_PAD + ox + (b & 7) * 8:]
+            addr = full.ctypes.data + (frames.FULL_PAD + oy + (b >> 3) * 8) * full.shape[1] + frames.FULL_PAD + ox + (b & 7) * 8
+            m = R.eb_vp9_compute_sub_mean8x8_sse2_intrin(addr, full.shape[1])
+            q = R.eb_vp9_compute_subd_mean_of_squared_values8x8_sse2_intrin(addr, full.shape[1])
+            assert ym[sb, 21 + b] == (m >> 8) & 0xff and var[sb, 21 + b] == ((q - m * m) >> 16) & 0xffff
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h", [(640, 384), (200, 136), (1920, 1088), (3840, 2160)])
+def test_cuda_block_stats_match_oracle(w, h):
+    pl, st = _pair(w, h, 5, 2)
+    ctx = api.Context(0)
+    ctx.picture_upload(0, st[1][0], st[1][1], st[1][2])
+    ym, var = ctx.block_stats_picture(0, w, h)
+    ctx.close()
+    eym, evar = _oracle_stats(st[1], w, h)
+    assert (ym == eym).all() and (var == evar).all()
+    assert var.max() > 0
