@@ -37,7 +37,10 @@ static int lf_launch(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int ys
         S->done_n = n; S->gen = 0;
         SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->done, 0, n * 4, c->stream));
     }
-    S->gen++;
+    if (++S->gen >= (1 << 20)) { /* the progress words carry the generation in their upper bits: restart well before it overflows */
+        S->gen = 1;
+        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->done, 0, S->done_n * 4, c->stream));
+    }
     A.ticket = S->ticket; A.done = S->done; A.gen = S->gen; A.trace = g_lf_trace;
     SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->ticket, 0, 4, c->stream));
     const size_t dyn = (size_t)A.sbs_w * (sizeof(SvtB200LfMask) + 16);
