@@ -45,9 +45,12 @@ N_FRAMES = 17
 ENCODE_ORDER = [16, 8, 4, 2, 1, 3, 6, 5, 7, 12, 10, 9, 11, 14, 13, 15]
 QINDEX = 180          # app default q 45 -> qindex (quantizer_to_qindex, VPX/vp9_quantize.c)
 LF_LEVEL = 30
-TU_ROWS, TU_COLS = H4K // 32, W4K // 32  # 67 x 120 luma 32x32 TUs (the last 16 rows of the 2160 are left to smaller TUs)
+TU_ROWS, TU_COLS = H4K // 32, W4K // 32  # 67 x 120 luma 32x32 TUs; the last 16 luma / 8 chroma rows of the 2160 take smaller TUs
 N_TU_Y = TU_ROWS * TU_COLS
 N_TU_C = TU_ROWS * TU_COLS               # per chroma plane, 16x16
+# every sample of the picture belongs to exactly one TU: (plane 0 Y / 1 U / 2 V, tx_size, TU size, TUs per row, TU rows, first sample row)
+TU_PASSES = [(0, 3, 32, 120, 67, 0), (0, 2, 16, 240, 1, 2144), (1, 2, 16, 120, 67, 0), (1, 1, 8, 240, 1, 1072),
+             (2, 2, 16, 120, 67, 0), (2, 1, 8, 240, 1, 1072)]
 METRIC = "encoded fps (hot path: motion estimation + transform/quant/recon + deblocking, 4K enc-mode 8)"
 
 
@@ -72,7 +75,7 @@ def me_bytes(P):
 
 def txq_bytes():
     """6N^2+2 per block + N^2 for the reconstruction"""
-    return N_TU_Y * (7 * 1024 + 2) + 2 * N_TU_C * (7 * 256 + 2)
+    return sum(cols * rows * (7 * size * size + 2) for _, _, size, cols, rows, _ in TU_PASSES)
 
 
 def lf_bytes():
@@ -84,13 +87,15 @@ def make_clip(seed):
     return synth.make_clip(w, h, N_FRAMES, seed, k, g, a, b, m, noise)
 
 
-def tu_jobs(stride_y, ox, oy, n, size, stride_out):
-    """One job per TU on a regular grid: src/pred offsets into the padded plane, recon offsets into a packed plane."""
+def tu_jobs(stride_y, ox, oy, n, size, stride_out, cols=None, row0=0):
+    """One job per TU on a regular grid (cols TUs per row, first sample row row0): src/pred offsets into the (padded) plane,
+    recon offsets into a packed plane."""
+    cols = cols or TU_COLS
     jobs = np.zeros(n, dtype=api.TX_JOB_DTYPE)
-    r, c = np.divmod(np.arange(n), TU_COLS)
-    jobs["src_offset"] = (oy + r * size) * stride_y + ox + c * size
+    r, c = np.divmod(np.arange(n), cols)
+    jobs["src_offset"] = (oy + row0 + r * size) * stride_y + ox + c * size
     jobs["pred_offset"] = jobs["src_offset"]
-    jobs["recon_offset"] = (r * size) * stride_out + c * size
+    jobs["recon_offset"] = (row0 + r * size) * stride_out + c * size
     jobs["qrow"] = 0
     jobs["tx_type"] = 0
     jobs["flags"] = 1
@@ -189,13 +194,15 @@ class CpuPath:
         self.luma = [aligned_copy(f[0]) for f in clip]  # unpadded, aligned: source / prediction planes of the transform stage
         self.chroma = [(aligned_copy(f[1]), aligned_copy(f[2])) for f in clip]
         self.rows = H.quant_rows([QINDEX])
-        self.jobs_y = tu_jobs(W4K, 0, 0, N_TU_Y, 32, W4K)
-        self.jobs_c = tu_jobs(W4K // 2, 0, 0, N_TU_C, 16, W4K // 2)
+        self.passes = []
+        for plane, ts, size, cols, rows, row0 in TU_PASSES:
+            w = W4K if plane == 0 else W4K // 2
+            n = cols * rows
+            self.passes.append((plane, ts, size, tu_jobs(w, 0, 0, n, size, w, cols, row0), [aligned((n, size, size), np.int16) for _ in range(3)],
+                                np.zeros(n, np.uint16)))
         self.lfm, self.thr = lf_masks_32x32(), H.lf_thresholds()
         self.recon = [aligned((H4K, W4K), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8)]
         self.out = np.zeros(N_SB * 85, dtype=api.ME_RESULT_DTYPE)
-        self.coef = {32: [aligned((N_TU_Y, 32, 32), np.int16) for _ in range(3)], 16: [aligned((N_TU_C, 16, 16), np.int16) for _ in range(3)]}
-        self.eob = {32: np.zeros(N_TU_Y, np.uint16), 16: np.zeros(N_TU_C, np.uint16)}
         if self.kind == "reference":
             self.L = H.refdrv(1)
             self.me_handles = [self.L.refdrv_me_new() for _ in range(threads)]
@@ -216,22 +223,20 @@ class CpuPath:
             list(self.pool.map(lambda a: L.refdrv_me_range(self.me_handles[a[0]], C.byref(P), cur, s0, s1, a[1], a[2], self.out.ctypes.data), self._split(N_SB)))
         else:
             list(self.pool.map(lambda a: L.svtb200_oracle_me_picture(C.byref(P), cur, s0, s1, self.out.ctypes.data, None, a[1], a[2]), self._split(N_SB)))
-        # transform / quantise / reconstruct
-        for size, jobs, planes in ((32, self.jobs_y, (self.luma[n], self.luma[r0], self.recon[0])),
-                                   (16, self.jobs_c, (self.chroma[n][0], self.chroma[r0][0], self.recon[1])),
-                                   (16, self.jobs_c, (self.chroma[n][1], self.chroma[r0][1], self.recon[2]))):
-            src, pred, rec = planes
+        # transform / quantise / reconstruct: every TU of the three planes
+        for plane, ts, size, jobs, (c, q, dq), eob in self.passes:
+            src = self.luma[n] if plane == 0 else self.chroma[n][plane - 1]
+            pred = self.luma[r0] if plane == 0 else self.chroma[r0][plane - 1]
+            rec = self.recon[plane]
             pl = api.TxPlanes()
             pl.src, pl.src_stride, pl.src_bytes = src.ctypes.data, src.shape[1], src.nbytes
             pl.pred, pl.pred_stride, pl.pred_bytes = pred.ctypes.data, pred.shape[1], pred.nbytes
             pl.recon, pl.recon_stride, pl.recon_bytes = rec.ctypes.data, rec.shape[1], rec.nbytes
-            c, q, dq = self.coef[size]
-            ts = 3 if size == 32 else 2
             if self.kind == "reference":
                 list(self.pool.map(lambda a: L.refdrv_txq(ts, a[1], a[2], jobs.ctypes.data, C.byref(pl), self.rows.ctypes.data, c.ctypes.data,
-                                                          q.ctypes.data, dq.ctypes.data, self.eob[size].ctypes.data), self._split(len(jobs))))
+                                                          q.ctypes.data, dq.ctypes.data, eob.ctypes.data), self._split(len(jobs))))
             else:
-                self._port_txq(ts, jobs, src, pred, rec, c, q, dq, self.eob[size])
+                self._port_txq(ts, jobs, src, pred, rec, c, q, dq, eob)
         if n == 16:
             if self.kind == "reference":
                 L.refdrv_deblock(C.byref(self.LfP), self.recon[0].ctypes.data, W4K, self.recon[1].ctypes.data, self.recon[2].ctypes.data, W4K // 2,
@@ -268,12 +273,13 @@ def main():
     ap.add_argument("--steps", type=int, default=320)
     ap.add_argument("--warmup", type=int, default=32)
     ap.add_argument("--impl", default="b200")
+    ap.add_argument("--verify", action="store_true", help="after the end-to-end leg, recompute its last pictures synchronously on one queue and compare every downloaded byte")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     config = {"workload": "configs[2]: 4K (3840x2160) 8-bit yuv420p, enc-mode 8 (tune 1 parameter set): per picture ME (2 lists) + one "
-                          "transform/quantise/reconstruct pass over every TU (luma 32x32, chroma 16x16, q 45) + deblocking on the "
+                          "transform/quantise/reconstruct pass over every TU (luma 32x32, chroma 16x16; 16x16 / 8x8 for the last 16 rows; q 45) + deblocking on the "
                           "base-layer picture; 16-picture hierarchical mini-GOP in encode order",
               "pictures_per_step": 1,
               "queues": "motion estimation on the context's first compute queue, transform pass + deblocking on its second (they belong to different "
@@ -349,25 +355,28 @@ def main():
         d = L.svtb200_dev_alloc(h, arr.nbytes)
         L.svtb200_memcpy_h2d(h, d, arr.ctypes.data, arr.nbytes)
         return d
-    jobs_y = tu_jobs(sy, frames.FULL_PAD, frames.FULL_PAD, N_TU_Y, 32, W4K)
-    jobs_c = tu_jobs(W4K // 2, 0, 0, N_TU_C, 16, W4K // 2)
-    d_jobs_y, d_jobs_c = to_dev(jobs_y), to_dev(jobs_c)
+    # one job table per TU pass: luma addresses the padded resident plane, chroma the packed buffers
+    pass_n = [cols * rows for _, _, _, cols, rows, _ in TU_PASSES]
+    pass_cb = [n * size * size * 2 for n, (_, _, size, _, _, _) in zip(pass_n, TU_PASSES)]   # bytes of one coefficient array
+    d_jobs = [to_dev(tu_jobs(sy, frames.FULL_PAD, frames.FULL_PAD, n, size, W4K, cols, row0) if plane == 0 else
+                     tu_jobs(W4K // 2, 0, 0, n, size, W4K // 2, cols, row0))
+              for n, (plane, _, size, cols, rows, row0) in zip(pass_n, TU_PASSES)]
     d_rows = to_dev(H.quant_rows([QINDEX]))
     d_lfm, d_thr = to_dev(lf_masks_32x32()), to_dev(H.lf_thresholds())
     # result buffers exist NSLOT times: the end-to-end leg downloads slot s while the kernels of the next pictures fill the others
     NSLOT = 3
     d_rec = [[L.svtb200_dev_alloc(h, W4K * H4K), L.svtb200_dev_alloc(h, csize), L.svtb200_dev_alloc(h, csize)] for _ in range(NSLOT)]
     d_me = [L.svtb200_dev_alloc(h, N_SB * 85 * 40) for _ in range(NSLOT)]
-    d_q = [{32: L.svtb200_dev_alloc(h, N_TU_Y * 2048), 16: [L.svtb200_dev_alloc(h, N_TU_C * 512) for _ in range(2)]} for _ in range(NSLOT)]
-    d_dq = {32: L.svtb200_dev_alloc(h, N_TU_Y * 2048), 16: [L.svtb200_dev_alloc(h, N_TU_C * 512) for _ in range(2)]}
-    d_eob = [{32: L.svtb200_dev_alloc(h, N_TU_Y * 2), 16: [L.svtb200_dev_alloc(h, N_TU_C * 2) for _ in range(2)]} for _ in range(NSLOT)]
+    d_q = [[L.svtb200_dev_alloc(h, b) for b in pass_cb] for _ in range(NSLOT)]
+    d_dq = [L.svtb200_dev_alloc(h, b) for b in pass_cb]
+    d_eob = [[L.svtb200_dev_alloc(h, n * 2) for n in pass_n] for _ in range(NSLOT)]
     LfP = api.LfParams()
     LfP.width, LfP.height, LfP.mi_rows, LfP.mi_cols, LfP.y_only, LfP.filter_level = W4K, H4K, H4K // 8, W4K // 8, 0, LF_LEVEL
     # pinned host result buffers for the e2e leg
     pinned = lambda n: torch.empty(n, dtype=torch.uint8).pin_memory()
     h_me = [pinned(N_SB * 85 * 40) for _ in range(NSLOT)]
-    h_q = [{32: pinned(N_TU_Y * 2048), 16: [pinned(N_TU_C * 512) for _ in range(2)]} for _ in range(NSLOT)]
-    h_eob = [{32: pinned(N_TU_Y * 2), 16: [pinned(N_TU_C * 2) for _ in range(2)]} for _ in range(NSLOT)]
+    h_q = [[pinned(b) for b in pass_cb] for _ in range(NSLOT)]
+    h_eob = [[pinned(n * 2) for n in pass_n] for _ in range(NSLOT)]
     h_rec = [[pinned(W4K * H4K), pinned(csize), pinned(csize)] for _ in range(NSLOT)]
 
     def txq_planes(src, sstride, sbytes, pred, rec, rstride, rbytes):
@@ -405,11 +414,13 @@ def main():
             e[2].record(s2)
         ybytes = sy * dplane[n].padded_height
         rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
-        pl = txq_planes(dplane[n].buf, sy, ybytes, dplane[r0].buf, rec[0], W4K, W4K * H4K)
-        ctx.check(L.svtb200_txq_batch_dev(h, 3, N_TU_Y, d_jobs_y, C.byref(pl), d_rows, 1, None, q[32], d_dq[32], eob[32]), "txq y")
-        for k, (dc, pc) in enumerate(((d_u, d_u), (d_v, d_v))):
-            pl = txq_planes(dc[n], W4K // 2, csize, pc[r0], rec[1 + k], W4K // 2, csize)
-            ctx.check(L.svtb200_txq_batch_dev(h, 2, N_TU_C, d_jobs_c, C.byref(pl), d_rows, 1, None, q[16][k], d_dq[16][k], eob[16][k]), "txq c")
+        for k, (plane, ts, size, cols, rows, row0) in enumerate(TU_PASSES):
+            if plane == 0:
+                pl = txq_planes(dplane[n].buf, sy, ybytes, dplane[r0].buf, rec[0], W4K, W4K * H4K)
+            else:
+                dc = d_u if plane == 1 else d_v
+                pl = txq_planes(dc[n], W4K // 2, csize, dc[r0], rec[plane], W4K // 2, csize)
+            ctx.check(L.svtb200_txq_batch_dev(h, ts, pass_n[k], d_jobs[k], C.byref(pl), d_rows, 1, None, q[k], d_dq[k], eob[k]), "txq pass %d" % k)
         if timed:
             e[3].record(s2)
         if n == 16:
@@ -453,11 +464,9 @@ def main():
         rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
         d2h = lambda hb, db, nb: ("d2h" in skip) or ctx.check(L.svtb200_memcpy_d2h_async(h, hb.data_ptr(), db, nb), "d2h")
         d2h(h_me[slot], d_me[slot], N_SB * 85 * 40)                             # D2H ME results
-        d2h(h_q[slot][32], q[32], N_TU_Y * 2048)                                # D2H quantised coefficients + eob
-        d2h(h_eob[slot][32], eob[32], N_TU_Y * 2)
-        for k in range(2):
-            d2h(h_q[slot][16][k], q[16][k], N_TU_C * 512)
-            d2h(h_eob[slot][16][k], eob[16][k], N_TU_C * 2)
+        for k in range(len(TU_PASSES)):                                         # D2H quantised coefficients + eob of every TU pass
+            d2h(h_q[slot][k], q[k], pass_cb[k])
+            d2h(h_eob[slot][k], eob[k], pass_n[k] * 2)
         if n == 16:                                                            # D2H filtered reference picture
             d2h(h_rec[slot][0], rec[0], W4K * H4K)
             d2h(h_rec[slot][1], rec[1], csize)
@@ -522,13 +531,37 @@ def main():
     ms_e2e = (time.perf_counter() - t0) * 1000.0
     sampler.stop()
 
+    if args.verify:
+        # the pipelined leg (4 queues, 3 slots) must have produced exactly what a synchronous single-queue run produces
+        checked = 0
+        for i in range(args.warmup + args.steps - NSLOT, args.warmup + args.steps):
+            slot, n = i % NSLOT, ENCODE_ORDER[i % 16]
+            got = [h_me[slot].numpy().copy()] + [h_q[slot][k].numpy().copy() for k in range(len(TU_PASSES))]
+            got += [h_eob[slot][k].numpy().copy() for k in range(len(TU_PASSES))]
+            if n == 16:
+                got += [h_rec[slot][k].numpy().copy() for k in range(3)]
+            kernels(i, False, slot, overlap=False)
+            ctx.sync()
+            devs = [(d_me[slot], N_SB * 85 * 40)] + [(d_q[slot][k], pass_cb[k]) for k in range(len(TU_PASSES))]
+            devs += [(d_eob[slot][k], pass_n[k] * 2) for k in range(len(TU_PASSES))]
+            if n == 16:
+                devs += [(d_rec[slot][0], W4K * H4K), (d_rec[slot][1], csize), (d_rec[slot][2], csize)]
+            for g, (dptr, nbytes) in zip(got, devs):
+                want = np.zeros(nbytes, dtype=np.uint8)
+                ctx.check(L.svtb200_memcpy_d2h(h, want.ctypes.data, dptr, nbytes), "verify d2h")
+                if not np.array_equal(g, want):
+                    sys.stderr.write("verify: MISMATCH at step %d (picture %d), buffer of %d bytes\n" % (i, n, nbytes))
+                    raise SystemExit(2)
+                checked += nbytes
+        sys.stderr.write("verify: ok (%d result bytes of the last %d pipelined pictures equal the synchronous run)\n" % (checked, NSLOT))
+
     # every rank processed its own pictures (svt-vp9_b200/sharding.py): time = max over ranks, units = sum over ranks
     ms_res, units = sharding.agree_step(ms_res, args.steps, device="cuda")
     ms_e2e, _ = sharding.agree_step(ms_e2e, args.steps, device="cuda")
     value = units / (ms_res / 1000.0)
     e2e = units / (ms_e2e / 1000.0)
     h2d = W4K * H4K + 2 * csize  # the picture area of the three planes (padding and the 1/16 plane are made on the device)
-    d2h = N_SB * 85 * 40 + N_TU_Y * 2050 + 2 * N_TU_C * 514 + (W4K * H4K * 3 // 2) // 16  # filtered planes on 1 of 16 pictures
+    d2h = N_SB * 85 * 40 + sum(pass_cb) + 2 * sum(pass_n) + (W4K * H4K * 3 // 2) // 16  # filtered planes on 1 of 16 pictures
 
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -550,7 +583,7 @@ def main():
             per_kernel[k] = {"ms_total": stage_ms[k], "share": stage_ms[k] / sum(stage_ms.values()), "achieved_gbs": a, "frac": a / peak,
                              "traffic": traffic.get(k), "ms_per_picture_alone": iso, "achieved_gbs_alone": per_pic / (iso / 1000.0) / 1e9 if iso else None,
                              "frac_alone": per_pic / (iso / 1000.0) / 1e9 / peak if iso else None}
-    launches_dom = n_me if dom == "me_sb_kernel" else (3 * n_me if dom == "txq_kernel" else max(1, args.steps // 16))
+    launches_dom = n_me if dom == "me_sb_kernel" else (len(TU_PASSES) * n_me if dom == "txq_kernel" else max(1, args.steps // 16))
     roof = {"bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"],
             "traffic": traffic.get(dom), "kernel": dom, "alg_bytes_per_launch": alg[dom] / launches_dom,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)", "per_kernel": per_kernel}
