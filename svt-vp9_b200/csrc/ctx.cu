@@ -1,4 +1,5 @@
 /* ctx.cu -- context life cycle, memory helpers and the picture cache of the C ABI. */
+#include <stdlib.h>
 #include "common.cuh"
 
 extern "C" {
@@ -8,6 +9,10 @@ int svtb200_create(int device, SvtB200Ctx **out) {
     *out = nullptr;
     int n = 0;
     if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) { cudaGetLastError(); return SVTB200_ENODEV; }
+    /* SVTB200_BLOCKING_SYNC=1: host threads sleep in the synchronising calls instead of spinning (hosts whose cores are all
+     * busy with the encoder's own threads); must be chosen before the device's context exists */
+    const char *bs = getenv("SVTB200_BLOCKING_SYNC");
+    if (bs && bs[0] == '1') { cudaSetDeviceFlags(cudaDeviceScheduleBlockingSync); cudaGetLastError(); }
     if (cudaSetDevice(device) != cudaSuccess) { cudaGetLastError(); return SVTB200_ENODEV; }
     SvtB200Ctx *c = new SvtB200Ctx();
     c->device = device;

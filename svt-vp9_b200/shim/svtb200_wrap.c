@@ -20,6 +20,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "svtb200_ref_glue.h"
 
@@ -32,6 +33,8 @@ static pthread_cond_t  g_cv = PTHREAD_COND_INITIALIZER;
 static SvtB200Ctx     *g_ctx;
 static int             g_state; /* 0 untried, 1 ready, -1 unavailable */
 static unsigned long   g_me_pictures, g_me_sbs, g_lf_pictures, g_fallbacks;
+static double          g_t_resident, g_t_me, g_t_lf; /* seconds spent in uploads / svtb200_me_picture / svtb200_deblock_picture */
+static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 static void report(void) {
     const char *p = getenv("SVT_VP9_GPU_REPORT");
@@ -40,6 +43,7 @@ static void report(void) {
     if (!f) return;
     fprintf(f, "state %d\nme_pictures %lu\nme_sbs %lu\nlf_pictures %lu\nfallbacks %lu\nlaunches %llu\n", g_state, g_me_pictures, g_me_sbs,
             g_lf_pictures, g_fallbacks, g_ctx ? (unsigned long long)svtb200_launch_count(g_ctx) : 0ull);
+    fprintf(f, "ms_upload %d\nms_me %d\nms_lf %d\n", (int)(1e3 * g_t_resident), (int)(1e3 * g_t_me), (int)(1e3 * g_t_lf));
     fclose(f);
 }
 
@@ -64,6 +68,7 @@ static void *warm_up(void *arg) {
 }
 __attribute__((constructor)) static void svtb200_wrap_init(void) {
     pthread_t th;
+    setenv("SVTB200_BLOCKING_SYNC", "1", 0); /* the encoder keeps every core busy: do not spin while the GPU works */
     if (pthread_create(&th, NULL, warm_up, NULL) == 0) pthread_detach(th);
 }
 
@@ -121,14 +126,21 @@ static int run_picture(MeSlot *s, MeContext *me) {
     EbPaReferenceObject *r1 = s->P.num_lists == 2 ? (EbPaReferenceObject *)pcs->ref_pa_pic_ptr_array[1]->object_ptr : r0;
     int rc;
     pthread_mutex_lock(&g_mu); /* residency table + uploads are serialised; the kernels of different pictures still overlap the uploads */
+    const double t0 = now_s();
     rc = ensure_resident(cur, pcs->picture_number, want_q);
     if (rc == SVTB200_OK) rc = ensure_resident(r0, pcs->ref_pic_poc_array[0], want_q);
     if (rc == SVTB200_OK && s->P.num_lists == 2) rc = ensure_resident(r1, pcs->ref_pic_poc_array[1], want_q);
+    g_t_resident += now_s() - t0;
     pthread_mutex_unlock(&g_mu);
     if (rc != SVTB200_OK) return rc;
     const uint64_t ids[2] = {(uint64_t)(uintptr_t)r0, (uint64_t)(uintptr_t)r1};
     (void)me;
-    return svtb200_me_picture(g_ctx, &s->P, (uint64_t)(uintptr_t)cur, ids, s->res, s->P.rate_control_mode ? s->rcme : NULL);
+    const double t1 = now_s();
+    rc = svtb200_me_picture(g_ctx, &s->P, (uint64_t)(uintptr_t)cur, ids, s->res, s->P.rate_control_mode ? s->rcme : NULL);
+    pthread_mutex_lock(&g_mu);
+    g_t_me += now_s() - t1;
+    pthread_mutex_unlock(&g_mu);
+    return rc;
 }
 
 EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_index, uint32_t sb_origin_x, uint32_t sb_origin_y,
@@ -216,9 +228,11 @@ void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_
         }
         pthread_mutex_unlock(&g_mu);
     }
+    const double t2 = now_s();
     const int rc = svtb200_deblock_picture(g_ctx, &P, xd->plane[0].dst.buf, xd->plane[0].dst.stride, xd->plane[1].dst.buf, xd->plane[2].dst.buf,
                                            xd->plane[1].dst.stride, (const SvtB200LfMask *)cm->lf.lfm, cm->lf.lfm_stride, thr);
     pthread_mutex_lock(&g_mu);
+    g_t_lf += now_s() - t2;
     if (rc == SVTB200_OK) g_lf_pictures++; else g_fallbacks++;
     pthread_mutex_unlock(&g_mu);
     if (rc != SVTB200_OK) __real_eb_vp9_loop_filter_frame(cm, xd, frame_filter_level, y_only, partial_frame);
