@@ -286,8 +286,9 @@ def main():
                           "transform/quantise/reconstruct pass over every TU (luma 32x32, chroma 16x16; 16x16 / 8x8 for the last 16 rows; q 45) + deblocking on the "
                           "base-layer picture; 16-picture hierarchical mini-GOP in encode order",
               "pictures_per_step": 1,
-              "queues": "motion estimation on the context's first compute queue, transform pass + deblocking on its second (they belong to different "
-                        "pictures in the encoder); value = CUDA events around the K steps with both queues joined inside the timed region",
+              "queues": "motion estimation (followed by the three small edge-row transform launches) on the context's first compute queue, the "
+                        "picture-sized transform launches + deblocking on its second (they belong to different pictures in the encoder); value = "
+                        "CUDA events around the K steps with both queues joined inside the timed region",
               "l2": "17 distinct pictures (165 MB of luma planes + 105 MB chroma) cycled: working set larger than the 126 MB L2",
               "parallelism": "pictures sharded across GPUs (independent mini-GOP streams per rank), no collective on the data path"}
 
@@ -402,6 +403,7 @@ def main():
     ctx.select_compute(api.COMPUTE)
 
     _txq_cache = {}
+    EDGE_PASSES = tuple(k for k, (_, _, _, cols, rows, _) in enumerate(TU_PASSES) if rows == 1)
 
     def txq_args(slot, n, r0):
         """ctypes argument tuples of the six transform launches of picture n into result slot 'slot' (built once)"""
@@ -431,17 +433,32 @@ def main():
         ctx.check(L.svtb200_me_picture_dev(h, C.byref(P), n, ids, d_me[slot], None), "me_picture_dev")
         if timed:
             e[1].record(stream)
+        targs = txq_args(slot, n, r0)
         if overlap:
+            # the three edge passes (240 small blocks each, latency-bound 5-7 us launches) ride in the tail of the ME grid on the
+            # first queue; the picture-sized passes go to the second queue
+            for k in EDGE_PASSES:
+                rc = L.svtb200_txq_batch_dev(*targs[k])
+                if rc:
+                    ctx.check(rc, "txq_batch_dev")
+            L.svtb200_picture_touch(h, n)
+            L.svtb200_picture_touch(h, r0)
+            if n == 16:
+                edge_done = ctx.marker(api.COMPUTE)
             ctx.select_compute(api.COMPUTE2)
         if timed:
             e[2].record(s2)
-        for a in txq_args(slot, n, r0):
+        for k, a in enumerate(targs):
+            if overlap and k in EDGE_PASSES:
+                continue
             rc = L.svtb200_txq_batch_dev(*a)
             if rc:
                 ctx.check(rc, "txq_batch_dev")
         if timed:
             e[3].record(s2)
         if n == 16:
+            if overlap:
+                ctx.stream_wait(api.COMPUTE2, edge_done)   # deblocking needs the reconstruction of the edge rows too
             rec = d_rec[slot]
             ctx.check(L.svtb200_deblock_picture_dev(h, C.byref(LfP), rec[0], W4K, rec[1], rec[2], W4K // 2, d_lfm, 60, d_thr), "deblock")
         if timed:
@@ -468,7 +485,8 @@ def main():
         if "h2d" not in skip:
             ctx.picture_upload_luma(n, PS[n][0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, False)   # H2D luma picture area; padding + 1/16 on the device
             if n in chroma_used:
-                ctx.stream_wait(api.UPLOAD, chroma_used[n])
+                for m in chroma_used[n]:
+                    ctx.stream_wait(api.UPLOAD, m)
             ctx.check(L.svtb200_memcpy_h2d_async(h, d_u[n], pu[n].data_ptr(), csize), "h2d u")     # H2D chroma
             ctx.check(L.svtb200_memcpy_h2d_async(h, d_v[n], pv[n].data_ptr(), csize), "h2d v")
             ctx.fence(api.UPLOAD, api.COMPUTE)
@@ -477,9 +495,9 @@ def main():
             r0 = n
         else:
             _, r0 = kernels(i, False, slot)
-        chroma_used[n] = chroma_used[r0] = ctx.marker(api.COMPUTE2)
-        ctx.stream_wait(api.DOWNLOAD, chroma_used[n])
-        ctx.fence(api.COMPUTE, api.DOWNLOAD)
+        chroma_used[n] = chroma_used[r0] = (ctx.marker(api.COMPUTE2), ctx.marker(api.COMPUTE))   # both queues read the chroma buffers
+        for m in chroma_used[n]:
+            ctx.stream_wait(api.DOWNLOAD, m)
         rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
         d2h = lambda hb, db, nb: ("d2h" in skip) or ctx.check(L.svtb200_memcpy_d2h_async(h, hb.data_ptr(), db, nb), "d2h")
         d2h(h_me[slot], d_me[slot], N_SB * 85 * 40)                             # D2H ME results
