@@ -19,6 +19,11 @@
  *            (batched twins of eb_vp9_fdct* / fht*, eb_vp9_quantize_b[_32x32], eb_vp9_idct*_add/iht*_add)
  *         -> svtb200_txq_batch (fused residual -> transform -> quantise -> [inverse + recon])
  *
+ *   around the seams (same library): svtb200_picture_upload_luma (padding + 1/4, 1/16 decimation of the picture-analysis
+ *       front end), svtb200_zz_sad_picture (compute_zz_sad), svtb200_block_stats_picture
+ *       (compute_block_mean_compute_variance), svtb200_build_masks (eb_vp9_build_mask_frame), svtb200_pick_filter_level
+ *       (eb_vp9_pick_filter_level), svtb200_pad_plane_dev (eb_vp9_generate_padding); each cites its reference lines below.
+ *
  * "Host" entry points take HOST pointers (pinned or pageable) and perform the host<->device copies
  * themselves; the "_dev" twins take device pointers already resident in HBM.
  */
@@ -65,7 +70,7 @@ void  svtb200_dev_free(SvtB200Ctx *ctx, void *p);
 int   svtb200_memcpy_h2d(SvtB200Ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int   svtb200_memcpy_d2h(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 
-/* A context owns three in-order queues: COMPUTE (every kernel, and the synchronous copies above), UPLOAD (picture
+/* A context owns four in-order queues: COMPUTE and COMPUTE2 (kernels, and the synchronous copies above), UPLOAD (picture
  * uploads and svtb200_memcpy_h2d_async) and DOWNLOAD (svtb200_memcpy_d2h_async), so that the PCIe traffic of the
  * previous / next picture overlaps the kernels of the current one -- the role the reference's picture-level pipeline
  * (EbEncHandle.c: one process per stage, several pictures in flight) plays on the CPU.  Picture uploads are ordered
