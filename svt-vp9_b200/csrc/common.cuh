@@ -35,7 +35,7 @@ struct SvtB200Ctx {
     cudaStream_t up = nullptr, down = nullptr;  /* host->device and device->host copy streams */
     cudaEvent_t  markers[SVTB200_MARKER_RING] = {};
     uint64_t     next_ticket = 1;
-    std::mutex   mu;
+    std::recursive_mutex mu; /* recursive: the host-pointer entry points hold it across their copy -> _dev call -> copy sequence */
     std::string  err;
     uint64_t     launches = 0;
     int          smem_optin = 0, sm_count = 0;

@@ -65,7 +65,7 @@ int svtb200_sync(SvtB200Ctx *c) {
 }
 int svtb200_select_compute(SvtB200Ctx *c, int which) {
     if (!c || (which != SVTB200_STREAM_COMPUTE && which != SVTB200_STREAM_COMPUTE2)) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     c->stream = which == SVTB200_STREAM_COMPUTE2 ? c->compute[1] : c->compute[0];
     return SVTB200_OK;
 }
@@ -83,7 +83,7 @@ int svtb200_memcpy_d2h_async(SvtB200Ctx *c, void *h, const void *d, size_t n) {
 }
 int svtb200_marker(SvtB200Ctx *c, int stream, uint64_t *ticket) {
     if (!c || !ticket || stream < 0 || stream > 3) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     const uint64_t t = c->next_ticket++;
     cudaEvent_t &e = c->markers[t % SVTB200_MARKER_RING];
     if (!e) SVTB200_CUDA_CHECK(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -99,7 +99,7 @@ static int marker_event(SvtB200Ctx *c, uint64_t ticket, cudaEvent_t *e) {
 }
 int svtb200_stream_wait(SvtB200Ctx *c, int stream, uint64_t ticket) {
     if (!c || stream < 0 || stream > 3) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaEvent_t e;
     int rc = marker_event(c, ticket, &e);
     if (rc) return rc;
@@ -115,7 +115,7 @@ int svtb200_wait(SvtB200Ctx *c, uint64_t ticket) {
     if (!c) return SVTB200_EINVAL;
     cudaEvent_t e;
     {
-        std::lock_guard<std::mutex> g(c->mu);
+        std::lock_guard<std::recursive_mutex> g(c->mu);
         int rc = marker_event(c, ticket, &e);
         if (rc) return rc;
     }
@@ -192,7 +192,7 @@ static int upload_end(SvtB200Ctx *c, DevPicture &p) {
 int svtb200_picture_upload(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *full, const SvtB200Plane *quarter,
                            const SvtB200Plane *sixteenth) {
     if (!c || !full || !full->buf) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     DevPicture &p = c->pics[pic_id];
     int rc;
@@ -245,7 +245,7 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
                                 int make_quarter) {
     if (!c || !full || !full->buf || full->stride <= 0 || full->padded_height <= 0 || quarter_pad < 0 || sixteenth_pad < 0) return SVTB200_EINVAL;
     if ((full->stride & 3) || full->width <= 0 || full->height <= 0) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     DevPicture &p = c->pics[pic_id];
     int rc;
@@ -277,7 +277,7 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
 
 int svtb200_picture_plane_dev(SvtB200Ctx *c, uint64_t pic_id, int which, SvtB200Plane *out) {
     if (!c || !out || which < 0 || which > 2) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     auto it = c->pics.find(pic_id);
     if (it == c->pics.end() || !it->second.pl[which].buf) return SVTB200_ENOENT;
     svtb200_pic_acquire(c, it->second); /* work queued on the compute stream after this call sees the uploaded contents */
@@ -291,7 +291,7 @@ int svtb200_picture_plane_dev(SvtB200Ctx *c, uint64_t pic_id, int which, SvtB200
 int svtb200_pad_plane_dev(SvtB200Ctx *c, uint8_t *buf, int32_t stride, int32_t width, int32_t height, int32_t pad_x, int32_t pad_y) {
     if (!c || !buf || stride <= 0 || width <= 0 || height <= 0 || pad_x < 0 || pad_y < 0 || width + 2 * pad_x > stride) return SVTB200_EINVAL;
     if ((stride & 3) || ((uintptr_t)buf & 3) || ((width + 2 * pad_x) & 3)) { c->err = "pad_plane: stride, base and padded width must be multiples of 4"; return SVTB200_EINVAL; }
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     const int cols = width + 2 * pad_x, rows = height + 2 * pad_y;
     /* the kernel treats 'cols' as the row length to write and 'stride' as the pitch */
@@ -303,7 +303,7 @@ int svtb200_pad_plane_dev(SvtB200Ctx *c, uint8_t *buf, int32_t stride, int32_t w
 
 int svtb200_picture_touch(SvtB200Ctx *c, uint64_t pic_id) {
     if (!c) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     auto it = c->pics.find(pic_id);
     if (it == c->pics.end()) return SVTB200_ENOENT;
     cudaSetDevice(c->device);
@@ -313,7 +313,7 @@ int svtb200_picture_touch(SvtB200Ctx *c, uint64_t pic_id) {
 
 int svtb200_picture_release(SvtB200Ctx *c, uint64_t pic_id) {
     if (!c) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     auto it = c->pics.find(pic_id);
     if (it == c->pics.end()) return SVTB200_ENOENT;
     cudaSetDevice(c->device);

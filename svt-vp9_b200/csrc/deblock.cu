@@ -56,7 +56,7 @@ extern "C" {
 int svtb200_deblock_picture_dev(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int32_t ys, uint8_t *u, uint8_t *v, int32_t cs,
                                 const SvtB200LfMask *lfm, int32_t lfm_stride, const SvtB200LfThresh *thr) {
     if (!c) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     return lf_launch(c, p, y, ys, u, v, cs, lfm, lfm_stride, thr);
 }
@@ -65,7 +65,7 @@ int svtb200_deblock_picture(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y,
                             const SvtB200LfMask *lfm, int32_t lfm_stride, const SvtB200LfThresh thr[64]) {
     if (!c || !p || !y || !lfm || !thr) return SVTB200_EINVAL;
     if (!p->filter_level) return SVTB200_OK;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     const int H = p->mi_rows * 8, W = p->mi_cols * 8, sbs_h = (p->mi_rows + 7) >> 3;
     const size_t yb = (size_t)H * W, cb = p->y_only ? 0 : (size_t)(H / 2) * (W / 2), mb = (size_t)lfm_stride * sbs_h * sizeof(SvtB200LfMask);

@@ -25,7 +25,7 @@ int svtb200_pick_filter_level(int32_t ac_q, int32_t is_key_frame) {
 int svtb200_build_masks_dev(SvtB200Ctx *c, int32_t mi_rows, int32_t mi_cols, const SvtB200LfModeInfo *mi, int32_t mi_stride,
                             SvtB200LfMask *lfm, int32_t lfm_stride) {
     if (!c) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     return lfm_launch(c, mi_rows, mi_cols, mi, mi_stride, lfm, lfm_stride);
 }
@@ -33,7 +33,7 @@ int svtb200_build_masks_dev(SvtB200Ctx *c, int32_t mi_rows, int32_t mi_cols, con
 int svtb200_build_masks(SvtB200Ctx *c, int32_t mi_rows, int32_t mi_cols, const SvtB200LfModeInfo *mi, int32_t mi_stride,
                         SvtB200LfMask *lfm, int32_t lfm_stride) {
     if (!c || !mi || !lfm || mi_rows <= 0 || mi_cols <= 0) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     const int sbs_h = (mi_rows + 7) >> 3;
     const size_t mib = (size_t)mi_rows * mi_stride * sizeof(SvtB200LfModeInfo), lb = (size_t)sbs_h * lfm_stride * sizeof(SvtB200LfMask);

@@ -61,7 +61,7 @@ extern "C" {
 int svtb200_me_picture_dev(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, const uint64_t ref_id[2],
                            SvtB200MeCuResult *out_dev, uint32_t *rcme_dev) {
     if (!c) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     return me_launch(c, P, cur_id, ref_id, out_dev, rcme_dev);
 }
@@ -69,7 +69,7 @@ int svtb200_me_picture_dev(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur
 int svtb200_me_picture(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, const uint64_t ref_id[2],
                        SvtB200MeCuResult *out, uint32_t *out_rcme) {
     if (!c || !P || !out) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     const int n_sb = ((P->luma_width + ME_SB - 1) / ME_SB) * ((P->luma_height + ME_SB - 1) / ME_SB);
     const size_t bytes = (size_t)n_sb * 85 * sizeof(SvtB200MeCuResult);

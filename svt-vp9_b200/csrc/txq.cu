@@ -292,7 +292,7 @@ extern "C" {
 
 int svtb200_set_scan(SvtB200Ctx *c, int tx_size, int tx_type, const int16_t *scan, const int16_t *iscan) {
     if (!c || tx_size < 0 || tx_size > 3 || tx_type < 0 || tx_type > 3 || !scan || !iscan) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     const int n = (4 << tx_size) * (4 << tx_size);
     ScanTable &s = c->scans[tx_size][tx_type];
@@ -309,7 +309,7 @@ int svtb200_set_scan(SvtB200Ctx *c, int tx_size, int tx_type, const int16_t *sca
 int svtb200_fwd_txfm_batch_dev(SvtB200Ctx *c, int tx_size, int tx_type, int partial32, int n, const int16_t *in, int16_t *out) {
     if (!c || tx_size < 0 || tx_size > 3 || tx_type < 0 || tx_type > 3 || n < 0 || !in || !out) return SVTB200_EINVAL;
     if (n == 0) return SVTB200_OK;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     TxqArgs A; memset(&A, 0, sizeof(A));
     A.in16 = in; A.coeff = out; A.n = n; A.tx_type = tx_size == 3 ? 0 : tx_type; A.partial32 = partial32 && tx_size == 3;
@@ -322,7 +322,7 @@ int svtb200_quantize_batch_dev(SvtB200Ctx *c, int tx_size, int tx_type, int n, c
                                int n_qrows, const uint16_t *qrow_index, int16_t *qcoeff, int16_t *dqcoeff, uint16_t *eob) {
     if (!c || tx_size < 0 || tx_size > 3 || tx_type < 0 || tx_type > 3 || n < 0 || !coeff || !qrows || n_qrows < 1 || !qcoeff || !dqcoeff || !eob) return SVTB200_EINVAL;
     if (n == 0) return SVTB200_OK;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     TxqArgs A; memset(&A, 0, sizeof(A));
     A.in16 = coeff; A.qrows = qrows; A.qrow_index = qrow_index; A.qcoeff = qcoeff; A.dqcoeff = dqcoeff; A.eob = eob;
@@ -337,7 +337,7 @@ int svtb200_quantize_batch_dev(SvtB200Ctx *c, int tx_size, int tx_type, int n, c
 int svtb200_inv_txfm_add_batch_dev(SvtB200Ctx *c, int tx_size, int tx_type, int n, const int16_t *dq, const uint16_t *eob, uint8_t *dest) {
     if (!c || tx_size < 0 || tx_size > 3 || tx_type < 0 || tx_type > 3 || n < 0 || !dq || !dest) return SVTB200_EINVAL;
     if (n == 0) return SVTB200_OK;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     TxqArgs A; memset(&A, 0, sizeof(A));
     A.in16 = dq; A.eob_in = eob; A.dest = dest; A.n = n; A.tx_type = tx_size == 3 ? 0 : tx_type;
@@ -350,7 +350,7 @@ int svtb200_txq_batch_dev(SvtB200Ctx *c, int tx_size, int n, const SvtB200TxJob 
                           const SvtB200QuantRow *qrows, int n_qrows, int16_t *coeff, int16_t *qcoeff, int16_t *dqcoeff, uint16_t *eob) {
     if (!c || tx_size < 0 || tx_size > 3 || n < 0 || !jobs || !pl || !qrows || n_qrows < 1 || !qcoeff || !dqcoeff || !eob) return SVTB200_EINVAL;
     if (n == 0) return SVTB200_OK;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     TxqArgs A; memset(&A, 0, sizeof(A));
     A.jobs = jobs; A.pl = *pl; A.qrows = qrows; A.coeff = coeff; A.qcoeff = qcoeff; A.dqcoeff = dqcoeff; A.eob = eob; A.n = n;
@@ -364,10 +364,11 @@ int svtb200_txq_batch_dev(SvtB200Ctx *c, int tx_size, int n, const SvtB200TxJob 
 /* ---- host-pointer variants: stage through device scratch, copies on the context stream ---- */
 int svtb200_fwd_txfm_batch(SvtB200Ctx *c, int tx_size, int tx_type, int partial32, int n, const int16_t *in, int16_t *out) {
     if (!c || n < 0 || !in || !out || tx_size < 0 || tx_size > 3) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> whole(c->mu); /* the staging buffer c->scratch is shared: one host call at a time */
     if (n == 0) return SVTB200_OK;
     const size_t bytes = (size_t)n * (4 << tx_size) * (4 << tx_size) * 2;
     {
-        std::lock_guard<std::mutex> g(c->mu);
+        std::lock_guard<std::recursive_mutex> g(c->mu);
         cudaSetDevice(c->device);
         int rc = svtb200_grow(c, (void **)&c->scratch, &c->scratch_bytes, 2 * bytes + 1024);
         if (rc) return rc;
@@ -385,11 +386,12 @@ int svtb200_fwd_txfm_batch(SvtB200Ctx *c, int tx_size, int tx_type, int partial3
 int svtb200_quantize_batch(SvtB200Ctx *c, int tx_size, int tx_type, int n, const int16_t *coeff, const SvtB200QuantRow *qrows,
                            int n_qrows, const uint16_t *qrow_index, int16_t *qcoeff, int16_t *dqcoeff, uint16_t *eob) {
     if (!c || n < 0 || !coeff || !qrows || n_qrows < 1 || !qcoeff || !dqcoeff || !eob || tx_size < 0 || tx_size > 3) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> whole(c->mu); /* the staging buffer c->scratch is shared: one host call at a time */
     if (n == 0) return SVTB200_OK;
     const size_t bytes = (size_t)n * (4 << tx_size) * (4 << tx_size) * 2;
     uint8_t *p;
     {
-        std::lock_guard<std::mutex> g(c->mu);
+        std::lock_guard<std::recursive_mutex> g(c->mu);
         cudaSetDevice(c->device);
         int rc = svtb200_grow(c, (void **)&c->scratch, &c->scratch_bytes, 3 * bytes + (size_t)n * 4 + (size_t)n_qrows * sizeof(SvtB200QuantRow) + 4096);
         if (rc) return rc;
@@ -412,11 +414,12 @@ int svtb200_quantize_batch(SvtB200Ctx *c, int tx_size, int tx_type, int n, const
 
 int svtb200_inv_txfm_add_batch(SvtB200Ctx *c, int tx_size, int tx_type, int n, const int16_t *dq, const uint16_t *eob, uint8_t *dest) {
     if (!c || n < 0 || !dq || !dest || tx_size < 0 || tx_size > 3) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> whole(c->mu); /* the staging buffer c->scratch is shared: one host call at a time */
     if (n == 0) return SVTB200_OK;
     const size_t nn = (size_t)(4 << tx_size) * (4 << tx_size), bytes = (size_t)n * nn * 2;
     uint8_t *p;
     {
-        std::lock_guard<std::mutex> g(c->mu);
+        std::lock_guard<std::recursive_mutex> g(c->mu);
         cudaSetDevice(c->device);
         int rc = svtb200_grow(c, (void **)&c->scratch, &c->scratch_bytes, bytes + (size_t)n * nn + 2048);
         if (rc) return rc;
@@ -437,11 +440,12 @@ int svtb200_inv_txfm_add_batch(SvtB200Ctx *c, int tx_size, int tx_type, int n, c
 int svtb200_txq_batch(SvtB200Ctx *c, int tx_size, int n, const SvtB200TxJob *jobs, const SvtB200TxPlanes *pl,
                       const SvtB200QuantRow *qrows, int n_qrows, int16_t *coeff, int16_t *qcoeff, int16_t *dqcoeff, uint16_t *eob) {
     if (!c || n < 0 || !jobs || !pl || !pl->src || !pl->pred || !qrows || n_qrows < 1 || !qcoeff || !dqcoeff || !eob || tx_size < 0 || tx_size > 3) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> whole(c->mu); /* the staging buffer c->scratch is shared: one host call at a time */
     if (n == 0) return SVTB200_OK;
     const size_t nn = (size_t)(4 << tx_size) * (4 << tx_size), cb = (size_t)n * nn * 2;
     uint8_t *p;
     {
-        std::lock_guard<std::mutex> g(c->mu);
+        std::lock_guard<std::recursive_mutex> g(c->mu);
         cudaSetDevice(c->device);
         const size_t need = pl->src_bytes + pl->pred_bytes + pl->recon_bytes + 3 * cb + (size_t)n * (sizeof(SvtB200TxJob) + 2) +
                             (size_t)n_qrows * sizeof(SvtB200QuantRow) + 8192;

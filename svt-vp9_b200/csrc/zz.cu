@@ -124,14 +124,14 @@ extern "C" {
 
 int svtb200_block_stats_picture_dev(SvtB200Ctx *c, uint64_t pic_id, int32_t w, int32_t h, uint8_t *y_mean, uint16_t *variance) {
     if (!c) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     return stats_launch(c, pic_id, w, h, y_mean, variance);
 }
 
 int svtb200_block_stats_picture(SvtB200Ctx *c, uint64_t pic_id, int32_t w, int32_t h, uint8_t *y_mean, uint16_t *variance) {
     if (!c || !y_mean || !variance || w <= 0 || h <= 0) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     const size_t n = (size_t)((w + 63) / 64) * ((h + 63) / 64) * 85;
     int rc = svtb200_grow(c, (void **)&c->scratch, &c->scratch_bytes, n * 3 + 512);
@@ -148,14 +148,14 @@ int svtb200_block_stats_picture(SvtB200Ctx *c, uint64_t pic_id, int32_t w, int32
 
 int svtb200_zz_sad_picture_dev(SvtB200Ctx *c, uint64_t cur_id, uint64_t prev_id, int32_t w, int32_t h, int32_t th_shift, uint8_t *scores, uint32_t *sads) {
     if (!c) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     return zz_launch(c, cur_id, prev_id, w, h, th_shift, scores, sads);
 }
 
 int svtb200_zz_sad_picture(SvtB200Ctx *c, uint64_t cur_id, uint64_t prev_id, int32_t w, int32_t h, int32_t th_shift, uint8_t *scores, uint32_t *sads) {
     if (!c || !scores || w <= 0 || h <= 0) return SVTB200_EINVAL;
-    std::lock_guard<std::mutex> g(c->mu);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     const size_t n = (size_t)((w + 63) / 64) * ((h + 63) / 64);
     int rc = svtb200_grow(c, (void **)&c->scratch, &c->scratch_bytes, n * 5 + 512);
