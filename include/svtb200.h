@@ -206,6 +206,16 @@ int svtb200_block_stats_picture(SvtB200Ctx *ctx, uint64_t pic_id, int32_t luma_w
 int svtb200_block_stats_picture_dev(SvtB200Ctx *ctx, uint64_t pic_id, int32_t luma_width, int32_t luma_height, uint8_t *y_mean_dev,
                                     uint16_t *variance_dev);
 
+/* sub_sample_luma_generate_pixel_intensity_histogram_bins() + calculate_histogram() (EbPictureAnalysisProcess.c:4237, :128;
+ * from gathering_picture_statistics :4893): the 256-bin intensity histograms of the picture's 1/16 plane over a regions_w x
+ * regions_h grid of regions (region = floor(size / regions); the last region of a row / column takes the remainder).  Each
+ * bin is (1 + count) << 4, exactly as the reference initialises and scales them.  hist: [regions_w][regions_h][256] uint32
+ * (the reference's picture_histogram[w][h][0][bin]); avg: [regions_w][regions_h] bytes = (sum + area / 2) / area
+ * (average_intensity_per_region[w][h][0]); sum16: the sum over regions of (region sum << 4)
+ * (sum_average_intensity_total_regions_luma).  The picture must be resident with its 1/16 plane. */
+int svtb200_luma_histogram_picture(SvtB200Ctx *ctx, uint64_t pic_id, int32_t regions_w, int32_t regions_h, uint32_t *hist_host,
+                                   uint8_t *avg_host, uint64_t *sum16_host);
+
 /* compute_zz_sad() (Source/Lib/Codec/EbMotionEstimationProcess.c:431; called per picture with look-ahead, :1079-1096):
  * for every COMPLETE 64x64 super-block the 16x16 SAD between the current picture's 1/16 plane and a 4:1 point decimation
  * (eb_vp9_decimation_2d, step 4) of the PREVIOUS picture's full-resolution plane at the same position, and the non-moving

@@ -790,3 +790,24 @@ void svtb200_oracle_block_stats_picture(const SvtB200Plane *full, int w, int h, 
         for (int i = 0; i < 85; i++) { y_mean[(size_t)sb * 85 + i] = (uint8_t)(m[i] >> 8); variance[(size_t)sb * 85 + i] = (uint16_t)((q[i] - m[i] * m[i]) >> 16); }
     }
 }
+
+
+/* sub_sample_luma_generate_pixel_intensity_histogram_bins + calculate_histogram (EbPictureAnalysisProcess.c:4237-4312, :128-150)
+ * on the 1/16 plane: bins start at 1, are counted with decimation step 1 and end up << 4; average = (sum + area/2) / area. */
+void svtb200_oracle_luma_histogram(const SvtB200Plane *p16, int rw, int rh, uint32_t *hist, uint8_t *avg, uint64_t *sum16) {
+    const int regw = p16->width / rw, regh = p16->height / rh;
+    *sum16 = 0;
+    for (int iw = 0; iw < rw; iw++)
+        for (int ih = 0; ih < rh; ih++) {
+            uint32_t *hg = hist + ((size_t)iw * rh + ih) * 256;
+            const int cw = regw + (iw == rw - 1 ? p16->width - rw * regw : 0), ch = regh + (ih == rh - 1 ? p16->height - rh * regh : 0);
+            const uint8_t *s = p16->buf + (size_t)(p16->origin_y + ih * regh) * p16->stride + p16->origin_x + iw * regw;
+            uint64_t sum = 0;
+            for (int b = 0; b < 256; b++) hg[b] = 1;
+            for (int y = 0; y < ch; y++)
+                for (int x = 0; x < cw; x++) { hg[s[(size_t)y * p16->stride + x]]++; sum += s[(size_t)y * p16->stride + x]; }
+            avg[iw * rh + ih] = (uint8_t)((sum + (((uint64_t)cw * ch) >> 1)) / ((uint64_t)cw * ch));
+            *sum16 += sum << 4;
+            for (int b = 0; b < 256; b++) hg[b] <<= 4;
+        }
+}

@@ -32,6 +32,8 @@ void svtb200_oracle_build_masks(int mi_rows, int mi_cols, const SvtB200LfModeInf
 
 void svtb200_oracle_block_stats_picture(const SvtB200Plane *full, int w, int h, uint8_t *y_mean, uint16_t *variance);
 
+void svtb200_oracle_luma_histogram(const SvtB200Plane *p16, int rw, int rh, uint32_t *hist, uint8_t *avg, uint64_t *sum16);
+
 #ifdef __cplusplus
 }
 #endif

@@ -23,7 +23,7 @@ EbErrorType __real_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static int   g_mode = -1; /* 0 off, 1 check, 2 dump */
 static char  g_dir[512];
-static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed, g_stats_bad;
+static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed, g_stats_bad, g_hist_pics, g_hist_bad;
 static int   g_max_dump_pics = 4, g_dump_from = 0;
 
 #define MAX_TRACKED 64
@@ -38,7 +38,7 @@ static void write_summary(void) {
     snprintf(path, sizeof(path), "%s/summary.txt", g_dir);
     FILE *f = fopen(path, "w");
     if (!f) return;
-    fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\nstats_bad %ld\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped, g_stats_bad);
+    fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\nstats_bad %ld\nhist_pics %ld\nhist_bad %ld\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped, g_stats_bad, g_hist_pics, g_hist_bad);
     fclose(f);
 }
 
@@ -97,6 +97,20 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
         svtb200_oracle_me_sb(&P, cur, r0, P.num_lists == 2 ? r1 : NULL, sb_origin_x / 64, sb_origin_y / 64, mine, &rcme, &tr);
         int bad = 0;
         for (int i = 0; i < 85; i++) if (memcmp(&mine[i], &refres[i], sizeof(mine[i]))) bad++;
+        if (sb_index == 0) { /* once per picture: the luma histograms of the 1/16 plane against the oracle restatement */
+            SequenceControlSet *scs = (SequenceControlSet *)pcs->sequence_control_set_wrapper_ptr->object_ptr;
+            const int rw = (int)scs->picture_analysis_number_of_regions_per_width, rh = (int)scs->picture_analysis_number_of_regions_per_height;
+            uint32_t *hg = (uint32_t *)malloc((size_t)rw * rh * 256 * sizeof(uint32_t));
+            uint8_t av[256]; uint64_t s16 = 0;
+            svtb200_oracle_luma_histogram(&cur[2], rw, rh, hg, av, &s16);
+            long hb = 0;
+            for (int iw = 0; iw < rw; iw++) for (int ih = 0; ih < rh; ih++) {
+                for (int b = 0; b < 256; b++) if (hg[((size_t)iw * rh + ih) * 256 + b] != pcs->picture_histogram[iw][ih][0][b]) hb++;
+                if (av[iw * rh + ih] != (uint8_t)pcs->average_intensity_per_region[iw][ih][0]) hb++;
+            }
+            free(hg);
+            pthread_mutex_lock(&g_mu); g_hist_pics++; g_hist_bad += hb; pthread_mutex_unlock(&g_mu);
+        }
         {   /* the picture-analysis statistics of this SB (compute_block_mean_compute_variance) against the oracle restatement */
             SvtB200Plane one = cur[0];
             uint8_t ym[85]; uint16_t var[85];

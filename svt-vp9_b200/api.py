@@ -235,6 +235,15 @@ class Context:
         self.check(self.L.svtb200_block_stats_picture(self.h, pic_id, width, height, ym.ctypes.data, var.ctypes.data), "block_stats_picture")
         return ym, var
 
+    def luma_histogram_picture(self, pic_id, regions_w=4, regions_h=4):
+        """-> (hist u32[rw, rh, 256], avg u8[rw, rh], sum16) of the resident picture's 1/16 plane"""
+        hist = np.zeros((regions_w, regions_h, 256), dtype=np.uint32)
+        avg = np.zeros((regions_w, regions_h), dtype=np.uint8)
+        s16 = C.c_uint64()
+        self.L.svtb200_luma_histogram_picture.argtypes = [C.c_void_p, C.c_uint64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+        self.check(self.L.svtb200_luma_histogram_picture(self.h, pic_id, regions_w, regions_h, hist.ctypes.data, avg.ctypes.data, C.byref(s16)), "luma_histogram_picture")
+        return hist, avg, s16.value
+
     def me_trace(self, n_sb):
         tr = np.zeros(n_sb, dtype=ME_TRACE_DTYPE)
         self.check(self.L.svtb200_me_read_trace(self.h, tr.ctypes.data, tr.nbytes), "me_read_trace")

@@ -102,6 +102,53 @@ static int stats_launch(SvtB200Ctx *c, uint64_t pic_id, int w, int h, uint8_t *y
     return SVTB200_OK;
 }
 
+/* ---- luma histograms of the 1/16 plane: one CTA per (region, slice of its rows), shared-memory bins ---- */
+struct HistArgs {
+    const uint8_t *p16; int32_t stride, ox, oy, w, h;
+    int32_t rw, rh, slices;
+    uint32_t *count;            /* [rw * rh][256], zeroed */
+    unsigned long long *sum;    /* [rw * rh], zeroed */
+};
+__device__ __forceinline__ void hist_region(const HistArgs &A, int ri, int *x0, int *y0, int *cw, int *ch) {
+    const int iw = ri / A.rh, ih = ri - iw * A.rh, regw = A.w / A.rw, regh = A.h / A.rh;
+    *x0 = iw * regw; *y0 = ih * regh;
+    *cw = regw + (iw == A.rw - 1 ? A.w - A.rw * regw : 0);
+    *ch = regh + (ih == A.rh - 1 ? A.h - A.rh * regh : 0);
+}
+__global__ void __launch_bounds__(256) hist_count_kernel(const HistArgs A) {
+    __shared__ uint32_t bins[256];
+    __shared__ unsigned long long ssum;
+    const int ri = blockIdx.x / A.slices, sl = blockIdx.x - ri * A.slices;
+    int x0, y0, cw, ch;
+    hist_region(A, ri, &x0, &y0, &cw, &ch);
+    bins[threadIdx.x] = 0;
+    if (threadIdx.x == 0) ssum = 0;
+    __syncthreads();
+    const int r0 = (int)((long long)ch * sl / A.slices), r1 = (int)((long long)ch * (sl + 1) / A.slices);
+    unsigned long long s = 0;
+    for (int i = threadIdx.x; i < (r1 - r0) * cw; i += 256) {
+        const int y = r0 + i / cw, x = i - (i / cw) * cw;
+        const uint32_t v = __ldg(A.p16 + (size_t)(A.oy + y0 + y) * A.stride + A.ox + x0 + x);
+        atomicAdd(&bins[v], 1u);
+        s += v;
+    }
+    atomicAdd(&ssum, s);
+    __syncthreads();
+    if (bins[threadIdx.x]) atomicAdd(&A.count[(size_t)ri * 256 + threadIdx.x], bins[threadIdx.x]);
+    if (threadIdx.x == 0 && ssum) atomicAdd(&A.sum[ri], ssum);
+}
+__global__ void hist_finish_kernel(const HistArgs A, uint32_t *hist, uint8_t *avg, unsigned long long *sum16) {
+    const int ri = blockIdx.x;
+    int x0, y0, cw, ch;
+    hist_region(A, ri, &x0, &y0, &cw, &ch);
+    hist[(size_t)ri * 256 + threadIdx.x] = (1u + A.count[(size_t)ri * 256 + threadIdx.x]) << 4;
+    if (threadIdx.x == 0) {
+        const unsigned long long area = (unsigned long long)cw * ch;
+        avg[ri] = (uint8_t)((A.sum[ri] + (area >> 1)) / area);
+        atomicAdd(sum16, A.sum[ri] << 4);
+    }
+}
+
 static int zz_launch(SvtB200Ctx *c, uint64_t cur_id, uint64_t prev_id, int w, int h, int th_shift, uint8_t *scores, uint32_t *sads) {
     if (!scores || w <= 0 || h <= 0 || th_shift < 0 || th_shift > 11) return SVTB200_EINVAL;
     auto ic = c->pics.find(cur_id), ip = c->pics.find(prev_id);
@@ -121,6 +168,40 @@ static int zz_launch(SvtB200Ctx *c, uint64_t cur_id, uint64_t prev_id, int w, in
 }
 
 extern "C" {
+
+int svtb200_luma_histogram_picture(SvtB200Ctx *c, uint64_t pic_id, int32_t rw, int32_t rh, uint32_t *hist, uint8_t *avg, uint64_t *sum16) {
+    if (!c || !hist || !avg || !sum16 || rw <= 0 || rh <= 0 || rw > 16 || rh > 16) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    auto it = c->pics.find(pic_id);
+    if (it == c->pics.end() || !it->second.pl[2].buf) { c->err = "luma_histogram: picture or its 1/16 plane not resident"; return SVTB200_ENOENT; }
+    const DevPlane &p = it->second.pl[2];
+    if (p.w < rw || p.h < rh) return SVTB200_EINVAL;
+    const int nr = rw * rh;
+    const size_t need = (size_t)nr * 256 * 4 * 2 + (size_t)nr * 8 + nr + 8 + 1024;
+    int rc = svtb200_grow(c, (void **)&c->scratch, &c->scratch_bytes, need);
+    if (rc) return rc;
+    uint8_t *q = c->scratch;
+    auto carve = [&](size_t b) { uint8_t *r = q; q += (b + 255) & ~(size_t)255; return r; };
+    HistArgs A;
+    A.p16 = p.buf; A.stride = p.stride; A.ox = p.ox; A.oy = p.oy; A.w = p.w; A.h = p.h; A.rw = rw; A.rh = rh; A.slices = 8;
+    A.count = (uint32_t *)carve((size_t)nr * 1024); A.sum = (unsigned long long *)carve((size_t)nr * 8);
+    uint32_t *d_hist = (uint32_t *)carve((size_t)nr * 1024);
+    unsigned long long *d_s16 = (unsigned long long *)carve(8);
+    uint8_t *d_avg = carve(nr);
+    SVTB200_CUDA_CHECK(c, cudaMemsetAsync(c->scratch, 0, (size_t)(q - c->scratch), c->stream));
+    svtb200_pic_acquire(c, it->second);
+    hist_count_kernel<<<nr * A.slices, 256, 0, c->stream>>>(A);
+    hist_finish_kernel<<<nr, 256, 0, c->stream>>>(A, d_hist, d_avg, d_s16);
+    svtb200_pic_release(c, it->second);
+    c->launches += 2;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(hist, d_hist, (size_t)nr * 1024, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(avg, d_avg, nr, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(sum16, d_s16, 8, cudaMemcpyDeviceToHost, c->stream));
+    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    return SVTB200_OK;
+}
 
 int svtb200_block_stats_picture_dev(SvtB200Ctx *c, uint64_t pic_id, int32_t w, int32_t h, uint8_t *y_mean, uint16_t *variance) {
     if (!c) return SVTB200_EINVAL;

@@ -98,3 +98,36 @@ def test_cuda_block_stats_match_oracle(w, h):
     eym, evar = _oracle_stats(st[1], w, h)
     assert (ym == eym).all() and (var == evar).all()
     assert var.max() > 0
+
+
+def _oracle_hist(st, rw, rh):
+    hist = np.zeros((rw, rh, 256), dtype=np.uint32)
+    avg = np.zeros((rw, rh), dtype=np.uint8)
+    s16 = C.c_uint64()
+    L = H.oracle()
+    L.svtb200_oracle_luma_histogram.argtypes = [C.POINTER(api.Plane), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    L.svtb200_oracle_luma_histogram(C.byref(st[2]), rw, rh, hist.ctypes.data, avg.ctypes.data, C.byref(s16))
+    return hist, avg, s16.value
+
+
+def test_oracle_histogram_properties():
+    """the restatement is pinned inside real encodes by the seam check (hist_bad 0 over 31 pictures); here its invariants"""
+    w, h = 456, 264
+    pl, st = _pair(w, h, 4, 2)
+    hist, avg, s16 = _oracle_hist(st[1], 4, 4)
+    six = pl[1]["sixteenth"][frames.SIXTEENTH_PAD:frames.SIXTEENTH_PAD + (h + 3) // 4, frames.SIXTEENTH_PAD:frames.SIXTEENTH_PAD + (w + 3) // 4]
+    assert int((hist >> 4).sum()) - 16 * 256 == six.size and (hist & 15).sum() == 0
+    assert s16 == int(six.astype(np.int64).sum()) << 4
+    assert abs(int(avg[0, 0]) - int(round(six[: six.shape[0] // 4, : six.shape[1] // 4].mean()))) <= 1
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,rw,rh", [(640, 384, 4, 4), (456, 264, 4, 4), (3840, 2160, 4, 4), (200, 136, 2, 3)])
+def test_cuda_histogram_matches_oracle(w, h, rw, rh):
+    pl, st = _pair(w, h, 6, 3)
+    ctx = api.Context(0)
+    ctx.picture_upload_luma(0, st[1][0])
+    hist, avg, s16 = ctx.luma_histogram_picture(0, rw, rh)
+    ctx.close()
+    eh, ea, es = _oracle_hist(st[1], rw, rh)
+    assert (hist == eh).all() and (avg == ea).all() and s16 == es
