@@ -161,43 +161,63 @@ struct LfPlaneMasks {
     int bw, rows /* block rows present */, px_rows /* sample rows present */, top;
 };
 
-/* all vertical edges crossing sample row 'row' (0..8*bw-1) of the tile; t points at tile sample (0,row) of the SB */
+/* lowest set bit of a non-zero word */
+__device__ __forceinline__ int lf_ctz(uint32_t v) {
+#ifdef SVTB200_CPU_EMU
+    return __builtin_ctz(v);
+#else
+    return __ffs((int)v) - 1;
+#endif
+}
+
+/* all vertical edges crossing sample row 'row' (0..8*bw-1) of the tile; t points at tile sample (0,row) of the SB.
+ * The row's bits of the four masks are extracted once; only block columns that carry an edge are visited. */
 __device__ static void lf_vertical_row(uint8_t *t, int row, const LfPlaneMasks &M, const SvtB200LfThresh *thr) {
     if (row >= M.px_rows) return;
-    const int r = row >> 3, pr = r & ~1, other = r ^ 1;
-    for (int c = 0; c < M.bw; c++) {
-        const int bit = r * M.bw + c;
+    const int r = row >> 3, pr = r & ~1, sh = r * M.bw, osh = (r ^ 1) * M.bw;
+    const uint32_t bwm = (1u << M.bw) - 1u;
+    const uint32_t l16 = (uint32_t)(M.l16 >> sh) & bwm, l8 = (uint32_t)(M.l8 >> sh) & bwm, l4 = (uint32_t)(M.l4 >> sh) & bwm;
+    const uint32_t i4 = (uint32_t)(M.i4v >> sh) & bwm, o16 = (uint32_t)(M.l16 >> osh) & bwm;
+    for (uint32_t any = l16 | l8 | l4 | i4; any; any &= any - 1) {
+        const int c = lf_ctz(any);
         uint8_t *s = t + c * 8;
-        const SvtB200LfThresh own = thr[M.lfl[bit]];
-        if (M.l16 >> bit & 1) {
+        const SvtB200LfThresh own = thr[M.lfl[sh + c]];
+        if (l16 >> c & 1) {
             /* a 16-wide edge present in both rows of a row pair takes the thresholds of the pair's first row */
-            const SvtB200LfThresh th = (M.l16 >> (other * M.bw + c) & 1) ? thr[M.lfl[pr * M.bw + c]] : own;
+            const SvtB200LfThresh th = (o16 >> c & 1) ? thr[M.lfl[pr * M.bw + c]] : own;
             lf_filter_across(s, 1, 16, th.mblim, th.lim, th.hev_thr);
         }
-        if (M.l8 >> bit & 1) lf_filter_across(s, 1, 8, own.mblim, own.lim, own.hev_thr);
-        if (M.l4 >> bit & 1) lf_filter_across(s, 1, 4, own.mblim, own.lim, own.hev_thr);
-        if (M.i4v >> bit & 1) lf_filter_across(s + 4, 1, 4, own.mblim, own.lim, own.hev_thr);
+        if (l8 >> c & 1) lf_filter_across(s, 1, 8, own.mblim, own.lim, own.hev_thr);
+        if (l4 >> c & 1) lf_filter_across(s, 1, 4, own.mblim, own.lim, own.hev_thr);
+        if (i4 >> c & 1) lf_filter_across(s + 4, 1, 4, own.mblim, own.lim, own.hev_thr);
     }
 }
 
-/* all horizontal edges crossing sample column 'col'; t points at tile sample (col,0) of the SB */
+/* all horizontal edges crossing sample column 'col'; t points at tile sample (col,0) of the SB.  The column's bits are
+ * gathered once (one bit per block row); only block rows that carry an edge are visited. */
 __device__ static void lf_horizontal_col(uint8_t *t, int col, int pitch, const LfPlaneMasks &M, const SvtB200LfThresh *thr) {
     const int c = col >> 3;
+    uint32_t a16 = 0, a8 = 0, a4 = 0, i4 = 0;
     for (int r = 0; r < M.rows; r++) {
         const int bit = r * M.bw + c;
+        a16 |= (uint32_t)(M.a16 >> bit & 1) << r; a8 |= (uint32_t)(M.a8 >> bit & 1) << r;
+        a4 |= (uint32_t)(M.a4 >> bit & 1) << r; i4 |= (uint32_t)(M.i4h >> bit & 1) << r;
+    }
+    for (uint32_t any = a16 | a8 | a4 | i4; any; any &= any - 1) {
+        const int r = lf_ctz(any), bit = r * M.bw + c;
         uint8_t *s = t + (r * 8) * pitch;
         const bool top = M.top && r == 0;
         const SvtB200LfThresh own = thr[M.lfl[bit]];
-        if (!top && (M.a16 >> bit & 1)) {
+        if (!top && (a16 >> r & 1)) {
             /* adjacent 16-wide edges are paired from the start of each run; a pair shares the first block's thresholds */
             int start = c;
             while (start > 0 && (M.a16 >> (r * M.bw + start - 1) & 1)) start--;
             const SvtB200LfThresh th = thr[M.lfl[r * M.bw + c - ((c - start) & 1)]];
             lf_filter_across(s, pitch, 16, th.mblim, th.lim, th.hev_thr);
         } else {
-            if (!top && (M.a8 >> bit & 1)) lf_filter_across(s, pitch, 8, own.mblim, own.lim, own.hev_thr);
-            else if (!top && (M.a4 >> bit & 1)) lf_filter_across(s, pitch, 4, own.mblim, own.lim, own.hev_thr);
-            if ((M.i4h >> bit & 1) && r * 8 + 4 < M.px_rows) lf_filter_across(s + 4 * pitch, pitch, 4, own.mblim, own.lim, own.hev_thr);
+            if (!top && (a8 >> r & 1)) lf_filter_across(s, pitch, 8, own.mblim, own.lim, own.hev_thr);
+            else if (!top && (a4 >> r & 1)) lf_filter_across(s, pitch, 4, own.mblim, own.lim, own.hev_thr);
+            if ((i4 >> r & 1) && r * 8 + 4 < M.px_rows) lf_filter_across(s + 4 * pitch, pitch, 4, own.mblim, own.lim, own.hev_thr);
         }
     }
 }

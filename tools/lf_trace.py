@@ -33,3 +33,11 @@ for rows, label in (([0], "row 0"), ([1, 2, 3], "rows 1-3"), (list(range(16, 20)
     nxt = t[rows][:, 6:56, 0]
     vals = [a[..., 1] - a[..., 0], a[..., 2] - a[..., 1], a[..., 3] - a[..., 2], nxt - a[..., 0], a[..., 4] - a[..., 0], a[..., 5] - a[..., 4], a[..., 6] - a[..., 5], a[..., 7] - a[..., 2]]
     print(label + ": " + "; ".join("%s %.0f" % (n, v.mean()) for n, v in zip(names, vals)) + "  [SM clocks, ~1.9 GHz]")
+# start of every row relative to the previous row's start, and where a row stands when the row below starts its first tile
+t0 = t[:, 0, 0].astype(np.float64)
+print("clock stamps are per SM: only durations inside a row are comparable; per-row total (first stamp of SB 0 -> S1 of the last SB):",
+      ["%.0f" % ((t[r, -1, 2] - t[r, 0, 0]) / 1.9e3) for r in (0, 1, 16, 33)], "us")
+for rows, label in (([1], "row 1"), ([16], "row 16")):
+    a = t[rows][0]
+    print(label, "first 6 steps, step time us:", ["%.1f" % ((a[c + 1, 0] - a[c, 0]) / 1.9e3) for c in range(6)],
+          " poll wait us:", ["%.1f" % ((a[c, 5] - a[c, 4]) / 1.9e3) for c in range(6)])
