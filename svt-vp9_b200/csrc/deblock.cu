@@ -27,19 +27,19 @@ static int lf_launch(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int ys
     A.P = *p; A.y = y; A.u = u; A.v = v; A.y_stride = ys; A.uv_stride = cs; A.lfm = lfm; A.lfm_stride = lfm_stride; A.thr = thr;
     A.sbs_w = (p->mi_cols + 7) >> 3; A.sbs_h = (p->mi_rows + 7) >> 3;
     if (A.sbs_w > 1023) return SVTB200_EINVAL;
-    const size_t n = (size_t)A.sbs_h; /* one progress word per super-block row */
+    const size_t n = (size_t)A.sbs_h; /* one progress word (in a 128-byte line of its own) per super-block row */
     LfScratch *S;
     { std::lock_guard<std::mutex> g(g_lf_mu); S = &g_lf[c]; }
     if (S->done_n < n) {
         if (S->done) cudaFree(S->done);
         if (!S->ticket && cudaMalloc((void **)&S->ticket, 4) != cudaSuccess) { cudaGetLastError(); return SVTB200_ENOMEM; }
-        if (cudaMalloc((void **)&S->done, n * 4) != cudaSuccess) { cudaGetLastError(); S->done = nullptr; S->done_n = 0; return SVTB200_ENOMEM; }
+        if (cudaMalloc((void **)&S->done, n * 4 * LF_FLAG_PAD) != cudaSuccess) { cudaGetLastError(); S->done = nullptr; S->done_n = 0; return SVTB200_ENOMEM; }
         S->done_n = n; S->gen = 0;
-        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->done, 0, n * 4, c->stream));
+        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->done, 0, n * 4 * LF_FLAG_PAD, c->stream));
     }
     if (++S->gen >= (1 << 20)) { /* the progress words carry the generation in their upper bits: restart well before it overflows */
         S->gen = 1;
-        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->done, 0, S->done_n * 4, c->stream));
+        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->done, 0, S->done_n * 4 * LF_FLAG_PAD, c->stream));
     }
     A.ticket = S->ticket; A.done = S->done; A.gen = S->gen; A.trace = g_lf_trace;
     SVTB200_CUDA_CHECK(c, cudaMemsetAsync(S->ticket, 0, 4, c->stream));

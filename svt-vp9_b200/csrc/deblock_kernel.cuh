@@ -27,6 +27,7 @@
 #define LF_HALF 128
 #define LF_YP 76 /* luma tile pitch (odd number of words: conflict-free column access) */
 #define LF_CP 44 /* chroma tile pitch */
+#define LF_FLAG_PAD 32 /* progress words are 128 bytes apart: rows poll and publish without sharing a line */
 
 struct LfKernelArgs {
     SvtB200LfParams P;
@@ -286,7 +287,7 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
     SvtB200LfMask *msk = (SvtB200LfMask *)dyn;
     uint8_t (*lfl_uv)[16] = (uint8_t (*)[16])(dyn + (size_t)A.sbs_w * sizeof(SvtB200LfMask));
     __shared__ SvtB200LfThresh thr[64];
-    __shared__ int row_s;
+    __shared__ int row_s, seen_s;
     const int t = threadIdx.x;
     const bool mover = t >= LF_HALF;
     const int mt = t - LF_HALF;
@@ -301,19 +302,75 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
     const bool vy = (((uintptr_t)A.y | (uintptr_t)A.y_stride) & 7) == 0;
     const bool vc0 = !A.P.y_only && ((((uintptr_t)A.u | (uintptr_t)A.v | (uintptr_t)A.uv_stride) & 7) == 0);
     const bool chroma = !A.P.y_only;
-    const int32_t *above = r > 0 ? A.done + (r - 1) : nullptr;
-    int32_t *mine = A.done + r;
+    const int32_t *above = r > 0 ? A.done + (size_t)(r - 1) * LF_FLAG_PAD : nullptr;
+    int32_t *mine = A.done + (size_t)r * LF_FLAG_PAD;
 
-    /* the row above must have finished 'need' super-blocks (their right 8 columns included) */
+    /* the row above must have finished 'need' super-blocks (their right 8 columns included).  One thread polls: it reads the
+     * progress word before its own stores of the step (a fence behind outstanding stores is expensive), keeps the count it saw
+     * and does not look again while that covers the request; the other movers are ordered behind it by their barrier. */
+    int seen = above ? 0 : 1 << 20;
     auto wait_above = [&](int need) {
-        if (!above) return;
         if (need > A.sbs_w) need = A.sbs_w;
+        if (seen >= need) return;
         for (;;) {
             const int f = lf_flag_load(above);
-            if ((f >> 10) == A.gen && (f & 1023) >= need) break;
+            if ((f >> 10) == A.gen && (f & 1023) >= need) { seen = f & 1023; break; }
             lf_sleep();
         }
         lf_fence();
+    };
+    /* the own samples of a whole-width tile (any height) as two steps: the loads are issued half a step before the buffer they go to is free */
+    auto own_fast = [&](int c) {
+        const LfSbGeom g = lf_geom(A, c);
+        return g.cols == 8 && c > 0 && vy && (!chroma || vc0);
+    };
+    auto own_issue = [&](int c, uint2 (&v)[6], int tid) {
+        const uint8_t *gy = A.y + (size_t)y0 * A.y_stride + c * 64;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = tid + 128 * k;
+            if ((i >> 3) < lh) v[k] = lf_ldcg8(gy + (ptrdiff_t)(i >> 3) * A.y_stride + (i & 7) * 8);
+        }
+        if (chroma && (tid >> 2) < ch) {
+            const uint8_t *gu = A.u + (size_t)cy0 * A.uv_stride + c * 32, *gv = A.v + (size_t)cy0 * A.uv_stride + c * 32;
+            v[4] = lf_ldcg8(gu + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
+            v[5] = lf_ldcg8(gv + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
+        }
+    };
+    auto own_commit = [&](int b, const uint2 (&v)[6], int tid) {
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int i = tid + 128 * k;
+            if ((i >> 3) >= lh) continue;
+            uint32_t *d = (uint32_t *)(ty[b] + ((i >> 3) + 8) * LF_YP + (i & 7) * 8 + 8);
+            d[0] = v[k].x; d[1] = v[k].y;
+        }
+        if (chroma && (tid >> 2) < ch) {
+            uint32_t *d = (uint32_t *)(tu[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
+            d[0] = v[4].x; d[1] = v[4].y;
+            d = (uint32_t *)(tv[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
+            d[0] = v[5].x; d[1] = v[5].y;
+        }
+    };
+    /* the 8 rows above a whole-width tile with the top-left corner (none for the first tile), as two steps like the own
+     * samples: luma 8 rows x 9 words of 8 bytes, chroma 2 planes x 8 rows x 5 */
+    auto strip_fast = [&](int c) {
+        const LfSbGeom g = lf_geom(A, c);
+        return lpy && g.cols == 8 && vy && (!chroma || vc0);
+    };
+    auto strip_issue = [&](int c, uint2 &a, uint2 &q, int tid) {
+        const int ty_y = tid / 9, ty_x = tid - ty_y * 9;
+        const int tc_p = tid >> 6, tc_i = tid & 63, tc_y = tc_i / 5, tc_x = tc_i - tc_y * 5;
+        a.x = a.y = q.x = q.y = 0;
+        if (tid < 72 && (ty_x || c)) a = lf_ldcg8(A.y + (size_t)y0 * A.y_stride + c * 64 + (ptrdiff_t)(ty_y - 8) * A.y_stride + (ty_x - 1) * 8);
+        if (chroma && tc_i < 40 && (tc_x || c))
+            q = lf_ldcg8((tc_p ? A.v : A.u) + (size_t)cy0 * A.uv_stride + c * 32 + (ptrdiff_t)(tc_y - 8) * A.uv_stride + (tc_x - 1) * 8);
+    };
+    auto strip_commit = [&](int c, int b, const uint2 &a, const uint2 &q, int tid) {
+        const int ty_y = tid / 9, ty_x = tid - ty_y * 9;
+        const int tc_p = tid >> 6, tc_i = tid & 63, tc_y = tc_i / 5, tc_x = tc_i - tc_y * 5;
+        if (tid < 72 && (ty_x || c)) { uint32_t *d = (uint32_t *)(ty[b] + ty_y * LF_YP + ty_x * 8); d[0] = a.x; d[1] = a.y; }
+        if (chroma && tc_i < 40 && (tc_x || c)) { uint32_t *d = (uint32_t *)((tc_p ? tv[b] : tu[b]) + tc_y * LF_CP + tc_x * 8); d[0] = q.x; d[1] = q.y; }
     };
     /* fetch into buffer b the samples of tile c nobody has modified yet (its own), or (strip) the 8 rows above it with the
      * top-left corner, final once the row above has published c + 1; the strip left of the tile comes from the previous
@@ -324,38 +381,16 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
         const bool vc = vc0 && (g.cw & 7) == 0;
         uint8_t *gy = A.y + (size_t)y0 * A.y_stride + c * 64;
         uint8_t *gu = chroma ? A.u + (size_t)cy0 * A.uv_stride + c * 32 : nullptr, *gv = chroma ? A.v + (size_t)cy0 * A.uv_stride + c * 32 : nullptr;
-        if (nthr == LF_HALF && g.cols == 8 && rows == 8 && lpx && vy && (vc || !chroma)) {
+        if (nthr == LF_HALF && g.cols == 8 && (lpx || strip) && vy && (vc || !chroma)) {
             /* whole interior tile, 128 threads: independent 8-byte loads issued together, then stored */
             if (!strip) {
                 uint2 v[6];
-#pragma unroll
-                for (int k = 0; k < 4; k++) { const int i = tid + 128 * k; v[k] = lf_ldcg8(gy + (ptrdiff_t)(i >> 3) * A.y_stride + (i & 7) * 8); }
-                if (chroma) {
-                    v[4] = lf_ldcg8(gu + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
-                    v[5] = lf_ldcg8(gv + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
-                }
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int i = tid + 128 * k;
-                    uint32_t *d = (uint32_t *)(ty[b] + ((i >> 3) + 8) * LF_YP + (i & 7) * 8 + 8);
-                    d[0] = v[k].x; d[1] = v[k].y;
-                }
-                if (chroma) {
-                    uint32_t *d = (uint32_t *)(tu[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
-                    d[0] = v[4].x; d[1] = v[4].y;
-                    d = (uint32_t *)(tv[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
-                    d[0] = v[5].x; d[1] = v[5].y;
-                }
+                own_issue(c, v, tid);
+                own_commit(b, v, tid);
             } else if (lpy) {
-                /* luma: 8 rows x 9 words-of-8; chroma: 2 planes x 8 rows x 5 */
-                const int ty_y = tid / 9, ty_x = tid - ty_y * 9;
-                const int tc_p = tid >> 6, tc_i = tid & 63, tc_y = tc_i / 5, tc_x = tc_i - tc_y * 5;
                 uint2 a, q;
-                a.x = a.y = q.x = q.y = 0;
-                if (tid < 72) a = lf_ldcg8(gy + (ptrdiff_t)(ty_y - 8) * A.y_stride + (ty_x - 1) * 8);
-                if (chroma && tc_i < 40) q = lf_ldcg8((tc_p ? gv : gu) + (ptrdiff_t)(tc_y - 8) * A.uv_stride + (tc_x - 1) * 8);
-                if (tid < 72) { uint32_t *d = (uint32_t *)(ty[b] + ty_y * LF_YP + ty_x * 8); d[0] = a.x; d[1] = a.y; }
-                if (chroma && tc_i < 40) { uint32_t *d = (uint32_t *)((tc_p ? tv[b] : tu[b]) + tc_y * LF_CP + tc_x * 8); d[0] = q.x; d[1] = q.y; }
+                strip_issue(c, a, q, tid);
+                strip_commit(c, b, a, q, tid);
             }
             return;
         }
@@ -371,35 +406,6 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
                 lf_tile_load<LF_CP>(tu[b], gu, A.uv_stride, -lpx, g.cw, -lpy, 0, vc, tid, nthr);
                 lf_tile_load<LF_CP>(tv[b], gv, A.uv_stride, -lpx, g.cw, -lpy, 0, vc, tid, nthr);
             }
-        }
-    };
-    /* the own samples of an interior tile as two steps: the loads are issued half a step before the buffer they go to is free */
-    auto own_fast = [&](int c) {
-        const LfSbGeom g = lf_geom(A, c);
-        return g.cols == 8 && rows == 8 && c > 0 && vy && (!chroma || vc0);
-    };
-    auto own_issue = [&](int c, uint2 (&v)[6], int tid) {
-        const uint8_t *gy = A.y + (size_t)y0 * A.y_stride + c * 64;
-#pragma unroll
-        for (int k = 0; k < 4; k++) { const int i = tid + 128 * k; v[k] = lf_ldcg8(gy + (ptrdiff_t)(i >> 3) * A.y_stride + (i & 7) * 8); }
-        if (chroma) {
-            const uint8_t *gu = A.u + (size_t)cy0 * A.uv_stride + c * 32, *gv = A.v + (size_t)cy0 * A.uv_stride + c * 32;
-            v[4] = lf_ldcg8(gu + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
-            v[5] = lf_ldcg8(gv + (ptrdiff_t)(tid >> 2) * A.uv_stride + (tid & 3) * 8);
-        }
-    };
-    auto own_commit = [&](int b, const uint2 (&v)[6], int tid) {
-#pragma unroll
-        for (int k = 0; k < 4; k++) {
-            const int i = tid + 128 * k;
-            uint32_t *d = (uint32_t *)(ty[b] + ((i >> 3) + 8) * LF_YP + (i & 7) * 8 + 8);
-            d[0] = v[k].x; d[1] = v[k].y;
-        }
-        if (chroma) {
-            uint32_t *d = (uint32_t *)(tu[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
-            d[0] = v[4].x; d[1] = v[4].y;
-            d = (uint32_t *)(tv[b] + ((tid >> 2) + 8) * LF_CP + (tid & 3) * 8 + 8);
-            d[0] = v[5].x; d[1] = v[5].y;
         }
     };
     /* write back a whole-width tile c-1 but for its right 8 columns, and the strip above it (the common case with
@@ -438,6 +444,7 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
     };
 
     /* ---- prologue: tile 0 */
+    if (t == 0) seen_s = above ? 0 : 1 << 20;
     for (int c = t; c < A.sbs_w; c += LF_THREADS) { /* every mask of the row, border-adjusted, once */
         msk[c] = A.lfm[c + r * A.lfm_stride];
         lf_adjust_mask(A.P.mi_rows, A.P.mi_cols, mi_row, c * 8, &msk[c]);
@@ -484,16 +491,23 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
                 lf_vertical_row(tc + (q + 8) * LF_CP + 8, q, MC, thr);
             }
         } else {
-            /* ---- movers, first half of the step: issue the loads of tile c+1's own samples (they land in registers); write
-             * tile c-1 back but for its right 8 columns (still the left context of tile c); then the strip above tile c
-             * (only the horizontal edges need it), as late as possible so that the row above has time to publish SB c */
+            /* ---- movers, first half of the step: issue the loads of tile c+1's own samples and - once the row above is known
+             * to have published SB c - of the strip above tile c (only the horizontal edges need it); both land in registers
+             * while tile c-1 is written back but for its right 8 columns (still the left context of tile c) */
             if (c + 1 < A.sbs_w && own_fast(c + 1)) { own_issue(c + 1, pre, mt); pre_valid = true; }
-            if (c > 0) put_body(c - 1, oth, mt, LF_HALF);
+            const bool sf = strip_fast(c);
+            const int need = c + 1 < A.sbs_w ? c + 1 : A.sbs_w;
+            uint2 sa, sq;
             if (tr && mt == 0) tr[4] = lf_clock();
-            if (mt == 0) wait_above(c + 1);
+            if (seen_s < need) { /* not known yet from the look at the end of the previous step: wait for it */
+                if (mt == 0) wait_above(need);
+                lf_sync_movers();
+            }
             if (tr && mt == 0) tr[5] = lf_clock();
-            lf_sync_movers();
-            fetch(c, cur, true, mt, LF_HALF);
+            if (sf) strip_issue(c, sa, sq, mt);
+            if (c > 0) put_body(c - 1, oth, mt, LF_HALF);
+            if (sf) strip_commit(c, cur, sa, sq, mt);
+            else fetch(c, cur, true, mt, LF_HALF);
             if (tr && mt == 0) tr[6] = lf_clock();
         }
         if (tr && t == 0) tr[1] = lf_clock();
@@ -509,14 +523,21 @@ __global__ void __launch_bounds__(LF_THREADS) lf_row_kernel(const __grid_constan
              * edges do not reach it): with it tile c-1 is complete in memory -> fence, publish at once; then tile c+1's own
              * samples go from the registers into the freed buffer */
             if (c > 0) put_left(c, cur, mt, LF_HALF);
-            lf_fence();
-            lf_sync_movers();
-            if (mt == 0 && c > 0) lf_flag_store(mine, (A.gen << 10) | c); /* SBs 0..c-1 are final in memory */
-            if (tr && mt == 0) tr[7] = lf_clock();
+            lf_sync_movers(); /* every mover's stores of SBs 0..c-1 are ordered before the one fence below */
             if (c + 1 < A.sbs_w) {
                 if (pre_valid) own_commit(oth, pre, mt);
                 else fetch(c + 1, oth, false, mt, LF_HALF);
             }
+            if (mt == 0) {
+                /* one fence serves both directions: behind the look at the row above (does it already cover the next step?
+                 * then that step fetches its strip at once), and in front of this row's own progress word */
+                const int f = above ? lf_flag_load(above) : 0;
+                if (above || c > 0) lf_fence();
+                if (c > 0) lf_flag_store(mine, (A.gen << 10) | c); /* SBs 0..c-1 are final in memory */
+                if (above && (f >> 10) == A.gen && (f & 1023) > seen) seen = f & 1023;
+                seen_s = seen;
+            }
+            if (tr && mt == 0) tr[7] = lf_clock();
         }
     }
     __syncthreads();

@@ -10,7 +10,7 @@ extern "C" int lf_emu_run(const SvtB200LfParams *p, uint8_t *y, int ys, uint8_t 
     memset(&A, 0, sizeof(A));
     A.P = *p; A.y = y; A.u = u; A.v = v; A.y_stride = ys; A.uv_stride = cs; A.lfm = lfm; A.lfm_stride = lfm_stride; A.thr = thr;
     A.sbs_w = (p->mi_cols + 7) >> 3; A.sbs_h = (p->mi_rows + 7) >> 3;
-    std::vector<int32_t> done((size_t)A.sbs_h, 0);
+    std::vector<int32_t> done((size_t)A.sbs_h * LF_FLAG_PAD, 0);
     int32_t ticket = 0;
     A.ticket = &ticket; A.done = done.data(); A.gen = 1;
     emu_launch(dim3(A.sbs_h), dim3(LF_THREADS), (size_t)A.sbs_w * (sizeof(SvtB200LfMask) + 16), [&] { lf_row_kernel(A); });

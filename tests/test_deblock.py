@@ -30,9 +30,10 @@ def test_emulated_kernel_matches_reference_dump(path):
     assert (y == p.ey).all() and (u == p.eu).all() and (v == p.ev).all()
 
 
-def test_emulated_kernel_matches_oracle_ragged():
+@pytest.mark.parametrize("w,h", [(200, 136), (264, 120), (136, 48)])
+def test_emulated_kernel_matches_oracle_ragged(w, h):
     rng = np.random.default_rng(3)
-    P, y, u, v, lfm, stride = H.synthetic_lf_case(rng, 200, 136, 20)  # 25 x 17 blocks: ragged right / bottom, odd rows
+    P, y, u, v, lfm, stride = H.synthetic_lf_case(rng, w, h, 20)  # e.g. 25 x 17 blocks: ragged right / bottom, odd rows
     thr = H.lf_thresholds()
     a = H.oracle_deblock(P, y, u, v, lfm, stride, thr)
     b = H.emu_deblock(P, y, u, v, lfm, stride, thr)
