@@ -22,7 +22,8 @@
  *   around the seams (same library): svtb200_picture_upload_luma (padding + 1/4, 1/16 decimation of the picture-analysis
  *       front end), svtb200_zz_sad_picture (compute_zz_sad), svtb200_block_stats_picture
  *       (compute_block_mean_compute_variance), svtb200_build_masks (eb_vp9_build_mask_frame), svtb200_pick_filter_level
- *       (eb_vp9_pick_filter_level), svtb200_pad_plane_dev (eb_vp9_generate_padding); each cites its reference lines below.
+ *       (eb_vp9_pick_filter_level), svtb200_pad_plane_dev (eb_vp9_generate_padding), svtb200_inter_predict_batch (inter_predictor),
+ *       svtb200_full_distortion_batch_dev (full_distortion_kernel32bit); each cites its reference lines below.
  *
  * "Host" entry points take HOST pointers (pinned or pageable) and perform the host<->device copies
  * themselves; the "_dev" twins take device pointers already resident in HBM.
@@ -358,6 +359,40 @@ int svtb200_deblock_picture_dev(SvtB200Ctx *ctx, const SvtB200LfParams *p, uint8
                                 int32_t y_stride, uint8_t *u_dev, uint8_t *v_dev, int32_t uv_stride,
                                 const SvtB200LfMask *lfm_dev, int32_t lfm_stride,
                                 const SvtB200LfThresh *thr_dev);
+
+/* =============================================================================================
+ * Next to S3: prediction of the encode pass and the full-loop distortion (the calls either side of every transform call)
+ * ============================================================================================= */
+
+/* One inter_predictor() call (Source/Lib/VPX/vp9_reconinter.h:23) as build_inter_predictors() makes it
+ * (Source/Lib/VPX/vp9_reconinter.c:102-250): the regular 8-tap kernel eb_vp9_filter_kernels[0] (:105, switchable filters are
+ * off in the reference), unscaled (xs = ys = 16), dispatched on (subpel_x != 0, subpel_y != 0) like scale_factors::predict
+ * (Source/Lib/VPX/vp9_scale.c:78-128): copy / eb_vp9_convolve8_horiz / _vert / eb_vp9_convolve8 (Source/Lib/VPX/vpx_convolve.c:101-180);
+ * a compound block (two references) is the second predictor averaged into the first (eb_vp9_convolve8_avg*, :170; eb_vp9_convolve_avg_c :200).
+ * All pointers are DEVICE pointers.  ref[i] points at sample (0,0) of the reference plane inside its padding; (x[i], y[i]) is
+ * the integer position of the block's top-left sample in that plane = block origin + (mv >> 4), which may lie in the padding
+ * (the 8-tap filter reads 3 samples before and 4 after, exactly the samples the reference functions read). */
+typedef struct SvtB200PredBlock {
+    const uint8_t *ref[2];
+    uint8_t       *dst;
+    int32_t ref_stride[2];
+    int32_t x[2], y[2];
+    int32_t dst_stride;
+    uint8_t subpel_x[2], subpel_y[2]; /* mv & 15, in 1/16 sample */
+    uint8_t w, h;                     /* 2 .. 64 */
+    uint8_t compound;                 /* 0: ref[0] only; 1: ref[1] averaged in */
+    uint8_t reserved;
+} SvtB200PredBlock;
+/* blocks: HOST array of n descriptors (copied to the device by the call); destinations of one batch must not overlap. */
+int svtb200_inter_predict_batch(SvtB200Ctx *ctx, const SvtB200PredBlock *blocks, int n);
+
+/* full_distortion_intrinsic_func_ptr_array[..][eob != 0][0][..] (Source/Lib/Codec/EbPictureOperators.h:240, call site
+ * Source/Lib/Codec/EbEncDecProcess.c:723): per transform block k of n (N x N coefficients each, block-major as svtb200_txq_batch
+ * writes them) dist[2k] = sum (coeff - recon_coeff)^2, dist[2k+1] = sum coeff^2; with eob[k] == 0 both are sum coeff^2
+ * (full_distortion_kernel32bit / _eob_zero32bit, Source/Lib/C_DEFAULT/EbPictureOperators_C.c:289,314; sums kept in 32 bits like there).
+ * Device pointers. */
+int svtb200_full_distortion_batch_dev(SvtB200Ctx *ctx, int tx_size, int n, const int16_t *coeff_dev, const int16_t *recon_coeff_dev,
+                                      const uint16_t *eob_dev, uint64_t *dist_dev);
 
 #ifdef __cplusplus
 }

@@ -34,6 +34,10 @@ void svtb200_oracle_block_stats_picture(const SvtB200Plane *full, int w, int h, 
 
 void svtb200_oracle_luma_histogram(const SvtB200Plane *p16, int rw, int rh, uint32_t *hist, uint8_t *avg, uint64_t *sum16);
 
+/* prediction of the encode pass (host pointers in the descriptors) and full-loop distortion: pred_port.c */
+void svtb200_oracle_inter_predict(const SvtB200PredBlock *blocks, int n);
+void svtb200_oracle_full_distortion(int tx_size, int n, const int16_t *coeff, const int16_t *recon_coeff, const uint16_t *eob, uint64_t *dist);
+
 #ifdef __cplusplus
 }
 #endif

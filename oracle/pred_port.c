@@ -1,0 +1,92 @@
+/* pred_port.c -- TEST INFRASTRUCTURE ONLY (CPU oracle; never linked into or called by the product library).
+ *
+ * Restatement of the prediction step of the reference's encode pass and of its full-loop distortion:
+ *   inter_predictor()                 Source/Lib/VPX/vp9_reconinter.h:23   (dispatch on subpel_x != 0 / subpel_y != 0)
+ *   scale_factors::predict, unscaled  Source/Lib/VPX/vp9_scale.c:78-83,127-128
+ *   convolve_horiz / convolve_vert    Source/Lib/VPX/vpx_convolve.c:20-38, 60-78
+ *   eb_vp9_convolve8_c (two passes through an 8-bit intermediate of h + 7 rows)   vpx_convolve.c:133-168
+ *   eb_vp9_convolve_copy_c / eb_vp9_convolve_avg_c / *_avg_* (second reference)   vpx_convolve.c:170-215
+ *   sub_pel_filters_8 (the only kernel build_inter_predictors uses, vp9_reconinter.c:105)   Source/Lib/VPX/vp9_filter.c:32
+ *   full_distortion_kernel32bit / full_distortion_kernel_eob_zero32bit   Source/Lib/C_DEFAULT/EbPictureOperators_C.c:289, 314
+ * Pinned against those reference functions (C and AVX2 flavours) through oracle/_ref (tests/test_pred.py).
+ */
+#include "oracle.h"
+#include <string.h>
+
+/* the normative VP9 regular 8-tap filter, 16 phases */
+static const int8_t k_regular[16][8] = {
+    {0, 0, 0, 127, 0, 0, 0, 0} /* phase 0 is never applied (its centre tap is 128: a copy) */,
+    {0, 1, -5, 126, 8, -3, 1, 0},    {-1, 3, -10, 122, 18, -6, 2, 0},  {-1, 4, -13, 118, 27, -9, 3, -1},
+    {-1, 4, -16, 112, 37, -11, 4, -1}, {-1, 5, -18, 105, 48, -14, 4, -1}, {-1, 5, -19, 97, 58, -16, 5, -1},
+    {-1, 6, -19, 88, 68, -18, 5, -1},  {-1, 6, -19, 78, 78, -19, 6, -1},  {-1, 5, -18, 68, 88, -19, 6, -1},
+    {-1, 5, -16, 58, 97, -19, 5, -1},  {-1, 4, -14, 48, 105, -18, 5, -1}, {-1, 4, -11, 37, 112, -16, 4, -1},
+    {-1, 3, -9, 27, 118, -13, 4, -1},  {0, 2, -6, 18, 122, -10, 3, -1},   {0, 1, -3, 8, 126, -5, 1, 0}};
+
+static uint8_t clip8(int v) { return (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); }
+
+/* one reference of one block into out (pitch 64) */
+static void predict_one(const uint8_t *src, int stride, int sx, int sy, int w, int h, uint8_t out[64 * 64]) {
+    uint8_t tmp[(64 + 7) * 64];
+    if (!sx && !sy) { /* vpx_convolve.c:182 */
+        for (int r = 0; r < h; r++) memcpy(out + r * 64, src + (ptrdiff_t)r * stride, (size_t)w);
+        return;
+    }
+    if (sx && !sy) { /* horizontal only: h rows (vpx_convolve.c:101) */
+        for (int r = 0; r < h; r++)
+            for (int c = 0; c < w; c++) {
+                int sum = 0;
+                for (int k = 0; k < 8; k++) sum += src[(ptrdiff_t)r * stride + c + k - 3] * k_regular[sx][k];
+                out[r * 64 + c] = clip8((sum + 64) >> 7);
+            }
+        return;
+    }
+    if (!sx) { /* vertical only (vpx_convolve.c:117) */
+        for (int r = 0; r < h; r++)
+            for (int c = 0; c < w; c++) {
+                int sum = 0;
+                for (int k = 0; k < 8; k++) sum += src[(ptrdiff_t)(r + k - 3) * stride + c] * k_regular[sy][k];
+                out[r * 64 + c] = clip8((sum + 64) >> 7);
+            }
+        return;
+    }
+    /* both: rows -3 .. h+3 horizontally into the intermediate, rounded and clipped to 8 bits, then vertically (vpx_convolve.c:133) */
+    for (int r = 0; r < h + 7; r++)
+        for (int c = 0; c < w; c++) {
+            int sum = 0;
+            for (int k = 0; k < 8; k++) sum += src[(ptrdiff_t)(r - 3) * stride + c + k - 3] * k_regular[sx][k];
+            tmp[r * 64 + c] = clip8((sum + 64) >> 7);
+        }
+    for (int r = 0; r < h; r++)
+        for (int c = 0; c < w; c++) {
+            int sum = 0;
+            for (int k = 0; k < 8; k++) sum += tmp[(r + k) * 64 + c] * k_regular[sy][k];
+            out[r * 64 + c] = clip8((sum + 64) >> 7);
+        }
+}
+
+/* Same descriptor as the product's, with HOST pointers. */
+void svtb200_oracle_inter_predict(const SvtB200PredBlock *b, int n) {
+    for (int i = 0; i < n; i++, b++) {
+        uint8_t p0[64 * 64], p1[64 * 64];
+        predict_one(b->ref[0] + (ptrdiff_t)b->y[0] * b->ref_stride[0] + b->x[0], b->ref_stride[0], b->subpel_x[0], b->subpel_y[0], b->w, b->h, p0);
+        if (b->compound)
+            predict_one(b->ref[1] + (ptrdiff_t)b->y[1] * b->ref_stride[1] + b->x[1], b->ref_stride[1], b->subpel_x[1], b->subpel_y[1], b->w, b->h, p1);
+        for (int r = 0; r < b->h; r++)
+            for (int c = 0; c < b->w; c++)
+                b->dst[(ptrdiff_t)r * b->dst_stride + c] = b->compound ? (uint8_t)((p0[r * 64 + c] + p1[r * 64 + c] + 1) >> 1) : p0[r * 64 + c];
+    }
+}
+
+void svtb200_oracle_full_distortion(int tx_size, int n, const int16_t *coeff, const int16_t *recon_coeff, const uint16_t *eob, uint64_t *dist) {
+    const int nn = (4 << tx_size) * (4 << tx_size);
+    for (int k = 0; k < n; k++) {
+        uint32_t res = 0, pred = 0; /* 32-bit sums, EbPictureOperators_C.c:293-294 */
+        for (int i = 0; i < nn; i++) {
+            const int32_t c = coeff[(size_t)k * nn + i], d = (int16_t)(c - recon_coeff[(size_t)k * nn + i]); /* sq_r16to32 takes an int16_t (:264) */
+            res += (uint32_t)(d * d);
+            pred += (uint32_t)(c * c);
+        }
+        dist[2 * k] = eob[k] ? res : pred;
+        dist[2 * k + 1] = pred;
+    }
+}

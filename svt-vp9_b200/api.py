@@ -77,6 +77,13 @@ class LfParams(C.Structure):
                 ("y_only", C.c_int32), ("filter_level", C.c_int32)]
 
 
+class PredBlock(C.Structure):
+    """SvtB200PredBlock: one inter_predictor() call (device pointers for the product, host pointers for the oracle)."""
+    _fields_ = [("ref", C.c_void_p * 2), ("dst", C.c_void_p), ("ref_stride", C.c_int32 * 2), ("x", C.c_int32 * 2), ("y", C.c_int32 * 2),
+                ("dst_stride", C.c_int32), ("subpel_x", C.c_uint8 * 2), ("subpel_y", C.c_uint8 * 2), ("w", C.c_uint8), ("h", C.c_uint8),
+                ("compound", C.c_uint8), ("reserved", C.c_uint8)]
+
+
 def plane_of(arr, origin_x, origin_y, width, height):
     """Describe a padded 2-D uint8 numpy array (C-contiguous) as an SvtB200Plane."""
     assert arr.dtype == np.uint8 and arr.flags["C_CONTIGUOUS"] and arr.ndim == 2
@@ -132,6 +139,8 @@ def lib():
         L.svtb200_zz_sad_picture_dev.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.svtb200_me_enable_trace.argtypes = [C.c_void_p, C.c_int]
         L.svtb200_me_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
+        L.svtb200_inter_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.svtb200_full_distortion_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
 
@@ -366,3 +375,31 @@ def _ctx_deblock(self, params, y, u, v, lfm, lfm_stride, thr):
 
 
 Context.deblock = _ctx_deblock
+
+
+# ---- next to S3: prediction of the encode pass, full-loop distortion -------------------------------------------------
+def _ctx_inter_predict(self, blocks):
+    """blocks: ctypes array of PredBlock with DEVICE pointers; asynchronous on the current compute queue."""
+    self.check(self.L.svtb200_inter_predict_batch(self.h, C.addressof(blocks), len(blocks)), "inter_predict_batch")
+
+
+def _ctx_full_distortion(self, tx_size, coeff, recon_coeff, eob):
+    """coeff / recon_coeff: (n, N*N) int16 host arrays, eob: (n,) uint16 -> (n, 2) uint64 [residual, prediction] distortion."""
+    L = self.L
+    coeff, recon_coeff, eob = (np.ascontiguousarray(a) for a in (coeff, recon_coeff, eob))
+    n = coeff.shape[0]
+    out = np.zeros((n, 2), dtype=np.uint64)
+    d = [L.svtb200_dev_alloc(self.h, max(a.nbytes, 8)) for a in (coeff, recon_coeff, eob, out)]
+    try:
+        for p, a in zip(d[:3], (coeff, recon_coeff, eob)):
+            self.check(L.svtb200_memcpy_h2d(self.h, p, a.ctypes.data, a.nbytes), "memcpy_h2d")
+        self.check(L.svtb200_full_distortion_batch_dev(self.h, tx_size, n, d[0], d[1], d[2], d[3]), "full_distortion_batch_dev")
+        self.check(L.svtb200_memcpy_d2h(self.h, out.ctypes.data, d[3], out.nbytes), "memcpy_d2h")
+    finally:
+        for p in d:
+            L.svtb200_dev_free(self.h, p)
+    return out
+
+
+Context.inter_predict = _ctx_inter_predict
+Context.full_distortion = _ctx_full_distortion

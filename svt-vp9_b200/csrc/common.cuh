@@ -51,6 +51,8 @@ struct SvtB200Ctx {
     ScanTable scans[4][4];
     /* generic device scratch for the host-pointer entry points */
     uint8_t *scratch = nullptr; size_t scratch_bytes = 0;
+    /* prediction descriptors of the batch in flight (pred.cu); pred_read: the kernel that reads them has finished */
+    void *pred_desc = nullptr; size_t pred_desc_bytes = 0; cudaEvent_t pred_read = nullptr;
 };
 
 #define SVTB200_CUDA_CHECK(ctx, call)                                                                 \
