@@ -385,6 +385,8 @@ typedef struct SvtB200PredBlock {
 } SvtB200PredBlock;
 /* blocks: HOST array of n descriptors (copied to the device by the call); destinations of one batch must not overlap. */
 int svtb200_inter_predict_batch(SvtB200Ctx *ctx, const SvtB200PredBlock *blocks, int n);
+/* the same with the descriptors already on the device (unchecked) */
+int svtb200_inter_predict_batch_dev(SvtB200Ctx *ctx, const SvtB200PredBlock *blocks_dev, int n);
 
 /* full_distortion_intrinsic_func_ptr_array[..][eob != 0][0][..] (Source/Lib/Codec/EbPictureOperators.h:240, call site
  * Source/Lib/Codec/EbEncDecProcess.c:723): per transform block k of n (N x N coefficients each, block-major as svtb200_txq_batch

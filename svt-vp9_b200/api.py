@@ -140,6 +140,7 @@ def lib():
         L.svtb200_me_enable_trace.argtypes = [C.c_void_p, C.c_int]
         L.svtb200_me_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.svtb200_inter_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.svtb200_inter_predict_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.svtb200_full_distortion_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib

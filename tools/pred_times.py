@@ -41,5 +41,13 @@ for name, sx, sy, comp in (("copy", 0, 0, 0), ("horizontal", 6, 0, 0), ("vertica
     for _ in range(10): ctx.inter_predict(arr)
     e1.record(stream); ctx.sync()
     t = 100.0 * e0.elapsed_time(e1)
+    nb = C.sizeof(arr)
+    d_arr = L.svtb200_dev_alloc(h, nb); L.svtb200_memcpy_h2d(h, d_arr, C.addressof(arr), nb)
+    for _ in range(3): L.svtb200_inter_predict_batch_dev(h, d_arr, len(arr))
+    e0.record(stream)
+    for _ in range(10): L.svtb200_inter_predict_batch_dev(h, d_arr, len(arr))
+    e1.record(stream); ctx.sync()
+    td = 100.0 * e0.elapsed_time(e1)
+    L.svtb200_dev_free(h, d_arr)
     alg = samples * (2 + comp)
-    print("%-16s %6d blocks  %8.1f us per picture  (incl. the descriptor upload)  %7.1f GB/s algorithmic" % (name, len(arr), t, alg / t / 1e3))
+    print("%-16s %6d blocks  host descriptors %7.1f us per picture   descriptors on the device %7.1f us  %7.1f GB/s algorithmic" % (name, len(arr), t, td, alg / td / 1e3))
