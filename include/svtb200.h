@@ -379,7 +379,7 @@ typedef struct SvtB200PredBlock {
     int32_t x[2], y[2];
     int32_t dst_stride;
     uint8_t subpel_x[2], subpel_y[2]; /* mv & 15, in 1/16 sample */
-    uint8_t w, h;                     /* 2 .. 64 */
+    uint8_t w, h;                     /* 4 .. 64 (the reference's SIMD kernels take no narrower blocks; its encoder asks for none) */
     uint8_t compound;                 /* 0: ref[0] only; 1: ref[1] averaged in */
     uint8_t reserved;
 } SvtB200PredBlock;

@@ -315,18 +315,27 @@ int refdrv_deblock(const SvtB200LfParams *P, uint8_t *y, int ys, uint8_t *u, uin
 #include "vp9_filter.h"
 #include "vp9_reconinter.h"
 /* inter_predictor() exactly as build_inter_predictors calls it (vp9_reconinter.c:246): unscaled scale factors, kernel 0.
- * 'ref' = 1 averages into dst (second reference of a compound block). */
-int refdrv_inter_predict(const uint8_t *pre, int ref_stride, uint8_t *dst, int dst_stride, int subpel_x, int subpel_y, int w, int h, int ref) {
+ * 'ref' = 1 averages into dst (second reference of a compound block).  flavour 0: the plain-C functions in the positions
+ * eb_vp9_setup_scale_factors_for_frame gives them (vp9_scale.c:78-83, 127-128); 1: what the RTCD dispatch selected.
+ * The SIMD copy / average kernels store aligned: dst must be aligned to the block width, as the encoder's buffers are. */
+int refdrv_inter_predict(const uint8_t *pre, int ref_stride, uint8_t *dst, int dst_stride, int subpel_x, int subpel_y, int w, int h, int ref,
+                         int flavour) {
     struct scale_factors sf;
     if (!g_init) return -1;
     eb_vp9_setup_scale_factors_for_frame(&sf, 1920, 1080, 1920, 1080);
+    if (!flavour) {
+        sf.predict[0][0][0] = eb_vp9_convolve_copy_c;   sf.predict[0][0][1] = eb_vp9_convolve_avg_c;
+        sf.predict[0][1][0] = eb_vp9_convolve8_vert_c;  sf.predict[0][1][1] = eb_vp9_convolve8_avg_vert_c;
+        sf.predict[1][0][0] = eb_vp9_convolve8_horiz_c; sf.predict[1][0][1] = eb_vp9_convolve8_avg_horiz_c;
+        sf.predict[1][1][0] = eb_vp9_convolve8_c;       sf.predict[1][1][1] = eb_vp9_convolve8_avg_c;
+    }
     inter_predictor(pre, ref_stride, dst, dst_stride, subpel_x, subpel_y, &sf, w, h, ref, eb_vp9_filter_kernels[0], 16, 16);
     return 0;
 }
-/* the table lookup of EbEncDecProcess.c:723 */
-int refdrv_full_distortion(int tx_size, int16_t *coeff, int16_t *recon_coeff, int eob, uint64_t out[2]) {
+/* the table lookup of EbEncDecProcess.c:723; flavour 0: the C_DEFAULT row of the table */
+int refdrv_full_distortion(int tx_size, int16_t *coeff, int16_t *recon_coeff, int eob, uint64_t out[2], int flavour) {
     const uint32_t n = 4u << tx_size;
     if (!g_init) return -1;
-    full_distortion_intrinsic_func_ptr_array[(eb_vp9_ASM_TYPES & PREAVX2_MASK) && 1][eob != 0][0][n >> 3](coeff, n, recon_coeff, n, out, n, n);
+    full_distortion_intrinsic_func_ptr_array[flavour ? ((eb_vp9_ASM_TYPES & PREAVX2_MASK) && 1) : 0][eob != 0][0][n >> 3](coeff, n, recon_coeff, n, out, n, n);
     return 0;
 }

@@ -153,7 +153,7 @@ extern "C" int svtb200_inter_predict_batch(SvtB200Ctx *c, const SvtB200PredBlock
     if (!n) return SVTB200_OK;
     for (int i = 0; i < n; i++) {
         const SvtB200PredBlock &b = blocks[i];
-        if (!b.ref[0] || !b.dst || b.w < 2 || b.w > 64 || b.h < 2 || b.h > 64 || b.subpel_x[0] > 15 || b.subpel_y[0] > 15 || b.compound > 1) return SVTB200_EINVAL;
+        if (!b.ref[0] || !b.dst || b.w < 4 || b.w > 64 || b.h < 4 || b.h > 64 || b.subpel_x[0] > 15 || b.subpel_y[0] > 15 || b.compound > 1) return SVTB200_EINVAL;
         if (b.compound && (!b.ref[1] || b.subpel_x[1] > 15 || b.subpel_y[1] > 15)) return SVTB200_EINVAL;
     }
     std::lock_guard<std::recursive_mutex> g(c->mu);

@@ -24,8 +24,8 @@ def _ref_plane(rng, w, h, kind):
 
 
 def _cases(rng, n, w, h):
-    """n blocks of every size the encode pass predicts (luma 8..64, chroma 4..32, 4:2:0 sub-8x8 2..4), every phase pair"""
-    sizes = [(64, 64), (32, 32), (16, 16), (8, 8), (4, 4), (64, 32), (32, 64), (16, 8), (8, 16), (32, 16), (4, 8), (8, 4), (2, 2), (2, 4), (4, 2), (16, 32)]
+    """n blocks of every size the encode pass predicts (luma 4..64, chroma 4..32; the reference's SIMD kernels do not take widths below 4, its encoder never asks for them), every phase pair"""
+    sizes = [(64, 64), (32, 32), (16, 16), (8, 8), (4, 4), (64, 32), (32, 64), (16, 8), (8, 16), (32, 16), (4, 8), (8, 4), (64, 16), (16, 64), (4, 16), (16, 32)]
     out = []
     for i in range(n):
         bw, bh = sizes[i % len(sizes)]
@@ -79,13 +79,17 @@ def _oracle_predict(cases, refs, w, h):
 
 
 def _reference_predict(cases, refs, w, h, simd):
-    R = H.refdrv(simd)
-    R.refdrv_inter_predict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
+    """the reference's functions block by block (simd 0: the plain-C ones, 1: the RTCD selection of this machine, AVX2 here).
+    The SIMD copy / average kernels use aligned stores, so each block is predicted into an aligned buffer like the encoder's."""
+    R = H.refdrv()
+    R.refdrv_inter_predict.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]
     dst = np.zeros((h, w), dtype=np.uint8)
     arr = _descriptors(cases, refs, [r.ctypes.data for r in refs], dst.ctypes.data, refs[0].shape[1], w, w, h)
-    for d in arr:
+    blk = H.aligned_zeros((64, 64), np.uint8)
+    for d, c in zip(arr, cases):
         for r in range(1 + d.compound):
-            assert R.refdrv_inter_predict(d.ref[r] + d.y[r] * d.ref_stride[r] + d.x[r], d.ref_stride[r], d.dst, d.dst_stride, d.subpel_x[r], d.subpel_y[r], d.w, d.h, r) == 0
+            assert R.refdrv_inter_predict(d.ref[r] + d.y[r] * d.ref_stride[r] + d.x[r], d.ref_stride[r], blk.ctypes.data, 64, d.subpel_x[r], d.subpel_y[r], d.w, d.h, r, simd) == 0
+        dst[c["by"]:c["by"] + c["h"], c["bx"]:c["bx"] + c["w"]] = blk[:c["h"], :c["w"]]
     return dst
 
 
@@ -144,12 +148,12 @@ def _oracle_distortion(tx_size, coeff, rc, eob):
 def test_oracle_distortion_matches_reference_functions(tx_size, simd):
     rng = np.random.default_rng(tx_size)
     coeff, rc, eob = _distortion_case(rng, tx_size, 64)
-    R = H.refdrv(simd)
-    R.refdrv_full_distortion.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    R = H.refdrv()
+    R.refdrv_full_distortion.argtypes = [C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int]
     exp = np.zeros((64, 2), dtype=np.uint64)
     for k in range(64):
         a, b = H.aligned_copy(coeff[k]), H.aligned_copy(rc[k])
-        assert R.refdrv_full_distortion(tx_size, a.ctypes.data, b.ctypes.data, int(eob[k]), exp[k].ctypes.data) == 0
+        assert R.refdrv_full_distortion(tx_size, a.ctypes.data, b.ctypes.data, int(eob[k]), exp[k].ctypes.data, simd) == 0
     assert (exp == _oracle_distortion(tx_size, coeff, rc, eob)).all()
 
 
@@ -202,4 +206,6 @@ def test_prediction_argument_checks():
     arr = (api.PredBlock * 1)()
     assert ctx.L.svtb200_inter_predict_batch(ctx.h, C.addressof(arr), 1) == -2  # null planes
     assert ctx.L.svtb200_inter_predict_batch(ctx.h, None, 0) == 0
+    arr[0].ref[0] = 4096; arr[0].dst = 4096; arr[0].w = 2; arr[0].h = 8
+    assert ctx.L.svtb200_inter_predict_batch(ctx.h, C.addressof(arr), 1) == -2  # narrower than the reference's kernels take
     ctx.close()
