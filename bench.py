@@ -400,7 +400,15 @@ def main():
     # a different (earlier) picture than the one being motion-estimated, and their CTAs fill the tail of the ME grid.
     ctx.select_compute(api.COMPUTE2)
     stream2 = torch.cuda.ExternalStream(L.svtb200_stream(h), device=torch.device("cuda", local_rank))
+    # Motion estimation of consecutive pictures is independent (the reference runs it several pictures ahead on separate
+    # threads): with SVTB200_BENCH_ME_QUEUES=2 it alternates between the first and the third compute queue, so that the next
+    # picture's CTAs could fill the tail of the current picture's grid (2040 CTAs = 3.45 waves of 4 x 148).  Measured: no gain
+    # (0.403 vs 0.400 ms per step) -- with the transform queue beside it the SMs are already busy, the step is bound by the
+    # instruction work of the kernels, not by their tails -- so one motion-estimation queue is the default.
+    ctx.select_compute(api.COMPUTE3)
+    stream3 = torch.cuda.ExternalStream(L.svtb200_stream(h), device=torch.device("cuda", local_rank))
     ctx.select_compute(api.COMPUTE)
+    ME_QUEUES = int(os.environ.get("SVTB200_BENCH_ME_QUEUES", "1"))
 
     _txq_cache = {}
     EDGE_PASSES = tuple(k for k, (_, _, _, cols, rows, _) in enumerate(TU_PASSES) if rows == 1)
@@ -425,14 +433,16 @@ def main():
     def kernels(i, timed, slot=0, overlap=True, sink=None):
         n = ENCODE_ORDER[i % 16]
         s2 = stream2 if overlap else stream
+        q1, s1 = (api.COMPUTE3, stream3) if overlap and ME_QUEUES == 2 and (i & 1) else (api.COMPUTE, stream)
         P, (r0, r1) = me_params(n)
         ids = (C.c_uint64 * 2)(r0, r1)
         e = [ev() for _ in range(6)] if timed else None
+        ctx.select_compute(q1)
         if timed:
-            e[0].record(stream)
+            e[0].record(s1)
         ctx.check(L.svtb200_me_picture_dev(h, C.byref(P), n, ids, d_me[slot], None), "me_picture_dev")
         if timed:
-            e[1].record(stream)
+            e[1].record(s1)
         targs = txq_args(slot, n, r0)
         if overlap:
             # the three edge passes (240 small blocks each, latency-bound 5-7 us launches) ride in the tail of the ME grid on the
@@ -444,7 +454,7 @@ def main():
             L.svtb200_picture_touch(h, n)
             L.svtb200_picture_touch(h, r0)
             if n == 16:
-                edge_done = ctx.marker(api.COMPUTE)
+                edge_done = ctx.marker(q1)
             ctx.select_compute(api.COMPUTE2)
         if timed:
             e[2].record(s2)
@@ -491,11 +501,12 @@ def main():
             ctx.check(L.svtb200_memcpy_h2d_async(h, d_v[n], pv[n].data_ptr(), csize), "h2d v")
             ctx.fence(api.UPLOAD, api.COMPUTE)
             ctx.fence(api.UPLOAD, api.COMPUTE2)
+            ctx.fence(api.UPLOAD, api.COMPUTE3)
         if "kernels" in skip:
             r0 = n
         else:
             _, r0 = kernels(i, False, slot)
-        chroma_used[n] = chroma_used[r0] = (ctx.marker(api.COMPUTE2), ctx.marker(api.COMPUTE))   # both queues read the chroma buffers
+        chroma_used[n] = chroma_used[r0] = (ctx.marker(api.COMPUTE2), ctx.marker(api.COMPUTE), ctx.marker(api.COMPUTE3))   # every compute queue reads the chroma buffers
         for m in chroma_used[n]:
             ctx.stream_wait(api.DOWNLOAD, m)
         rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
@@ -519,21 +530,23 @@ def main():
     ctx.L.svtb200_deblock_picture_dev.argtypes = [C.c_void_p, C.POINTER(api.LfParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
     sampler = ClockSampler(local_rank)
     for i in range(args.warmup):
-        kernels(i, False)
+        kernels(i, False, i % NSLOT)
     ctx.sync()
     barrier()
     sampler.start()
     e0, e1 = ev(), ev()
     launches0 = ctx.launches()
     e0.record(stream)
-    ctx.fence(api.COMPUTE, api.COMPUTE2)   # the second queue starts inside the timed region ...
+    ctx.fence(api.COMPUTE, api.COMPUTE2)   # the other queues start inside the timed region ...
+    ctx.fence(api.COMPUTE, api.COMPUTE3)
     t_host = time.perf_counter()
     for i in range(args.steps):
-        kernels(args.warmup + i, True)
+        kernels(args.warmup + i, True, (args.warmup + i) % NSLOT)
     t_host = time.perf_counter() - t_host
     if os.environ.get("SVTB200_BENCH_DEBUG"):
         sys.stderr.write("value leg: host issue time %.3f ms/step\n" % (1000.0 * t_host / args.steps))
-    ctx.fence(api.COMPUTE2, api.COMPUTE)   # ... and ends inside it
+    ctx.fence(api.COMPUTE2, api.COMPUTE)   # ... and end inside it
+    ctx.fence(api.COMPUTE3, api.COMPUTE)
     e1.record(stream)
     ctx.sync()
     barrier()

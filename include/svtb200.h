@@ -71,7 +71,7 @@ void  svtb200_dev_free(SvtB200Ctx *ctx, void *p);
 int   svtb200_memcpy_h2d(SvtB200Ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int   svtb200_memcpy_d2h(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 
-/* A context owns four in-order queues: COMPUTE and COMPUTE2 (kernels, and the synchronous copies above), UPLOAD (picture
+/* A context owns five in-order queues: COMPUTE, COMPUTE2 and COMPUTE3 (kernels, and the synchronous copies above), UPLOAD (picture
  * uploads and svtb200_memcpy_h2d_async) and DOWNLOAD (svtb200_memcpy_d2h_async), so that the PCIe traffic of the
  * previous / next picture overlaps the kernels of the current one -- the role the reference's picture-level pipeline
  * (EbEncHandle.c: one process per stage, several pictures in flight) plays on the CPU.  Picture uploads are ordered
@@ -86,7 +86,8 @@ int   svtb200_memcpy_d2h(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, s
 #define SVTB200_STREAM_DOWNLOAD 2
 #define SVTB200_STREAM_COMPUTE2 3 /* second compute queue: work of a DIFFERENT picture (e.g. the deblocking of picture n beside the
                                     motion estimation of picture n+1) fills the tail of the other queue's kernels */
-/* kernels of the following *_dev / host-pointer calls go to compute queue 'which' (COMPUTE or COMPUTE2); not thread safe */
+#define SVTB200_STREAM_COMPUTE3 4 /* third compute queue, e.g. the motion estimation of every other picture */
+/* kernels of the following *_dev / host-pointer calls go to compute queue 'which' (COMPUTE, COMPUTE2 or COMPUTE3); not thread safe */
 int svtb200_select_compute(SvtB200Ctx *ctx, int which);
 int svtb200_memcpy_h2d_async(SvtB200Ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
 int svtb200_memcpy_d2h_async(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);

@@ -146,7 +146,7 @@ def lib():
     return _lib
 
 
-COMPUTE, UPLOAD, DOWNLOAD, COMPUTE2 = 0, 1, 2, 3
+COMPUTE, UPLOAD, DOWNLOAD, COMPUTE2, COMPUTE3 = 0, 1, 2, 3, 4
 
 
 class Context:

@@ -31,7 +31,7 @@ struct ScanTable {
 struct SvtB200Ctx {
     int          device = 0;
     cudaStream_t stream = nullptr;              /* the compute queue kernels are launched on (one of compute[]) */
-    cudaStream_t compute[2] = {nullptr, nullptr};
+    cudaStream_t compute[3] = {nullptr, nullptr, nullptr};
     cudaStream_t up = nullptr, down = nullptr;  /* host->device and device->host copy streams */
     cudaEvent_t  markers[SVTB200_MARKER_RING] = {};
     uint64_t     next_ticket = 1;
@@ -87,7 +87,7 @@ static inline int svtb200_grow_pinned(SvtB200Ctx *ctx, size_t need) {
 void svtb200_lf_release(SvtB200Ctx *c); /* deblock.cu: per-context wavefront scratch */
 
 static inline cudaStream_t svtb200_pick_stream(SvtB200Ctx *c, int which) {
-    return which == SVTB200_STREAM_UPLOAD ? c->up : which == SVTB200_STREAM_DOWNLOAD ? c->down : which == SVTB200_STREAM_COMPUTE2 ? c->compute[1] : c->compute[0];
+    return which == SVTB200_STREAM_UPLOAD ? c->up : which == SVTB200_STREAM_DOWNLOAD ? c->down : which == SVTB200_STREAM_COMPUTE2 ? c->compute[1] : which == SVTB200_STREAM_COMPUTE3 ? c->compute[2] : c->compute[0];
 }
 /* a kernel about to read picture p on the compute stream: wait for its upload; afterwards note the use */
 static inline void svtb200_pic_acquire(SvtB200Ctx *c, DevPicture &p) { if (p.ready) cudaStreamWaitEvent(c->stream, p.ready, 0); }

@@ -20,6 +20,7 @@ int svtb200_create(int device, SvtB200Ctx **out) {
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
     if (cudaStreamCreateWithFlags(&c->compute[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->compute[1], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&c->compute[2], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->up, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->down, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete c; cudaGetLastError(); return SVTB200_ENODEV; }
     c->stream = c->compute[0];
@@ -32,7 +33,7 @@ int svtb200_create(int device, SvtB200Ctx **out) {
 void svtb200_destroy(SvtB200Ctx *c) {
     if (!c) return;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->up); cudaStreamSynchronize(c->compute[0]); cudaStreamSynchronize(c->compute[1]); cudaStreamSynchronize(c->down);
+    cudaStreamSynchronize(c->up); cudaStreamSynchronize(c->compute[0]); cudaStreamSynchronize(c->compute[1]); cudaStreamSynchronize(c->compute[2]); cudaStreamSynchronize(c->down);
     for (auto &kv : c->pics) {
         for (int i = 0; i < 3; i++) if (kv.second.pl[i].buf) cudaFree(kv.second.pl[i].buf);
         if (kv.second.ready) cudaEventDestroy(kv.second.ready);
@@ -49,7 +50,7 @@ void svtb200_destroy(SvtB200Ctx *c) {
     if (c->pred_read) cudaEventDestroy(c->pred_read);
     if (c->pin) cudaFreeHost(c->pin);
     for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { if (c->scans[a][b].scan) cudaFree(c->scans[a][b].scan); if (c->scans[a][b].iscan) cudaFree(c->scans[a][b].iscan); }
-    cudaStreamDestroy(c->compute[0]); cudaStreamDestroy(c->compute[1]); cudaStreamDestroy(c->up); cudaStreamDestroy(c->down);
+    cudaStreamDestroy(c->compute[0]); cudaStreamDestroy(c->compute[1]); cudaStreamDestroy(c->compute[2]); cudaStreamDestroy(c->up); cudaStreamDestroy(c->down);
     delete c;
 }
 
@@ -62,13 +63,14 @@ int svtb200_sync(SvtB200Ctx *c) {
     SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->up));
     SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->compute[0]));
     SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->compute[1]));
+    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->compute[2]));
     SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->down));
     return SVTB200_OK;
 }
 int svtb200_select_compute(SvtB200Ctx *c, int which) {
-    if (!c || (which != SVTB200_STREAM_COMPUTE && which != SVTB200_STREAM_COMPUTE2)) return SVTB200_EINVAL;
+    if (!c || (which != SVTB200_STREAM_COMPUTE && which != SVTB200_STREAM_COMPUTE2 && which != SVTB200_STREAM_COMPUTE3)) return SVTB200_EINVAL;
     std::lock_guard<std::recursive_mutex> g(c->mu);
-    c->stream = which == SVTB200_STREAM_COMPUTE2 ? c->compute[1] : c->compute[0];
+    c->stream = svtb200_pick_stream(c, which);
     return SVTB200_OK;
 }
 
@@ -84,7 +86,7 @@ int svtb200_memcpy_d2h_async(SvtB200Ctx *c, void *h, const void *d, size_t n) {
     return SVTB200_OK;
 }
 int svtb200_marker(SvtB200Ctx *c, int stream, uint64_t *ticket) {
-    if (!c || !ticket || stream < 0 || stream > 3) return SVTB200_EINVAL;
+    if (!c || !ticket || stream < 0 || stream > SVTB200_STREAM_COMPUTE3) return SVTB200_EINVAL;
     std::lock_guard<std::recursive_mutex> g(c->mu);
     const uint64_t t = c->next_ticket++;
     cudaEvent_t &e = c->markers[t % SVTB200_MARKER_RING];
@@ -100,7 +102,7 @@ static int marker_event(SvtB200Ctx *c, uint64_t ticket, cudaEvent_t *e) {
     return SVTB200_OK;
 }
 int svtb200_stream_wait(SvtB200Ctx *c, int stream, uint64_t ticket) {
-    if (!c || stream < 0 || stream > 3) return SVTB200_EINVAL;
+    if (!c || stream < 0 || stream > SVTB200_STREAM_COMPUTE3) return SVTB200_EINVAL;
     std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaEvent_t e;
     int rc = marker_event(c, ticket, &e);
@@ -319,7 +321,7 @@ int svtb200_picture_release(SvtB200Ctx *c, uint64_t pic_id) {
     auto it = c->pics.find(pic_id);
     if (it == c->pics.end()) return SVTB200_ENOENT;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->up); cudaStreamSynchronize(c->compute[0]); cudaStreamSynchronize(c->compute[1]);
+    cudaStreamSynchronize(c->up); cudaStreamSynchronize(c->compute[0]); cudaStreamSynchronize(c->compute[1]); cudaStreamSynchronize(c->compute[2]);
     for (int i = 0; i < 3; i++) if (it->second.pl[i].buf) cudaFree(it->second.pl[i].buf);
     if (it->second.ready) cudaEventDestroy(it->second.ready);
     if (it->second.used) cudaEventDestroy(it->second.used);
