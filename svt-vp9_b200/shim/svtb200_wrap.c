@@ -30,7 +30,9 @@ void __real_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_
 
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t  g_cv = PTHREAD_COND_INITIALIZER;
-static SvtB200Ctx     *g_ctx;
+static SvtB200Ctx     *g_ctx;    /* picture residency + motion estimation */
+static SvtB200Ctx     *g_ctx_lf; /* deblocking: its own queues and lock, so that a picture being filtered never waits behind (or blocks) the
+                                    motion estimation of the pictures after it -- they are different pipeline stages in the reference too */
 static int             g_state; /* 0 untried, 1 ready, -1 unavailable */
 static unsigned long   g_me_pictures, g_me_sbs, g_lf_pictures, g_fallbacks;
 static double          g_t_resident, g_t_me, g_t_lf; /* seconds spent in uploads / svtb200_me_picture / svtb200_deblock_picture */
@@ -42,7 +44,7 @@ static void report(void) {
     FILE *f = fopen(p, "w");
     if (!f) return;
     fprintf(f, "state %d\nme_pictures %lu\nme_sbs %lu\nlf_pictures %lu\nfallbacks %lu\nlaunches %llu\n", g_state, g_me_pictures, g_me_sbs,
-            g_lf_pictures, g_fallbacks, g_ctx ? (unsigned long long)svtb200_launch_count(g_ctx) : 0ull);
+            g_lf_pictures, g_fallbacks, g_ctx ? (unsigned long long)(svtb200_launch_count(g_ctx) + svtb200_launch_count(g_ctx_lf)) : 0ull);
     fprintf(f, "ms_upload %d\nms_me %d\nms_lf %d\n", (int)(1e3 * g_t_resident), (int)(1e3 * g_t_me), (int)(1e3 * g_t_lf));
     fclose(f);
 }
@@ -52,7 +54,10 @@ static int ctx_ready(void) {
     if (g_state == 0) {
         const char *e = getenv("SVT_VP9_GPU");
         g_state = -1;
-        if (!(e && !strcmp(e, "off")) && svtb200_create(e ? atoi(e) : 0, &g_ctx) == SVTB200_OK) g_state = 1;
+        if (!(e && !strcmp(e, "off")) && svtb200_create(e ? atoi(e) : 0, &g_ctx) == SVTB200_OK) {
+            if (svtb200_create(e ? atoi(e) : 0, &g_ctx_lf) == SVTB200_OK) g_state = 1;
+            else { svtb200_destroy(g_ctx); g_ctx = NULL; }
+        }
         if (g_state < 0 && getenv("SVT_VP9_GPU_VERBOSE")) fprintf(stderr, "svtb200: no GPU context, using the CPU kernels\n");
     }
     return g_state == 1;
@@ -229,7 +234,7 @@ void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_
         pthread_mutex_unlock(&g_mu);
     }
     const double t2 = now_s();
-    const int rc = svtb200_deblock_picture(g_ctx, &P, xd->plane[0].dst.buf, xd->plane[0].dst.stride, xd->plane[1].dst.buf, xd->plane[2].dst.buf,
+    const int rc = svtb200_deblock_picture(g_ctx_lf, &P, xd->plane[0].dst.buf, xd->plane[0].dst.stride, xd->plane[1].dst.buf, xd->plane[2].dst.buf,
                                            xd->plane[1].dst.stride, (const SvtB200LfMask *)cm->lf.lfm, cm->lf.lfm_stride, thr);
     pthread_mutex_lock(&g_mu);
     g_t_lf += now_s() - t2;
