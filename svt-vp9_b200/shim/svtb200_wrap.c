@@ -107,7 +107,9 @@ static int ensure_resident(const EbPaReferenceObject *o, uint64_t poc, int want_
     if (free_i < 0) return SVTB200_ENOMEM;
     SvtB200Plane pl[3];
     svtb200_glue_pa_planes(o, pl);
-    if (!g_res[free_i].valid || g_res[free_i].obj != (const void *)o) /* a buffer of the reference's pool, first time seen: page-lock it */
+    static int pagelock = -1; /* SVT_VP9_GPU_PAGELOCK=0: leave the reference's buffers pageable (staged copies, no page-locking cost) */
+    if (pagelock < 0) { const char *e = getenv("SVT_VP9_GPU_PAGELOCK"); pagelock = !(e && e[0] == '0'); }
+    if (pagelock && (!g_res[free_i].valid || g_res[free_i].obj != (const void *)o)) /* a buffer of the reference's pool, first time seen: page-lock it */
         for (int k = 0; k < 3; k++)
             if (pl[k].buf && pl[k].stride > 0 && pl[k].padded_height > 0) svtb200_host_register((void *)pl[k].buf, (size_t)pl[k].stride * pl[k].padded_height);
     int rc = svtb200_picture_upload(g_ctx, (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
@@ -148,60 +150,69 @@ static int run_picture(MeSlot *s, MeContext *me) {
     return rc;
 }
 
+/* One call per super-block from many threads.  Only the first call for a picture (which runs it on the GPU) and the calls that
+ * arrive while it runs take the lock; afterwards each thread remembers the picture's slot and copies its super-block's results
+ * out of the pinned buffer without any lock.  A slot is recycled when its last super-block has been handed out (atomic count),
+ * which cannot happen while a call that has not yet been counted is still reading it. */
 EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_index, uint32_t sb_origin_x, uint32_t sb_origin_y,
                                       MeContext *me, EbPictureBufferDesc *input) {
-    pthread_mutex_lock(&g_mu);
-    if (!ctx_ready()) {
-        pthread_mutex_unlock(&g_mu);
-        return __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input);
-    }
-    MeSlot *s = NULL, *fr = NULL;
-    for (int i = 0; i < MAX_IN_FLIGHT; i++) {
-        if (g_slots[i].state && g_slots[i].pcs == pcs && g_slots[i].picture_number == pcs->picture_number) { s = &g_slots[i]; break; }
-        if (!g_slots[i].state && !fr) fr = &g_slots[i];
-    }
-    int owner = 0;
-    if (!s) {
-        if (!fr) { g_fallbacks++; pthread_mutex_unlock(&g_mu); return __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input); }
-        s = fr;
-        s->pcs = pcs; s->picture_number = pcs->picture_number; s->state = 1; s->served = 0;
-        svtb200_glue_me_params(pcs, me, &s->P);
-        s->n_sb = ((s->P.luma_width + 63) / 64) * ((s->P.luma_height + 63) / 64);
-        if (s->cap_sb < (size_t)s->n_sb) {
-            if (s->res) svtb200_host_free(s->res);
-            if (s->rcme) svtb200_host_free(s->rcme);
-            s->res = (SvtB200MeCuResult *)svtb200_host_alloc((size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult));
-            s->rcme = (uint32_t *)svtb200_host_alloc((size_t)s->n_sb * sizeof(uint32_t));
-            s->cap_sb = (s->res && s->rcme) ? (size_t)s->n_sb : 0;
-        }
-        owner = 1;
-        g_me_pictures++;
-    }
-    if (owner) {
-        pthread_mutex_unlock(&g_mu);
-        const int rc = s->cap_sb ? run_picture(s, me) : SVTB200_ENOMEM;
+    static __thread MeSlot *tl_slot;
+    MeSlot *s = tl_slot;
+    if (!(s && __atomic_load_n(&s->state, __ATOMIC_ACQUIRE) >= 2 && s->pcs == pcs && s->picture_number == pcs->picture_number)) {
         pthread_mutex_lock(&g_mu);
-        s->state = rc == SVTB200_OK ? 2 : 3;
-        if (rc != SVTB200_OK && getenv("SVT_VP9_GPU_VERBOSE")) fprintf(stderr, "svtb200: ME on the GPU failed (%d: %s)\n", rc, svtb200_last_error(g_ctx));
-        pthread_cond_broadcast(&g_cv);
-    } else {
-        while (s->state == 1) pthread_cond_wait(&g_cv, &g_mu);
+        if (!ctx_ready()) {
+            pthread_mutex_unlock(&g_mu);
+            return __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input);
+        }
+        MeSlot *fr = NULL;
+        s = NULL;
+        for (int i = 0; i < MAX_IN_FLIGHT; i++) {
+            if (g_slots[i].state && g_slots[i].pcs == pcs && g_slots[i].picture_number == pcs->picture_number) { s = &g_slots[i]; break; }
+            if (!g_slots[i].state && !fr) fr = &g_slots[i];
+        }
+        if (!s) {
+            if (!fr) { g_fallbacks++; pthread_mutex_unlock(&g_mu); return __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input); }
+            s = fr;
+            s->pcs = pcs; s->picture_number = pcs->picture_number; s->served = 0;
+            __atomic_store_n(&s->state, 1, __ATOMIC_RELEASE);
+            svtb200_glue_me_params(pcs, me, &s->P);
+            s->n_sb = ((s->P.luma_width + 63) / 64) * ((s->P.luma_height + 63) / 64);
+            if (s->cap_sb < (size_t)s->n_sb) {
+                if (s->res) svtb200_host_free(s->res);
+                if (s->rcme) svtb200_host_free(s->rcme);
+                s->res = (SvtB200MeCuResult *)svtb200_host_alloc((size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult));
+                s->rcme = (uint32_t *)svtb200_host_alloc((size_t)s->n_sb * sizeof(uint32_t));
+                s->cap_sb = (s->res && s->rcme) ? (size_t)s->n_sb : 0;
+            }
+            g_me_pictures++;
+            pthread_mutex_unlock(&g_mu);
+            const int rc = s->cap_sb ? run_picture(s, me) : SVTB200_ENOMEM;
+            pthread_mutex_lock(&g_mu);
+            __atomic_store_n(&s->state, rc == SVTB200_OK ? 2 : 3, __ATOMIC_RELEASE);
+            if (rc != SVTB200_OK && getenv("SVT_VP9_GPU_VERBOSE")) fprintf(stderr, "svtb200: ME on the GPU failed (%d: %s)\n", rc, svtb200_last_error(g_ctx));
+            pthread_cond_broadcast(&g_cv);
+        } else {
+            while (s->state == 1) pthread_cond_wait(&g_cv, &g_mu);
+        }
+        pthread_mutex_unlock(&g_mu);
+        tl_slot = s;
     }
-    const int ok = s->state == 2;
-    SvtB200MeCuResult mine[85];
-    uint32_t rcme = 0;
-    if (ok) {
-        memcpy(mine, s->res + (size_t)sb_index * 85, sizeof(mine));
-        rcme = s->rcme[sb_index];
-    }
+    const int ok = __atomic_load_n(&s->state, __ATOMIC_ACQUIRE) == 2;
     const int rc_mode = s->P.rate_control_mode;
-    g_me_sbs++;
-    if (!ok) g_fallbacks++;
-    if (++s->served == s->n_sb) s->state = 0; /* every super-block of the picture has been handed out */
-    pthread_mutex_unlock(&g_mu);
+    if (ok) {
+        const SvtB200MeCuResult *mine = s->res + (size_t)sb_index * 85;
+        for (int i = 0; i < 85; i++) abi_to_ref(&mine[i], &pcs->me_results[sb_index][i]);
+        if (rc_mode) pcs->rcme_distortion[sb_index] = s->rcme[sb_index];
+    }
+    __atomic_add_fetch(&g_me_sbs, 1, __ATOMIC_RELAXED);
+    if (!ok) __atomic_add_fetch(&g_fallbacks, 1, __ATOMIC_RELAXED);
+    if (__atomic_add_fetch(&s->served, 1, __ATOMIC_ACQ_REL) == s->n_sb) { /* every super-block of the picture has been handed out */
+        tl_slot = NULL;
+        pthread_mutex_lock(&g_mu);
+        __atomic_store_n(&s->state, 0, __ATOMIC_RELEASE);
+        pthread_mutex_unlock(&g_mu);
+    }
     if (!ok) return __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input);
-    for (int i = 0; i < 85; i++) abi_to_ref(&mine[i], &pcs->me_results[sb_index][i]);
-    if (rc_mode) pcs->rcme_distortion[sb_index] = rcme;
     return EB_ErrorNone;
 }
 

@@ -19,7 +19,7 @@ with open(yuv, "wb") as f:
         f.write(y.tobytes()); f.write(u.tobytes()); f.write(v.tobytes())
 env = dict(os.environ)
 env["LD_LIBRARY_PATH"] = os.path.dirname(H.cudart_path()) + ":" + env.get("LD_LIBRARY_PATH", "")
-for name in ("SvtVp9EncApp_ref", "SvtVp9EncApp_b200", "SvtVp9EncApp_b200"):
+for name in os.environ.get("ENCODER_FPS_APPS", "SvtVp9EncApp_ref,SvtVp9EncApp_b200,SvtVp9EncApp_b200").split(","):
     out = os.path.join(d, name + ".ivf")
     rep = os.path.join(d, "rep.txt")
     e = dict(env, SVT_VP9_GPU_REPORT=rep)
