@@ -22,7 +22,7 @@
  *   around the seams (same library): svtb200_picture_upload_luma (padding + 1/4, 1/16 decimation of the picture-analysis
  *       front end), svtb200_zz_sad_picture (compute_zz_sad), svtb200_block_stats_picture
  *       (compute_block_mean_compute_variance), svtb200_build_masks (eb_vp9_build_mask_frame), svtb200_pick_filter_level
- *       (eb_vp9_pick_filter_level), svtb200_pad_plane_dev (eb_vp9_generate_padding), svtb200_inter_predict_batch (inter_predictor),
+ *       (eb_vp9_pick_filter_level), svtb200_pad_plane_dev (eb_vp9_generate_padding), svtb200_inter_predict_batch (inter_predictor), svtb200_intra_predict_batch (the intra predictors),
  *       svtb200_full_distortion_batch_dev (full_distortion_kernel32bit); each cites its reference lines below.
  *
  * "Host" entry points take HOST pointers (pinned or pageable) and perform the host<->device copies
@@ -388,6 +388,23 @@ typedef struct SvtB200PredBlock {
 int svtb200_inter_predict_batch(SvtB200Ctx *ctx, const SvtB200PredBlock *blocks, int n);
 /* the same with the descriptors already on the device (unchecked) */
 int svtb200_inter_predict_batch_dev(SvtB200Ctx *ctx, const SvtB200PredBlock *blocks_dev, int n);
+
+/* One intra prediction call of the encode pass: pred[mode][tx_size](dst, stride, above, left), or for DC_PRED
+ * dc_pred[have_left][have_top][tx_size] (build_intra_predictors, Source/Lib/VPX/vp9_reconintra.c:397-407; the predictors:
+ * Source/Lib/VPX/intrapred.c:22-218 and the 4x4 forms :253-417), on the reference sample arrays the reference's host code
+ * prepares (generate_intra_reference_samples: const_above_row / left_col of EncDecContext).  Device pointers: above[-1] ..
+ * above[2 * bs - 1] and left[0 .. bs - 1] must be readable (bs = 4 << tx_size).  mode is a PREDICTION_MODE value:
+ * 0 DC, 1 V, 2 H, 3 D45, 4 D135, 5 D117, 6 D153, 7 D207, 8 D63, 9 TM. */
+typedef struct SvtB200IntraBlock {
+    const uint8_t *above;
+    const uint8_t *left;
+    uint8_t       *dst;
+    int32_t        dst_stride;
+    uint8_t        mode, tx_size;
+    uint8_t        have_left, have_top; /* DC_PRED only */
+} SvtB200IntraBlock;
+/* blocks: HOST array (copied to the device by the call) */
+int svtb200_intra_predict_batch(SvtB200Ctx *ctx, const SvtB200IntraBlock *blocks, int n);
 
 /* full_distortion_intrinsic_func_ptr_array[..][eob != 0][0][..] (Source/Lib/Codec/EbPictureOperators.h:240, call site
  * Source/Lib/Codec/EbEncDecProcess.c:723): per transform block k of n (N x N coefficients each, block-major as svtb200_txq_batch

@@ -7,6 +7,8 @@
  *   eb_vp9_convolve8_c (two passes through an 8-bit intermediate of h + 7 rows)   vpx_convolve.c:133-168
  *   eb_vp9_convolve_copy_c / eb_vp9_convolve_avg_c / *_avg_* (second reference)   vpx_convolve.c:170-215
  *   sub_pel_filters_8 (the only kernel build_inter_predictors uses, vp9_reconinter.c:105)   Source/Lib/VPX/vp9_filter.c:32
+ *   the intra predictors (d207 .. dc, generic :22-218 and the 4x4 forms :253-417)   Source/Lib/VPX/intrapred.c
+ *     selected as build_intra_predictors does   Source/Lib/VPX/vp9_reconintra.c:397-407 (table :64-87)
  *   full_distortion_kernel32bit / full_distortion_kernel_eob_zero32bit   Source/Lib/C_DEFAULT/EbPictureOperators_C.c:289, 314
  * Pinned against those reference functions (C and AVX2 flavours) through oracle/_ref (tests/test_pred.py).
  */
@@ -88,5 +90,94 @@ void svtb200_oracle_full_distortion(int tx_size, int n, const int16_t *coeff, co
         }
         dist[2 * k] = eob[k] ? res : pred;
         dist[2 * k + 1] = pred;
+    }
+}
+
+/* ---- intra prediction.  Written as the fill order the predictors define (first rows / columns from the edge samples, the
+ * rest by the diagonal recurrences), which is a different formulation from the closed forms the CUDA kernel evaluates. ---- */
+#define A2(a, b) (((a) + (b) + 1) >> 1)
+#define A3(a, b, c) (((a) + 2 * (b) + (c) + 2) >> 2)
+
+static void intra_one(int mode, int bs, int have_left, int have_top, const uint8_t *a /* above, a[-1] valid */, const uint8_t *l, uint8_t *o /* pitch 32 */) {
+    int r, c;
+#define O(r, c) o[(r) * 32 + (c)]
+    switch (mode) {
+    case 0: { /* DC: dc_128 / dc_top / dc_left / dc (intrapred.c:167-218) */
+        int sum = 0, v;
+        if (have_left && have_top) { for (c = 0; c < bs; c++) sum += a[c] + l[c]; v = (sum + bs) / (2 * bs); }
+        else if (have_left) { for (c = 0; c < bs; c++) sum += l[c]; v = (sum + (bs >> 1)) / bs; }
+        else if (have_top) { for (c = 0; c < bs; c++) sum += a[c]; v = (sum + (bs >> 1)) / bs; }
+        else v = 128;
+        for (r = 0; r < bs; r++) for (c = 0; c < bs; c++) O(r, c) = (uint8_t)v;
+        break;
+    }
+    case 1: for (r = 0; r < bs; r++) for (c = 0; c < bs; c++) O(r, c) = a[c]; break;                       /* V :137 */
+    case 2: for (r = 0; r < bs; r++) for (c = 0; c < bs; c++) O(r, c) = l[r]; break;                       /* H :147 */
+    case 9: for (r = 0; r < bs; r++) for (c = 0; c < bs; c++) { int v = l[r] + a[c] - a[-1]; O(r, c) = (uint8_t)(v < 0 ? 0 : v > 255 ? 255 : v); } break; /* TM :157 */
+    case 3: /* D45 :59, 4x4 :313 (which runs on to above[7]) */
+        if (bs == 4) {
+            for (r = 0; r < 4; r++) for (c = 0; c < 4; c++) O(r, c) = (uint8_t)(r + c < 6 ? A3(a[r + c], a[r + c + 1], a[r + c + 2]) : a[7]);
+        } else {
+            for (c = 0; c < bs - 1; c++) O(0, c) = (uint8_t)A3(a[c], a[c + 1], a[c + 2]);
+            O(0, bs - 1) = a[bs - 1];
+            for (r = 1; r < bs; r++) for (c = 0; c < bs; c++) O(r, c) = c < bs - 1 - r ? O(0, r + c) : a[bs - 1];
+        }
+        break;
+    case 8: /* D63 :43, 4x4 :268 (no replication of above[3]) */
+        for (c = 0; c < bs; c++) { O(0, c) = (uint8_t)A2(a[c], a[c + 1]); O(1, c) = (uint8_t)A3(a[c], a[c + 1], a[c + 2]); }
+        for (r = 2; r < bs; r++) {
+            const int k = r >> 1, size = bs - 1 - k;
+            for (c = 0; c < bs; c++) {
+                if (bs == 4) O(r, c) = (uint8_t)((r & 1) ? A3(a[k + c], a[k + c + 1], a[k + c + 2]) : A2(a[k + c], a[k + c + 1]));
+                else O(r, c) = c < size ? O(r & 1, k + c) : a[bs - 1];
+            }
+        }
+        break;
+    case 7: /* D207 :22 */
+        for (r = 0; r < bs - 1; r++) O(r, 0) = (uint8_t)A2(l[r], l[r + 1]);
+        O(bs - 1, 0) = l[bs - 1];
+        for (r = 0; r < bs - 2; r++) O(r, 1) = (uint8_t)A3(l[r], l[r + 1], l[r + 2]);
+        O(bs - 2, 1) = (uint8_t)A3(l[bs - 2], l[bs - 1], l[bs - 1]);
+        O(bs - 1, 1) = l[bs - 1];
+        for (c = 2; c < bs; c++) O(bs - 1, c) = l[bs - 1];
+        for (r = bs - 2; r >= 0; r--) for (c = 2; c < bs; c++) O(r, c) = O(r + 1, c - 2);
+        break;
+    case 5: /* D117 :75 */
+        for (c = 0; c < bs; c++) O(0, c) = (uint8_t)A2(a[c - 1], a[c]);
+        O(1, 0) = (uint8_t)A3(l[0], a[-1], a[0]);
+        for (c = 1; c < bs; c++) O(1, c) = (uint8_t)A3(a[c - 2], a[c - 1], a[c]);
+        O(2, 0) = (uint8_t)A3(a[-1], l[0], l[1]);
+        for (r = 3; r < bs; r++) O(r, 0) = (uint8_t)A3(l[r - 3], l[r - 2], l[r - 1]);
+        for (r = 2; r < bs; r++) for (c = 1; c < bs; c++) O(r, c) = O(r - 2, c - 1);
+        break;
+    case 4: { /* D135 :98: the outer border from bottom-left to top-right, every row a window of it */
+        uint8_t b[63];
+        for (c = 0; c < bs - 2; c++) b[c] = (uint8_t)A3(l[bs - 3 - c], l[bs - 2 - c], l[bs - 1 - c]);
+        b[bs - 2] = (uint8_t)A3(a[-1], l[0], l[1]);
+        b[bs - 1] = (uint8_t)A3(l[0], a[-1], a[0]);
+        b[bs] = (uint8_t)A3(a[-1], a[0], a[1]);
+        for (c = 0; c < bs - 2; c++) b[bs + 1 + c] = (uint8_t)A3(a[c], a[c + 1], a[c + 2]);
+        for (r = 0; r < bs; r++) for (c = 0; c < bs; c++) O(r, c) = b[bs - 1 - r + c];
+        break;
+    }
+    case 6: /* D153 :117 */
+        O(0, 0) = (uint8_t)A2(a[-1], l[0]);
+        for (r = 1; r < bs; r++) O(r, 0) = (uint8_t)A2(l[r - 1], l[r]);
+        O(0, 1) = (uint8_t)A3(l[0], a[-1], a[0]);
+        O(1, 1) = (uint8_t)A3(a[-1], l[0], l[1]);
+        for (r = 2; r < bs; r++) O(r, 1) = (uint8_t)A3(l[r - 2], l[r - 1], l[r]);
+        for (c = 2; c < bs; c++) O(0, c) = (uint8_t)A3(a[c - 3], a[c - 2], a[c - 1]);
+        for (r = 1; r < bs; r++) for (c = 2; c < bs; c++) O(r, c) = O(r - 1, c - 2);
+        break;
+    }
+#undef O
+}
+
+void svtb200_oracle_intra_predict(const SvtB200IntraBlock *b, int n) {
+    for (int i = 0; i < n; i++, b++) {
+        uint8_t o[32 * 32];
+        const int bs = 4 << b->tx_size;
+        intra_one(b->mode, bs, b->have_left, b->have_top, b->above, b->left, o);
+        for (int r = 0; r < bs; r++) memcpy(b->dst + (ptrdiff_t)r * b->dst_stride, o + r * 32, (size_t)bs);
     }
 }

@@ -339,3 +339,20 @@ int refdrv_full_distortion(int tx_size, int16_t *coeff, int16_t *recon_coeff, in
     full_distortion_intrinsic_func_ptr_array[flavour ? ((eb_vp9_ASM_TYPES & PREAVX2_MASK) && 1) : 0][eob != 0][0][n >> 3](coeff, n, recon_coeff, n, out, n, n);
     return 0;
 }
+
+/* pred[mode][tx_size] / dc_pred[have_left][have_top][tx_size] as eb_vp9_init_intra_predictors_internal fills them
+ * (vp9_reconintra.c:64-87); flavour 0: the _c functions, 1: the RTCD selection. */
+typedef void (*refdrv_intra_fn)(uint8_t *dst, ptrdiff_t stride, const uint8_t *above, const uint8_t *left);
+#define RD_SIZES(type, suffix) {eb_vp9_##type##_predictor_4x4##suffix, eb_vp9_##type##_predictor_8x8##suffix, eb_vp9_##type##_predictor_16x16##suffix, eb_vp9_##type##_predictor_32x32##suffix}
+int refdrv_intra_predict(int mode, int tx_size, int have_left, int have_top, uint8_t *dst, int stride, const uint8_t *above, const uint8_t *left, int flavour) {
+    if (!g_init || mode < 0 || mode > 9 || tx_size < 0 || tx_size > 3) return -1;
+    const refdrv_intra_fn c_tab[10][4] = {RD_SIZES(dc, _c), RD_SIZES(v, _c), RD_SIZES(h, _c), RD_SIZES(d45, _c), RD_SIZES(d135, _c), RD_SIZES(d117, _c),
+                                          RD_SIZES(d153, _c), RD_SIZES(d207, _c), RD_SIZES(d63, _c), RD_SIZES(tm, _c)};
+    const refdrv_intra_fn s_tab[10][4] = {RD_SIZES(dc, ), RD_SIZES(v, ), RD_SIZES(h, ), RD_SIZES(d45, ), RD_SIZES(d135, ), RD_SIZES(d117, ),
+                                          RD_SIZES(d153, ), RD_SIZES(d207, ), RD_SIZES(d63, ), RD_SIZES(tm, )};
+    const refdrv_intra_fn c_dc[2][2][4] = {{RD_SIZES(dc_128, _c), RD_SIZES(dc_top, _c)}, {RD_SIZES(dc_left, _c), RD_SIZES(dc, _c)}};
+    const refdrv_intra_fn s_dc[2][2][4] = {{RD_SIZES(dc_128, ), RD_SIZES(dc_top, )}, {RD_SIZES(dc_left, ), RD_SIZES(dc, )}};
+    refdrv_intra_fn f = mode == 0 ? (flavour ? s_dc : c_dc)[!!have_left][!!have_top][tx_size] : (flavour ? s_tab : c_tab)[mode][tx_size];
+    f(dst, stride, above, left);
+    return 0;
+}

@@ -84,6 +84,12 @@ class PredBlock(C.Structure):
                 ("compound", C.c_uint8), ("reserved", C.c_uint8)]
 
 
+class IntraBlock(C.Structure):
+    """SvtB200IntraBlock: one intra predictor call (device pointers for the product, host pointers for the oracle)."""
+    _fields_ = [("above", C.c_void_p), ("left", C.c_void_p), ("dst", C.c_void_p), ("dst_stride", C.c_int32), ("mode", C.c_uint8), ("tx_size", C.c_uint8),
+                ("have_left", C.c_uint8), ("have_top", C.c_uint8)]
+
+
 def plane_of(arr, origin_x, origin_y, width, height):
     """Describe a padded 2-D uint8 numpy array (C-contiguous) as an SvtB200Plane."""
     assert arr.dtype == np.uint8 and arr.flags["C_CONTIGUOUS"] and arr.ndim == 2
@@ -141,6 +147,7 @@ def lib():
         L.svtb200_me_read_trace.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t]
         L.svtb200_inter_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.svtb200_inter_predict_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.svtb200_intra_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.svtb200_full_distortion_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -402,5 +409,11 @@ def _ctx_full_distortion(self, tx_size, coeff, recon_coeff, eob):
     return out
 
 
+def _ctx_intra_predict(self, blocks):
+    """blocks: ctypes array of IntraBlock with DEVICE pointers; asynchronous on the current compute queue."""
+    self.check(self.L.svtb200_intra_predict_batch(self.h, C.addressof(blocks), len(blocks)), "intra_predict_batch")
+
+
 Context.inter_predict = _ctx_inter_predict
+Context.intra_predict = _ctx_intra_predict
 Context.full_distortion = _ctx_full_distortion

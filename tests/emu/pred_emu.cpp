@@ -1,0 +1,16 @@
+// CPU execution of the closed-form intra predictors the CUDA kernel evaluates (test infrastructure only).
+#define SVTB200_CPU_EMU 1
+#include "../../svt-vp9_b200/csrc/emu/cuda_emu.h"
+#include "../../svt-vp9_b200/csrc/intra_device.cuh"
+#include "../../include/svtb200.h"
+
+extern "C" int intra_emu_run(const SvtB200IntraBlock *b, int n) {
+    for (int i = 0; i < n; i++, b++) {
+        const int bs = 4 << b->tx_size;
+        IntraEdge E; E.a = b->above; E.l = b->left;
+        const int dc = b->mode == 0 ? intra_dc_value(bs, b->have_left, b->have_top, E) : 0;
+        for (int r = 0; r < bs; r++)
+            for (int c = 0; c < bs; c++) b->dst[(ptrdiff_t)r * b->dst_stride + c] = (uint8_t)intra_sample(b->mode, bs, dc, E, r, c);
+    }
+    return 0;
+}

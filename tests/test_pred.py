@@ -157,6 +157,81 @@ def test_oracle_distortion_matches_reference_functions(tx_size, simd):
     assert (exp == _oracle_distortion(tx_size, coeff, rc, eob)).all()
 
 
+# ---- intra prediction ------------------------------------------------------------------------------------------------
+def _intra_cases(rng, n, kind):
+    """n predictor calls: every mode x size x DC variant, edge samples random / saturating / smooth.
+    Returns (edges, cases): edges is one byte pool, a case is (mode, tx_size, have_left, have_top, above_offset, left_offset)."""
+    pool = np.zeros(n * 128, dtype=np.uint8)
+    cases = []
+    for i in range(n):
+        mode, ts = i % 10, (i // 10) % 4
+        bs = 4 << ts
+        if kind == "noise":
+            e = rng.integers(0, 256, size=112)
+        elif kind == "extreme":
+            e = rng.integers(0, 2, size=112) * 255
+        else:
+            e = (128 + 60 * np.sin(np.arange(112) / 9.0 + i) + rng.integers(-4, 5, size=112)).clip(0, 255)
+        pool[i * 128:i * 128 + 112] = e
+        # layout inside the 128-byte record: left at 0..31, above[-1] at 47, above[0..63] at 48..111
+        cases.append((mode, ts, (i // 40) & 1, (i // 80) & 1, i * 128 + 48, i * 128))
+        assert 2 * bs <= 64
+    return pool, cases
+
+
+def _intra_blocks(cases, pool_addr, dst_addr):
+    arr = (api.IntraBlock * len(cases))()
+    for k, (d, (mode, ts, hl, ht, ao, lo)) in enumerate(zip(arr, cases)):
+        d.above, d.left, d.dst, d.dst_stride = pool_addr + ao, pool_addr + lo, dst_addr + k * 1024, 32
+        d.mode, d.tx_size, d.have_left, d.have_top = mode, ts, hl, ht
+    return arr
+
+
+def _oracle_intra(cases, pool):
+    out = np.zeros((len(cases), 32, 32), dtype=np.uint8)
+    arr = _intra_blocks(cases, pool.ctypes.data, out.ctypes.data)
+    O = H.oracle()
+    O.svtb200_oracle_intra_predict.argtypes = [C.c_void_p, C.c_int]
+    O.svtb200_oracle_intra_predict(C.addressof(arr), len(arr))
+    return out
+
+
+@pytest.mark.parametrize("kind", ["noise", "extreme", "smooth"])
+def test_emulated_intra_closed_forms_match_oracle(kind):
+    """the per-sample closed forms of csrc/intra_device.cuh (what the CUDA kernel evaluates), run on the CPU"""
+    rng = np.random.default_rng(53)
+    pool, cases = _intra_cases(rng, 960, kind)
+    exp = _oracle_intra(cases, pool)
+    got = np.zeros_like(exp)
+    arr = _intra_blocks(cases, pool.ctypes.data, got.ctypes.data)
+    E = H.emu()
+    E.intra_emu_run.argtypes = [C.c_void_p, C.c_int]
+    assert E.intra_emu_run(C.addressof(arr), len(arr)) == 0
+    assert (got == exp).all()
+
+
+@pytest.mark.skipif(not H.have_refdrv(), reason="oracle/_ref path driver not built")
+@pytest.mark.parametrize("simd", [0, 1])
+@pytest.mark.parametrize("kind", ["noise", "extreme", "smooth"])
+def test_oracle_intra_matches_reference_functions(kind, simd):
+    rng = np.random.default_rng(31 + simd)
+    pool, cases = _intra_cases(rng, 480, kind)
+    got = _oracle_intra(cases, pool)
+    R = H.refdrv()
+    R.refdrv_intra_predict.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    blk = H.aligned_zeros((32, 32), np.uint8)
+    edges = H.aligned_zeros(256, np.uint8)  # the SIMD predictors load the above row with aligned 16-byte loads: above[0] at a 16-byte boundary
+    for k, (mode, ts, hl, ht, ao, lo) in enumerate(cases):
+        bs = 4 << ts
+        edges[:] = 0
+        edges[64 - 1:64 + 64] = pool[ao - 1:ao + 64]
+        edges[160:160 + 32] = pool[lo:lo + 32]
+        blk[:] = 0
+        assert R.refdrv_intra_predict(mode, ts, hl, ht, blk.ctypes.data, 32, edges.ctypes.data + 64, edges.ctypes.data + 160, simd) == 0
+        assert (blk[:bs, :bs] == got[k, :bs, :bs]).all(), (mode, ts, hl, ht)
+    assert len({(c[0], c[1]) for c in cases}) == 40
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("kind", ["noise", "extreme", "smooth"])
 def test_cuda_prediction_matches_oracle(kind):
@@ -209,3 +284,27 @@ def test_prediction_argument_checks():
     arr[0].ref[0] = 4096; arr[0].dst = 4096; arr[0].w = 2; arr[0].h = 8
     assert ctx.L.svtb200_inter_predict_batch(ctx.h, C.addressof(arr), 1) == -2  # narrower than the reference's kernels take
     ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind", ["noise", "extreme", "smooth"])
+def test_cuda_intra_matches_oracle(kind):
+    rng = np.random.default_rng(77)
+    pool, cases = _intra_cases(rng, 1600, kind)
+    exp = _oracle_intra(cases, pool)
+    ctx = api.Context(0)
+    L, hd = ctx.L, ctx.h
+    d_pool = L.svtb200_dev_alloc(hd, pool.nbytes)
+    d_out = L.svtb200_dev_alloc(hd, exp.nbytes)
+    ctx.check(L.svtb200_memcpy_h2d(hd, d_pool, pool.ctypes.data, pool.nbytes), "h2d")
+    got = np.zeros_like(exp)
+    ctx.check(L.svtb200_memcpy_h2d(hd, d_out, got.ctypes.data, got.nbytes), "h2d")
+    ctx.intra_predict(_intra_blocks(cases, d_pool, d_out))
+    ctx.sync()
+    ctx.check(L.svtb200_memcpy_d2h(hd, got.ctypes.data, d_out, got.nbytes), "d2h")
+    L.svtb200_dev_free(hd, d_pool); L.svtb200_dev_free(hd, d_out)
+    arr = (api.IntraBlock * 1)()
+    arr[0].above = arr[0].left = arr[0].dst = 4096; arr[0].mode = 10
+    assert L.svtb200_intra_predict_batch(hd, C.addressof(arr), 1) == -2
+    ctx.close()
+    assert (got == exp).all()

@@ -51,3 +51,24 @@ for name, sx, sy, comp in (("copy", 0, 0, 0), ("horizontal", 6, 0, 0), ("vertica
     L.svtb200_dev_free(h, d_arr)
     alg = samples * (2 + comp)
     print("%-16s %6d blocks  host descriptors %7.1f us per picture   descriptors on the device %7.1f us  %7.1f GB/s algorithmic" % (name, len(arr), t, td, alg / td / 1e3))
+
+# ---- intra predictors: every 32x32 luma block and 16x16 chroma block of a 4K picture, one mode per run
+n32, n16 = (W // 32) * (HH // 32), 2 * (W // 32) * (HH // 32)
+pool = rng.integers(0, 256, size=(n32 + n16) * 128, dtype=np.uint8)
+d_pool = L.svtb200_dev_alloc(h, pool.nbytes); L.svtb200_memcpy_h2d(h, d_pool, pool.ctypes.data, pool.nbytes)
+d_out = L.svtb200_dev_alloc(h, W * HH * 3 // 2)
+for mode, name in ((0, "DC"), (1, "V"), (9, "TM"), (3, "D45"), (4, "D135"), (5, "D117"), (7, "D207")):
+    arr = (api.IntraBlock * (n32 + n16))()
+    off = 0
+    for k, d in enumerate(arr):
+        ts = 3 if k < n32 else 2
+        d.above, d.left, d.dst, d.dst_stride = d_pool + k * 128 + 48, d_pool + k * 128, d_out + off, 4 << ts
+        d.mode, d.tx_size, d.have_left, d.have_top = mode, ts, 1, 1
+        off += (4 << ts) ** 2
+    for _ in range(3): ctx.intra_predict(arr)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(10): ctx.intra_predict(arr)
+    e1.record(stream); ctx.sync()
+    t = 100.0 * e0.elapsed_time(e1)
+    print("intra %-5s %6d blocks  %7.1f us per picture (host descriptors)  %7.1f GB/s written" % (name, len(arr), t, samples / t / 1e3))
