@@ -62,6 +62,14 @@ static inline uint32_t __vavgu4(uint32_t a, uint32_t b) {
     for (int i = 0; i < 4; i++) { uint32_t x = (a >> (8 * i)) & 255, y = (b >> (8 * i)) & 255; r |= ((x + y + 1) >> 1) << (8 * i); }
     return r;
 }
+static inline uint32_t __vminu2(uint32_t a, uint32_t b) {
+    const uint32_t l = (a & 0xffff) < (b & 0xffff) ? (a & 0xffff) : (b & 0xffff), h = (a >> 16) < (b >> 16) ? (a >> 16) : (b >> 16);
+    return l | h << 16;
+}
+static inline uint32_t __vmaxu2(uint32_t a, uint32_t b) {
+    const uint32_t l = (a & 0xffff) > (b & 0xffff) ? (a & 0xffff) : (b & 0xffff), h = (a >> 16) > (b >> 16) ? (a >> 16) : (b >> 16);
+    return l | h << 16;
+}
 static inline int __dp4a(uint32_t a, uint32_t b, int c) {
     for (int i = 0; i < 4; i++) c += (int)((a >> (8 * i)) & 255) * (int)((b >> (8 * i)) & 255);
     return c;

@@ -1,7 +1,9 @@
-// CPU execution of the closed-form intra predictors the CUDA kernel evaluates (test infrastructure only).
+// CPU execution of the prediction kernels' device code: the closed-form intra predictors and the inter-prediction kernel
+// (test infrastructure only).
 #define SVTB200_CPU_EMU 1
 #include "../../svt-vp9_b200/csrc/emu/cuda_emu.h"
 #include "../../svt-vp9_b200/csrc/intra_device.cuh"
+#include "../../svt-vp9_b200/csrc/pred_device.cuh"
 #include "../../include/svtb200.h"
 
 extern "C" int intra_emu_run(const SvtB200IntraBlock *b, int n) {
@@ -12,5 +14,10 @@ extern "C" int intra_emu_run(const SvtB200IntraBlock *b, int n) {
         for (int r = 0; r < bs; r++)
             for (int c = 0; c < bs; c++) b->dst[(ptrdiff_t)r * b->dst_stride + c] = (uint8_t)intra_sample(b->mode, bs, dc, E, r, c);
     }
+    return 0;
+}
+
+extern "C" int pred_emu_run(const SvtB200PredBlock *blocks, int n, int grid) {
+    emu_launch(dim3((unsigned)(n < grid ? n : grid)), dim3(PRED_THREADS), 0, [&] { pred_kernel(blocks, n); });
     return 0;
 }

@@ -157,6 +157,24 @@ def test_oracle_distortion_matches_reference_functions(tx_size, simd):
     assert (exp == _oracle_distortion(tx_size, coeff, rc, eob)).all()
 
 
+@pytest.mark.parametrize("kind", ["noise", "extreme"])
+def test_emulated_prediction_kernel_matches_oracle(kind):
+    """csrc/pred_device.cuh (the CUDA kernel's source: packed dot products, 16-bit-halves vertical pass, reciprocal indexing)
+    executed on the CPU; fewer CTAs than blocks, so the grid-stride loop is exercised too"""
+    rng = np.random.default_rng(91)
+    w, h = 320, 192
+    refs = [_ref_plane(rng, w, h, kind), _ref_plane(rng, w, h, kind)]
+    cases = _non_overlapping(_cases(rng, 700, w, h))
+    assert len(cases) > 40 and any(c["compound"] for c in cases)
+    exp, _ = _oracle_predict(cases, refs, w, h)
+    got = np.zeros((h, w), dtype=np.uint8)
+    arr = _descriptors(cases, refs, [r.ctypes.data for r in refs], got.ctypes.data, refs[0].shape[1], w, w, h)
+    E = H.emu()
+    E.pred_emu_run.argtypes = [C.c_void_p, C.c_int, C.c_int]
+    assert E.pred_emu_run(C.addressof(arr), len(arr), 7) == 0
+    assert (got == exp).all()
+
+
 # ---- intra prediction ------------------------------------------------------------------------------------------------
 def _intra_cases(rng, n, kind):
     """n predictor calls: every mode x size x DC variant, edge samples random / saturating / smooth.
