@@ -1,7 +1,7 @@
 /*
  * cuda_emu.h -- minimal single-block-at-a-time CPU emulation of the CUDA execution model, used
- * ONLY by the "-m 'not gpu'" unit tests (tests/test_kernels_emulated.py) to exercise the kernel
- * sources' control logic on a box without a GPU.  It is not a product path and not a fallback:
+ * ONLY by the "-m 'not gpu'" unit tests (tests/emu/*.cpp: motion estimation, deblocking, mask building,
+ * prediction) to exercise the kernel sources on a box without a GPU.  It is not a product path and not a fallback:
  * libsvtvp9_b200.so is built by nvcc from the same .cu sources and never includes this file.
  *
  * Model: a launch runs its blocks one after another; the threads of a block are real OS threads
