@@ -1,9 +1,9 @@
 #!/usr/bin/env python
 """bench.py -- hot-path throughput on B200.
 
-A "step" is one pass of the hot path over one 3840x2160 picture of BASELINE.json's configs[2] (4K 8-bit 4:2:0,
-enc-mode 8): the pictures of a 16-picture hierarchical mini-GOP are processed in encode order with their real reference
-structure and per-temporal-layer search parameters:
+A "step" is one pass of the hot path over one 16-picture hierarchical mini-GOP of 3840x2160 pictures of BASELINE.json's
+configs[2] (4K 8-bit 4:2:0, enc-mode 8), processed in encode order with the real reference structure and
+per-temporal-layer search parameters; per picture:
     motion estimation (2 lists)  ->  transform / quantise / reconstruct every TU once (luma 32x32, chroma 16x16,
     prediction = list-0 reference at zero motion)  ->  deblocking of the base-layer picture (enc-mode 8 filters
     temporal layer 0 only).
@@ -13,17 +13,25 @@ structure and per-temporal-layer search parameters:
                 kernels, download of ME results, quantised coefficients + eob and (base layer) the filtered planes
   roofline      algorithmic bytes of the dominant kernel / its CUDA-event time, against the measured HBM peak
   cpu_baseline  the same pictures through the CPU implementation on the host cores: the reference's own functions
-                (oracle/_ref, kind "reference") or the oracle port (kind "port")
+                (oracle/_ref, kind "reference") on a native pinned thread pool, or the oracle port (kind "port")
+  check         two pictures of the end-to-end leg (one of them deblocked) compared, buffer by buffer, with the CPU arm
+  encoder       BASELINE.json's own metric: the reference application against the same objects with the GPU hot path
+                bound in (oracle/_ref/SvtVp9EncApp_ref vs SvtVp9EncApp_b200): fps as the application reports it
+                (first send_picture -> last packet, Source/App/EbAppProcessCmd.c:669-672), bitstream md5s
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--no-encoder] [--no-cpu]
 """
 import argparse
 import ctypes as C
+import hashlib
 import importlib
 import json
 import os
+import re
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -42,16 +50,15 @@ sharding = importlib.import_module("svt-vp9_b200.sharding")
 W4K, H4K = 3840, 2160
 N_SB = 60 * 34
 N_FRAMES = 17
+PICS_PER_STEP = 16
 ENCODE_ORDER = [16, 8, 4, 2, 1, 3, 6, 5, 7, 12, 10, 9, 11, 14, 13, 15]
 QINDEX = 180          # app default q 45 -> qindex (quantizer_to_qindex, VPX/vp9_quantize.c)
 LF_LEVEL = 30
 TU_ROWS, TU_COLS = H4K // 32, W4K // 32  # 67 x 120 luma 32x32 TUs; the last 16 luma / 8 chroma rows of the 2160 take smaller TUs
-N_TU_Y = TU_ROWS * TU_COLS
-N_TU_C = TU_ROWS * TU_COLS               # per chroma plane, 16x16
 # every sample of the picture belongs to exactly one TU: (plane 0 Y / 1 U / 2 V, tx_size, TU size, TUs per row, TU rows, first sample row)
 TU_PASSES = [(0, 3, 32, 120, 67, 0), (0, 2, 16, 240, 1, 2144), (1, 2, 16, 120, 67, 0), (1, 1, 8, 240, 1, 1072),
              (2, 2, 16, 120, 67, 0), (2, 1, 8, 240, 1, 1072)]
-METRIC = "encoded fps (hot path: motion estimation + transform/quant/recon + deblocking, 4K enc-mode 8)"
+METRIC = "pictures/s through the encode hot path (motion estimation + transform/quant/recon + deblocking; 4K, enc-mode 8 parameter set)"
 
 
 def refs_of(n):
@@ -133,7 +140,7 @@ class ClockSampler(threading.Thread):
             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits",
-                                          "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+                                          "-lms", "20"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([c.strip() for c in line.split(",")])
         except Exception:
@@ -165,7 +172,7 @@ class ClockSampler(threading.Thread):
 
 
 # ---------------------------------------------------------------------------------------------------------------------
-# CPU arm: the reference's own functions (oracle/_ref) or the oracle port, all host threads
+# CPU arm: the reference's own functions (oracle/_ref) on a native thread pool, or the oracle port
 # ---------------------------------------------------------------------------------------------------------------------
 def aligned(shape, dtype, align=64):
     """numpy array whose data pointer is 'align'-byte aligned (the reference's SIMD kernels use aligned loads on
@@ -183,109 +190,264 @@ def aligned_copy(a):
 
 
 class CpuPath:
-    def __init__(self, clip, threads):
+    """The bench workload on the host cores.  kind "reference": one call per mini-GOP into oracle/ref_path_driver.c's pinned
+    thread pool (super-block / transform-block granular tasks of all 16 pictures in one queue, deblocking as one task per
+    picture, as the reference runs it) -- every picture has its own result buffers, so the pictures of a mini-GOP overlap
+    freely.  kind "port" (no oracle/_ref): the oracle restatement, picture by picture, from a Python thread pool."""
+
+    def __init__(self, clip, threads, n_buffers=PICS_PER_STEP):
         import helpers as H
-        from concurrent.futures import ThreadPoolExecutor
         self.H, self.threads = H, threads
-        self.pool = ThreadPoolExecutor(threads)
         self.kind = "reference" if H.have_refdrv() else "port"
         self.pics = [frames.pa_planes(f[0]) for f in clip]
         self.structs = [frames.plane_structs(p) for p in self.pics]
         self.luma = [aligned_copy(f[0]) for f in clip]  # unpadded, aligned: source / prediction planes of the transform stage
         self.chroma = [(aligned_copy(f[1]), aligned_copy(f[2])) for f in clip]
         self.rows = H.quant_rows([QINDEX])
-        self.passes = []
-        for plane, ts, size, cols, rows, row0 in TU_PASSES:
-            w = W4K if plane == 0 else W4K // 2
-            n = cols * rows
-            self.passes.append((plane, ts, size, tu_jobs(w, 0, 0, n, size, w, cols, row0), [aligned((n, size, size), np.int16) for _ in range(3)],
-                                np.zeros(n, np.uint16)))
         self.lfm, self.thr = lf_masks_32x32(), H.lf_thresholds()
-        self.recon = [aligned((H4K, W4K), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8)]
-        self.out = np.zeros(N_SB * 85, dtype=api.ME_RESULT_DTYPE)
-        if self.kind == "reference":
-            self.L = H.refdrv(1)
-            self.me_handles = [self.L.refdrv_me_new() for _ in range(threads)]
-        else:
-            self.L = H.oracle()
         self.LfP = api.LfParams()
         self.LfP.width, self.LfP.height, self.LfP.mi_rows, self.LfP.mi_cols, self.LfP.y_only, self.LfP.filter_level = W4K, H4K, H4K // 8, W4K // 8, 0, LF_LEVEL
+        self.jobs = []
+        for plane, ts, size, cols, rows, row0 in TU_PASSES:
+            w = W4K if plane == 0 else W4K // 2
+            self.jobs.append(tu_jobs(w, 0, 0, cols * rows, size, w, cols, row0))
+        # result buffers of picture slot b
+        self.n_buffers = n_buffers
+        self.me_out = [np.zeros(N_SB * 85, dtype=api.ME_RESULT_DTYPE) for _ in range(n_buffers)]
+        self.q = [[aligned((cols * rows, size, size), np.int16) for _, _, size, cols, rows, _ in TU_PASSES] for _ in range(n_buffers)]
+        self.dq = [[aligned((cols * rows, size, size), np.int16) for _, _, size, cols, rows, _ in TU_PASSES] for _ in range(n_buffers)]
+        self.eob = [[np.zeros(cols * rows, np.uint16) for _, _, _, cols, rows, _ in TU_PASSES] for _ in range(n_buffers)]
+        self.recon = [[aligned((H4K, W4K), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8)]
+                      for _ in range(n_buffers)]
+        self.stage_cpu_s = [0.0, 0.0, 0.0]
+        if self.kind == "reference":
+            self.L = H.refdrv(1)
+            self.pool = self.L.refdrv_pool_new(threads, 1)
+            if not self.pool:
+                raise RuntimeError("refdrv_pool_new failed")
+        else:
+            from concurrent.futures import ThreadPoolExecutor
+            self.L = H.oracle()
+            self.tpool = ThreadPoolExecutor(threads)
+
+    def close(self):
+        if self.kind == "reference" and self.pool:
+            self.L.refdrv_pool_free(self.pool)
+            self.pool = None
+
+    def _picture_desc(self, d, n, b):
+        """fill RefdrvPicture d: picture n (display offset in the mini-GOP) into result slot b"""
+        P, (r0, r1) = me_params(n)
+        d.P = P
+        d.cur, d.ref0, d.ref1 = self.structs[n], self.structs[r0], self.structs[r1]
+        d.me_out = self.me_out[b].ctypes.data
+        d.n_pass = len(TU_PASSES)
+        for k, (plane, ts, size, cols, rows, row0) in enumerate(TU_PASSES):
+            src = self.luma[n] if plane == 0 else self.chroma[n][plane - 1]
+            pred = self.luma[r0] if plane == 0 else self.chroma[r0][plane - 1]
+            rec = self.recon[b][plane]
+            tp = d.passes[k]
+            tp.tx_size, tp.n, tp.jobs = ts, cols * rows, self.jobs[k].ctypes.data
+            tp.pl.src, tp.pl.src_stride, tp.pl.src_bytes = src.ctypes.data, src.shape[1], src.nbytes
+            tp.pl.pred, tp.pl.pred_stride, tp.pl.pred_bytes = pred.ctypes.data, pred.shape[1], pred.nbytes
+            tp.pl.recon, tp.pl.recon_stride, tp.pl.recon_bytes = rec.ctypes.data, rec.shape[1], rec.nbytes
+            tp.coeff, tp.qcoeff, tp.dqcoeff, tp.eob = None, self.q[b][k].ctypes.data, self.dq[b][k].ctypes.data, self.eob[b][k].ctypes.data
+        d.qrows = self.rows.ctypes.data
+        d.deblock = 1 if n == 16 else 0
+        d.lf = self.LfP
+        d.y, d.u, d.v = (r.ctypes.data for r in self.recon[b])
+        d.ys, d.cs = W4K, W4K // 2
+        d.lfm, d.lfm_stride, d.thr = self.lfm.ctypes.data, 60, self.thr.ctypes.data
+
+    def run(self, order):
+        """the pictures of 'order' (display offsets, encode order), picture j into result slot j"""
+        assert len(order) <= self.n_buffers
+        if self.kind != "reference":
+            for b, n in enumerate(order):
+                self._port_step(n, b)
+            return
+        H = self.H
+        arr = (H.RefdrvPicture * len(order))()
+        for b, n in enumerate(order):
+            self._picture_desc(arr[b], n, b)
+        cpu_s = (C.c_double * 3)()
+        rc = self.L.refdrv_pool_run(self.pool, arr, len(order), 4, 64, cpu_s)
+        if rc:
+            raise RuntimeError("refdrv_pool_run: %d" % rc)
+        for k in range(3):
+            self.stage_cpu_s[k] += cpu_s[k]
+
+    def minigop(self):
+        self.run(ENCODE_ORDER)
 
     def _split(self, n):
         chunk = (n + self.threads - 1) // self.threads
         return [(i, s, min(n, s + chunk)) for i, s in enumerate(range(0, n, chunk))]
 
-    def step(self, n):
+    def _port_step(self, n, b):
         H, L = self.H, self.L
         P, (r0, r1) = me_params(n)
         cur, s0, s1 = self.structs[n], self.structs[r0], self.structs[r1]
-        if self.kind == "reference":
-            list(self.pool.map(lambda a: L.refdrv_me_range(self.me_handles[a[0]], C.byref(P), cur, s0, s1, a[1], a[2], self.out.ctypes.data), self._split(N_SB)))
-        else:
-            list(self.pool.map(lambda a: L.svtb200_oracle_me_picture(C.byref(P), cur, s0, s1, self.out.ctypes.data, None, a[1], a[2]), self._split(N_SB)))
-        # transform / quantise / reconstruct: every TU of the three planes
-        for plane, ts, size, jobs, (c, q, dq), eob in self.passes:
+        out = self.me_out[b]
+        list(self.tpool.map(lambda a: L.svtb200_oracle_me_picture(C.byref(P), cur, s0, s1, out.ctypes.data, None, a[1], a[2]), self._split(N_SB)))
+        Lt = H.oracle_tx()
+        for k, (plane, ts, size, cols, rows, row0) in enumerate(TU_PASSES):
             src = self.luma[n] if plane == 0 else self.chroma[n][plane - 1]
             pred = self.luma[r0] if plane == 0 else self.chroma[r0][plane - 1]
-            rec = self.recon[plane]
-            pl = api.TxPlanes()
-            pl.src, pl.src_stride, pl.src_bytes = src.ctypes.data, src.shape[1], src.nbytes
-            pl.pred, pl.pred_stride, pl.pred_bytes = pred.ctypes.data, pred.shape[1], pred.nbytes
-            pl.recon, pl.recon_stride, pl.recon_bytes = rec.ctypes.data, rec.shape[1], rec.nbytes
-            if self.kind == "reference":
-                if len(jobs) < 2048:   # a few hundred small blocks: one call, the thread pool's dispatch would cost more than the work
-                    L.refdrv_txq(ts, 0, len(jobs), jobs.ctypes.data, C.byref(pl), self.rows.ctypes.data, c.ctypes.data, q.ctypes.data, dq.ctypes.data,
-                                 eob.ctypes.data)
-                else:
-                    list(self.pool.map(lambda a: L.refdrv_txq(ts, a[1], a[2], jobs.ctypes.data, C.byref(pl), self.rows.ctypes.data, c.ctypes.data,
-                                                              q.ctypes.data, dq.ctypes.data, eob.ctypes.data), self._split(len(jobs))))
-            else:
-                self._port_txq(ts, jobs, src, pred, rec, c, q, dq, eob)
+            rec, jobs, q, dq, eob = self.recon[b][plane], self.jobs[k], self.q[b][k], self.dq[b][k], self.eob[b][k]
+            N = size
+            scan = np.ascontiguousarray(H.scan_of(ts, 0)[0])
+
+            def work(a):
+                c = np.zeros((N, N), np.int16)
+                for i in range(a[1], a[2]):
+                    so, ro = int(jobs["src_offset"][i]), int(jobs["recon_offset"][i])
+                    sy, sx = divmod(so, src.shape[1])
+                    resid = np.ascontiguousarray(src[sy:sy + N, sx:sx + N].astype(np.int16) - pred[sy:sy + N, sx:sx + N].astype(np.int16))
+                    Lt.svtb200_oracle_fwd_txfm(ts, 0, 0, resid.ctypes.data, N, c.ctypes.data)
+                    Lt.svtb200_oracle_quantize(ts, c.ctypes.data, self.rows.ctypes.data, scan.ctypes.data, q[i].ctypes.data, dq[i].ctypes.data, eob[i:].ctypes.data)
+                    ry, rx = divmod(ro, rec.shape[1])
+                    blk = np.ascontiguousarray(pred[sy:sy + N, sx:sx + N])
+                    Lt.svtb200_oracle_inv_txfm_add(ts, 0, dq[i].ctypes.data, int(eob[i]), blk.ctypes.data, N)
+                    rec[ry:ry + N, rx:rx + N] = blk
+            list(self.tpool.map(work, self._split(len(jobs))))
         if n == 16:
-            if self.kind == "reference":
-                L.refdrv_deblock(C.byref(self.LfP), self.recon[0].ctypes.data, W4K, self.recon[1].ctypes.data, self.recon[2].ctypes.data, W4K // 2,
-                                 self.lfm.ctypes.data, 60, self.thr.ctypes.data)
-            else:
-                m = self.lfm.copy()
-                L.svtb200_oracle_deblock_picture(C.byref(self.LfP), self.recon[0].ctypes.data, W4K, self.recon[1].ctypes.data, self.recon[2].ctypes.data,
-                                                 W4K // 2, m.ctypes.data, 60, self.thr.ctypes.data)
+            m = self.lfm.copy()
+            L.svtb200_oracle_deblock_picture(C.byref(self.LfP), self.recon[b][0].ctypes.data, W4K, self.recon[b][1].ctypes.data, self.recon[b][2].ctypes.data,
+                                             W4K // 2, m.ctypes.data, 60, self.thr.ctypes.data)
 
-    def _port_txq(self, ts, jobs, src, pred, rec, c, q, dq, eob):
-        H = self.H
-        N = 4 << ts
-        scan, _ = H.scan_of(ts, 0)
-        scan = np.ascontiguousarray(scan)
-        Lt = H.oracle_tx()
+    def stage_share(self):
+        t = sum(self.stage_cpu_s)
+        return None if t <= 0 else {"motion_estimation": self.stage_cpu_s[0] / t, "transform_chain": self.stage_cpu_s[1] / t, "deblocking": self.stage_cpu_s[2] / t}
 
-        def work(a):
-            for i in range(a[1], a[2]):
-                so, ro = int(jobs["src_offset"][i]), int(jobs["recon_offset"][i])
-                sy, sx = divmod(so, src.shape[1])
-                resid = np.ascontiguousarray(src[sy:sy + N, sx:sx + N].astype(np.int16) - pred[sy:sy + N, sx:sx + N].astype(np.int16))
-                Lt.svtb200_oracle_fwd_txfm(ts, 0, 0, resid.ctypes.data, N, c[i].ctypes.data)
-                Lt.svtb200_oracle_quantize(ts, c[i].ctypes.data, self.rows.ctypes.data, scan.ctypes.data, q[i].ctypes.data, dq[i].ctypes.data, eob[i:].ctypes.data)
-                ry, rx = divmod(ro, rec.shape[1])
-                blk = np.ascontiguousarray(pred[sy:sy + N, sx:sx + N])
-                Lt.svtb200_oracle_inv_txfm_add(ts, 0, dq[i].ctypes.data, int(eob[i]), blk.ctypes.data, N)
-                rec[ry:ry + N, rx:rx + N] = blk
-        list(self.pool.map(work, self._split(len(jobs))))
+
+# ---------------------------------------------------------------------------------------------------------------------
+# whole-encoder record: BASELINE.json's metric through the reference's own application
+# ---------------------------------------------------------------------------------------------------------------------
+REF_DIR = os.path.join(ROOT, "oracle", "_ref")
+APP_REF, APP_B200 = os.path.join(REF_DIR, "SvtVp9EncApp_ref"), os.path.join(REF_DIR, "SvtVp9EncApp_b200")
+
+
+def run_encoder(app, yuv, out, w, h, n_frames, n_buffered, mode, tune, env_extra=None, timeout=600):
+    """One run of the reference application (or of the same objects with the GPU path bound in).  Frames are preloaded into
+    RAM by the application itself (-nb), fps is its own "Average Speed" (frames / time from the first send_picture to the last
+    packet); stdout is unbuffered because at 3840x2160 the reference aborts inside its own teardown after the summary."""
+    import helpers as H
+    env = dict(os.environ)
+    env["LD_LIBRARY_PATH"] = ":".join(p for p in (os.path.dirname(H.cudart_path()), env.get("LD_LIBRARY_PATH", "")) if p)
+    env.update(env_extra or {})
+    cmd = [app, "-i", yuv, "-w", str(w), "-h", str(h), "-n", str(n_frames), "-nb", str(n_buffered), "-enc-mode", str(mode), "-tune", str(tune),
+           "-q", "45", "-fps", "60", "-b", out]
+    if shutil.which("stdbuf"):
+        cmd = ["stdbuf", "-o0"] + cmd
+    t0 = time.perf_counter()
+    try:
+        r = subprocess.run(cmd, env=env, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, timeout=timeout)
+        txt, rc = r.stdout.decode(errors="replace"), r.returncode
+    except subprocess.TimeoutExpired as e:
+        txt, rc = (e.stdout or b"").decode(errors="replace"), -9
+    wall = time.perf_counter() - t0
+    m = re.search(r"Average Speed:\s*([0-9.]+)\s*fps", txt)
+    m2 = re.search(r"Total Encoding Time:\s*([0-9.]+)\s*ms", txt)
+    md5 = hashlib.md5(open(out, "rb").read()).hexdigest() if os.path.exists(out) and os.path.getsize(out) else None
+    return {"fps": float(m.group(1)) if m else None, "encode_ms": float(m2.group(1)) if m2 else None, "wall_s": round(wall, 2), "rc": rc, "md5": md5,
+            "tail": None if m else txt[-300:]}
+
+
+def gpu_report(path):
+    try:
+        return dict((l.split()[0], int(l.split()[1])) for l in open(path) if len(l.split()) == 2)
+    except Exception:
+        return None
+
+
+def encoder_record(local_rank, world, clip4k, budget_s=150.0):
+    """configs[1] (1080p, enc-mode 8, 300 frames) and configs[2] (4K, enc-mode 8; a bounded number of frames) through the
+    application, reference build against drop-in build, one process per rank when world > 1 (configs[4]: concurrent streams,
+    one per GPU).  Returns the per-rank record; the caller aggregates over ranks."""
+    if not (os.path.exists(APP_REF) and os.path.exists(APP_B200)):
+        return {"unavailable": "oracle/_ref applications not built"}
+    t_start = time.perf_counter()
+    d = tempfile.mkdtemp(prefix="svtb200_enc_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    rec = {"host_threads": len(os.sched_getaffinity(0))}
+    try:
+        w, h, sd, k, g, a, b, m, noise, distinct = synth.CONFIGS["B"]
+        clipb = synth.make_clip(w, h, distinct, sd + local_rank, k, g, a, b, m, noise)
+        yuv_b = os.path.join(d, "b.yuv")
+        synth.write_yuv(yuv_b, clipb)
+        del clipb
+        cases = [("1080p_m8", yuv_b, 1920, 1080, 300, 40)]
+        if world == 1 and clip4k is not None:
+            yuv_c = os.path.join(d, "c.yuv")
+            synth.write_yuv(yuv_c, clip4k[:16])
+            cases.append(("4k_m8", yuv_c, 3840, 2160, int(os.environ.get("SVTB200_BENCH_4K_FRAMES", "130")), 16))
+        for name, yuv, cw, ch, n_frames, n_buf in cases:
+            if time.perf_counter() - t_start > budget_s:
+                rec[name] = {"skipped": "time budget of the encoder record used up"}
+                continue
+            rep = os.path.join(d, "rep.txt")
+            ref = run_encoder(APP_REF, yuv, os.path.join(d, "ref.ivf"), cw, ch, n_frames, n_buf, 8, 1)
+            gpu = run_encoder(APP_B200, yuv, os.path.join(d, "b200.ivf"), cw, ch, n_frames, n_buf, 8, 1,
+                              {"SVT_VP9_GPU": str(local_rank), "SVT_VP9_GPU_REPORT": rep})
+            one = {"frames": n_frames, "distinct_frames": n_buf, "reference": ref, "b200": gpu, "b200_gpu_report": gpu_report(rep),
+                   "bitstream_identical": bool(ref["md5"]) and ref["md5"] == gpu["md5"],
+                   "speedup": (gpu["fps"] / ref["fps"]) if ref["fps"] and gpu["fps"] else None}
+            if name == "1080p_m8" and world == 1 and time.perf_counter() - t_start < budget_s:
+                # host-bound ceiling: the same encode with motion estimation served from a table recorded by a previous run
+                # (zero-cost ME: no GPU, no CPU kernel) -- what the pipeline around the seam allows at best
+                tab = os.path.join(d, "me_table.bin")
+                run_encoder(APP_B200, yuv, os.path.join(d, "rec.ivf"), cw, ch, n_frames, n_buf, 8, 1, {"SVT_VP9_GPU": str(local_rank), "SVT_VP9_ME_RECORD": tab})
+                if os.path.exists(tab):
+                    rp = run_encoder(APP_B200, yuv, os.path.join(d, "rep.ivf"), cw, ch, n_frames, n_buf, 8, 1, {"SVT_VP9_GPU": "off", "SVT_VP9_ME_REPLAY": tab})
+                    one["me_free_ceiling"] = {"fps": rp["fps"], "bitstream_identical": rp["md5"] == ref["md5"],
+                                              "note": "motion estimation replayed from a table (no ME work anywhere): the bound the host pipeline around seam S1 sets"}
+            rec[name] = one
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+    rec["seconds"] = round(time.perf_counter() - t_start, 1)
+    return rec
+
+
+def numa_bind(local_rank):
+    """Run this rank (and place its pinned buffers, first-touch) on the host cores next to its GPU; returns the affinity before."""
+    before = os.sched_getaffinity(0)
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open("/sys/bus/pci/devices/%s/numa_node" % bdf).read())
+        if node < 0:
+            return before, None
+        cpus = set()
+        for part in open("/sys/devices/system/node/node%d/cpulist" % node).read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+        cpus &= before
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return before, node
+    except Exception:
+        pass
+    return before, None
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=320)
-    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200")
     ap.add_argument("--verify", action="store_true", help="after the end-to-end leg, recompute its last pictures synchronously on one queue and compare every downloaded byte")
+    ap.add_argument("--no-encoder", action="store_true", help="skip the whole-encoder record")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline and check legs")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     config = {"workload": "configs[2]: 4K (3840x2160) 8-bit yuv420p, enc-mode 8 (tune 1 parameter set): per picture ME (2 lists) + one "
                           "transform/quantise/reconstruct pass over every TU (luma 32x32, chroma 16x16; 16x16 / 8x8 for the last 16 rows; q 45) + deblocking on the "
-                          "base-layer picture; 16-picture hierarchical mini-GOP in encode order",
-              "pictures_per_step": 1,
+                          "base-layer picture; step = one 16-picture hierarchical mini-GOP in encode order",
+              "pictures_per_step": PICS_PER_STEP,
               "queues": "motion estimation (followed by the three small edge-row transform launches) on the context's first compute queue, the "
                         "picture-sized transform launches + deblocking on its second (they belong to different pictures in the encoder); value = "
                         "CUDA events around the K steps with both queues joined inside the timed region",
@@ -300,21 +462,24 @@ def main():
         times, t_all = [], time.perf_counter()
         for i in range(args.warmup + args.steps):
             t0 = time.perf_counter()
-            cpu.step(ENCODE_ORDER[i % 16])
+            cpu.minigop()
             if i >= args.warmup:
                 times.append(time.perf_counter() - t0)
-            if time.perf_counter() - t_all > 200 and len(times) >= 3:
+            else:
+                cpu.stage_cpu_s = [0.0, 0.0, 0.0]
+            if time.perf_counter() - t_all > 200 and len(times) >= 2:
                 break
             if time.perf_counter() - t_all > 200 and i < args.warmup:
                 args.warmup = i  # bounded run: cut the warm-up short
         steps = len(times)
-        v = steps / sum(times) if times else 0.0
+        v = PICS_PER_STEP * steps / sum(times) if times else 0.0
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": v, "unit": "fps", "n_gpus": args.gpus, "steps": steps,
-                          "warmup": args.warmup, "ms_per_step": 1000.0 / v if v else None, "higher_is_better": True, "scaling": "weak",
+                          "warmup": args.warmup, "ms_per_step": 1000.0 * PICS_PER_STEP / v if v else None, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
-                          "cpu_baseline": {"value": v, "unit": "fps", "cores": ncores, "kind": cpu.kind,
-                                           "sample": "one whole 4K picture per step (all 2040 SBs, all TUs), mini-GOP encode order, %d host threads" % ncores},
+                          "cpu_baseline": {"value": v, "unit": "fps", "cores": ncores, "kind": cpu.kind, "stage_share_of_cpu_time": cpu.stage_share(),
+                                           "sample": "whole 4K mini-GOPs (16 pictures, all 2040 SBs and all TUs each), one native call per mini-GOP, %d pinned host threads" % ncores},
                           "e2e": {"value": v, "unit": "fps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        cpu.close()
         return
 
     import torch
@@ -322,6 +487,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
+    affinity_before, numa_node = numa_bind(local_rank) if world > 1 else (os.sched_getaffinity(0), None)
+    config["host_binding"] = ("rank bound to NUMA node %d (the GPU's), pinned buffers allocated after binding" % numa_node) if numa_node is not None else "none"
     import helpers as H
     ctx = api.Context(local_rank)
     ctx.register_scans(H.vp9_tables())
@@ -363,7 +530,7 @@ def main():
     # one job table per TU pass: luma addresses the padded resident plane, chroma the packed buffers
     pass_n = [cols * rows for _, _, _, cols, rows, _ in TU_PASSES]
     pass_cb = [n * size * size * 2 for n, (_, _, size, _, _, _) in zip(pass_n, TU_PASSES)]   # bytes of one coefficient array
-    d_jobs = [to_dev(tu_jobs(sy, frames.FULL_PAD, frames.FULL_PAD, n, size, W4K, cols, row0) if plane == 0 else
+    d_jobs = [to_dev(tu_jobs(sy, dplane[0].origin_x, dplane[0].origin_y, n, size, W4K, cols, row0) if plane == 0 else
                      tu_jobs(W4K // 2, 0, 0, n, size, W4K // 2, cols, row0))
               for n, (plane, _, size, cols, rows, row0) in zip(pass_n, TU_PASSES)]
     d_rows = to_dev(H.quant_rows([QINDEX]))
@@ -400,11 +567,6 @@ def main():
     # a different (earlier) picture than the one being motion-estimated, and their CTAs fill the tail of the ME grid.
     ctx.select_compute(api.COMPUTE2)
     stream2 = torch.cuda.ExternalStream(L.svtb200_stream(h), device=torch.device("cuda", local_rank))
-    # Motion estimation of consecutive pictures is independent (the reference runs it several pictures ahead on separate
-    # threads): with SVTB200_BENCH_ME_QUEUES=2 it alternates between the first and the third compute queue, so that the next
-    # picture's CTAs could fill the tail of the current picture's grid (2040 CTAs = 3.45 waves of 4 x 148).  Measured: no gain
-    # (0.403 vs 0.400 ms per step) -- with the transform queue beside it the SMs are already busy, the step is bound by the
-    # instruction work of the kernels, not by their tails -- so one motion-estimation queue is the default.
     ctx.select_compute(api.COMPUTE3)
     stream3 = torch.cuda.ExternalStream(L.svtb200_stream(h), device=torch.device("cuda", local_rank))
     ctx.select_compute(api.COMPUTE)
@@ -528,23 +690,25 @@ def main():
 
     L._bound = True
     ctx.L.svtb200_deblock_picture_dev.argtypes = [C.c_void_p, C.POINTER(api.LfParams), C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+    n_timed, n_warm = args.steps * PICS_PER_STEP, args.warmup * PICS_PER_STEP
     sampler = ClockSampler(local_rank)
-    for i in range(args.warmup):
+    sampler.start()
+    for i in range(n_warm):
         kernels(i, False, i % NSLOT)
     ctx.sync()
     barrier()
-    sampler.start()
+    del sampler.rows[:]   # keep only the samples taken under load: the timed legs from here on
     e0, e1 = ev(), ev()
     launches0 = ctx.launches()
     e0.record(stream)
     ctx.fence(api.COMPUTE, api.COMPUTE2)   # the other queues start inside the timed region ...
     ctx.fence(api.COMPUTE, api.COMPUTE3)
     t_host = time.perf_counter()
-    for i in range(args.steps):
-        kernels(args.warmup + i, True, (args.warmup + i) % NSLOT)
+    for i in range(n_timed):
+        kernels(n_warm + i, True, (n_warm + i) % NSLOT)
     t_host = time.perf_counter() - t_host
     if os.environ.get("SVTB200_BENCH_DEBUG"):
-        sys.stderr.write("value leg: host issue time %.3f ms/step\n" % (1000.0 * t_host / args.steps))
+        sys.stderr.write("value leg: host issue time %.3f ms/picture\n" % (1000.0 * t_host / n_timed))
     ctx.fence(api.COMPUTE2, api.COMPUTE)   # ... and end inside it
     ctx.fence(api.COMPUTE3, api.COMPUTE)
     e1.record(stream)
@@ -569,18 +733,19 @@ def main():
         iso_ms["txq_kernel"] += e[2].elapsed_time(e[3]); iso_n["txq_kernel"] += 1
         if n == 16:
             iso_ms["lf_row_kernel"] += e[3].elapsed_time(e[4]); iso_n["lf_row_kernel"] += 1
-    for i in range(min(args.warmup, 4)):
+    for i in range(min(n_warm, 8)):
         step_e2e(i)
+    ctx.sync()
     barrier()
     t0 = time.perf_counter()
     t_issue = 0.0
-    for i in range(args.steps):
+    for i in range(n_timed):
         ti = time.perf_counter()
-        step_e2e(args.warmup + i)
+        step_e2e(n_warm + i)
         t_issue += time.perf_counter() - ti
     ctx.sync()
     if os.environ.get("SVTB200_BENCH_DEBUG"):
-        sys.stderr.write("e2e host time in step_e2e (issue + waits): %.3f ms/step\n" % (1000.0 * t_issue / args.steps))
+        sys.stderr.write("e2e host time in step_e2e (issue + waits): %.3f ms/picture\n" % (1000.0 * t_issue / n_timed))
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1000.0
     sampler.stop()
@@ -588,7 +753,7 @@ def main():
     if args.verify:
         # the pipelined leg (4 queues, 3 slots) must have produced exactly what a synchronous single-queue run produces
         checked = 0
-        for i in range(args.warmup + args.steps - NSLOT, args.warmup + args.steps):
+        for i in range(n_warm + n_timed - NSLOT, n_warm + n_timed):
             slot, n = i % NSLOT, ENCODE_ORDER[i % 16]
             got = [h_me[slot].numpy().copy()] + [h_q[slot][k].numpy().copy() for k in range(len(TU_PASSES))]
             got += [h_eob[slot][k].numpy().copy() for k in range(len(TU_PASSES))]
@@ -610,8 +775,8 @@ def main():
         sys.stderr.write("verify: ok (%d result bytes of the last %d pipelined pictures equal the synchronous run)\n" % (checked, NSLOT))
 
     # every rank processed its own pictures (svt-vp9_b200/sharding.py): time = max over ranks, units = sum over ranks
-    ms_res, units = sharding.agree_step(ms_res, args.steps, device="cuda")
-    ms_e2e, _ = sharding.agree_step(ms_e2e, args.steps, device="cuda")
+    ms_res, units = sharding.agree_step(ms_res, n_timed, device="cuda")
+    ms_e2e, _ = sharding.agree_step(ms_e2e, n_timed, device="cuda")
     value = units / (ms_res / 1000.0)
     e2e = units / (ms_e2e / 1000.0)
     h2d = W4K * H4K + 2 * csize  # the picture area of the three planes (padding and the 1/16 plane are made on the device)
@@ -642,32 +807,88 @@ def main():
                              "traffic": traffic.get(k), "ms_per_picture_alone": iso, "achieved_gbs_alone": per_pic / (iso / 1000.0) / 1e9 if iso else None,
                              "frac_alone": per_pic / (iso / 1000.0) / 1e9 / peak if iso else None,
                              "share_alone": per_step_alone[k] / sum(per_step_alone.values())}
-    launches_dom = n_me if dom == "me_sb_kernel" else (len(TU_PASSES) * n_me if dom == "txq_kernel" else max(1, args.steps // 16))
+    launches_dom = n_me if dom == "me_sb_kernel" else (len(TU_PASSES) * n_me if dom == "txq_kernel" else max(1, n_timed // 16))
     roof = {"bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"],
             "traffic": traffic.get(dom), "kernel": dom, "alg_bytes_per_launch": alg[dom] / launches_dom,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)", "per_kernel": per_kernel}
 
-    if rank == 0:
-        cpu_line = None
+    # ---- check leg: two more pictures through the SAME end-to-end path (picture 16 -- deblocked -- and picture 8), then every
+    # downloaded buffer against the CPU arm (the reference's own functions when oracle/_ref is present)
+    check, cpu_line = None, None
+    os.sched_setaffinity(0, affinity_before)
+    if rank == 0 and not args.no_cpu:
+        cpu = CpuPath(clip, ncores, n_buffers=PICS_PER_STEP if world == 1 else 2)
+        base = ((n_warm + n_timed + 15) // 16) * 16        # i = base -> picture 16, base + 1 -> picture 8
+        got = []
+        for i in (base, base + 1):
+            step_e2e(i)
+            ctx.sync()
+            slot, n = i % NSLOT, ENCODE_ORDER[i % 16]
+            got.append((n, h_me[slot].numpy().copy(), [h_q[slot][k].numpy().copy() for k in range(len(TU_PASSES))],
+                        [h_eob[slot][k].numpy().copy() for k in range(len(TU_PASSES))], [h_rec[slot][k].numpy().copy() for k in range(3)] if n == 16 else None))
+        cpu.run([g[0] for g in got])
+        bad, compared = [], 0
+        for b, (n, me, q, eob, rec) in enumerate(got):
+            ok = H.me_equal(me.view(api.ME_RESULT_DTYPE), cpu.me_out[b], 2)
+            compared += me.nbytes
+            if not ok.all():
+                bad.append("picture %d: %d ME partitions differ" % (n, int((~ok).sum())))
+            for k in range(len(TU_PASSES)):
+                compared += q[k].nbytes + eob[k].nbytes
+                if not np.array_equal(q[k].view(np.int16), cpu.q[b][k].reshape(-1)):
+                    bad.append("picture %d: quantised coefficients of TU pass %d differ" % (n, k))
+                if not np.array_equal(eob[k].view(np.uint16), cpu.eob[b][k]):
+                    bad.append("picture %d: eob of TU pass %d differ" % (n, k))
+            if rec is not None:
+                for k in range(3):
+                    compared += rec[k].nbytes
+                    if not np.array_equal(rec[k], cpu.recon[b][k].reshape(-1)):
+                        bad.append("picture %d: filtered plane %d differs" % (n, k))
+        check = {"pictures": [g[0] for g in got], "bytes_compared": compared, "against": cpu.kind, "identical": not bad, "mismatches": bad[:8]}
+        if bad:
+            sys.stderr.write("check: MISMATCH " + "; ".join(bad[:8]) + "\n")
         if world == 1:
-            cpu = CpuPath(clip, ncores)
-            sample = [16, 8, 4, 2, 1, 3]
-            for n in sample[:2]:          # thread pool / page-fault warm-up, untimed
-                cpu.step(n)
-            t0 = time.perf_counter()
-            reps = 3
-            for _ in range(reps):
-                for n in sample:
-                    cpu.step(n)
+            cpu.minigop()          # page-fault / cache warm-up, untimed
+            cpu.stage_cpu_s = [0.0, 0.0, 0.0]
+            t0, reps = time.perf_counter(), 0
+            while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 64):
+                cpu.minigop()
+                reps += 1
             dt = time.perf_counter() - t0
-            cpu_line = {"value": reps * len(sample) / dt, "unit": "fps", "cores": ncores, "kind": cpu.kind,
-                        "sample": "%d whole 4K pictures (3 x temporal layers 0,1,2,3,4,4) through ME + transform/quant/recon (+ deblock on the "
-                                  "base-layer picture), %d host threads, %.1f s" % (reps * len(sample), ncores, dt)}
+            cpu_line = {"value": reps * PICS_PER_STEP / dt, "unit": "fps", "cores": ncores, "kind": cpu.kind, "stage_share_of_cpu_time": cpu.stage_share(),
+                        "sample": "%d whole 4K mini-GOPs (16 pictures each: ME + transform/quant/recon, deblocking of the base-layer picture), one native "
+                                  "call per mini-GOP on %d pinned host threads, %.1f s" % (reps, ncores, dt)}
+        cpu.close()
+        del cpu
+
+    # ---- BASELINE.json's own metric through the application (every rank encodes its own stream when world > 1)
+    encoder = None
+    if not args.no_encoder:
+        enc = encoder_record(local_rank, world, clip if world == 1 else None)
+        if world > 1:
+            allenc = [None] * world
+            dist.all_gather_object(allenc, enc)
+        else:
+            allenc = [enc]
+        if rank == 0:
+            encoder = {"streams": world, "per_stream": allenc[0] if world == 1 else None}
+            if world > 1:
+                agg = {}
+                for arm in ("reference", "b200"):
+                    fps = [(e.get("1080p_m8") or {}).get(arm, {}).get("fps") for e in allenc]
+                    agg[arm + "_fps_sum"] = sum(fps) if all(fps) else None
+                    agg[arm + "_fps_each"] = fps
+                agg["bitstreams_identical"] = all((e.get("1080p_m8") or {}).get("bitstream_identical") for e in allenc)
+                agg["speedup"] = (agg["b200_fps_sum"] / agg["reference_fps_sum"]) if agg["b200_fps_sum"] and agg["reference_fps_sum"] else None
+                agg["note"] = "configs[4]: %d concurrent 1080p enc-mode 8 streams, one per GPU, reference run then drop-in run" % world
+                encoder["concurrent_1080p_m8"] = agg
+
+    if rank == 0:
         print(json.dumps({"metric": METRIC, "value": value, "unit": "fps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                           "ms_per_step": ms_res / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                           "dtype": "u8", "data": "synthetic", "config": config, "clocks": sampler.summary(),
-                          "e2e": {"value": e2e, "unit": "fps", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
-                          "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_line}))
+                          "e2e": {"value": e2e, "unit": "fps", "h2d_bytes_per_step": h2d * PICS_PER_STEP, "d2h_bytes_per_step": d2h * PICS_PER_STEP},
+                          "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu_line, "check": check, "encoder": encoder}))
     ctx.close()
     if world > 1:
         dist.destroy_process_group()

@@ -44,6 +44,8 @@ extern "C" {
 #define SVTB200_ENOMEM (-3)   /* device or pinned allocation failed */
 #define SVTB200_ECUDA (-4)    /* a launch or copy failed; see svtb200_last_error() */
 #define SVTB200_ENOENT (-5)   /* unknown picture id */
+#define SVTB200_EPARTIAL (-6) /* a host-pointer call failed AFTER it had begun to overwrite its in/out buffer (deblocking write-back):
+                                 the caller's CPU fallback would not start from the original data any more */
 
 typedef struct SvtB200Ctx SvtB200Ctx;
 
@@ -352,7 +354,11 @@ int svtb200_build_masks(SvtB200Ctx *ctx, int32_t mi_rows, int32_t mi_cols, const
 int svtb200_build_masks_dev(SvtB200Ctx *ctx, int32_t mi_rows, int32_t mi_cols, const SvtB200LfModeInfo *mi_dev, int32_t mi_stride,
                             SvtB200LfMask *lfm_dev, int32_t lfm_stride);
 
-/* In-place eb_vp9_loop_filter_frame on HOST planes y/u/v (pointers at picture origin). */
+/* In-place eb_vp9_loop_filter_frame on HOST planes y/u/v (pointers at picture origin).  Errors up to and including the kernel launch
+ * leave the planes untouched (the caller may filter on the CPU instead); a failure while the filtered planes are being copied back
+ * returns SVTB200_EPARTIAL: the planes hold a mixture and must not be filtered again.
+ * The wavefront scratch of the _dev variant exists once per compute queue: pictures on DIFFERENT queues of one context may be in
+ * flight together, launches on one queue are ordered by the queue. */
 int svtb200_deblock_picture(SvtB200Ctx *ctx, const SvtB200LfParams *p, uint8_t *y, int32_t y_stride,
                             uint8_t *u, uint8_t *v, int32_t uv_stride, const SvtB200LfMask *lfm,
                             int32_t lfm_stride /* SBs per row */, const SvtB200LfThresh thr[64]);

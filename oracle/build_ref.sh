@@ -58,12 +58,25 @@ gcc -shared -o $OUT/libSvtVp9Enc_refdrv.so $OUT/obj/*.o $OUT/ref_path_driver.o -
 echo "build_ref: path driver ok"
 
 # ---- drop-in flavour: the same reference objects with the two seam functions bound to libsvtvp9_b200.so
-# (svt-vp9_b200/shim/svtb200_wrap.c); used by the encoder-level parity test on the GPU box
+# (svt-vp9_b200/shim/svtb200_wrap.c); used by the encoder-level parity test on the GPU box.
+# Shape of the reference's own library (Source/Lib/CMakeLists.txt / CMakeLists.txt:61): SONAME libSvtVp9Enc.so.1, symbol map
+# Source/API/EbApi.version (SVT_VP9_0 { global: Eb*; eb*; local: *; }) -- read where it lies at link time, not copied.
+# eb_vp9_deinit_encoder is provided by the shim (it drops the GPU state first); the reference's definition stays in the link
+# under another name: objcopy renames the symbol in a COPY of the compiled object, the source is untouched.
 if [ -f $HERE/../svt-vp9_b200/libsvtvp9_b200.so ]; then
+  D=$OUT/dropin; mkdir -p $D/obj
+  for o in $OUT/obj/*.o; do
+    case $(basename $o) in
+      Codec_EbEncHandle.o) objcopy --redefine-sym eb_vp9_deinit_encoder=svtb200_real_eb_vp9_deinit_encoder $o $D/obj/$(basename $o) ;;
+      *) ln -f $o $D/obj/$(basename $o) 2>/dev/null || cp $o $D/obj/$(basename $o) ;;
+    esac
+  done
   gcc $CF $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/../svt-vp9_b200/shim/svtb200_wrap.c -o $OUT/svtb200_wrap.o
-  gcc -shared -o $OUT/libSvtVp9Enc_b200.so $OUT/obj/*.o $OUT/svtb200_wrap.o -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm \
-      -Wl,--wrap=motion_estimate_sb -Wl,--wrap=eb_vp9_loop_filter_frame -Wl,-rpath,'$ORIGIN/../../svt-vp9_b200'
+  gcc -shared -o $D/libSvtVp9Enc.so.1 $D/obj/*.o $OUT/svtb200_wrap.o -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm \
+      -Wl,-soname,libSvtVp9Enc.so.1 -Wl,--version-script=$REF/Source/API/EbApi.version \
+      -Wl,--wrap=motion_estimate_sb -Wl,--wrap=eb_vp9_loop_filter_frame -Wl,-rpath,'$ORIGIN/../../../svt-vp9_b200'
   gcc -std=gnu99 -O2 -w -I$OUT/inc -I$REF/Source/API $REF/Source/App/*.c -o $OUT/SvtVp9EncApp_b200 \
-      -L$OUT -lSvtVp9Enc_b200 -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../svt-vp9_b200'
+      -L$D -l:libSvtVp9Enc.so.1 -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN/dropin' -Wl,-rpath,'$ORIGIN/../../svt-vp9_b200'
+  rm -rf $D/obj $OUT/libSvtVp9Enc_b200.so
   echo "build_ref: drop-in flavour ok"
 fi

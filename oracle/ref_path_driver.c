@@ -10,7 +10,10 @@
  *                               buffer set-up of eb_vp9_motion_estimation_kernel (EbMotionEstimationProcess.c:978-1035)
  *   refdrv_txq(...)             the kernel sequence of perform_coding_loop (EbEncDecProcess.c:365-587)
  *   refdrv_deblock(...)         eb_vp9_loop_filter_frame (vp9_loopfilter.c:1521)
+ *   refdrv_pool_run(...)        a mini-GOP of pictures through the three calls above on a native, pinned thread pool
+ *                               (the CPU arm of bench.py: one call per step, no interpreter in the timed region)
  */
+#define _GNU_SOURCE
 #define RTCD_C /* the two headers then provide the static setup_rtcd_internal*; built with -fcommon so that the
                   function-pointer variables merge with the definitions in the reference objects */
 #include <stdio.h>
@@ -355,4 +358,178 @@ int refdrv_intra_predict(int mode, int tx_size, int have_left, int have_top, uin
     refdrv_intra_fn f = mode == 0 ? (flavour ? s_dc : c_dc)[!!have_left][!!have_top][tx_size] : (flavour ? s_tab : c_tab)[mode][tx_size];
     f(dst, stride, above, left);
     return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------ CPU arm of bench.py
+ * A native thread pool that runs the hot path of a whole mini-GOP with the reference's own functions: the unit of work is
+ * a small range of super-blocks (motion estimation) or transform blocks (perform_coding_loop chain); one picture's
+ * deblocking is one task (eb_vp9_loop_filter_frame is a single-threaded call in the reference as well) that becomes
+ * runnable when the transform tasks of its picture have completed; idle threads keep pulling the tasks of the other
+ * pictures meanwhile, as the reference's picture-level pipeline would.  One call per mini-GOP: no interpreter, no
+ * per-stage barrier across pictures.  Threads are pinned round-robin to the CPUs the process may run on. */
+#include <pthread.h>
+#include <sched.h>
+#include <time.h>
+
+typedef struct {
+    int32_t              tx_size, n;
+    const SvtB200TxJob  *jobs;
+    SvtB200TxPlanes      pl;
+    int16_t             *coeff, *qcoeff, *dqcoeff;
+    uint16_t            *eob;
+} RefdrvTuPass;
+
+typedef struct {
+    SvtB200MeParams        P;
+    const SvtB200Plane    *cur, *ref0, *ref1; /* three planes each */
+    SvtB200MeCuResult     *me_out;            /* n_sb * 85 */
+    int32_t                n_pass;
+    RefdrvTuPass           pass[8];
+    const SvtB200QuantRow *qrows;
+    int32_t                deblock;
+    SvtB200LfParams        lf;
+    uint8_t               *y, *u, *v;
+    int32_t                ys, cs;
+    const SvtB200LfMask   *lfm;
+    int32_t                lfm_stride;
+    const SvtB200LfThresh *thr;
+} RefdrvPicture;
+
+typedef struct { int32_t kind, pic, pass, begin, end; } PoolTask; /* kind 0 ME, 1 TU, 2 LF */
+
+typedef struct RefPool {
+    int                  n_threads, stop;
+    pthread_t           *th;
+    void               **me;       /* one RefMe per worker */
+    pthread_mutex_t      mu;
+    pthread_cond_t       cv_go, cv_done;
+    unsigned             generation;
+    int                  running;
+    const RefdrvPicture *pics;
+    int                  n_pics;
+    PoolTask            *tasks;
+    int                  n_tasks, cap_tasks;
+    int                  next;     /* atomic */
+    int                 *tu_left;  /* per picture: transform tasks not yet finished (atomic) */
+    double               cpu_s[3]; /* per kind, summed over threads */
+} RefPool;
+
+typedef struct { RefPool *p; int idx; } PoolArg;
+
+static double pool_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+static void pool_do(RefPool *p, int w, const PoolTask *t, double acc[3]) {
+    const RefdrvPicture *pic = &p->pics[t->pic];
+    const double t0 = pool_now();
+    if (t->kind == 0) {
+        refdrv_me_range(p->me[w], &pic->P, pic->cur, pic->ref0, pic->ref1, t->begin, t->end, pic->me_out);
+    } else if (t->kind == 1) {
+        const RefdrvTuPass *s = &pic->pass[t->pass];
+        refdrv_txq(s->tx_size, t->begin, t->end, s->jobs, &s->pl, pic->qrows, s->coeff, s->qcoeff, s->dqcoeff, s->eob);
+        __atomic_sub_fetch(&p->tu_left[t->pic], 1, __ATOMIC_ACQ_REL);
+    } else {
+        while (__atomic_load_n(&p->tu_left[t->pic], __ATOMIC_ACQUIRE) > 0) sched_yield(); /* earlier tasks: already claimed by someone */
+        refdrv_deblock(&pic->lf, pic->y, pic->ys, pic->u, pic->v, pic->cs, pic->lfm, pic->lfm_stride, pic->thr);
+    }
+    acc[t->kind] += pool_now() - t0;
+}
+
+static void *pool_worker(void *a) {
+    PoolArg *pa = (PoolArg *)a;
+    RefPool *p = pa->p;
+    const int w = pa->idx;
+    unsigned seen = 0;
+    free(pa);
+    for (;;) {
+        pthread_mutex_lock(&p->mu);
+        while (!p->stop && p->generation == seen) pthread_cond_wait(&p->cv_go, &p->mu);
+        if (p->stop) { pthread_mutex_unlock(&p->mu); return NULL; }
+        seen = p->generation;
+        pthread_mutex_unlock(&p->mu);
+        double acc[3] = {0, 0, 0};
+        for (;;) {
+            const int i = __atomic_fetch_add(&p->next, 1, __ATOMIC_RELAXED);
+            if (i >= p->n_tasks) break;
+            pool_do(p, w, &p->tasks[i], acc);
+        }
+        pthread_mutex_lock(&p->mu);
+        for (int k = 0; k < 3; k++) p->cpu_s[k] += acc[k];
+        if (--p->running == 0) pthread_cond_signal(&p->cv_done);
+        pthread_mutex_unlock(&p->mu);
+    }
+}
+
+void *refdrv_pool_new(int threads, int pin) {
+    if (!g_init || threads < 1) return NULL;
+    RefPool *p = (RefPool *)calloc(1, sizeof(RefPool));
+    p->n_threads = threads;
+    p->th = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
+    p->me = (void **)calloc((size_t)threads, sizeof(void *));
+    for (int i = 0; i < threads; i++) p->me[i] = refdrv_me_new(); /* the constructors share a global allocation map: single-threaded here */
+    pthread_mutex_init(&p->mu, NULL);
+    pthread_cond_init(&p->cv_go, NULL);
+    pthread_cond_init(&p->cv_done, NULL);
+    cpu_set_t allowed;
+    int cpus[1024], n_cpus = 0;
+    if (pin && sched_getaffinity(0, sizeof(allowed), &allowed) == 0)
+        for (int c = 0; c < 1024 && c < CPU_SETSIZE; c++) if (CPU_ISSET(c, &allowed)) cpus[n_cpus++] = c;
+    for (int i = 0; i < threads; i++) {
+        PoolArg *a = (PoolArg *)malloc(sizeof(PoolArg));
+        a->p = p; a->idx = i;
+        pthread_create(&p->th[i], NULL, pool_worker, a);
+        if (n_cpus) {
+            cpu_set_t one;
+            CPU_ZERO(&one); CPU_SET(cpus[i % n_cpus], &one);
+            pthread_setaffinity_np(p->th[i], sizeof(one), &one);
+        }
+    }
+    return p;
+}
+
+static void pool_push(RefPool *p, int kind, int pic, int pass, int begin, int end) {
+    if (p->n_tasks == p->cap_tasks) {
+        p->cap_tasks = p->cap_tasks ? 2 * p->cap_tasks : 4096;
+        p->tasks = (PoolTask *)realloc(p->tasks, (size_t)p->cap_tasks * sizeof(PoolTask));
+    }
+    PoolTask t = {kind, pic, pass, begin, end};
+    p->tasks[p->n_tasks++] = t;
+}
+
+/* Runs the pictures (in the order given: encode order) and returns when all are done; stage_cpu_s = thread-seconds spent in
+ * motion estimation / transform chain / deblocking.  me_chunk / tu_chunk = super-blocks / transform blocks per task. */
+int refdrv_pool_run(void *h, const RefdrvPicture *pics, int n_pics, int me_chunk, int tu_chunk, double stage_cpu_s[3]) {
+    RefPool *p = (RefPool *)h;
+    if (!p || n_pics < 1) return -1;
+    p->pics = pics; p->n_pics = n_pics; p->n_tasks = 0;
+    p->tu_left = (int *)realloc(p->tu_left, (size_t)n_pics * sizeof(int));
+    for (int i = 0; i < n_pics; i++) {
+        const RefdrvPicture *pic = &pics[i];
+        const int n_sb = ((pic->P.luma_width + 63) / 64) * ((pic->P.luma_height + 63) / 64);
+        if (pic->me_out) for (int s = 0; s < n_sb; s += me_chunk) pool_push(p, 0, i, 0, s, s + me_chunk < n_sb ? s + me_chunk : n_sb);
+        int n_tu = 0;
+        for (int k = 0; k < pic->n_pass; k++)
+            for (int s = 0; s < pic->pass[k].n; s += tu_chunk, n_tu++) pool_push(p, 1, i, k, s, s + tu_chunk < pic->pass[k].n ? s + tu_chunk : pic->pass[k].n);
+        p->tu_left[i] = n_tu;
+        if (pic->deblock) pool_push(p, 2, i, 0, 0, 0);
+    }
+    pthread_mutex_lock(&p->mu);
+    p->next = 0; p->running = p->n_threads;
+    for (int k = 0; k < 3; k++) p->cpu_s[k] = 0;
+    p->generation++;
+    pthread_cond_broadcast(&p->cv_go);
+    while (p->running) pthread_cond_wait(&p->cv_done, &p->mu);
+    if (stage_cpu_s) for (int k = 0; k < 3; k++) stage_cpu_s[k] = p->cpu_s[k];
+    pthread_mutex_unlock(&p->mu);
+    return 0;
+}
+
+void refdrv_pool_free(void *h) {
+    RefPool *p = (RefPool *)h;
+    if (!p) return;
+    pthread_mutex_lock(&p->mu);
+    p->stop = 1;
+    pthread_cond_broadcast(&p->cv_go);
+    pthread_mutex_unlock(&p->mu);
+    for (int i = 0; i < p->n_threads; i++) pthread_join(p->th[i], NULL);
+    free(p->tasks); free(p->tu_left); free(p->th); free(p->me); free(p);
 }

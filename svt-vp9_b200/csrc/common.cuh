@@ -11,7 +11,7 @@
 #include <vector>
 #include "../../include/svtb200.h"
 
-#define SVTB200_MARKER_RING 256
+#define SVTB200_MARKER_RING 1024
 
 struct DevPlane {
     uint8_t *buf = nullptr;
@@ -20,7 +20,7 @@ struct DevPlane {
 struct DevPicture {
     DevPlane    pl[3];            /* full, quarter, sixteenth */
     cudaEvent_t ready = nullptr;  /* recorded on the upload stream after the picture's copies / front-end kernels */
-    cudaEvent_t used = nullptr;   /* recorded on the compute stream after the last kernel that reads the picture */
+    cudaEvent_t used[3] = {nullptr, nullptr, nullptr}; /* one per compute queue: recorded after the last kernel on that queue that reads the picture */
 };
 
 struct ScanTable {
@@ -91,8 +91,10 @@ static inline cudaStream_t svtb200_pick_stream(SvtB200Ctx *c, int which) {
 }
 /* a kernel about to read picture p on the compute stream: wait for its upload; afterwards note the use */
 static inline void svtb200_pic_acquire(SvtB200Ctx *c, DevPicture &p) { if (p.ready) cudaStreamWaitEvent(c->stream, p.ready, 0); }
+static inline int svtb200_compute_index(const SvtB200Ctx *c) { return c->stream == c->compute[1] ? 1 : c->stream == c->compute[2] ? 2 : 0; }
 static inline void svtb200_pic_release(SvtB200Ctx *c, DevPicture &p) {
-    if (!p.used) cudaEventCreateWithFlags(&p.used, cudaEventDisableTiming);
-    cudaEventRecord(p.used, c->stream);
+    cudaEvent_t &e = p.used[svtb200_compute_index(c)];
+    if (!e) cudaEventCreateWithFlags(&e, cudaEventDisableTiming);
+    cudaEventRecord(e, c->stream);
 }
 #endif

@@ -37,7 +37,7 @@ void svtb200_destroy(SvtB200Ctx *c) {
     for (auto &kv : c->pics) {
         for (int i = 0; i < 3; i++) if (kv.second.pl[i].buf) cudaFree(kv.second.pl[i].buf);
         if (kv.second.ready) cudaEventDestroy(kv.second.ready);
-        if (kv.second.used) cudaEventDestroy(kv.second.used);
+        for (int q = 0; q < 3; q++) if (kv.second.used[q]) cudaEventDestroy(kv.second.used[q]);
     }
     for (int i = 0; i < SVTB200_MARKER_RING; i++) if (c->markers[i]) cudaEventDestroy(c->markers[i]);
     svtb200_lf_release(c);
@@ -77,11 +77,13 @@ int svtb200_select_compute(SvtB200Ctx *c, int which) {
 /* ---- the three in-order queues of a context and the markers that order work between them ---- */
 int svtb200_memcpy_h2d_async(SvtB200Ctx *c, void *d, const void *h, size_t n) {
     if (!c) return SVTB200_EINVAL;
+    cudaSetDevice(c->device);
     SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->up));
     return SVTB200_OK;
 }
 int svtb200_memcpy_d2h_async(SvtB200Ctx *c, void *h, const void *d, size_t n) {
     if (!c) return SVTB200_EINVAL;
+    cudaSetDevice(c->device);
     SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->down));
     return SVTB200_OK;
 }
@@ -97,7 +99,10 @@ int svtb200_marker(SvtB200Ctx *c, int stream, uint64_t *ticket) {
 }
 static int marker_event(SvtB200Ctx *c, uint64_t ticket, cudaEvent_t *e) {
     if (ticket == 0 || ticket >= c->next_ticket) return SVTB200_EINVAL;
-    if (c->next_ticket - ticket > SVTB200_MARKER_RING) { *e = nullptr; return SVTB200_OK; } /* recycled: long since reached */
+    if (c->next_ticket - ticket > SVTB200_MARKER_RING) { /* its event has been reused for a newer marker: no ordering can be promised any more */
+        c->err = "marker ticket too old (more than SVTB200_MARKER_RING markers ago)";
+        return SVTB200_EINVAL;
+    }
     *e = c->markers[ticket % SVTB200_MARKER_RING];
     return SVTB200_OK;
 }
@@ -157,14 +162,18 @@ void svtb200_dev_free(SvtB200Ctx *c, void *p) { if (c && p) { cudaSetDevice(c->d
 
 int svtb200_memcpy_h2d(SvtB200Ctx *c, void *d, const void *h, size_t n) {
     if (!c) return SVTB200_EINVAL;
-    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->stream));
-    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    cudaStream_t s;
+    { std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device); s = c->stream; }
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s));
+    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(s));
     return SVTB200_OK;
 }
 int svtb200_memcpy_d2h(SvtB200Ctx *c, void *h, const void *d, size_t n) {
     if (!c) return SVTB200_EINVAL;
-    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, c->stream));
-    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    cudaStream_t s;
+    { std::lock_guard<std::recursive_mutex> g(c->mu); cudaSetDevice(c->device); s = c->stream; }
+    SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s));
+    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(s));
     return SVTB200_OK;
 }
 
@@ -186,7 +195,7 @@ static int upload_plane(SvtB200Ctx *c, const SvtB200Plane *src, DevPlane *dst) {
 }
 /* uploads run on the upload queue: after every kernel that still reads the picture's previous contents, and
  * followed by the event the compute queue waits on before it touches the new contents */
-static void upload_begin(SvtB200Ctx *c, DevPicture &p) { if (p.used) cudaStreamWaitEvent(c->up, p.used, 0); }
+static void upload_begin(SvtB200Ctx *c, DevPicture &p) { for (int q = 0; q < 3; q++) if (p.used[q]) cudaStreamWaitEvent(c->up, p.used[q], 0); }
 static int upload_end(SvtB200Ctx *c, DevPicture &p) {
     if (!p.ready) SVTB200_CUDA_CHECK(c, cudaEventCreateWithFlags(&p.ready, cudaEventDisableTiming));
     SVTB200_CUDA_CHECK(c, cudaEventRecord(p.ready, c->up));
@@ -324,7 +333,7 @@ int svtb200_picture_release(SvtB200Ctx *c, uint64_t pic_id) {
     cudaStreamSynchronize(c->up); cudaStreamSynchronize(c->compute[0]); cudaStreamSynchronize(c->compute[1]); cudaStreamSynchronize(c->compute[2]);
     for (int i = 0; i < 3; i++) if (it->second.pl[i].buf) cudaFree(it->second.pl[i].buf);
     if (it->second.ready) cudaEventDestroy(it->second.ready);
-    if (it->second.used) cudaEventDestroy(it->second.used);
+    for (int q = 0; q < 3; q++) if (it->second.used[q]) cudaEventDestroy(it->second.used[q]);
     c->pics.erase(it);
     return SVTB200_OK;
 }

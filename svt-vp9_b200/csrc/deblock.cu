@@ -2,8 +2,11 @@
 #include "common.cuh"
 #include "deblock_kernel.cuh"
 
+/* wavefront scratch (row ticket counter + per-row progress words): one set per context AND compute queue, so that two pictures
+ * being filtered on different queues of a context never share a counter; launches on one queue are ordered by the queue itself */
 struct LfScratch { int32_t *ticket = nullptr, *done = nullptr; size_t done_n = 0; int32_t gen = 0; };
-static std::map<SvtB200Ctx *, LfScratch> g_lf;
+struct LfScratchSet { LfScratch q[3]; };
+static std::map<SvtB200Ctx *, LfScratchSet> g_lf;
 static std::mutex g_lf_mu;
 static unsigned long long *g_lf_trace; /* tools only */
 extern "C" void svtb200_lf_set_trace(void *dev) { g_lf_trace = (unsigned long long *)dev; }
@@ -13,8 +16,10 @@ void svtb200_lf_release(SvtB200Ctx *c) {
     std::lock_guard<std::mutex> g(g_lf_mu);
     auto it = g_lf.find(c);
     if (it == g_lf.end()) return;
-    if (it->second.ticket) cudaFree(it->second.ticket);
-    if (it->second.done) cudaFree(it->second.done);
+    for (int q = 0; q < 3; q++) {
+        if (it->second.q[q].ticket) cudaFree(it->second.q[q].ticket);
+        if (it->second.q[q].done) cudaFree(it->second.q[q].done);
+    }
     g_lf.erase(it);
 }
 
@@ -29,7 +34,7 @@ static int lf_launch(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y, int ys
     if (A.sbs_w > 1023) return SVTB200_EINVAL;
     const size_t n = (size_t)A.sbs_h; /* one progress word (in a 128-byte line of its own) per super-block row */
     LfScratch *S;
-    { std::lock_guard<std::mutex> g(g_lf_mu); S = &g_lf[c]; }
+    { std::lock_guard<std::mutex> g(g_lf_mu); S = &g_lf[c].q[svtb200_compute_index(c)]; }
     if (S->done_n < n) {
         if (S->done) cudaFree(S->done);
         if (!S->ticket && cudaMalloc((void **)&S->ticket, 4) != cudaSuccess) { cudaGetLastError(); return SVTB200_ENOMEM; }
@@ -86,12 +91,19 @@ int svtb200_deblock_picture(SvtB200Ctx *c, const SvtB200LfParams *p, uint8_t *y,
     SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(dt, thr, 64 * sizeof(SvtB200LfThresh), cudaMemcpyHostToDevice, c->stream));
     rc = lf_launch(c, p, dy, W, du, dv, W / 2, dm, lfm_stride, dt);
     if (rc) return rc;
-    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(y, ys, dy, W, W, H, cudaMemcpyDeviceToHost, c->stream));
+    /* from here on filtered samples land in the caller's planes: a failure can no longer be answered with "filter it on the CPU" */
+#define LF_WRITEBACK_CHECK(call)                                                                                   \
+    do {                                                                                                           \
+        cudaError_t e_ = (call);                                                                                   \
+        if (e_ != cudaSuccess) { c->err = std::string("deblock write-back: ") + cudaGetErrorString(e_); return SVTB200_EPARTIAL; } \
+    } while (0)
+    LF_WRITEBACK_CHECK(cudaMemcpy2DAsync(y, ys, dy, W, W, H, cudaMemcpyDeviceToHost, c->stream));
     if (!p->y_only) {
-        SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(u, cs, du, W / 2, W / 2, H / 2, cudaMemcpyDeviceToHost, c->stream));
-        SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(v, cs, dv, W / 2, W / 2, H / 2, cudaMemcpyDeviceToHost, c->stream));
+        LF_WRITEBACK_CHECK(cudaMemcpy2DAsync(u, cs, du, W / 2, W / 2, H / 2, cudaMemcpyDeviceToHost, c->stream));
+        LF_WRITEBACK_CHECK(cudaMemcpy2DAsync(v, cs, dv, W / 2, W / 2, H / 2, cudaMemcpyDeviceToHost, c->stream));
     }
-    SVTB200_CUDA_CHECK(c, cudaStreamSynchronize(c->stream));
+    LF_WRITEBACK_CHECK(cudaStreamSynchronize(c->stream));
+#undef LF_WRITEBACK_CHECK
     return SVTB200_OK;
 }
 

@@ -31,6 +31,7 @@ extern "C" int svtb200_inter_predict_batch_dev(SvtB200Ctx *c, const SvtB200PredB
     if (!c || n < 0 || (n && !blocks_dev)) return SVTB200_EINVAL;
     if (!n) return SVTB200_OK;
     std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
     const int cap = (c->sm_count > 0 ? c->sm_count : 148) * 10; /* 20 KB of shared memory per CTA: ten resident per SM */
     pred_kernel<<<n < cap ? n : cap, PRED_THREADS, 0, c->stream>>>(blocks_dev, n);
     c->launches++;
@@ -47,6 +48,7 @@ extern "C" int svtb200_inter_predict_batch(SvtB200Ctx *c, const SvtB200PredBlock
         if (b.compound && (!b.ref[1] || b.subpel_x[1] > 15 || b.subpel_y[1] > 15)) return SVTB200_EINVAL;
     }
     std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
     SvtB200PredBlock *d = (SvtB200PredBlock *)pred_upload_desc(c, blocks, (size_t)n * sizeof(SvtB200PredBlock));
     if (!d) return c->err.empty() ? SVTB200_ENOMEM : SVTB200_ECUDA;
     int rc = svtb200_inter_predict_batch_dev(c, d, n);
@@ -90,6 +92,7 @@ extern "C" int svtb200_intra_predict_batch(SvtB200Ctx *c, const SvtB200IntraBloc
     for (int i = 0; i < n; i++)
         if (!blocks[i].above || !blocks[i].left || !blocks[i].dst || blocks[i].mode > 9 || blocks[i].tx_size > 3) return SVTB200_EINVAL;
     std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
     SvtB200IntraBlock *d = (SvtB200IntraBlock *)pred_upload_desc(c, blocks, (size_t)n * sizeof(SvtB200IntraBlock));
     if (!d) return c->err.empty() ? SVTB200_ENOMEM : SVTB200_ECUDA;
     const int cap = (c->sm_count > 0 ? c->sm_count : 148) * 16;
@@ -120,6 +123,7 @@ extern "C" int svtb200_full_distortion_batch_dev(SvtB200Ctx *c, int tx_size, int
     if (!c || tx_size < 0 || tx_size > 3 || n < 0 || (n && (!coeff || !recon_coeff || !eob || !dist))) return SVTB200_EINVAL;
     if (!n) return SVTB200_OK;
     std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
     const int nn = (4 << tx_size) * (4 << tx_size);
     full_dist_kernel<<<(n + 7) / 8, 256, 0, c->stream>>>(nn, n, coeff, recon_coeff, eob, dist);
     c->launches++;

@@ -48,3 +48,40 @@ def me_params_1080p_m8(width=1920, height=1080, temporal_layer=4, num_lists=2, r
         P.hme_level2_search_area_in_width[i], P.hme_level2_search_area_in_height[i] = 4, 2
     P.search_area_width, P.search_area_height = 16, 9
     return P
+
+
+# hme_level_0_search_area_multiplier_x/y[hierarchical_levels = 3][temporal layer] (EbDefinitions.h:994, :1003; tune 0 encodes with 3 levels)
+HME_L0_MULT_3LEVELS = [200, 140, 100, 70]
+
+# temporal layer of picture n (1..8) inside an 8-picture mini-GOP with 3 hierarchical levels
+MINIGOP8_TL = [3, 2, 3, 1, 3, 2, 3, 0]
+
+
+def me_params_480p_m9(width=640, height=480, temporal_layer=4, num_lists=2, ref_poc=(0, 2)):
+    """config A: 640x480, enc-mode 9, tune 1 (read back with oracle/dump_me_params.py 640 480 9 1): 2x2 quadrants of 16x12 at level 0
+    (scaled per layer), 4x4 / 4x2 refinements (widened to 8 columns) at levels 1 / 2, 16x7 full-pel area, sub-sampled-SAD
+    refinement gated by su_pel_enable, no 8x8 refinement."""
+    P = me_params_1080p_m8(width, height, temporal_layer, num_lists, ref_poc)
+    P.hme_level0_total_search_area_width, P.hme_level0_total_search_area_height = 32, 24
+    for i in range(2):
+        P.hme_level0_search_area_in_width[i], P.hme_level0_search_area_in_height[i] = 16, 12
+    P.search_area_width, P.search_area_height = 16, 7
+    return P
+
+
+def me_params_4k_m5_tune0(width=3840, height=2160, temporal_layer=3, num_lists=2, ref_poc=(0, 2)):
+    """config D: 4K, enc-mode 5, tune 0 (3 hierarchical levels; read back with oracle/dump_me_params.py 3840 2160 5 0): 2x2 quadrants of
+    64x32 at level 0 (128x64 in all, scaled 200 / 140 / 100 / 70 % per layer: the wide areas are searched in row stripes), levels 1 / 2
+    on, 16x16 full-pel area; 8x8 partitions refined except in the top layer, whose pictures run without sub-pel search
+    (use_subpel_flag 0 -> fractional_search_model 2)."""
+    P = me_params_1080p_m8(width, height, temporal_layer, num_lists, ref_poc)
+    P.hierarchical_levels = 3
+    P.hme_level0_total_search_area_width, P.hme_level0_total_search_area_height = 128, 64
+    for i in range(2):
+        P.hme_level0_search_area_in_width[i], P.hme_level0_search_area_in_height[i] = 64, 32
+    P.hme_l0_multiplier_x = P.hme_l0_multiplier_y = HME_L0_MULT_3LEVELS[temporal_layer]
+    P.search_area_width, P.search_area_height = 16, 16
+    top = temporal_layer == 3
+    P.fractional_search_model = 2 if top else 1
+    P.cu8x8_mode = 1 if top else 0
+    return P

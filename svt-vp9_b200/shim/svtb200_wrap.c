@@ -2,18 +2,27 @@
  * svtb200_wrap.c -- the reference-side binding of libsvtvp9_b200.so, as INTEGRATION.md describes it: link-time wrappers
  * around the two non-static seam functions of the UNMODIFIED reference objects
  *
- *     gcc -shared -o libSvtVp9Enc.so <reference objects> svtb200_wrap.o -lsvtvp9_b200 \
+ *     gcc -shared -o libSvtVp9Enc.so.1 <reference objects> svtb200_wrap.o -lsvtvp9_b200 \
  *         -Wl,--wrap=motion_estimate_sb -Wl,--wrap=eb_vp9_loop_filter_frame
  *
  *   S1  motion_estimate_sb()        Source/Lib/Codec/EbMotionEstimation.c:4524 (call site EbMotionEstimationProcess.c:1037)
  *   S2  eb_vp9_loop_filter_frame()  Source/Lib/VPX/vp9_loopfilter.c:1521       (call site EbEncDecProcess.c:5678)
+ *   teardown: eb_vp9_deinit_encoder() (Source/Lib/Codec/EbEncHandle.c:1711) is exported from here; the reference's own
+ *       definition is kept under the name svtb200_real_eb_vp9_deinit_encoder (objcopy --redefine-sym on a COPY of the
+ *       compiled object, oracle/build_ref.sh) and called after the GPU state of that encoder instance has been dropped.
  *
  * Compiled only against the reference's headers and include/svtb200.h; no reference code is copied.  The reference calls
  * motion_estimate_sb() once per super-block from up to 20 ME threads; the GPU works per picture: the first thread that
- * reaches a picture uploads what is not resident yet, runs svtb200_me_picture() for all super-blocks and publishes the
- * results, every call then copies its own super-block's 85 entries into pcs->me_results.  If no GPU context can be created
- * the wrappers fall through to the reference functions (__real_*), so the library still works on a CPU-only box.
- * Environment: SVT_VP9_GPU=<device index> (default 0), SVT_VP9_GPU=off disables the GPU path.
+ * reaches a picture uploads what is not resident yet (per-picture locks: uploads of different pictures do not wait for each
+ * other), queues svtb200_me_picture_dev() and the download of the results on the context's queues WITHOUT blocking inside the
+ * library, then waits for that picture's marker; calls for other pictures queue their own work behind it meanwhile.  Every call
+ * then copies its own super-block's 85 entries into pcs->me_results.  If no GPU context can be created the wrappers fall
+ * through to the reference functions (__real_*), so the library still works on a CPU-only box.
+ *
+ * Environment: SVT_VP9_GPU=<device index> (default 0), SVT_VP9_GPU=off disables the GPU path; SVT_VP9_GPU_REPORT=<file> counters
+ * at exit.  Measurement aids (tools / bench.py): SVT_VP9_ME_RECORD=<file> writes every picture's ME results to a table at exit;
+ * SVT_VP9_ME_REPLAY=<file> serves motion estimation from such a table (no ME work at all: the speed the pipeline around the
+ * seam would reach with a zero-cost motion estimation).
  */
 #define _GNU_SOURCE
 #include <pthread.h>
@@ -23,28 +32,111 @@
 #include <time.h>
 
 #include "svtb200_ref_glue.h"
+#include "EbEncHandle.h"
 
 EbErrorType __real_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_index, uint32_t sb_origin_x, uint32_t sb_origin_y,
                                       MeContext *me, EbPictureBufferDesc *input);
 void __real_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_filter_level, int y_only, int partial_frame);
 
-static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
+static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;    /* slot table, residency table, counters */
+static pthread_mutex_t g_queue_mu = PTHREAD_MUTEX_INITIALIZER; /* one picture at a time issues its kernel + download (queue order) */
+static pthread_mutex_t g_lf_mu = PTHREAD_MUTEX_INITIALIZER; /* deblocking: page-lock table + the (library-serialised) call */
 static pthread_cond_t  g_cv = PTHREAD_COND_INITIALIZER;
 static SvtB200Ctx     *g_ctx;    /* picture residency + motion estimation */
 static SvtB200Ctx     *g_ctx_lf; /* deblocking: its own queues and lock, so that a picture being filtered never waits behind (or blocks) the
                                     motion estimation of the pictures after it -- they are different pipeline stages in the reference too */
 static int             g_state; /* 0 untried, 1 ready, -1 unavailable */
-static unsigned long   g_me_pictures, g_me_sbs, g_lf_pictures, g_fallbacks;
-static double          g_t_resident, g_t_me, g_t_lf; /* seconds spent in uploads / svtb200_me_picture / svtb200_deblock_picture */
+static unsigned long   g_me_pictures, g_me_sbs, g_lf_pictures, g_fallbacks, g_replayed;
+static double          g_t_resident, g_t_me, g_t_lf; /* seconds spent in uploads / waiting for ME results / svtb200_deblock_picture */
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
+
+/* ------------------------------------------------------------------------------------------------ record / replay */
+typedef struct { uint64_t picture_number; uint32_t n_sb, rc_mode; SvtB200MeCuResult *res; uint32_t *rcme; } TabEntry;
+#define TAB_MAX 65536
+static TabEntry *g_tab;
+static size_t    g_tab_n, g_tab_cap;
+static int       g_replay; /* table loaded: serve ME from it */
+static const char *g_record_path;
+
+static void table_put(uint64_t picture_number, int n_sb, int rc_mode, const SvtB200MeCuResult *res, const uint32_t *rcme) { /* g_mu held */
+    if (!g_tab) { g_tab_cap = TAB_MAX; g_tab = (TabEntry *)calloc(g_tab_cap, sizeof(TabEntry)); } /* never moved: readers hold pointers into it */
+    if (g_tab_n == g_tab_cap) return;
+    TabEntry *e = &g_tab[g_tab_n++];
+    e->picture_number = picture_number; e->n_sb = (uint32_t)n_sb; e->rc_mode = (uint32_t)rc_mode;
+    e->res = (SvtB200MeCuResult *)malloc((size_t)n_sb * 85 * sizeof(SvtB200MeCuResult));
+    e->rcme = (uint32_t *)malloc((size_t)n_sb * sizeof(uint32_t));
+    memcpy(e->res, res, (size_t)n_sb * 85 * sizeof(SvtB200MeCuResult));
+    memcpy(e->rcme, rcme, (size_t)n_sb * sizeof(uint32_t));
+}
+/* CPU-path recording (no GPU): one super-block of the reference's own results */
+static void table_put_sb(PictureParentControlSet *pcs, uint32_t sb_index) {
+    SequenceControlSet *scs = (SequenceControlSet *)pcs->sequence_control_set_wrapper_ptr->object_ptr;
+    const uint32_t n_sb = (uint32_t)(((scs->luma_width + 63) / 64) * ((scs->luma_height + 63) / 64));
+    pthread_mutex_lock(&g_mu);
+    TabEntry *e = NULL;
+    for (size_t i = g_tab_n; i-- > 0;) if (g_tab[i].picture_number == pcs->picture_number) { e = &g_tab[i]; break; }
+    if (!e) {
+        if (!g_tab) { g_tab_cap = TAB_MAX; g_tab = (TabEntry *)calloc(g_tab_cap, sizeof(TabEntry)); }
+        if (g_tab_n == g_tab_cap) { pthread_mutex_unlock(&g_mu); return; }
+        e = &g_tab[g_tab_n++];
+        e->picture_number = pcs->picture_number; e->n_sb = n_sb; e->rc_mode = scs->static_config.rate_control_mode;
+        e->res = (SvtB200MeCuResult *)calloc((size_t)n_sb * 85, sizeof(SvtB200MeCuResult));
+        e->rcme = (uint32_t *)calloc(n_sb, sizeof(uint32_t));
+    }
+    pthread_mutex_unlock(&g_mu);
+    for (int i = 0; i < 85; i++) {
+        const MeCuResults *m = &pcs->me_results[sb_index][i];
+        SvtB200MeCuResult *o = &e->res[(size_t)sb_index * 85 + i];
+        o->x_mv_l0 = m->x_mv_l0; o->y_mv_l0 = m->y_mv_l0; o->x_mv_l1 = m->x_mv_l1; o->y_mv_l1 = m->y_mv_l1;
+        o->total_me_candidate_index = m->total_me_candidate_index;
+        for (int k = 0; k < 3; k++) { o->cand[k].distortion = m->distortion_direction[k].distortion; o->cand[k].direction = m->distortion_direction[k].direction; }
+    }
+    if (e->rc_mode) e->rcme[sb_index] = pcs->rcme_distortion[sb_index];
+}
+static void table_write(void) {
+    if (!g_record_path || !g_tab_n) return;
+    FILE *f = fopen(g_record_path, "wb");
+    if (!f) return;
+    uint64_t n = g_tab_n;
+    fwrite(&n, 8, 1, f);
+    for (size_t i = 0; i < g_tab_n; i++) {
+        const TabEntry *e = &g_tab[i];
+        fwrite(&e->picture_number, 8, 1, f); fwrite(&e->n_sb, 4, 1, f); fwrite(&e->rc_mode, 4, 1, f);
+        fwrite(e->res, sizeof(SvtB200MeCuResult), (size_t)e->n_sb * 85, f);
+        fwrite(e->rcme, 4, e->n_sb, f);
+    }
+    fclose(f);
+}
+static void table_read(const char *path) {
+    FILE *f = fopen(path, "rb");
+    uint64_t n = 0;
+    if (!f) return;
+    if (fread(&n, 8, 1, f) == 1 && n < (1u << 24)) {
+        const uint64_t cap = 2 * n + 1024; /* indexed by picture number: pictures without ME (intra) leave holes */
+        g_tab = (TabEntry *)calloc((size_t)cap, sizeof(TabEntry));
+        for (uint64_t i = 0; i < n; i++) {
+            TabEntry e;
+            if (fread(&e.picture_number, 8, 1, f) != 1 || fread(&e.n_sb, 4, 1, f) != 1 || fread(&e.rc_mode, 4, 1, f) != 1) break;
+            e.res = (SvtB200MeCuResult *)malloc((size_t)e.n_sb * 85 * sizeof(SvtB200MeCuResult));
+            e.rcme = (uint32_t *)malloc((size_t)e.n_sb * sizeof(uint32_t));
+            if (fread(e.res, sizeof(SvtB200MeCuResult), (size_t)e.n_sb * 85, f) != (size_t)e.n_sb * 85 || fread(e.rcme, 4, e.n_sb, f) != e.n_sb) break;
+            if (e.picture_number < cap) g_tab[e.picture_number] = e; /* indexed by picture number for the lock-free lookup */
+            g_tab_n++;
+        }
+        g_replay = g_tab_n > 0;
+        g_tab_cap = (size_t)cap;
+    }
+    fclose(f);
+}
 
 static void report(void) {
     const char *p = getenv("SVT_VP9_GPU_REPORT");
+    table_write();
     if (!p) return;
     FILE *f = fopen(p, "w");
     if (!f) return;
-    fprintf(f, "state %d\nme_pictures %lu\nme_sbs %lu\nlf_pictures %lu\nfallbacks %lu\nlaunches %llu\n", g_state, g_me_pictures, g_me_sbs,
-            g_lf_pictures, g_fallbacks, g_ctx ? (unsigned long long)(svtb200_launch_count(g_ctx) + svtb200_launch_count(g_ctx_lf)) : 0ull);
+    fprintf(f, "state %d\nme_pictures %lu\nme_sbs %lu\nlf_pictures %lu\nfallbacks %lu\nreplayed_sbs %lu\nlaunches %llu\n", g_state, g_me_pictures, g_me_sbs,
+            g_lf_pictures, g_fallbacks, g_replayed, g_ctx ? (unsigned long long)(svtb200_launch_count(g_ctx) + svtb200_launch_count(g_ctx_lf)) : 0ull);
     fprintf(f, "ms_upload %d\nms_me %d\nms_lf %d\n", (int)(1e3 * g_t_resident), (int)(1e3 * g_t_me), (int)(1e3 * g_t_lf));
     fclose(f);
 }
@@ -73,8 +165,11 @@ static void *warm_up(void *arg) {
 }
 __attribute__((constructor)) static void svtb200_wrap_init(void) {
     pthread_t th;
+    const char *rp = getenv("SVT_VP9_ME_REPLAY");
+    g_record_path = getenv("SVT_VP9_ME_RECORD");
+    if (rp) table_read(rp);
     setenv("SVTB200_BLOCKING_SYNC", "1", 0); /* the encoder keeps every core busy: do not spin while the GPU works */
-    if (pthread_create(&th, NULL, warm_up, NULL) == 0) pthread_detach(th);
+    if (!g_replay && pthread_create(&th, NULL, warm_up, NULL) == 0) pthread_detach(th);
 }
 
 /* ------------------------------------------------------------------------------------------------------------ S1 */
@@ -87,35 +182,51 @@ typedef struct {
     SvtB200MeParams          P;
     SvtB200MeCuResult       *res;   /* pinned, n_sb * 85 */
     uint32_t                *rcme;  /* pinned, n_sb */
+    SvtB200MeCuResult       *d_res; /* device twins */
+    uint32_t                *d_rcme;
     size_t                   cap_sb;
 } MeSlot;
 static MeSlot g_slots[MAX_IN_FLIGHT];
 
-/* device residency of the picture-analysis reference objects: id = object address, tag = display number of its contents */
+/* device residency of the picture-analysis reference objects: id = object address, tag = display number of its contents, inst = the
+ * encoder instance (its EncodeContext) the object belongs to -- eb_vp9_deinit_encoder drops that instance's entries, so that a later
+ * encoder in the same process whose buffers land on the same addresses never matches a stale picture */
 #define MAX_RESIDENT 256
-static struct { const void *obj; uint64_t poc; int valid; } g_res[MAX_RESIDENT];
+typedef struct { const void *obj, *inst; uint64_t poc; int valid, locked; void *reg[3]; pthread_mutex_t mu; } ResEntry;
+static ResEntry g_res[MAX_RESIDENT];
+static pthread_once_t g_res_once = PTHREAD_ONCE_INIT;
+static void res_init(void) { for (int i = 0; i < MAX_RESIDENT; i++) pthread_mutex_init(&g_res[i].mu, NULL); }
 
-static int ensure_resident(const EbPaReferenceObject *o, uint64_t poc, int want_quarter) {
-    int free_i = -1;
+static int ensure_resident(const EbPaReferenceObject *o, uint64_t poc, const void *inst, int want_quarter) {
+    int idx = -1, fresh = 0;
+    pthread_once(&g_res_once, res_init);
+    pthread_mutex_lock(&g_mu);
     for (int i = 0; i < MAX_RESIDENT; i++) {
-        if (g_res[i].valid && g_res[i].obj == (const void *)o) {
-            if (g_res[i].poc == poc) return SVTB200_OK;
-            free_i = i; break; /* same buffer, new picture: upload over it */
-        }
-        if (!g_res[i].valid && free_i < 0) free_i = i;
+        if (g_res[i].obj == (const void *)o && g_res[i].inst == inst) { idx = i; break; }
+        if (!g_res[i].obj && idx < 0) idx = i;
     }
-    if (free_i < 0) return SVTB200_ENOMEM;
-    SvtB200Plane pl[3];
-    svtb200_glue_pa_planes(o, pl);
-    static int pagelock = -1; /* SVT_VP9_GPU_PAGELOCK=0: leave the reference's buffers pageable (staged copies, no page-locking cost) */
-    if (pagelock < 0) { const char *e = getenv("SVT_VP9_GPU_PAGELOCK"); pagelock = !(e && e[0] == '0'); }
-    if (pagelock && (!g_res[free_i].valid || g_res[free_i].obj != (const void *)o)) /* a buffer of the reference's pool, first time seen: page-lock it */
-        for (int k = 0; k < 3; k++)
-            if (pl[k].buf && pl[k].stride > 0 && pl[k].padded_height > 0) svtb200_host_register((void *)pl[k].buf, (size_t)pl[k].stride * pl[k].padded_height);
-    int rc = svtb200_picture_upload(g_ctx, (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
-    if (rc != SVTB200_OK) return rc;
-    g_res[free_i].obj = o; g_res[free_i].poc = poc; g_res[free_i].valid = 1;
-    return SVTB200_OK;
+    if (idx >= 0 && g_res[idx].obj != (const void *)o) { g_res[idx].obj = o; g_res[idx].inst = inst; g_res[idx].valid = 0; fresh = 1; }
+    pthread_mutex_unlock(&g_mu);
+    if (idx < 0) return SVTB200_ENOMEM;
+    ResEntry *e = &g_res[idx];
+    pthread_mutex_lock(&e->mu); /* only callers that need THIS picture wait here */
+    int rc = SVTB200_OK;
+    if (!(e->valid && e->poc == poc)) {
+        SvtB200Plane pl[3];
+        svtb200_glue_pa_planes(o, pl);
+        static int pagelock = -1; /* SVT_VP9_GPU_PAGELOCK=0: leave the reference's buffers pageable (staged copies, no page-locking cost) */
+        if (pagelock < 0) { const char *ev = getenv("SVT_VP9_GPU_PAGELOCK"); pagelock = !(ev && ev[0] == '0'); }
+        if (pagelock && (fresh || !e->locked)) { /* a buffer of the reference's pool, first time seen: page-lock it */
+            for (int k = 0; k < 3; k++)
+                if (pl[k].buf && pl[k].stride > 0 && pl[k].padded_height > 0 &&
+                    svtb200_host_register((void *)pl[k].buf, (size_t)pl[k].stride * pl[k].padded_height) == SVTB200_OK) e->reg[k] = (void *)pl[k].buf;
+            e->locked = 1;
+        }
+        rc = svtb200_picture_upload(g_ctx, (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
+        if (rc == SVTB200_OK) { e->poc = poc; e->valid = 1; } else e->valid = 0;
+    }
+    pthread_mutex_unlock(&e->mu);
+    return rc;
 }
 
 static void abi_to_ref(const SvtB200MeCuResult *r, MeCuResults *o) {
@@ -125,26 +236,35 @@ static void abi_to_ref(const SvtB200MeCuResult *r, MeCuResults *o) {
 }
 
 /* runs the whole picture on the GPU; called WITHOUT g_mu (the slot is marked "running") */
-static int run_picture(MeSlot *s, MeContext *me) {
+static int run_picture(MeSlot *s) {
     PictureParentControlSet *pcs = s->pcs;
+    SequenceControlSet *scs = (SequenceControlSet *)pcs->sequence_control_set_wrapper_ptr->object_ptr;
+    const void *inst = (const void *)scs->encode_context_ptr;
     const int want_q = s->P.enable_hme_flag && s->P.enable_hme_level1;
     EbPaReferenceObject *cur = (EbPaReferenceObject *)pcs->pareference_picture_wrapper_ptr->object_ptr;
     EbPaReferenceObject *r0 = (EbPaReferenceObject *)pcs->ref_pa_pic_ptr_array[0]->object_ptr;
     EbPaReferenceObject *r1 = s->P.num_lists == 2 ? (EbPaReferenceObject *)pcs->ref_pa_pic_ptr_array[1]->object_ptr : r0;
-    int rc;
-    pthread_mutex_lock(&g_mu); /* residency table + uploads are serialised; the kernels of different pictures still overlap the uploads */
+    const size_t rb = (size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult);
     const double t0 = now_s();
-    rc = ensure_resident(cur, pcs->picture_number, want_q);
-    if (rc == SVTB200_OK) rc = ensure_resident(r0, pcs->ref_pic_poc_array[0], want_q);
-    if (rc == SVTB200_OK && s->P.num_lists == 2) rc = ensure_resident(r1, pcs->ref_pic_poc_array[1], want_q);
-    g_t_resident += now_s() - t0;
-    pthread_mutex_unlock(&g_mu);
-    if (rc != SVTB200_OK) return rc;
-    const uint64_t ids[2] = {(uint64_t)(uintptr_t)r0, (uint64_t)(uintptr_t)r1};
-    (void)me;
+    int rc = ensure_resident(cur, pcs->picture_number, inst, want_q);
+    if (rc == SVTB200_OK) rc = ensure_resident(r0, pcs->ref_pic_poc_array[0], inst, want_q);
+    if (rc == SVTB200_OK && s->P.num_lists == 2) rc = ensure_resident(r1, pcs->ref_pic_poc_array[1], inst, want_q);
     const double t1 = now_s();
-    rc = svtb200_me_picture(g_ctx, &s->P, (uint64_t)(uintptr_t)cur, ids, s->res, s->P.rate_control_mode ? s->rcme : NULL);
+    uint64_t ticket = 0;
+    if (rc == SVTB200_OK) {
+        const uint64_t ids[2] = {(uint64_t)(uintptr_t)r0, (uint64_t)(uintptr_t)r1};
+        pthread_mutex_lock(&g_queue_mu); /* kernel, fence, download, marker: queued as one unit; nothing here waits for the GPU */
+        rc = svtb200_me_picture_dev(g_ctx, &s->P, (uint64_t)(uintptr_t)cur, ids, s->d_res, s->P.rate_control_mode ? s->d_rcme : NULL);
+        if (rc == SVTB200_OK) rc = svtb200_fence(g_ctx, SVTB200_STREAM_COMPUTE, SVTB200_STREAM_DOWNLOAD);
+        if (rc == SVTB200_OK) rc = svtb200_memcpy_d2h_async(g_ctx, s->res, s->d_res, rb);
+        if (rc == SVTB200_OK && s->P.rate_control_mode) rc = svtb200_memcpy_d2h_async(g_ctx, s->rcme, s->d_rcme, (size_t)s->n_sb * 4);
+        if (rc == SVTB200_OK) rc = svtb200_marker(g_ctx, SVTB200_STREAM_DOWNLOAD, &ticket);
+        pthread_mutex_unlock(&g_queue_mu);
+    }
+    if (rc == SVTB200_OK) rc = svtb200_wait(g_ctx, ticket);
+    else svtb200_sync(g_ctx); /* an upload of this picture may still be reading the encoder's buffer: let it finish before the CPU path takes over */
     pthread_mutex_lock(&g_mu);
+    g_t_resident += t1 - t0;
     g_t_me += now_s() - t1;
     pthread_mutex_unlock(&g_mu);
     return rc;
@@ -157,12 +277,25 @@ static int run_picture(MeSlot *s, MeContext *me) {
 EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_index, uint32_t sb_origin_x, uint32_t sb_origin_y,
                                       MeContext *me, EbPictureBufferDesc *input) {
     static __thread MeSlot *tl_slot;
+    if (g_replay) { /* measurement aid: zero-cost motion estimation from a recorded table */
+        const uint64_t pn = pcs->picture_number;
+        if (pn < g_tab_cap && g_tab[pn].res && sb_index < g_tab[pn].n_sb) {
+            const SvtB200MeCuResult *mine = g_tab[pn].res + (size_t)sb_index * 85;
+            for (int i = 0; i < 85; i++) abi_to_ref(&mine[i], &pcs->me_results[sb_index][i]);
+            if (g_tab[pn].rc_mode) pcs->rcme_distortion[sb_index] = g_tab[pn].rcme[sb_index];
+            __atomic_add_fetch(&g_replayed, 1, __ATOMIC_RELAXED);
+            return EB_ErrorNone;
+        }
+        return __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input);
+    }
     MeSlot *s = tl_slot;
     if (!(s && __atomic_load_n(&s->state, __ATOMIC_ACQUIRE) >= 2 && s->pcs == pcs && s->picture_number == pcs->picture_number)) {
         pthread_mutex_lock(&g_mu);
         if (!ctx_ready()) {
             pthread_mutex_unlock(&g_mu);
-            return __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input);
+            const EbErrorType er = __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input);
+            if (g_record_path) table_put_sb(pcs, sb_index);
+            return er;
         }
         MeSlot *fr = NULL;
         s = NULL;
@@ -180,14 +313,19 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
             if (s->cap_sb < (size_t)s->n_sb) {
                 if (s->res) svtb200_host_free(s->res);
                 if (s->rcme) svtb200_host_free(s->rcme);
+                if (s->d_res) svtb200_dev_free(g_ctx, s->d_res);
+                if (s->d_rcme) svtb200_dev_free(g_ctx, s->d_rcme);
                 s->res = (SvtB200MeCuResult *)svtb200_host_alloc((size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult));
                 s->rcme = (uint32_t *)svtb200_host_alloc((size_t)s->n_sb * sizeof(uint32_t));
-                s->cap_sb = (s->res && s->rcme) ? (size_t)s->n_sb : 0;
+                s->d_res = (SvtB200MeCuResult *)svtb200_dev_alloc(g_ctx, (size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult));
+                s->d_rcme = (uint32_t *)svtb200_dev_alloc(g_ctx, (size_t)s->n_sb * sizeof(uint32_t));
+                s->cap_sb = (s->res && s->rcme && s->d_res && s->d_rcme) ? (size_t)s->n_sb : 0;
             }
             g_me_pictures++;
             pthread_mutex_unlock(&g_mu);
-            const int rc = s->cap_sb ? run_picture(s, me) : SVTB200_ENOMEM;
+            const int rc = s->cap_sb ? run_picture(s) : SVTB200_ENOMEM;
             pthread_mutex_lock(&g_mu);
+            if (rc == SVTB200_OK && g_record_path) table_put(s->picture_number, s->n_sb, s->P.rate_control_mode, s->res, s->rcme);
             __atomic_store_n(&s->state, rc == SVTB200_OK ? 2 : 3, __ATOMIC_RELEASE);
             if (rc != SVTB200_OK && getenv("SVT_VP9_GPU_VERBOSE")) fprintf(stderr, "svtb200: ME on the GPU failed (%d: %s)\n", rc, svtb200_last_error(g_ctx));
             pthread_cond_broadcast(&g_cv);
@@ -217,10 +355,16 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
 }
 
 /* ------------------------------------------------------------------------------------------------------------ S2 */
+static void *g_lf_reg[192];
+static int   g_lf_reg_n;
+
 void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_filter_level, int y_only, int partial_frame) {
-    pthread_mutex_lock(&g_mu);
-    const int ready = ctx_ready();
-    pthread_mutex_unlock(&g_mu);
+    int ready = 0;
+    if (!g_replay || g_ctx) {
+        pthread_mutex_lock(&g_mu);
+        ready = ctx_ready();
+        pthread_mutex_unlock(&g_mu);
+    }
     if (!ready || partial_frame || !frame_filter_level) {
         __real_eb_vp9_loop_filter_frame(cm, xd, frame_filter_level, y_only, partial_frame);
         return;
@@ -228,30 +372,88 @@ void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_
     SvtB200LfParams P;
     SvtB200LfThresh thr[64];
     svtb200_glue_lf(cm, frame_filter_level, y_only, &P, thr);
+    pthread_mutex_lock(&g_lf_mu);
     {   /* the reconstruction buffers come from a small pool: page-lock each plane the first time it is filtered */
-        static const void *seen[64];
-        static int n_seen;
-        pthread_mutex_lock(&g_mu);
         int known = 0;
-        for (int i = 0; i < n_seen; i++) known |= seen[i] == (const void *)xd->plane[0].dst.buf;
-        if (!known && n_seen < 64) {
-            seen[n_seen++] = xd->plane[0].dst.buf;
-            svtb200_host_register(xd->plane[0].dst.buf, (size_t)xd->plane[0].dst.stride * (P.height - 1) + P.width);
+        for (int i = 0; i < g_lf_reg_n; i++) known |= g_lf_reg[i] == (void *)xd->plane[0].dst.buf;
+        if (!known && g_lf_reg_n + 3 <= 192) {
+            if (svtb200_host_register(xd->plane[0].dst.buf, (size_t)xd->plane[0].dst.stride * (P.height - 1) + P.width) == SVTB200_OK)
+                g_lf_reg[g_lf_reg_n++] = xd->plane[0].dst.buf;
             if (!y_only) {
-                svtb200_host_register(xd->plane[1].dst.buf, (size_t)xd->plane[1].dst.stride * (P.height / 2 - 1) + P.width / 2);
-                svtb200_host_register(xd->plane[2].dst.buf, (size_t)xd->plane[2].dst.stride * (P.height / 2 - 1) + P.width / 2);
+                if (svtb200_host_register(xd->plane[1].dst.buf, (size_t)xd->plane[1].dst.stride * (P.height / 2 - 1) + P.width / 2) == SVTB200_OK)
+                    g_lf_reg[g_lf_reg_n++] = xd->plane[1].dst.buf;
+                if (svtb200_host_register(xd->plane[2].dst.buf, (size_t)xd->plane[2].dst.stride * (P.height / 2 - 1) + P.width / 2) == SVTB200_OK)
+                    g_lf_reg[g_lf_reg_n++] = xd->plane[2].dst.buf;
             }
         }
-        pthread_mutex_unlock(&g_mu);
     }
     const double t2 = now_s();
     const int rc = svtb200_deblock_picture(g_ctx_lf, &P, xd->plane[0].dst.buf, xd->plane[0].dst.stride, xd->plane[1].dst.buf, xd->plane[2].dst.buf,
                                            xd->plane[1].dst.stride, (const SvtB200LfMask *)cm->lf.lfm, cm->lf.lfm_stride, thr);
+    pthread_mutex_unlock(&g_lf_mu);
     pthread_mutex_lock(&g_mu);
     g_t_lf += now_s() - t2;
     if (rc == SVTB200_OK) g_lf_pictures++; else g_fallbacks++;
     pthread_mutex_unlock(&g_mu);
+    if (rc == SVTB200_EPARTIAL) {
+        /* the device failed AFTER filtered samples had started to land in the reconstruction: neither filtering again nor skipping the
+         * filter gives the reference's picture any more.  A CUDA error at that point is a lost device; stop instead of writing a
+         * bitstream that silently differs. */
+        fprintf(stderr, "svtb200: GPU failure while the filtered picture was being written back (%s); aborting\n", svtb200_last_error(g_ctx_lf));
+        abort();
+    }
     if (rc != SVTB200_OK) __real_eb_vp9_loop_filter_frame(cm, xd, frame_filter_level, y_only, partial_frame);
+}
+
+/* ------------------------------------------------------------------------------------------------------------ teardown */
+EbErrorType svtb200_real_eb_vp9_deinit_encoder(EbComponentType *svt_enc_component); /* the reference's definition, renamed at link time */
+
+/* Drops every piece of GPU state that refers to buffers of this encoder instance BEFORE the reference frees them: resident pictures,
+ * page-locked ranges, result slots of its pictures.  The worker threads are idle by now (the application has drained the packets). */
+#if defined(__linux__)
+__attribute__((visibility("default")))
+#endif
+EbErrorType eb_vp9_deinit_encoder(EbComponentType *svt_enc_component) {
+    const void *inst = NULL;
+    if (svt_enc_component && svt_enc_component->p_component_private) {
+        EbEncHandle *h = (EbEncHandle *)svt_enc_component->p_component_private;
+        if (h->sequence_control_set_instance_array && h->sequence_control_set_instance_array[0])
+            inst = (const void *)h->sequence_control_set_instance_array[0]->encode_context_ptr;
+    }
+    pthread_mutex_lock(&g_mu);
+    const int live = g_state == 1;
+    pthread_mutex_unlock(&g_mu);
+    if (live) {
+        int cs;
+        pthread_setcancelstate(PTHREAD_CANCEL_DISABLE, &cs);
+        svtb200_sync(g_ctx);
+        svtb200_sync(g_ctx_lf);
+        pthread_once(&g_res_once, res_init);
+        for (int i = 0; i < MAX_RESIDENT; i++) {
+            ResEntry *e = &g_res[i];
+            pthread_mutex_lock(&g_mu);
+            const int mine = e->obj && (e->inst == inst || !inst);
+            pthread_mutex_unlock(&g_mu);
+            if (!mine) continue;
+            pthread_mutex_lock(&e->mu);
+            svtb200_picture_release(g_ctx, (uint64_t)(uintptr_t)e->obj);
+            for (int k = 0; k < 3; k++) if (e->reg[k]) { svtb200_host_unregister(e->reg[k]); e->reg[k] = NULL; }
+            pthread_mutex_lock(&g_mu);
+            e->obj = NULL; e->inst = NULL; e->valid = 0; e->locked = 0;
+            pthread_mutex_unlock(&g_mu);
+            pthread_mutex_unlock(&e->mu);
+        }
+        pthread_mutex_lock(&g_lf_mu); /* reconstruction buffers carry no instance tag: another live encoder simply registers its planes again */
+        for (int i = 0; i < g_lf_reg_n; i++) svtb200_host_unregister(g_lf_reg[i]);
+        g_lf_reg_n = 0;
+        pthread_mutex_unlock(&g_lf_mu);
+        pthread_mutex_lock(&g_mu);
+        for (int i = 0; i < MAX_IN_FLIGHT; i++) if (g_slots[i].state != 1) g_slots[i].state = 0; /* no picture of a finished encode is mid-flight */
+        pthread_mutex_unlock(&g_mu);
+        pthread_setcancelstate(cs, NULL);
+    }
+    report(); /* counters / recorded table now: the reference's own teardown aborts at 3840x2160, which skips destructors */
+    return svtb200_real_eb_vp9_deinit_encoder(svt_enc_component);
 }
 
 __attribute__((destructor)) static void svtb200_wrap_fini(void) { report(); }

@@ -423,6 +423,20 @@ def synthetic_lf_case(rng, width, height, level):
 _refdrv = None
 
 
+class RefdrvTuPass(C.Structure):
+    """oracle/ref_path_driver.c: one transform pass of a picture (job table + planes + result arrays)"""
+    _fields_ = [("tx_size", C.c_int32), ("n", C.c_int32), ("jobs", C.c_void_p), ("pl", api.TxPlanes), ("coeff", C.c_void_p), ("qcoeff", C.c_void_p),
+                ("dqcoeff", C.c_void_p), ("eob", C.c_void_p)]
+
+
+class RefdrvPicture(C.Structure):
+    """oracle/ref_path_driver.c: the hot-path work of one picture for refdrv_pool_run"""
+    _fields_ = [("P", api.MeParams), ("cur", C.POINTER(api.Plane)), ("ref0", C.POINTER(api.Plane)), ("ref1", C.POINTER(api.Plane)), ("me_out", C.c_void_p),
+                ("n_pass", C.c_int32), ("passes", RefdrvTuPass * 8), ("qrows", C.c_void_p), ("deblock", C.c_int32), ("lf", api.LfParams),
+                ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("ys", C.c_int32), ("cs", C.c_int32), ("lfm", C.c_void_p), ("lfm_stride", C.c_int32),
+                ("thr", C.c_void_p)]
+
+
 def have_refdrv():
     return os.path.exists(os.path.join(REF_DIR, "libSvtVp9Enc_refdrv.so"))
 
@@ -438,6 +452,10 @@ def refdrv(use_simd=1):
         L.refdrv_txq.argtypes = [C.c_int, C.c_int, C.c_int, C.c_void_p, C.POINTER(api.TxPlanes), C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         L.refdrv_zz_sad.argtypes = [C.c_void_p, C.POINTER(api.Plane), C.POINTER(api.Plane), C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.refdrv_deblock.argtypes = [C.POINTER(api.LfParams), C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
+        L.refdrv_pool_new.argtypes = [C.c_int, C.c_int]
+        L.refdrv_pool_new.restype = C.c_void_p
+        L.refdrv_pool_run.argtypes = [C.c_void_p, C.POINTER(RefdrvPicture), C.c_int, C.c_int, C.c_int, C.POINTER(C.c_double)]
+        L.refdrv_pool_free.argtypes = [C.c_void_p]
         L.refdrv_init(use_simd)
         _refdrv = L
     return _refdrv

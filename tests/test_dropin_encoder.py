@@ -50,9 +50,40 @@ def test_wrapper_falls_back_to_reference_kernels_without_a_gpu():
         assert _report(os.path.join(d, "rep.txt"))["me_pictures"] == 0
 
 
+def test_recorded_motion_estimation_table_replays_to_the_same_bitstream():
+    """SVT_VP9_ME_RECORD / SVT_VP9_ME_REPLAY (the "zero-cost motion estimation" ceiling measurement of bench.py): a table recorded
+    from the CPU path and replayed yields the reference bitstream, with every ME super-block served from the table."""
+    with tempfile.TemporaryDirectory() as d:
+        yuv, tab = os.path.join(d, "clip.yuv"), os.path.join(d, "tab.bin")
+        _write_yuv(yuv, 320, 192, 20, 5)
+        a = _encode(APP_REF, yuv, os.path.join(d, "ref.ivf"), 320, 192, 20, 8)
+        b = _encode(APP_B200, yuv, os.path.join(d, "rec.ivf"), 320, 192, 20, 8, {"SVT_VP9_GPU": "off", "SVT_VP9_ME_RECORD": tab})
+        c = _encode(APP_B200, yuv, os.path.join(d, "rep.ivf"), 320, 192, 20, 8, {"SVT_VP9_GPU": "off", "SVT_VP9_ME_REPLAY": tab, "SVT_VP9_GPU_REPORT": os.path.join(d, "rep.txt")})
+        assert a == b == c
+        assert _report(os.path.join(d, "rep.txt"))["replayed_sbs"] == 19 * 15
+
+
+def test_dropin_library_has_the_shape_of_the_reference_library():
+    """SONAME libSvtVp9Enc.so.1 and the reference's symbol map (Source/API/EbApi.version: Eb*, eb* only)."""
+    lib = os.path.join(REF_DIR, "dropin", "libSvtVp9Enc.so.1")
+    if not os.path.exists(lib):
+        pytest.skip("drop-in library not built")
+    dyn = subprocess.run(["readelf", "-d", lib], stdout=subprocess.PIPE).stdout.decode()
+    assert "libSvtVp9Enc.so.1" in [l.split("[")[-1].rstrip("]") for l in dyn.splitlines() if "SONAME" in l]
+    syms = [l.split()[-1] for l in subprocess.run(["nm", "-D", "--defined-only", lib], stdout=subprocess.PIPE).stdout.decode().splitlines() if l.strip()]
+    names = [s.split("@")[0] for s in syms]
+    assert all(n.startswith(("eb", "Eb")) or n == "SVT_VP9_0" for n in names), [n for n in names if not n.startswith(("eb", "Eb"))][:5]
+    for api_fn in ("eb_vp9_svt_init_handle", "eb_vp9_svt_enc_set_parameter", "eb_vp9_init_encoder", "eb_vp9_svt_enc_stream_header", "eb_vp9_svt_enc_eos_nal",
+                   "eb_vp9_svt_enc_send_picture", "eb_vp9_svt_get_packet", "eb_vp9_svt_release_out_buffer", "eb_vp9_svt_get_recon", "eb_vp9_deinit_encoder",
+                   "eb_vp9_deinit_handle"):
+        assert api_fn in names, api_fn
+
+
 @pytest.mark.gpu
-@pytest.mark.parametrize("w,h,n,mode", [(640, 384, 34, 8), (448, 256, 20, 3), (1920, 1088, 18, 8)], ids=["640x384-m8", "448x256-m3", "1920x1088-m8"])
+@pytest.mark.parametrize("w,h,n,mode", [(640, 384, 34, 8), (448, 256, 20, 3), (1920, 1088, 18, 8), (1920, 1080, 18, 8), (640, 480, 34, 9), (3840, 2160, 34, 8)],
+                         ids=["640x384-m8", "448x256-m3", "1920x1088-m8", "1920x1080-m8", "640x480-m9", "3840x2160-m8"])
 def test_encoder_with_gpu_hot_path_writes_the_reference_bitstream(w, h, n, mode):
+    """(at 3840x2160 the reference aborts in its own teardown after the last packet -- both builds do; the bitstream is complete)"""
     with tempfile.TemporaryDirectory() as d:
         yuv = os.path.join(d, "clip.yuv")
         _write_yuv(yuv, w, h, n, 11 + mode)

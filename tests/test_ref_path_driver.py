@@ -23,6 +23,11 @@ ME_CASES = [
     ("4k_params_P", 448, 304, lambda w, h: presets.me_params_4k_m8(w, h, 3, 1, (16, 0))),
     ("1080p_params_tl2_ragged_height", 448, 248, lambda w, h: presets.me_params_1080p_m8(w, h, 2, 2, (0, 8))),
     ("1080p_params_tl1", 384, 256, lambda w, h: presets.me_params_1080p_m8(w, h, 1, 2, (0, 16))),
+    ("480p_m9_params_tl0", 640, 480, lambda w, h: presets.me_params_480p_m9(w, h, 0, 2, (0, 0))),
+    ("480p_m9_params_tl3", 640, 480, lambda w, h: presets.me_params_480p_m9(w, h, 3, 2, (0, 4))),
+    ("4k_m5t0_params_tl0_stripes", 704, 448, lambda w, h: presets.me_params_4k_m5_tune0(w, h, 0, 2, (0, 0))),
+    ("4k_m5t0_params_tl2_8x8", 512, 320, lambda w, h: presets.me_params_4k_m5_tune0(w, h, 2, 2, (0, 4))),
+    ("4k_m5t0_params_tl3_nosubpel", 448, 256, lambda w, h: presets.me_params_4k_m5_tune0(w, h, 3, 1, (8, 0))),
 ]
 
 
@@ -71,6 +76,49 @@ def test_cuda_me_full_4k_picture_matches_reference_functions(tl, nl, poc):
     n_sb = ((w + 63) // 64) * ((h + 63) // 64)
     threads = max(1, min(64, len(os.sched_getaffinity(0))))
     ref = H.refdrv_me_picture(P, st[1], st[0], st[2] if nl == 2 else None, n_sb, threads=threads)
+    ctx = api.Context(0)
+    for i, s_ in enumerate(st):
+        ctx.picture_upload(i, s_[0], s_[1], s_[2])
+    out = ctx.me_picture(P, 1, [0, 2] if nl == 2 else [0])
+    ctx.close()
+    ok = H.me_equal(out, ref, nl)
+    assert ok.all(), "%d of %d PUs differ from the reference" % ((~ok).sum(), ok.size)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tl,nl,poc", [(0, 2, (0, 0)), (1, 2, (0, 8)), (2, 2, (0, 4)), (3, 2, (0, 2)), (3, 1, (8, 0))], ids=["tl0", "tl1", "tl2", "tl3", "P"])
+def test_cuda_me_full_4k_m5_tune0_picture_matches_reference_functions(tl, nl, poc):
+    """BASELINE config D at full size (3840x2160, enc-mode 5, tune 0: 2x2 quadrants of 64x32 scaled up to 200 % -- the HME row-stripe
+    path --, HME levels 1 / 2, 16x16 full-pel area, 8x8 refinement): every super-block against the reference's motion_estimate_sb."""
+    import os
+    w, h = 3840, 2160
+    P = presets.me_params_4k_m5_tune0(w, h, tl, nl, poc)
+    clip = H.synth.make_clip(w, h, 3, seed=51 + tl, k=3, g=4, a=9, b=5, m=64, noise=2)
+    pl = [frames.pa_planes(f[0]) for f in clip]
+    st = [frames.plane_structs(p) for p in pl]
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    threads = max(1, min(64, len(os.sched_getaffinity(0))))
+    ref = H.refdrv_me_picture(P, st[1], st[0], st[2] if nl == 2 else None, n_sb, threads=threads)
+    ctx = api.Context(0)
+    for i, s_ in enumerate(st):
+        ctx.picture_upload(i, s_[0], s_[1], s_[2])
+    out = ctx.me_picture(P, 1, [0, 2] if nl == 2 else [0])
+    ctx.close()
+    ok = H.me_equal(out, ref, nl)
+    assert ok.all(), "%d of %d PUs differ from the reference" % ((~ok).sum(), ok.size)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tl,nl,poc", [(0, 2, (0, 0)), (1, 2, (0, 16)), (2, 2, (0, 8)), (3, 2, (0, 4)), (4, 2, (0, 2)), (3, 1, (16, 0))], ids=["tl0", "tl1", "tl2", "tl3", "tl4", "P"])
+def test_cuda_me_full_480p_m9_picture_matches_reference_functions(tl, nl, poc):
+    """BASELINE config A at full size (640x480, enc-mode 9, tune 1)."""
+    w, h = 640, 480
+    P = presets.me_params_480p_m9(w, h, tl, nl, poc)
+    clip = H.synth.make_clip(w, h, 3, seed=71 + tl, k=3, g=3, a=3, b=2, m=32, noise=0)
+    pl = [frames.pa_planes(f[0]) for f in clip]
+    st = [frames.plane_structs(p) for p in pl]
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    ref = H.refdrv_me_picture(P, st[1], st[0], st[2] if nl == 2 else None, n_sb, threads=4)
     ctx = api.Context(0)
     for i, s_ in enumerate(st):
         ctx.picture_upload(i, s_[0], s_[1], s_[2])
@@ -133,3 +181,78 @@ def test_cuda_deblock_matches_reference_functions(w, h, level):
     ctx.close()
     for x, z in zip(a, b):
         assert (x == z).all()
+
+
+def test_thread_pool_of_the_cpu_arm_equals_direct_calls():
+    """bench.py's CPU arm runs the pictures of a mini-GOP through refdrv_pool_run (native threads, SB / TU granular tasks,
+    deblocking gated on its picture's transform tasks): same results as the single calls."""
+    import ctypes as C
+    L = H.refdrv()
+    w, h = 384, 256
+    clip = H.synth.make_clip(w, h, 3, seed=77, k=3, g=4, a=5, b=3, m=32, noise=2)
+    pl = [frames.pa_planes(f[0]) for f in clip]
+    st = [frames.plane_structs(p) for p in pl]
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    rows = H.quant_rows([45, 180])
+    thr = H.lf_thresholds()
+    rng = np.random.default_rng(9)
+    P_lf, _, _, _, lfm, lfm_stride = H.synthetic_lf_case(rng, w, h, 28)
+    keep, pics, want = [], (H.RefdrvPicture * 2)(), []
+    for b, (cur, r0, r1, tl) in enumerate([(1, 0, 2, 4), (2, 0, 0, 0)]):
+        P = presets.me_params_1080p_m8(w, h, tl, 2, (r0, r1))
+        d = pics[b]
+        d.P, d.cur, d.ref0, d.ref1 = P, st[cur], st[r0], st[r1]
+        me = np.zeros(n_sb * 85, dtype=api.ME_RESULT_DTYPE)
+        d.me_out = me.ctypes.data
+        planes = [H.aligned_copy(clip[cur][0]), H.aligned_copy(clip[cur][1])]
+        preds = [H.aligned_copy(clip[r0][0]), H.aligned_copy(clip[r0][1])]
+        recs = [H.aligned_zeros((h + 16, w + 16), np.uint8), H.aligned_zeros((h // 2 + 16, w // 2 + 16), np.uint8), H.aligned_zeros((h // 2 + 16, w // 2 + 16), np.uint8)]
+        outs = []
+        d.n_pass = 2
+        for k, (ts, N, pw, ph) in enumerate([(3, 32, w, h), (2, 16, w // 2, h // 2)]):
+            by, bx = np.meshgrid(np.arange(0, ph, N), np.arange(0, pw, N), indexing="ij")
+            jobs = np.zeros(by.size, dtype=api.TX_JOB_DTYPE)
+            jobs["src_offset"] = jobs["pred_offset"] = by.ravel() * pw + bx.ravel()
+            jobs["recon_offset"] = by.ravel() * recs[k].shape[1] + bx.ravel()
+            jobs["qrow"], jobs["flags"] = np.arange(by.size) & 1, 1
+            q, dq = H.aligned_zeros((by.size, N, N), np.int16), H.aligned_zeros((by.size, N, N), np.int16)
+            eob = np.zeros(by.size, np.uint16)
+            tp = d.passes[k]
+            tp.tx_size, tp.n, tp.jobs = ts, by.size, jobs.ctypes.data
+            tp.pl.src, tp.pl.src_stride, tp.pl.src_bytes = planes[k].ctypes.data, pw, planes[k].nbytes
+            tp.pl.pred, tp.pl.pred_stride, tp.pl.pred_bytes = preds[k].ctypes.data, pw, preds[k].nbytes
+            tp.pl.recon, tp.pl.recon_stride, tp.pl.recon_bytes = recs[k].ctypes.data, recs[k].shape[1], recs[k].nbytes
+            tp.coeff, tp.qcoeff, tp.dqcoeff, tp.eob = None, q.ctypes.data, dq.ctypes.data, eob.ctypes.data
+            outs.append((jobs, q, dq, eob))
+        d.qrows = rows.ctypes.data
+        d.deblock = 1 if b == 1 else 0
+        d.lf = P_lf
+        d.y, d.u, d.v, d.ys, d.cs = recs[0].ctypes.data, recs[1].ctypes.data, recs[2].ctypes.data, recs[0].shape[1], recs[1].shape[1]
+        d.lfm, d.lfm_stride, d.thr = lfm.ctypes.data, lfm_stride, thr.ctypes.data
+        keep.append((me, planes, preds, recs, outs, P))
+        want.append(H.refdrv_me_picture(P, st[cur], st[r0], st[r1], n_sb))
+    pool = L.refdrv_pool_new(4, 1)
+    assert pool
+    cpu_s = (C.c_double * 3)()
+    assert L.refdrv_pool_run(pool, pics, 2, 2, 8, cpu_s) == 0
+    L.refdrv_pool_free(pool)
+    assert cpu_s[0] > 0 and cpu_s[1] > 0 and cpu_s[2] > 0
+    for b, (me, planes, preds, recs, outs, P) in enumerate(keep):
+        assert H.me_equal(me, want[b], 2).all()
+        for k, (jobs, q, dq, eob) in enumerate(outs):
+            j2 = jobs.copy()
+            pw = planes[k].shape[1]
+            j2["recon_offset"] = j2["src_offset"]
+            _, q0, d0, e0, r0 = H.refdrv_txq(3 - k, j2, planes[k], preds[k], np.zeros_like(planes[k]), rows)
+            assert (q == q0).all() and (dq == d0).all() and (eob == e0).all()
+            if b == 0:
+                assert (recs[k][:planes[k].shape[0], :pw] == r0).all()
+        if b == 1:   # deblocked in place after its transform tasks: equal to the direct call on the unfiltered reconstruction
+            unf = []
+            for k in range(2):
+                j2 = outs[k][0].copy()
+                j2["recon_offset"] = j2["src_offset"]
+                unf.append(H.refdrv_txq(3 - k, j2, planes[k], preds[k], np.zeros_like(planes[k]), rows)[4])
+            assert not (recs[0][:h, :w] == unf[0]).all()
+            fy, fu, fv = H.refdrv_deblock(P_lf, unf[0], unf[1], np.zeros_like(unf[1]), lfm, lfm_stride, thr)
+            assert (recs[0][:h, :w] == fy).all() and (recs[1][:h // 2, :w // 2] == fu).all() and (recs[2][:h // 2, :w // 2] == fv).all()
