@@ -361,7 +361,7 @@ def gpu_report(path):
         return None
 
 
-def encoder_record(local_rank, world, clip4k, budget_s=150.0):
+def encoder_record(local_rank, world, clip4k, budget_s=120.0):
     """configs[1] (1080p, enc-mode 8, 300 frames) and configs[2] (4K, enc-mode 8; a bounded number of frames) through the
     application, reference build against drop-in build, one process per rank when world > 1 (configs[4]: concurrent streams,
     one per GPU).  Returns the per-rank record; the caller aggregates over ranks."""
@@ -380,17 +380,25 @@ def encoder_record(local_rank, world, clip4k, budget_s=150.0):
         if world == 1 and clip4k is not None:
             yuv_c = os.path.join(d, "c.yuv")
             synth.write_yuv(yuv_c, clip4k[:16])
-            cases.append(("4k_m8", yuv_c, 3840, 2160, int(os.environ.get("SVTB200_BENCH_4K_FRAMES", "130")), 16))
+            cases.append(("4k_m8", yuv_c, 3840, 2160, int(os.environ.get("SVTB200_BENCH_4K_FRAMES", "100")), 16))
         for name, yuv, cw, ch, n_frames, n_buf in cases:
             if time.perf_counter() - t_start > budget_s:
                 rec[name] = {"skipped": "time budget of the encoder record used up"}
                 continue
             rep = os.path.join(d, "rep.txt")
-            ref = run_encoder(APP_REF, yuv, os.path.join(d, "ref.ivf"), cw, ch, n_frames, n_buf, 8, 1)
-            gpu = run_encoder(APP_B200, yuv, os.path.join(d, "b200.ivf"), cw, ch, n_frames, n_buf, 8, 1,
-                              {"SVT_VP9_GPU": str(local_rank), "SVT_VP9_GPU_REPORT": rep})
+            # alternate the two builds (page cache, clocks and the pools' first touches favour whoever runs later); the better run of each counts
+            refs, gpus = [], []
+            for r_i in range(2 if name == "1080p_m8" else 1):
+                refs.append(run_encoder(APP_REF, yuv, os.path.join(d, "ref.ivf"), cw, ch, n_frames, n_buf, 8, 1))
+                gpus.append(run_encoder(APP_B200, yuv, os.path.join(d, "b200.ivf"), cw, ch, n_frames, n_buf, 8, 1,
+                                        {"SVT_VP9_GPU": str(local_rank), "SVT_VP9_GPU_REPORT": rep}))
+            if name != "1080p_m8":   # one more reference run after the drop-in run, so that the reference is never the only cold one
+                refs.append(run_encoder(APP_REF, yuv, os.path.join(d, "ref.ivf"), cw, ch, n_frames, n_buf, 8, 1))
+            best = lambda runs: max(runs, key=lambda r: r["fps"] or 0.0)
+            ref, gpu = best(refs), best(gpus)
             one = {"frames": n_frames, "distinct_frames": n_buf, "reference": ref, "b200": gpu, "b200_gpu_report": gpu_report(rep),
-                   "bitstream_identical": bool(ref["md5"]) and ref["md5"] == gpu["md5"],
+                   "reference_fps_runs": [r["fps"] for r in refs], "b200_fps_runs": [r["fps"] for r in gpus],
+                   "bitstream_identical": bool(ref["md5"]) and all(r["md5"] == ref["md5"] for r in refs + gpus),
                    "speedup": (gpu["fps"] / ref["fps"]) if ref["fps"] and gpu["fps"] else None}
             if name == "1080p_m8" and world == 1 and time.perf_counter() - t_start < budget_s:
                 # host-bound ceiling: the same encode with motion estimation served from a table recorded by a previous run

@@ -31,7 +31,7 @@ def test_reference_arm_line():
     assert d["unit"] == "fps" and d["higher_is_better"] is True and d["dtype"] == "u8" and d["vs_baseline"] is None
     assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "fps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
-    assert "workload" in d["config"] and d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0) < 1.0
+    assert "workload" in d["config"] and d["value"] > 0 and abs(d["ms_per_step"] * d["value"] - 1000.0 * d["config"]["pictures_per_step"]) < 1.0
 
 
 @pytest.mark.skipif(not H.have_refdrv(), reason="oracle/_ref not built")
