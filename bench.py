@@ -456,8 +456,8 @@ def main():
                           "transform/quantise/reconstruct pass over every TU (luma 32x32, chroma 16x16; 16x16 / 8x8 for the last 16 rows; q 45) + deblocking on the "
                           "base-layer picture; step = one 16-picture hierarchical mini-GOP in encode order",
               "pictures_per_step": PICS_PER_STEP,
-              "queues": "motion estimation (followed by the three small edge-row transform launches) on the context's first compute queue, the "
-                        "picture-sized transform launches + deblocking on its second (they belong to different pictures in the encoder); value = "
+              "queues": "motion estimation on the context's first compute queue, the picture's transform launch (all six TU batches in one "
+                        "kernel) + deblocking on its second (they belong to different pictures in the encoder); value = "
                         "CUDA events around the K steps with both queues joined inside the timed region",
               "l2": "17 distinct pictures (165 MB of luma planes + 105 MB chroma) cycled: working set larger than the 126 MB L2",
               "parallelism": "pictures sharded across GPUs (independent mini-GOP streams per rank), no collective on the data path"}
@@ -521,7 +521,7 @@ def main():
     d_u = [L.svtb200_dev_alloc(h, csize) for _ in range(N_FRAMES)]
     d_v = [L.svtb200_dev_alloc(h, csize) for _ in range(N_FRAMES)]
     for i in range(N_FRAMES):
-        ctx.picture_upload(i, PS[i][0], None, PS[i][2])
+        ctx.picture_upload_luma(i, PS[i][0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, False)   # aligned device geometry, padding + 1/16 plane made on the device
         L.svtb200_memcpy_h2d(h, d_u[i], pu[i].data_ptr(), csize)
         L.svtb200_memcpy_h2d(h, d_v[i], pv[i].data_ptr(), csize)
     dplane = []
@@ -581,24 +581,26 @@ def main():
     ME_QUEUES = int(os.environ.get("SVTB200_BENCH_ME_QUEUES", "1"))
 
     _txq_cache = {}
-    EDGE_PASSES = tuple(k for k, (_, _, _, cols, rows, _) in enumerate(TU_PASSES) if rows == 1)
+    api._bind_txq(L)
 
-    def txq_args(slot, n, r0):
-        """ctypes argument tuples of the six transform launches of picture n into result slot 'slot' (built once)"""
+    def txq_batches(slot, n, r0):
+        """the SvtB200TxBatch array (six batches: every TU of the three planes) of picture n into result slot 'slot' (built once)"""
         key = (slot, n)
         if key not in _txq_cache:
             ybytes = sy * dplane[n].padded_height
             rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
-            lst = []
+            arr = (api.TxBatch * len(TU_PASSES))()
             for k, (plane, ts, size, cols, rows, row0) in enumerate(TU_PASSES):
                 if plane == 0:
                     pl = txq_planes(dplane[n].buf, sy, ybytes, dplane[r0].buf, rec[0], W4K, W4K * H4K)
                 else:
                     dc = d_u if plane == 1 else d_v
                     pl = txq_planes(dc[n], W4K // 2, csize, dc[r0], rec[plane], W4K // 2, csize)
-                lst.append((h, ts, pass_n[k], d_jobs[k], C.byref(pl), d_rows, 1, None, q[k], d_dq[k], eob[k], pl))
-            _txq_cache[key] = [a[:-1] for a in lst], [a[-1] for a in lst]   # keep the structs alive
-        return _txq_cache[key][0]
+                b = arr[k]
+                b.tx_size, b.n, b.jobs, b.planes = ts, pass_n[k], d_jobs[k], pl
+                b.coeff, b.qcoeff, b.dqcoeff, b.eob = None, q[k], d_dq[k], eob[k]
+            _txq_cache[key] = arr
+        return _txq_cache[key]
 
     def kernels(i, timed, slot=0, overlap=True, sink=None):
         n = ENCODE_ORDER[i % 16]
@@ -613,38 +615,23 @@ def main():
         ctx.check(L.svtb200_me_picture_dev(h, C.byref(P), n, ids, d_me[slot], None), "me_picture_dev")
         if timed:
             e[1].record(s1)
-        targs = txq_args(slot, n, r0)
         if overlap:
-            # the three edge passes (240 small blocks each, latency-bound 5-7 us launches) ride in the tail of the ME grid on the
-            # first queue; the picture-sized passes go to the second queue
-            for k in EDGE_PASSES:
-                rc = L.svtb200_txq_batch_dev(*targs[k])
-                if rc:
-                    ctx.check(rc, "txq_batch_dev")
-            L.svtb200_picture_touch(h, n)
-            L.svtb200_picture_touch(h, r0)
-            if n == 16:
-                edge_done = ctx.marker(q1)
             ctx.select_compute(api.COMPUTE2)
         if timed:
             e[2].record(s2)
-        for k, a in enumerate(targs):
-            if overlap and k in EDGE_PASSES:
-                continue
-            rc = L.svtb200_txq_batch_dev(*a)
-            if rc:
-                ctx.check(rc, "txq_batch_dev")
+        # every TU of the picture (luma 32x32 + the 16x16 edge row, chroma 16x16 + 8x8 edge rows) in ONE launch
+        rc = L.svtb200_txq_multi_dev(h, txq_batches(slot, n, r0), len(TU_PASSES), d_rows, 1)
+        if rc:
+            ctx.check(rc, "txq_multi_dev")
         if timed:
             e[3].record(s2)
         if n == 16:
-            if overlap:
-                ctx.stream_wait(api.COMPUTE2, edge_done)   # deblocking needs the reconstruction of the edge rows too
             rec = d_rec[slot]
             ctx.check(L.svtb200_deblock_picture_dev(h, C.byref(LfP), rec[0], W4K, rec[1], rec[2], W4K // 2, d_lfm, 60, d_thr), "deblock")
         if timed:
             e[4].record(s2)
             (marks if sink is None else sink).append((e, P, n))
-        L.svtb200_picture_touch(h, n)      # the transform kernels read the planes of pictures n and r0 on this queue
+        L.svtb200_picture_touch(h, n)      # the transform kernel reads the planes of pictures n and r0 on this queue
         L.svtb200_picture_touch(h, r0)
         ctx.select_compute(api.COMPUTE)
         return n, r0
@@ -815,7 +802,7 @@ def main():
                              "traffic": traffic.get(k), "ms_per_picture_alone": iso, "achieved_gbs_alone": per_pic / (iso / 1000.0) / 1e9 if iso else None,
                              "frac_alone": per_pic / (iso / 1000.0) / 1e9 / peak if iso else None,
                              "share_alone": per_step_alone[k] / sum(per_step_alone.values())}
-    launches_dom = n_me if dom == "me_sb_kernel" else (len(TU_PASSES) * n_me if dom == "txq_kernel" else max(1, n_timed // 16))
+    launches_dom = n_me if dom in ("me_sb_kernel", "txq_kernel") else max(1, n_timed // 16)
     roof = {"bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"],
             "traffic": traffic.get(dom), "kernel": dom, "alg_bytes_per_launch": alg[dom] / launches_dom,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)", "per_kernel": per_kernel}

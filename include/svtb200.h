@@ -121,7 +121,12 @@ int svtb200_picture_upload(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane 
 /* Upload only the full-resolution padded luma; the 1/4 and 1/16 decimations (+ their padding)
  * are produced on the device exactly as eb_vp9_decimation_2d + eb_vp9_generate_padding would
  * (Source/Lib/Codec/EbPictureAnalysisProcess.c:102, :5025). quarter_pad/sixteenth_pad are the
- * origin_x(=origin_y) of the decimated planes (reference: 32+... see DESIGN.md). */
+ * origin_x(=origin_y) of the decimated planes (reference: 32+... see DESIGN.md).
+ * Only the picture area of 'full' is read from the host.  The device copy of the full-resolution plane has its own geometry
+ * (svtb200_picture_plane_dev reports it): pitch a multiple of 16 and the picture 80 columns into the row, so that the picture's
+ * 16-sample groups are 16-byte aligned vectors and rows are legal TMA rows; the columns beyond the host row's padding hold the
+ * bytes a read past the end of the (contiguous) host row finds -- the reference's search windows do that, and the results depend
+ * on it. */
 int svtb200_picture_upload_luma(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane *full,
                                 int32_t quarter_pad, int32_t sixteenth_pad, int make_quarter);
 int svtb200_picture_release(SvtB200Ctx *ctx, uint64_t pic_id);
@@ -303,6 +308,24 @@ int svtb200_txq_batch_dev(SvtB200Ctx *ctx, int tx_size, int n, const SvtB200TxJo
                           const SvtB200TxPlanes *planes_dev, const SvtB200QuantRow *qrows_dev,
                           int n_qrows, int16_t *coeff_dev, int16_t *qcoeff_dev,
                           int16_t *dqcoeff_dev, uint16_t *eob_dev);
+/* Source / prediction samples may sit at any byte address (rows are fetched as 16-byte vectors where the address allows, as
+ * aligned words otherwise).  Reconstruction rows are stored as 32-bit words / 16-byte vectors: the recon plane's base, its
+ * stride and every recon_offset must be multiples of 4 (block positions are multiples of 4 samples; svtb200_txq_batch checks
+ * the offsets, the _dev entry points check base and stride). */
+
+/* Several fused batches of one picture -- different transform sizes, different planes (luma 32x32, chroma 16x16, the smaller
+ * blocks of the picture's last rows ...) -- in ONE launch (up to 8).  The array lives in HOST memory, the pointers inside are
+ * device pointers; one quantiser table serves all batches. */
+typedef struct SvtB200TxBatch {
+    int32_t              tx_size, n;
+    const SvtB200TxJob  *jobs;
+    SvtB200TxPlanes      planes;
+    int16_t             *coeff;   /* may be NULL */
+    int16_t             *qcoeff, *dqcoeff;
+    uint16_t            *eob;
+} SvtB200TxBatch;
+int svtb200_txq_multi_dev(SvtB200Ctx *ctx, const SvtB200TxBatch *batches, int n_batches,
+                          const SvtB200QuantRow *qrows_dev, int n_qrows);
 
 /* =============================================================================================
  * S2  Deblocking loop filter

@@ -65,6 +65,12 @@ class TxPlanes(C.Structure):
                 ("recon", C.c_void_p), ("recon_stride", C.c_int32), ("recon_bytes", C.c_size_t)]
 
 
+class TxBatch(C.Structure):
+    """SvtB200TxBatch: one fused batch of svtb200_txq_multi_dev (device pointers)"""
+    _fields_ = [("tx_size", C.c_int32), ("n", C.c_int32), ("jobs", C.c_void_p), ("planes", TxPlanes), ("coeff", C.c_void_p), ("qcoeff", C.c_void_p),
+                ("dqcoeff", C.c_void_p), ("eob", C.c_void_p)]
+
+
 LF_MASK_DTYPE = np.dtype([("left_y", "<u8", 4), ("above_y", "<u8", 4), ("int_4x4_y", "<u8"), ("left_uv", "<u2", 4),
                           ("above_uv", "<u2", 4), ("int_4x4_uv", "<u2"), ("lfl_y", "u1", 64), ("pad", "u1", 6)])
 assert LF_MASK_DTYPE.itemsize == 160
@@ -281,6 +287,7 @@ def _bind_txq(L):
     L.svtb200_inv_txfm_add_batch_dev.argtypes = [vp, C.c_int, C.c_int, C.c_int, vp, vp, vp]
     L.svtb200_txq_batch.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(TxPlanes), vp, C.c_int, vp, vp, vp, vp]
     L.svtb200_txq_batch_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(TxPlanes), vp, C.c_int, vp, vp, vp, vp]
+    L.svtb200_txq_multi_dev.argtypes = [vp, C.POINTER(TxBatch), C.c_int, vp, C.c_int]
     L._txq_bound = True
 
 
@@ -343,6 +350,46 @@ def _ctx_txq(self, tx_size, jobs, src, pred, recon, rows, want_coeff=True):
     return coeff, q, dq, eob, rec
 
 
+def _ctx_txq_multi(self, batches, rows):
+    """batches: list of (tx_size, jobs, src, pred, recon) with 2-D uint8 planes (each batch its own planes); ONE launch through
+    svtb200_txq_multi_dev.  Returns a list of (q, dq, eob, recon) per batch."""
+    _bind_txq(self.L)
+    L, h = self.L, self.h
+    rows = np.ascontiguousarray(rows)
+    dev, arr, outs = [], (TxBatch * len(batches))(), []
+
+    def up(a):
+        d = L.svtb200_dev_alloc(h, max(a.nbytes, 16))
+        self.check(L.svtb200_memcpy_h2d(h, d, a.ctypes.data, a.nbytes), "h2d")
+        dev.append(d)
+        return d
+    try:
+        d_rows = up(rows)
+        for k, (ts, jobs, src, pred, recon) in enumerate(batches):
+            N, n = 4 << ts, len(jobs)
+            jobs, src, pred, recon = (np.ascontiguousarray(a) for a in (jobs, src, pred, recon))
+            b = arr[k]
+            b.tx_size, b.n, b.jobs = ts, n, up(jobs)
+            b.planes.src, b.planes.src_stride, b.planes.src_bytes = up(src), src.shape[1], src.nbytes
+            b.planes.pred, b.planes.pred_stride, b.planes.pred_bytes = up(pred), pred.shape[1], pred.nbytes
+            b.planes.recon, b.planes.recon_stride, b.planes.recon_bytes = up(recon), recon.shape[1], recon.nbytes
+            q, dq, eob = np.zeros((n, N, N), np.int16), np.zeros((n, N, N), np.int16), np.zeros(n, np.uint16)
+            b.coeff, b.qcoeff, b.dqcoeff, b.eob = None, up(q), up(dq), up(eob)
+            outs.append((q, dq, eob, recon.copy(), b))
+        self.check(L.svtb200_txq_multi_dev(h, arr, len(batches), d_rows, len(rows)), "txq_multi_dev")
+        self.sync()
+        res = []
+        for q, dq, eob, rec, b in outs:
+            for a, d in ((q, b.qcoeff), (dq, b.dqcoeff), (eob, b.eob), (rec, b.planes.recon)):
+                self.check(L.svtb200_memcpy_d2h(h, a.ctypes.data, d, a.nbytes), "d2h")
+            res.append((q, dq, eob, rec))
+        return res
+    finally:
+        for d in dev:
+            L.svtb200_dev_free(h, d)
+
+
+Context.txq_multi = _ctx_txq_multi
 Context.register_scans = _ctx_register_scans
 Context.fwd_txfm = _ctx_fwd_txfm
 Context.quantize = _ctx_quantize

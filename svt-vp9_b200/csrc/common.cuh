@@ -12,6 +12,8 @@
 #include "../../include/svtb200.h"
 
 #define SVTB200_MARKER_RING 1024
+#define SVTB200_DEV_PAD_L 80   /* svtb200_picture_upload_luma: device columns left of the picture (multiple of 16, >= the reference's 68) */
+#define SVTB200_DEV_PAD_R 96   /* ... and right of it: the reference's 68 + the samples its windows read past the row end */
 
 struct DevPlane {
     uint8_t *buf = nullptr;

@@ -218,15 +218,29 @@ int svtb200_picture_upload(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *f
 
 /* Edge replication of the padded source plane (eb_vp9_generate_padding, EbPictureOperators.c) and the point decimations
  * of eb_vp9_decimation_2d (EbPictureAnalysisProcess.c:102) with their own padding, one thread per 4 output bytes. */
-__global__ void pa_pad_full_kernel(uint8_t *buf, int pitch, int ox, int oy, int w, int h, int rows, int cols /* bytes of a row to write */) {
+__global__ void pa_pad_full_kernel(uint8_t *buf, int pitch, int ox, int oy, int w, int h, int rows, int cols /* bytes of a row to write */,
+                                   int host_pad /* padding of the HOST row on each side */) {
     const int x4 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
     if (x4 >= cols || y >= rows) return;
-    const int sy = min(max(y - oy, 0), h - 1);
     if (y >= oy && y < oy + h && x4 >= ox && x4 + 4 <= ox + w) return; /* interior word */
-    const uint8_t *row = buf + (size_t)(oy + sy) * pitch + ox;
+    /* Columns further out than the host row's own padding hold what a read past the end of the HOST row finds: the padded
+     * planes of the reference are contiguous (pitch w + 2 * host_pad), so column w + host_pad + k of row y is column -host_pad + k
+     * of row y + 1, and column -host_pad - k is the tail of row y - 1.  The reference's search windows do run a few samples over
+     * (EbMotionEstimation.c:855-856 matches two 16x16 blocks sixteen samples to the right); a device pitch of its own must
+     * reproduce those bytes. */
+    const int hp = w + 2 * host_pad;
     uint32_t v = 0;
 #pragma unroll
-    for (int k = 0; k < 4; k++) v |= (uint32_t)row[min(max(x4 + k - ox, 0), w - 1)] << (8 * k);
+    for (int k = 0; k < 4; k++) {
+        int xs = x4 + k - ox, yy = y;      /* picture-relative column, padded-plane row */
+        if (xs < -host_pad || xs >= w + host_pad) {
+            const int a = xs + host_pad;     /* offset from the start of host row yy */
+            const int dr = a >= 0 ? a / hp : -((-a + hp - 1) / hp);
+            yy += dr; xs = a - dr * hp - host_pad;
+        }
+        const int sy = min(max(yy - oy, 0), h - 1);
+        v |= (uint32_t)buf[(size_t)(oy + sy) * pitch + ox + min(max(xs, 0), w - 1)] << (8 * k);
+    }
     if (x4 + 4 <= cols) *(uint32_t *)(buf + (size_t)y * pitch + x4) = v;
     else for (int k = 0; x4 + k < cols; k++) buf[(size_t)y * pitch + x4 + k] = (uint8_t)(v >> (8 * k));
 }
@@ -264,13 +278,21 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
     int rc;
     upload_begin(c, p);
     DevPlane *f = &p.pl[0];
-    if ((rc = alloc_plane(c, f, full->stride, full->padded_height))) return rc;
-    f->ox = full->origin_x; f->oy = full->origin_y; f->w = full->width; f->h = full->height;
+    /* Device geometry of the full-resolution plane: the picture starts SVTB200_DEV_PAD_L columns into a row whose pitch is a multiple
+     * of 16, so that every 16-sample group of the picture is a 16-byte aligned vector (the transform kernels' loads) and a row is a
+     * legal TMA row (the motion-estimation windows); SVTB200_DEV_PAD_R columns follow the picture.  Columns beyond the host row's own
+     * padding carry the bytes a read past the host row would find (pa_pad_full_kernel). */
+    const int dpitch = (full->width + SVTB200_DEV_PAD_L + SVTB200_DEV_PAD_R + 15) & ~15;
+    if (full->origin_x > SVTB200_DEV_PAD_L) { c->err = "upload_luma: host padding wider than the device layout"; return SVTB200_EINVAL; }
+    if ((rc = alloc_plane(c, f, dpitch, full->padded_height))) return rc;
+    f->ox = SVTB200_DEV_PAD_L; f->oy = full->origin_y; f->w = full->width; f->h = full->height;
     /* only the picture area crosses PCIe; the padding is regenerated on the device */
-    const size_t off = (size_t)f->oy * f->stride + f->ox;
-    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(f->buf + off, f->stride, full->buf + off, full->stride, f->w, f->h, cudaMemcpyHostToDevice, c->up));
+    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(f->buf + (size_t)f->oy * f->stride + f->ox, f->stride,
+                                            full->buf + (size_t)full->origin_y * full->stride + full->origin_x, full->stride, f->w, f->h,
+                                            cudaMemcpyHostToDevice, c->up));
     dim3 blk(128);
-    pa_pad_full_kernel<<<dim3((f->stride / 4 + 127) / 128, f->rows), blk, 0, c->up>>>(f->buf, f->stride, f->ox, f->oy, f->w, f->h, f->rows, f->stride);
+    pa_pad_full_kernel<<<dim3((f->stride / 4 + 127) / 128, f->rows), blk, 0, c->up>>>(f->buf, f->stride, f->ox, f->oy, f->w, f->h, f->rows, f->stride,
+                                                                                     full->origin_x);
     c->launches++;
     for (int lvl = 1; lvl <= 2; lvl++) {
         DevPlane *d = &p.pl[lvl];
@@ -308,7 +330,7 @@ int svtb200_pad_plane_dev(SvtB200Ctx *c, uint8_t *buf, int32_t stride, int32_t w
     cudaSetDevice(c->device);
     const int cols = width + 2 * pad_x, rows = height + 2 * pad_y;
     /* the kernel treats 'cols' as the row length to write and 'stride' as the pitch */
-    pa_pad_full_kernel<<<dim3((cols / 4 + 127) / 128, rows), dim3(128), 0, c->stream>>>(buf, stride, pad_x, pad_y, width, height, rows, cols);
+    pa_pad_full_kernel<<<dim3((cols / 4 + 127) / 128, rows), dim3(128), 0, c->stream>>>(buf, stride, pad_x, pad_y, width, height, rows, cols, pad_x);
     c->launches++;
     SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return SVTB200_OK;

@@ -141,6 +141,86 @@ template <int N> __device__ __forceinline__ void load_row16(const int16_t *src, 
     }
 }
 
+/* 4 * W consecutive bytes at ANY byte address as W little-endian words, without byte loads: one aligned vector load when the
+ * address allows it, else the enclosing aligned words re-aligned with funnel shifts (reads at most the aligned word that holds the
+ * last byte). */
+template <int W> __device__ __forceinline__ void ld_bytes(const uint8_t *p, uint32_t (&w)[W]) {
+    const uintptr_t a = (uintptr_t)p;
+    if constexpr (W == 4) { if ((a & 15) == 0) { const uint4 v = __ldg((const uint4 *)p); w[0] = v.x; w[1] = v.y; w[2] = v.z; w[3] = v.w; return; } }
+    if constexpr (W == 2) { if ((a & 7) == 0) { const uint2 v = __ldg((const uint2 *)p); w[0] = v.x; w[1] = v.y; return; } }
+    const uint32_t *q = (const uint32_t *)(a & ~(uintptr_t)3);
+    const uint32_t sh = (uint32_t)(a & 3) * 8;
+    uint32_t lo = __ldg(q);
+    if (sh == 0) {
+        w[0] = lo;
+#pragma unroll
+        for (int k = 1; k < W; k++) w[k] = __ldg(q + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < W; k++) { const uint32_t hi = __ldg(q + k + 1); w[k] = __funnelshift_r(lo, hi, sh); lo = hi; }
+    }
+}
+/* 4 * W bytes to a 4-byte aligned address (16-byte vector when the address allows it) */
+template <int W> __device__ __forceinline__ void st_bytes(uint8_t *p, const uint32_t (&w)[W]) {
+    const uintptr_t a = (uintptr_t)p;
+    if constexpr (W == 4) { if ((a & 15) == 0) { *(uint4 *)p = make_uint4(w[0], w[1], w[2], w[3]); return; } }
+    if constexpr (W == 2) { if ((a & 7) == 0) { *(uint2 *)p = make_uint2(w[0], w[1]); return; } }
+#pragma unroll
+    for (int k = 0; k < W; k++) ((uint32_t *)p)[k] = w[k];
+}
+/* The rows of an NxN block are moved by the block's N lanes in segments of SEG = min(N, 16) samples: lane -> (row, column of the
+ * segment); N == 32 takes two passes of 16 rows x 2 segments. */
+template <int N> struct SegMap {
+    static constexpr int SEG = N < 16 ? N : 16, PER_ROW = N / SEG, ROWS = N / PER_ROW, PASSES = N / ROWS, W = SEG / 4;
+};
+
+/* residual = src - pred of the block at (s, p): every lane fetches whole segments (vector loads), the block is handed over through
+ * the tile, lane c leaves with column c in v[] */
+template <int N>
+__device__ __forceinline__ void load_residual_columns(const uint8_t *s, int ss, const uint8_t *p, int ps, int (&v)[N], int *tile, int lane, unsigned gmask) {
+    typedef SegMap<N> M;
+#pragma unroll
+    for (int i = 0; i < M::PASSES; i++) {
+        const int r = i * M::ROWS + lane / M::PER_ROW, c0 = (lane % M::PER_ROW) * M::SEG;
+        uint32_t a[M::W], b[M::W];
+        ld_bytes<M::W>(s + (size_t)r * ss + c0, a);
+        ld_bytes<M::W>(p + (size_t)r * ps + c0, b);
+#pragma unroll
+        for (int k = 0; k < M::SEG; k++)
+            tile[r * (N + 1) + c0 + k] = (int)((a[k >> 2] >> (8 * (k & 3))) & 0xff) - (int)((b[k >> 2] >> (8 * (k & 3))) & 0xff);
+    }
+    __syncwarp(gmask);
+#pragma unroll
+    for (int j = 0; j < N; j++) v[j] = tile[j * (N + 1) + lane];
+    __syncwarp(gmask);
+}
+/* reconstruction: lane c holds the inverse transform's column c (res[], already rounded and shifted); handed back through the tile,
+ * every lane adds the prediction to whole segments and stores them as vectors */
+template <int N>
+__device__ __forceinline__ void store_recon_rows(const int (&res)[N], const uint8_t *p, int ps, uint8_t *d, int ds, int *tile, int lane, unsigned gmask, bool live) {
+    typedef SegMap<N> M;
+#pragma unroll
+    for (int j = 0; j < N; j++) tile[j * (N + 1) + lane] = res[j];
+    __syncwarp(gmask);
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < M::PASSES; i++) {
+            const int r = i * M::ROWS + lane / M::PER_ROW, c0 = (lane % M::PER_ROW) * M::SEG;
+            uint32_t b[M::W], o[M::W];
+            ld_bytes<M::W>(p + (size_t)r * ps + c0, b);
+#pragma unroll
+            for (int k = 0; k < M::W; k++) o[k] = 0;
+#pragma unroll
+            for (int k = 0; k < M::SEG; k++) {
+                const int x = (int)((b[k >> 2] >> (8 * (k & 3))) & 0xff) + tile[r * (N + 1) + c0 + k];
+                o[k >> 2] |= (uint32_t)min(max(x, 0), 255) << (8 * (k & 3));
+            }
+            st_bytes<M::W>(d + (size_t)r * ds + c0, o);
+        }
+    }
+    __syncwarp(gmask);
+}
+
 /* quantise coefficient row 'lane' (c[]): writes the q / dq rows (16-byte stores) when live, keeps dq[] for the
  * inverse transform; returns the block's eob on every lane */
 template <int N>
@@ -186,77 +266,97 @@ __device__ __forceinline__ int quant_row(const int (&c)[N], int (&dq)[N], const 
     return group_max<N>(eob) + 1;
 }
 
-/* MODE 0 fused from planes, 1 forward only, 2 quantise only, 3 inverse + add only */
+/* MODE 0 fused from planes, 1 forward only, 2 quantise only, 3 inverse + add only.
+ * One pass = the G = TXQ_THREADS / N blocks [blk0, blk0 + G) of a batch, one block per group of N lanes. */
 template <int N, int MODE>
-__global__ void __launch_bounds__(TXQ_THREADS, 4) txq_kernel(const __grid_constant__ TxqArgs A) {
-    constexpr int G = TXQ_THREADS / N; /* blocks per CTA pass */
+__device__ __forceinline__ void txq_pass(const TxqArgs &A, int blk0, int *tiles) {
     constexpr int SHIFT = TxCfg<N>::SHIFT, TS = TxCfg<N>::TS;
-    __shared__ int tiles[G * N * (N + 1)];
     const int grp = threadIdx.x / N, lane = threadIdx.x % N;
     int *tile = tiles + grp * N * (N + 1);
     const unsigned gmask = N == 32 ? 0xffffffffu : (((1u << N) - 1u) << ((threadIdx.x & 31) - (threadIdx.x & 31) % N));
-    /* all lanes of a warp iterate together (blocks past the end are processed on dummy data, stores masked) */
-    for (int blk0 = blockIdx.x * G; blk0 < A.n; blk0 += gridDim.x * G) {
-        const int blk = blk0 + grp;
-        const bool live = blk < A.n;
-        const int b = live ? blk : A.n - 1;
-        int v[N], dq[N];
-        int tx_type = A.tx_type, flags = 0, qrow = 0;
-        const uint8_t *pred_p = nullptr;
-        int pred_s = 0;
-        if (MODE == 0) {
-            const SvtB200TxJob job = A.jobs[b];
-            tx_type = TS == 3 ? 0 : job.tx_type; flags = job.flags; qrow = job.qrow;
-            const uint8_t *s = A.pl.src + job.src_offset + lane;
-            pred_p = A.pl.pred + job.pred_offset + lane; pred_s = A.pl.pred_stride;
+    /* all lanes of a warp work together (blocks past the end are processed on dummy data, stores masked) */
+    const int blk = blk0 + grp;
+    const bool live = blk < A.n;
+    const int b = live ? blk : A.n - 1;
+    int v[N], dq[N];
+    int tx_type = A.tx_type, flags = 0, qrow = 0;
+    const uint8_t *pred_p = nullptr;
+    int pred_s = 0;
+    uint32_t recon_off = 0;
+    if (MODE == 0) {
+        const uint4 jw = __ldg((const uint4 *)(A.jobs + b)); /* SvtB200TxJob as one 16-byte vector: src, pred, recon offsets, qrow | tx_type << 16 | flags << 24 */
+        tx_type = TS == 3 ? 0 : (int)((jw.w >> 16) & 0xff); flags = (int)(jw.w >> 24); qrow = (int)(jw.w & 0xffff); recon_off = jw.z;
+        pred_p = A.pl.pred + jw.y; pred_s = A.pl.pred_stride;
+        load_residual_columns<N>(A.pl.src + jw.x, A.pl.src_stride, pred_p, pred_s, v, tile, lane, gmask);
+    } else if (MODE == 1) {
+        load_row16<N>(A.in16 + (size_t)b * N * N + lane * N, v); /* row 'lane' with vector loads, then lane c takes column c */
+        tile_transpose<N>(v, tile, lane, gmask);
+        flags = A.partial32 ? SVTB200_TXJ_PARTIAL32 : 0;
+    } else {
+        load_row16<N>(A.in16 + (size_t)b * N * N + lane * N, v);
+        if (MODE == 2 && A.qrow_index) qrow = A.qrow_index[b];
+    }
+    if (MODE == 0 || MODE == 1) {
+        fwd2d<N>(v, tx_type, tile, lane, gmask);
+        if (TS == 3 && (flags & SVTB200_TXJ_PARTIAL32)) {
 #pragma unroll
-            for (int j = 0; j < N; j++) v[j] = (int)__ldg(s + (size_t)j * A.pl.src_stride) - (int)__ldg(pred_p + (size_t)j * pred_s);
-        } else if (MODE == 1) {
-            const int16_t *s = A.in16 + (size_t)b * N * N + lane;
-#pragma unroll
-            for (int j = 0; j < N; j++) v[j] = __ldg(s + j * N);
-            flags = A.partial32 ? SVTB200_TXJ_PARTIAL32 : 0;
-        } else {
-            load_row16<N>(A.in16 + (size_t)b * N * N + lane * N, v);
-            if (MODE == 2 && A.qrow_index) qrow = A.qrow_index[b];
+            for (int k = 0; k < N; k++) if (lane >= 16 || k >= 16) v[k] = 0;
         }
-        if (MODE == 0 || MODE == 1) {
-            fwd2d<N>(v, tx_type, tile, lane, gmask);
-            if (TS == 3 && (flags & SVTB200_TXJ_PARTIAL32)) {
+        if (A.coeff && live) store_row16<N>(A.coeff + (size_t)b * N * N + lane * N, v);
+    }
+    if (MODE == 0 || MODE == 2) {
+        const SvtB200QuantRow qr = A.qrows[qrow];
+        const int eob = quant_row<N>(v, dq, qr, A.iscan[TS == 3 ? 0 : tx_type], lane, A.qcoeff + (size_t)b * N * N + lane * N,
+                                     A.dqcoeff + (size_t)b * N * N + lane * N, live);
+        if (live && lane == 0) A.eob[b] = (uint16_t)eob;
+    }
+    if (MODE == 3 || (MODE == 0 && (flags & SVTB200_TXJ_RECON))) {
+        int t[N];
+        if (MODE == 3) {
 #pragma unroll
-                for (int k = 0; k < N; k++) if (lane >= 16 || k >= 16) v[k] = 0;
-            }
-            if (A.coeff && live) store_row16<N>(A.coeff + (size_t)b * N * N + lane * N, v);
+            for (int k = 0; k < N; k++) dq[k] = v[k];
         }
-        if (MODE == 0 || MODE == 2) {
-            const SvtB200QuantRow qr = A.qrows[qrow];
-            const int eob = quant_row<N>(v, dq, qr, A.iscan[TS == 3 ? 0 : tx_type], lane, A.qcoeff + (size_t)b * N * N + lane * N,
-                                         A.dqcoeff + (size_t)b * N * N + lane * N, live);
-            if (live && lane == 0) A.eob[b] = (uint16_t)eob;
-        }
-        if (MODE == 3 || (MODE == 0 && (flags & SVTB200_TXJ_RECON))) {
-            int t[N];
-            if (MODE == 3) {
+        /* rows first, then columns (vp9_idct.c / inv_txfm.c 2-D drivers) */
+        Tx1D<N>::inv(TS < 3 && (tx_type & 2), dq, t);
+        tile_transpose<N>(t, tile, lane, gmask);
+        Tx1D<N>::inv(TS < 3 && (tx_type & 1), t, dq);
 #pragma unroll
-                for (int k = 0; k < N; k++) dq[k] = v[k];
-            }
-            /* rows first, then columns (vp9_idct.c / inv_txfm.c 2-D drivers) */
-            Tx1D<N>::inv(TS < 3 && (tx_type & 2), dq, t);
-            tile_transpose<N>(t, tile, lane, gmask);
-            Tx1D<N>::inv(TS < 3 && (tx_type & 1), t, dq);
-            uint8_t *d;
-            int ds;
-            const uint8_t *p;
-            int ps;
-            if (MODE == 3) { d = A.dest + (size_t)b * N * N + lane; ds = N; p = d; ps = N; }
-            else { d = A.pl.recon + A.jobs[b].recon_offset + lane; ds = A.pl.recon_stride; p = pred_p; ps = pred_s; }
-            if (live) {
-#pragma unroll
-                for (int j = 0; j < N; j++) {
-                    const int r = (int)p[(size_t)j * ps] + w16((dq[j] + (1 << (SHIFT - 1))) >> SHIFT);
-                    d[(size_t)j * ds] = (uint8_t)min(max(r, 0), 255);
-                }
-            }
+        for (int j = 0; j < N; j++) dq[j] = w16((dq[j] + (1 << (SHIFT - 1))) >> SHIFT);
+        if (MODE == 3) { uint8_t *d = A.dest + (size_t)b * N * N; store_recon_rows<N>(dq, d, N, d, N, tile, lane, gmask, live); }
+        else store_recon_rows<N>(dq, pred_p, pred_s, A.pl.recon + recon_off, A.pl.recon_stride, tile, lane, gmask, live);
+    }
+}
+
+template <int N, int MODE>
+__global__ void __launch_bounds__(TXQ_THREADS, 4) txq_kernel(const __grid_constant__ TxqArgs A) {
+    constexpr int G = TXQ_THREADS / N; /* blocks per CTA pass */
+    __shared__ int tiles[G * N * (N + 1)];
+    for (int blk0 = blockIdx.x * G; blk0 < A.n; blk0 += gridDim.x * G) txq_pass<N, MODE>(A, blk0, tiles);
+}
+
+/* Several fused batches (different transform sizes, different planes) in ONE launch: a picture's luma 32x32, chroma 16x16 and
+ * edge-row batches are a few hundred to a few thousand blocks each; launched one by one the small ones are latency-bound 5-7 us
+ * kernels.  Work unit = one CTA pass of one batch; units of all batches form one index space. */
+#define TXQ_MAX_BATCHES 8
+struct TxqMultiArgs {
+    TxqArgs batch[TXQ_MAX_BATCHES];
+    int32_t tx_size[TXQ_MAX_BATCHES];
+    int32_t unit_end[TXQ_MAX_BATCHES]; /* cumulative number of CTA passes */
+    int32_t n_batches;
+};
+__global__ void __launch_bounds__(TXQ_THREADS, 4) txq_multi_kernel(const __grid_constant__ TxqMultiArgs M) {
+    __shared__ int tiles[4 * 32 * 33];
+    const int total = M.unit_end[M.n_batches - 1];
+    for (int u = blockIdx.x; u < total; u += gridDim.x) {
+        int k = 0;
+        while (u >= M.unit_end[k]) k++;
+        const int local = u - (k ? M.unit_end[k - 1] : 0);
+        const TxqArgs &A = M.batch[k];
+        switch (M.tx_size[k]) { /* uniform over the CTA */
+        case 0: txq_pass<4, 0>(A, local * (TXQ_THREADS / 4), tiles); break;
+        case 1: txq_pass<8, 0>(A, local * (TXQ_THREADS / 8), tiles); break;
+        case 2: txq_pass<16, 0>(A, local * (TXQ_THREADS / 16), tiles); break;
+        default: txq_pass<32, 0>(A, local * (TXQ_THREADS / 32), tiles); break;
         }
     }
 }
@@ -283,6 +383,12 @@ static int fill_scans(SvtB200Ctx *c, int tx_size, TxqArgs *A) {
         A->iscan[t] = s.iscan;
     }
     if (!A->iscan[0]) { c->err = "scan tables not registered (svtb200_set_scan)"; return SVTB200_EINVAL; }
+    return 0;
+}
+
+/* planes of a fused batch: reconstruction segments are stored as 32-bit words (16-byte vectors when aligned) */
+static int check_planes(SvtB200Ctx *c, const SvtB200TxPlanes *pl) {
+    if (pl->recon && ((pl->recon_stride & 3) || ((uintptr_t)pl->recon & 3))) { c->err = "txq: recon plane base and stride must be multiples of 4"; return SVTB200_EINVAL; }
     return 0;
 }
 
@@ -354,10 +460,43 @@ int svtb200_txq_batch_dev(SvtB200Ctx *c, int tx_size, int n, const SvtB200TxJob 
     cudaSetDevice(c->device);
     TxqArgs A; memset(&A, 0, sizeof(A));
     A.jobs = jobs; A.pl = *pl; A.qrows = qrows; A.coeff = coeff; A.qcoeff = qcoeff; A.dqcoeff = dqcoeff; A.eob = eob; A.n = n;
-    int rc = fill_scans(c, tx_size, &A);
+    int rc = check_planes(c, pl);
     if (rc) return rc;
+    if ((rc = fill_scans(c, tx_size, &A))) return rc;
     SVTB200_CUDA_CHECK(c, launch_mode<0>(tx_size, A, c->sm_count, c->stream));
     c->launches++;
+    return SVTB200_OK;
+}
+
+int svtb200_txq_multi_dev(SvtB200Ctx *c, const SvtB200TxBatch *batches, int n_batches, const SvtB200QuantRow *qrows, int n_qrows) {
+    if (!c || !batches || n_batches < 1 || n_batches > TXQ_MAX_BATCHES || !qrows || n_qrows < 1) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    TxqMultiArgs M;
+    memset(&M, 0, sizeof(M));
+    int units = 0, nb = 0;
+    for (int k = 0; k < n_batches; k++) {
+        const SvtB200TxBatch &b = batches[k];
+        if (b.tx_size < 0 || b.tx_size > 3 || b.n < 0 || (b.n && (!b.jobs || !b.qcoeff || !b.dqcoeff || !b.eob || !b.planes.src || !b.planes.pred))) return SVTB200_EINVAL;
+        if (!b.n) continue;
+        int rc = check_planes(c, &b.planes);
+        if (rc) return rc;
+        TxqArgs &A = M.batch[nb];
+        A.jobs = b.jobs; A.pl = b.planes; A.qrows = qrows; A.coeff = b.coeff; A.qcoeff = b.qcoeff; A.dqcoeff = b.dqcoeff; A.eob = b.eob; A.n = b.n;
+        if ((rc = fill_scans(c, b.tx_size, &A))) return rc;
+        const int G = TXQ_THREADS / (4 << b.tx_size);
+        units += (b.n + G - 1) / G;
+        M.tx_size[nb] = b.tx_size; M.unit_end[nb] = units;
+        nb++;
+    }
+    if (!nb) return SVTB200_OK;
+    M.n_batches = nb;
+    int grid = units;
+    const int cap = (c->sm_count > 0 ? c->sm_count : 148) * 16;
+    if (grid > cap) grid = cap;
+    txq_multi_kernel<<<grid, TXQ_THREADS, 0, c->stream>>>(M);
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return SVTB200_OK;
 }
 
@@ -442,6 +581,7 @@ int svtb200_txq_batch(SvtB200Ctx *c, int tx_size, int n, const SvtB200TxJob *job
     if (!c || n < 0 || !jobs || !pl || !pl->src || !pl->pred || !qrows || n_qrows < 1 || !qcoeff || !dqcoeff || !eob || tx_size < 0 || tx_size > 3) return SVTB200_EINVAL;
     std::lock_guard<std::recursive_mutex> whole(c->mu); /* the staging buffer c->scratch is shared: one host call at a time */
     if (n == 0) return SVTB200_OK;
+    if (pl->recon) for (int i = 0; i < n; i++) if ((jobs[i].flags & SVTB200_TXJ_RECON) && (jobs[i].recon_offset & 3)) { c->err = "txq: recon_offset must be a multiple of 4"; return SVTB200_EINVAL; }
     const size_t nn = (size_t)(4 << tx_size) * (4 << tx_size), cb = (size_t)n * nn * 2;
     uint8_t *p;
     {

@@ -62,8 +62,20 @@ def test_device_decimation_and_padding_match_host_front_end(w, h, hme1):
             continue
         got, d = ctx.picture_plane(7, which)
         want = pl[key]
-        assert (d.origin_x, d.origin_y, d.width, d.height) == (st[which].origin_x, st[which].origin_y, st[which].width, st[which].height)
-        assert (got[:, :want.shape[1]] == want).all(), key
+        assert (d.origin_y, d.width, d.height) == (st[which].origin_y, st[which].width, st[which].height)
+        if which:
+            assert d.origin_x == st[which].origin_x
+            assert (got[:, :want.shape[1]] == want).all(), key
+            continue
+        # the full-resolution plane has the device's own geometry: aligned pitch / origin, the host's padded row inside it ...
+        assert d.stride % 16 == 0 and d.origin_x % 16 == 0 and d.origin_x >= frames.FULL_PAD
+        x0, hp = d.origin_x - frames.FULL_PAD, want.shape[1]
+        assert (got[:, x0:x0 + hp] == want).all(), key
+        # ... and beyond it the bytes a read past the end (before the start) of the contiguous host row finds: the next (previous) row
+        right = d.stride - (x0 + hp)
+        assert right >= 24
+        assert (got[:-1, x0 + hp:] == want[1:, :right]).all()
+        assert (got[1:, :x0] == want[:-1, hp - x0:]).all()
     ctx.close()
 
 

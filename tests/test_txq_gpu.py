@@ -108,3 +108,67 @@ def test_large_batch_properties(ctx):
     # a sample against the oracle
     idx = rng.choice(n, 64, replace=False)
     assert (c[idx] == H.oracle_fwd(3, 0, 0, x[idx])).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("shift", [0, 4, 1, 7])
+def test_txq_rows_at_any_byte_alignment(shift):
+    """Source / prediction blocks are fetched as 16-byte vectors when their address allows it and as re-aligned words otherwise:
+    every alignment of the block origin (plane stride 1004 keeps rows from sharing an alignment) against the oracle chain."""
+    rng = np.random.default_rng(60 + shift)
+    Hh, W, pad = 128, 1004 - 12, 12
+    src = rng.integers(0, 256, size=(Hh, W + pad), dtype=np.uint8)
+    pred = np.clip(src.astype(int) + rng.integers(-40, 41, size=src.shape), 0, 255).astype(np.uint8)
+    rows = H.quant_rows([45, 120])
+    ctx = api.Context(0)
+    ctx.register_scans(H.vp9_tables())
+    for ts in (3, 2, 1, 0):
+        N = 4 << ts
+        by, bx = np.meshgrid(np.arange(0, Hh - N + 1, N), np.arange(0, 256, N), indexing="ij")
+        jobs = np.zeros(by.size, dtype=api.TX_JOB_DTYPE)
+        jobs["src_offset"] = by.ravel() * src.shape[1] + bx.ravel() + shift
+        jobs["pred_offset"] = jobs["src_offset"] + 3 * ((shift & 1) and 1)      # the two planes need not share an alignment
+        jobs["recon_offset"] = by.ravel() * src.shape[1] + bx.ravel()
+        jobs["qrow"] = np.arange(by.size) & 1
+        jobs["tx_type"] = 0 if ts == 3 else np.arange(by.size) & 3
+        jobs["flags"] = 1
+        c1, q1, d1, e1, r1 = ctx.txq(ts, jobs, src, pred, np.zeros_like(src), rows)
+        for i, j in enumerate(jobs):
+            sy, sx = divmod(int(j["src_offset"]), src.shape[1])
+            py, px = divmod(int(j["pred_offset"]), src.shape[1])
+            ry, rx = divmod(int(j["recon_offset"]), src.shape[1])
+            resid = (src[sy:sy + N, sx:sx + N].astype(np.int16) - pred[py:py + N, px:px + N].astype(np.int16))[None]
+            c0 = H.oracle_fwd(ts, int(j["tx_type"]), 0, resid)
+            q0, d0, e0 = H.oracle_quant(ts, int(j["tx_type"]), c0, rows, [int(j["qrow"])])
+            r0 = H.oracle_inv_add(ts, int(j["tx_type"]), d0, e0, pred[py:py + N, px:px + N][None])[0]
+            assert (c1[i] == c0[0]).all() and (q1[i] == q0[0]).all() and (d1[i] == d0[0]).all() and e1[i] == e0[0], (ts, i)
+            assert (r1[ry:ry + N, rx:rx + N] == r0).all(), (ts, i)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_txq_multi_launch_equals_single_batches():
+    """svtb200_txq_multi_dev: batches of all four transform sizes on different planes in ONE launch == the same batches one by one."""
+    rng = np.random.default_rng(77)
+    rows = H.quant_rows([30, 180])
+    batches = []
+    for ts, (Hh, W) in zip((3, 2, 1, 0, 2), ((160, 416), (80, 208), (40, 200), (36, 100), (16, 2000))):
+        N = 4 << ts
+        src = rng.integers(0, 256, size=(Hh, W), dtype=np.uint8)
+        pred = np.clip(src.astype(int) + rng.integers(-25, 26, size=src.shape), 0, 255).astype(np.uint8)
+        by, bx = np.meshgrid(np.arange(0, Hh - N + 1, N), np.arange(0, W - N + 1, N), indexing="ij")
+        jobs = np.zeros(by.size, dtype=api.TX_JOB_DTYPE)
+        jobs["src_offset"] = jobs["pred_offset"] = jobs["recon_offset"] = by.ravel() * W + bx.ravel()
+        jobs["qrow"] = np.arange(by.size) % 2
+        jobs["tx_type"] = 0 if ts == 3 else np.arange(by.size) & 3
+        jobs["flags"] = 1
+        batches.append((ts, jobs, src, pred, np.zeros_like(src)))
+    ctx = api.Context(0)
+    ctx.register_scans(H.vp9_tables())
+    launches0 = ctx.launches()
+    got = ctx.txq_multi(batches, rows)
+    assert ctx.launches() - launches0 == 1
+    for (ts, jobs, src, pred, rec), (q, dq, eob, r) in zip(batches, got):
+        _, q0, d0, e0, r0 = ctx.txq(ts, jobs, src, pred, rec, rows)
+        assert (q == q0).all() and (dq == d0).all() and (eob == e0).all() and (r == r0).all(), ts
+    ctx.close()
