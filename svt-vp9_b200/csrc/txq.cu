@@ -358,6 +358,7 @@ __global__ void __launch_bounds__(TXQ_THREADS, 4) txq_multi_kernel(const __grid_
         case 2: txq_pass<16, 0>(A, local * (TXQ_THREADS / 16), tiles); break;
         default: txq_pass<32, 0>(A, local * (TXQ_THREADS / 32), tiles); break;
         }
+        __syncthreads(); /* the next unit may belong to a batch of another size, which partitions the tile memory differently between the warps */
     }
 }
 
