@@ -15,9 +15,15 @@
 #define SVTB200_DEV_PAD_L 80   /* svtb200_picture_upload_luma: device columns left of the picture (multiple of 16, >= the reference's 68) */
 #define SVTB200_DEV_PAD_R 96   /* ... and right of it: the reference's 68 + the samples its windows read past the row end */
 
+struct DevTensorMap { /* a cached CUtensorMap of one plane for one box shape (me.cu) */
+    alignas(64) uint64_t opaque[16];
+    const uint8_t *buf = nullptr;
+    int32_t stride = 0, rows = 0, box_w = 0, box_h = 0;
+};
 struct DevPlane {
     uint8_t *buf = nullptr;
     int32_t  stride = 0, ox = 0, oy = 0, w = 0, h = 0, rows = 0;
+    DevTensorMap tm[2]; /* two box shapes per plane at most (source super-block / search window) */
 };
 struct DevPicture {
     DevPlane    pl[3];            /* full, quarter, sixteenth */
@@ -42,6 +48,7 @@ struct SvtB200Ctx {
     uint64_t     launches = 0;
     int          smem_optin = 0, sm_count = 0;
     std::map<uint64_t, DevPicture> pics;
+    uint32_t *me_counter = nullptr; int me_counter_next = 0; /* ring of super-block counters of the persistent ME grid, one per launch in flight */
     /* ME scratch, grown on demand */
     uint8_t *interp_scratch = nullptr; size_t interp_scratch_bytes = 0;
     void    *me_out = nullptr;  size_t me_out_bytes = 0;

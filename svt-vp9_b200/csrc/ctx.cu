@@ -44,6 +44,7 @@ void svtb200_destroy(SvtB200Ctx *c) {
     if (c->interp_scratch) cudaFree(c->interp_scratch);
     if (c->me_out) cudaFree(c->me_out);
     if (c->me_rcme) cudaFree(c->me_rcme);
+    if (c->me_counter) cudaFree(c->me_counter);
     if (c->me_trace) cudaFree(c->me_trace);
     if (c->scratch) cudaFree(c->scratch);
     if (c->pred_desc) cudaFree(c->pred_desc);
@@ -299,7 +300,7 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
         if (lvl == 1 && !make_quarter) { if (d->buf) cudaFree(d->buf); *d = DevPlane(); continue; }
         const int step = lvl == 1 ? 2 : 4, pad = lvl == 1 ? quarter_pad : sixteenth_pad;
         const int w = (f->w + step - 1) / step, h = (f->h + step - 1) / step;
-        const int stride = (w + 2 * pad + 3) & ~3; /* multiple of 4 for the word stores; the reference's strides are */
+        const int stride = (w + 2 * pad + 15) & ~15; /* multiple of 16: word stores here, legal TMA rows for the HME windows */
         if ((rc = alloc_plane(c, d, stride, h + 2 * pad))) return rc;
         d->ox = pad; d->oy = pad; d->w = w; d->h = h;
         pa_decimate_kernel<<<dim3((stride / 4 + 127) / 128, d->rows), blk, 0, c->up>>>(f->buf, f->stride, f->ox, f->oy, d->buf, stride, pad, pad, w, h,

@@ -1,6 +1,48 @@
 /* me.cu -- host side of S1: svtb200_me_picture[_dev] (see include/svtb200.h). */
+#include <cuda.h>
+#include <algorithm>
+#include <stdlib.h>
 #include "common.cuh"
 #include "me_kernel.cuh"
+
+/* cuTensorMapEncodeTiled through the runtime's driver entry point (no link-time dependency on libcuda) */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *, const cuuint32_t *,
+                                  const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess && q == cudaDriverEntryPointSuccess) fn = (EncodeTiledFn)p;
+        else cudaGetLastError();
+    }
+    return fn;
+}
+static_assert(sizeof(CUtensorMap) == sizeof(MeTensorMap), "tensor map size");
+
+/* 2-D byte tensor over a whole device plane (pitch x rows) with a box_w x box_h box; cached in the plane.  Fails (-> software
+ * staging) when the plane is not TMA-legal: base and pitch multiples of 16, box sides <= 256, box width a multiple of 16. */
+static bool plane_tensor_map(DevPlane &pl, int box_w, int box_h, MeTensorMap *out) {
+    if (!pl.buf || ((uintptr_t)pl.buf & 15) || (pl.stride & 15) || box_w <= 0 || box_h <= 0 || box_w > 256 || box_h > 256 || (box_w & 15)) return false;
+    for (int i = 0; i < 2; i++) {
+        DevTensorMap &t = pl.tm[i];
+        if (t.buf == pl.buf && t.stride == pl.stride && t.rows == pl.rows && t.box_w == box_w && t.box_h == box_h) { memcpy(out, t.opaque, sizeof(*out)); return true; }
+    }
+    EncodeTiledFn enc = encode_tiled();
+    if (!enc) return false;
+    CUtensorMap m;
+    const cuuint64_t dims[2] = {(cuuint64_t)pl.stride, (cuuint64_t)pl.rows}, strides[1] = {(cuuint64_t)pl.stride};
+    const cuuint32_t box[2] = {(cuuint32_t)box_w, (cuuint32_t)box_h}, estr[2] = {1, 1};
+    if (enc(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, pl.buf, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+            CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS) return false;
+    DevTensorMap &t = (pl.tm[0].buf == pl.buf && pl.tm[0].stride == pl.stride && pl.tm[0].rows == pl.rows) ? pl.tm[1] : pl.tm[0]; /* keep the other shape of the same buffer */
+    memcpy(t.opaque, &m, sizeof(m));
+    t.buf = pl.buf; t.stride = pl.stride; t.rows = pl.rows; t.box_w = box_w; t.box_h = box_h;
+    memcpy(out, &m, sizeof(*out));
+    return true;
+}
 
 static void to_dev(const DevPlane &d, MePlaneDev *o) { o->buf = d.buf; o->stride = d.stride; o->ox = d.ox; o->oy = d.oy; o->w = d.w; o->h = d.h; }
 
@@ -27,9 +69,41 @@ static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, c
     A.sbs_w = (P->luma_width + ME_SB - 1) / ME_SB;
     A.n_sb  = A.sbs_w * ((P->luma_height + ME_SB - 1) / ME_SB);
     A.out = out_dev; A.rcme = rcme_dev;
+    A.n_work = A.n_sb;
     A.win_bytes = me_window_bytes(*P);
     A.interp_plane_bytes = me_interp_plane_bytes(*P);
     A.interp_in_smem = 1;
+    /* ---- TMA staging where the planes allow it (svtb200_picture_upload_luma's device geometry does) */
+    static const bool no_tma = getenv("SVTB200_ME_NO_TMA") != nullptr;
+    if (!no_tma) {
+        DevPicture &pc = itc->second;
+        if (plane_tensor_map(pc.pl[0], ME_SB, ME_SB, &A.tm_cur)) A.tma |= ME_TMA_SRC;
+        const int saw = P->search_area_width < 127 ? P->search_area_width : 127, sah = P->search_area_height < 127 ? P->search_area_height : 127;
+        const int fw = (saw + ME_SB - 1 + 16 + ME_HALO_X + 8 + 15) & ~15, fh = me_fp_rows(sah) + 1;
+        bool ok = true;
+        for (int l = 0; l < 2 && ok; l++) ok = plane_tensor_map(c->pics.find(ref_id[l < P->num_lists ? l : 0])->second.pl[0], fw, fh, &A.tm_ref[l]);
+        if (ok) { A.tma |= ME_TMA_FP; A.fp_box_w = fw; A.fp_box_h = fh; if (fw * fh + 16 > A.win_bytes) A.win_bytes = fw * fh + 16; }
+        if (P->enable_hme_flag && P->enable_hme_level0) {
+            /* level-0 stripes: the widest quadrant (or the whole area in single-quadrant mode), as many candidate rows as fit the buffer */
+            int tw = (P->hme_level0_total_search_area_width * P->hme_l0_multiplier_x) / 100, th = (P->hme_level0_total_search_area_height * P->hme_l0_multiplier_y) / 100;
+            const bool single = P->single_hme_quadrant && !P->enable_hme_level1 && !P->enable_hme_level2;
+            if (!single) {
+                tw = th = 0;
+                for (int i = 0; i < 2; i++) {
+                    tw = std::max(tw, (P->hme_level0_search_area_in_width[i] * P->hme_l0_multiplier_x) / 100);
+                    th = std::max(th, (P->hme_level0_search_area_in_height[i] * P->hme_l0_multiplier_y) / 100);
+                }
+            }
+            const int hw = (tw + 16 + 8 + 15) & ~15, extra = 14;
+            int stripe = th < ME_HME_STRIPE ? th : ME_HME_STRIPE;
+            if (stripe < 1) stripe = 1;
+            while (stripe > 8 && hw * (stripe + extra) + 16 > A.win_bytes) stripe -= 8;
+            const int hh = stripe + extra;
+            ok = hw <= 256 && hh <= 256;
+            for (int l = 0; l < 2 && ok; l++) ok = plane_tensor_map(c->pics.find(ref_id[l < P->num_lists ? l : 0])->second.pl[2], hw, hh, &A.tm_ref16[l]);
+            if (ok) { A.tma |= ME_TMA_HME0; A.hme_box_w = hw; A.hme_box_h = hh; if (hw * hh + 16 > A.win_bytes) A.win_bytes = hw * hh + 16; }
+        }
+    }
     MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 1, me_bip0_bytes(*P));
     if (L.total > c->smem_optin) {
         A.interp_in_smem = 0;
@@ -46,9 +120,23 @@ static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, c
         A.trace = (MeTraceDev *)c->me_trace;
     }
     SVTB200_CUDA_CHECK(c, cudaFuncSetAttribute(me_sb_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, L.total));
+    /* persistent grid: as many CTAs as stay resident (4 per SM by registers, fewer if the windows are large), pulling super-blocks
+     * from a counter; 64 counters in a ring so that launches in flight on different queues never share one */
+    int grid = A.n_sb;
+    static const bool no_persist = getenv("SVTB200_ME_NO_PERSISTENT") != nullptr;
+    if (!no_persist) {
+        if (!c->me_counter && cudaMalloc((void **)&c->me_counter, 64 * sizeof(uint32_t)) != cudaSuccess) { cudaGetLastError(); c->me_counter = nullptr; }
+        if (c->me_counter) {
+            int per_sm = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, me_sb_kernel, ME_THREADS, (size_t)L.total) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+            A.sb_counter = c->me_counter + (c->me_counter_next++ & 63);
+            SVTB200_CUDA_CHECK(c, cudaMemsetAsync(A.sb_counter, 0, sizeof(uint32_t), c->stream));
+            grid = std::min(A.n_sb, per_sm * (c->sm_count > 0 ? c->sm_count : 148));
+        }
+    }
     svtb200_pic_acquire(c, itc->second);
     for (int l = 0; l < P->num_lists; l++) svtb200_pic_acquire(c, c->pics.find(ref_id[l])->second);
-    me_sb_kernel<<<A.n_sb, ME_THREADS, L.total, c->stream>>>(A);
+    me_sb_kernel<<<grid, ME_THREADS, L.total, c->stream>>>(A);
     svtb200_pic_release(c, itc->second);
     for (int l = 0; l < P->num_lists; l++) svtb200_pic_release(c, c->pics.find(ref_id[l])->second);
     c->launches++;

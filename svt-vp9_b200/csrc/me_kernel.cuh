@@ -50,7 +50,14 @@ struct MeTraceDev { /* optional per-SB stage outputs, same fields as the oracle'
     uint8_t  subpel_enable[2];
 };
 
+/* a CUtensorMap (cuda.h) without the header: 128 opaque bytes, 64-byte aligned, passed inside the __grid_constant__ kernel argument */
+struct alignas(64) MeTensorMap { uint64_t opaque[16]; };
+#define ME_TMA_SRC 1  /* source super-block: 64x64 box of the current picture's full plane */
+#define ME_TMA_FP  2  /* full-pel search window (+ halo): fp_box_w x fp_box_h box of the reference's full plane */
+#define ME_TMA_HME0 4 /* HME level-0 stripes: hme_box_w x hme_box_h box of the reference's 1/16 plane */
+
 struct MeKernelArgs {
+    MeTensorMap        tm_cur, tm_ref[2], tm_ref16[2]; /* valid per the bits of 'tma' */
     SvtB200MeParams    P;
     MePlaneDev         cur[3], ref[2][3];
     SvtB200MeCuResult *out;
@@ -61,7 +68,11 @@ struct MeKernelArgs {
     int32_t            interp_plane_bytes; /* capacity of one half-pel plane */
     int32_t            win_bytes;          /* capacity of the search-window staging buffer */
     int32_t            sbs_w, n_sb;
+    int32_t            n_work;             /* super-blocks of this launch (n_sb for a whole picture) */
     int32_t            sb_first;           /* SB index of block 0 (partial launches in the logic tests) */
+    int32_t            tma;                /* ME_TMA_* bits: windows staged by cp.async.bulk.tensor + mbarrier instead of by the threads */
+    int32_t            fp_box_w, fp_box_h, hme_box_w, hme_box_h;
+    uint32_t          *sb_counter;         /* persistent grid: next super-block to take (null: block b takes super-block b) */
 };
 
 /* z-order tables (raster PU index -> internal index), EbMotionEstimation.c:51-54 */
@@ -84,6 +95,7 @@ struct MeSbState { /* scalar control state of one SB, written by thread 0 */
     int16_t  l0x[2][2], l0y[2][2], l1x[2][2], l1y[2][2], l2x[2][2], l2y[2][2];
     uint64_t l0s[2][2], l1s[2][2], l2s[2][2];
     int16_t  hme_x, hme_y;
+    int32_t  next_sb;               /* persistent grid: the super-block this CTA took from the counter */
     int32_t  srh;                   /* the reference's never-reset quadrant row counter */
     int32_t  e32, e16, e8, eq;      /* sub-pel enables of the current list */
     int32_t  istride[2], interp_ok[2];
@@ -102,6 +114,41 @@ __device__ __forceinline__ const uint8_t *me_pix(const MePlaneDev &p, int x, int
 __device__ __forceinline__ int16_t me_mvx(uint32_t mv) { return (int16_t)(mv & 0xffff); }
 __device__ __forceinline__ int16_t me_mvy(uint32_t mv) { return (int16_t)(mv >> 16); }
 __device__ __forceinline__ uint32_t me_mkmv(int x, int y) { return ((uint32_t)(uint16_t)y << 16) | (uint16_t)x; }
+
+/* ---------------------------------------------------------------------------------------------
+ * TMA window staging: one elected thread arms the CTA's mbarrier with the box size and issues cp.async.bulk.tensor (the copy
+ * engine fetches the 2-D box at ANY byte coordinate and lays it down densely, i.e. the re-alignment the software path does with
+ * funnel shifts comes for free); every thread then waits on the barrier's phase.  Out-of-range parts of a box are zero-filled
+ * and never consumed.
+ * ------------------------------------------------------------------------------------------- */
+struct MeTmaState { uint32_t mbar, phase; }; /* shared-memory address of the mbarrier, parity of the next completion */
+#if defined(__CUDA_ARCH__)
+__device__ __forceinline__ uint32_t me_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void me_mbar_init(uint32_t mbar) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(mbar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+/* thread 0 only.  Every thread of the CTA has passed a barrier since its last access to dst. */
+__device__ __forceinline__ void me_tma_issue(const MeTensorMap *tm, uint8_t *dst, int x, int y, uint32_t bytes, const MeTmaState &ts) {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic-proxy accesses to dst before the async-proxy write */
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(ts.mbar), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(me_smem_u32(dst)), "l"(tm), "r"(ts.mbar), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void me_tma_wait(MeTmaState &ts) {
+    uint32_t done = 0;
+    for (uint32_t spins = 0; !done; spins++) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(ts.mbar), "r"(ts.phase) : "memory");
+        if (spins > (1u << 24)) __trap(); /* a copy that never lands (bad descriptor) must end the launch with an error, not hang the device */
+    }
+    ts.phase ^= 1;
+}
+#else
+__device__ __forceinline__ void me_mbar_init(uint32_t) {}
+__device__ __forceinline__ void me_tma_issue(const MeTensorMap *, uint8_t *, int, int, uint32_t, const MeTmaState &) {}
+__device__ __forceinline__ void me_tma_wait(MeTmaState &) {}
+#endif
 
 /* ---------------------------------------------------------------------------------------------
  * packed-byte primitives
@@ -420,7 +467,7 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
  * level 0/1 read the source block from the decimated planes of the current picture, level 2
  * from the shared-memory SB. */
 __device__ static void me_hme_search(const MeKernelArgs &A, int list, int level, MeSbState *st, const uint8_t *src,
-                                     uint8_t *hsrc, uint8_t *win, uint32_t *posacc) {
+                                     uint8_t *hsrc, uint8_t *win, uint32_t *posacc, MeTmaState &tma) {
     const int w = st->s_w, h = st->s_h;
     /* source block: every other row of the (decimated) SB */
     if (level == 2) {
@@ -440,11 +487,17 @@ __device__ static void me_hme_search(const MeKernelArgs &A, int list, int level,
     if (threadIdx.x == 0) st->best_key = ~0ull;
     const MePlaneDev &rp = A.ref[list][level == 0 ? 2 : level == 1 ? 1 : 0];
     const int extra = 2 * (h - 1), sah = st->w_sah;
-    int stripe = A.win_bytes / st->w_pitch - extra - 1; /* candidate rows the buffer can hold */
+    const bool by_tma = level == 0 && (A.tma & ME_TMA_HME0); /* thread 0 set w_pitch = hme_box_w */
+    int stripe = by_tma ? A.hme_box_h - extra : A.win_bytes / st->w_pitch - extra - 1; /* candidate rows the buffer can hold */
     if (stripe < 1) stripe = 1;
     for (int y0 = 0; y0 < sah; y0 += stripe) {
         const int n = min(stripe, sah - y0);
-        me_stage_window(win, st->w_pitch, rp, st->w_x, st->w_y + y0, st->w_saw + w - 1, n + extra);
+        if (by_tma) {
+            if (threadIdx.x == 0) me_tma_issue(&A.tm_ref16[list], win, rp.ox + st->w_x, rp.oy + st->w_y + y0, (uint32_t)(A.hme_box_w * A.hme_box_h), tma);
+            me_tma_wait(tma);
+        } else {
+            me_stage_window(win, st->w_pitch, rp, st->w_x, st->w_y + y0, st->w_saw + w - 1, n + extra);
+        }
         __syncthreads();
         me_window_search(hsrc, win, st, posacc, y0, n);
         __syncthreads();
@@ -938,7 +991,7 @@ __device__ __forceinline__ uint32_t me_pred_word(const MePred &p, int y, int k) 
  * shared-memory layout of one CTA and the launch plan (shared by the host code and the emulation)
  * ------------------------------------------------------------------------------------------- */
 struct MeSmemLayout {
-    int src, hsrc, win, interp, bip0, pu_key, bsad, bmv, bssd, bip, dir, posacc, dist, sad, state, total;
+    int src, hsrc, win, interp, bip0, pu_key, bsad, bmv, bssd, bip, dir, posacc, dist, sad, state, mbar, total;
 };
 __host__ __device__ static inline int me_align16(int v) { return (v + 15) & ~15; }
 __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int interp_plane_bytes, int interp_in_smem, int bip0_bytes) {
@@ -946,7 +999,7 @@ __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int
     int o = 0;
     L.src = o; o += ME_SB * ME_SB;
     L.hsrc = o; o += 64 * 32;
-    L.win = o; o += me_align16(win_bytes);
+    L.win = o; o += (win_bytes + 127) & ~127; /* TMA destinations are 128-byte aligned (src and hsrc keep it so) */
     L.interp = o; o += interp_in_smem ? 3 * me_align16(interp_plane_bytes) : 0; /* the planes of the list being searched */
     L.bip0 = o; o += me_align16(bip0_bytes);                                  /* list-0 predictions kept for bi-prediction */
     L.pu_key = o; o += me_align16(85 * 8);
@@ -959,6 +1012,7 @@ __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int
     L.dist = o; o += me_align16(85 * 9 * 4);
     L.sad = o; o += me_align16(85 * 9 * 4);
     L.state = o; o += me_align16((int)sizeof(MeSbState));
+    L.mbar = o; o += 16;
     L.total = o;
     return L;
 }
@@ -1012,12 +1066,12 @@ static inline int me_interp_plane_bytes(const SvtB200MeParams &P) {
 #ifdef SVTB200_CPU_EMU
 #define ME_DYN_SMEM(name) uint8_t *name = emu_dyn_smem
 #else
-#define ME_DYN_SMEM(name) extern __shared__ __align__(16) uint8_t name[]
+#define ME_DYN_SMEM(name) extern __shared__ __align__(128) uint8_t name[]
 #endif
 
 /* one HME level over all quadrants of one list (uniform control flow: every thread runs this) */
 __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, int single, MeSbState *st, const uint8_t *src,
-                                    uint8_t *hsrc, uint8_t *win, uint32_t *posacc) {
+                                    uint8_t *hsrc, uint8_t *win, uint32_t *posacc, MeTmaState &tma) {
     const SvtB200MeParams &P = A.P;
     const int nqx = single ? 1 : P.number_hme_search_region_in_width, nqy = single ? 1 : P.number_hme_search_region_in_height;
     for (int qy = 0; qy < nqy; qy++)
@@ -1047,6 +1101,7 @@ __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, 
                     me_clip_window(oy, &y_org, &sah, rp.oy - 1, rp.h);
                     if (single && (saw & 15)) saw = (int16_t)((saw >> 4) << 4);
                     me_set_window(st, st->sbw >> 2, (st->sbh >> 2) >> 1, ox + x_org, oy + y_org, saw, sah);
+                    if (A.tma & ME_TMA_HME0) st->w_pitch = A.hme_box_w; /* the box lands densely at its own width */
                 } else if (level == 1) {
                     const MePlaneDev &rp = A.ref[list][1];
                     const int ox = st->ox >> 1, oy = st->oy >> 1;
@@ -1070,7 +1125,7 @@ __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, 
                 x_org_s = x_org; y_org_s = y_org;
             }
             __syncthreads();
-            me_hme_search(A, list, level, st, src, hsrc, win, posacc);
+            me_hme_search(A, list, level, st, src, hsrc, win, posacc, tma);
             if (threadIdx.x == 0) {
                 /* outputs keep their previous contents when no candidate beat 0xffffff */
                 int16_t *px = level == 0 ? &st->l0x[qx][qy] : level == 1 ? &st->l1x[qx][qy] : &st->l2x[qx][qy];
@@ -1106,8 +1161,30 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
     uint32_t *dist = (uint32_t *)(smem + L.dist), *sadv = (uint32_t *)(smem + L.sad);
     uint8_t  *bip0 = smem + L.bip0;
     MeSbState *st = (MeSbState *)(smem + L.state);
-    const int sb = blockIdx.x + A.sb_first, t = threadIdx.x, nl = P.num_lists;
+    const int t = threadIdx.x, nl = P.num_lists;
     const int ipb = me_align16(A.interp_plane_bytes);
+    MeTmaState tma;
+    tma.phase = 0;
+#if defined(__CUDA_ARCH__)
+    tma.mbar = me_smem_u32(smem + L.mbar);
+    if (A.tma && t == 0) me_mbar_init(tma.mbar);
+#else
+    tma.mbar = 0;
+#endif
+    /* persistent grid: a CTA keeps taking super-blocks from the picture's counter until none is left (without a counter block b
+     * does super-block b) -- no tail of partly filled waves, and the work of a slow super-block is balanced by the others */
+    for (int round = 0;; round++) {
+    int sb;
+    if (A.sb_counter) {
+        __syncthreads(); /* everyone has finished the previous super-block (st, the result arrays and the windows are reused) */
+        if (t == 0) st->next_sb = (int)atomicAdd(A.sb_counter, 1u);
+        __syncthreads();
+        sb = st->next_sb;
+    } else {
+        sb = round ? A.n_sb : (int)blockIdx.x;
+    }
+    if (sb >= A.n_work) break;
+    sb += A.sb_first;
     MeInterp ip[2];
     for (int l = 0; l < 2; l++) {
         uint8_t *base = A.interp_in_smem ? smem + L.interp /* one set, reused by list 1 */
@@ -1125,12 +1202,14 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
             st->l0s[a][b] = st->l1s[a][b] = st->l2s[a][b] = 0;
         }
         st->interp_ok[0] = st->interp_ok[1] = 0;
+        /* source SB: all 64 rows from the padded plane */
+        if (A.tma & ME_TMA_SRC) me_tma_issue(&A.tm_cur, src, A.cur[0].ox + st->ox, A.cur[0].oy + st->oy, ME_SB * ME_SB, tma);
     }
     for (int i = t; i < 2 * 85; i += ME_THREADS) { bsad[i] = ME_MAX_SAD; bmv[i] = 0; bssd[i] = 0; }
     for (int i = t; i < 85; i += ME_THREADS) { bip[i] = 0; dir[i] = 0; }
     __syncthreads();
-    /* source SB: all 64 rows from the padded plane */
-    me_stage_window(src, ME_SB, A.cur[0], st->ox, st->oy, ME_SB - 4, ME_SB);
+    if (A.tma & ME_TMA_SRC) me_tma_wait(tma);
+    else me_stage_window(src, ME_SB, A.cur[0], st->ox, st->oy, ME_SB - 4, ME_SB);
     __syncthreads();
 
     for (int list = 0; list < nl; list++) {
@@ -1190,9 +1269,9 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
                     if (P.enable_hme_level0 && single) st->srh = 0;
                 }
                 __syncthreads();
-                if (P.enable_hme_level0) me_hme_level(A, list, 0, single, st, src, hsrc, win, posacc);
-                if (P.enable_hme_level1) me_hme_level(A, list, 1, 0, st, src, hsrc, win, posacc);
-                if (P.enable_hme_level2) me_hme_level(A, list, 2, 0, st, src, hsrc, win, posacc);
+                if (P.enable_hme_level0) me_hme_level(A, list, 0, single, st, src, hsrc, win, posacc, tma);
+                if (P.enable_hme_level1) me_hme_level(A, list, 1, 0, st, src, hsrc, win, posacc, tma);
+                if (P.enable_hme_level2) me_hme_level(A, list, 2, 0, st, src, hsrc, win, posacc, tma);
                 if (t == 0) {
                     int16_t (*fx)[2] = 0, (*fy)[2] = 0;
                     uint64_t (*fs)[2] = 0;
@@ -1244,16 +1323,21 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
             me_clip_window(st->ox, &xo, &saw, ME_SB - 1, P.luma_width);
             me_clip_window(st->oy, &yo, &sah, ME_SB - 1, P.luma_height);
             st->sa_ox[list] = xo; st->sa_oy[list] = yo; st->saw[list] = saw; st->sah[list] = sah;
-            st->fp_pitch = me_fp_pitch(saw);
+            st->fp_pitch = (A.tma & ME_TMA_FP) ? A.fp_box_w : me_fp_pitch(saw);
+            if (A.tma & ME_TMA_FP) /* the window buffer's last readers (HME, or list 0's bi-prediction stash) are behind a barrier */
+                me_tma_issue(&A.tm_ref[list], win, rp.ox + st->ox + xo - ME_HALO_X, rp.oy + st->oy + yo - ME_HALO_Y, (uint32_t)(A.fp_box_w * A.fp_box_h), tma);
             if (A.trace) { A.trace[sb].sa_ox[list] = xo; A.trace[sb].sa_oy[list] = yo; A.trace[sb].sa_w[list] = saw; A.trace[sb].sa_h[list] = sah; }
         }
         __syncthreads();
         /* ---- full-pel search: the window (with the halo the half-pel filters need) is staged once */
         const int fpp = st->fp_pitch;
         const uint8_t *rb = win + ME_HALO_Y * fpp + ME_HALO_X;
-        me_stage_window(win, fpp, rp, st->ox + st->sa_ox[list] - ME_HALO_X, st->oy + st->sa_oy[list] - ME_HALO_Y,
-                        st->saw[list] + ME_SB - 1 + 16 + ME_HALO_X, me_fp_rows(st->sah[list]));
-        __syncthreads();
+        if (A.tma & ME_TMA_FP) me_tma_wait(tma);
+        else {
+            me_stage_window(win, fpp, rp, st->ox + st->sa_ox[list] - ME_HALO_X, st->oy + st->sa_oy[list] - ME_HALO_Y,
+                            st->saw[list] + ME_SB - 1 + 16 + ME_HALO_X, me_fp_rows(st->sah[list]));
+            __syncthreads();
+        }
         me_fullpel(src, rb, fpp, st, list, pu_key);
         if (t < 85) {
             const unsigned long long k = pu_key[t];
@@ -1378,6 +1462,7 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
         for (int i = 5; i < 21; i++) s += dist[i];
         A.rcme[sb] = s;
     }
+    } /* next super-block */
 }
 
 #endif /* SVTB200_ME_KERNEL_CUH */

@@ -23,8 +23,13 @@ extern "C" int me_emu_run(const SvtB200MeParams *P, const SvtB200Plane cur[3], c
     std::vector<uint8_t> scratch;
     if (force_global_interp) { scratch.resize((size_t)A.n_sb * 6 * me_align16(A.interp_plane_bytes)); A.interp_scratch = scratch.data(); }
     A.sb_first = sb_begin;
+    A.n_work = sb_end - sb_begin;
+    /* as the host code launches it: a persistent grid pulling super-blocks from a counter (two CTAs here), so that state carried
+     * from one super-block of a CTA to its next is exercised too */
+    uint32_t counter = 0;
+    A.sb_counter = &counter;
     MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, A.interp_in_smem, me_bip0_bytes(*P));
-    emu_launch(dim3(sb_end - sb_begin), dim3(ME_THREADS), L.total, [&] { me_sb_kernel(A); });
+    emu_launch(dim3(A.n_work < 2 ? A.n_work : 2), dim3(ME_THREADS), L.total, [&] { me_sb_kernel(A); });
     return L.total;
 }
 extern "C" int me_emu_check_tables() {

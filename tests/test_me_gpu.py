@@ -31,19 +31,29 @@ def ctx():
     c.close()
 
 
-def _upload(ctx, pic_id, planes3):
-    ctx.picture_upload(pic_id, planes3[0], planes3[1] if planes3[1].buf else None, planes3[2] if planes3[2].buf else None)
+LAYOUTS = ["host_layout", "device_layout"]
 
 
+def _upload(ctx, pic_id, planes3, layout="host_layout"):
+    """host_layout: the three planes as the reference holds them (svtb200_picture_upload; pitch 2 * 68 + width: windows staged by the
+    threads); device_layout: svtb200_picture_upload_luma (aligned pitch, padding and decimations made on the device: windows staged by
+    TMA)."""
+    if layout == "host_layout":
+        ctx.picture_upload(pic_id, planes3[0], planes3[1] if planes3[1].buf else None, planes3[2] if planes3[2].buf else None)
+    else:
+        ctx.picture_upload_luma(pic_id, planes3[0], planes3[1].origin_x if planes3[1].buf else 32, planes3[2].origin_x, bool(planes3[1].buf))
+
+
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(p)[:-7] for p in FIXTURES])
-def test_cuda_matches_reference_dump(ctx, path):
+def test_cuda_matches_reference_dump(ctx, path, layout):
     pic = H.MePicture(path)
     cur, r0 = pic.cur_planes(), pic.ref_planes(0)
-    _upload(ctx, 1, cur)
-    _upload(ctx, 2, r0)
+    _upload(ctx, 1, cur, layout)
+    _upload(ctx, 2, r0, layout)
     ids = [2]
     if pic.params.num_lists == 2:
-        _upload(ctx, 3, pic.ref_planes(1))
+        _upload(ctx, 3, pic.ref_planes(1), layout)
         ids.append(3)
     out = ctx.me_picture(pic.params, 1, ids)
     ok = H.me_equal(out, pic.expected, pic.params.num_lists)
@@ -64,13 +74,14 @@ CASES = [
 ]
 
 
+@pytest.mark.parametrize("layout", LAYOUTS)
 @pytest.mark.parametrize("name,w,h,mk", CASES, ids=[c[0] for c in CASES])
-def test_cuda_matches_oracle(ctx, name, w, h, mk):
+def test_cuda_matches_oracle(ctx, name, w, h, mk, layout):
     P = mk(w, h)
     pl = _synthetic_pair(w, h, seed=zlib.crc32(name.encode()) & 0xffff)
     structs = [frames.plane_structs(p) for p in pl]
     for i, s in enumerate(structs):
-        _upload(ctx, 10 + i, s)
+        _upload(ctx, 10 + i, s, layout)
     ids = [10, 12] if P.num_lists == 2 else [10]
     out, rcme = ctx.me_picture(P, 11, ids, want_rcme=True)
     n_sb = ((w + 63) // 64) * ((h + 63) // 64)
@@ -84,13 +95,14 @@ def test_cuda_matches_oracle(ctx, name, w, h, mk):
     assert (rcme == d16).all()
 
 
-def test_full_size_4k_picture(ctx):
+@pytest.mark.parametrize("layout", LAYOUTS)
+def test_full_size_4k_picture(ctx, layout):
     w, h = 3840, 2160
     P = presets.me_params_4k_m8(w, h, 2, 2, (0, 8))
     pl = _synthetic_pair(w, h, seed=11, shift=(7, 5))
     structs = [frames.plane_structs(p) for p in pl]
     for i, s in enumerate(structs):
-        _upload(ctx, 20 + i, s)
+        _upload(ctx, 20 + i, s, layout)
     out = ctx.me_picture(P, 21, [20, 22])
     n_sb = 60 * 34
     r = out.reshape(n_sb, 85)

@@ -77,8 +77,8 @@ def test_cuda_me_full_4k_picture_matches_reference_functions(tl, nl, poc):
     threads = max(1, min(64, len(os.sched_getaffinity(0))))
     ref = H.refdrv_me_picture(P, st[1], st[0], st[2] if nl == 2 else None, n_sb, threads=threads)
     ctx = api.Context(0)
-    for i, s_ in enumerate(st):
-        ctx.picture_upload(i, s_[0], s_[1], s_[2])
+    for i, s_ in enumerate(st):   # the bench's path: device geometry, windows staged by TMA
+        ctx.picture_upload_luma(i, s_[0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, bool(P.enable_hme_level1))
     out = ctx.me_picture(P, 1, [0, 2] if nl == 2 else [0])
     ctx.close()
     ok = H.me_equal(out, ref, nl)
@@ -100,8 +100,8 @@ def test_cuda_me_full_4k_m5_tune0_picture_matches_reference_functions(tl, nl, po
     threads = max(1, min(64, len(os.sched_getaffinity(0))))
     ref = H.refdrv_me_picture(P, st[1], st[0], st[2] if nl == 2 else None, n_sb, threads=threads)
     ctx = api.Context(0)
-    for i, s_ in enumerate(st):
-        ctx.picture_upload(i, s_[0], s_[1], s_[2])
+    for i, s_ in enumerate(st):   # the bench's path: device geometry, windows staged by TMA
+        ctx.picture_upload_luma(i, s_[0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, bool(P.enable_hme_level1))
     out = ctx.me_picture(P, 1, [0, 2] if nl == 2 else [0])
     ctx.close()
     ok = H.me_equal(out, ref, nl)
@@ -120,8 +120,8 @@ def test_cuda_me_full_480p_m9_picture_matches_reference_functions(tl, nl, poc):
     n_sb = ((w + 63) // 64) * ((h + 63) // 64)
     ref = H.refdrv_me_picture(P, st[1], st[0], st[2] if nl == 2 else None, n_sb, threads=4)
     ctx = api.Context(0)
-    for i, s_ in enumerate(st):
-        ctx.picture_upload(i, s_[0], s_[1], s_[2])
+    for i, s_ in enumerate(st):   # the bench's path: device geometry, windows staged by TMA
+        ctx.picture_upload_luma(i, s_[0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, bool(P.enable_hme_level1))
     out = ctx.me_picture(P, 1, [0, 2] if nl == 2 else [0])
     ctx.close()
     ok = H.me_equal(out, ref, nl)
