@@ -73,36 +73,11 @@ static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, c
     A.win_bytes = me_window_bytes(*P);
     A.interp_plane_bytes = me_interp_plane_bytes(*P);
     A.interp_in_smem = 1;
-    /* ---- TMA staging where the planes allow it (svtb200_picture_upload_luma's device geometry does) */
+    /* ---- TMA staging of the source super-block where the plane allows it (svtb200_picture_upload_luma's device geometry does) */
     static const bool no_tma = getenv("SVTB200_ME_NO_TMA") != nullptr;
     if (!no_tma) {
         DevPicture &pc = itc->second;
-        if (plane_tensor_map(pc.pl[0], ME_SB, ME_SB, &A.tm_cur)) A.tma |= ME_TMA_SRC;
-        const int saw = P->search_area_width < 127 ? P->search_area_width : 127, sah = P->search_area_height < 127 ? P->search_area_height : 127;
-        const int fw = (saw + ME_SB - 1 + 16 + ME_HALO_X + 8 + 15) & ~15, fh = me_fp_rows(sah) + 1;
-        bool ok = true;
-        for (int l = 0; l < 2 && ok; l++) ok = plane_tensor_map(c->pics.find(ref_id[l < P->num_lists ? l : 0])->second.pl[0], fw, fh, &A.tm_ref[l]);
-        if (ok) { A.tma |= ME_TMA_FP; A.fp_box_w = fw; A.fp_box_h = fh; if (fw * fh + 16 > A.win_bytes) A.win_bytes = fw * fh + 16; }
-        if (P->enable_hme_flag && P->enable_hme_level0) {
-            /* level-0 stripes: the widest quadrant (or the whole area in single-quadrant mode), as many candidate rows as fit the buffer */
-            int tw = (P->hme_level0_total_search_area_width * P->hme_l0_multiplier_x) / 100, th = (P->hme_level0_total_search_area_height * P->hme_l0_multiplier_y) / 100;
-            const bool single = P->single_hme_quadrant && !P->enable_hme_level1 && !P->enable_hme_level2;
-            if (!single) {
-                tw = th = 0;
-                for (int i = 0; i < 2; i++) {
-                    tw = std::max(tw, (P->hme_level0_search_area_in_width[i] * P->hme_l0_multiplier_x) / 100);
-                    th = std::max(th, (P->hme_level0_search_area_in_height[i] * P->hme_l0_multiplier_y) / 100);
-                }
-            }
-            const int hw = (tw + 16 + 8 + 15) & ~15, extra = 14;
-            int stripe = th < ME_HME_STRIPE ? th : ME_HME_STRIPE;
-            if (stripe < 1) stripe = 1;
-            while (stripe > 8 && hw * (stripe + extra) + 16 > A.win_bytes) stripe -= 8;
-            const int hh = stripe + extra;
-            ok = hw <= 256 && hh <= 256;
-            for (int l = 0; l < 2 && ok; l++) ok = plane_tensor_map(c->pics.find(ref_id[l < P->num_lists ? l : 0])->second.pl[2], hw, hh, &A.tm_ref16[l]);
-            if (ok) { A.tma |= ME_TMA_HME0; A.hme_box_w = hw; A.hme_box_h = hh; if (hw * hh + 16 > A.win_bytes) A.win_bytes = hw * hh + 16; }
-        }
+        if ((pc.pl[0].ox & 15) == 0 && plane_tensor_map(pc.pl[0], ME_SB, ME_SB, &A.tm_cur)) A.tma |= ME_TMA_SRC; /* box start = ox + 64 k: 16-byte aligned */
     }
     MeSmemLayout L = me_smem_layout(A.win_bytes, A.interp_plane_bytes, 1, me_bip0_bytes(*P));
     if (L.total > c->smem_optin) {

@@ -53,11 +53,15 @@ struct MeTraceDev { /* optional per-SB stage outputs, same fields as the oracle'
 /* a CUtensorMap (cuda.h) without the header: 128 opaque bytes, 64-byte aligned, passed inside the __grid_constant__ kernel argument */
 struct alignas(64) MeTensorMap { uint64_t opaque[16]; };
 #define ME_TMA_SRC 1  /* source super-block: 64x64 box of the current picture's full plane */
-#define ME_TMA_FP  2  /* full-pel search window (+ halo): fp_box_w x fp_box_h box of the reference's full plane */
-#define ME_TMA_HME0 4 /* HME level-0 stripes: hme_box_w x hme_box_h box of the reference's 1/16 plane */
+/* The search WINDOWS cannot come through TMA (nor through cp.async): a tiled copy must start at a 16-byte aligned byte offset of
+ * the row -- measured on B200 (tools/tma_probe2.cu: box start columns 16 and 32 land, 1, 4, 8 and 13 raise "illegal instruction",
+ * the same when the row is described as 32-bit elements) -- while a window starts at any byte (search centre + clipping), and
+ * everything downstream reads the staged rows as aligned 32-bit words.  Their re-alignment therefore stays in registers
+ * (aligned word loads + funnel shift, me_stage_window).  The source super-block always starts at a multiple of 64 samples of a
+ * plane whose origin is a multiple of 16 (svtb200_picture_upload_luma's geometry): it is the TMA case. */
 
 struct MeKernelArgs {
-    MeTensorMap        tm_cur, tm_ref[2], tm_ref16[2]; /* valid per the bits of 'tma' */
+    MeTensorMap        tm_cur;             /* valid when tma & ME_TMA_SRC */
     SvtB200MeParams    P;
     MePlaneDev         cur[3], ref[2][3];
     SvtB200MeCuResult *out;
@@ -70,8 +74,7 @@ struct MeKernelArgs {
     int32_t            sbs_w, n_sb;
     int32_t            n_work;             /* super-blocks of this launch (n_sb for a whole picture) */
     int32_t            sb_first;           /* SB index of block 0 (partial launches in the logic tests) */
-    int32_t            tma;                /* ME_TMA_* bits: windows staged by cp.async.bulk.tensor + mbarrier instead of by the threads */
-    int32_t            fp_box_w, fp_box_h, hme_box_w, hme_box_h;
+    int32_t            tma;                /* ME_TMA_* bits: staged by cp.async.bulk.tensor + mbarrier instead of by the threads */
     uint32_t          *sb_counter;         /* persistent grid: next super-block to take (null: block b takes super-block b) */
 };
 
@@ -116,10 +119,8 @@ __device__ __forceinline__ int16_t me_mvy(uint32_t mv) { return (int16_t)(mv >> 
 __device__ __forceinline__ uint32_t me_mkmv(int x, int y) { return ((uint32_t)(uint16_t)y << 16) | (uint16_t)x; }
 
 /* ---------------------------------------------------------------------------------------------
- * TMA window staging: one elected thread arms the CTA's mbarrier with the box size and issues cp.async.bulk.tensor (the copy
- * engine fetches the 2-D box at ANY byte coordinate and lays it down densely, i.e. the re-alignment the software path does with
- * funnel shifts comes for free); every thread then waits on the barrier's phase.  Out-of-range parts of a box are zero-filled
- * and never consumed.
+ * TMA staging: one elected thread arms the CTA's mbarrier with the box size and issues cp.async.bulk.tensor; every thread then
+ * waits on the barrier's phase.  (Box start = a multiple of 16 bytes, see ME_TMA_SRC.)
  * ------------------------------------------------------------------------------------------- */
 struct MeTmaState { uint32_t mbar, phase; }; /* shared-memory address of the mbarrier, parity of the next completion */
 #if defined(__CUDA_ARCH__)
@@ -467,7 +468,7 @@ __device__ static void me_window_search(const uint8_t *sblk, const uint8_t *win,
  * level 0/1 read the source block from the decimated planes of the current picture, level 2
  * from the shared-memory SB. */
 __device__ static void me_hme_search(const MeKernelArgs &A, int list, int level, MeSbState *st, const uint8_t *src,
-                                     uint8_t *hsrc, uint8_t *win, uint32_t *posacc, MeTmaState &tma) {
+                                     uint8_t *hsrc, uint8_t *win, uint32_t *posacc) {
     const int w = st->s_w, h = st->s_h;
     /* source block: every other row of the (decimated) SB */
     if (level == 2) {
@@ -487,17 +488,11 @@ __device__ static void me_hme_search(const MeKernelArgs &A, int list, int level,
     if (threadIdx.x == 0) st->best_key = ~0ull;
     const MePlaneDev &rp = A.ref[list][level == 0 ? 2 : level == 1 ? 1 : 0];
     const int extra = 2 * (h - 1), sah = st->w_sah;
-    const bool by_tma = level == 0 && (A.tma & ME_TMA_HME0); /* thread 0 set w_pitch = hme_box_w */
-    int stripe = by_tma ? A.hme_box_h - extra : A.win_bytes / st->w_pitch - extra - 1; /* candidate rows the buffer can hold */
+    int stripe = A.win_bytes / st->w_pitch - extra - 1; /* candidate rows the buffer can hold */
     if (stripe < 1) stripe = 1;
     for (int y0 = 0; y0 < sah; y0 += stripe) {
         const int n = min(stripe, sah - y0);
-        if (by_tma) {
-            if (threadIdx.x == 0) me_tma_issue(&A.tm_ref16[list], win, rp.ox + st->w_x, rp.oy + st->w_y + y0, (uint32_t)(A.hme_box_w * A.hme_box_h), tma);
-            me_tma_wait(tma);
-        } else {
-            me_stage_window(win, st->w_pitch, rp, st->w_x, st->w_y + y0, st->w_saw + w - 1, n + extra);
-        }
+        me_stage_window(win, st->w_pitch, rp, st->w_x, st->w_y + y0, st->w_saw + w - 1, n + extra);
         __syncthreads();
         me_window_search(hsrc, win, st, posacc, y0, n);
         __syncthreads();
@@ -1071,7 +1066,7 @@ static inline int me_interp_plane_bytes(const SvtB200MeParams &P) {
 
 /* one HME level over all quadrants of one list (uniform control flow: every thread runs this) */
 __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, int single, MeSbState *st, const uint8_t *src,
-                                    uint8_t *hsrc, uint8_t *win, uint32_t *posacc, MeTmaState &tma) {
+                                    uint8_t *hsrc, uint8_t *win, uint32_t *posacc) {
     const SvtB200MeParams &P = A.P;
     const int nqx = single ? 1 : P.number_hme_search_region_in_width, nqy = single ? 1 : P.number_hme_search_region_in_height;
     for (int qy = 0; qy < nqy; qy++)
@@ -1101,7 +1096,6 @@ __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, 
                     me_clip_window(oy, &y_org, &sah, rp.oy - 1, rp.h);
                     if (single && (saw & 15)) saw = (int16_t)((saw >> 4) << 4);
                     me_set_window(st, st->sbw >> 2, (st->sbh >> 2) >> 1, ox + x_org, oy + y_org, saw, sah);
-                    if (A.tma & ME_TMA_HME0) st->w_pitch = A.hme_box_w; /* the box lands densely at its own width */
                 } else if (level == 1) {
                     const MePlaneDev &rp = A.ref[list][1];
                     const int ox = st->ox >> 1, oy = st->oy >> 1;
@@ -1125,7 +1119,7 @@ __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, 
                 x_org_s = x_org; y_org_s = y_org;
             }
             __syncthreads();
-            me_hme_search(A, list, level, st, src, hsrc, win, posacc, tma);
+            me_hme_search(A, list, level, st, src, hsrc, win, posacc);
             if (threadIdx.x == 0) {
                 /* outputs keep their previous contents when no candidate beat 0xffffff */
                 int16_t *px = level == 0 ? &st->l0x[qx][qy] : level == 1 ? &st->l1x[qx][qy] : &st->l2x[qx][qy];
@@ -1269,9 +1263,9 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
                     if (P.enable_hme_level0 && single) st->srh = 0;
                 }
                 __syncthreads();
-                if (P.enable_hme_level0) me_hme_level(A, list, 0, single, st, src, hsrc, win, posacc, tma);
-                if (P.enable_hme_level1) me_hme_level(A, list, 1, 0, st, src, hsrc, win, posacc, tma);
-                if (P.enable_hme_level2) me_hme_level(A, list, 2, 0, st, src, hsrc, win, posacc, tma);
+                if (P.enable_hme_level0) me_hme_level(A, list, 0, single, st, src, hsrc, win, posacc);
+                if (P.enable_hme_level1) me_hme_level(A, list, 1, 0, st, src, hsrc, win, posacc);
+                if (P.enable_hme_level2) me_hme_level(A, list, 2, 0, st, src, hsrc, win, posacc);
                 if (t == 0) {
                     int16_t (*fx)[2] = 0, (*fy)[2] = 0;
                     uint64_t (*fs)[2] = 0;
@@ -1323,21 +1317,16 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
             me_clip_window(st->ox, &xo, &saw, ME_SB - 1, P.luma_width);
             me_clip_window(st->oy, &yo, &sah, ME_SB - 1, P.luma_height);
             st->sa_ox[list] = xo; st->sa_oy[list] = yo; st->saw[list] = saw; st->sah[list] = sah;
-            st->fp_pitch = (A.tma & ME_TMA_FP) ? A.fp_box_w : me_fp_pitch(saw);
-            if (A.tma & ME_TMA_FP) /* the window buffer's last readers (HME, or list 0's bi-prediction stash) are behind a barrier */
-                me_tma_issue(&A.tm_ref[list], win, rp.ox + st->ox + xo - ME_HALO_X, rp.oy + st->oy + yo - ME_HALO_Y, (uint32_t)(A.fp_box_w * A.fp_box_h), tma);
+            st->fp_pitch = me_fp_pitch(saw);
             if (A.trace) { A.trace[sb].sa_ox[list] = xo; A.trace[sb].sa_oy[list] = yo; A.trace[sb].sa_w[list] = saw; A.trace[sb].sa_h[list] = sah; }
         }
         __syncthreads();
         /* ---- full-pel search: the window (with the halo the half-pel filters need) is staged once */
         const int fpp = st->fp_pitch;
         const uint8_t *rb = win + ME_HALO_Y * fpp + ME_HALO_X;
-        if (A.tma & ME_TMA_FP) me_tma_wait(tma);
-        else {
-            me_stage_window(win, fpp, rp, st->ox + st->sa_ox[list] - ME_HALO_X, st->oy + st->sa_oy[list] - ME_HALO_Y,
-                            st->saw[list] + ME_SB - 1 + 16 + ME_HALO_X, me_fp_rows(st->sah[list]));
-            __syncthreads();
-        }
+        me_stage_window(win, fpp, rp, st->ox + st->sa_ox[list] - ME_HALO_X, st->oy + st->sa_oy[list] - ME_HALO_Y,
+                        st->saw[list] + ME_SB - 1 + 16 + ME_HALO_X, me_fp_rows(st->sah[list]));
+        __syncthreads();
         me_fullpel(src, rb, fpp, st, list, pu_key);
         if (t < 85) {
             const unsigned long long k = pu_key[t];
