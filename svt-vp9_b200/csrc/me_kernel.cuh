@@ -33,6 +33,8 @@
 
 #define ME_THREADS 256
 #define ME_SB 64
+#define ME_SRC_PITCH 72   /* shared-memory pitch of the source SB and of the stashed list-0 predictions: rows two apart (the sub-sampled
+                            metrics, one row per lane) are 36 words apart, i.e. eight lanes hit eight different banks (at 64 they all hit one) */
 #define ME_MAX_SAD (64 * 64 * 255)
 #define ME_HALO_X 4       /* staged full-pel window: columns left of the search-area origin (word aligned) */
 #define ME_HALO_Y 2       /* rows above / below (the 4-tap filters reach 2 rows up, 1+1 down) */
@@ -301,7 +303,7 @@ __device__ static void me_sb_sad_multi(const uint8_t *src, const MeSbState *st, 
         const int nseg = sbw >> 3, seg = threadIdx.x;
         const int y = (nseg == 8) ? seg >> 3 : seg / nseg, x = (seg - y * nseg) * 8;
         if (y < rows) {
-            const uint32_t *sp = (const uint32_t *)(src + (2 * y) * ME_SB + x);
+            const uint32_t *sp = (const uint32_t *)(src + (2 * y) * ME_SRC_PITCH + x);
             const uint32_t s0 = sp[0], s1 = sp[1];
 #pragma unroll
             for (int c = 0; c < 5; c++) {
@@ -321,7 +323,7 @@ __device__ static void me_sb_sad_multi(const uint8_t *src, const MeSbState *st, 
             const uint8_t *r = me_pix(rp, st->ox + dx[c], st->oy + dy[c]);
             for (int i = threadIdx.x; i < cnt; i += ME_THREADS) {
                 const int y = i / sbw, x = i - y * sbw;
-                const int a = src[(2 * y) * ME_SB + x], b = __ldg(r + (ptrdiff_t)(2 * y) * rp.stride + x);
+                const int a = src[(2 * y) * ME_SRC_PITCH + x], b = __ldg(r + (ptrdiff_t)(2 * y) * rp.stride + x);
                 acc[c] += (uint32_t)(a > b ? a - b : b - a);
             }
         }
@@ -474,7 +476,7 @@ __device__ static void me_hme_search(const MeKernelArgs &A, int list, int level,
     if (level == 2) {
         for (int i = threadIdx.x; i < w * h; i += ME_THREADS) {
             const int y = i / w, x = i - y * w;
-            hsrc[y * st->s_pitch + x] = src[(2 * y) * ME_SB + x];
+            hsrc[y * st->s_pitch + x] = src[(2 * y) * ME_SRC_PITCH + x];
         }
     } else {
         const MePlaneDev &cp = A.cur[level == 0 ? 2 : 1];
@@ -540,7 +542,7 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
     /* raster position of the 16x16 block with internal index z16 */
     const int b16 = (z16 & 1) | ((z16 & 4) >> 1) | ((z16 & 2) << 1) | (z16 & 8);
     const int bx = (b16 & 3) * 16, by = (b16 >> 2) * 16;
-    const uint32_t *sp = (const uint32_t *)(src + by * ME_SB + bx);
+    const uint32_t *sp = (const uint32_t *)(src + by * ME_SRC_PITCH + bx);
     const int p2 = wpitch >> 1; /* two rows, in words */
     const bool skewed = (z16 == 12 || z16 == 13);
     const MeBest none = {ME_MAX_SAD, 0xffffffffu};
@@ -560,7 +562,7 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
         for (int r = 0; r < 8; r++) {
             const uint32_t *w = wp + r * p2;
             const uint32_t w0 = w[0], w1 = w[1], w2 = w[2], w3 = w[3], w4 = w[4];
-            const uint32_t s0 = sp[r * 32], s1 = sp[r * 32 + 1], s2 = sp[r * 32 + 2], s3 = sp[r * 32 + 3];
+            const uint32_t s0 = sp[r * (ME_SRC_PITCH / 2)], s1 = sp[r * (ME_SRC_PITCH / 2) + 1], s2 = sp[r * (ME_SRC_PITCH / 2) + 2], s3 = sp[r * (ME_SRC_PITCH / 2) + 3];
             const int q = r < 4 ? 0 : 2;
 #pragma unroll
             for (int j = 0; j < 4; j++) {
@@ -734,20 +736,20 @@ __device__ __forceinline__ uint32_t me_pred_row(const uint32_t *srow, const MePr
     }
     return acc;
 }
-/* distortion share of thread 'part' of T for the w x w PU at s (pitch ME_SB); method as the reference:
+/* distortion share of thread 'part' of T for the w x w PU at s (pitch ME_SRC_PITCH); method as the reference:
  * 0 SUB_SAD (even rows, doubled), 1 full SAD, 2 SSD (+ the full SAD in *sad) */
 __device__ __forceinline__ uint32_t me_pred_part(const uint8_t *s, const MePred &pr, int w, int part, int T, int method, uint32_t *sad) {
     const int wwords = w >> 2;
     uint32_t d = 0, a = 0;
     if (method == 0) {
-        for (int y = 2 * part; y < w; y += 2 * T) d += me_pred_row((const uint32_t *)(s + y * ME_SB), pr, y, wwords, 0);
+        for (int y = 2 * part; y < w; y += 2 * T) d += me_pred_row((const uint32_t *)(s + y * ME_SRC_PITCH), pr, y, wwords, 0);
         d <<= 1;
     } else if (method == 1) {
-        for (int y = part; y < w; y += T) d += me_pred_row((const uint32_t *)(s + y * ME_SB), pr, y, wwords, 0);
+        for (int y = part; y < w; y += T) d += me_pred_row((const uint32_t *)(s + y * ME_SRC_PITCH), pr, y, wwords, 0);
     } else {
         for (int y = part; y < w; y += T) {
-            d += me_pred_row((const uint32_t *)(s + y * ME_SB), pr, y, wwords, 1);
-            a += me_pred_row((const uint32_t *)(s + y * ME_SB), pr, y, wwords, 0);
+            d += me_pred_row((const uint32_t *)(s + y * ME_SRC_PITCH), pr, y, wwords, 1);
+            a += me_pred_row((const uint32_t *)(s + y * ME_SRC_PITCH), pr, y, wwords, 0);
         }
     }
     *sad = a;
@@ -847,7 +849,7 @@ __device__ static void me_subpel(const MeKernelArgs &A, const uint8_t *src, MeSb
             default: pr.p1 = ip.rb + xs + px + (ys + py) * ip.rp; pr.s1 = ip.rp; break;
             }
             uint32_t a = 0;
-            uint32_t d = me_pred_part(src + py * ME_SB + px, pr, w, part, T, method, &a);
+            uint32_t d = me_pred_part(src + py * ME_SRC_PITCH + px, pr, w, part, T, method, &a);
             d = me_group_sum(d, tlog);
             if (method == 2) a = me_group_sum(a, tlog);
             if (part == 0) { dist[idx * 9 + k] = d; if (method == 2) sadv[idx * 9 + k] = a; }
@@ -911,7 +913,7 @@ __device__ static void me_subpel(const MeKernelArgs &A, const uint8_t *src, MeSb
             pr.p1 = me_qsrc_ptr(is, ip, me_qtab[phase][k][0], xs + px, ys + py, &pr.s1);
             pr.p2 = me_qsrc_ptr(is, ip, me_qtab[phase][k][1], xs + px, ys + py, &pr.s2);
             uint32_t a = 0, d = 0;
-            if (active) d = me_pred_part(src + py * ME_SB + px, pr, w, part, T, method, &a);
+            if (active) d = me_pred_part(src + py * ME_SRC_PITCH + px, pr, w, part, T, method, &a);
             d = me_group_sum(d, tlog);
             if (method == 2) a = me_group_sum(a, tlog);
             if (active && part == 0) { dist[idx * 9 + k] = d; if (method == 2) sadv[idx * 9 + k] = a; }
@@ -992,7 +994,7 @@ __host__ __device__ static inline int me_align16(int v) { return (v + 15) & ~15;
 __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int interp_plane_bytes, int interp_in_smem, int bip0_bytes) {
     MeSmemLayout L;
     int o = 0;
-    L.src = o; o += ME_SB * ME_SB;
+    L.src = o; o += ME_SB * ME_SRC_PITCH;
     L.hsrc = o; o += 64 * 32;
     L.win = o; o += (win_bytes + 127) & ~127; /* TMA destinations are 128-byte aligned (src and hsrc keep it so) */
     L.interp = o; o += interp_in_smem ? 3 * me_align16(interp_plane_bytes) : 0; /* the planes of the list being searched */
@@ -1011,6 +1013,9 @@ __host__ __device__ static inline MeSmemLayout me_smem_layout(int win_bytes, int
     L.total = o;
     return L;
 }
+/* pitch of the half-pel planes of a W-column search region: the columns the reference computes (W + 2 rounded up to 8) rounded up
+ * to an ODD multiple of 8 bytes, so that rows two apart (one per lane in the sub-sampled metrics) fall into different banks */
+__host__ __device__ static inline int me_istride(int W) { const int s = (W + 2 + 7) & ~7; return (s & 8) ? s : s + 8; }
 /* pitch / rows of the staged full-pel window of a saw x sah search area */
 __host__ __device__ static inline int me_fp_pitch(int saw) { return (saw + ME_SB - 1 + 16 + ME_HALO_X + 8 + 3) & ~3; }
 __host__ __device__ static inline int me_fp_rows(int sah) { return sah + ME_SB - 1 + 2 * ME_HALO_Y; }
@@ -1051,11 +1056,11 @@ static inline int me_window_bytes(const SvtB200MeParams &P) {
 __host__ __device__ static inline int me_bip0_bytes(const SvtB200MeParams &P) {
     if (P.num_lists < 2) return 0;
     const int ncls = 2 + (P.cu16x16_mode == 0 ? 1 : 0) + ((P.cu16x16_mode == 0 && P.cu8x8_mode == 0) ? 1 : 0);
-    return ncls * ME_SB * (P.fractional_search_method == 0 ? ME_SB / 2 : ME_SB);
+    return ncls * ME_SRC_PITCH * (P.fractional_search_method == 0 ? ME_SB / 2 : ME_SB);
 }
 static inline int me_interp_plane_bytes(const SvtB200MeParams &P) {
     const int saw = P.search_area_width < 127 ? P.search_area_width : 127, sah = P.search_area_height < 127 ? P.search_area_height : 127;
-    return (((saw + ME_SB - 1 + 2) + 7) & ~7) * (sah + ME_SB - 1 + 4);
+    return me_istride(saw + ME_SB - 1) * (sah + ME_SB - 1 + 4);
 }
 
 #ifdef SVTB200_CPU_EMU
@@ -1197,13 +1202,17 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
         }
         st->interp_ok[0] = st->interp_ok[1] = 0;
         /* source SB: all 64 rows from the padded plane */
-        if (A.tma & ME_TMA_SRC) me_tma_issue(&A.tm_cur, src, A.cur[0].ox + st->ox, A.cur[0].oy + st->oy, ME_SB * ME_SB, tma);
+        if (A.tma & ME_TMA_SRC) me_tma_issue(&A.tm_cur, win, A.cur[0].ox + st->ox, A.cur[0].oy + st->oy, ME_SB * ME_SB, tma); /* dense box into the idle window buffer */
     }
     for (int i = t; i < 2 * 85; i += ME_THREADS) { bsad[i] = ME_MAX_SAD; bmv[i] = 0; bssd[i] = 0; }
     for (int i = t; i < 85; i += ME_THREADS) { bip[i] = 0; dir[i] = 0; }
     __syncthreads();
-    if (A.tma & ME_TMA_SRC) me_tma_wait(tma);
-    else me_stage_window(src, ME_SB, A.cur[0], st->ox, st->oy, ME_SB - 4, ME_SB);
+    if (A.tma & ME_TMA_SRC) {
+        me_tma_wait(tma);
+        for (int i = t; i < ME_SB * ME_SB / 4; i += ME_THREADS) ((uint32_t *)(src + (i >> 4) * ME_SRC_PITCH))[i & 15] = ((const uint32_t *)win)[i]; /* to the padded pitch */
+    } else {
+        me_stage_window(src, ME_SRC_PITCH, A.cur[0], st->ox, st->oy, ME_SB - 4, ME_SB);
+    }
     __syncthreads();
 
     for (int list = 0; list < nl; list++) {
@@ -1346,7 +1355,7 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
             else if (P.fractional_search_model == 1) { me_su_pel_enable(ls, lm, P.temporal_layer_index, &e32, &e16, &e8); eq = 1; }
             st->e32 = e32; st->e16 = e16; st->e8 = e8; st->eq = eq;
             const int W = st->saw[list] + ME_SB - 1;
-            st->istride[list] = (W + 2 + 7) & ~7;
+            st->istride[list] = me_istride(W);
             if (A.trace) A.trace[sb].subpel_enable[list] = (uint8_t)(e32 | (e16 << 1) | (e8 << 2) | (eq << 3));
         }
         __syncthreads();
@@ -1370,7 +1379,7 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
                 if (cls == 3 && P.cu8x8_mode != 0) continue;
                 if (cls >= 2 && P.cu16x16_mode != 0) continue;
                 const int tlog = 5 - cls, T = 1 << tlog, idx0 = me_cls_idx0(cls), nunits = me_cls_npu(cls) * T;
-                uint8_t *img = bip0 + cls * (ME_SB * (ME_SB >> rsh));
+                uint8_t *img = bip0 + cls * (ME_SRC_PITCH * (ME_SB >> rsh));
                 for (int u = t; u < nunits; u += ME_THREADS) {
                     const int idx = idx0 + (u >> tlog), part = u & (T - 1);
                     int px, py, w;
@@ -1379,7 +1388,7 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
                     me_bipred_pred(st->sa_ox[0], st->sa_oy[0], st->istride[0], ip[0], bmv[idx], px, py, &p0);
                     const int wwords = w >> 2;
                     for (int y = sub ? 2 * part : part; y < w; y += sub ? 2 * T : T) {
-                        uint32_t *d = (uint32_t *)(img + ((py + y) >> rsh) * ME_SB + px);
+                        uint32_t *d = (uint32_t *)(img + ((py + y) >> rsh) * ME_SRC_PITCH + px);
                         for (int k = 0; k < wwords; k++) d[k] = me_pred_word(p0, y, k);
                     }
                 }
@@ -1397,7 +1406,7 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
             if (cls == 3 && P.cu8x8_mode != 0) continue;
             if (cls >= 2 && P.cu16x16_mode != 0) continue;
             const int tlog = 5 - cls, T = 1 << tlog, idx0 = me_cls_idx0(cls), nunits = me_cls_npu(cls) * T;
-            const uint8_t *img = bip0 + cls * (ME_SB * (ME_SB >> rsh));
+            const uint8_t *img = bip0 + cls * (ME_SRC_PITCH * (ME_SB >> rsh));
             for (int u = t; u < nunits; u += ME_THREADS) {
                 const int idx = idx0 + (u >> tlog), part = u & (T - 1);
                 int px, py, w;
@@ -1407,8 +1416,8 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
                 const int wwords = w >> 2;
                 uint32_t acc = 0;
                 for (int y = sub ? 2 * part : part; y < w; y += sub ? 2 * T : T) {
-                    const uint32_t *srow = (const uint32_t *)(src + (py + y) * ME_SB + px);
-                    const uint32_t *p0 = (const uint32_t *)(img + ((py + y) >> rsh) * ME_SB + px);
+                    const uint32_t *srow = (const uint32_t *)(src + (py + y) * ME_SRC_PITCH + px);
+                    const uint32_t *p0 = (const uint32_t *)(img + ((py + y) >> rsh) * ME_SRC_PITCH + px);
                     for (int k = 0; k < wwords; k++) acc = me_absdiff_acc(__vavgu4(p0[k], me_pred_word(p1, y, k)), srow[k], acc);
                 }
                 acc = me_group_sum(acc, tlog);
