@@ -327,6 +327,29 @@ typedef struct SvtB200TxBatch {
 int svtb200_txq_multi_dev(SvtB200Ctx *ctx, const SvtB200TxBatch *batches, int n_batches,
                           const SvtB200QuantRow *qrows_dev, int n_qrows);
 
+/* ---- coefficient rate estimation ---------------------------------------------------------------------
+ * coeff_rate_estimate() (Source/Lib/Codec/EbRateDistortionCost.c:55; the libvpx cost_coeffs, Source/Lib/VPX/vp9_rdopt.c:334) with
+ * use_fast_coef_costing == 0, as perform_dist_rate_calc calls it after every transform (Source/Lib/Codec/EbEncDecProcess.c:736):
+ * the cost, in the 1/256-bit units of the tables, of the tokens of one block's quantised coefficients -- batched over the
+ * qcoeff / eob arrays svtb200_txq_batch_dev leaves on the device.  Control values arrive as data:
+ *   svtb200_set_scan_neighbors  scan_order::neighbors of every (tx_size, tx_type) (Source/Lib/VPX/vp9_scan.c; MAX_NEIGHBORS * (N*N + 1) entries)
+ *   svtb200_set_rate_tables     eb_vp9_dct_cat_lt_10_value_tokens[v].token and eb_vp9_dct_cat_lt_10_value_cost[v] for v = -66 .. 66
+ *                               (index v + 66), eb_vp9_cat6_low_cost[256], eb_vp9_cat6_high_cost[64] (Source/Lib/VPX/vp9_tokenize.c)
+ *   token_costs                 MACROBLOCK::token_costs[tx_size] of the picture (Source/Lib/VPX/vp9_block.h:141, filled by
+ *                               fill_token_costs, vp9_rd.c:93): [plane type 2][ref 2][band 6][2][ctx 6][token 12] unsigned
+ * Per block: the plane type (0 luma, 1 chroma), is_inter_block(mi), the transform type (scan selection, 32x32: DCT only) and the
+ * entropy context of the block = combine_entropy_contexts(left, above) (EbEncDecProcess.c:734). */
+typedef struct SvtB200RateBlock {
+    uint8_t plane_type, is_inter, tx_type, coeff_ctx;
+} SvtB200RateBlock;
+int svtb200_set_scan_neighbors(SvtB200Ctx *ctx, int tx_size, int tx_type, const int16_t *neighbors);
+int svtb200_set_rate_tables(SvtB200Ctx *ctx, const int16_t value_token[133], const int32_t value_cost[133],
+                            const int16_t cat6_low_cost[256], const uint16_t cat6_high_cost[64]);
+int svtb200_coeff_rate_batch(SvtB200Ctx *ctx, int tx_size, int n, const int16_t *qcoeff, const uint16_t *eob,
+                             const SvtB200RateBlock *blocks, const uint32_t *token_costs, int32_t *rate);
+int svtb200_coeff_rate_batch_dev(SvtB200Ctx *ctx, int tx_size, int n, const int16_t *qcoeff_dev, const uint16_t *eob_dev,
+                                 const SvtB200RateBlock *blocks_dev, const uint32_t *token_costs_dev, int32_t *rate_dev);
+
 /* =============================================================================================
  * S2  Deblocking loop filter
  * ============================================================================================= */

@@ -28,6 +28,22 @@ def main():
     L.eb_vp9_ac_quant.restype = C.c_int16
     out["dc_q"] = np.array([L.eb_vp9_dc_quant(q, 0, 8) for q in range(256)], dtype=np.int16)
     out["ac_q"] = np.array([L.eb_vp9_ac_quant(q, 0, 8) for q in range(256)], dtype=np.int16)
+    # rate estimation (coeff_rate_estimate): scan neighbours, value -> token / cost tables, the token costs of the default
+    # coefficient probabilities -- through the path driver, which reads the reference's own tables (ref_path_driver.c)
+    D = C.CDLL(os.path.join(ROOT, "oracle", "_ref", "libSvtVp9Enc_refdrv.so"))
+    for ts in range(4):
+        n = (4 << ts) ** 2
+        for tt in range(4):
+            nb = np.zeros(2 * (n + 1), dtype=np.int16)
+            D.refdrv_scan_neighbors(ts, tt, C.c_void_p(nb.ctypes.data))
+            out["nb_%d_%d" % (ts, tt)] = nb
+    vtok, vcost = np.zeros(133, dtype=np.int16), np.zeros(133, dtype=np.int32)
+    c6lo, c6hi = np.zeros(256, dtype=np.int16), np.zeros(64, dtype=np.uint16)
+    D.refdrv_value_tables(*(C.c_void_p(a.ctypes.data) for a in (vtok, vcost, c6lo, c6hi)))
+    out.update(rate_vtok=vtok, rate_vcost=vcost, rate_c6lo=c6lo, rate_c6hi=c6hi)
+    tc = np.zeros((4, 2, 2, 6, 2, 6, 12), dtype=np.uint32)
+    assert D.refdrv_token_costs(C.c_void_p(tc.ctypes.data)) == tc.nbytes
+    out["token_costs_default"] = tc
     dst = os.path.join(ROOT, "svt-vp9_b200", "data", "vp9_tables.npz")
     np.savez_compressed(dst, **out)
     print("wrote", dst, os.path.getsize(dst))

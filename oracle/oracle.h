@@ -39,6 +39,11 @@ void svtb200_oracle_inter_predict(const SvtB200PredBlock *blocks, int n);
 void svtb200_oracle_intra_predict(const SvtB200IntraBlock *blocks, int n); /* host pointers */
 void svtb200_oracle_full_distortion(int tx_size, int n, const int16_t *coeff, const int16_t *recon_coeff, const uint16_t *eob, uint64_t *dist);
 
+/* coefficient rate estimation (coeff_rate_estimate, use_fast_coef_costing == 0): rate_port.c */
+void svtb200_oracle_coeff_rate(int tx_size, int n, const int16_t *qcoeff, const uint16_t *eob, const SvtB200RateBlock *blocks,
+                               const uint32_t *token_costs, const int16_t *const scans[4], const int16_t *const neighbors[4],
+                               const int16_t *vtok, const int32_t *vcost, const int16_t *c6lo, const uint16_t *c6hi, int32_t *rate);
+
 #ifdef __cplusplus
 }
 #endif

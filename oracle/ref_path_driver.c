@@ -360,6 +360,78 @@ int refdrv_intra_predict(int mode, int tx_size, int have_left, int have_top, uin
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------ rate estimation */
+#include "EbEncDecProcess.h"
+#include "vp9_block.h"
+#include "vp9_entropy.h"
+#include "vp9_tokenize.h"
+#include "vp9_cost.h"
+#include "vp9_onyxc_int.h"
+int coeff_rate_estimate(struct EncDecContext *context_ptr, MACROBLOCK *x, int16_t *trans_coeff_buffer, uint16_t eob, int plane, int block, TX_SIZE tx_size,
+                        int pt, int use_fast_coef_costing);
+
+/* MACROBLOCK::token_costs as the reference fills them (fill_token_costs, vp9_rd.c:93-107 -- static there, so its loop is driven
+ * from here with the reference's own non-static helpers) from its default coefficient probabilities (vp9_entropy.c):
+ * out[tx_size 4][plane type 2][ref 2][band 6][2][ctx 6][token 12] */
+int refdrv_token_costs(uint32_t *out) {
+    VP9_COMMON *cm = (VP9_COMMON *)calloc(1, sizeof(VP9_COMMON));
+    FRAME_CONTEXT *fc = (FRAME_CONTEXT *)calloc(1, sizeof(FRAME_CONTEXT));
+    vp9_coeff_cost *c = (vp9_coeff_cost *)out;
+    cm->fc = fc;
+    eb_vp9_default_coef_probs(cm); /* the static default tables of vp9_entropy.c:258-919 */
+    memset(out, 0, sizeof(vp9_coeff_cost) * TX_SIZES);
+    for (int t = TX_4X4; t <= TX_32X32; ++t)
+        for (int i = 0; i < PLANE_TYPES; ++i)
+            for (int j = 0; j < REF_TYPES; ++j)
+                for (int k = 0; k < COEF_BANDS; ++k)
+                    for (int l = 0; l < BAND_COEFF_CONTEXTS(k); ++l) {
+                        vpx_prob probs[ENTROPY_NODES];
+                        eb_vp9_model_to_full_probs(fc->coef_probs[t][i][j][k][l], probs);
+                        eb_vp9_cost_tokens((int *)c[t][i][j][k][0][l], probs, eb_vp9_coef_tree);
+                        eb_vp9_cost_tokens_skip((int *)c[t][i][j][k][1][l], probs, eb_vp9_coef_tree);
+                    }
+    free(fc); free(cm);
+    return (int)(sizeof(vp9_coeff_cost) * TX_SIZES);
+}
+/* the value -> token / cost tables and the cat6 cost tables of vp9_tokenize.c, as plain arrays */
+int refdrv_value_tables(int16_t tok[133], int32_t cost[133], int16_t cat6_low[256], uint16_t cat6_high[64]) {
+    for (int v = -66; v <= 66; v++) { tok[v + 66] = eb_vp9_dct_cat_lt_10_value_tokens[v].token; cost[v + 66] = eb_vp9_dct_cat_lt_10_value_cost[v]; }
+    memcpy(cat6_low, eb_vp9_cat6_low_cost, 256 * sizeof(int16_t));
+    memcpy(cat6_high, eb_vp9_cat6_high_cost, 64 * sizeof(uint16_t));
+    return 0;
+}
+/* scan_order::neighbors of (tx_size, tx_type): MAX_NEIGHBORS * (N * N + 1) entries */
+int refdrv_scan_neighbors(int tx_size, int tx_type, int16_t *out) {
+    const int nn = (4 << tx_size) * (4 << tx_size);
+    const scan_order *so = tx_size == 3 ? &eb_vp9_default_scan_orders[TX_32X32] : &eb_vp9_scan_orders[tx_size][tx_type];
+    memcpy(out, so->neighbors, (size_t)MAX_NEIGHBORS * (nn + 1) * sizeof(int16_t));
+    return 0;
+}
+/* the reference's coeff_rate_estimate on every block of a batch; token_costs as refdrv_token_costs lays them out (all sizes) */
+int refdrv_coeff_rate(int tx_size, int n, const int16_t *qcoeff, const uint16_t *eob, const SvtB200RateBlock *blocks, const uint32_t *token_costs_all,
+                      int32_t *rate) {
+    static const PREDICTION_MODE mode_of_tx_type[4] = {DC_PRED, V_PRED, H_PRED, TM_PRED}; /* eb_vp9_intra_mode_to_tx_type_lookup backwards */
+    const int nn = (4 << tx_size) * (4 << tx_size);
+    EncDecContext *ctx = (EncDecContext *)calloc(1, sizeof(EncDecContext));
+    MACROBLOCK *x = (MACROBLOCK *)calloc(1, sizeof(MACROBLOCK));
+    MACROBLOCKD *xd = (MACROBLOCKD *)calloc(1, sizeof(MACROBLOCKD));
+    ModeInfo mi, *mip = &mi;
+    memcpy(x->token_costs, token_costs_all, sizeof(x->token_costs));
+    ctx->e_mbd = xd;
+    xd->mi = &mip;
+    for (int b = 0; b < n; b++) {
+        memset(&mi, 0, sizeof(mi));
+        mi.sb_type = BLOCK_8X8;
+        mi.ref_frame[0] = blocks[b].is_inter ? LAST_FRAME : INTRA_FRAME;
+        mi.ref_frame[1] = NONE;
+        mi.mode = blocks[b].is_inter ? ZEROMV : mode_of_tx_type[blocks[b].tx_type & 3];
+        for (int k = 0; k < 4; k++) mi.bmi[k].as_mode = mi.mode;
+        rate[b] = coeff_rate_estimate(ctx, x, (int16_t *)(qcoeff + (size_t)b * nn), eob[b], blocks[b].plane_type ? 1 : 0, 0, (TX_SIZE)tx_size, blocks[b].coeff_ctx, 0);
+    }
+    free(xd); free(x); free(ctx);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------ CPU arm of bench.py
  * A native thread pool that runs the hot path of a whole mini-GOP with the reference's own functions: the unit of work is
  * a small range of super-blocks (motion estimation) or transform blocks (perform_coding_loop chain); one picture's

@@ -461,6 +461,51 @@ def _ctx_intra_predict(self, blocks):
     self.check(self.L.svtb200_intra_predict_batch(self.h, C.addressof(blocks), len(blocks)), "intra_predict_batch")
 
 
+RATE_BLOCK_DTYPE = np.dtype([("plane_type", "u1"), ("is_inter", "u1"), ("tx_type", "u1"), ("coeff_ctx", "u1")])
+
+
+def _bind_rate(L):
+    if getattr(L, "_rate_bound", False):
+        return
+    vp = C.c_void_p
+    L.svtb200_set_scan_neighbors.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.svtb200_set_rate_tables.argtypes = [vp, vp, vp, vp, vp]
+    L.svtb200_coeff_rate_batch.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.svtb200_coeff_rate_batch_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L._rate_bound = True
+
+
+def _ctx_register_rate_tables(self, tables):
+    """tables: svt-vp9_b200/data/vp9_tables.npz (nb_<ts>_<tt>, rate_vtok / rate_vcost / rate_c6lo / rate_c6hi); the scans
+    themselves come from register_scans."""
+    _bind_rate(self.L)
+    self._rate_keep = []
+    for ts in range(4):
+        for tt in range(4):
+            nb = np.ascontiguousarray(tables["nb_%d_%d" % (ts, tt)], dtype=np.int16)
+            self.check(self.L.svtb200_set_scan_neighbors(self.h, ts, tt, nb.ctypes.data), "set_scan_neighbors")
+    a = [np.ascontiguousarray(tables[k], dtype=d) for k, d in (("rate_vtok", np.int16), ("rate_vcost", np.int32), ("rate_c6lo", np.int16), ("rate_c6hi", np.uint16))]
+    self.check(self.L.svtb200_set_rate_tables(self.h, *(x.ctypes.data for x in a)), "set_rate_tables")
+
+
+def _ctx_coeff_rate(self, tx_size, qcoeff, eob, blocks, token_costs):
+    """qcoeff (n, N*N) int16, eob (n,) uint16, blocks (n,) RATE_BLOCK_DTYPE, token_costs (2, 2, 6, 2, 6, 12) uint32 of this
+    transform size -> (n,) int32 rates."""
+    _bind_rate(self.L)
+    qcoeff = np.ascontiguousarray(qcoeff, dtype=np.int16)
+    eob = np.ascontiguousarray(eob, dtype=np.uint16)
+    blocks = np.ascontiguousarray(blocks, dtype=RATE_BLOCK_DTYPE)
+    token_costs = np.ascontiguousarray(token_costs, dtype=np.uint32)
+    assert token_costs.size == 2 * 2 * 6 * 2 * 6 * 12
+    n = len(eob)
+    rate = np.zeros(n, dtype=np.int32)
+    self.check(self.L.svtb200_coeff_rate_batch(self.h, tx_size, n, qcoeff.ctypes.data, eob.ctypes.data, blocks.ctypes.data,
+                                               token_costs.ctypes.data, rate.ctypes.data), "coeff_rate_batch")
+    return rate
+
+
+Context.register_rate_tables = _ctx_register_rate_tables
+Context.coeff_rate = _ctx_coeff_rate
 Context.inter_predict = _ctx_inter_predict
 Context.intra_predict = _ctx_intra_predict
 Context.full_distortion = _ctx_full_distortion

@@ -58,6 +58,8 @@ struct SvtB200Ctx {
     uint8_t *pin = nullptr; size_t pin_bytes = 0;
     /* transform / quant */
     ScanTable scans[4][4];
+    int16_t  *scan_nb[4][4] = {};  /* neighbour tables of the scans (rate estimation) */
+    uint8_t  *rate_tables = nullptr; /* value -> token / cost tables (rate.cu) */
     /* generic device scratch for the host-pointer entry points */
     uint8_t *scratch = nullptr; size_t scratch_bytes = 0;
     /* prediction descriptors of the batch in flight (pred.cu); pred_read: the kernel that reads them has finished */

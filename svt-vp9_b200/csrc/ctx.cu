@@ -50,7 +50,8 @@ void svtb200_destroy(SvtB200Ctx *c) {
     if (c->pred_desc) cudaFree(c->pred_desc);
     if (c->pred_read) cudaEventDestroy(c->pred_read);
     if (c->pin) cudaFreeHost(c->pin);
-    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { if (c->scans[a][b].scan) cudaFree(c->scans[a][b].scan); if (c->scans[a][b].iscan) cudaFree(c->scans[a][b].iscan); }
+    for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { if (c->scans[a][b].scan) cudaFree(c->scans[a][b].scan); if (c->scans[a][b].iscan) cudaFree(c->scans[a][b].iscan); if (c->scan_nb[a][b]) cudaFree(c->scan_nb[a][b]); }
+    if (c->rate_tables) cudaFree(c->rate_tables);
     cudaStreamDestroy(c->compute[0]); cudaStreamDestroy(c->compute[1]); cudaStreamDestroy(c->compute[2]); cudaStreamDestroy(c->up); cudaStreamDestroy(c->down);
     delete c;
 }

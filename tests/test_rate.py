@@ -1,0 +1,194 @@
+"""Coefficient rate estimation (coeff_rate_estimate, Source/Lib/Codec/EbRateDistortionCost.c:55, use_fast_coef_costing == 0):
+the oracle restatement (oracle/rate_port.c) against the reference's own function through the path driver, the CUDA kernel
+(csrc/rate.cu, one warp per block, position-parallel) against both."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import helpers as H
+
+api = H.api
+
+
+def _blocks(rng, tx_size, n, kind):
+    """n blocks as the quantiser leaves them: zero beyond eob in scan order, the coefficient at eob - 1 non-zero."""
+    N = 4 << tx_size
+    nn = N * N
+    T = H.vp9_tables()
+    blk = np.zeros(n, dtype=api.RATE_BLOCK_DTYPE)
+    blk["plane_type"] = rng.integers(0, 2, n)
+    blk["is_inter"] = rng.integers(0, 2, n)
+    # the reference derives the transform type from the block's intra mode: luma intra blocks of 4x4 .. 16x16 only
+    tt = rng.integers(0, 4, n)
+    tt[(blk["plane_type"] == 1) | (blk["is_inter"] == 1)] = 0
+    if tx_size == 3:
+        tt[:] = 0
+    blk["tx_type"] = tt
+    blk["coeff_ctx"] = rng.integers(0, 3, n)  # combine_entropy_contexts: 0, 1 or 2
+    q = np.zeros((n, nn), dtype=np.int16)
+    eob = np.zeros(n, dtype=np.uint16)
+    for b in range(n):
+        if kind == "empty":
+            e = 0
+        elif kind == "full":
+            e = nn
+        elif kind == "dc":
+            e = 1
+        else:
+            e = int(min(nn, rng.geometric(1.0 / (1 + nn // 6))))
+            if b % 7 == 0:
+                e = int(rng.integers(0, nn + 1))
+        eob[b] = e
+        if e == 0:
+            continue
+        scan = T["scan_%d_%d" % (tx_size, int(tt[b]))]
+        # category-6 tokens and the value-table edges (+-66 / +-67); |v| - 67 < 2^14 is what eb_vp9_cat6_high_cost[64] covers
+        # (8-bit coefficients never exceed it; beyond it the reference reads past its table)
+        if kind == "large":
+            vals = rng.choice(np.array([0, 1, -1, 2, 4, 5, 10, 34, 66, -66, 67, -67, 68, 300, -2000, 15000, -16450, 16450], dtype=np.int64), size=e)
+        elif kind == "sparse":  # runs of zeros: the skip-EOB-node cost tables and the energy-class contexts
+            vals = rng.integers(-3, 4, size=e) * (rng.integers(0, 3, size=e) == 0)
+        else:
+            mag = np.maximum(1, 40 // (1 + np.arange(e) // 2))
+            vals = rng.integers(-mag, mag + 1)
+        vals = np.asarray(vals, dtype=np.int64)
+        if vals[e - 1] == 0:
+            vals[e - 1] = 1 if b & 1 else -1
+        q[b, scan[:e]] = vals.astype(np.int16)
+    return q, eob, blk
+
+
+def _token_costs(rng, kind):
+    T = H.vp9_tables()
+    if kind == "default":
+        return np.ascontiguousarray(T["token_costs_default"])
+    # every entry distinct in its low bits: a wrong band / context / skip / token index cannot cancel out
+    return rng.integers(1, 1 << 14, size=(4, 2, 2, 6, 2, 6, 12)).astype(np.uint32)
+
+
+def _oracle_rate(tx_size, q, eob, blk, tc_all):
+    L = H.oracle()
+    T = H.vp9_tables()
+    scans = [np.ascontiguousarray(T["scan_%d_%d" % (tx_size, 0 if tx_size == 3 else t)], dtype=np.int16) for t in range(4)]
+    nbs = [np.ascontiguousarray(T["nb_%d_%d" % (tx_size, 0 if tx_size == 3 else t)], dtype=np.int16) for t in range(4)]
+    sp = (C.c_void_p * 4)(*[s.ctypes.data for s in scans])
+    npp = (C.c_void_p * 4)(*[s.ctypes.data for s in nbs])
+    tabs = [np.ascontiguousarray(T[k]) for k in ("rate_vtok", "rate_vcost", "rate_c6lo", "rate_c6hi")]
+    tc = np.ascontiguousarray(tc_all[tx_size])
+    rate = np.zeros(len(eob), dtype=np.int32)
+    L.svtb200_oracle_coeff_rate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 11
+    L.svtb200_oracle_coeff_rate.restype = None
+    L.svtb200_oracle_coeff_rate(tx_size, len(eob), q.ctypes.data, eob.ctypes.data, blk.ctypes.data, tc.ctypes.data, sp, npp,
+                                *(t.ctypes.data for t in tabs), rate.ctypes.data)
+    return rate
+
+
+def _ref_rate(tx_size, q, eob, blk, tc_all):
+    L = H.refdrv()
+    L.refdrv_coeff_rate.argtypes = [C.c_int, C.c_int] + [C.c_void_p] * 5
+    rate = np.zeros(len(eob), dtype=np.int32)
+    tc_all = np.ascontiguousarray(tc_all)
+    assert L.refdrv_coeff_rate(tx_size, len(eob), q.ctypes.data, eob.ctypes.data, blk.ctypes.data, tc_all.ctypes.data, rate.ctypes.data) == 0
+    return rate
+
+
+KINDS = ["typical", "sparse", "large", "empty", "full", "dc"]
+
+
+def test_tables_match_reference():
+    """the committed rate tables are the reference's (regenerate with oracle/extract_vp9_tables.py)"""
+    if not H.have_refdrv():
+        pytest.skip("oracle/_ref not built")
+    T = H.vp9_tables()
+    L = H.refdrv()
+    tc = np.zeros((4, 2, 2, 6, 2, 6, 12), dtype=np.uint32)
+    assert L.refdrv_token_costs(C.c_void_p(tc.ctypes.data)) == tc.nbytes
+    assert (tc == T["token_costs_default"]).all()
+    for ts in range(4):
+        for tt in range(4):
+            nb = np.zeros(2 * ((4 << ts) ** 2 + 1), dtype=np.int16)
+            L.refdrv_scan_neighbors(ts, tt, C.c_void_p(nb.ctypes.data))
+            assert (nb == T["nb_%d_%d" % (ts, tt)]).all()
+
+
+@pytest.mark.parametrize("tx_size", [0, 1, 2, 3])
+@pytest.mark.parametrize("costs", ["default", "random"])
+def test_oracle_vs_reference(tx_size, costs):
+    if not H.have_refdrv():
+        pytest.skip("oracle/_ref not built")
+    rng = np.random.default_rng(100 + tx_size)
+    tc = _token_costs(rng, costs)
+    for kind in KINDS:
+        q, eob, blk = _blocks(rng, tx_size, 600 if tx_size < 3 else 200, kind)
+        want = _ref_rate(tx_size, q, eob, blk, tc)
+        got = _oracle_rate(tx_size, q, eob, blk, tc)
+        assert (got == want).all(), (kind, np.flatnonzero(got != want)[:5])
+
+
+def test_golden_rates():
+    """fixture made from the reference function (tests/golden/make_rate_golden.py): travels to boxes without oracle/_ref"""
+    import os
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "rate_golden.npz"))
+    tc = H.vp9_tables()["token_costs_default"]
+    for ts in range(4):
+        got = _oracle_rate(ts, np.ascontiguousarray(g["q%d" % ts]), np.ascontiguousarray(g["eob%d" % ts]),
+                           np.ascontiguousarray(g["blk%d" % ts].view(api.RATE_BLOCK_DTYPE).reshape(-1)), tc)
+        assert (got == g["rate%d" % ts]).all()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("tx_size", [0, 1, 2, 3])
+def test_cuda_vs_oracle(tx_size):
+    rng = np.random.default_rng(200 + tx_size)
+    ctx = api.Context(0)
+    ctx.register_scans(H.vp9_tables())
+    ctx.register_rate_tables(H.vp9_tables())
+    try:
+        for costs in ("default", "random"):
+            tc = _token_costs(rng, costs)
+            for kind in KINDS:
+                q, eob, blk = _blocks(rng, tx_size, 3000 if tx_size < 3 else 700, kind)
+                want = _oracle_rate(tx_size, q, eob, blk, tc)
+                got = ctx.coeff_rate(tx_size, q, eob, blk, tc[tx_size])
+                assert (got == want).all(), (kind, costs, np.flatnonzero(got != want)[:5])
+                if H.have_refdrv():
+                    assert (got == _ref_rate(tx_size, q, eob, blk, tc)).all()
+        # empty batch and the golden fixture
+        assert len(ctx.coeff_rate(tx_size, np.zeros((0, (4 << tx_size) ** 2), np.int16), np.zeros(0, np.uint16), np.zeros(0, api.RATE_BLOCK_DTYPE),
+                                  tc[tx_size])) == 0
+    finally:
+        ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_rate_of_txq_output():
+    """the rate of the coefficients the fused transform kernel leaves on the device (the chain perform_dist_rate_calc runs,
+    EbEncDecProcess.c:723-745): 4K-picture-sized batch, device-resident"""
+    rng = np.random.default_rng(9)
+    T = H.vp9_tables()
+    ctx = api.Context(0)
+    ctx.register_scans(T)
+    ctx.register_rate_tables(T)
+    try:
+        src = rng.integers(0, 256, size=(512, 1024), dtype=np.uint8)
+        pred = np.clip(src.astype(int) + rng.integers(-25, 26, size=src.shape), 0, 255).astype(np.uint8)
+        rows = H.quant_rows([45, 120])
+        for ts in (3, 2, 1, 0):
+            N = 4 << ts
+            by, bx = np.meshgrid(np.arange(0, 512, N), np.arange(0, 1024, N), indexing="ij")
+            jobs = np.zeros(by.size, dtype=api.TX_JOB_DTYPE)
+            jobs["src_offset"] = jobs["pred_offset"] = jobs["recon_offset"] = by.ravel() * 1024 + bx.ravel()
+            jobs["qrow"] = np.arange(by.size) & 1
+            jobs["tx_type"] = 0 if ts == 3 else np.arange(by.size) & 3
+            jobs["flags"] = 1
+            coeff, q, dq, eob, rec = ctx.txq(ts, jobs, src, pred, np.zeros_like(src), rows)
+            blk = np.zeros(len(jobs), dtype=api.RATE_BLOCK_DTYPE)
+            blk["tx_type"] = jobs["tx_type"]
+            blk["coeff_ctx"] = np.arange(len(jobs)) % 3
+            q2 = np.ascontiguousarray(q.reshape(len(jobs), -1))
+            e2 = np.ascontiguousarray(eob, dtype=np.uint16)
+            got = ctx.coeff_rate(ts, q2, e2, blk, T["token_costs_default"][ts])
+            assert (got == _oracle_rate(ts, q2, e2, blk, T["token_costs_default"])).all()
+    finally:
+        ctx.close()
