@@ -4,13 +4,16 @@
 A "step" is one pass of the hot path over one 16-picture hierarchical mini-GOP of 3840x2160 pictures of BASELINE.json's
 configs[2] (4K 8-bit 4:2:0, enc-mode 8), processed in encode order with the real reference structure and
 per-temporal-layer search parameters; per picture:
-    motion estimation (2 lists)  ->  transform / quantise / reconstruct every TU once (luma 32x32, chroma 16x16,
-    prediction = list-0 reference at zero motion)  ->  deblocking of the base-layer picture (enc-mode 8 filters
+    motion estimation (2 lists)  ->  inter prediction of an open-loop partition (every 32x32 block -- 16x16 in the last 16 rows --
+    motion compensated with the best candidate motion estimation found for it: the encode pass's block walk + 8-tap predictors,
+    three planes)  ->  transform / quantise / reconstruct every TU once (luma 32x32, chroma 16x16)  ->  the coefficients packed as
+    the entropy coder reads them + their rate (coeff_rate_estimate)  ->  deblocking of the base-layer picture (enc-mode 8 filters
     temporal layer 0 only).
 
   value         pictures / s, planes already resident in HBM, results left in HBM (CUDA events on the context stream)
   e2e           pictures / s through the host-pointer side of the C ABI: pinned-host upload of the picture's planes,
-                kernels, download of ME results, quantised coefficients + eob and (base layer) the filtered planes
+                kernels, download of ME results, quantised coefficients (scan-order prefixes) + eob + rates and (base layer) the
+                filtered planes
   roofline      algorithmic bytes of the dominant kernel / its CUDA-event time, against the measured HBM peak
   cpu_baseline  the same pictures through the CPU implementation on the host cores: the reference's own functions
                 (oracle/_ref, kind "reference") on a native pinned thread pool, or the oracle port (kind "port")
@@ -58,7 +61,9 @@ TU_ROWS, TU_COLS = H4K // 32, W4K // 32  # 67 x 120 luma 32x32 TUs; the last 16 
 # every sample of the picture belongs to exactly one TU: (plane 0 Y / 1 U / 2 V, tx_size, TU size, TUs per row, TU rows, first sample row)
 TU_PASSES = [(0, 3, 32, 120, 67, 0), (0, 2, 16, 240, 1, 2144), (1, 2, 16, 120, 67, 0), (1, 1, 8, 240, 1, 1072),
              (2, 2, 16, 120, 67, 0), (2, 1, 8, 240, 1, 1072)]
-METRIC = "pictures/s through the encode hot path (motion estimation + transform/quant/recon + deblocking; 4K, enc-mode 8 parameter set)"
+N_BLK = (W4K // 32) * (H4K // 32) + (H4K // 16 - 2 * (H4K // 32)) * (W4K // 16)   # blocks of the open-loop partition: 8040 32x32 + 240 16x16
+CPAD = 40             # padding of the chroma reference planes (the reference pads chroma by half the luma padding)
+METRIC = "pictures/s through the encode hot path (motion estimation + inter prediction + transform/quant/recon + coefficient packing / rate + deblocking; 4K, enc-mode 8 parameter set)"
 
 
 def refs_of(n):
@@ -83,6 +88,12 @@ def me_bytes(P):
 def txq_bytes():
     """6N^2+2 per block + N^2 for the reconstruction"""
     return sum(cols * rows * (7 * size * size + 2) for _, _, size, cols, rows, _ in TU_PASSES)
+
+
+def pred_bytes(P):
+    """lower bound: every predicted sample read from one reference (compound blocks read two) and written once; per block the
+    motion-estimation result (40 B), the block record (16 B) and three descriptors (64 B each)"""
+    return (W4K * H4K * 3 // 2) * 2 + N_BLK * (40 + 16 + 3 * 64)
 
 
 def lf_bytes():
@@ -201,8 +212,16 @@ class CpuPath:
         self.kind = "reference" if H.have_refdrv() else "port"
         self.pics = [frames.pa_planes(f[0]) for f in clip]
         self.structs = [frames.plane_structs(p) for p in self.pics]
-        self.luma = [aligned_copy(f[0]) for f in clip]  # unpadded, aligned: source / prediction planes of the transform stage
+        self.luma = [aligned_copy(f[0]) for f in clip]  # unpadded, aligned: source planes of the transform stage
         self.chroma = [(aligned_copy(f[1]), aligned_copy(f[2])) for f in clip]
+        # reference planes of the inter prediction: the padded luma of the picture-analysis stage, chroma padded by CPAD
+        self.chroma_pad = [(aligned_copy(np.pad(f[1], CPAD, mode="edge")), aligned_copy(np.pad(f[2], CPAD, mode="edge"))) for f in clip]
+        self.token_costs = np.ascontiguousarray(H.vp9_tables()["token_costs_default"])
+        self.rblk = []
+        for plane, ts, size, cols, rows, row0 in TU_PASSES:
+            rb = np.zeros(cols * rows, dtype=api.RATE_BLOCK_DTYPE)
+            rb["plane_type"], rb["is_inter"] = (1 if plane else 0), 1
+            self.rblk.append(rb)
         self.rows = H.quant_rows([QINDEX])
         self.lfm, self.thr = lf_masks_32x32(), H.lf_thresholds()
         self.LfP = api.LfParams()
@@ -219,7 +238,10 @@ class CpuPath:
         self.eob = [[np.zeros(cols * rows, np.uint16) for _, _, _, cols, rows, _ in TU_PASSES] for _ in range(n_buffers)]
         self.recon = [[aligned((H4K, W4K), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8)]
                       for _ in range(n_buffers)]
-        self.stage_cpu_s = [0.0, 0.0, 0.0]
+        self.pred = [[aligned((H4K, W4K), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8), aligned((H4K // 2, W4K // 2), np.uint8)]
+                     for _ in range(n_buffers)]
+        self.rate = [[np.zeros(cols * rows, np.int32) for _, _, _, cols, rows, _ in TU_PASSES] for _ in range(n_buffers)]
+        self.stage_cpu_s = [0.0, 0.0, 0.0, 0.0]
         if self.kind == "reference":
             self.L = H.refdrv(1)
             self.pool = self.L.refdrv_pool_new(threads, 1)
@@ -244,7 +266,7 @@ class CpuPath:
         d.n_pass = len(TU_PASSES)
         for k, (plane, ts, size, cols, rows, row0) in enumerate(TU_PASSES):
             src = self.luma[n] if plane == 0 else self.chroma[n][plane - 1]
-            pred = self.luma[r0] if plane == 0 else self.chroma[r0][plane - 1]
+            pred = self.pred[b][plane]
             rec = self.recon[b][plane]
             tp = d.passes[k]
             tp.tx_size, tp.n, tp.jobs = ts, cols * rows, self.jobs[k].ctypes.data
@@ -252,12 +274,31 @@ class CpuPath:
             tp.pl.pred, tp.pl.pred_stride, tp.pl.pred_bytes = pred.ctypes.data, pred.shape[1], pred.nbytes
             tp.pl.recon, tp.pl.recon_stride, tp.pl.recon_bytes = rec.ctypes.data, rec.shape[1], rec.nbytes
             tp.coeff, tp.qcoeff, tp.dqcoeff, tp.eob = None, self.q[b][k].ctypes.data, self.dq[b][k].ctypes.data, self.eob[b][k].ctypes.data
+            tp.rblk, tp.rate = self.rblk[k].ctypes.data, self.rate[b][k].ctypes.data
+        d.n_blocks = N_BLK
+        d.pred = self._pred_picture(b, r0, r1)
+        d.token_costs_all = self.token_costs.ctypes.data
         d.qrows = self.rows.ctypes.data
         d.deblock = 1 if n == 16 else 0
         d.lf = self.LfP
         d.y, d.u, d.v = (r.ctypes.data for r in self.recon[b])
         d.ys, d.cs = W4K, W4K // 2
         d.lfm, d.lfm_stride, d.thr = self.lfm.ctypes.data, 60, self.thr.ctypes.data
+
+    def _pred_picture(self, b, r0, r1):
+        pp = api.PredPicture()
+        pp.width, pp.height, pp.use_subpel_flag = W4K, H4K, 1
+        for l, r in enumerate((r0, r1)):
+            full = self.pics[r]["full"]
+            pp.ref[l][0] = full.ctypes.data + frames.FULL_PAD * full.shape[1] + frames.FULL_PAD
+            pp.ref_stride[l][0] = full.shape[1]
+            for c in range(2):
+                a = self.chroma_pad[r][c]
+                pp.ref[l][1 + c] = a.ctypes.data + CPAD * a.shape[1] + CPAD
+                pp.ref_stride[l][1 + c] = a.shape[1]
+        for k in range(3):
+            pp.dst[k], pp.dst_stride[k] = self.pred[b][k].ctypes.data, self.pred[b][k].shape[1]
+        return pp
 
     def run(self, order):
         """the pictures of 'order' (display offsets, encode order), picture j into result slot j"""
@@ -270,11 +311,11 @@ class CpuPath:
         arr = (H.RefdrvPicture * len(order))()
         for b, n in enumerate(order):
             self._picture_desc(arr[b], n, b)
-        cpu_s = (C.c_double * 3)()
+        cpu_s = (C.c_double * 4)()
         rc = self.L.refdrv_pool_run(self.pool, arr, len(order), 4, 64, cpu_s)
         if rc:
             raise RuntimeError("refdrv_pool_run: %d" % rc)
-        for k in range(3):
+        for k in range(4):
             self.stage_cpu_s[k] += cpu_s[k]
 
     def minigop(self):
@@ -290,10 +331,20 @@ class CpuPath:
         cur, s0, s1 = self.structs[n], self.structs[r0], self.structs[r1]
         out = self.me_out[b]
         list(self.tpool.map(lambda a: L.svtb200_oracle_me_picture(C.byref(P), cur, s0, s1, out.ctypes.data, None, a[1], a[2]), self._split(N_SB)))
+        # open-loop partition -> descriptors -> prediction planes (oracle/blocks_port.c, pred_port.c)
+        blocks = np.zeros(N_BLK, dtype=api.INTER_BLOCK_DTYPE)
+        L.svtb200_oracle_me_best_blocks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        L.svtb200_oracle_inter_expand.argtypes = [C.c_void_p, C.c_int, C.POINTER(api.PredPicture), C.c_void_p]
+        L.svtb200_oracle_inter_predict.argtypes = [C.c_void_p, C.c_int]
+        assert L.svtb200_oracle_me_best_blocks(out.ctypes.data, W4K, H4K, blocks.ctypes.data) == N_BLK
+        pp = self._pred_picture(b, r0, r1)
+        desc = (api.PredBlock * (3 * N_BLK))()
+        L.svtb200_oracle_inter_expand(blocks.ctypes.data, N_BLK, C.byref(pp), C.addressof(desc))
+        list(self.tpool.map(lambda a: L.svtb200_oracle_inter_predict(C.addressof(desc) + a[1] * C.sizeof(api.PredBlock), a[2] - a[1]), self._split(3 * N_BLK)))
         Lt = H.oracle_tx()
         for k, (plane, ts, size, cols, rows, row0) in enumerate(TU_PASSES):
             src = self.luma[n] if plane == 0 else self.chroma[n][plane - 1]
-            pred = self.luma[r0] if plane == 0 else self.chroma[r0][plane - 1]
+            pred = self.pred[b][plane]
             rec, jobs, q, dq, eob = self.recon[b][plane], self.jobs[k], self.q[b][k], self.dq[b][k], self.eob[b][k]
             N = size
             scan = np.ascontiguousarray(H.scan_of(ts, 0)[0])
@@ -311,6 +362,8 @@ class CpuPath:
                     Lt.svtb200_oracle_inv_txfm_add(ts, 0, dq[i].ctypes.data, int(eob[i]), blk.ctypes.data, N)
                     rec[ry:ry + N, rx:rx + N] = blk
             list(self.tpool.map(work, self._split(len(jobs))))
+            import test_rate as TR
+            self.rate[b][k][:] = TR._oracle_rate(ts, np.ascontiguousarray(q.reshape(len(jobs), -1)), eob, self.rblk[k], self.token_costs)
         if n == 16:
             m = self.lfm.copy()
             L.svtb200_oracle_deblock_picture(C.byref(self.LfP), self.recon[b][0].ctypes.data, W4K, self.recon[b][1].ctypes.data, self.recon[b][2].ctypes.data,
@@ -318,7 +371,8 @@ class CpuPath:
 
     def stage_share(self):
         t = sum(self.stage_cpu_s)
-        return None if t <= 0 else {"motion_estimation": self.stage_cpu_s[0] / t, "transform_chain": self.stage_cpu_s[1] / t, "deblocking": self.stage_cpu_s[2] / t}
+        return None if t <= 0 else {"motion_estimation": self.stage_cpu_s[0] / t, "inter_prediction": self.stage_cpu_s[3] / t,
+                                    "transform_chain_and_rate": self.stage_cpu_s[1] / t, "deblocking": self.stage_cpu_s[2] / t}
 
 
 # ---------------------------------------------------------------------------------------------------------------------
@@ -453,12 +507,16 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     config = {"workload": "configs[2]: 4K (3840x2160) 8-bit yuv420p, enc-mode 8 (tune 1 parameter set): per picture ME (2 lists) + one "
-                          "transform/quantise/reconstruct pass over every TU (luma 32x32, chroma 16x16; 16x16 / 8x8 for the last 16 rows; q 45) + deblocking on the "
-                          "base-layer picture; step = one 16-picture hierarchical mini-GOP in encode order",
+                          "transform/quantise/reconstruct pass over every TU (luma 32x32, chroma 16x16; 16x16 / 8x8 for the last 16 rows; q 45; prediction = every "
+                          "32x32 block motion compensated with its best motion-estimation candidate, 3 planes) + scan-order packing and rate of the coefficients + "
+                          "deblocking on the base-layer picture; step = one 16-picture hierarchical mini-GOP in encode order",
               "pictures_per_step": PICS_PER_STEP,
-              "queues": "motion estimation on the context's first compute queue, the picture's transform launch (all six TU batches in one "
-                        "kernel) + deblocking on its second (they belong to different pictures in the encoder); value = "
+              "queues": "motion estimation on the context's first compute queue; the rest of the picture's chain (open-loop partition, block walk, "
+                        "inter prediction, the transform launch with all six TU batches, coefficient packing, rate, deblocking) on its second, "
+                        "behind the picture's motion estimation and beside the next picture's; value = "
                         "CUDA events around the K steps with both queues joined inside the timed region",
+              "coefficients": "quantised coefficients leave the device as the scan-order prefix (eob entries) of every TU -- what the entropy coder reads "
+                              "(svtb200_coeff_pack_dev); in the end-to-end leg the pack kernel stores them straight into page-locked host memory",
               "l2": "17 distinct pictures (165 MB of luma planes + 105 MB chroma) cycled: working set larger than the 126 MB L2",
               "parallelism": "pictures sharded across GPUs (independent mini-GOP streams per rank), no collective on the data path"}
 
@@ -474,7 +532,7 @@ def main():
             if i >= args.warmup:
                 times.append(time.perf_counter() - t0)
             else:
-                cpu.stage_cpu_s = [0.0, 0.0, 0.0]
+                cpu.stage_cpu_s = [0.0, 0.0, 0.0, 0.0]
             if time.perf_counter() - t_all > 200 and len(times) >= 2:
                 break
             if time.perf_counter() - t_all > 200 and i < args.warmup:
@@ -485,7 +543,7 @@ def main():
                           "warmup": args.warmup, "ms_per_step": 1000.0 * PICS_PER_STEP / v if v else None, "higher_is_better": True, "scaling": "weak",
                           "vs_baseline": None, "dtype": "u8", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": v, "unit": "fps", "cores": ncores, "kind": cpu.kind, "stage_share_of_cpu_time": cpu.stage_share(),
-                                           "sample": "whole 4K mini-GOPs (16 pictures, all 2040 SBs and all TUs each), one native call per mini-GOP, %d pinned host threads" % ncores},
+                                           "sample": "whole 4K mini-GOPs (16 pictures, all 2040 SBs, all prediction blocks and all TUs each), one native call per mini-GOP, %d pinned host threads" % ncores},
                           "e2e": {"value": v, "unit": "fps", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         cpu.close()
         return
@@ -518,12 +576,28 @@ def main():
         return arr
     PS = [pstructs(i) for i in range(N_FRAMES)]
     csize = (W4K // 2) * (H4K // 2)
-    d_u = [L.svtb200_dev_alloc(h, csize) for _ in range(N_FRAMES)]
-    d_v = [L.svtb200_dev_alloc(h, csize) for _ in range(N_FRAMES)]
+    # chroma planes live padded on the device (they are reference planes of the inter prediction): the picture area is uploaded into
+    # the interior, the padding is made on the device (svtb200_pad_plane_dev = eb_vp9_generate_padding)
+    cw, chh = W4K // 2, H4K // 2
+    cstride, cbytes = cw + 2 * CPAD, (cw + 2 * CPAD) * (chh + 2 * CPAD)
+    corg = CPAD * cstride + CPAD
+    d_u = [L.svtb200_dev_alloc(h, cbytes) for _ in range(N_FRAMES)]
+    d_v = [L.svtb200_dev_alloc(h, cbytes) for _ in range(N_FRAMES)]
+
+    def upload_chroma(n):
+        for d, src in ((d_u[n], pu[n]), (d_v[n], pv[n])):
+            ctx.check(L.svtb200_memcpy_h2d_2d_async(h, d + corg, cstride, src.data_ptr(), cw, cw, chh), "h2d chroma")
+
+    def pad_chroma(n):
+        """on the current compute queue"""
+        for d in (d_u[n], d_v[n]):
+            ctx.check(L.svtb200_pad_plane_dev(h, d, cstride, cw, chh, CPAD, CPAD), "pad chroma")
     for i in range(N_FRAMES):
         ctx.picture_upload_luma(i, PS[i][0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, False)   # aligned device geometry, padding + 1/16 plane made on the device
-        L.svtb200_memcpy_h2d(h, d_u[i], pu[i].data_ptr(), csize)
-        L.svtb200_memcpy_h2d(h, d_v[i], pv[i].data_ptr(), csize)
+        upload_chroma(i)
+        ctx.sync()
+        pad_chroma(i)
+    ctx.sync()
     dplane = []
     for i in range(N_FRAMES):
         p = api.Plane()
@@ -538,37 +612,69 @@ def main():
     # one job table per TU pass: luma addresses the padded resident plane, chroma the packed buffers
     pass_n = [cols * rows for _, _, _, cols, rows, _ in TU_PASSES]
     pass_cb = [n * size * size * 2 for n, (_, _, size, _, _, _) in zip(pass_n, TU_PASSES)]   # bytes of one coefficient array
-    d_jobs = [to_dev(tu_jobs(sy, dplane[0].origin_x, dplane[0].origin_y, n, size, W4K, cols, row0) if plane == 0 else
-                     tu_jobs(W4K // 2, 0, 0, n, size, W4K // 2, cols, row0))
-              for n, (plane, _, size, cols, rows, row0) in zip(pass_n, TU_PASSES)]
+    def gpu_jobs(plane, n, size, cols, row0):
+        """source offsets into the padded resident planes; prediction and reconstruction offsets into packed planes"""
+        j = tu_jobs(sy, dplane[0].origin_x, dplane[0].origin_y, n, size, W4K, cols, row0) if plane == 0 else tu_jobs(cstride, CPAD, CPAD, n, size, cw, cols, row0)
+        j["pred_offset"] = j["recon_offset"]
+        return j
+    d_jobs = [to_dev(gpu_jobs(plane, n, size, cols, row0)) for n, (plane, _, size, cols, rows, row0) in zip(pass_n, TU_PASSES)]
     d_rows = to_dev(H.quant_rows([QINDEX]))
     d_lfm, d_thr = to_dev(lf_masks_32x32()), to_dev(H.lf_thresholds())
     # result buffers exist NSLOT times: the end-to-end leg downloads slot s while the kernels of the next pictures fill the others
     NSLOT = 3
     d_rec = [[L.svtb200_dev_alloc(h, W4K * H4K), L.svtb200_dev_alloc(h, csize), L.svtb200_dev_alloc(h, csize)] for _ in range(NSLOT)]
+    d_pred = [[L.svtb200_dev_alloc(h, W4K * H4K), L.svtb200_dev_alloc(h, csize), L.svtb200_dev_alloc(h, csize)] for _ in range(NSLOT)]
+    d_blk = [L.svtb200_dev_alloc(h, N_BLK * 16) for _ in range(NSLOT)]
+    d_desc = [L.svtb200_dev_alloc(h, 3 * N_BLK * C.sizeof(api.PredBlock)) for _ in range(NSLOT)]
+    d_rate_all = [L.svtb200_dev_alloc(h, rate_off[-1]) for _ in range(NSLOT)]
+    d_rate = [[d_rate_all[s_] + rate_off[k] for k in range(len(pass_n))] for s_ in range(NSLOT)]
+    rblk = []
+    for plane, _, _, cols, rows, _ in TU_PASSES:
+        rb = np.zeros(cols * rows, dtype=api.RATE_BLOCK_DTYPE)
+        rb["plane_type"], rb["is_inter"] = (1 if plane else 0), 1
+        rblk.append(to_dev(rb))
+    d_tc = [to_dev(np.ascontiguousarray(H.vp9_tables()["token_costs_default"][ts])) for ts in range(4)]
+    ctx.register_rate_tables(H.vp9_tables())
     d_me = [L.svtb200_dev_alloc(h, N_SB * 85 * 40) for _ in range(NSLOT)]
     d_q = [[L.svtb200_dev_alloc(h, b) for b in pass_cb] for _ in range(NSLOT)]
     d_dq = [L.svtb200_dev_alloc(h, b) for b in pass_cb]
-    d_eob = [[L.svtb200_dev_alloc(h, n * 2) for n in pass_n] for _ in range(NSLOT)]
+    # eob (and, below, rate) arrays of the six passes are carved from one allocation per slot: one download each
+    al = lambda v: (v + 255) & ~255
+    eob_off = [sum(al(m * 2) for m in pass_n[:k]) for k in range(len(pass_n) + 1)]
+    rate_off = [sum(al(m * 4) for m in pass_n[:k]) for k in range(len(pass_n) + 1)]
+    d_eob_all = [L.svtb200_dev_alloc(h, eob_off[-1]) for _ in range(NSLOT)]
+    d_eob = [[d_eob_all[s_] + eob_off[k] for k in range(len(pass_n))] for s_ in range(NSLOT)]
     LfP = api.LfParams()
     LfP.width, LfP.height, LfP.mi_rows, LfP.mi_cols, LfP.y_only, LfP.filter_level = W4K, H4K, H4K // 8, W4K // 8, 0, LF_LEVEL
     # pinned host result buffers for the e2e leg
     pinned = lambda n: torch.empty(n, dtype=torch.uint8).pin_memory()
     h_me = [pinned(N_SB * 85 * 40) for _ in range(NSLOT)]
-    h_q = [[pinned(b) for b in pass_cb] for _ in range(NSLOT)]
-    h_eob = [[pinned(n * 2) for n in pass_n] for _ in range(NSLOT)]
+    # quantised coefficients leave the device as scan-order prefixes (svtb200_coeff_pack_dev): one stream + offsets per picture.  The
+    # value leg keeps them in HBM; the end-to-end leg lets the pack kernel store straight into these page-locked host buffers
+    n_tu, n_coef = sum(pass_n), sum(pass_cb) // 2
+    d_stream = [L.svtb200_dev_alloc(h, n_coef * 2) for _ in range(NSLOT)]
+    d_off = [L.svtb200_dev_alloc(h, (n_tu + 1) * 4) for _ in range(NSLOT)]
+    h_stream = [pinned(n_coef * 2) for _ in range(NSLOT)]
+    h_off = [pinned((n_tu + 1) * 4) for _ in range(NSLOT)]
+    h_off_np = [x.numpy().view(np.uint32) for x in h_off]
+    h_eob_all = [pinned(eob_off[-1]) for _ in range(NSLOT)]
+    h_rate_all = [pinned(rate_off[-1]) for _ in range(NSLOT)]
+    h_eob = [[h_eob_all[s_][eob_off[k]:eob_off[k] + pass_n[k] * 2] for k in range(len(pass_n))] for s_ in range(NSLOT)]
+    h_rate = [[h_rate_all[s_][rate_off[k]:rate_off[k] + pass_n[k] * 4] for k in range(len(pass_n))] for s_ in range(NSLOT)]
     h_rec = [[pinned(W4K * H4K), pinned(csize), pinned(csize)] for _ in range(NSLOT)]
 
     def txq_planes(src, sstride, sbytes, pred, rec, rstride, rbytes):
+        """prediction and reconstruction planes share their (packed) geometry"""
         pl = api.TxPlanes()
         pl.src, pl.src_stride, pl.src_bytes = src, sstride, sbytes
-        pl.pred, pl.pred_stride, pl.pred_bytes = pred, sstride, sbytes
+        pl.pred, pl.pred_stride, pl.pred_bytes = pred, rstride, rbytes
         pl.recon, pl.recon_stride, pl.recon_bytes = rec, rstride, rbytes
         return pl
 
     ev = lambda: torch.cuda.Event(enable_timing=True)
-    stage_ms = {"me_sb_kernel": 0.0, "txq_kernel": 0.0, "lf_row_kernel": 0.0}
-    alg = {"me_sb_kernel": 0, "txq_kernel": 0, "lf_row_kernel": 0}
+    KERNELS = ("me_sb_kernel", "pred_kernel", "txq_kernel", "pack_kernel", "rate_kernel", "lf_row_kernel")
+    stage_ms = {k: 0.0 for k in KERNELS}
+    alg = {k: 0 for k in KERNELS}
     marks = []
 
     # The transform pass and the deblocking of a picture go to the context's second compute queue: in the encoder they belong to
@@ -583,7 +689,33 @@ def main():
     _txq_cache = {}
     api._bind_txq(L)
 
-    def txq_batches(slot, n, r0):
+    _pp_cache, _rb_cache = {}, {}
+
+    def pred_picture(slot, r0, r1):
+        """reference planes of both lists (resident, padded), prediction planes of the slot"""
+        key = (slot, r0, r1)
+        if key not in _pp_cache:
+            pp = api.PredPicture()
+            pp.width, pp.height, pp.use_subpel_flag = W4K, H4K, 1
+            for l, r in enumerate((r0, r1)):
+                pp.ref[l][0] = dplane[r].buf + dplane[r].origin_y * sy + dplane[r].origin_x
+                pp.ref[l][1], pp.ref[l][2] = d_u[r] + corg, d_v[r] + corg
+                pp.ref_stride[l][0], pp.ref_stride[l][1], pp.ref_stride[l][2] = sy, cstride, cstride
+            for k in range(3):
+                pp.dst[k], pp.dst_stride[k] = d_pred[slot][k], (W4K if k == 0 else cw)
+            _pp_cache[key] = pp
+        return _pp_cache[key]
+
+    def rate_batches(slot):
+        if slot not in _rb_cache:
+            arr = (api.RateBatch * len(TU_PASSES))()
+            for k, (plane, ts, size, cols, rows, row0) in enumerate(TU_PASSES):
+                b = arr[k]
+                b.tx_size, b.n, b.qcoeff, b.eob, b.blocks, b.token_costs, b.rate = ts, pass_n[k], d_q[slot][k], d_eob[slot][k], rblk[k], d_tc[ts], d_rate[slot][k]
+            _rb_cache[slot] = arr
+        return _rb_cache[slot]
+
+    def txq_batches(slot, n, r0=None):
         """the SvtB200TxBatch array (six batches: every TU of the three planes) of picture n into result slot 'slot' (built once)"""
         key = (slot, n)
         if key not in _txq_cache:
@@ -592,23 +724,45 @@ def main():
             arr = (api.TxBatch * len(TU_PASSES))()
             for k, (plane, ts, size, cols, rows, row0) in enumerate(TU_PASSES):
                 if plane == 0:
-                    pl = txq_planes(dplane[n].buf, sy, ybytes, dplane[r0].buf, rec[0], W4K, W4K * H4K)
+                    pl = txq_planes(dplane[n].buf, sy, ybytes, d_pred[slot][0], rec[0], W4K, W4K * H4K)
                 else:
                     dc = d_u if plane == 1 else d_v
-                    pl = txq_planes(dc[n], W4K // 2, csize, dc[r0], rec[plane], W4K // 2, csize)
+                    pl = txq_planes(dc[n], cstride, cbytes, d_pred[slot][plane], rec[plane], cw, csize)
                 b = arr[k]
                 b.tx_size, b.n, b.jobs, b.planes = ts, pass_n[k], d_jobs[k], pl
                 b.coeff, b.qcoeff, b.dqcoeff, b.eob = None, q[k], d_dq[k], eob[k]
             _txq_cache[key] = arr
         return _txq_cache[key]
 
-    def kernels(i, timed, slot=0, overlap=True, sink=None):
+    _chain_cache = {}
+
+    def chain_of(slot, n, r0, r1, pack_host, behind):
+        """the SvtB200InterChain of picture n into result slot 'slot' (built once)"""
+        key = (slot, n, pack_host, behind)
+        if key not in _chain_cache:
+            ch = api.InterChain()
+            ch.after_queue = behind
+            ch.me, ch.blocks, ch.n_blocks, ch.pic, ch.desc = d_me[slot], d_blk[slot], N_BLK, pred_picture(slot, r0, r1), d_desc[slot]
+            ch.tx, ch.n_tx, ch.qrows, ch.n_qrows = txq_batches(slot, n), len(TU_PASSES), d_rows, 1
+            ch.stream, ch.offsets = (h_stream[slot].data_ptr(), h_off[slot].data_ptr()) if pack_host else (d_stream[slot], d_off[slot])
+            ch.capacity = n_coef
+            ch.rate, ch.n_rate = rate_batches(slot), len(TU_PASSES)
+            rd = sorted({n, r0, r1})
+            for k, r in enumerate(rd):
+                ch.reads[k] = r
+            ch.n_reads = len(rd)
+            _chain_cache[key] = ch
+        return _chain_cache[key]
+
+    def kernels(i, timed, slot=0, overlap=True, sink=None, pack_host=False, detail=False):
+        """the kernels of step i: motion estimation on the first compute queue, the rest of the picture's chain on the second (one
+        svtb200_inter_chain_dev call; detail=True: the chain's stages through their own entry points, an event after each)"""
         n = ENCODE_ORDER[i % 16]
         s2 = stream2 if overlap else stream
         q1, s1 = (api.COMPUTE3, stream3) if overlap and ME_QUEUES == 2 and (i & 1) else (api.COMPUTE, stream)
         P, (r0, r1) = me_params(n)
         ids = (C.c_uint64 * 2)(r0, r1)
-        e = [ev() for _ in range(6)] if timed else None
+        e = [ev() for _ in range(9)] if timed else None
         ctx.select_compute(q1)
         if timed:
             e[0].record(s1)
@@ -617,29 +771,48 @@ def main():
             e[1].record(s1)
         if overlap:
             ctx.select_compute(api.COMPUTE2)
-        if timed:
+        if not detail:
+            if timed:
+                e[2].record(s2)
+            # open-loop partition -> block walk -> inter prediction (3 planes) -> every TU of the picture -> packing -> rate: one call,
+            # queued behind the picture's motion estimation
+            rc = L.svtb200_inter_chain_dev(h, C.addressof(chain_of(slot, n, r0, r1, pack_host, q1 if overlap else -1)))
+            if rc:
+                ctx.check(rc, "inter_chain_dev")
+            if timed:
+                e[7].record(s2)
+        else:
+            if overlap:
+                ctx.stream_wait(api.COMPUTE2, ctx.marker(q1))
             e[2].record(s2)
-        # every TU of the picture (luma 32x32 + the 16x16 edge row, chroma 16x16 + 8x8 edge rows) in ONE launch
-        rc = L.svtb200_txq_multi_dev(h, txq_batches(slot, n, r0), len(TU_PASSES), d_rows, 1)
-        if rc:
-            ctx.check(rc, "txq_multi_dev")
-        if timed:
+            rc = L.svtb200_me_best_blocks_dev(h, d_me[slot], W4K, H4K, d_blk[slot])
+            if rc != N_BLK:
+                ctx.check(rc if rc < 0 else -1, "me_best_blocks_dev")
+            ctx.check(L.svtb200_inter_blocks_expand_dev(h, d_blk[slot], N_BLK, C.byref(pred_picture(slot, r0, r1)), d_desc[slot]), "inter_blocks_expand_dev")
+            ctx.check(L.svtb200_inter_predict_batch_dev(h, d_desc[slot], 3 * N_BLK), "inter_predict_batch_dev")
+            e[6].record(s2)
+            ctx.check(L.svtb200_txq_multi_dev(h, txq_batches(slot, n), len(TU_PASSES), d_rows, 1), "txq_multi_dev")
             e[3].record(s2)
+            ctx.check(L.svtb200_coeff_pack_dev(h, txq_batches(slot, n), len(TU_PASSES), d_stream[slot], n_coef, d_off[slot]), "coeff_pack_dev")
+            e[5].record(s2)
+            ctx.check(L.svtb200_coeff_rate_multi_dev(h, rate_batches(slot), len(TU_PASSES)), "coeff_rate_multi_dev")
+            e[7].record(s2)
+            for r in {n, r0, r1}:
+                L.svtb200_picture_touch(h, r)
         if n == 16:
             rec = d_rec[slot]
             ctx.check(L.svtb200_deblock_picture_dev(h, C.byref(LfP), rec[0], W4K, rec[1], rec[2], W4K // 2, d_lfm, 60, d_thr), "deblock")
         if timed:
             e[4].record(s2)
             (marks if sink is None else sink).append((e, P, n))
-        L.svtb200_picture_touch(h, n)      # the transform kernel reads the planes of pictures n and r0 on this queue
-        L.svtb200_picture_touch(h, r0)
         ctx.select_compute(api.COMPUTE)
-        return n, r0
+        return n, r0, r1
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI's three queues.  Picture i+1 uploads and
     # picture i-1 downloads while picture i computes; the host collects picture i-3's results (the previous user of the slot)
     # before it queues picture i, i.e. three pictures are in flight (upload / kernels / download).
     downloaded = [0] * NSLOT   # marker after the last download out of each result slot
+    stream_coefs = [0, 0]      # coefficients the pack kernel stored into host memory, pictures counted
     chroma_used = {}      # marker after the last kernel that read the chroma buffers of a picture
 
     skip = os.environ.get("SVTB200_E2E_SKIP", "").split(",")  # diagnosis only: "h2d", "d2h", "kernels"
@@ -649,34 +822,48 @@ def main():
         slot = i % NSLOT
         if downloaded[slot]:
             ctx.wait(downloaded[slot])                                          # picture i-NSLOT is complete in host memory; its slot is free
+            stream_coefs[0] += int(h_off_np[slot][n_tu]); stream_coefs[1] += 1  # what the pack kernel stored for it
         if "h2d" not in skip:
             ctx.picture_upload_luma(n, PS[n][0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, False)   # H2D luma picture area; padding + 1/16 on the device
             if n in chroma_used:
                 for m in chroma_used[n]:
                     ctx.stream_wait(api.UPLOAD, m)
-            ctx.check(L.svtb200_memcpy_h2d_async(h, d_u[n], pu[n].data_ptr(), csize), "h2d u")     # H2D chroma
-            ctx.check(L.svtb200_memcpy_h2d_async(h, d_v[n], pv[n].data_ptr(), csize), "h2d v")
-            ctx.fence(api.UPLOAD, api.COMPUTE)
-            ctx.fence(api.UPLOAD, api.COMPUTE2)
-            ctx.fence(api.UPLOAD, api.COMPUTE3)
+            upload_chroma(n)                                                    # H2D chroma into the interior of the padded planes
+            ctx.fence(api.UPLOAD, api.COMPUTE2)                                 # the chain reads the planes by address (motion estimation is
+            ctx.select_compute(api.COMPUTE2)                                    # ordered behind the luma upload by the library); chroma padding
+            pad_chroma(n)                                                       # on the queue that reads chroma
+            ctx.select_compute(api.COMPUTE)
         if "kernels" in skip:
-            r0 = n
+            r0 = r1 = n
         else:
-            _, r0 = kernels(i, False, slot)
-        chroma_used[n] = chroma_used[r0] = (ctx.marker(api.COMPUTE2), ctx.marker(api.COMPUTE), ctx.marker(api.COMPUTE3))   # every compute queue reads the chroma buffers
-        for m in chroma_used[n]:
-            ctx.stream_wait(api.DOWNLOAD, m)
-        rec, q, eob = d_rec[slot], d_q[slot], d_eob[slot]
+            _, r0, r1 = kernels(i, False, slot, pack_host="d2h" not in skip)
+        m2 = ctx.marker(api.COMPUTE2)                                           # the end of the picture's chain (which started behind its ME)
+        chroma_used[n] = chroma_used[r0] = chroma_used[r1] = (m2,)              # the second compute queue reads the chroma planes
+        ctx.stream_wait(api.DOWNLOAD, m2)
+        rec = d_rec[slot]
         d2h = lambda hb, db, nb: ("d2h" in skip) or ctx.check(L.svtb200_memcpy_d2h_async(h, hb.data_ptr(), db, nb), "d2h")
         d2h(h_me[slot], d_me[slot], N_SB * 85 * 40)                             # D2H ME results
-        for k in range(len(TU_PASSES)):                                         # D2H quantised coefficients + eob of every TU pass
-            d2h(h_q[slot][k], q[k], pass_cb[k])
-            d2h(h_eob[slot][k], eob[k], pass_n[k] * 2)
+        d2h(h_eob_all[slot], d_eob_all[slot], eob_off[-1])                      # D2H eob of every TU (the coefficients themselves were stored
+        d2h(h_rate_all[slot], d_rate_all[slot], rate_off[-1])                   # into h_stream / h_off by the pack kernel) and their rates
         if n == 16:                                                            # D2H filtered reference picture
             d2h(h_rec[slot][0], rec[0], W4K * H4K)
             d2h(h_rec[slot][1], rec[1], csize)
             d2h(h_rec[slot][2], rec[2], csize)
         downloaded[slot] = ctx.marker(api.DOWNLOAD)
+
+    def unpack_stream(stream, offsets, eobs):
+        """the host-side consumer of the packed stream: dense per-pass coefficient arrays (all TUs of the bench are DCT_DCT)"""
+        T, out, t = H.vp9_tables(), [], 0
+        for k, (_, ts, size, _, _, _) in enumerate(TU_PASSES):
+            scan = T["scan_%d_0" % ts].astype(np.int64)
+            q = np.zeros((pass_n[k], size * size), dtype=np.int16)
+            e = eobs[k].view(np.uint16).astype(np.int64)
+            o = offsets[t:t + pass_n[k]].astype(np.int64)
+            for j in np.flatnonzero(e):
+                q[j, scan[:e[j]]] = stream[o[j]:o[j] + e[j]]
+            out.append(q.reshape(-1).view(np.uint8))
+            t += pass_n[k]
+        return out
 
     def barrier():
         if world > 1:
@@ -712,22 +899,26 @@ def main():
     ms_res = e0.elapsed_time(e1)
     launches = ctx.launches() - launches0
     n_me = 0
+    chain_ms = [0.0]   # inter chain (partition + block walk + prediction + transform + packing + rate) inside the timed region
     for e, P, n in marks:
         stage_ms["me_sb_kernel"] += e[0].elapsed_time(e[1]); alg["me_sb_kernel"] += me_bytes(P); n_me += 1
-        stage_ms["txq_kernel"] += e[2].elapsed_time(e[3]); alg["txq_kernel"] += txq_bytes()
+        chain_ms[0] += e[2].elapsed_time(e[7]); alg["pred_kernel"] += pred_bytes(P); alg["txq_kernel"] += txq_bytes()
         if n == 16:
-            stage_ms["lf_row_kernel"] += e[3].elapsed_time(e[4]); alg["lf_row_kernel"] += lf_bytes()
+            stage_ms["lf_row_kernel"] += e[7].elapsed_time(e[4]); alg["lf_row_kernel"] += lf_bytes()
     # the same kernels one at a time (single queue): durations without the other queue's interference
-    iso_marks, iso_ms = [], {"me_sb_kernel": 0.0, "txq_kernel": 0.0, "lf_row_kernel": 0.0}
-    iso_n = {"me_sb_kernel": 0, "txq_kernel": 0, "lf_row_kernel": 0}
+    iso_marks, iso_ms = [], {k: 0.0 for k in KERNELS}
+    iso_n = {k: 0 for k in KERNELS}
     for i in range(16):
-        kernels(i, True, 0, overlap=False, sink=iso_marks)
+        kernels(i, True, 0, overlap=False, sink=iso_marks, detail=True)
     ctx.sync()
     for e, P, n in iso_marks:
         iso_ms["me_sb_kernel"] += e[0].elapsed_time(e[1]); iso_n["me_sb_kernel"] += 1
-        iso_ms["txq_kernel"] += e[2].elapsed_time(e[3]); iso_n["txq_kernel"] += 1
+        iso_ms["pred_kernel"] += e[2].elapsed_time(e[6]); iso_n["pred_kernel"] += 1
+        iso_ms["txq_kernel"] += e[6].elapsed_time(e[3]); iso_n["txq_kernel"] += 1
+        iso_ms["pack_kernel"] += e[3].elapsed_time(e[5]); iso_n["pack_kernel"] += 1
+        iso_ms["rate_kernel"] += e[5].elapsed_time(e[7]); iso_n["rate_kernel"] += 1
         if n == 16:
-            iso_ms["lf_row_kernel"] += e[3].elapsed_time(e[4]); iso_n["lf_row_kernel"] += 1
+            iso_ms["lf_row_kernel"] += e[7].elapsed_time(e[4]); iso_n["lf_row_kernel"] += 1
     for i in range(min(n_warm, 8)):
         step_e2e(i)
     ctx.sync()
@@ -744,20 +935,29 @@ def main():
     barrier()
     ms_e2e = (time.perf_counter() - t0) * 1000.0
     sampler.stop()
+    for slot in range(NSLOT):
+        if downloaded[slot]:
+            stream_coefs[0] += int(h_off_np[slot][n_tu]); stream_coefs[1] += 1
+    stream_bytes = 2.0 * stream_coefs[0] / max(1, stream_coefs[1])   # mean packed stream of a picture
+    alg["pack_kernel"] = int((2 * stream_bytes + n_tu * 6) * n_me)      # coefficients read + written once, eob in, offset out
+    alg["rate_kernel"] = int((stream_bytes + n_tu * 10) * n_me)         # coefficients up to eob read once; eob + descriptor in, rate out
 
     if args.verify:
         # the pipelined leg (4 queues, 3 slots) must have produced exactly what a synchronous single-queue run produces
         checked = 0
         for i in range(n_warm + n_timed - NSLOT, n_warm + n_timed):
             slot, n = i % NSLOT, ENCODE_ORDER[i % 16]
-            got = [h_me[slot].numpy().copy()] + [h_q[slot][k].numpy().copy() for k in range(len(TU_PASSES))]
+            ncoef = int(h_off_np[slot][n_tu])
+            got = [h_me[slot].numpy().copy(), h_off[slot].numpy().copy(), h_stream[slot].numpy()[:2 * ncoef].copy()]
             got += [h_eob[slot][k].numpy().copy() for k in range(len(TU_PASSES))]
+            got += [h_rate[slot][k].numpy().copy() for k in range(len(TU_PASSES))]
             if n == 16:
                 got += [h_rec[slot][k].numpy().copy() for k in range(3)]
             kernels(i, False, slot, overlap=False)
             ctx.sync()
-            devs = [(d_me[slot], N_SB * 85 * 40)] + [(d_q[slot][k], pass_cb[k]) for k in range(len(TU_PASSES))]
+            devs = [(d_me[slot], N_SB * 85 * 40), (d_off[slot], (n_tu + 1) * 4), (d_stream[slot], 2 * ncoef)]
             devs += [(d_eob[slot][k], pass_n[k] * 2) for k in range(len(TU_PASSES))]
+            devs += [(d_rate[slot][k], pass_n[k] * 4) for k in range(len(TU_PASSES))]
             if n == 16:
                 devs += [(d_rec[slot][0], W4K * H4K), (d_rec[slot][1], csize), (d_rec[slot][2], csize)]
             for g, (dptr, nbytes) in zip(got, devs):
@@ -775,7 +975,8 @@ def main():
     value = units / (ms_res / 1000.0)
     e2e = units / (ms_e2e / 1000.0)
     h2d = W4K * H4K + 2 * csize  # the picture area of the three planes (padding and the 1/16 plane are made on the device)
-    d2h = N_SB * 85 * 40 + sum(pass_cb) + 2 * sum(pass_n) + (W4K * H4K * 3 // 2) // 16  # filtered planes on 1 of 16 pictures
+    # ME results, the packed coefficient stream + its offsets (stored by the pack kernel), eob + rate, filtered planes on 1 of 16 pictures
+    d2h = N_SB * 85 * 40 + int(stream_bytes) + (n_tu + 1) * 4 + (2 + 4) * n_tu + (W4K * H4K * 3 // 2) // 16
 
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -793,16 +994,19 @@ def main():
     per_step_alone = {k: (iso_ms[k] / max(1, iso_n[k])) * (1.0 / 16 if k == "lf_row_kernel" else 1.0) for k in stage_ms}
     dom = max(per_step_alone, key=lambda k: per_step_alone[k])
     per_kernel = {}
+    timed_total = stage_ms["me_sb_kernel"] + chain_ms[0] + stage_ms["lf_row_kernel"]
     for k in stage_ms:
-        if stage_ms[k] > 0:
+        per_pic = alg[k] / (max(1, sum(1 for m in marks if m[2] == 16)) if k == "lf_row_kernel" else n_me)
+        iso = iso_ms[k] / max(1, iso_n[k])
+        row = {"traffic": traffic.get(k), "ms_per_picture_alone": iso, "achieved_gbs_alone": per_pic / (iso / 1000.0) / 1e9 if iso else None,
+               "frac_alone": per_pic / (iso / 1000.0) / 1e9 / peak if iso else None, "share_alone": per_step_alone[k] / sum(per_step_alone.values())}
+        if stage_ms[k] > 0:   # the kernels with events of their own inside the timed region (the chain's stages are one call there)
             a = alg[k] / (stage_ms[k] / 1000.0) / 1e9
-            per_pic = alg[k] / {"me_sb_kernel": n_me, "txq_kernel": n_me, "lf_row_kernel": max(1, sum(1 for m in marks if m[2] == 16))}[k]
-            iso = iso_ms[k] / max(1, iso_n[k])
-            per_kernel[k] = {"ms_total": stage_ms[k], "share": stage_ms[k] / sum(stage_ms.values()), "achieved_gbs": a, "frac": a / peak,
-                             "traffic": traffic.get(k), "ms_per_picture_alone": iso, "achieved_gbs_alone": per_pic / (iso / 1000.0) / 1e9 if iso else None,
-                             "frac_alone": per_pic / (iso / 1000.0) / 1e9 / peak if iso else None,
-                             "share_alone": per_step_alone[k] / sum(per_step_alone.values())}
-    launches_dom = n_me if dom in ("me_sb_kernel", "txq_kernel") else max(1, n_timed // 16)
+            row.update({"ms_total": stage_ms[k], "share": stage_ms[k] / timed_total, "achieved_gbs": a, "frac": a / peak})
+        per_kernel[k] = row
+    per_kernel["inter_chain"] = {"ms_total": chain_ms[0], "share": chain_ms[0] / timed_total,
+                                 "stages": "open-loop partition + block walk + pred_kernel + txq_kernel + pack_kernel + rate_kernel (svtb200_inter_chain_dev), overlapped with the next picture's motion estimation"}
+    launches_dom = n_me if dom != "lf_row_kernel" else max(1, n_timed // 16)
     roof = {"bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"],
             "traffic": traffic.get(dom), "kernel": dom, "alg_bytes_per_launch": alg[dom] / launches_dom,
             "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 (B200_PROFILING.md)", "per_kernel": per_kernel}
@@ -819,11 +1023,12 @@ def main():
             step_e2e(i)
             ctx.sync()
             slot, n = i % NSLOT, ENCODE_ORDER[i % 16]
-            got.append((n, h_me[slot].numpy().copy(), [h_q[slot][k].numpy().copy() for k in range(len(TU_PASSES))],
-                        [h_eob[slot][k].numpy().copy() for k in range(len(TU_PASSES))], [h_rec[slot][k].numpy().copy() for k in range(3)] if n == 16 else None))
+            eobs = [h_eob[slot][k].numpy().copy() for k in range(len(TU_PASSES))]
+            got.append((n, h_me[slot].numpy().copy(), unpack_stream(h_stream[slot].numpy().view(np.int16), h_off_np[slot], eobs), eobs,
+                        [h_rec[slot][k].numpy().copy() for k in range(3)] if n == 16 else None, [h_rate[slot][k].numpy().copy() for k in range(len(TU_PASSES))]))
         cpu.run([g[0] for g in got])
         bad, compared = [], 0
-        for b, (n, me, q, eob, rec) in enumerate(got):
+        for b, (n, me, q, eob, rec, rate) in enumerate(got):
             ok = H.me_equal(me.view(api.ME_RESULT_DTYPE), cpu.me_out[b], 2)
             compared += me.nbytes
             if not ok.all():
@@ -834,6 +1039,9 @@ def main():
                     bad.append("picture %d: quantised coefficients of TU pass %d differ" % (n, k))
                 if not np.array_equal(eob[k].view(np.uint16), cpu.eob[b][k]):
                     bad.append("picture %d: eob of TU pass %d differ" % (n, k))
+                compared += rate[k].nbytes
+                if not np.array_equal(rate[k].view(np.int32), cpu.rate[b][k]):
+                    bad.append("picture %d: rates of TU pass %d differ" % (n, k))
             if rec is not None:
                 for k in range(3):
                     compared += rec[k].nbytes
@@ -844,14 +1052,14 @@ def main():
             sys.stderr.write("check: MISMATCH " + "; ".join(bad[:8]) + "\n")
         if world == 1:
             cpu.minigop()          # page-fault / cache warm-up, untimed
-            cpu.stage_cpu_s = [0.0, 0.0, 0.0]
+            cpu.stage_cpu_s = [0.0, 0.0, 0.0, 0.0]
             t0, reps = time.perf_counter(), 0
             while reps < 3 or (time.perf_counter() - t0 < 10.0 and reps < 64):
                 cpu.minigop()
                 reps += 1
             dt = time.perf_counter() - t0
             cpu_line = {"value": reps * PICS_PER_STEP / dt, "unit": "fps", "cores": ncores, "kind": cpu.kind, "stage_share_of_cpu_time": cpu.stage_share(),
-                        "sample": "%d whole 4K mini-GOPs (16 pictures each: ME + transform/quant/recon, deblocking of the base-layer picture), one native "
+                        "sample": "%d whole 4K mini-GOPs (16 pictures each: ME + inter prediction + transform/quant/recon + rate, deblocking of the base-layer picture), one native "
                                   "call per mini-GOP on %d pinned host threads, %.1f s" % (reps, ncores, dt)}
         cpu.close()
         del cpu

@@ -92,6 +92,10 @@ int   svtb200_memcpy_d2h(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, s
 /* kernels of the following *_dev / host-pointer calls go to compute queue 'which' (COMPUTE, COMPUTE2 or COMPUTE3); not thread safe */
 int svtb200_select_compute(SvtB200Ctx *ctx, int which);
 int svtb200_memcpy_h2d_async(SvtB200Ctx *ctx, void *dst_dev, const void *src_host, size_t bytes);
+/* rows x width_bytes out of a pitched host array into a pitched device array (a chroma plane into the picture area of its padded
+ * device plane; svtb200_pad_plane_dev then makes the padding), on the UPLOAD queue */
+int svtb200_memcpy_h2d_2d_async(SvtB200Ctx *ctx, void *dst_dev, size_t dst_pitch, const void *src_host, size_t src_pitch, size_t width_bytes,
+                                size_t rows);
 int svtb200_memcpy_d2h_async(SvtB200Ctx *ctx, void *dst_host, const void *src_dev, size_t bytes);
 int svtb200_marker(SvtB200Ctx *ctx, int stream, uint64_t *ticket);
 int svtb200_stream_wait(SvtB200Ctx *ctx, int stream, uint64_t ticket);
@@ -327,6 +331,16 @@ typedef struct SvtB200TxBatch {
 int svtb200_txq_multi_dev(SvtB200Ctx *ctx, const SvtB200TxBatch *batches, int n_batches,
                           const SvtB200QuantRow *qrows_dev, int n_qrows);
 
+/* The quantised coefficients of the batches' blocks as the entropy coder consumes them (tokenize_b, Source/Lib/VPX/vp9_tokenize.c:275:
+ * qcoeff[scan[c]] for c < eob): for every block -- batch after batch, in job order -- its first eob coefficients in scan order, padded
+ * with a zero to an even count, back to back in stream[]; offsets[t] = first coefficient of block t, offsets[n_total] = length of the
+ * stream in coefficients (when it exceeds `capacity` the blocks that did not fit are missing).  Only jobs / qcoeff / eob / tx_size / n of
+ * the batches are read.  stream (4-byte aligned) and offsets (n_total + 1 entries) may be device memory or page-locked host memory
+ * (svtb200_host_alloc / svtb200_host_register: mapped into the device's address space): with host memory the kernel's stores are the
+ * device-to-host transfer -- a 4K picture's dense coefficients are 24.9 MB, the prefixes a few MB. */
+int svtb200_coeff_pack_dev(SvtB200Ctx *ctx, const SvtB200TxBatch *batches, int n_batches, int16_t *stream, uint32_t capacity,
+                           uint32_t *offsets);
+
 /* ---- coefficient rate estimation ---------------------------------------------------------------------
  * coeff_rate_estimate() (Source/Lib/Codec/EbRateDistortionCost.c:55; the libvpx cost_coeffs, Source/Lib/VPX/vp9_rdopt.c:334) with
  * use_fast_coef_costing == 0, as perform_dist_rate_calc calls it after every transform (Source/Lib/Codec/EbEncDecProcess.c:736):
@@ -349,6 +363,16 @@ int svtb200_coeff_rate_batch(SvtB200Ctx *ctx, int tx_size, int n, const int16_t 
                              const SvtB200RateBlock *blocks, const uint32_t *token_costs, int32_t *rate);
 int svtb200_coeff_rate_batch_dev(SvtB200Ctx *ctx, int tx_size, int n, const int16_t *qcoeff_dev, const uint16_t *eob_dev,
                                  const SvtB200RateBlock *blocks_dev, const uint32_t *token_costs_dev, int32_t *rate_dev);
+/* several batches (different transform sizes / planes of one picture) in ONE launch, up to 8; HOST array of device pointers */
+typedef struct SvtB200RateBatch {
+    int32_t                 tx_size, n;
+    const int16_t          *qcoeff;
+    const uint16_t         *eob;
+    const SvtB200RateBlock *blocks;
+    const uint32_t         *token_costs; /* of this transform size */
+    int32_t                *rate;
+} SvtB200RateBatch;
+int svtb200_coeff_rate_multi_dev(SvtB200Ctx *ctx, const SvtB200RateBatch *batches, int n_batches);
 
 /* =============================================================================================
  * S2  Deblocking loop filter
@@ -440,6 +464,65 @@ typedef struct SvtB200PredBlock {
 int svtb200_inter_predict_batch(SvtB200Ctx *ctx, const SvtB200PredBlock *blocks, int n);
 /* the same with the descriptors already on the device (unchecked) */
 int svtb200_inter_predict_batch_dev(SvtB200Ctx *ctx, const SvtB200PredBlock *blocks_dev, int n);
+
+/* The block walk of the encode pass's inter prediction on the device: what inter_prediction() / build_inter_predictors() read of a
+ * block (Source/Lib/Codec/EbIntraPrediction.c:49-73, Source/Lib/VPX/vp9_reconinter.c:102-250) -> the three inter_predictor() calls
+ * (one per plane, 4:2:0) as SvtB200PredBlock descriptors for svtb200_inter_predict_batch_dev:
+ *   - the motion vector of each reference scaled to 1/16 sample of the plane and clamped so that the block reaches at most
+ *     VP9_INTERP_EXTEND + block size samples out of the picture (eb_vp9_clamp_mv_to_umv_border_sb, vp9_reconinter.c:68-87, with
+ *     mb_to_*_edge as the encode pass sets them, EbEncDecProcess.c:2052-2066);
+ *   - use_subpel_flag == 0: the vector rounded to whole luma samples (vp9_reconinter.c:168-180);
+ *   - reference plane of the vector's list, chroma origin (block_origin & ~7) >> 1 (ROUND_UV, vp9_reconinter.c:146-160).
+ * Blocks of 8x8 luma samples and larger (sb_type >= BLOCK_8X8: one vector per reference for the whole block). */
+typedef struct SvtB200InterBlock {
+    uint16_t x, y;       /* block_origin_x / y: luma position of the block in the picture */
+    uint8_t  bw, bh;     /* luma size: 8, 16, 32 or 64 each */
+    uint8_t  list[2];    /* reference list (0 / 1) of mv[0] and mv[1]; list[1] == 0xff: one reference only */
+    int16_t  mv[2][2];   /* ModeInfo::mv[ref].as_mv {row, col}: 1/8 luma sample */
+} SvtB200InterBlock;
+typedef struct SvtB200PredPicture {
+    int32_t        width, height;      /* luma size of the picture (mi_cols / mi_rows = size rounded up to 8, as vp9_set_mi_size) */
+    const uint8_t *ref[2][3];          /* [list][plane]: DEVICE pointer to sample (0,0) inside the padding */
+    int32_t        ref_stride[2][3];
+    uint8_t       *dst[3];             /* prediction planes (position (0,0)) */
+    int32_t        dst_stride[3];
+    int32_t        use_subpel_flag;
+} SvtB200PredPicture;
+/* blocks_dev: n blocks; out_dev: 3 * n descriptors (block i: out[3 * i + plane]); pic: HOST struct holding device pointers. */
+int svtb200_inter_blocks_expand_dev(SvtB200Ctx *ctx, const SvtB200InterBlock *blocks_dev, int n, const SvtB200PredPicture *pic,
+                                    SvtB200PredBlock *out_dev);
+/* Open-loop stand-in for mode decision (bench and tests; in the encoder ModeInfo comes from the host's mode decision): the picture
+ * tiled with 32x32 blocks (16x16 where only 16 rows / columns remain; width and height multiples of 16), every block inter coded
+ * with the best candidate motion estimation found for that partition (cand[0].direction: list 0, list 1 or both; vectors
+ * me << 1 like EbModeDecision.c:222-227).  me_dev: svtb200_me_picture_dev's output.  Blocks are numbered: the 32x32 blocks in
+ * raster order, then the 16x16 blocks of the bottom strip, then those of the right strip; returns their number (or < 0). */
+int svtb200_me_best_blocks_dev(SvtB200Ctx *ctx, const SvtB200MeCuResult *me_dev, int32_t width, int32_t height, SvtB200InterBlock *blocks_dev);
+
+/* The inter chain of one picture in ONE call (one lock, seven launches on the current compute queue, no host round trip between the
+ * stages): [open-loop partition from the motion-estimation results ->] block walk -> inter prediction of the three planes ->
+ * fused transform batches (prediction = the planes just written) -> [scan-order packing of the coefficients] -> [rate of every block].
+ * The same work as the single entry points in this order: svtb200_me_best_blocks_dev, svtb200_inter_blocks_expand_dev,
+ * svtb200_inter_predict_batch_dev, svtb200_txq_multi_dev, svtb200_coeff_pack_dev, svtb200_coeff_rate_multi_dev. */
+typedef struct SvtB200InterChain {
+    int32_t                  after_queue;   /* SVTB200_STREAM_*: start behind everything queued there so far (the picture's motion estimation); -1: none */
+    const SvtB200MeCuResult *me;            /* non-NULL: blocks := svtb200_me_best_blocks_dev(me) (n_blocks must be the tiling's count) */
+    SvtB200InterBlock       *blocks;        /* DEVICE, n_blocks */
+    int32_t                  n_blocks;
+    SvtB200PredPicture       pic;
+    SvtB200PredBlock        *desc;          /* DEVICE scratch: 3 * n_blocks descriptors */
+    const SvtB200TxBatch    *tx;            /* HOST array of n_tx batches (device pointers inside) */
+    int32_t                  n_tx;
+    const SvtB200QuantRow   *qrows;         /* DEVICE */
+    int32_t                  n_qrows;
+    int16_t                 *stream;        /* NULL: no packing */
+    uint32_t                 capacity;
+    uint32_t                *offsets;
+    const SvtB200RateBatch  *rate;          /* HOST array of n_rate batches; n_rate 0: no rate */
+    int32_t                  n_rate;
+    uint64_t                 reads[3];      /* picture ids (svtb200_picture_upload*) whose planes the chain reads: svtb200_picture_touch */
+    int32_t                  n_reads;
+} SvtB200InterChain;
+int svtb200_inter_chain_dev(SvtB200Ctx *ctx, const SvtB200InterChain *chain);
 
 /* One intra prediction call of the encode pass: pred[mode][tx_size](dst, stride, above, left), or for DC_PRED
  * dc_pred[have_left][have_top][tx_size] (build_intra_predictors, Source/Lib/VPX/vp9_reconintra.c:397-407; the predictors:

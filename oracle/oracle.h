@@ -44,6 +44,10 @@ void svtb200_oracle_coeff_rate(int tx_size, int n, const int16_t *qcoeff, const 
                                const uint32_t *token_costs, const int16_t *const scans[4], const int16_t *const neighbors[4],
                                const int16_t *vtok, const int32_t *vcost, const int16_t *c6lo, const uint16_t *c6hi, int32_t *rate);
 
+/* block walk in front of the inter predictors, open-loop partition of the bench: blocks_port.c */
+void svtb200_oracle_inter_expand(const SvtB200InterBlock *blocks, int n, const SvtB200PredPicture *pic, SvtB200PredBlock *out);
+int  svtb200_oracle_me_best_blocks(const SvtB200MeCuResult *me, int width, int height, SvtB200InterBlock *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -432,6 +432,82 @@ int refdrv_coeff_rate(int tx_size, int n, const int16_t *qcoeff, const uint16_t 
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------ block walk of the encode pass
+ * The reference's own inter_prediction() (EbIntraPrediction.c:49) -> build_inter_predictors() (vp9_reconinter.c:102) for blocks
+ * [begin, end) and all three planes, on an EncDecContext / MACROBLOCKD filled the way the encode pass fills them
+ * (EbEncDecProcess.c:2052-2066, :5431, :5507).  pic holds HOST pointers. */
+#include "EbIntraPrediction.h"
+#include "EbUtility.h"
+#include "vp9_common_data.h"
+void inter_prediction(struct EncDecContext *context_ptr, EbByte pred_buffer, uint16_t pred_stride, int plane);
+
+typedef struct {
+    EncDecContext       ctx;
+    MACROBLOCKD         xd;
+    ModeInfo            mi, *mip;
+    EpBlockStats        bs;
+    struct scale_factors sf;
+    EbPictureBufferDesc ref[2];
+} RefPredCtx;
+
+void *refdrv_pred_new(void) {
+    RefPredCtx *c = (RefPredCtx *)calloc(1, sizeof(RefPredCtx));
+    c->ctx.e_mbd = &c->xd;
+    c->mip = &c->mi;
+    c->xd.mi = &c->mip;
+    c->ctx.ep_block_stats_ptr = &c->bs;
+    c->ctx.sf = &c->sf;
+    c->ctx.ref_pic_list[0] = &c->ref[0];
+    c->ctx.ref_pic_list[1] = &c->ref[1];
+    c->xd.plane[1].subsampling_x = c->xd.plane[1].subsampling_y = 1;
+    c->xd.plane[2].subsampling_x = c->xd.plane[2].subsampling_y = 1;
+    return c;
+}
+void refdrv_pred_free(void *h) { free(h); }
+
+static BLOCK_SIZE refdrv_bsize(int bw, int bh) {
+    for (int b = BLOCK_8X8; b < BLOCK_SIZES; b++)
+        if (4 * eb_vp9_num_4x4_blocks_wide_lookup[b] == bw && 4 * eb_vp9_num_4x4_blocks_high_lookup[b] == bh) return (BLOCK_SIZE)b;
+    return BLOCK_INVALID;
+}
+
+int refdrv_inter_prediction(void *h, const SvtB200InterBlock *blocks, int begin, int end, const SvtB200PredPicture *pic) {
+    RefPredCtx *c = (RefPredCtx *)h;
+    if (!g_init || !c) return -1;
+    const int mi_cols = (pic->width + 7) >> 3, mi_rows = (pic->height + 7) >> 3;
+    eb_vp9_setup_scale_factors_for_frame(&c->sf, pic->width, pic->height, pic->width, pic->height);
+    for (int l = 0; l < 2; l++) {
+        c->ref[l].buffer_y = (EbByte)pic->ref[l][0]; c->ref[l].buffer_cb = (EbByte)pic->ref[l][1]; c->ref[l].buffer_cr = (EbByte)pic->ref[l][2];
+        c->ref[l].stride_y = (uint16_t)pic->ref_stride[l][0]; c->ref[l].stride_cb = (uint16_t)pic->ref_stride[l][1]; c->ref[l].stride_cr = (uint16_t)pic->ref_stride[l][2];
+        c->ref[l].origin_x = c->ref[l].origin_y = 0; /* the pointers already stand at sample (0,0) */
+    }
+    c->ctx.use_subpel_flag = (uint8_t)pic->use_subpel_flag;
+    for (int i = begin; i < end; i++) {
+        const SvtB200InterBlock *b = &blocks[i];
+        const BLOCK_SIZE bsize = refdrv_bsize(b->bw, b->bh);
+        if (bsize == BLOCK_INVALID) return -2;
+        const int mi_col = b->x >> 3, mi_row = b->y >> 3;
+        c->bs.bsize = bsize;
+        c->bs.bsize_uv = eb_vp9_ss_size_lookup[bsize][1][1];
+        c->ctx.block_origin_x = b->x; c->ctx.block_origin_y = b->y;
+        c->xd.mb_to_top_edge = -((mi_row * MI_SIZE) * 8);
+        c->xd.mb_to_bottom_edge = ((mi_rows - eb_vp9_num_8x8_blocks_high_lookup[bsize] - mi_row) * MI_SIZE) * 8;
+        c->xd.mb_to_left_edge = -((mi_col * MI_SIZE) * 8);
+        c->xd.mb_to_right_edge = ((mi_cols - eb_vp9_num_8x8_blocks_wide_lookup[bsize] - mi_col) * MI_SIZE) * 8;
+        memset(&c->mi, 0, sizeof(c->mi));
+        c->mi.sb_type = bsize;
+        c->mi.mode = NEWMV;
+        c->mi.ref_frame[0] = b->list[0] ? ALTREF_FRAME : LAST_FRAME;
+        c->mi.ref_frame[1] = b->list[1] == 0xff ? NONE : (b->list[1] ? ALTREF_FRAME : LAST_FRAME);
+        for (int r = 0; r < 2; r++) { c->mi.mv[r].as_mv.row = b->mv[r][0]; c->mi.mv[r].as_mv.col = b->mv[r][1]; }
+        for (int plane = 0; plane < 3; plane++) {
+            const int ox = plane ? ROUND_UV(b->x) >> 1 : b->x, oy = plane ? ROUND_UV(b->y) >> 1 : b->y;
+            inter_prediction(&c->ctx, pic->dst[plane] + (ptrdiff_t)oy * pic->dst_stride[plane] + ox, (uint16_t)pic->dst_stride[plane], plane);
+        }
+    }
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------ CPU arm of bench.py
  * A native thread pool that runs the hot path of a whole mini-GOP with the reference's own functions: the unit of work is
  * a small range of super-blocks (motion estimation) or transform blocks (perform_coding_loop chain); one picture's
@@ -449,6 +525,8 @@ typedef struct {
     SvtB200TxPlanes      pl;
     int16_t             *coeff, *qcoeff, *dqcoeff;
     uint16_t            *eob;
+    const SvtB200RateBlock *rblk;  /* with rate: coeff_rate_estimate of every block after its transform chain */
+    int32_t             *rate;
 } RefdrvTuPass;
 
 typedef struct {
@@ -465,9 +543,14 @@ typedef struct {
     const SvtB200LfMask   *lfm;
     int32_t                lfm_stride;
     const SvtB200LfThresh *thr;
+    /* n_blocks > 0: inter prediction of the open-loop partition (32x32 blocks, 16x16 in the last strip; best motion-estimation
+     * candidate each) into pred before the transform passes, which then take their prediction from there */
+    int32_t                n_blocks;
+    SvtB200PredPicture     pred;            /* HOST pointers */
+    const uint32_t        *token_costs_all; /* [tx_size 4][...]: MACROBLOCK::token_costs, for the rate of the transform passes */
 } RefdrvPicture;
 
-typedef struct { int32_t kind, pic, pass, begin, end; } PoolTask; /* kind 0 ME, 1 TU, 2 LF */
+typedef struct { int32_t kind, pic, pass, begin, end; } PoolTask; /* kind 0 ME, 1 TU, 2 LF, 3 inter prediction */
 
 typedef struct RefPool {
     int                  n_threads, stop;
@@ -483,24 +566,78 @@ typedef struct RefPool {
     int                  n_tasks, cap_tasks;
     int                  next;     /* atomic */
     int                 *tu_left;  /* per picture: transform tasks not yet finished (atomic) */
-    double               cpu_s[3]; /* per kind, summed over threads */
+    int                 *me_left, *pred_left; /* per picture: motion-estimation / prediction tasks not yet finished */
+    void               **pred;     /* one RefPredCtx per worker */
+    void               **rate;     /* one RefRateCtx per worker */
+    double               cpu_s[4]; /* per kind, summed over threads */
 } RefPool;
 
 typedef struct { RefPool *p; int idx; } PoolArg;
 
+typedef struct { EncDecContext ctx; MACROBLOCK x; MACROBLOCKD xd; ModeInfo mi, *mip; const uint32_t *loaded; } RefRateCtx;
+static void *rate_ctx_new(void) {
+    RefRateCtx *r = (RefRateCtx *)calloc(1, sizeof(RefRateCtx));
+    r->ctx.e_mbd = &r->xd; r->mip = &r->mi; r->xd.mi = &r->mip;
+    r->mi.sb_type = BLOCK_32X32; r->mi.ref_frame[0] = LAST_FRAME; r->mi.ref_frame[1] = NONE; r->mi.mode = NEWMV;
+    return r;
+}
+/* coeff_rate_estimate over blocks [begin, end) of a transform pass (inter blocks: DCT_DCT scan) */
+static void rate_range(RefRateCtx *r, const RefdrvTuPass *s, const uint32_t *token_costs_all, int begin, int end) {
+    const int nn = (4 << s->tx_size) * (4 << s->tx_size);
+    if (r->loaded != token_costs_all) { memcpy(r->x.token_costs, token_costs_all, sizeof(r->x.token_costs)); r->loaded = token_costs_all; }
+    for (int b = begin; b < end; b++) {
+        r->mi.ref_frame[0] = s->rblk[b].is_inter ? LAST_FRAME : INTRA_FRAME;
+        s->rate[b] = coeff_rate_estimate(&r->ctx, &r->x, s->qcoeff + (size_t)b * nn, s->eob[b], s->rblk[b].plane_type ? 1 : 0, 0, (TX_SIZE)s->tx_size,
+                                         s->rblk[b].coeff_ctx, 0);
+    }
+}
+/* block i of the open-loop partition (the bench's stand-in for mode decision; the same rule as svtb200_me_best_blocks_dev) */
+static SvtB200InterBlock open_loop_block(const SvtB200MeCuResult *me, int width, int height, int i) {
+    const int w32 = width / 32, h32 = height / 32, w16 = width / 16, n32 = w32 * h32, nbot = (height / 16 - 2 * h32) * w16;
+    int x, y, size = 16;
+    if (i < n32) { y = (i / w32) * 32; x = (i % w32) * 32; size = 32; }
+    else if (i < n32 + nbot) { y = (2 * h32 + (i - n32) / w16) * 16; x = ((i - n32) % w16) * 16; }
+    else { const int j = i - n32 - nbot, wr = w16 - 2 * w32; y = (j / wr) * 16; x = (2 * w32 + j % wr) * 16; }
+    const SvtB200MeCuResult *sb = me + (size_t)((y / 64) * ((width + 63) / 64) + x / 64) * 85;
+    const SvtB200MeCuResult *r = size == 32 ? &sb[1 + ((y % 64) / 32) * 2 + (x % 64) / 32] : &sb[5 + ((y % 64) / 16) * 4 + (x % 64) / 16];
+    const unsigned d = r->cand[0].direction;
+    SvtB200InterBlock b;
+    b.x = (uint16_t)x; b.y = (uint16_t)y; b.bw = b.bh = (uint8_t)size;
+    b.list[0] = d == 1; b.list[1] = d == 2 ? 1 : 0xff;
+    b.mv[0][0] = (int16_t)((d == 1 ? r->y_mv_l1 : r->y_mv_l0) << 1); b.mv[0][1] = (int16_t)((d == 1 ? r->x_mv_l1 : r->x_mv_l0) << 1);
+    b.mv[1][0] = (int16_t)(d == 2 ? r->y_mv_l1 << 1 : 0); b.mv[1][1] = (int16_t)(d == 2 ? r->x_mv_l1 << 1 : 0);
+    return b;
+}
+
 static double pool_now(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
-static void pool_do(RefPool *p, int w, const PoolTask *t, double acc[3]) {
+static void pool_do(RefPool *p, int w, const PoolTask *t, double acc[4]) {
     const RefdrvPicture *pic = &p->pics[t->pic];
-    const double t0 = pool_now();
+    double t0 = pool_now();
     if (t->kind == 0) {
         refdrv_me_range(p->me[w], &pic->P, pic->cur, pic->ref0, pic->ref1, t->begin, t->end, pic->me_out);
+        __atomic_sub_fetch(&p->me_left[t->pic], 1, __ATOMIC_ACQ_REL);
+    } else if (t->kind == 3) {
+        /* the tasks this one depends on were queued earlier, i.e. are already claimed by some thread: the wait is short */
+        while (__atomic_load_n(&p->me_left[t->pic], __ATOMIC_ACQUIRE) > 0) sched_yield();
+        t0 = pool_now();
+        SvtB200InterBlock blk[64];
+        for (int i = t->begin; i < t->end; i += 64) {
+            const int n = t->end - i < 64 ? t->end - i : 64;
+            for (int k = 0; k < n; k++) blk[k] = open_loop_block(pic->me_out, pic->pred.width, pic->pred.height, i + k);
+            refdrv_inter_prediction(p->pred[w], blk, 0, n, &pic->pred);
+        }
+        __atomic_sub_fetch(&p->pred_left[t->pic], 1, __ATOMIC_ACQ_REL);
     } else if (t->kind == 1) {
         const RefdrvTuPass *s = &pic->pass[t->pass];
+        while (__atomic_load_n(&p->pred_left[t->pic], __ATOMIC_ACQUIRE) > 0) sched_yield();
+        t0 = pool_now();
         refdrv_txq(s->tx_size, t->begin, t->end, s->jobs, &s->pl, pic->qrows, s->coeff, s->qcoeff, s->dqcoeff, s->eob);
+        if (s->rate && pic->token_costs_all) rate_range((RefRateCtx *)p->rate[w], s, pic->token_costs_all, t->begin, t->end);
         __atomic_sub_fetch(&p->tu_left[t->pic], 1, __ATOMIC_ACQ_REL);
     } else {
-        while (__atomic_load_n(&p->tu_left[t->pic], __ATOMIC_ACQUIRE) > 0) sched_yield(); /* earlier tasks: already claimed by someone */
+        while (__atomic_load_n(&p->tu_left[t->pic], __ATOMIC_ACQUIRE) > 0) sched_yield();
+        t0 = pool_now();
         refdrv_deblock(&pic->lf, pic->y, pic->ys, pic->u, pic->v, pic->cs, pic->lfm, pic->lfm_stride, pic->thr);
     }
     acc[t->kind] += pool_now() - t0;
@@ -518,14 +655,14 @@ static void *pool_worker(void *a) {
         if (p->stop) { pthread_mutex_unlock(&p->mu); return NULL; }
         seen = p->generation;
         pthread_mutex_unlock(&p->mu);
-        double acc[3] = {0, 0, 0};
+        double acc[4] = {0, 0, 0, 0};
         for (;;) {
             const int i = __atomic_fetch_add(&p->next, 1, __ATOMIC_RELAXED);
             if (i >= p->n_tasks) break;
             pool_do(p, w, &p->tasks[i], acc);
         }
         pthread_mutex_lock(&p->mu);
-        for (int k = 0; k < 3; k++) p->cpu_s[k] += acc[k];
+        for (int k = 0; k < 4; k++) p->cpu_s[k] += acc[k];
         if (--p->running == 0) pthread_cond_signal(&p->cv_done);
         pthread_mutex_unlock(&p->mu);
     }
@@ -537,7 +674,9 @@ void *refdrv_pool_new(int threads, int pin) {
     p->n_threads = threads;
     p->th = (pthread_t *)calloc((size_t)threads, sizeof(pthread_t));
     p->me = (void **)calloc((size_t)threads, sizeof(void *));
-    for (int i = 0; i < threads; i++) p->me[i] = refdrv_me_new(); /* the constructors share a global allocation map: single-threaded here */
+    p->pred = (void **)calloc((size_t)threads, sizeof(void *));
+    p->rate = (void **)calloc((size_t)threads, sizeof(void *));
+    for (int i = 0; i < threads; i++) { p->me[i] = refdrv_me_new(); p->pred[i] = refdrv_pred_new(); p->rate[i] = rate_ctx_new(); } /* the constructors share a global allocation map: single-threaded here */
     pthread_mutex_init(&p->mu, NULL);
     pthread_cond_init(&p->cv_go, NULL);
     pthread_cond_init(&p->cv_done, NULL);
@@ -568,29 +707,41 @@ static void pool_push(RefPool *p, int kind, int pic, int pass, int begin, int en
 }
 
 /* Runs the pictures (in the order given: encode order) and returns when all are done; stage_cpu_s = thread-seconds spent in
- * motion estimation / transform chain / deblocking.  me_chunk / tu_chunk = super-blocks / transform blocks per task. */
-int refdrv_pool_run(void *h, const RefdrvPicture *pics, int n_pics, int me_chunk, int tu_chunk, double stage_cpu_s[3]) {
+ * motion estimation / transform chain (+ rate) / deblocking / inter prediction.  me_chunk / tu_chunk = super-blocks / transform
+ * blocks per task.  Tasks are claimed in queue order; a picture's prediction, transform and deblocking tasks are queued behind the
+ * NEXT picture's motion estimation, so that the tasks they wait for have long been claimed when their turn comes. */
+static void pool_push_rest(RefPool *p, const RefdrvPicture *pic, int i, int tu_chunk) {
+    int n_pred = 0, n_tu = 0;
+    for (int s = 0; s < pic->n_blocks; s += 256, n_pred++) pool_push(p, 3, i, 0, s, s + 256 < pic->n_blocks ? s + 256 : pic->n_blocks);
+    p->pred_left[i] = n_pred;
+    for (int k = 0; k < pic->n_pass; k++)
+        for (int s = 0; s < pic->pass[k].n; s += tu_chunk, n_tu++) pool_push(p, 1, i, k, s, s + tu_chunk < pic->pass[k].n ? s + tu_chunk : pic->pass[k].n);
+    p->tu_left[i] = n_tu;
+    if (pic->deblock) pool_push(p, 2, i, 0, 0, 0);
+}
+int refdrv_pool_run(void *h, const RefdrvPicture *pics, int n_pics, int me_chunk, int tu_chunk, double stage_cpu_s[4]) {
     RefPool *p = (RefPool *)h;
     if (!p || n_pics < 1) return -1;
     p->pics = pics; p->n_pics = n_pics; p->n_tasks = 0;
     p->tu_left = (int *)realloc(p->tu_left, (size_t)n_pics * sizeof(int));
+    p->me_left = (int *)realloc(p->me_left, (size_t)n_pics * sizeof(int));
+    p->pred_left = (int *)realloc(p->pred_left, (size_t)n_pics * sizeof(int));
     for (int i = 0; i < n_pics; i++) {
         const RefdrvPicture *pic = &pics[i];
         const int n_sb = ((pic->P.luma_width + 63) / 64) * ((pic->P.luma_height + 63) / 64);
-        if (pic->me_out) for (int s = 0; s < n_sb; s += me_chunk) pool_push(p, 0, i, 0, s, s + me_chunk < n_sb ? s + me_chunk : n_sb);
-        int n_tu = 0;
-        for (int k = 0; k < pic->n_pass; k++)
-            for (int s = 0; s < pic->pass[k].n; s += tu_chunk, n_tu++) pool_push(p, 1, i, k, s, s + tu_chunk < pic->pass[k].n ? s + tu_chunk : pic->pass[k].n);
-        p->tu_left[i] = n_tu;
-        if (pic->deblock) pool_push(p, 2, i, 0, 0, 0);
+        int n_me = 0;
+        if (pic->me_out) for (int s = 0; s < n_sb; s += me_chunk, n_me++) pool_push(p, 0, i, 0, s, s + me_chunk < n_sb ? s + me_chunk : n_sb);
+        p->me_left[i] = n_me;
+        if (i > 0) pool_push_rest(p, &pics[i - 1], i - 1, tu_chunk);
     }
+    pool_push_rest(p, &pics[n_pics - 1], n_pics - 1, tu_chunk);
     pthread_mutex_lock(&p->mu);
     p->next = 0; p->running = p->n_threads;
-    for (int k = 0; k < 3; k++) p->cpu_s[k] = 0;
+    for (int k = 0; k < 4; k++) p->cpu_s[k] = 0;
     p->generation++;
     pthread_cond_broadcast(&p->cv_go);
     while (p->running) pthread_cond_wait(&p->cv_done, &p->mu);
-    if (stage_cpu_s) for (int k = 0; k < 3; k++) stage_cpu_s[k] = p->cpu_s[k];
+    if (stage_cpu_s) for (int k = 0; k < 4; k++) stage_cpu_s[k] = p->cpu_s[k];
     pthread_mutex_unlock(&p->mu);
     return 0;
 }
@@ -603,5 +754,6 @@ void refdrv_pool_free(void *h) {
     pthread_cond_broadcast(&p->cv_go);
     pthread_mutex_unlock(&p->mu);
     for (int i = 0; i < p->n_threads; i++) pthread_join(p->th[i], NULL);
-    free(p->tasks); free(p->tu_left); free(p->th); free(p->me); free(p);
+    for (int i = 0; i < p->n_threads; i++) { refdrv_pred_free(p->pred[i]); free(p->rate[i]); }
+    free(p->tasks); free(p->tu_left); free(p->me_left); free(p->pred_left); free(p->th); free(p->me); free(p->pred); free(p->rate); free(p);
 }

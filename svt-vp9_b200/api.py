@@ -90,6 +90,16 @@ class PredBlock(C.Structure):
                 ("compound", C.c_uint8), ("reserved", C.c_uint8)]
 
 
+INTER_BLOCK_DTYPE = np.dtype([("x", "<u2"), ("y", "<u2"), ("bw", "u1"), ("bh", "u1"), ("list", "u1", 2), ("mv", "<i2", (2, 2))])
+assert INTER_BLOCK_DTYPE.itemsize == 16
+
+
+class PredPicture(C.Structure):
+    """SvtB200PredPicture: reference planes of both lists, prediction planes (device pointers for the product, host for the oracle)."""
+    _fields_ = [("width", C.c_int32), ("height", C.c_int32), ("ref", (C.c_void_p * 3) * 2), ("ref_stride", (C.c_int32 * 3) * 2),
+                ("dst", C.c_void_p * 3), ("dst_stride", C.c_int32 * 3), ("use_subpel_flag", C.c_int32)]
+
+
 class IntraBlock(C.Structure):
     """SvtB200IntraBlock: one intra predictor call (device pointers for the product, host pointers for the oracle)."""
     _fields_ = [("above", C.c_void_p), ("left", C.c_void_p), ("dst", C.c_void_p), ("dst_stride", C.c_int32), ("mode", C.c_uint8), ("tx_size", C.c_uint8),
@@ -139,6 +149,8 @@ def lib():
         L.svtb200_picture_touch.argtypes = [C.c_void_p, C.c_uint64]
         L.svtb200_memcpy_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.svtb200_memcpy_d2h_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.svtb200_memcpy_h2d_2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_size_t, C.c_size_t]
+        L.svtb200_pad_plane_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32]
         L.svtb200_select_compute.argtypes = [C.c_void_p, C.c_int]
         L.svtb200_marker.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_uint64)]
         L.svtb200_stream_wait.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
@@ -154,6 +166,9 @@ def lib():
         L.svtb200_inter_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.svtb200_inter_predict_batch_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.svtb200_intra_predict_batch.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.svtb200_inter_blocks_expand_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PredPicture), C.c_void_p]
+        L.svtb200_me_best_blocks_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+        L.svtb200_inter_chain_dev.argtypes = [C.c_void_p, C.c_void_p]
         L.svtb200_full_distortion_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
         _lib = L
     return _lib
@@ -288,6 +303,7 @@ def _bind_txq(L):
     L.svtb200_txq_batch.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(TxPlanes), vp, C.c_int, vp, vp, vp, vp]
     L.svtb200_txq_batch_dev.argtypes = [vp, C.c_int, C.c_int, vp, C.POINTER(TxPlanes), vp, C.c_int, vp, vp, vp, vp]
     L.svtb200_txq_multi_dev.argtypes = [vp, C.POINTER(TxBatch), C.c_int, vp, C.c_int]
+    L.svtb200_coeff_pack_dev.argtypes = [vp, C.POINTER(TxBatch), C.c_int, vp, C.c_uint32, vp]
     L._txq_bound = True
 
 
@@ -350,9 +366,10 @@ def _ctx_txq(self, tx_size, jobs, src, pred, recon, rows, want_coeff=True):
     return coeff, q, dq, eob, rec
 
 
-def _ctx_txq_multi(self, batches, rows):
+def _ctx_txq_multi(self, batches, rows, pack=None):
     """batches: list of (tx_size, jobs, src, pred, recon) with 2-D uint8 planes (each batch its own planes); ONE launch through
-    svtb200_txq_multi_dev.  Returns a list of (q, dq, eob, recon) per batch."""
+    svtb200_txq_multi_dev.  Returns a list of (q, dq, eob, recon) per batch.  pack: a dict that receives "stream" / "offsets" of
+    svtb200_coeff_pack_dev over the same batches ("host": True -> written by the kernel into page-locked host memory)."""
     _bind_txq(self.L)
     L, h = self.L, self.h
     rows = np.ascontiguousarray(rows)
@@ -377,6 +394,26 @@ def _ctx_txq_multi(self, batches, rows):
             b.coeff, b.qcoeff, b.dqcoeff, b.eob = None, up(q), up(dq), up(eob)
             outs.append((q, dq, eob, recon.copy(), b))
         self.check(L.svtb200_txq_multi_dev(h, arr, len(batches), d_rows, len(rows)), "txq_multi_dev")
+        if pack is not None:
+            n_total = sum(len(b[1]) for b in batches)
+            cap = pack.get("capacity", sum(len(b[1]) * (4 << b[0]) ** 2 for b in batches))
+            stream, offsets = np.zeros(max(cap, 2), np.int16), np.zeros(n_total + 1, np.uint32)
+            if pack.get("host"):
+                hs, ho = L.svtb200_host_alloc(stream.nbytes), L.svtb200_host_alloc(offsets.nbytes)
+                C.memset(hs, 0, stream.nbytes)
+                self.check(L.svtb200_coeff_pack_dev(h, arr, len(batches), hs, cap, ho), "coeff_pack_dev")
+                self.sync()
+                C.memmove(stream.ctypes.data, hs, stream.nbytes)
+                C.memmove(offsets.ctypes.data, ho, offsets.nbytes)
+                L.svtb200_host_free(hs)
+                L.svtb200_host_free(ho)
+            else:
+                ds, do = up(stream), up(offsets)
+                self.check(L.svtb200_coeff_pack_dev(h, arr, len(batches), ds, cap, do), "coeff_pack_dev")
+                self.sync()
+                self.check(L.svtb200_memcpy_d2h(h, stream.ctypes.data, ds, stream.nbytes), "d2h")
+                self.check(L.svtb200_memcpy_d2h(h, offsets.ctypes.data, do, offsets.nbytes), "d2h")
+            pack["stream"], pack["offsets"] = stream, offsets
         self.sync()
         res = []
         for q, dq, eob, rec, b in outs:
@@ -461,6 +498,19 @@ def _ctx_intra_predict(self, blocks):
     self.check(self.L.svtb200_intra_predict_batch(self.h, C.addressof(blocks), len(blocks)), "intra_predict_batch")
 
 
+class RateBatch(C.Structure):
+    """SvtB200RateBatch (device pointers)"""
+    _fields_ = [("tx_size", C.c_int32), ("n", C.c_int32), ("qcoeff", C.c_void_p), ("eob", C.c_void_p), ("blocks", C.c_void_p),
+                ("token_costs", C.c_void_p), ("rate", C.c_void_p)]
+
+
+class InterChain(C.Structure):
+    """SvtB200InterChain: the inter chain of one picture for svtb200_inter_chain_dev"""
+    _fields_ = [("after_queue", C.c_int32), ("me", C.c_void_p), ("blocks", C.c_void_p), ("n_blocks", C.c_int32), ("pic", PredPicture), ("desc", C.c_void_p),
+                ("tx", C.POINTER(TxBatch)), ("n_tx", C.c_int32), ("qrows", C.c_void_p), ("n_qrows", C.c_int32), ("stream", C.c_void_p), ("capacity", C.c_uint32),
+                ("offsets", C.c_void_p), ("rate", C.POINTER(RateBatch)), ("n_rate", C.c_int32), ("reads", C.c_uint64 * 3), ("n_reads", C.c_int32)]
+
+
 RATE_BLOCK_DTYPE = np.dtype([("plane_type", "u1"), ("is_inter", "u1"), ("tx_type", "u1"), ("coeff_ctx", "u1")])
 
 
@@ -472,6 +522,7 @@ def _bind_rate(L):
     L.svtb200_set_rate_tables.argtypes = [vp, vp, vp, vp, vp]
     L.svtb200_coeff_rate_batch.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
     L.svtb200_coeff_rate_batch_dev.argtypes = [vp, C.c_int, C.c_int, vp, vp, vp, vp, vp]
+    L.svtb200_coeff_rate_multi_dev.argtypes = [vp, C.POINTER(RateBatch), C.c_int]
     L._rate_bound = True
 
 

@@ -52,6 +52,7 @@ void svtb200_destroy(SvtB200Ctx *c) {
     if (c->pin) cudaFreeHost(c->pin);
     for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { if (c->scans[a][b].scan) cudaFree(c->scans[a][b].scan); if (c->scans[a][b].iscan) cudaFree(c->scans[a][b].iscan); if (c->scan_nb[a][b]) cudaFree(c->scan_nb[a][b]); }
     if (c->rate_tables) cudaFree(c->rate_tables);
+    if (c->chain_ev) cudaEventDestroy(c->chain_ev);
     cudaStreamDestroy(c->compute[0]); cudaStreamDestroy(c->compute[1]); cudaStreamDestroy(c->compute[2]); cudaStreamDestroy(c->up); cudaStreamDestroy(c->down);
     delete c;
 }
@@ -81,6 +82,12 @@ int svtb200_memcpy_h2d_async(SvtB200Ctx *c, void *d, const void *h, size_t n) {
     if (!c) return SVTB200_EINVAL;
     cudaSetDevice(c->device);
     SVTB200_CUDA_CHECK(c, cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, c->up));
+    return SVTB200_OK;
+}
+int svtb200_memcpy_h2d_2d_async(SvtB200Ctx *c, void *d, size_t d_pitch, const void *h, size_t h_pitch, size_t width_bytes, size_t rows) {
+    if (!c || !d || !h || width_bytes > d_pitch || width_bytes > h_pitch) return SVTB200_EINVAL;
+    cudaSetDevice(c->device);
+    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(d, d_pitch, h, h_pitch, width_bytes, rows, cudaMemcpyHostToDevice, c->up));
     return SVTB200_OK;
 }
 int svtb200_memcpy_d2h_async(SvtB200Ctx *c, void *h, const void *d, size_t n) {

@@ -53,50 +53,86 @@ __device__ __forceinline__ int rate_band(int c, int tx_size) { /* the band of sc
     return c < 21 ? 4 : 5;
 }
 
+/* one block by one warp; qs: the warp's staging buffer (N * N coefficients) */
+template <int N>
+__device__ __forceinline__ void rate_block(const RateArgs &A, int b, int16_t *qs, int lane) {
+    constexpr int NN = N * N;
+    const int eob = A.eob[b];
+    const SvtB200RateBlock B = A.blk[b];
+    const uint32_t *tc = A.tc + (size_t)((B.plane_type ? 1 : 0) * 2 + (B.is_inter ? 1 : 0)) * (6 * 2 * 6 * RATE_TOKENS);
+    int cost = 0;
+    if (eob == 0) {
+        if (lane == 0) A.rate[b] = (int)tc[(0 * 2 + 0) * 6 * RATE_TOKENS + B.coeff_ctx * RATE_TOKENS + RATE_EOB_TOKEN];
+        return;
+    }
+    const int tt = N == 32 ? 0 : (B.tx_type & 3);
+    const int16_t *scan = A.scan[tt], *nb = A.nb[tt];
+    /* long runs: stage the block (vector loads; every term gathers four coefficients); short runs, the common case after motion
+     * compensation, gather the few coefficients they touch straight from global memory */
+    const int16_t *q = A.qcoeff + (size_t)b * NN;
+    const bool staged = NN <= 64 || eob > 48;
+    if (staged) {
+        if (NN >= 256) { for (int i = lane; i < NN / 8; i += 32) ((uint4 *)qs)[i] = __ldg((const uint4 *)q + i); }
+        else { for (int i = lane; i < NN / 2; i += 32) ((uint32_t *)qs)[i] = __ldg((const uint32_t *)q + i); }
+        __syncwarp();
+    }
+    const int16_t *src = staged ? qs : q;
+    for (int c = lane; c < eob; c += 32) {
+        int vc;
+        const int tok = rate_token(A, src[__ldg(scan + c)], &vc);
+        int ctx, skip;
+        if (c == 0) { ctx = B.coeff_ctx; skip = 0; }
+        else {
+            int dummy;
+            const int e0 = rate_energy(rate_token(A, src[__ldg(nb + 2 * c)], &dummy));
+            const int e1 = rate_energy(rate_token(A, src[__ldg(nb + 2 * c + 1)], &dummy));
+            ctx = (1 + e0 + e1) >> 1;
+            skip = src[__ldg(scan + c - 1)] == 0; /* previous token ZERO_TOKEN <=> previous value 0 */
+        }
+        cost += vc + (int)__ldg(tc + ((rate_band(c, A.tx_size) * 2 + skip) * 6 + ctx) * RATE_TOKENS + tok);
+    }
+    if (lane == 0 && eob < NN) { /* the end-of-block token, unless the last position of the block was coded */
+        int dummy;
+        const int e0 = rate_energy(rate_token(A, src[__ldg(nb + 2 * eob)], &dummy));
+        const int e1 = rate_energy(rate_token(A, src[__ldg(nb + 2 * eob + 1)], &dummy));
+        cost += (int)__ldg(tc + ((rate_band(eob, A.tx_size) * 2 + 0) * 6 + ((1 + e0 + e1) >> 1)) * RATE_TOKENS + RATE_EOB_TOKEN);
+    }
+    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+    if (lane == 0) A.rate[b] = cost;
+    __syncwarp();
+}
+
 template <int N>
 __global__ void __launch_bounds__(RATE_THREADS) rate_kernel(const __grid_constant__ RateArgs A) {
-    constexpr int NN = N * N, WARPS = RATE_THREADS / 32;
-    __shared__ __align__(16) int16_t qs[WARPS][NN];
+    constexpr int WARPS = RATE_THREADS / 32;
+    __shared__ __align__(16) int16_t qs[WARPS][N * N];
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int b = blockIdx.x * WARPS + warp; b < A.n; b += gridDim.x * WARPS) {
-        const int eob = A.eob[b];
-        const SvtB200RateBlock B = A.blk[b];
-        const uint32_t *tc = A.tc + (size_t)((B.plane_type ? 1 : 0) * 2 + (B.is_inter ? 1 : 0)) * (6 * 2 * 6 * RATE_TOKENS);
-        int cost = 0;
-        if (eob == 0) {
-            if (lane == 0) A.rate[b] = (int)tc[(0 * 2 + 0) * 6 * RATE_TOKENS + B.coeff_ctx * RATE_TOKENS + RATE_EOB_TOKEN];
-            continue;
+    for (int b = blockIdx.x * WARPS + warp; b < A.n; b += gridDim.x * WARPS) rate_block<N>(A, b, qs[warp], lane);
+}
+
+/* several batches in one launch: the blocks of all batches form one index space, a warp takes every (grid warps)-th */
+#define RATE_MAX_BATCHES 8
+struct RateMultiArgs {
+    RateArgs b[RATE_MAX_BATCHES];
+    int32_t  end[RATE_MAX_BATCHES]; /* running block count */
+    int32_t  nb;
+};
+__global__ void __launch_bounds__(RATE_THREADS) rate_multi_kernel(const __grid_constant__ RateMultiArgs M) {
+    constexpr int WARPS = RATE_THREADS / 32;
+    __shared__ __align__(16) int16_t qs[WARPS][32 * 32];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, total = M.end[M.nb - 1];
+    for (int g = blockIdx.x * WARPS + warp; g < total; g += gridDim.x * WARPS) {
+        int k = 0;
+#pragma unroll
+        for (int i = 1; i < RATE_MAX_BATCHES; i++) if (i < M.nb && g >= M.end[i - 1]) k = i;
+        const RateArgs &A = M.b[k];
+        const int b = g - (k ? M.end[k - 1] : 0);
+        switch (A.tx_size) { /* warp-uniform */
+        case 0: rate_block<4>(A, b, qs[warp], lane); break;
+        case 1: rate_block<8>(A, b, qs[warp], lane); break;
+        case 2: rate_block<16>(A, b, qs[warp], lane); break;
+        default: rate_block<32>(A, b, qs[warp], lane); break;
         }
-        const int tt = N == 32 ? 0 : (B.tx_type & 3);
-        const int16_t *scan = A.scan[tt], *nb = A.nb[tt];
-        /* stage the block (vector loads; the positions past eob in scan order are never read, but staging all is cheaper than gathering) */
-        const int16_t *q = A.qcoeff + (size_t)b * NN;
-        if (NN >= 256) { for (int i = lane; i < NN / 8; i += 32) ((uint4 *)qs[warp])[i] = __ldg((const uint4 *)q + i); }
-        else { for (int i = lane; i < NN / 2; i += 32) ((uint32_t *)qs[warp])[i] = __ldg((const uint32_t *)q + i); }
-        __syncwarp();
-        for (int c = lane; c < eob; c += 32) {
-            int vc;
-            const int tok = rate_token(A, qs[warp][__ldg(scan + c)], &vc);
-            int ctx, skip;
-            if (c == 0) { ctx = B.coeff_ctx; skip = 0; }
-            else {
-                int dummy;
-                const int e0 = rate_energy(rate_token(A, qs[warp][__ldg(nb + 2 * c)], &dummy));
-                const int e1 = rate_energy(rate_token(A, qs[warp][__ldg(nb + 2 * c + 1)], &dummy));
-                ctx = (1 + e0 + e1) >> 1;
-                skip = qs[warp][__ldg(scan + c - 1)] == 0; /* previous token ZERO_TOKEN <=> previous value 0 */
-            }
-            cost += vc + (int)__ldg(tc + ((rate_band(c, A.tx_size) * 2 + skip) * 6 + ctx) * RATE_TOKENS + tok);
-        }
-        if (lane == 0 && eob < NN) { /* the end-of-block token, unless the last position of the block was coded */
-            int dummy;
-            const int e0 = rate_energy(rate_token(A, qs[warp][__ldg(nb + 2 * eob)], &dummy));
-            const int e1 = rate_energy(rate_token(A, qs[warp][__ldg(nb + 2 * eob + 1)], &dummy));
-            cost += (int)__ldg(tc + ((rate_band(eob, A.tx_size) * 2 + 0) * 6 + ((1 + e0 + e1) >> 1)) * RATE_TOKENS + RATE_EOB_TOKEN);
-        }
-        for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
-        if (lane == 0) A.rate[b] = cost;
-        __syncwarp();
     }
 }
 
@@ -130,14 +166,9 @@ int svtb200_set_rate_tables(SvtB200Ctx *c, const int16_t value_token[133], const
     return SVTB200_OK;
 }
 
-int svtb200_coeff_rate_batch_dev(SvtB200Ctx *c, int tx_size, int n, const int16_t *qcoeff, const uint16_t *eob, const SvtB200RateBlock *blocks,
-                                 const uint32_t *token_costs, int32_t *rate) {
-    if (!c || tx_size < 0 || tx_size > 3 || n < 0 || (n && (!qcoeff || !eob || !blocks || !token_costs || !rate))) return SVTB200_EINVAL;
-    if (!n) return SVTB200_OK;
-    std::lock_guard<std::recursive_mutex> g(c->mu);
-    cudaSetDevice(c->device);
+static int rate_fill(SvtB200Ctx *c, RateArgs &A, int tx_size, int n, const int16_t *qcoeff, const uint16_t *eob, const SvtB200RateBlock *blocks,
+                     const uint32_t *token_costs, int32_t *rate) {
     if (!c->rate_tables) { c->err = "rate tables not registered (svtb200_set_rate_tables)"; return SVTB200_EINVAL; }
-    RateArgs A;
     memset(&A, 0, sizeof(A));
     for (int t = 0; t < 4; t++) {
         const int tt = tx_size == 3 ? 0 : t;
@@ -147,6 +178,45 @@ int svtb200_coeff_rate_batch_dev(SvtB200Ctx *c, int tx_size, int n, const int16_
     A.qcoeff = qcoeff; A.eob = eob; A.blk = blocks; A.tc = token_costs; A.rate = rate; A.n = n; A.tx_size = tx_size;
     A.vcost = (const int32_t *)c->rate_tables; A.vtok = (const int16_t *)(c->rate_tables + 133 * 4);
     A.c6lo = (const int16_t *)(c->rate_tables + 133 * 4 + 134 * 2); A.c6hi = (const uint16_t *)(c->rate_tables + 133 * 4 + 134 * 2 + 256 * 2);
+    return SVTB200_OK;
+}
+
+int svtb200_coeff_rate_multi_dev(SvtB200Ctx *c, const SvtB200RateBatch *batches, int n_batches) {
+    if (!c || !batches || n_batches < 1 || n_batches > RATE_MAX_BATCHES) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    RateMultiArgs M;
+    memset(&M, 0, sizeof(M));
+    int total = 0;
+    for (int k = 0; k < n_batches; k++) {
+        const SvtB200RateBatch &b = batches[k];
+        if (b.tx_size < 0 || b.tx_size > 3 || b.n < 0 || (b.n && (!b.qcoeff || !b.eob || !b.blocks || !b.token_costs || !b.rate))) return SVTB200_EINVAL;
+        if (!b.n) continue;
+        const int rc = rate_fill(c, M.b[M.nb], b.tx_size, b.n, b.qcoeff, b.eob, b.blocks, b.token_costs, b.rate);
+        if (rc) return rc;
+        total += b.n;
+        M.end[M.nb++] = total;
+    }
+    if (!total) return SVTB200_OK;
+    const int warps = RATE_THREADS / 32;
+    int grid = (total + warps - 1) / warps;
+    const int cap = (c->sm_count > 0 ? c->sm_count : 148) * 8;
+    if (grid > cap) grid = cap;
+    rate_multi_kernel<<<grid, RATE_THREADS, 0, c->stream>>>(M);
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
+int svtb200_coeff_rate_batch_dev(SvtB200Ctx *c, int tx_size, int n, const int16_t *qcoeff, const uint16_t *eob, const SvtB200RateBlock *blocks,
+                                 const uint32_t *token_costs, int32_t *rate) {
+    if (!c || tx_size < 0 || tx_size > 3 || n < 0 || (n && (!qcoeff || !eob || !blocks || !token_costs || !rate))) return SVTB200_EINVAL;
+    if (!n) return SVTB200_OK;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    RateArgs A;
+    const int frc = rate_fill(c, A, tx_size, n, qcoeff, eob, blocks, token_costs, rate);
+    if (frc) return frc;
     const int warps = RATE_THREADS / 32;
     int grid = (n + warps - 1) / warps;
     const int cap = (c->sm_count > 0 ? c->sm_count : 148) * 16;

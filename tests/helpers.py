@@ -426,7 +426,7 @@ _refdrv = None
 class RefdrvTuPass(C.Structure):
     """oracle/ref_path_driver.c: one transform pass of a picture (job table + planes + result arrays)"""
     _fields_ = [("tx_size", C.c_int32), ("n", C.c_int32), ("jobs", C.c_void_p), ("pl", api.TxPlanes), ("coeff", C.c_void_p), ("qcoeff", C.c_void_p),
-                ("dqcoeff", C.c_void_p), ("eob", C.c_void_p)]
+                ("dqcoeff", C.c_void_p), ("eob", C.c_void_p), ("rblk", C.c_void_p), ("rate", C.c_void_p)]
 
 
 class RefdrvPicture(C.Structure):
@@ -434,7 +434,7 @@ class RefdrvPicture(C.Structure):
     _fields_ = [("P", api.MeParams), ("cur", C.POINTER(api.Plane)), ("ref0", C.POINTER(api.Plane)), ("ref1", C.POINTER(api.Plane)), ("me_out", C.c_void_p),
                 ("n_pass", C.c_int32), ("passes", RefdrvTuPass * 8), ("qrows", C.c_void_p), ("deblock", C.c_int32), ("lf", api.LfParams),
                 ("y", C.c_void_p), ("u", C.c_void_p), ("v", C.c_void_p), ("ys", C.c_int32), ("cs", C.c_int32), ("lfm", C.c_void_p), ("lfm_stride", C.c_int32),
-                ("thr", C.c_void_p)]
+                ("thr", C.c_void_p), ("n_blocks", C.c_int32), ("pred", api.PredPicture), ("token_costs_all", C.c_void_p)]
 
 
 def have_refdrv():

@@ -192,3 +192,46 @@ def test_cuda_rate_of_txq_output():
             assert (got == _oracle_rate(ts, q2, e2, blk, T["token_costs_default"])).all()
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_rate_multi_launch():
+    """svtb200_coeff_rate_multi_dev: batches of all four sizes in ONE launch == the batches one by one (and the oracle)"""
+    rng = np.random.default_rng(31)
+    T = H.vp9_tables()
+    ctx = api.Context(0)
+    ctx.register_scans(T)
+    ctx.register_rate_tables(T)
+    L, h = ctx.L, ctx.h
+    api._bind_rate(L)
+    dev = []
+
+    def up(a):
+        a = np.ascontiguousarray(a)
+        d = L.svtb200_dev_alloc(h, max(a.nbytes, 16))
+        ctx.check(L.svtb200_memcpy_h2d(h, d, a.ctypes.data, a.nbytes), "h2d")
+        dev.append(d)
+        return d
+    try:
+        tc = _token_costs(rng, "random")
+        arr = (api.RateBatch * 6)()
+        want, outs = [], []
+        for k, (ts, kind, n) in enumerate(((3, "typical", 700), (2, "sparse", 900), (1, "typical", 1500), (0, "typical", 2000), (2, "dc", 300), (3, "large", 100))):
+            q, eob, blk = _blocks(rng, ts, n, kind)
+            want.append(_oracle_rate(ts, q, eob, blk, tc))
+            b = arr[k]
+            b.tx_size, b.n, b.qcoeff, b.eob, b.blocks, b.token_costs = ts, n, up(q), up(eob), up(blk), up(tc[ts])
+            b.rate = up(np.zeros(n, np.int32))
+            outs.append((b.rate, n))
+        l0 = ctx.launches()
+        ctx.check(L.svtb200_coeff_rate_multi_dev(h, arr, 6), "rate_multi")
+        assert ctx.launches() - l0 == 1
+        ctx.sync()
+        for (d, n), w in zip(outs, want):
+            got = np.zeros(n, np.int32)
+            ctx.check(L.svtb200_memcpy_d2h(h, got.ctypes.data, d, got.nbytes), "d2h")
+            assert (got == w).all()
+    finally:
+        for d in dev:
+            L.svtb200_dev_free(h, d)
+        ctx.close()

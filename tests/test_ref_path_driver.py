@@ -233,7 +233,7 @@ def test_thread_pool_of_the_cpu_arm_equals_direct_calls():
         want.append(H.refdrv_me_picture(P, st[cur], st[r0], st[r1], n_sb))
     pool = L.refdrv_pool_new(4, 1)
     assert pool
-    cpu_s = (C.c_double * 3)()
+    cpu_s = (C.c_double * 4)()
     assert L.refdrv_pool_run(pool, pics, 2, 2, 8, cpu_s) == 0
     L.refdrv_pool_free(pool)
     assert cpu_s[0] > 0 and cpu_s[1] > 0 and cpu_s[2] > 0

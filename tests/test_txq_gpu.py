@@ -172,3 +172,63 @@ def test_txq_multi_launch_equals_single_batches():
         _, q0, d0, e0, r0 = ctx.txq(ts, jobs, src, pred, rec, rows)
         assert (q == q0).all() and (dq == d0).all() and (eob == e0).all() and (r == r0).all(), ts
     ctx.close()
+
+
+def unpack_coeffs(batches, eobs, stream, offsets):
+    """host-side reader of svtb200_coeff_pack_dev's stream: dense (n, N, N) qcoeff arrays per batch."""
+    T = H.vp9_tables()
+    out, t = [], 0
+    for (ts, jobs, *_), eob in zip(batches, eobs):
+        N = 4 << ts
+        q = np.zeros((len(jobs), N * N), np.int16)
+        for j in range(len(jobs)):
+            e, o = int(eob[j]), int(offsets[t])
+            assert int(offsets[t + 1]) - o == (e + 1) & ~1
+            scan = T["scan_%d_%d" % (ts, 0 if ts == 3 else int(jobs["tx_type"][j]) & 3)]
+            q[j, scan[:e]] = stream[o:o + e]
+            if e & 1:
+                assert stream[o + e] == 0
+            t += 1
+        out.append(q.reshape(len(jobs), N, N))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("host", [False, True])
+def test_coeff_pack_roundtrip(host):
+    """svtb200_coeff_pack_dev: scan-order prefixes of every block's coefficients, into device memory and straight into
+    page-locked host memory; unpacked on the host they are the dense arrays (tokenize_b reads nothing else)."""
+    rng = np.random.default_rng(78)
+    rows = H.quant_rows([20, 200])
+    batches = []
+    for ts, (Hh, W) in zip((3, 2, 1, 0, 2, 3), ((160, 416), (80, 208), (40, 200), (36, 100), (16, 2000), (64, 64))):
+        N = 4 << ts
+        src = rng.integers(0, 256, size=(Hh, W), dtype=np.uint8)
+        spread = 3 if ts == 3 and Hh == 64 else 25   # the last batch: (almost) empty blocks
+        pred = np.clip(src.astype(int) + rng.integers(-spread, spread + 1, size=src.shape), 0, 255).astype(np.uint8)
+        by, bx = np.meshgrid(np.arange(0, Hh - N + 1, N), np.arange(0, W - N + 1, N), indexing="ij")
+        jobs = np.zeros(by.size, dtype=api.TX_JOB_DTYPE)
+        jobs["src_offset"] = jobs["pred_offset"] = jobs["recon_offset"] = by.ravel() * W + bx.ravel()
+        jobs["qrow"] = np.arange(by.size) % 2
+        jobs["tx_type"] = 0 if ts == 3 else np.arange(by.size) & 3
+        jobs["flags"] = 1
+        batches.append((ts, jobs, src, pred, np.zeros_like(src)))
+    ctx = api.Context(0)
+    ctx.register_scans(H.vp9_tables())
+    pack = {"host": host}
+    got = ctx.txq_multi(batches, rows, pack=pack)
+    eobs = [g[2] for g in got]
+    n_total = sum(len(b[1]) for b in batches)
+    assert int(pack["offsets"][n_total]) == sum(int(((e.astype(np.int64) + 1) & ~1).sum()) for e in eobs)
+    assert any((e == 0).any() for e in eobs) and any((e & 1).any() for e in eobs)
+    dense = unpack_coeffs(batches, eobs, pack["stream"], pack["offsets"])
+    for (q, dq, eob, r), d in zip(got, dense):
+        assert (q == d).all()
+    # a stream that is too small: the total still reports the need, the blocks that fit are intact
+    small = {"host": host, "capacity": int(pack["offsets"][n_total]) // 2}
+    ctx.txq_multi(batches, rows, pack=small)
+    assert int(small["offsets"][n_total]) == int(pack["offsets"][n_total])
+    fit = np.flatnonzero(small["offsets"][1:] <= small["capacity"])
+    k = int(fit[-1]) + 1
+    assert (small["stream"][:int(small["offsets"][k])] == pack["stream"][:int(small["offsets"][k])]).all()
+    ctx.close()
