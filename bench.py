@@ -622,6 +622,10 @@ def main():
     d_lfm, d_thr = to_dev(lf_masks_32x32()), to_dev(H.lf_thresholds())
     # result buffers exist NSLOT times: the end-to-end leg downloads slot s while the kernels of the next pictures fill the others
     NSLOT = 3
+    # eob and rate arrays of the six passes are carved from one allocation per slot: one download each
+    al = lambda v: (v + 255) & ~255
+    eob_off = [sum(al(m * 2) for m in pass_n[:k]) for k in range(len(pass_n) + 1)]
+    rate_off = [sum(al(m * 4) for m in pass_n[:k]) for k in range(len(pass_n) + 1)]
     d_rec = [[L.svtb200_dev_alloc(h, W4K * H4K), L.svtb200_dev_alloc(h, csize), L.svtb200_dev_alloc(h, csize)] for _ in range(NSLOT)]
     d_pred = [[L.svtb200_dev_alloc(h, W4K * H4K), L.svtb200_dev_alloc(h, csize), L.svtb200_dev_alloc(h, csize)] for _ in range(NSLOT)]
     d_blk = [L.svtb200_dev_alloc(h, N_BLK * 16) for _ in range(NSLOT)]
@@ -638,10 +642,6 @@ def main():
     d_me = [L.svtb200_dev_alloc(h, N_SB * 85 * 40) for _ in range(NSLOT)]
     d_q = [[L.svtb200_dev_alloc(h, b) for b in pass_cb] for _ in range(NSLOT)]
     d_dq = [L.svtb200_dev_alloc(h, b) for b in pass_cb]
-    # eob (and, below, rate) arrays of the six passes are carved from one allocation per slot: one download each
-    al = lambda v: (v + 255) & ~255
-    eob_off = [sum(al(m * 2) for m in pass_n[:k]) for k in range(len(pass_n) + 1)]
-    rate_off = [sum(al(m * 4) for m in pass_n[:k]) for k in range(len(pass_n) + 1)]
     d_eob_all = [L.svtb200_dev_alloc(h, eob_off[-1]) for _ in range(NSLOT)]
     d_eob = [[d_eob_all[s_] + eob_off[k] for k in range(len(pass_n))] for s_ in range(NSLOT)]
     LfP = api.LfParams()

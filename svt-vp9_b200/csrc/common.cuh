@@ -61,6 +61,7 @@ struct SvtB200Ctx {
     int16_t  *scan_nb[4][4] = {};  /* neighbour tables of the scans (rate estimation) */
     uint8_t  *rate_tables = nullptr; /* value -> token / cost tables (rate.cu) */
     cudaEvent_t chain_ev = nullptr;  /* svtb200_inter_chain_dev: "behind the other queue" */
+    uint32_t *pack_scratch[3] = {nullptr, nullptr, nullptr}; int pack_chunks[3] = {0, 0, 0}; /* pack.cu: ticket + chunk bases per compute queue */
     /* generic device scratch for the host-pointer entry points */
     uint8_t *scratch = nullptr; size_t scratch_bytes = 0;
     /* prediction descriptors of the batch in flight (pred.cu); pred_read: the kernel that reads them has finished */

@@ -53,6 +53,7 @@ void svtb200_destroy(SvtB200Ctx *c) {
     for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { if (c->scans[a][b].scan) cudaFree(c->scans[a][b].scan); if (c->scans[a][b].iscan) cudaFree(c->scans[a][b].iscan); if (c->scan_nb[a][b]) cudaFree(c->scan_nb[a][b]); }
     if (c->rate_tables) cudaFree(c->rate_tables);
     if (c->chain_ev) cudaEventDestroy(c->chain_ev);
+    for (int q = 0; q < 3; q++) if (c->pack_scratch[q]) cudaFree(c->pack_scratch[q]);
     cudaStreamDestroy(c->compute[0]); cudaStreamDestroy(c->compute[1]); cudaStreamDestroy(c->compute[2]); cudaStreamDestroy(c->up); cudaStreamDestroy(c->down);
     delete c;
 }

@@ -11,16 +11,17 @@
  *                     every block's run is padded to an even count with a zero, so runs start 4-byte aligned
  *   offsets[n_total]  total length in coefficients
  *   stream[]          int16 coefficients
- * Two launches: an exclusive scan of the (even-padded) eob values on one CTA, then one warp per block gathering
- * qcoeff[scan[c]] and storing 32-bit pairs (128 contiguous bytes per warp store).  stream / offsets may be device memory or
+ * Two launches over chunks of 64 consecutive blocks: the chunk totals of the (even-padded) eob values, turned into chunk bases by
+ * the last CTA to finish; then per chunk a CTA scan for the block offsets and one warp per block gathering qcoeff[scan[c]] and
+ * storing 32-bit pairs (128 contiguous bytes per warp store).  stream / offsets may be device memory or
  * page-locked host memory mapped into the device's address space: in the second case the kernel's stores ARE the device-to-host
  * transfer (no staging copy whose size the host would first have to learn).
  */
 #include "common.cuh"
 
 #define PACK_MAX_BATCHES 8
-#define PACK_SCAN_THREADS 1024
 #define PACK_THREADS 256
+#define PACK_CHUNK 64 /* blocks per CTA: 8 per warp, so that the dependent loads of a block (scan entry -> coefficient) overlap across many warps */
 
 struct PackBatch {
     const SvtB200TxJob *jobs;
@@ -37,52 +38,111 @@ struct PackArgs {
     uint32_t  capacity;
 };
 
-__device__ __forceinline__ uint32_t pack_len(const PackArgs &A, int t) { /* even-padded eob of block t */
+/* block t of the concatenated batches -> its batch */
+__device__ __forceinline__ int pack_batch_of(const PackArgs &A, int t) {
     int k = 0;
 #pragma unroll
     for (int i = 1; i < PACK_MAX_BATCHES; i++) if (i < A.nb && t >= A.b[i].first) k = i;
+    return k;
+}
+__device__ __forceinline__ uint32_t pack_len(const PackArgs &A, int t) { /* even-padded eob of block t */
+    const int k = pack_batch_of(A, t);
     return ((uint32_t)A.b[k].eob[t - A.b[k].first] + 1u) & ~1u;
 }
-
-__global__ void __launch_bounds__(PACK_SCAN_THREADS) pack_scan_kernel(const __grid_constant__ PackArgs A) {
-    __shared__ uint32_t wsum[PACK_SCAN_THREADS / 32];
-    const int t = threadIdx.x, per = (A.n_total + PACK_SCAN_THREADS - 1) / PACK_SCAN_THREADS;
-    const int t0 = min(t * per, A.n_total), t1 = min(t0 + per, A.n_total);
-    uint32_t s = 0;
-    for (int i = t0; i < t1; i++) s += pack_len(A, i);
-    uint32_t inc = s; /* inclusive scan over the CTA */
-    for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, inc, o); if ((t & 31) >= o) inc += v; }
+/* inclusive scan over the CTA's PACK_THREADS values; every thread gets its own inclusive value, *total the CTA's sum */
+__device__ __forceinline__ uint32_t pack_cta_scan(uint32_t v, uint32_t *wsum, uint32_t *total) {
+    const int t = threadIdx.x;
+    uint32_t inc = v;
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if ((t & 31) >= o) inc += x; }
+    __syncthreads(); /* wsum from the previous use */
     if ((t & 31) == 31) wsum[t >> 5] = inc;
     __syncthreads();
-    if (t < 32) {
-        uint32_t w = wsum[t], wi = w;
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t v = __shfl_up_sync(0xffffffffu, wi, o); if (t >= o) wi += v; }
-        wsum[t] = wi - w;
-    }
-    __syncthreads();
-    uint32_t run = wsum[t >> 5] + inc - s;
-    for (int i = t0; i < t1; i++) { A.offsets[i] = run; run += pack_len(A, i); }
-    if (t == PACK_SCAN_THREADS - 1) A.offsets[A.n_total] = run;
+    uint32_t base = 0, all = 0;
+#pragma unroll
+    for (int w = 0; w < PACK_THREADS / 32; w++) { const uint32_t x = wsum[w]; if (w < (t >> 5)) base += x; all += x; }
+    *total = all;
+    return base + inc;
 }
 
-__global__ void __launch_bounds__(PACK_THREADS) pack_kernel(const __grid_constant__ PackArgs A) {
-    const int lane = threadIdx.x & 31, wpb = PACK_THREADS / 32;
-    for (int t = blockIdx.x * wpb + (threadIdx.x >> 5); t < A.n_total; t += gridDim.x * wpb) {
-        int k = 0;
-#pragma unroll
-        for (int i = 1; i < PACK_MAX_BATCHES; i++) if (i < A.nb && t >= A.b[i].first) k = i;
-        const PackBatch &B = A.b[k];
-        const int j = t - B.first, eob = B.eob[j];
-        if (!eob) continue;
-        const uint32_t off = A.offsets[t];
-        if (off + ((eob + 1) & ~1) > A.capacity) continue; /* the caller sees offsets[n_total] > capacity */
-        const int16_t *q = B.qcoeff + (size_t)j * B.nn, *scan = B.scan[B.jobs[j].tx_type & 3];
-        uint32_t *out = (uint32_t *)(A.stream + off);
-        for (int c = 2 * lane; c < eob; c += 64) {
-            const uint32_t sc = __ldg((const uint32_t *)(scan + c)); /* two scan entries */
-            const uint32_t lo = (uint16_t)q[sc & 0xffff], hi = (c + 1 < eob) ? (uint16_t)q[sc >> 16] : 0u;
-            out[c >> 1] = lo | (hi << 16);
+/* pass 1: one CTA per PACK_CHUNK consecutive blocks: the chunk's total length; the LAST CTA to finish (ticket counter) turns the
+ * chunk totals into exclusive chunk bases and writes the stream length -- no second tiny launch, no serial walk over 24 000 blocks */
+__global__ void __launch_bounds__(PACK_THREADS) pack_sum_kernel(const __grid_constant__ PackArgs A, uint32_t *chunk_base, uint32_t *ticket) {
+    __shared__ uint32_t wsum[PACK_THREADS / 32];
+    __shared__ uint32_t last;
+    const int t = blockIdx.x * PACK_CHUNK + threadIdx.x;
+    const bool mine = threadIdx.x < PACK_CHUNK && t < A.n_total;
+    const uint32_t len = mine ? pack_len(A, t) : 0u;
+    uint32_t total;
+    const uint32_t inc = pack_cta_scan(len, wsum, &total);
+    if (mine) A.offsets[t] = inc - len; /* relative to the chunk base for now; pass 2 makes it absolute */
+    if (threadIdx.x == 0) {
+        chunk_base[blockIdx.x] = total;
+        __threadfence();
+        last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
+    __syncthreads();
+    if (!last) return;
+    __threadfence();
+    /* exclusive scan of the chunk totals, PACK_THREADS at a time */
+    uint32_t run = 0;
+    for (int c0 = 0; c0 < (int)gridDim.x; c0 += PACK_THREADS) {
+        const int c = c0 + threadIdx.x;
+        const uint32_t v = c < (int)gridDim.x ? ((volatile uint32_t *)chunk_base)[c] : 0u;
+        uint32_t tot;
+        const uint32_t inc = pack_cta_scan(v, wsum, &tot);
+        if (c < (int)gridDim.x) chunk_base[c] = run + inc - v;
+        run += tot;
+    }
+    if (threadIdx.x == 0) { A.offsets[A.n_total] = run; *ticket = 0; }
+}
+
+/* pass 2: the same chunks.  The first PACK_CHUNK threads fetch what is needed of their block (eob, coefficient and scan pointers)
+ * and scan the lengths on top of the chunk base; then the chunk's coefficient PAIRS are one index space walked by all threads:
+ * a thread finds the block of its pair by bisection in shared memory, gathers qcoeff[scan[c]], qcoeff[scan[c + 1]] and stores one
+ * word -- consecutive threads store consecutive words, no lane idles on a short block, and every pair is an independent chain
+ * of two loads */
+__global__ void __launch_bounds__(PACK_THREADS) pack_kernel(const __grid_constant__ PackArgs A, const uint32_t *chunk_base) {
+    __shared__ uint32_t wsum[PACK_THREADS / 32];
+    __shared__ uint32_t off_s[PACK_CHUNK + 1]; /* relative to the chunk base, in coefficients */
+    __shared__ const int16_t *q_s[PACK_CHUNK], *scan_s[PACK_CHUNK];
+    __shared__ uint16_t eob_s[PACK_CHUNK];
+    /* this CTA's blocks are t = blockIdx.x + k * gridDim.x (neighbouring blocks, which tend to be equally busy, go to different
+     * CTAs); out_s[k]: where block k's run starts in the stream, off_s[]: running pair count of the CTA's own blocks */
+    __shared__ uint32_t out_s[PACK_CHUNK];
+    const int tid = threadIdx.x;
+    {
+        const int t = (int)blockIdx.x + tid * (int)gridDim.x;
+        const bool mine = tid < PACK_CHUNK && t < A.n_total;
+        uint32_t len = 0;
+        if (mine) {
+            const PackBatch &B = A.b[pack_batch_of(A, t)];
+            const int j = t - B.first, eob = B.eob[j];
+            len = ((uint32_t)eob + 1u) & ~1u;
+            eob_s[tid] = (uint16_t)eob;
+            q_s[tid] = B.qcoeff + (size_t)j * B.nn;
+            scan_s[tid] = B.scan[B.jobs[j].tx_type & 3];
+            const uint32_t off = chunk_base[t / PACK_CHUNK] + A.offsets[t];
+            out_s[tid] = off;
+            A.offsets[t] = off;
         }
+        uint32_t total;
+        const uint32_t inc = pack_cta_scan(len, wsum, &total);
+        if (tid < PACK_CHUNK) off_s[tid] = inc - len;
+        if (tid == 0) off_s[PACK_CHUNK] = total;
+    }
+    __syncthreads();
+    const uint32_t pairs = off_s[PACK_CHUNK] >> 1;
+    for (uint32_t p = tid; p < pairs; p += PACK_THREADS) {
+        const uint32_t pos = 2 * p;
+        int i = 0; /* the block with off_s[i] <= pos < off_s[i + 1] (empty blocks have equal bounds and are never selected) */
+#pragma unroll
+        for (int step = PACK_CHUNK / 2; step > 0; step >>= 1) if (off_s[i + step] <= pos) i += step;
+        const uint32_t c = pos - off_s[i], eob = eob_s[i];
+        if (out_s[i] + ((eob + 1u) & ~1u) > A.capacity) continue; /* the caller sees offsets[n_total] > capacity */
+        const uint32_t sc = __ldg((const uint32_t *)(scan_s[i] + c)); /* two scan entries */
+        const int16_t *q = q_s[i];
+        const uint32_t lo = (uint16_t)q[sc & 0xffff], hi = (c + 1 < eob) ? (uint16_t)q[sc >> 16] : 0u;
+        ((uint32_t *)A.stream)[(out_s[i] + c) >> 1] = lo | (hi << 16);
     }
 }
 
@@ -107,13 +167,22 @@ extern "C" int svtb200_coeff_pack_dev(SvtB200Ctx *c, const SvtB200TxBatch *batch
         total += b.n;
     }
     A.n_total = total; A.offsets = offsets; A.stream = stream; A.capacity = capacity;
-    pack_scan_kernel<<<1, PACK_SCAN_THREADS, 0, c->stream>>>(A);
+    const int chunks = total ? (total + PACK_CHUNK - 1) / PACK_CHUNK : 1;
+    /* chunk bases + the ticket word: per compute queue (launches on different queues may be in flight together) */
+    const int qi = svtb200_compute_index(c);
+    if (c->pack_chunks[qi] < chunks) {
+        if (c->pack_scratch[qi]) cudaFree(c->pack_scratch[qi]);
+        c->pack_scratch[qi] = nullptr; c->pack_chunks[qi] = 0;
+        const int cap = chunks + chunks / 2 + 64;
+        if (cudaMalloc((void **)&c->pack_scratch[qi], (size_t)(cap + 1) * 4) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMalloc failed"; return SVTB200_ENOMEM; }
+        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(c->pack_scratch[qi], 0, (size_t)(cap + 1) * 4, c->stream));
+        c->pack_chunks[qi] = cap;
+    }
+    uint32_t *chunk_base = c->pack_scratch[qi] + 1, *ticket = c->pack_scratch[qi];
+    pack_sum_kernel<<<chunks, PACK_THREADS, 0, c->stream>>>(A, chunk_base, ticket);
     c->launches++;
     if (total) {
-        int grid = (total + PACK_THREADS / 32 - 1) / (PACK_THREADS / 32);
-        const int cap = (c->sm_count > 0 ? c->sm_count : 148) * 8;
-        if (grid > cap) grid = cap;
-        pack_kernel<<<grid, PACK_THREADS, 0, c->stream>>>(A);
+        pack_kernel<<<chunks, PACK_THREADS, 0, c->stream>>>(A, chunk_base);
         c->launches++;
     }
     SVTB200_CUDA_CHECK(c, cudaGetLastError());

@@ -11,13 +11,12 @@
  * position (vp9_get_token_cost, Source/Lib/VPX/vp9_tokenize.h:118; eb_vp9_pt_energy_class, vp9_entropy.c:111), the band only on
  * the scan index (band_counts, EbRateDistortionCost.c:48), the context only on the two earlier neighbours' energy classes
  * (get_coef_context, vp9_scan.h:34) and the "skip EOB node" flag only on the previous coefficient in scan order.  The cost of a
- * block is therefore a sum of independent per-position terms: one warp per block, lanes stride over the scan positions below
- * eob, the block's coefficients staged once in shared memory (every term gathers four of them), shuffle reduction at the end.
+ * block is therefore a sum of independent per-position terms, and the kernel is parallel over scan POSITIONS (rate_multi_kernel).
  * Integer arithmetic only: bit-exact by construction.
  */
 #include "common.cuh"
 
-#define RATE_THREADS 128
+#define RATE_THREADS 256
 #define RATE_TOKENS 12
 #define RATE_EOB_TOKEN 11
 #define RATE_CAT6_TOKEN 10
@@ -37,14 +36,24 @@ struct RateArgs {
     int32_t                  n, tx_size;
 };
 
-__device__ __forceinline__ int rate_token(const RateArgs &A, int v, int *cost) {
+/* the value -> token / cost tables of the small values, copied into shared memory once per CTA (every term looks three values up) */
+struct RateTables { int32_t vcost[133]; int16_t vtok[134]; };
+__device__ __forceinline__ void rate_load_tables(const RateArgs &A, RateTables &T) {
+    for (int i = threadIdx.x; i < 133; i += blockDim.x) { T.vcost[i] = __ldg(A.vcost + i); T.vtok[i] = __ldg(A.vtok + i); }
+    __syncthreads();
+}
+__device__ __forceinline__ int rate_token(const RateArgs &A, const RateTables &T, int v, int *cost) {
     if (v >= RATE_CAT6_MIN || v <= -RATE_CAT6_MIN) {
         const int e = (v < 0 ? -v : v) - RATE_CAT6_MIN;
         *cost = (int)__ldg(A.c6lo + (e & 0xff)) + (int)__ldg(A.c6hi + (e >> 8));
         return RATE_CAT6_TOKEN;
     }
-    *cost = __ldg(A.vcost + v + 66);
-    return __ldg(A.vtok + v + 66);
+    *cost = T.vcost[v + 66];
+    return T.vtok[v + 66];
+}
+/* token only (the neighbours' energy classes) */
+__device__ __forceinline__ int rate_token_only(const RateTables &T, int v) {
+    return (v >= RATE_CAT6_MIN || v <= -RATE_CAT6_MIN) ? RATE_CAT6_TOKEN : T.vtok[v + 66];
 }
 __device__ __forceinline__ int rate_energy(int tok) { return tok < 3 ? tok : tok < 5 ? 3 : tok < 7 ? 4 : 5; } /* eb_vp9_pt_energy_class */
 __device__ __forceinline__ int rate_band(int c, int tx_size) { /* the band of scan position c (band_counts) */
@@ -53,85 +62,125 @@ __device__ __forceinline__ int rate_band(int c, int tx_size) { /* the band of sc
     return c < 21 ? 4 : 5;
 }
 
-/* one block by one warp; qs: the warp's staging buffer (N * N coefficients) */
-template <int N>
-__device__ __forceinline__ void rate_block(const RateArgs &A, int b, int16_t *qs, int lane) {
-    constexpr int NN = N * N;
-    const int eob = A.eob[b];
-    const SvtB200RateBlock B = A.blk[b];
-    const uint32_t *tc = A.tc + (size_t)((B.plane_type ? 1 : 0) * 2 + (B.is_inter ? 1 : 0)) * (6 * 2 * 6 * RATE_TOKENS);
-    int cost = 0;
-    if (eob == 0) {
-        if (lane == 0) A.rate[b] = (int)tc[(0 * 2 + 0) * 6 * RATE_TOKENS + B.coeff_ctx * RATE_TOKENS + RATE_EOB_TOKEN];
-        return;
-    }
-    const int tt = N == 32 ? 0 : (B.tx_type & 3);
-    const int16_t *scan = A.scan[tt], *nb = A.nb[tt];
-    /* long runs: stage the block (vector loads; every term gathers four coefficients); short runs, the common case after motion
-     * compensation, gather the few coefficients they touch straight from global memory */
-    const int16_t *q = A.qcoeff + (size_t)b * NN;
-    const bool staged = NN <= 64 || eob > 48;
-    if (staged) {
-        if (NN >= 256) { for (int i = lane; i < NN / 8; i += 32) ((uint4 *)qs)[i] = __ldg((const uint4 *)q + i); }
-        else { for (int i = lane; i < NN / 2; i += 32) ((uint32_t *)qs)[i] = __ldg((const uint32_t *)q + i); }
-        __syncwarp();
-    }
-    const int16_t *src = staged ? qs : q;
-    for (int c = lane; c < eob; c += 32) {
-        int vc;
-        const int tok = rate_token(A, src[__ldg(scan + c)], &vc);
-        int ctx, skip;
-        if (c == 0) { ctx = B.coeff_ctx; skip = 0; }
-        else {
-            int dummy;
-            const int e0 = rate_energy(rate_token(A, src[__ldg(nb + 2 * c)], &dummy));
-            const int e1 = rate_energy(rate_token(A, src[__ldg(nb + 2 * c + 1)], &dummy));
-            ctx = (1 + e0 + e1) >> 1;
-            skip = src[__ldg(scan + c - 1)] == 0; /* previous token ZERO_TOKEN <=> previous value 0 */
-        }
-        cost += vc + (int)__ldg(tc + ((rate_band(c, A.tx_size) * 2 + skip) * 6 + ctx) * RATE_TOKENS + tok);
-    }
-    if (lane == 0 && eob < NN) { /* the end-of-block token, unless the last position of the block was coded */
-        int dummy;
-        const int e0 = rate_energy(rate_token(A, src[__ldg(nb + 2 * eob)], &dummy));
-        const int e1 = rate_energy(rate_token(A, src[__ldg(nb + 2 * eob + 1)], &dummy));
-        cost += (int)__ldg(tc + ((rate_band(eob, A.tx_size) * 2 + 0) * 6 + ((1 + e0 + e1) >> 1)) * RATE_TOKENS + RATE_EOB_TOKEN);
-    }
-    for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
-    if (lane == 0) A.rate[b] = cost;
-    __syncwarp();
-}
-
-template <int N>
-__global__ void __launch_bounds__(RATE_THREADS) rate_kernel(const __grid_constant__ RateArgs A) {
-    constexpr int WARPS = RATE_THREADS / 32;
-    __shared__ __align__(16) int16_t qs[WARPS][N * N];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    for (int b = blockIdx.x * WARPS + warp; b < A.n; b += gridDim.x * WARPS) rate_block<N>(A, b, qs[warp], lane);
-}
-
-/* several batches in one launch: the blocks of all batches form one index space, a warp takes every (grid warps)-th */
+/* The blocks of all batches form one index space, cut into chunks of RATE_CHUNK consecutive blocks, one CTA each.  The first
+ * RATE_CHUNK threads fetch their block's descriptor (eob, coefficient / scan / neighbour / cost-table pointers, context) into shared
+ * memory and add the end-of-block term; then the scan POSITIONS of the whole chunk are one index space walked by all threads (a
+ * thread finds the block of its position by bisection over the running eob sums): no lane idles on a short block, and every
+ * position is an independent chain of loads.  The terms of a block are summed in shared memory (one atomic per warp when the
+ * warp's positions all belong to one block, which is the common case). */
+#define RATE_CHUNK 64
 #define RATE_MAX_BATCHES 8
 struct RateMultiArgs {
     RateArgs b[RATE_MAX_BATCHES];
     int32_t  end[RATE_MAX_BATCHES]; /* running block count */
     int32_t  nb;
 };
+struct RateBlockS { /* one block's working set */
+    const int16_t  *q, *scan, *nb;
+    const uint32_t *tc;  /* cost table of the block's (plane type, reference type) */
+    int32_t         eob, ctx, tx_size, nn;
+};
 __global__ void __launch_bounds__(RATE_THREADS) rate_multi_kernel(const __grid_constant__ RateMultiArgs M) {
-    constexpr int WARPS = RATE_THREADS / 32;
-    __shared__ __align__(16) int16_t qs[WARPS][32 * 32];
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, total = M.end[M.nb - 1];
-    for (int g = blockIdx.x * WARPS + warp; g < total; g += gridDim.x * WARPS) {
-        int k = 0;
+    __shared__ RateTables T;
+    __shared__ RateBlockS S[RATE_CHUNK];
+    __shared__ uint32_t pos_s[RATE_CHUNK + 1]; /* exclusive running sum of eob over the chunk */
+    __shared__ int32_t rate_s[RATE_CHUNK];
+    __shared__ uint32_t wsum[RATE_THREADS / 32];
+    /* block k of this CTA is g = blockIdx.x + k * gridDim.x: neighbouring blocks (which tend to be equally busy) go to different CTAs */
+    const int tid = threadIdx.x, lane = tid & 31, total = M.end[M.nb - 1];
+    rate_load_tables(M.b[0], T); /* the value tables are the context's: the same for every batch */
+    const RateArgs &A0 = M.b[0];
+    {
+        const int g = (int)blockIdx.x + tid * (int)gridDim.x;
+        const bool mine = tid < RATE_CHUNK && g < total;
+        uint32_t len = 0;
+        if (mine) {
+            int k = 0;
 #pragma unroll
-        for (int i = 1; i < RATE_MAX_BATCHES; i++) if (i < M.nb && g >= M.end[i - 1]) k = i;
-        const RateArgs &A = M.b[k];
-        const int b = g - (k ? M.end[k - 1] : 0);
-        switch (A.tx_size) { /* warp-uniform */
-        case 0: rate_block<4>(A, b, qs[warp], lane); break;
-        case 1: rate_block<8>(A, b, qs[warp], lane); break;
-        case 2: rate_block<16>(A, b, qs[warp], lane); break;
-        default: rate_block<32>(A, b, qs[warp], lane); break;
+            for (int i = 1; i < RATE_MAX_BATCHES; i++) if (i < M.nb && g >= M.end[i - 1]) k = i;
+            const RateArgs &A = M.b[k];
+            const int b = g - (k ? M.end[k - 1] : 0), nn = (4 << A.tx_size) * (4 << A.tx_size);
+            const SvtB200RateBlock B = A.blk[b];
+            const int tt = A.tx_size == 3 ? 0 : (B.tx_type & 3), eob = A.eob[b];
+            RateBlockS s;
+            s.q = A.qcoeff + (size_t)b * nn; s.scan = A.scan[tt]; s.nb = A.nb[tt];
+            s.tc = A.tc + (size_t)((B.plane_type ? 1 : 0) * 2 + (B.is_inter ? 1 : 0)) * (6 * 2 * 6 * RATE_TOKENS);
+            s.eob = eob; s.ctx = B.coeff_ctx; s.tx_size = A.tx_size; s.nn = nn;
+            S[tid] = s;
+            len = (uint32_t)eob;
+            /* the end-of-block token: the only term of an empty block, absent when the last position of the block was coded */
+            int r = 0;
+            if (eob == 0) r = (int)__ldg(s.tc + (0 * 2 + 0) * 6 * RATE_TOKENS + B.coeff_ctx * RATE_TOKENS + RATE_EOB_TOKEN);
+            else if (eob < nn) {
+                const int e0 = rate_energy(rate_token_only(T, s.q[__ldg(s.nb + 2 * eob)]));
+                const int e1 = rate_energy(rate_token_only(T, s.q[__ldg(s.nb + 2 * eob + 1)]));
+                r = (int)__ldg(s.tc + ((rate_band(eob, A.tx_size) * 2 + 0) * 6 + ((1 + e0 + e1) >> 1)) * RATE_TOKENS + RATE_EOB_TOKEN);
+            }
+            rate_s[tid] = r;
+        }
+        /* exclusive scan of the eob values over the first RATE_CHUNK threads (two warps) */
+        uint32_t inc = len;
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
+        if (lane == 31) wsum[tid >> 5] = inc;
+        __syncthreads();
+        if (tid < RATE_CHUNK) {
+            uint32_t base = 0;
+            for (int w = 0; w < (tid >> 5); w++) base += wsum[w];
+            pos_s[tid] = base + inc - len;
+            if (tid == RATE_CHUNK - 1) pos_s[RATE_CHUNK] = base + inc;
+        }
+    }
+    __syncthreads();
+    const uint32_t npos = pos_s[RATE_CHUNK];
+    for (uint32_t p0 = 0; p0 < npos; p0 += RATE_THREADS) {
+        const uint32_t p = p0 + tid;
+        const bool act = p < npos;
+        int i = 0, cost = 0, v = 0, cpos = 0;
+        if (act) {
+#pragma unroll
+            for (int step = RATE_CHUNK / 2; step > 0; step >>= 1) if (pos_s[i + step] <= p) i += step;
+            const RateBlockS &s = S[i];
+            const int c = (int)(p - pos_s[i]);
+            v = s.q[__ldg(s.scan + c)];
+            cpos = c;
+        }
+        /* the previous coefficient in scan order sits in the lane below when that lane works on the same block */
+        const int v_below = __shfl_up_sync(0xffffffffu, v, 1), i_below = __shfl_up_sync(0xffffffffu, i, 1);
+        if (act) {
+            const RateBlockS &s = S[i];
+            const int c = cpos;
+            int vc;
+            const int tok = rate_token(A0, T, v, &vc);
+            int ctx, skip;
+            if (c == 0) { ctx = s.ctx; skip = 0; }
+            else {
+                const uint32_t nbp = __ldg((const uint32_t *)(s.nb + 2 * c)); /* both neighbour positions */
+                const int e0 = rate_energy(rate_token_only(T, s.q[nbp & 0xffff]));
+                const int e1 = rate_energy(rate_token_only(T, s.q[nbp >> 16]));
+                ctx = (1 + e0 + e1) >> 1;
+                const int prev = (lane > 0 && i_below == i) ? v_below : s.q[__ldg(s.scan + c - 1)];
+                skip = prev == 0; /* previous token ZERO_TOKEN <=> previous value 0 */
+            }
+            cost = vc + (int)__ldg(s.tc + ((rate_band(c, s.tx_size) * 2 + skip) * 6 + ctx) * RATE_TOKENS + tok);
+        }
+        /* sum per block: one atomic per warp when all its (active) lanes work on the same block */
+        const unsigned m = __ballot_sync(0xffffffffu, act);
+        if (m) {
+            const int lead = __ffs(m) - 1, i0 = __shfl_sync(0xffffffffu, i, lead);
+            if (__all_sync(0xffffffffu, !act || i == i0)) {
+                for (int o = 16; o > 0; o >>= 1) cost += __shfl_xor_sync(0xffffffffu, cost, o);
+                if (lane == lead) atomicAdd(&rate_s[i0], cost);
+            } else if (act) atomicAdd(&rate_s[i], cost);
+        }
+    }
+    __syncthreads();
+    {
+        const int g = (int)blockIdx.x + tid * (int)gridDim.x;
+        if (tid < RATE_CHUNK && g < total) {
+            int k = 0;
+#pragma unroll
+            for (int i = 1; i < RATE_MAX_BATCHES; i++) if (i < M.nb && g >= M.end[i - 1]) k = i;
+            M.b[k].rate[g - (k ? M.end[k - 1] : 0)] = rate_s[tid];
         }
     }
 }
@@ -198,11 +247,7 @@ int svtb200_coeff_rate_multi_dev(SvtB200Ctx *c, const SvtB200RateBatch *batches,
         M.end[M.nb++] = total;
     }
     if (!total) return SVTB200_OK;
-    const int warps = RATE_THREADS / 32;
-    int grid = (total + warps - 1) / warps;
-    const int cap = (c->sm_count > 0 ? c->sm_count : 148) * 8;
-    if (grid > cap) grid = cap;
-    rate_multi_kernel<<<grid, RATE_THREADS, 0, c->stream>>>(M);
+    rate_multi_kernel<<<(total + RATE_CHUNK - 1) / RATE_CHUNK, RATE_THREADS, 0, c->stream>>>(M); /* the kernel's block assignment relies on this grid size */
     c->launches++;
     SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return SVTB200_OK;
@@ -214,19 +259,12 @@ int svtb200_coeff_rate_batch_dev(SvtB200Ctx *c, int tx_size, int n, const int16_
     if (!n) return SVTB200_OK;
     std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
-    RateArgs A;
-    const int frc = rate_fill(c, A, tx_size, n, qcoeff, eob, blocks, token_costs, rate);
+    RateMultiArgs M;
+    memset(&M, 0, sizeof(M));
+    const int frc = rate_fill(c, M.b[0], tx_size, n, qcoeff, eob, blocks, token_costs, rate);
     if (frc) return frc;
-    const int warps = RATE_THREADS / 32;
-    int grid = (n + warps - 1) / warps;
-    const int cap = (c->sm_count > 0 ? c->sm_count : 148) * 16;
-    if (grid > cap) grid = cap;
-    switch (tx_size) {
-    case 0: rate_kernel<4><<<grid, RATE_THREADS, 0, c->stream>>>(A); break;
-    case 1: rate_kernel<8><<<grid, RATE_THREADS, 0, c->stream>>>(A); break;
-    case 2: rate_kernel<16><<<grid, RATE_THREADS, 0, c->stream>>>(A); break;
-    default: rate_kernel<32><<<grid, RATE_THREADS, 0, c->stream>>>(A); break;
-    }
+    M.end[0] = n; M.nb = 1;
+    rate_multi_kernel<<<(n + RATE_CHUNK - 1) / RATE_CHUNK, RATE_THREADS, 0, c->stream>>>(M);
     c->launches++;
     SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return SVTB200_OK;
