@@ -219,6 +219,23 @@ int svtb200_block_stats_picture(SvtB200Ctx *ctx, uint64_t pic_id, int32_t luma_w
 int svtb200_block_stats_picture_dev(SvtB200Ctx *ctx, uint64_t pic_id, int32_t luma_width, int32_t luma_height, uint8_t *y_mean_dev,
                                     uint16_t *variance_dev);
 
+/* compute_chroma_block_mean() / zero_out_chroma_block_mean() (Source/Lib/Codec/EbPictureAnalysisProcess.c:1828, :1760; per SB from
+ * compute_picture_spatial_statistics :4810-4822): for every COMPLETE 64x64 super-block the means of its 16 chroma 8x8 blocks (the
+ * luma 16x16 positions; rows 0, 2, 4, 6 of the block only, 8.8 fixed point), of the four 16x16 and of the 32x32 chroma block, each
+ * larger size = (sum of four) >> 2 -- the 32x32 one as the reference computes it, i.e. with the last quadrant added twice and the
+ * third never (:2011-2016) --, stored >> 8 in ME_TIER_ZERO_PU order (64x64, 32x32 x 4, 16x16 x 16: 21 bytes per super-block and
+ * plane); incomplete super-blocks get zeros.  cb / cr: DEVICE pointers to sample (0,0) of the chroma planes (8-byte aligned, stride a
+ * multiple of 8); outputs n_sb x 21 bytes each, device memory.  Runs on the current compute queue. */
+int svtb200_chroma_block_mean_dev(SvtB200Ctx *ctx, const uint8_t *cb_dev, const uint8_t *cr_dev, int32_t chroma_stride, int32_t luma_width,
+                                  int32_t luma_height, uint8_t *cb_mean_dev, uint8_t *cr_mean_dev);
+/* sub_sample_chroma_generate_pixel_intensity_histogram_bins() + calculate_histogram() (EbPictureAnalysisProcess.c:4313, :127): per
+ * picture region (regions_w x regions_h, sized in luma samples like the luma histograms) the 256-bin histograms of every 4th sample
+ * of every 4th row of the Cb and Cr planes; bin = (1 + count) << 4.  hist: [regions_w][regions_h][2][256] uint32 (the reference's
+ * picture_histogram[w][h][1 + plane][bin]), avg: [regions_w][regions_h][2] bytes = ((sum << 4) + (area >> 3)) / (area >> 2) with the
+ * region's luma area, sum16[2]: the sums over the regions of (region sum << 4).  All DEVICE pointers. */
+int svtb200_chroma_histogram_dev(SvtB200Ctx *ctx, const uint8_t *cb_dev, const uint8_t *cr_dev, int32_t chroma_stride, int32_t luma_width,
+                                 int32_t luma_height, int32_t regions_w, int32_t regions_h, uint32_t *hist_dev, uint8_t *avg_dev, uint64_t *sum16_dev);
+
 /* sub_sample_luma_generate_pixel_intensity_histogram_bins() + calculate_histogram() (EbPictureAnalysisProcess.c:4237, :128;
  * from gathering_picture_statistics :4893): the 256-bin intensity histograms of the picture's 1/16 plane over a regions_w x
  * regions_h grid of regions (region = floor(size / regions); the last region of a row / column takes the remainder).  Each

@@ -44,6 +44,11 @@ void svtb200_oracle_coeff_rate(int tx_size, int n, const int16_t *qcoeff, const 
                                const uint32_t *token_costs, const int16_t *const scans[4], const int16_t *const neighbors[4],
                                const int16_t *vtok, const int32_t *vcost, const int16_t *c6lo, const uint16_t *c6hi, int32_t *rate);
 
+/* chroma statistics of the picture-analysis stage: pa_port.c (cb / cr at sample (0,0) of the planes) */
+void svtb200_oracle_chroma_block_mean(const uint8_t *cb, const uint8_t *cr, int stride, int luma_width, int luma_height, uint8_t *cb_mean, uint8_t *cr_mean);
+void svtb200_oracle_chroma_histogram(const uint8_t *cb, const uint8_t *cr, int stride, int luma_width, int luma_height, int rw, int rh,
+                                     uint32_t *hist, uint8_t *avg, uint64_t sum16[2]);
+
 /* block walk in front of the inter predictors, open-loop partition of the bench: blocks_port.c */
 void svtb200_oracle_inter_expand(const SvtB200InterBlock *blocks, int n, const SvtB200PredPicture *pic, SvtB200PredBlock *out);
 int  svtb200_oracle_me_best_blocks(const SvtB200MeCuResult *me, int width, int height, SvtB200InterBlock *out);

@@ -23,7 +23,7 @@ EbErrorType __real_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static int   g_mode = -1; /* 0 off, 1 check, 2 dump */
 static char  g_dir[512];
-static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed, g_stats_bad, g_hist_pics, g_hist_bad;
+static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed, g_stats_bad, g_hist_pics, g_hist_bad, g_chroma_bad, g_chroma_hist_bad;
 static int   g_max_dump_pics = 4, g_dump_from = 0;
 
 #define MAX_TRACKED 64
@@ -38,7 +38,7 @@ static void write_summary(void) {
     snprintf(path, sizeof(path), "%s/summary.txt", g_dir);
     FILE *f = fopen(path, "w");
     if (!f) return;
-    fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\nstats_bad %ld\nhist_pics %ld\nhist_bad %ld\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped, g_stats_bad, g_hist_pics, g_hist_bad);
+    fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\nstats_bad %ld\nhist_pics %ld\nhist_bad %ld\nchroma_bad %ld\nchroma_hist_bad %ld\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped, g_stats_bad, g_hist_pics, g_hist_bad, g_chroma_bad, g_chroma_hist_bad);
     fclose(f);
 }
 
@@ -109,7 +109,25 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
                 if (av[iw * rh + ih] != (uint8_t)pcs->average_intensity_per_region[iw][ih][0]) hb++;
             }
             free(hg);
-            pthread_mutex_lock(&g_mu); g_hist_pics++; g_hist_bad += hb; pthread_mutex_unlock(&g_mu);
+            /* ... and the chroma statistics of the picture (block means of every super-block, region histograms) */
+            EbPictureBufferDesc *ip = pcs->enhanced_picture_ptr;
+            const uint8_t *cb = ip->buffer_cb + (size_t)(ip->origin_y >> 1) * ip->stride_cb + (ip->origin_x >> 1);
+            const uint8_t *cr = ip->buffer_cr + (size_t)(ip->origin_y >> 1) * ip->stride_cr + (ip->origin_x >> 1);
+            const int n_sb = (int)pcs->sb_total_count;
+            uint8_t *mb = (uint8_t *)malloc((size_t)n_sb * 21), *mr = (uint8_t *)malloc((size_t)n_sb * 21);
+            long cbad = 0, chb = 0;
+            svtb200_oracle_chroma_block_mean(cb, cr, ip->stride_cb, ip->width, ip->height, mb, mr);
+            for (int s = 0; s < n_sb; s++) for (int i = 0; i < 21; i++) if (mb[s * 21 + i] != pcs->cb_mean[s][i] || mr[s * 21 + i] != pcs->cr_mean[s][i]) cbad++;
+            free(mb); free(mr);
+            uint32_t *ch = (uint32_t *)malloc((size_t)rw * rh * 2 * 256 * sizeof(uint32_t));
+            uint8_t cav[512]; uint64_t cs16[2];
+            svtb200_oracle_chroma_histogram(cb, cr, ip->stride_cb, ip->width, ip->height, rw, rh, ch, cav, cs16);
+            for (int iw = 0; iw < rw; iw++) for (int ih = 0; ih < rh; ih++) for (int p = 0; p < 2; p++) {
+                for (int b = 0; b < 256; b++) if (ch[(((size_t)iw * rh + ih) * 2 + p) * 256 + b] != pcs->picture_histogram[iw][ih][1 + p][b]) chb++;
+                if (cav[(iw * rh + ih) * 2 + p] != (uint8_t)pcs->average_intensity_per_region[iw][ih][1 + p]) chb++;
+            }
+            free(ch);
+            pthread_mutex_lock(&g_mu); g_hist_pics++; g_hist_bad += hb; g_chroma_bad += cbad; g_chroma_hist_bad += chb; pthread_mutex_unlock(&g_mu);
         }
         {   /* the picture-analysis statistics of this SB (compute_block_mean_compute_variance) against the oracle restatement */
             SvtB200Plane one = cur[0];
