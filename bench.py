@@ -470,6 +470,26 @@ def encoder_record(local_rank, world, clip4k, budget_s=120.0):
     return rec
 
 
+def encoder_all_gpus_record(world, clip4k):
+    """ONE encoder handle on all the GPUs of the launch (SVT_VP9_GPU=0,1,..: pictures dealt to the devices by picture number): configs[2]
+    through the application, reference build against drop-in build.  Runs on rank 0 while the other ranks wait."""
+    if not (os.path.exists(APP_REF) and os.path.exists(APP_B200)):
+        return {"unavailable": "oracle/_ref applications not built"}
+    d = tempfile.mkdtemp(prefix="svtb200_encN_", dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+    try:
+        yuv = os.path.join(d, "c.yuv")
+        synth.write_yuv(yuv, clip4k[:16])
+        n_frames, rep = int(os.environ.get("SVTB200_BENCH_4K_FRAMES", "100")), os.path.join(d, "rep.txt")
+        ref = run_encoder(APP_REF, yuv, os.path.join(d, "ref.ivf"), 3840, 2160, n_frames, 16, 8, 1)
+        gpu = run_encoder(APP_B200, yuv, os.path.join(d, "b200.ivf"), 3840, 2160, n_frames, 16, 8, 1,
+                          {"SVT_VP9_GPU": ",".join(str(i) for i in range(world)), "SVT_VP9_GPU_REPORT": rep})
+        return {"frames": n_frames, "gpus": world, "reference": ref, "b200": gpu, "b200_gpu_report": gpu_report(rep),
+                "bitstream_identical": bool(ref["md5"]) and ref["md5"] == gpu["md5"], "speedup": (gpu["fps"] / ref["fps"]) if ref["fps"] and gpu["fps"] else None,
+                "note": "one EbEncHandle pipeline, motion estimation and deblocking of its pictures dealt to %d GPUs by picture number (no exchange between devices)" % world}
+    finally:
+        shutil.rmtree(d, ignore_errors=True)
+
+
 def numa_bind(local_rank):
     """Run this rank (and place its pinned buffers, first-touch) on the host cores next to its GPU; returns the affinity before."""
     before = os.sched_getaffinity(0)
@@ -1068,9 +1088,16 @@ def main():
     encoder = None
     if not args.no_encoder:
         enc = encoder_record(local_rank, world, clip if world == 1 else None)
+        enc_all = None
         if world > 1:
             allenc = [None] * world
             dist.all_gather_object(allenc, enc)
+            if rank == 0:
+                try:
+                    enc_all = encoder_all_gpus_record(world, clip)
+                except Exception as ex:   # never lose the bench line to the extra record
+                    enc_all = {"error": repr(ex)}
+            dist.barrier()
         else:
             allenc = [enc]
         if rank == 0:
@@ -1085,6 +1112,7 @@ def main():
                 agg["speedup"] = (agg["b200_fps_sum"] / agg["reference_fps_sum"]) if agg["b200_fps_sum"] and agg["reference_fps_sum"] else None
                 agg["note"] = "configs[4]: %d concurrent 1080p enc-mode 8 streams, one per GPU, reference run then drop-in run" % world
                 encoder["concurrent_1080p_m8"] = agg
+                encoder["one_encoder_all_gpus_4k_m8"] = enc_all
 
     if rank == 0:
         print(json.dumps({"metric": METRIC, "value": value, "unit": "fps", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,

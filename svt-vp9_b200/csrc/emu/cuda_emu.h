@@ -33,6 +33,7 @@ extern thread_local uint64_t *emu_warp_xchg; /* 32 slots per warp */
 #define __device__
 #define __host__
 #define __forceinline__ inline
+#define __noinline__
 #define __shared__ static
 #define __restrict__
 #define __launch_bounds__(...)

@@ -606,21 +606,26 @@ __device__ static void me_fullpel(const uint8_t *src, const uint8_t *rb, int wpi
 }
 
 /* ---------------------------------------------------------------------------------------------
- * su_pel_enable (EbMotionEstimation.c:3839-4258), thread 0
+ * su_pel_enable (EbMotionEstimation.c:3839-4258), one warp
  * ------------------------------------------------------------------------------------------- */
 __device__ static void me_su_pel_enable(const uint32_t *bs, const uint32_t *bm, int tl, int *e32, int *e16, int *e8) {
-    int sx = 0, sy = 0;
-    uint32_t ss = 0;
-    for (int i = 1; i < 5; i++) { sx += me_mvx(bm[i]); sy += me_mvy(bm[i]); ss += bs[i]; }
-    uint32_t ax = (uint32_t)(sx >> 2), ay = (uint32_t)(sy >> 2);
-    const uint32_t mag32 = ax * ax + ay * ay, sad32 = ss >> 2;
-    ss = 0;
-    for (int i = 5; i < 21; i++) ss += bs[i];
-    const uint32_t sad16 = ss >> 4;
-    sx = sy = 0; ss = 0;
-    for (int i = 21; i < 85; i++) { sx += me_mvx(bm[i]); sy += me_mvy(bm[i]); ss += bs[i]; }
-    ax = (uint32_t)(sx >> 6); ay = (uint32_t)(sy >> 6);
-    const uint32_t mag8 = ax * ax + ay * ay, sad8 = ss >> 6;
+    /* called by the 32 lanes of one warp: the sums over the 4 + 16 + 64 partitions by shuffles (integer sums: any order) */
+    const int lane = threadIdx.x & 31;
+    int sx32 = 0, sy32 = 0, sx8 = 0, sy8 = 0;
+    uint32_t ss32 = 0, ss16 = 0, ss8 = 0;
+    if (lane < 4) { sx32 = me_mvx(bm[1 + lane]); sy32 = me_mvy(bm[1 + lane]); ss32 = bs[1 + lane]; }
+    if (lane < 16) ss16 = bs[5 + lane];
+    for (int i = 21 + lane; i < 85; i += 32) { sx8 += me_mvx(bm[i]); sy8 += me_mvy(bm[i]); ss8 += bs[i]; }
+    for (int o = 16; o > 0; o >>= 1) {
+        sx32 += __shfl_xor_sync(0xffffffffu, sx32, o); sy32 += __shfl_xor_sync(0xffffffffu, sy32, o); ss32 += __shfl_xor_sync(0xffffffffu, ss32, o);
+        ss16 += __shfl_xor_sync(0xffffffffu, ss16, o);
+        sx8 += __shfl_xor_sync(0xffffffffu, sx8, o); sy8 += __shfl_xor_sync(0xffffffffu, sy8, o); ss8 += __shfl_xor_sync(0xffffffffu, ss8, o);
+    }
+    uint32_t ax = (uint32_t)(sx32 >> 2), ay = (uint32_t)(sy32 >> 2);
+    const uint32_t mag32 = ax * ax + ay * ay, sad32 = ss32 >> 2;
+    const uint32_t sad16 = ss16 >> 4;
+    ax = (uint32_t)(sx8 >> 6); ay = (uint32_t)(sy8 >> 6);
+    const uint32_t mag8 = ax * ax + ay * ay, sad8 = ss8 >> 6;
     const uint32_t th = (tl == 1) ? 32u * 32u : (tl == 2) ? 80u * 80u : 48u * 48u;
     const int near32 = mag32 < th, low32 = sad32 < 32 * 32 * 6;
     if (tl == 0 || tl == 2) *e32 = low32;
@@ -1142,7 +1147,8 @@ __device__ static void me_hme_level(const MeKernelArgs &A, int list, int level, 
                 *px = (int16_t)((*px + x_org_s) * mul);
                 *py = (int16_t)((*py + y_org_s) * mul);
             }
-            __syncthreads();
+            /* no barrier here: me_hme_search ended with one, the fields above are thread 0's alone, and the window geometry thread 0
+             * writes next is not read by the others before the barrier that follows it */
         }
 }
 /* ---------------------------------------------------------------------------------------------
@@ -1196,6 +1202,7 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
         st->ox = (sb % A.sbs_w) * ME_SB; st->oy = (sb / A.sbs_w) * ME_SB;
         st->sbw = min(ME_SB, A.cur[0].w - st->ox); st->sbh = min(ME_SB, A.cur[0].h - st->oy);
         st->srh = 0; st->hme_x = 0; st->hme_y = 0;
+        st->xsc = 0; st->ysc = 0; /* search centre of list 0 (list 1: reset where list 0 has finished with it) */
         for (int a = 0; a < 2; a++) for (int b = 0; b < 2; b++) {
             st->l0x[a][b] = st->l0y[a][b] = st->l1x[a][b] = st->l1y[a][b] = st->l2x[a][b] = st->l2y[a][b] = 0;
             st->l0s[a][b] = st->l1s[a][b] = st->l2s[a][b] = 0;
@@ -1218,8 +1225,9 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
     for (int list = 0; list < nl; list++) {
         const MePlaneDev &rp = A.ref[list][0];
         uint32_t *ls = bsad + list * 85, *lm = bmv + list * 85, *lq = bssd + list * 85;
-        if (t == 0) { st->xsc = 0; st->ysc = 0; }
-        __syncthreads();
+        /* the running search centre (st->xsc, st->ysc) is (0,0) here; every thread carries a copy in registers: the decisions below
+         * depend on CTA-wide sums every thread holds, so all threads take them redundantly instead of waiting for thread 0 */
+        int16_t xsc_r = 0, ysc_r = 0;
         uint32_t sad_zero = 0;
         int have_zero = 0;
         if (P.temporal_layer_index > 0 || list == 0) {
@@ -1242,21 +1250,20 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
             const uint32_t c_o = cs[0], c_b = cs[1], c_c = cs[2], c_d = cs[3];
             const uint64_t c_dir = (list == 1) ? (uint64_t)cs[4] : 0xFFFFFFFFFFFFFull;
             sad_zero = c_o; have_zero = 1;
-            if (t == 0) {
+            {
                 uint64_t best = c_o;
                 if (c_b < best) best = c_b;
                 if (c_c < best) best = c_c;
                 if (c_d < best) best = c_d;
                 if (c_dir < best) best = c_dir;
-                int16_t xsc, ysc; /* tie order O, A(==O), B, C, direct, D; unclipped offsets */
-                if (best == c_o) { xsc = 0; ysc = 0; }
-                else if (best == c_b) { xsc = (int16_t)W0; ysc = 0; }
-                else if (best == c_c) { xsc = 0; ysc = (int16_t)(0 - H0); }
-                else if (best == c_dir) { xsc = dirx; ysc = diry; }
-                else { xsc = 0; ysc = (int16_t)H0; }
-                st->xsc = xsc; st->ysc = ysc;
+                /* tie order O, A(==O), B, C, direct, D; unclipped offsets */
+                if (best == c_o) { xsc_r = 0; ysc_r = 0; }
+                else if (best == c_b) { xsc_r = (int16_t)W0; ysc_r = 0; }
+                else if (best == c_c) { xsc_r = 0; ysc_r = (int16_t)(0 - H0); }
+                else if (best == c_dir) { xsc_r = dirx; ysc_r = diry; }
+                else { xsc_r = 0; ysc_r = (int16_t)H0; }
+                if (t == 0) { st->xsc = xsc_r; st->ysc = ysc_r; } /* thread 0's hierarchical-search set-up reads it from there */
             }
-            __syncthreads();
             if (P.enable_hme_flag && st->sbh == ME_SB) {
                 const int nqx = P.number_hme_search_region_in_width, nqy = P.number_hme_search_region_in_height;
                 const int single = P.single_hme_quadrant && !P.enable_hme_level1 && !P.enable_hme_level2;
@@ -1271,7 +1278,7 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
                     }
                     if (P.enable_hme_level0 && single) st->srh = 0;
                 }
-                __syncthreads();
+                /* (no barrier: only thread 0 touches these fields before me_hme_level's own) */
                 if (P.enable_hme_level0) me_hme_level(A, list, 0, single, st, src, hsrc, win, posacc);
                 if (P.enable_hme_level1) me_hme_level(A, list, 1, 0, st, src, hsrc, win, posacc);
                 if (P.enable_hme_level2) me_hme_level(A, list, 2, 0, st, src, hsrc, win, posacc);
@@ -1305,24 +1312,23 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
                     st->xsc = st->hme_x; st->ysc = st->hme_y;
                 }
                 __syncthreads();
+                xsc_r = st->xsc; ysc_r = st->ysc;
             }
         }
-        if (A.trace && t == 0) { A.trace[sb].hme_center_x[list] = st->xsc; A.trace[sb].hme_center_y[list] = st->ysc; }
+        if (A.trace && t == 0) { A.trace[sb].hme_center_x[list] = xsc_r; A.trace[sb].hme_center_y[list] = ysc_r; }
         /* ---- (0,0) versus the HME centre */
-        if (st->xsc != 0 || st->ysc != 0) {
+        if (xsc_r != 0 || ysc_r != 0) {
             int16_t cdx[5] = {0, 0, 0, 0, 0}, cdy[5] = {0, 0, 0, 0, 0};
-            const int16_t cx = me_clip_center(st->ox, st->xsc, ME_SB - 1, rp.w), cy = me_clip_center(st->oy, st->ysc, ME_SB - 1, rp.h);
+            const int16_t cx = me_clip_center(st->ox, xsc_r, ME_SB - 1, rp.w), cy = me_clip_center(st->oy, ysc_r, ME_SB - 1, rp.h);
             cdx[0] = cx; cdy[0] = cy;
             uint32_t cs[5];
             me_sb_sad_multi(src, st, rp, have_zero ? 1 : 2, cdx, cdy, cs, st->red); /* candidate 1 = (0,0) when not yet known */
             const uint32_t hme = cs[0], zero = have_zero ? sad_zero : cs[1];
-            __syncthreads();
-            if (t == 0) { if (zero <= hme) { st->xsc = 0; st->ysc = 0; } else { st->xsc = cx; st->ysc = cy; } }
-            __syncthreads();
+            if (zero <= hme) { xsc_r = 0; ysc_r = 0; } else { xsc_r = cx; ysc_r = cy; } /* every thread holds the sums: no hand-off */
         }
         if (t == 0) {
             int16_t saw = (int16_t)min(P.search_area_width, 127), sah = (int16_t)min(P.search_area_height, 127);
-            int16_t xo = (int16_t)(st->xsc - (saw >> 1)), yo = (int16_t)(st->ysc - (sah >> 1));
+            int16_t xo = (int16_t)(xsc_r - (saw >> 1)), yo = (int16_t)(ysc_r - (sah >> 1));
             me_clip_window(st->ox, &xo, &saw, ME_SB - 1, P.luma_width);
             me_clip_window(st->oy, &yo, &sah, ME_SB - 1, P.luma_height);
             st->sa_ox[list] = xo; st->sa_oy[list] = yo; st->saw[list] = saw; st->sah[list] = sah;
@@ -1349,14 +1355,17 @@ __global__ void __launch_bounds__(ME_THREADS, 4) me_sb_kernel(const __grid_const
         }
         __syncthreads();
         /* ---- sub-pel */
-        if (t == 0) {
+        if (t < 32) { /* warp 0 */
             int e32 = 0, e16 = 0, e8 = 0, eq = 0;
             if (P.fractional_search_model == 0) e32 = e16 = e8 = eq = 1;
             else if (P.fractional_search_model == 1) { me_su_pel_enable(ls, lm, P.temporal_layer_index, &e32, &e16, &e8); eq = 1; }
-            st->e32 = e32; st->e16 = e16; st->e8 = e8; st->eq = eq;
-            const int W = st->saw[list] + ME_SB - 1;
-            st->istride[list] = me_istride(W);
-            if (A.trace) A.trace[sb].subpel_enable[list] = (uint8_t)(e32 | (e16 << 1) | (e8 << 2) | (eq << 3));
+            if (t == 0) {
+                st->xsc = 0; st->ysc = 0; /* for the next list: nothing reads the centre of this list any more */
+                st->e32 = e32; st->e16 = e16; st->e8 = e8; st->eq = eq;
+                const int W = st->saw[list] + ME_SB - 1;
+                st->istride[list] = me_istride(W);
+                if (A.trace) A.trace[sb].subpel_enable[list] = (uint8_t)(e32 | (e16 << 1) | (e8 << 2) | (eq << 3));
+            }
         }
         __syncthreads();
         ip[list].rb = rb; ip[list].rp = fpp;

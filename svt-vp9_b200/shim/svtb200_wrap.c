@@ -19,8 +19,10 @@
  * then copies its own super-block's 85 entries into pcs->me_results.  If no GPU context can be created the wrappers fall
  * through to the reference functions (__real_*), so the library still works on a CPU-only box.
  *
- * Environment: SVT_VP9_GPU=<device index> (default 0), SVT_VP9_GPU=off disables the GPU path; SVT_VP9_GPU_REPORT=<file> counters
- * at exit.  Measurement aids (tools / bench.py): SVT_VP9_ME_RECORD=<file> writes every picture's ME results to a table at exit;
+ * Environment: SVT_VP9_GPU=<device index> (default 0) or a comma-separated list of devices ("0,1,2,3": ONE encoder, its pictures
+ * dealt to the devices by picture number -- motion estimation is open loop, a picture needs only its own and its references' SOURCE
+ * planes, which are uploaded to the device that runs it; filtered pictures are dealt round-robin; no exchange between devices),
+ * SVT_VP9_GPU=off disables the GPU path; SVT_VP9_GPU_REPORT=<file> counters at exit.  Measurement aids (tools / bench.py): SVT_VP9_ME_RECORD=<file> writes every picture's ME results to a table at exit;
  * SVT_VP9_ME_REPLAY=<file> serves motion estimation from such a table (no ME work at all: the speed the pipeline around the
  * seam would reach with a zero-cost motion estimation).
  */
@@ -39,12 +41,18 @@ EbErrorType __real_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
 void __real_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_filter_level, int y_only, int partial_frame);
 
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;    /* slot table, residency table, counters */
-static pthread_mutex_t g_queue_mu = PTHREAD_MUTEX_INITIALIZER; /* one picture at a time issues its kernel + download (queue order) */
-static pthread_mutex_t g_lf_mu = PTHREAD_MUTEX_INITIALIZER; /* deblocking: page-lock table + the (library-serialised) call */
+static pthread_mutex_t g_lf_mu = PTHREAD_MUTEX_INITIALIZER; /* deblocking: page-lock table */
 static pthread_cond_t  g_cv = PTHREAD_COND_INITIALIZER;
-static SvtB200Ctx     *g_ctx;    /* picture residency + motion estimation */
-static SvtB200Ctx     *g_ctx_lf; /* deblocking: its own queues and lock, so that a picture being filtered never waits behind (or blocks) the
-                                    motion estimation of the pictures after it -- they are different pipeline stages in the reference too */
+#define MAX_DEV 8
+static int             g_ndev;              /* devices in use (SVT_VP9_GPU list) */
+static SvtB200Ctx     *g_ctxs[MAX_DEV];     /* per device: picture residency + motion estimation */
+static SvtB200Ctx     *g_ctxs_lf[MAX_DEV];  /* per device: deblocking on its own queues and lock, so that a picture being filtered never waits behind
+                                               (or blocks) the motion estimation of the pictures after it -- different pipeline stages in the reference too */
+static pthread_mutex_t g_queue_mus[MAX_DEV], g_lf_mus[MAX_DEV];
+static unsigned long   g_dev_pictures[MAX_DEV];
+static unsigned        g_lf_next;
+#define g_ctx g_ctxs[0]
+#define g_ctx_lf g_ctxs_lf[0]
 static int             g_state; /* 0 untried, 1 ready, -1 unavailable */
 static unsigned long   g_me_pictures, g_me_sbs, g_lf_pictures, g_fallbacks, g_replayed;
 static double          g_t_resident, g_t_me, g_t_lf; /* seconds spent in uploads / waiting for ME results / svtb200_deblock_picture */
@@ -129,6 +137,11 @@ static void table_read(const char *path) {
     fclose(f);
 }
 
+static unsigned long long launches_total(void) {
+    unsigned long long n = 0;
+    for (int d = 0; d < g_ndev; d++) n += svtb200_launch_count(g_ctxs[d]) + svtb200_launch_count(g_ctxs_lf[d]);
+    return n;
+}
 static void report(void) {
     const char *p = getenv("SVT_VP9_GPU_REPORT");
     table_write();
@@ -136,7 +149,9 @@ static void report(void) {
     FILE *f = fopen(p, "w");
     if (!f) return;
     fprintf(f, "state %d\nme_pictures %lu\nme_sbs %lu\nlf_pictures %lu\nfallbacks %lu\nreplayed_sbs %lu\nlaunches %llu\n", g_state, g_me_pictures, g_me_sbs,
-            g_lf_pictures, g_fallbacks, g_replayed, g_ctx ? (unsigned long long)(svtb200_launch_count(g_ctx) + svtb200_launch_count(g_ctx_lf)) : 0ull);
+            g_lf_pictures, g_fallbacks, g_replayed, launches_total());
+    fprintf(f, "devices %d\n", g_ndev);
+    for (int d = 0; d < g_ndev; d++) fprintf(f, "me_pictures_dev%d %lu\n", d, g_dev_pictures[d]);
     fprintf(f, "ms_upload %d\nms_me %d\nms_lf %d\n", (int)(1e3 * g_t_resident), (int)(1e3 * g_t_me), (int)(1e3 * g_t_lf));
     fclose(f);
 }
@@ -146,9 +161,21 @@ static int ctx_ready(void) {
     if (g_state == 0) {
         const char *e = getenv("SVT_VP9_GPU");
         g_state = -1;
-        if (!(e && !strcmp(e, "off")) && svtb200_create(e ? atoi(e) : 0, &g_ctx) == SVTB200_OK) {
-            if (svtb200_create(e ? atoi(e) : 0, &g_ctx_lf) == SVTB200_OK) g_state = 1;
-            else { svtb200_destroy(g_ctx); g_ctx = NULL; }
+        if (!(e && !strcmp(e, "off"))) {
+            int devs[MAX_DEV], n = 0;
+            for (const char *q = e ? e : "0"; *q && n < MAX_DEV;) { /* "2" or "0,1,2,3" */
+                devs[n++] = atoi(q);
+                while (*q && *q != ',') q++;
+                if (*q == ',') q++;
+            }
+            int ok = n > 0;
+            for (int d = 0; d < n && ok; d++) {
+                ok = svtb200_create(devs[d], &g_ctxs[d]) == SVTB200_OK && svtb200_create(devs[d], &g_ctxs_lf[d]) == SVTB200_OK;
+                pthread_mutex_init(&g_queue_mus[d], NULL);
+                pthread_mutex_init(&g_lf_mus[d], NULL);
+            }
+            if (ok) { g_ndev = n; g_state = 1; }
+            else for (int d = 0; d < n; d++) { if (g_ctxs[d]) svtb200_destroy(g_ctxs[d]); if (g_ctxs_lf[d]) svtb200_destroy(g_ctxs_lf[d]); g_ctxs[d] = g_ctxs_lf[d] = NULL; }
         }
         if (g_state < 0 && getenv("SVT_VP9_GPU_VERBOSE")) fprintf(stderr, "svtb200: no GPU context, using the CPU kernels\n");
     }
@@ -182,9 +209,10 @@ typedef struct {
     SvtB200MeParams          P;
     SvtB200MeCuResult       *res;   /* pinned, n_sb * 85 */
     uint32_t                *rcme;  /* pinned, n_sb */
-    SvtB200MeCuResult       *d_res; /* device twins */
-    uint32_t                *d_rcme;
-    size_t                   cap_sb;
+    int                      dev;   /* the device (index into g_ctxs) this picture runs on */
+    SvtB200MeCuResult       *d_res_dev[MAX_DEV]; /* device twins, one set per device the slot has been used with */
+    uint32_t                *d_rcme_dev[MAX_DEV];
+    size_t                   cap_sb, cap_dev[MAX_DEV];
 } MeSlot;
 static MeSlot g_slots[MAX_IN_FLIGHT];
 
@@ -192,12 +220,12 @@ static MeSlot g_slots[MAX_IN_FLIGHT];
  * encoder instance (its EncodeContext) the object belongs to -- eb_vp9_deinit_encoder drops that instance's entries, so that a later
  * encoder in the same process whose buffers land on the same addresses never matches a stale picture */
 #define MAX_RESIDENT 256
-typedef struct { const void *obj, *inst; uint64_t poc; int valid, locked; void *reg[3]; pthread_mutex_t mu; } ResEntry;
+typedef struct { const void *obj, *inst; uint64_t poc[MAX_DEV]; int valid[MAX_DEV], locked; void *reg[3]; pthread_mutex_t mu; } ResEntry;
 static ResEntry g_res[MAX_RESIDENT];
 static pthread_once_t g_res_once = PTHREAD_ONCE_INIT;
 static void res_init(void) { for (int i = 0; i < MAX_RESIDENT; i++) pthread_mutex_init(&g_res[i].mu, NULL); }
 
-static int ensure_resident(const EbPaReferenceObject *o, uint64_t poc, const void *inst, int want_quarter) {
+static int ensure_resident(int dev, const EbPaReferenceObject *o, uint64_t poc, const void *inst, int want_quarter) {
     int idx = -1, fresh = 0;
     pthread_once(&g_res_once, res_init);
     pthread_mutex_lock(&g_mu);
@@ -205,13 +233,13 @@ static int ensure_resident(const EbPaReferenceObject *o, uint64_t poc, const voi
         if (g_res[i].obj == (const void *)o && g_res[i].inst == inst) { idx = i; break; }
         if (!g_res[i].obj && idx < 0) idx = i;
     }
-    if (idx >= 0 && g_res[idx].obj != (const void *)o) { g_res[idx].obj = o; g_res[idx].inst = inst; g_res[idx].valid = 0; fresh = 1; }
+    if (idx >= 0 && g_res[idx].obj != (const void *)o) { g_res[idx].obj = o; g_res[idx].inst = inst; memset(g_res[idx].valid, 0, sizeof(g_res[idx].valid)); fresh = 1; }
     pthread_mutex_unlock(&g_mu);
     if (idx < 0) return SVTB200_ENOMEM;
     ResEntry *e = &g_res[idx];
     pthread_mutex_lock(&e->mu); /* only callers that need THIS picture wait here */
     int rc = SVTB200_OK;
-    if (!(e->valid && e->poc == poc)) {
+    if (!(e->valid[dev] && e->poc[dev] == poc)) {
         SvtB200Plane pl[3];
         svtb200_glue_pa_planes(o, pl);
         static int pagelock = -1; /* SVT_VP9_GPU_PAGELOCK=0: leave the reference's buffers pageable (staged copies, no page-locking cost) */
@@ -222,8 +250,8 @@ static int ensure_resident(const EbPaReferenceObject *o, uint64_t poc, const voi
                     svtb200_host_register((void *)pl[k].buf, (size_t)pl[k].stride * pl[k].padded_height) == SVTB200_OK) e->reg[k] = (void *)pl[k].buf;
             e->locked = 1;
         }
-        rc = svtb200_picture_upload(g_ctx, (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
-        if (rc == SVTB200_OK) { e->poc = poc; e->valid = 1; } else e->valid = 0;
+        rc = svtb200_picture_upload(g_ctxs[dev], (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
+        if (rc == SVTB200_OK) { e->poc[dev] = poc; e->valid[dev] = 1; } else e->valid[dev] = 0;
     }
     pthread_mutex_unlock(&e->mu);
     return rc;
@@ -246,23 +274,27 @@ static int run_picture(MeSlot *s) {
     EbPaReferenceObject *r1 = s->P.num_lists == 2 ? (EbPaReferenceObject *)pcs->ref_pa_pic_ptr_array[1]->object_ptr : r0;
     const size_t rb = (size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult);
     const double t0 = now_s();
-    int rc = ensure_resident(cur, pcs->picture_number, inst, want_q);
-    if (rc == SVTB200_OK) rc = ensure_resident(r0, pcs->ref_pic_poc_array[0], inst, want_q);
-    if (rc == SVTB200_OK && s->P.num_lists == 2) rc = ensure_resident(r1, pcs->ref_pic_poc_array[1], inst, want_q);
+    const int dev = s->dev;
+    SvtB200Ctx *ctx = g_ctxs[dev];
+    SvtB200MeCuResult *d_res = s->d_res_dev[dev];
+    uint32_t *d_rcme = s->d_rcme_dev[dev];
+    int rc = ensure_resident(dev, cur, pcs->picture_number, inst, want_q);
+    if (rc == SVTB200_OK) rc = ensure_resident(dev, r0, pcs->ref_pic_poc_array[0], inst, want_q);
+    if (rc == SVTB200_OK && s->P.num_lists == 2) rc = ensure_resident(dev, r1, pcs->ref_pic_poc_array[1], inst, want_q);
     const double t1 = now_s();
     uint64_t ticket = 0;
     if (rc == SVTB200_OK) {
         const uint64_t ids[2] = {(uint64_t)(uintptr_t)r0, (uint64_t)(uintptr_t)r1};
-        pthread_mutex_lock(&g_queue_mu); /* kernel, fence, download, marker: queued as one unit; nothing here waits for the GPU */
-        rc = svtb200_me_picture_dev(g_ctx, &s->P, (uint64_t)(uintptr_t)cur, ids, s->d_res, s->P.rate_control_mode ? s->d_rcme : NULL);
-        if (rc == SVTB200_OK) rc = svtb200_fence(g_ctx, SVTB200_STREAM_COMPUTE, SVTB200_STREAM_DOWNLOAD);
-        if (rc == SVTB200_OK) rc = svtb200_memcpy_d2h_async(g_ctx, s->res, s->d_res, rb);
-        if (rc == SVTB200_OK && s->P.rate_control_mode) rc = svtb200_memcpy_d2h_async(g_ctx, s->rcme, s->d_rcme, (size_t)s->n_sb * 4);
-        if (rc == SVTB200_OK) rc = svtb200_marker(g_ctx, SVTB200_STREAM_DOWNLOAD, &ticket);
-        pthread_mutex_unlock(&g_queue_mu);
+        pthread_mutex_lock(&g_queue_mus[dev]); /* kernel, fence, download, marker: queued as one unit; nothing here waits for the GPU */
+        rc = svtb200_me_picture_dev(ctx, &s->P, (uint64_t)(uintptr_t)cur, ids, d_res, s->P.rate_control_mode ? d_rcme : NULL);
+        if (rc == SVTB200_OK) rc = svtb200_fence(ctx, SVTB200_STREAM_COMPUTE, SVTB200_STREAM_DOWNLOAD);
+        if (rc == SVTB200_OK) rc = svtb200_memcpy_d2h_async(ctx, s->res, d_res, rb);
+        if (rc == SVTB200_OK && s->P.rate_control_mode) rc = svtb200_memcpy_d2h_async(ctx, s->rcme, d_rcme, (size_t)s->n_sb * 4);
+        if (rc == SVTB200_OK) rc = svtb200_marker(ctx, SVTB200_STREAM_DOWNLOAD, &ticket);
+        pthread_mutex_unlock(&g_queue_mus[dev]);
     }
-    if (rc == SVTB200_OK) rc = svtb200_wait(g_ctx, ticket);
-    else svtb200_sync(g_ctx); /* an upload of this picture may still be reading the encoder's buffer: let it finish before the CPU path takes over */
+    if (rc == SVTB200_OK) rc = svtb200_wait(ctx, ticket);
+    else svtb200_sync(ctx); /* an upload of this picture may still be reading the encoder's buffer: let it finish before the CPU path takes over */
     pthread_mutex_lock(&g_mu);
     g_t_resident += t1 - t0;
     g_t_me += now_s() - t1;
@@ -310,24 +342,30 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
             __atomic_store_n(&s->state, 1, __ATOMIC_RELEASE);
             svtb200_glue_me_params(pcs, me, &s->P);
             s->n_sb = ((s->P.luma_width + 63) / 64) * ((s->P.luma_height + 63) / 64);
+            s->dev = (int)(pcs->picture_number % (uint64_t)g_ndev); /* pictures dealt to the devices by display number */
             if (s->cap_sb < (size_t)s->n_sb) {
                 if (s->res) svtb200_host_free(s->res);
                 if (s->rcme) svtb200_host_free(s->rcme);
-                if (s->d_res) svtb200_dev_free(g_ctx, s->d_res);
-                if (s->d_rcme) svtb200_dev_free(g_ctx, s->d_rcme);
                 s->res = (SvtB200MeCuResult *)svtb200_host_alloc((size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult));
                 s->rcme = (uint32_t *)svtb200_host_alloc((size_t)s->n_sb * sizeof(uint32_t));
-                s->d_res = (SvtB200MeCuResult *)svtb200_dev_alloc(g_ctx, (size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult));
-                s->d_rcme = (uint32_t *)svtb200_dev_alloc(g_ctx, (size_t)s->n_sb * sizeof(uint32_t));
-                s->cap_sb = (s->res && s->rcme && s->d_res && s->d_rcme) ? (size_t)s->n_sb : 0;
+                s->cap_sb = (s->res && s->rcme) ? (size_t)s->n_sb : 0;
             }
+            if (s->cap_dev[s->dev] < (size_t)s->n_sb) {
+                const int d = s->dev;
+                if (s->d_res_dev[d]) svtb200_dev_free(g_ctxs[d], s->d_res_dev[d]);
+                if (s->d_rcme_dev[d]) svtb200_dev_free(g_ctxs[d], s->d_rcme_dev[d]);
+                s->d_res_dev[d] = (SvtB200MeCuResult *)svtb200_dev_alloc(g_ctxs[d], (size_t)s->n_sb * 85 * sizeof(SvtB200MeCuResult));
+                s->d_rcme_dev[d] = (uint32_t *)svtb200_dev_alloc(g_ctxs[d], (size_t)s->n_sb * sizeof(uint32_t));
+                s->cap_dev[d] = (s->d_res_dev[d] && s->d_rcme_dev[d]) ? (size_t)s->n_sb : 0;
+            }
+            g_dev_pictures[s->dev]++;
             g_me_pictures++;
             pthread_mutex_unlock(&g_mu);
-            const int rc = s->cap_sb ? run_picture(s) : SVTB200_ENOMEM;
+            const int rc = (s->cap_sb && s->cap_dev[s->dev]) ? run_picture(s) : SVTB200_ENOMEM;
             pthread_mutex_lock(&g_mu);
             if (rc == SVTB200_OK && g_record_path) table_put(s->picture_number, s->n_sb, s->P.rate_control_mode, s->res, s->rcme);
             __atomic_store_n(&s->state, rc == SVTB200_OK ? 2 : 3, __ATOMIC_RELEASE);
-            if (rc != SVTB200_OK && getenv("SVT_VP9_GPU_VERBOSE")) fprintf(stderr, "svtb200: ME on the GPU failed (%d: %s)\n", rc, svtb200_last_error(g_ctx));
+            if (rc != SVTB200_OK && getenv("SVT_VP9_GPU_VERBOSE")) fprintf(stderr, "svtb200: ME on the GPU failed (%d: %s)\n", rc, svtb200_last_error(g_ctxs[s->dev]));
             pthread_cond_broadcast(&g_cv);
         } else {
             while (s->state == 1) pthread_cond_wait(&g_cv, &g_mu);
@@ -387,10 +425,13 @@ void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_
             }
         }
     }
-    const double t2 = now_s();
-    const int rc = svtb200_deblock_picture(g_ctx_lf, &P, xd->plane[0].dst.buf, xd->plane[0].dst.stride, xd->plane[1].dst.buf, xd->plane[2].dst.buf,
-                                           xd->plane[1].dst.stride, (const SvtB200LfMask *)cm->lf.lfm, cm->lf.lfm_stride, thr);
+    const int ldev = (int)(g_lf_next++ % (unsigned)g_ndev); /* filtered pictures are dealt round-robin */
     pthread_mutex_unlock(&g_lf_mu);
+    const double t2 = now_s();
+    pthread_mutex_lock(&g_lf_mus[ldev]);
+    const int rc = svtb200_deblock_picture(g_ctxs_lf[ldev], &P, xd->plane[0].dst.buf, xd->plane[0].dst.stride, xd->plane[1].dst.buf, xd->plane[2].dst.buf,
+                                           xd->plane[1].dst.stride, (const SvtB200LfMask *)cm->lf.lfm, cm->lf.lfm_stride, thr);
+    pthread_mutex_unlock(&g_lf_mus[ldev]);
     pthread_mutex_lock(&g_mu);
     g_t_lf += now_s() - t2;
     if (rc == SVTB200_OK) g_lf_pictures++; else g_fallbacks++;
@@ -399,7 +440,7 @@ void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_
         /* the device failed AFTER filtered samples had started to land in the reconstruction: neither filtering again nor skipping the
          * filter gives the reference's picture any more.  A CUDA error at that point is a lost device; stop instead of writing a
          * bitstream that silently differs. */
-        fprintf(stderr, "svtb200: GPU failure while the filtered picture was being written back (%s); aborting\n", svtb200_last_error(g_ctx_lf));
+        fprintf(stderr, "svtb200: GPU failure while the filtered picture was being written back (%s); aborting\n", svtb200_last_error(g_ctxs_lf[ldev]));
         abort();
     }
     if (rc != SVTB200_OK) __real_eb_vp9_loop_filter_frame(cm, xd, frame_filter_level, y_only, partial_frame);
@@ -426,8 +467,7 @@ EbErrorType eb_vp9_deinit_encoder(EbComponentType *svt_enc_component) {
     if (live) {
         int cs;
         pthread_setcancelstate(PTHREAD_CANCEL_DISABLE, &cs);
-        svtb200_sync(g_ctx);
-        svtb200_sync(g_ctx_lf);
+        for (int d = 0; d < g_ndev; d++) { svtb200_sync(g_ctxs[d]); svtb200_sync(g_ctxs_lf[d]); }
         pthread_once(&g_res_once, res_init);
         for (int i = 0; i < MAX_RESIDENT; i++) {
             ResEntry *e = &g_res[i];
@@ -436,10 +476,10 @@ EbErrorType eb_vp9_deinit_encoder(EbComponentType *svt_enc_component) {
             pthread_mutex_unlock(&g_mu);
             if (!mine) continue;
             pthread_mutex_lock(&e->mu);
-            svtb200_picture_release(g_ctx, (uint64_t)(uintptr_t)e->obj);
+            for (int d = 0; d < g_ndev; d++) svtb200_picture_release(g_ctxs[d], (uint64_t)(uintptr_t)e->obj);
             for (int k = 0; k < 3; k++) if (e->reg[k]) { svtb200_host_unregister(e->reg[k]); e->reg[k] = NULL; }
             pthread_mutex_lock(&g_mu);
-            e->obj = NULL; e->inst = NULL; e->valid = 0; e->locked = 0;
+            e->obj = NULL; e->inst = NULL; memset(e->valid, 0, sizeof(e->valid)); e->locked = 0;
             pthread_mutex_unlock(&g_mu);
             pthread_mutex_unlock(&e->mu);
         }

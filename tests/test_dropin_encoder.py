@@ -93,3 +93,33 @@ def test_encoder_with_gpu_hot_path_writes_the_reference_bitstream(w, h, n, mode)
         r = _report(rep)
         assert r["state"] == 1 and r["me_pictures"] >= n - 2 and r["fallbacks"] == 0 and r["launches"] > 0, r   # the GPU did the work
         assert a == b, "bitstreams differ (%s)" % r
+
+
+def _n_gpus():
+    try:
+        import torch
+        return torch.cuda.device_count() if torch.cuda.is_available() else 0
+    except Exception:
+        return 0
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,mode", [(1920, 1080, 34, 8), (3840, 2160, 34, 8)], ids=["1920x1080-m8", "3840x2160-m8"])
+def test_one_encoder_on_several_gpus_writes_the_reference_bitstream(w, h, n, mode):
+    """SVT_VP9_GPU=0,1[,2,3]: ONE encoder handle, its pictures dealt to the devices by picture number (each device gets the source
+    planes it needs; no exchange between devices).  Same bitstream as the reference; every device took its share of the pictures."""
+    g = _n_gpus()
+    if g < 2:
+        pytest.skip("needs at least two GPUs (gpurun --gpus 2)")
+    g = min(g, 4)
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "clip.yuv")
+        _write_yuv(yuv, w, h, n, 3 + mode)
+        a = _encode(APP_REF, yuv, os.path.join(d, "ref.ivf"), w, h, n, mode)
+        rep = os.path.join(d, "rep.txt")
+        b = _encode(APP_B200, yuv, os.path.join(d, "b200.ivf"), w, h, n, mode,
+                    {"SVT_VP9_GPU": ",".join(str(i) for i in range(g)), "SVT_VP9_GPU_REPORT": rep, "SVT_VP9_GPU_VERBOSE": "1"})
+        r = _report(rep)
+        assert r["state"] == 1 and r["devices"] == g and r["fallbacks"] == 0, r
+        assert all(r["me_pictures_dev%d" % i] >= (n - 2) // g - 1 for i in range(g)), r
+        assert a == b, "bitstreams differ (%s)" % r
