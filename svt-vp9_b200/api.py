@@ -9,7 +9,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvtvp9_b200.so")
+LIB_PATH = os.environ.get("SVTB200_LIB") or os.path.join(_HERE, "libsvtvp9_b200.so")   # SVTB200_LIB: an experimental build of the same sources (tools)
 
 
 class Plane(C.Structure):

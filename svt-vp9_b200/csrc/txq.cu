@@ -17,6 +17,9 @@
 #include "txfm_device.cuh"
 
 #define TXQ_THREADS 128
+#ifndef TXQ_MIN_BLOCKS
+#define TXQ_MIN_BLOCKS 6 /* resident CTAs per SM the register allocation aims at */
+#endif
 
 struct TxqArgs {
     /* mode 0: fused from planes */
@@ -328,7 +331,7 @@ __device__ __forceinline__ void txq_pass(const TxqArgs &A, int blk0, int *tiles)
 }
 
 template <int N, int MODE>
-__global__ void __launch_bounds__(TXQ_THREADS, 4) txq_kernel(const __grid_constant__ TxqArgs A) {
+__global__ void __launch_bounds__(TXQ_THREADS, TXQ_MIN_BLOCKS) txq_kernel(const __grid_constant__ TxqArgs A) {
     constexpr int G = TXQ_THREADS / N; /* blocks per CTA pass */
     __shared__ int tiles[G * N * (N + 1)];
     for (int blk0 = blockIdx.x * G; blk0 < A.n; blk0 += gridDim.x * G) txq_pass<N, MODE>(A, blk0, tiles);
@@ -344,7 +347,7 @@ struct TxqMultiArgs {
     int32_t unit_end[TXQ_MAX_BATCHES]; /* cumulative number of CTA passes */
     int32_t n_batches;
 };
-__global__ void __launch_bounds__(TXQ_THREADS, 4) txq_multi_kernel(const __grid_constant__ TxqMultiArgs M) {
+__global__ void __launch_bounds__(TXQ_THREADS, TXQ_MIN_BLOCKS) txq_multi_kernel(const __grid_constant__ TxqMultiArgs M) {
     __shared__ int tiles[4 * 32 * 33];
     const int total = M.unit_end[M.n_batches - 1];
     for (int u = blockIdx.x; u < total; u += gridDim.x) {
