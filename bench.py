@@ -415,10 +415,12 @@ def gpu_report(path):
         return None
 
 
-def encoder_record(local_rank, world, clip4k, budget_s=120.0):
+def encoder_record(local_rank, world, clip4k, budget_s=120.0, sync=None):
     """configs[1] (1080p, enc-mode 8, 300 frames) and configs[2] (4K, enc-mode 8; a bounded number of frames) through the
     application, reference build against drop-in build, one process per rank when world > 1 (configs[4]: concurrent streams,
-    one per GPU).  Returns the per-rank record; the caller aggregates over ranks."""
+    one per GPU; sync() lines the ranks up before every run so that the N reference encoders run together and the N drop-in encoders
+    run together).  Returns the per-rank record; the caller aggregates over ranks."""
+    sync = sync or (lambda: None)
     if not (os.path.exists(APP_REF) and os.path.exists(APP_B200)):
         return {"unavailable": "oracle/_ref applications not built"}
     t_start = time.perf_counter()
@@ -436,14 +438,16 @@ def encoder_record(local_rank, world, clip4k, budget_s=120.0):
             synth.write_yuv(yuv_c, clip4k[:16])
             cases.append(("4k_m8", yuv_c, 3840, 2160, int(os.environ.get("SVTB200_BENCH_4K_FRAMES", "100")), 16))
         for name, yuv, cw, ch, n_frames, n_buf in cases:
-            if time.perf_counter() - t_start > budget_s:
+            if world == 1 and time.perf_counter() - t_start > budget_s:   # (with several ranks every rank must make the same calls to sync)
                 rec[name] = {"skipped": "time budget of the encoder record used up"}
                 continue
             rep = os.path.join(d, "rep.txt")
             # alternate the two builds (page cache, clocks and the pools' first touches favour whoever runs later); the better run of each counts
             refs, gpus = [], []
             for r_i in range(2 if name == "1080p_m8" else 1):
+                sync()
                 refs.append(run_encoder(APP_REF, yuv, os.path.join(d, "ref.ivf"), cw, ch, n_frames, n_buf, 8, 1))
+                sync()
                 gpus.append(run_encoder(APP_B200, yuv, os.path.join(d, "b200.ivf"), cw, ch, n_frames, n_buf, 8, 1,
                                         {"SVT_VP9_GPU": str(local_rank), "SVT_VP9_GPU_REPORT": rep}))
             if name != "1080p_m8":   # one more reference run after the drop-in run, so that the reference is never the only cold one
@@ -1087,7 +1091,7 @@ def main():
     # ---- BASELINE.json's own metric through the application (every rank encodes its own stream when world > 1)
     encoder = None
     if not args.no_encoder:
-        enc = encoder_record(local_rank, world, clip if world == 1 else None)
+        enc = encoder_record(local_rank, world, clip if world == 1 else None, sync=(dist.barrier if world > 1 else None))
         enc_all = None
         if world > 1:
             allenc = [None] * world

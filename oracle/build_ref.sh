@@ -75,7 +75,8 @@ if [ -f $HERE/../svt-vp9_b200/libsvtvp9_b200.so ]; then
   gcc $CF $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/../svt-vp9_b200/shim/svtb200_wrap.c -o $OUT/svtb200_wrap.o
   gcc -shared -o $D/libSvtVp9Enc.so.1 $D/obj/*.o $OUT/svtb200_wrap.o -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm \
       -Wl,-soname,libSvtVp9Enc.so.1 -Wl,--version-script=$REF/Source/API/EbApi.version \
-      -Wl,--wrap=motion_estimate_sb -Wl,--wrap=eb_vp9_loop_filter_frame -Wl,-rpath,'$ORIGIN/../../../svt-vp9_b200'
+      -Wl,--wrap=motion_estimate_sb -Wl,--wrap=eb_vp9_loop_filter_frame -Wl,--wrap=eb_vp9_post_full_object -Wl,--wrap=eb_vp9_picture_analysis_context_ctor \
+      -Wl,-rpath,'$ORIGIN/../../../svt-vp9_b200'
   gcc -std=gnu99 -O2 -w -I$OUT/inc -I$REF/Source/API $REF/Source/App/*.c -o $OUT/SvtVp9EncApp_b200 \
       -L$D -l:libSvtVp9Enc.so.1 -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN/dropin' -Wl,-rpath,'$ORIGIN/../../svt-vp9_b200'
   rm -rf $D/obj $OUT/libSvtVp9Enc_b200.so

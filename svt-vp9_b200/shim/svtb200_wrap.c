@@ -7,6 +7,11 @@
  *
  *   S1  motion_estimate_sb()        Source/Lib/Codec/EbMotionEstimation.c:4524 (call site EbMotionEstimationProcess.c:1037)
  *   S2  eb_vp9_loop_filter_frame()  Source/Lib/VPX/vp9_loopfilter.c:1521       (call site EbEncDecProcess.c:5678)
+ *   prefetch: eb_vp9_post_full_object() (Source/Lib/Codec/EbSystemResourceManager.c:482) is wrapped only to SEE the picture-analysis results go
+ *       by (EbPictureAnalysisProcess.c, end of the kernel loop): that is the moment a picture's padded / decimated planes are final, a whole
+ *       mini-GOP of look-ahead before motion estimation asks for them, so the upload is queued there instead of inside the first
+ *       motion_estimate_sb() call of the picture.  The results objects are recognised by their system resource, learnt from the wrapped
+ *       eb_vp9_picture_analysis_context_ctor() (EbPictureAnalysisProcess.c:46).  SVT_VP9_GPU_PREFETCH=0 turns it off.
  *   teardown: eb_vp9_deinit_encoder() (Source/Lib/Codec/EbEncHandle.c:1711) is exported from here; the reference's own
  *       definition is kept under the name svtb200_real_eb_vp9_deinit_encoder (objcopy --redefine-sym on a COPY of the
  *       compiled object, oracle/build_ref.sh) and called after the GPU state of that encoder instance has been dropped.
@@ -35,6 +40,9 @@
 
 #include "svtb200_ref_glue.h"
 #include "EbEncHandle.h"
+#include "EbPictureAnalysisProcess.h"
+#include "EbPictureAnalysisResults.h"
+#include "EbSystemResourceManager.h"
 
 EbErrorType __real_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_index, uint32_t sb_origin_x, uint32_t sb_origin_y,
                                       MeContext *me, EbPictureBufferDesc *input);
@@ -54,8 +62,8 @@ static unsigned        g_lf_next;
 #define g_ctx g_ctxs[0]
 #define g_ctx_lf g_ctxs_lf[0]
 static int             g_state; /* 0 untried, 1 ready, -1 unavailable */
-static unsigned long   g_me_pictures, g_me_sbs, g_lf_pictures, g_fallbacks, g_replayed;
-static double          g_t_resident, g_t_me, g_t_lf; /* seconds spent in uploads / waiting for ME results / svtb200_deblock_picture */
+static unsigned long   g_me_pictures, g_me_sbs, g_lf_pictures, g_fallbacks, g_replayed, g_prefetched;
+static double          g_t_resident, g_t_me, g_t_lf, g_t_prefetch; /* seconds spent in uploads / waiting for ME results / svtb200_deblock_picture */
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
 /* ------------------------------------------------------------------------------------------------ record / replay */
@@ -152,7 +160,8 @@ static void report(void) {
             g_lf_pictures, g_fallbacks, g_replayed, launches_total());
     fprintf(f, "devices %d\n", g_ndev);
     for (int d = 0; d < g_ndev; d++) fprintf(f, "me_pictures_dev%d %lu\n", d, g_dev_pictures[d]);
-    fprintf(f, "ms_upload %d\nms_me %d\nms_lf %d\n", (int)(1e3 * g_t_resident), (int)(1e3 * g_t_me), (int)(1e3 * g_t_lf));
+    fprintf(f, "ms_upload %d\nms_me %d\nms_lf %d\nprefetched %lu\nms_prefetch %d\n", (int)(1e3 * g_t_resident), (int)(1e3 * g_t_me), (int)(1e3 * g_t_lf),
+            g_prefetched, (int)(1e3 * g_t_prefetch));
     fclose(f);
 }
 
@@ -220,7 +229,7 @@ static MeSlot g_slots[MAX_IN_FLIGHT];
  * encoder instance (its EncodeContext) the object belongs to -- eb_vp9_deinit_encoder drops that instance's entries, so that a later
  * encoder in the same process whose buffers land on the same addresses never matches a stale picture */
 #define MAX_RESIDENT 256
-typedef struct { const void *obj, *inst; uint64_t poc[MAX_DEV]; int valid[MAX_DEV], locked; void *reg[3]; pthread_mutex_t mu; } ResEntry;
+typedef struct { const void *obj, *inst; uint64_t poc[MAX_DEV]; int valid[MAX_DEV], has_q[MAX_DEV], locked; void *reg[3]; pthread_mutex_t mu; } ResEntry;
 static ResEntry g_res[MAX_RESIDENT];
 static pthread_once_t g_res_once = PTHREAD_ONCE_INIT;
 static void res_init(void) { for (int i = 0; i < MAX_RESIDENT; i++) pthread_mutex_init(&g_res[i].mu, NULL); }
@@ -239,7 +248,7 @@ static int ensure_resident(int dev, const EbPaReferenceObject *o, uint64_t poc, 
     ResEntry *e = &g_res[idx];
     pthread_mutex_lock(&e->mu); /* only callers that need THIS picture wait here */
     int rc = SVTB200_OK;
-    if (!(e->valid[dev] && e->poc[dev] == poc)) {
+    if (!(e->valid[dev] && e->poc[dev] == poc && (e->has_q[dev] || !want_quarter))) {
         SvtB200Plane pl[3];
         svtb200_glue_pa_planes(o, pl);
         static int pagelock = -1; /* SVT_VP9_GPU_PAGELOCK=0: leave the reference's buffers pageable (staged copies, no page-locking cost) */
@@ -251,7 +260,7 @@ static int ensure_resident(int dev, const EbPaReferenceObject *o, uint64_t poc, 
             e->locked = 1;
         }
         rc = svtb200_picture_upload(g_ctxs[dev], (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
-        if (rc == SVTB200_OK) { e->poc[dev] = poc; e->valid[dev] = 1; } else e->valid[dev] = 0;
+        if (rc == SVTB200_OK) { e->poc[dev] = poc; e->valid[dev] = 1; e->has_q[dev] = want_quarter; } else e->valid[dev] = 0;
     }
     pthread_mutex_unlock(&e->mu);
     return rc;
@@ -390,6 +399,57 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
     }
     if (!ok) return __real_motion_estimate_sb(pcs, sb_index, sb_origin_x, sb_origin_y, me, input);
     return EB_ErrorNone;
+}
+
+/* ------------------------------------------------------------------------------------------------------------ prefetch */
+EbErrorType __real_eb_vp9_picture_analysis_context_ctor(EbPictureBufferDescInitData *init, EB_BOOL denoise_flag, PictureAnalysisContext **ctx,
+                                                        EbFifo *in_fifo, EbFifo *out_fifo, uint16_t sb_total_count);
+EbErrorType __real_eb_vp9_post_full_object(EbObjectWrapper *w);
+#define MAX_PA_QUEUES 16
+static const void *g_pa_queues[MAX_PA_QUEUES]; /* empty queues of the picture-analysis results resources of the live encoders */
+
+EbErrorType __wrap_eb_vp9_picture_analysis_context_ctor(EbPictureBufferDescInitData *init, EB_BOOL denoise_flag, PictureAnalysisContext **ctx,
+                                                        EbFifo *in_fifo, EbFifo *out_fifo, uint16_t sb_total_count) {
+    if (out_fifo && out_fifo->queue_ptr) {
+        pthread_mutex_lock(&g_mu);
+        int known = 0, fr = -1;
+        for (int i = 0; i < MAX_PA_QUEUES; i++) { known |= g_pa_queues[i] == (const void *)out_fifo->queue_ptr; if (!g_pa_queues[i] && fr < 0) fr = i; }
+        if (!known && fr >= 0) g_pa_queues[fr] = (const void *)out_fifo->queue_ptr;
+        pthread_mutex_unlock(&g_mu);
+    }
+    return __real_eb_vp9_picture_analysis_context_ctor(init, denoise_flag, ctx, in_fifo, out_fifo, sb_total_count);
+}
+
+EbErrorType __wrap_eb_vp9_post_full_object(EbObjectWrapper *w) {
+    static int enabled = -1;
+    if (enabled < 0) { const char *e = getenv("SVT_VP9_GPU_PREFETCH"); enabled = !(e && e[0] == '0'); }
+    if (enabled && !g_replay && w && w->system_resource_ptr && w->object_ptr) {
+        const void *q = (const void *)w->system_resource_ptr->empty_queue;
+        int is_pa = 0;
+        for (int i = 0; i < MAX_PA_QUEUES; i++) is_pa |= g_pa_queues[i] && g_pa_queues[i] == q; /* written once at start-up, before any picture */
+        if (is_pa) {
+            PictureAnalysisResults *r = (PictureAnalysisResults *)w->object_ptr;
+            PictureParentControlSet *pcs = r->picture_control_set_wrapper_ptr ? (PictureParentControlSet *)r->picture_control_set_wrapper_ptr->object_ptr : NULL;
+            pthread_mutex_lock(&g_mu);
+            const int ready = ctx_ready();
+            pthread_mutex_unlock(&g_mu);
+            if (ready && pcs && pcs->pareference_picture_wrapper_ptr && pcs->sequence_control_set_wrapper_ptr) {
+                SequenceControlSet *scs = (SequenceControlSet *)pcs->sequence_control_set_wrapper_ptr->object_ptr;
+                const double t0 = now_s();
+                int cs;
+                pthread_setcancelstate(PTHREAD_CANCEL_DISABLE, &cs);
+                /* to the device that will run this picture's motion estimation; as a reference on other devices it is uploaded on demand */
+                if (ensure_resident((int)(pcs->picture_number % (uint64_t)g_ndev), (EbPaReferenceObject *)pcs->pareference_picture_wrapper_ptr->object_ptr,
+                                    pcs->picture_number, (const void *)scs->encode_context_ptr, pcs->enable_hme_flag && pcs->enable_hme_level_1_flag) == SVTB200_OK)
+                    __atomic_add_fetch(&g_prefetched, 1, __ATOMIC_RELAXED);
+                pthread_setcancelstate(cs, NULL);
+                pthread_mutex_lock(&g_mu);
+                g_t_prefetch += now_s() - t0;
+                pthread_mutex_unlock(&g_mu);
+            }
+        }
+    }
+    return __real_eb_vp9_post_full_object(w);
 }
 
 /* ------------------------------------------------------------------------------------------------------------ S2 */
