@@ -16,6 +16,7 @@
 #define _GNU_SOURCE
 #define RTCD_C /* the two headers then provide the static setup_rtcd_internal*; built with -fcommon so that the
                   function-pointer variables merge with the definitions in the reference objects */
+#include <stddef.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -518,6 +519,12 @@ int refdrv_inter_prediction(void *h, const SvtB200InterBlock *blocks, int begin,
 #include <pthread.h>
 #include <sched.h>
 #include <time.h>
+#include <execinfo.h>
+#include <signal.h>
+#include <unistd.h>
+/* test aid: a backtrace on SIGSEGV (faults inside the reference's functions are otherwise silent under pytest) */
+static void refdrv_segv(int sig) { void *bt[40]; int n = backtrace(bt, 40); (void)sig; backtrace_symbols_fd(bt, n, 2); _exit(139); }
+void refdrv_debug_segv(void) { signal(SIGSEGV, refdrv_segv); }
 
 typedef struct {
     int32_t              tx_size, n;

@@ -256,3 +256,92 @@ def test_thread_pool_of_the_cpu_arm_equals_direct_calls():
             assert not (recs[0][:h, :w] == unf[0]).all()
             fy, fu, fv = H.refdrv_deblock(P_lf, unf[0], unf[1], np.zeros_like(unf[1]), lfm, lfm_stride, thr)
             assert (recs[0][:h, :w] == fy).all() and (recs[1][:h // 2, :w // 2] == fu).all() and (recs[2][:h // 2, :w // 2] == fv).all()
+
+
+def test_thread_pool_with_inter_prediction_and_rate_equals_direct_calls():
+    """the CPU arm's round-2 chain inside refdrv_pool_run -- motion estimation -> open-loop partition -> the reference's inter_prediction()
+    into prediction planes -> transform passes reading them -> coeff_rate_estimate of every block -- against the same steps called one
+    by one (oracle partition, refdrv_inter_prediction, refdrv_txq, refdrv_coeff_rate)"""
+    import ctypes as C
+    import test_rate as TR
+    L = H.refdrv()
+    w, h = 384, 256
+    clip = H.synth.make_clip(w, h, 3, seed=78, k=3, g=4, a=5, b=3, m=32, noise=2)
+    pl = [frames.pa_planes(f[0]) for f in clip]
+    st = [frames.plane_structs(p) for p in pl]
+    cpad = [[H.aligned_copy(np.pad(f[1], 40, mode="edge")), H.aligned_copy(np.pad(f[2], 40, mode="edge"))] for f in clip]
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    rows = H.quant_rows([120])
+    tc = np.ascontiguousarray(H.vp9_tables()["token_costs_default"])
+    cur, r0, r1 = 1, 0, 2
+    P = presets.me_params_1080p_m8(w, h, 4, 2, (r0, r1))
+    n_blk = (w // 32) * (h // 32)
+
+    def pred_picture(dst):
+        pp = api.PredPicture()
+        pp.width, pp.height, pp.use_subpel_flag = w, h, 1
+        for l, r in enumerate((r0, r1)):
+            full = pl[r]["full"]
+            pp.ref[l][0], pp.ref_stride[l][0] = full.ctypes.data + frames.FULL_PAD * full.shape[1] + frames.FULL_PAD, full.shape[1]
+            for c in range(2):
+                a = cpad[r][c]
+                pp.ref[l][1 + c], pp.ref_stride[l][1 + c] = a.ctypes.data + 40 * a.shape[1] + 40, a.shape[1]
+        for k in range(3):
+            pp.dst[k], pp.dst_stride[k] = dst[k].ctypes.data, dst[k].shape[1]
+        return pp
+    planes = [H.aligned_copy(clip[cur][0]), H.aligned_copy(clip[cur][1]), H.aligned_copy(clip[cur][2])]
+    preds = [H.aligned_zeros((h, w), np.uint8), H.aligned_zeros((h // 2, w // 2), np.uint8), H.aligned_zeros((h // 2, w // 2), np.uint8)]
+    recs = [H.aligned_zeros(p.shape, np.uint8) for p in preds]   # the reference's SIMD reconstruction stores aligned
+    pics = (H.RefdrvPicture * 1)()
+    d = pics[0]
+    d.P, d.cur, d.ref0, d.ref1 = P, st[cur], st[r0], st[r1]
+    me = np.zeros(n_sb * 85, dtype=api.ME_RESULT_DTYPE)
+    d.me_out = me.ctypes.data
+    d.n_pass, outs = 3, []
+    for k, (ts, N, plane) in enumerate([(3, 32, 0), (2, 16, 1), (2, 16, 2)]):
+        pw, ph = planes[plane].shape[1], planes[plane].shape[0]
+        by, bx = np.meshgrid(np.arange(0, ph, N), np.arange(0, pw, N), indexing="ij")
+        jobs = np.zeros(by.size, dtype=api.TX_JOB_DTYPE)
+        jobs["src_offset"] = jobs["pred_offset"] = jobs["recon_offset"] = by.ravel() * pw + bx.ravel()
+        jobs["flags"] = 1
+        q, dq = H.aligned_zeros((by.size, N, N), np.int16), H.aligned_zeros((by.size, N, N), np.int16)
+        eob, rate = np.zeros(by.size, np.uint16), np.zeros(by.size, np.int32)
+        rb = np.zeros(by.size, dtype=api.RATE_BLOCK_DTYPE)
+        rb["plane_type"], rb["is_inter"] = (1 if plane else 0), 1
+        tp = d.passes[k]
+        tp.tx_size, tp.n, tp.jobs = ts, by.size, jobs.ctypes.data
+        tp.pl.src, tp.pl.src_stride, tp.pl.src_bytes = planes[plane].ctypes.data, pw, planes[plane].nbytes
+        tp.pl.pred, tp.pl.pred_stride, tp.pl.pred_bytes = preds[plane].ctypes.data, pw, preds[plane].nbytes
+        tp.pl.recon, tp.pl.recon_stride, tp.pl.recon_bytes = recs[plane].ctypes.data, pw, recs[plane].nbytes
+        tp.coeff, tp.qcoeff, tp.dqcoeff, tp.eob = None, q.ctypes.data, dq.ctypes.data, eob.ctypes.data
+        tp.rblk, tp.rate = rb.ctypes.data, rate.ctypes.data
+        outs.append((ts, plane, jobs, q, eob, rate, rb, dq))   # (dq only to keep the array alive)
+    d.qrows = rows.ctypes.data
+    d.n_blocks, d.pred, d.token_costs_all = n_blk, pred_picture(preds), tc.ctypes.data
+    pool = L.refdrv_pool_new(4, 1)
+    cpu_s = (C.c_double * 4)()
+    assert L.refdrv_pool_run(pool, pics, 1, 2, 8, cpu_s) == 0
+    L.refdrv_pool_free(pool)
+    assert cpu_s[0] > 0 and cpu_s[1] > 0 and cpu_s[3] > 0
+    # the same, step by step
+    want_me = H.refdrv_me_picture(P, st[cur], st[r0], st[r1], n_sb)
+    assert H.me_equal(me, want_me, 2).all()
+    O = H.oracle()
+    O.svtb200_oracle_me_best_blocks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    blocks = np.zeros(n_blk, dtype=api.INTER_BLOCK_DTYPE)
+    assert O.svtb200_oracle_me_best_blocks(want_me.ctypes.data, w, h, blocks.ctypes.data) == n_blk
+    want_pred = [H.aligned_zeros(p.shape, np.uint8) for p in preds]
+    L.refdrv_pred_new.restype = C.c_void_p
+    L.refdrv_inter_prediction.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.POINTER(api.PredPicture)]
+    L.refdrv_pred_free.argtypes = [C.c_void_p]
+    hd = L.refdrv_pred_new()
+    pp = pred_picture(want_pred)
+    assert L.refdrv_inter_prediction(hd, blocks.ctypes.data, 0, n_blk, C.byref(pp)) == 0
+    L.refdrv_pred_free(hd)
+    for a, b in zip(preds, want_pred):
+        assert (a == b).all() and a.any()
+    assert (blocks["list"][:, 1] != 0xff).any()   # some blocks are compound: both lists were read
+    for ts, plane, jobs, q, eob, rate, rb, _dq in outs:
+        _, q0, d0, e0, r0_ = H.refdrv_txq(ts, jobs, planes[plane], want_pred[plane], np.zeros_like(planes[plane]), rows)
+        assert (q == q0).all() and (eob == e0).all() and (recs[plane] == r0_).all()
+        assert (rate == TR._ref_rate(ts, np.ascontiguousarray(q0.reshape(len(jobs), -1)), e0, rb, tc)).all() and rate.any()
