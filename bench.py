@@ -786,7 +786,7 @@ def main():
         q1, s1 = (api.COMPUTE3, stream3) if overlap and ME_QUEUES == 2 and (i & 1) else (api.COMPUTE, stream)
         P, (r0, r1) = me_params(n)
         ids = (C.c_uint64 * 2)(r0, r1)
-        e = [ev() for _ in range(9)] if timed else None
+        e = ([ev() for _ in range(9)] if detail else [ev(), ev()]) if timed else None
         ctx.select_compute(q1)
         if timed:
             e[0].record(s1)
@@ -796,15 +796,13 @@ def main():
         if overlap:
             ctx.select_compute(api.COMPUTE2)
         if not detail:
-            if timed:
-                e[2].record(s2)
+            # (inside the timed region only the dominant kernel -- motion estimation -- carries events of its own: every event between
+            # two kernels of a queue costs overlap, 15 % of the step with five of them per picture)
             # open-loop partition -> block walk -> inter prediction (3 planes) -> every TU of the picture -> packing -> rate: one call,
             # queued behind the picture's motion estimation
             rc = L.svtb200_inter_chain_dev(h, C.addressof(chain_of(slot, n, r0, r1, pack_host, q1 if overlap else -1)))
             if rc:
                 ctx.check(rc, "inter_chain_dev")
-            if timed:
-                e[7].record(s2)
         else:
             if overlap:
                 ctx.stream_wait(api.COMPUTE2, ctx.marker(q1))
@@ -827,7 +825,8 @@ def main():
             rec = d_rec[slot]
             ctx.check(L.svtb200_deblock_picture_dev(h, C.byref(LfP), rec[0], W4K, rec[1], rec[2], W4K // 2, d_lfm, 60, d_thr), "deblock")
         if timed:
-            e[4].record(s2)
+            if detail:
+                e[4].record(s2)
             (marks if sink is None else sink).append((e, P, n))
         ctx.select_compute(api.COMPUTE)
         return n, r0, r1
@@ -839,7 +838,12 @@ def main():
     stream_coefs = [0, 0]      # coefficients the pack kernel stored into host memory, pictures counted
     chroma_used = {}      # marker after the last kernel that read the chroma buffers of a picture
 
-    skip = os.environ.get("SVTB200_E2E_SKIP", "").split(",")  # diagnosis only: "h2d", "d2h", "kernels"
+    # how the packed coefficients reach the host: "copy" (default): the pack kernel writes HBM, the offsets (with the stream length) come
+    # down with the other results, and the exact-size copy of picture i's stream is queued one step later, when its length is known;
+    # "mapped": the pack kernel stores straight into page-locked host memory (no second phase; measured slower: the stores hold the queue)
+    PACK_MODE = os.environ.get("SVTB200_E2E_PACK", "copy")
+    pending_stream = []        # [(slot, marker after the download of its offsets)]: pictures whose stream copy is still to be queued
+    skip = os.environ.get("SVTB200_E2E_SKIP", "").split(",")  # diagnosis only: "h2d", "d2h", "kernels", "pack" (stream stays on the device), "me" (no ME download)
 
     def step_e2e(i):
         n = ENCODE_ORDER[i % 16]
@@ -860,20 +864,36 @@ def main():
         if "kernels" in skip:
             r0 = r1 = n
         else:
-            _, r0, r1 = kernels(i, False, slot, pack_host="d2h" not in skip)
+            _, r0, r1 = kernels(i, False, slot, pack_host=PACK_MODE == "mapped" and "d2h" not in skip and "pack" not in skip)
         m2 = ctx.marker(api.COMPUTE2)                                           # the end of the picture's chain (which started behind its ME)
         chroma_used[n] = chroma_used[r0] = chroma_used[r1] = (m2,)              # the second compute queue reads the chroma planes
         ctx.stream_wait(api.DOWNLOAD, m2)
         rec = d_rec[slot]
         d2h = lambda hb, db, nb: ("d2h" in skip) or ctx.check(L.svtb200_memcpy_d2h_async(h, hb.data_ptr(), db, nb), "d2h")
-        d2h(h_me[slot], d_me[slot], N_SB * 85 * 40)                             # D2H ME results
+        if "me" not in skip:
+            d2h(h_me[slot], d_me[slot], N_SB * 85 * 40)                         # D2H ME results
         d2h(h_eob_all[slot], d_eob_all[slot], eob_off[-1])                      # D2H eob of every TU (the coefficients themselves were stored
         d2h(h_rate_all[slot], d_rate_all[slot], rate_off[-1])                   # into h_stream / h_off by the pack kernel) and their rates
         if n == 16:                                                            # D2H filtered reference picture
             d2h(h_rec[slot][0], rec[0], W4K * H4K)
             d2h(h_rec[slot][1], rec[1], csize)
             d2h(h_rec[slot][2], rec[2], csize)
+        if PACK_MODE != "mapped" and "d2h" not in skip and "pack" not in skip:
+            d2h(h_off[slot], d_off[slot], (n_tu + 1) * 4)                       # D2H block offsets + stream length
         downloaded[slot] = ctx.marker(api.DOWNLOAD)
+        if PACK_MODE != "mapped" and "d2h" not in skip and "pack" not in skip:
+            finish_streams()                                                    # the previous picture's stream: its length has arrived by now
+            pending_stream.append((slot, downloaded[slot]))
+
+    def finish_streams():
+        """queue the exact-size stream copies of the pictures whose offsets are (being) downloaded"""
+        while pending_stream:
+            sl, mk = pending_stream.pop(0)
+            ctx.wait(mk)
+            nbytes = 2 * int(h_off_np[sl][n_tu])
+            if nbytes:
+                ctx.check(L.svtb200_memcpy_d2h_async(h, h_stream[sl].data_ptr(), d_stream[sl], nbytes), "d2h stream")
+            downloaded[sl] = ctx.marker(api.DOWNLOAD)
 
     def unpack_stream(stream, offsets, eobs):
         """the host-side consumer of the packed stream: dense per-pass coefficient arrays (all TUs of the bench are DCT_DCT)"""
@@ -921,14 +941,14 @@ def main():
     ctx.sync()
     barrier()
     ms_res = e0.elapsed_time(e1)
+    ms_res_local = ms_res
     launches = ctx.launches() - launches0
     n_me = 0
-    chain_ms = [0.0]   # inter chain (partition + block walk + prediction + transform + packing + rate) inside the timed region
     for e, P, n in marks:
         stage_ms["me_sb_kernel"] += e[0].elapsed_time(e[1]); alg["me_sb_kernel"] += me_bytes(P); n_me += 1
-        chain_ms[0] += e[2].elapsed_time(e[7]); alg["pred_kernel"] += pred_bytes(P); alg["txq_kernel"] += txq_bytes()
+        alg["pred_kernel"] += pred_bytes(P); alg["txq_kernel"] += txq_bytes()
         if n == 16:
-            stage_ms["lf_row_kernel"] += e[7].elapsed_time(e[4]); alg["lf_row_kernel"] += lf_bytes()
+            alg["lf_row_kernel"] += lf_bytes()
     # the same kernels one at a time (single queue): durations without the other queue's interference
     iso_marks, iso_ms = [], {k: 0.0 for k in KERNELS}
     iso_n = {k: 0 for k in KERNELS}
@@ -945,6 +965,7 @@ def main():
             iso_ms["lf_row_kernel"] += e[7].elapsed_time(e[4]); iso_n["lf_row_kernel"] += 1
     for i in range(min(n_warm, 8)):
         step_e2e(i)
+    finish_streams()
     ctx.sync()
     barrier()
     t0 = time.perf_counter()
@@ -953,6 +974,7 @@ def main():
         ti = time.perf_counter()
         step_e2e(n_warm + i)
         t_issue += time.perf_counter() - ti
+    finish_streams()
     ctx.sync()
     if os.environ.get("SVTB200_BENCH_DEBUG"):
         sys.stderr.write("e2e host time in step_e2e (issue + waits): %.3f ms/picture\n" % (1000.0 * t_issue / n_timed))
@@ -1018,18 +1040,16 @@ def main():
     per_step_alone = {k: (iso_ms[k] / max(1, iso_n[k])) * (1.0 / 16 if k == "lf_row_kernel" else 1.0) for k in stage_ms}
     dom = max(per_step_alone, key=lambda k: per_step_alone[k])
     per_kernel = {}
-    timed_total = stage_ms["me_sb_kernel"] + chain_ms[0] + stage_ms["lf_row_kernel"]
     for k in stage_ms:
         per_pic = alg[k] / (max(1, sum(1 for m in marks if m[2] == 16)) if k == "lf_row_kernel" else n_me)
         iso = iso_ms[k] / max(1, iso_n[k])
         row = {"traffic": traffic.get(k), "ms_per_picture_alone": iso, "achieved_gbs_alone": per_pic / (iso / 1000.0) / 1e9 if iso else None,
                "frac_alone": per_pic / (iso / 1000.0) / 1e9 / peak if iso else None, "share_alone": per_step_alone[k] / sum(per_step_alone.values())}
-        if stage_ms[k] > 0:   # the kernels with events of their own inside the timed region (the chain's stages are one call there)
+        if stage_ms[k] > 0:   # the dominant kernel carries events of its own inside the timed region (the other queue's kernels overlap it)
             a = alg[k] / (stage_ms[k] / 1000.0) / 1e9
-            row.update({"ms_total": stage_ms[k], "share": stage_ms[k] / timed_total, "achieved_gbs": a, "frac": a / peak})
+            row.update({"ms_total": stage_ms[k], "ms_per_launch_in_timed_region": stage_ms[k] / n_me, "share_of_timed_region": stage_ms[k] / ms_res_local,
+                        "achieved_gbs": a, "frac": a / peak})
         per_kernel[k] = row
-    per_kernel["inter_chain"] = {"ms_total": chain_ms[0], "share": chain_ms[0] / timed_total,
-                                 "stages": "open-loop partition + block walk + pred_kernel + txq_kernel + pack_kernel + rate_kernel (svtb200_inter_chain_dev), overlapped with the next picture's motion estimation"}
     launches_dom = n_me if dom != "lf_row_kernel" else max(1, n_timed // 16)
     roof = {"bound": "hbm", "achieved": per_kernel[dom]["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": per_kernel[dom]["frac"],
             "traffic": traffic.get(dom), "kernel": dom, "alg_bytes_per_launch": alg[dom] / launches_dom,
@@ -1045,6 +1065,7 @@ def main():
         got = []
         for i in (base, base + 1):
             step_e2e(i)
+            finish_streams()
             ctx.sync()
             slot, n = i % NSLOT, ENCODE_ORDER[i % 16]
             eobs = [h_eob[slot][k].numpy().copy() for k in range(len(TU_PASSES))]

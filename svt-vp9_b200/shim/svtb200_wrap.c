@@ -11,7 +11,7 @@
  *       by (EbPictureAnalysisProcess.c, end of the kernel loop): that is the moment a picture's padded / decimated planes are final, a whole
  *       mini-GOP of look-ahead before motion estimation asks for them, so the upload is queued there instead of inside the first
  *       motion_estimate_sb() call of the picture.  The results objects are recognised by their system resource, learnt from the wrapped
- *       eb_vp9_picture_analysis_context_ctor() (EbPictureAnalysisProcess.c:46).  SVT_VP9_GPU_PREFETCH=0 turns it off.
+ *       eb_vp9_picture_analysis_context_ctor() (EbPictureAnalysisProcess.c:46).  SVT_VP9_GPU_PREFETCH=1 turns it on (off by default: measured slower).
  *   teardown: eb_vp9_deinit_encoder() (Source/Lib/Codec/EbEncHandle.c:1711) is exported from here; the reference's own
  *       definition is kept under the name svtb200_real_eb_vp9_deinit_encoder (objcopy --redefine-sym on a COPY of the
  *       compiled object, oracle/build_ref.sh) and called after the GPU state of that encoder instance has been dropped.
@@ -420,9 +420,37 @@ EbErrorType __wrap_eb_vp9_picture_analysis_context_ctor(EbPictureBufferDescInitD
     return __real_eb_vp9_picture_analysis_context_ctor(init, denoise_flag, ctx, in_fifo, out_fifo, sb_total_count);
 }
 
+/* the uploads run on a thread of their own: the picture-analysis thread only drops a note and goes on */
+typedef struct { const EbPaReferenceObject *obj; uint64_t poc; const void *inst; int want_q; } PrefetchNote;
+#define PREFETCH_RING 256
+static PrefetchNote    g_pf_ring[PREFETCH_RING];
+static unsigned        g_pf_head, g_pf_tail; /* g_mu */
+static pthread_cond_t  g_pf_cv = PTHREAD_COND_INITIALIZER;
+static int             g_pf_thread_started;
+
+static void *prefetch_thread(void *arg) {
+    (void)arg;
+    for (;;) {
+        pthread_mutex_lock(&g_mu);
+        while (g_pf_head == g_pf_tail) pthread_cond_wait(&g_pf_cv, &g_mu);
+        const PrefetchNote n = g_pf_ring[g_pf_tail % PREFETCH_RING];
+        g_pf_tail++;
+        const int live = g_state == 1;
+        pthread_mutex_unlock(&g_mu);
+        if (!live) continue;
+        const double t0 = now_s();
+        /* to the device that will run this picture's motion estimation; as a reference on other devices it is uploaded on demand */
+        if (ensure_resident((int)(n.poc % (uint64_t)g_ndev), n.obj, n.poc, n.inst, n.want_q) == SVTB200_OK) __atomic_add_fetch(&g_prefetched, 1, __ATOMIC_RELAXED);
+        pthread_mutex_lock(&g_mu);
+        g_t_prefetch += now_s() - t0;
+        pthread_mutex_unlock(&g_mu);
+    }
+    return NULL;
+}
+
 EbErrorType __wrap_eb_vp9_post_full_object(EbObjectWrapper *w) {
     static int enabled = -1;
-    if (enabled < 0) { const char *e = getenv("SVT_VP9_GPU_PREFETCH"); enabled = !(e && e[0] == '0'); }
+    if (enabled < 0) { const char *e = getenv("SVT_VP9_GPU_PREFETCH"); enabled = e && e[0] == '1'; } /* off unless asked for: see DESIGN.md section 5 */
     if (enabled && !g_replay && w && w->system_resource_ptr && w->object_ptr) {
         const void *q = (const void *)w->system_resource_ptr->empty_queue;
         int is_pa = 0;
@@ -430,21 +458,17 @@ EbErrorType __wrap_eb_vp9_post_full_object(EbObjectWrapper *w) {
         if (is_pa) {
             PictureAnalysisResults *r = (PictureAnalysisResults *)w->object_ptr;
             PictureParentControlSet *pcs = r->picture_control_set_wrapper_ptr ? (PictureParentControlSet *)r->picture_control_set_wrapper_ptr->object_ptr : NULL;
-            pthread_mutex_lock(&g_mu);
-            const int ready = ctx_ready();
-            pthread_mutex_unlock(&g_mu);
-            if (ready && pcs && pcs->pareference_picture_wrapper_ptr && pcs->sequence_control_set_wrapper_ptr) {
+            if (pcs && pcs->pareference_picture_wrapper_ptr && pcs->sequence_control_set_wrapper_ptr) {
                 SequenceControlSet *scs = (SequenceControlSet *)pcs->sequence_control_set_wrapper_ptr->object_ptr;
-                const double t0 = now_s();
-                int cs;
-                pthread_setcancelstate(PTHREAD_CANCEL_DISABLE, &cs);
-                /* to the device that will run this picture's motion estimation; as a reference on other devices it is uploaded on demand */
-                if (ensure_resident((int)(pcs->picture_number % (uint64_t)g_ndev), (EbPaReferenceObject *)pcs->pareference_picture_wrapper_ptr->object_ptr,
-                                    pcs->picture_number, (const void *)scs->encode_context_ptr, pcs->enable_hme_flag && pcs->enable_hme_level_1_flag) == SVTB200_OK)
-                    __atomic_add_fetch(&g_prefetched, 1, __ATOMIC_RELAXED);
-                pthread_setcancelstate(cs, NULL);
                 pthread_mutex_lock(&g_mu);
-                g_t_prefetch += now_s() - t0;
+                if (ctx_ready() && g_pf_head - g_pf_tail < PREFETCH_RING) {
+                    PrefetchNote *n = &g_pf_ring[g_pf_head % PREFETCH_RING];
+                    n->obj = (const EbPaReferenceObject *)pcs->pareference_picture_wrapper_ptr->object_ptr; n->poc = pcs->picture_number;
+                    n->inst = (const void *)scs->encode_context_ptr; n->want_q = pcs->enable_hme_flag && pcs->enable_hme_level_1_flag;
+                    g_pf_head++;
+                    if (!g_pf_thread_started) { pthread_t th; if (pthread_create(&th, NULL, prefetch_thread, NULL) == 0) { pthread_detach(th); g_pf_thread_started = 1; } }
+                    pthread_cond_signal(&g_pf_cv);
+                }
                 pthread_mutex_unlock(&g_mu);
             }
         }
@@ -527,6 +551,9 @@ EbErrorType eb_vp9_deinit_encoder(EbComponentType *svt_enc_component) {
     if (live) {
         int cs;
         pthread_setcancelstate(PTHREAD_CANCEL_DISABLE, &cs);
+        pthread_mutex_lock(&g_mu);
+        g_pf_tail = g_pf_head; /* notes not yet served refer to buffers that are about to be freed (one in flight holds its entry's lock, taken below) */
+        pthread_mutex_unlock(&g_mu);
         for (int d = 0; d < g_ndev; d++) { svtb200_sync(g_ctxs[d]); svtb200_sync(g_ctxs_lf[d]); }
         pthread_once(&g_res_once, res_init);
         for (int i = 0; i < MAX_RESIDENT; i++) {
