@@ -760,12 +760,12 @@ def main():
 
     _chain_cache = {}
 
-    def chain_of(slot, n, r0, r1, pack_host, behind):
+    def chain_of(slot, n, r0, r1, pack_host, behind, on):
         """the SvtB200InterChain of picture n into result slot 'slot' (built once)"""
-        key = (slot, n, pack_host, behind)
+        key = (slot, n, pack_host, behind, on)
         if key not in _chain_cache:
             ch = api.InterChain()
-            ch.after_queue = behind
+            ch.after_queue, ch.on_queue = behind, on
             ch.me, ch.blocks, ch.n_blocks, ch.pic, ch.desc = d_me[slot], d_blk[slot], N_BLK, pred_picture(slot, r0, r1), d_desc[slot]
             ch.tx, ch.n_tx, ch.qrows, ch.n_qrows = txq_batches(slot, n), len(TU_PASSES), d_rows, 1
             ch.stream, ch.offsets = (h_stream[slot].data_ptr(), h_off[slot].data_ptr()) if pack_host else (d_stream[slot], d_off[slot])
@@ -787,24 +787,26 @@ def main():
         P, (r0, r1) = me_params(n)
         ids = (C.c_uint64 * 2)(r0, r1)
         e = ([ev() for _ in range(9)] if detail else [ev(), ev()]) if timed else None
-        ctx.select_compute(q1)
+        if q1 != api.COMPUTE or detail:
+            ctx.select_compute(q1)          # (the first compute queue is the selected one between calls)
         if timed:
             e[0].record(s1)
         ctx.check(L.svtb200_me_picture_dev(h, C.byref(P), n, ids, d_me[slot], None), "me_picture_dev")
         if timed:
             e[1].record(s1)
-        if overlap:
-            ctx.select_compute(api.COMPUTE2)
         if not detail:
             # (inside the timed region only the dominant kernel -- motion estimation -- carries events of its own: every event between
-            # two kernels of a queue costs overlap, 15 % of the step with five of them per picture)
+            # two kernels of a queue, and every extra host call, costs overlap)
             # open-loop partition -> block walk -> inter prediction (3 planes) -> every TU of the picture -> packing -> rate: one call,
-            # queued behind the picture's motion estimation
-            rc = L.svtb200_inter_chain_dev(h, C.addressof(chain_of(slot, n, r0, r1, pack_host, q1 if overlap else -1)))
+            # on the second compute queue, queued behind the picture's motion estimation
+            rc = L.svtb200_inter_chain_dev(h, C.addressof(chain_of(slot, n, r0, r1, pack_host, q1 if overlap else -1, api.COMPUTE2 if overlap else q1)))
             if rc:
                 ctx.check(rc, "inter_chain_dev")
+            if n == 16 and overlap:
+                ctx.select_compute(api.COMPUTE2)
         else:
             if overlap:
+                ctx.select_compute(api.COMPUTE2)
                 ctx.stream_wait(api.COMPUTE2, ctx.marker(q1))
             e[2].record(s2)
             rc = L.svtb200_me_best_blocks_dev(h, d_me[slot], W4K, H4K, d_blk[slot])
@@ -828,7 +830,8 @@ def main():
             if detail:
                 e[4].record(s2)
             (marks if sink is None else sink).append((e, P, n))
-        ctx.select_compute(api.COMPUTE)
+        if detail or q1 != api.COMPUTE or (n == 16 and overlap):
+            ctx.select_compute(api.COMPUTE)
         return n, r0, r1
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI's three queues.  Picture i+1 uploads and
@@ -930,8 +933,17 @@ def main():
     ctx.fence(api.COMPUTE, api.COMPUTE2)   # the other queues start inside the timed region ...
     ctx.fence(api.COMPUTE, api.COMPUTE3)
     t_host = time.perf_counter()
+    NOEV = bool(os.environ.get("SVTB200_BENCH_NOEVENTS"))   # diagnosis: the timed region without the per-launch events of the dominant kernel
+    # at most DEPTH pictures queued ahead of the GPU (as the end-to-end leg, which collects picture i-3 before it queues picture i):
+    # with the launch queue filled to the brim the two compute queues overlap worse (measured: 1.72 k against 2.0 k pictures/s)
+    DEPTH = int(os.environ.get("SVTB200_BENCH_DEPTH", "4"))
+    inflight = []
     for i in range(n_timed):
-        kernels(n_warm + i, True, (n_warm + i) % NSLOT)
+        if DEPTH and len(inflight) >= DEPTH:
+            ctx.wait(inflight.pop(0))
+        kernels(n_warm + i, not NOEV, (n_warm + i) % NSLOT)
+        if DEPTH:
+            inflight.append(ctx.marker(api.COMPUTE2))
     t_host = time.perf_counter() - t_host
     if os.environ.get("SVTB200_BENCH_DEBUG"):
         sys.stderr.write("value leg: host issue time %.3f ms/picture\n" % (1000.0 * t_host / n_timed))
@@ -943,6 +955,10 @@ def main():
     ms_res = e0.elapsed_time(e1)
     ms_res_local = ms_res
     launches = ctx.launches() - launches0
+    if NOEV:
+        sys.stderr.write("no per-launch events: %.1f pictures/s\n" % (n_timed / (ms_res / 1000.0)))
+        ctx.close()
+        return
     n_me = 0
     for e, P, n in marks:
         stage_ms["me_sb_kernel"] += e[0].elapsed_time(e[1]); alg["me_sb_kernel"] += me_bytes(P); n_me += 1

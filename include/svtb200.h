@@ -522,6 +522,7 @@ int svtb200_me_best_blocks_dev(SvtB200Ctx *ctx, const SvtB200MeCuResult *me_dev,
  * svtb200_inter_predict_batch_dev, svtb200_txq_multi_dev, svtb200_coeff_pack_dev, svtb200_coeff_rate_multi_dev. */
 typedef struct SvtB200InterChain {
     int32_t                  after_queue;   /* SVTB200_STREAM_*: start behind everything queued there so far (the picture's motion estimation); -1: none */
+    int32_t                  on_queue;      /* SVTB200_STREAM_COMPUTE / _COMPUTE2 / _COMPUTE3: run the chain there (the selected queue is left as it was); -1: the selected queue */
     const SvtB200MeCuResult *me;            /* non-NULL: blocks := svtb200_me_best_blocks_dev(me) (n_blocks must be the tiling's count) */
     SvtB200InterBlock       *blocks;        /* DEVICE, n_blocks */
     int32_t                  n_blocks;

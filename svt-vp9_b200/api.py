@@ -508,7 +508,7 @@ class RateBatch(C.Structure):
 
 class InterChain(C.Structure):
     """SvtB200InterChain: the inter chain of one picture for svtb200_inter_chain_dev"""
-    _fields_ = [("after_queue", C.c_int32), ("me", C.c_void_p), ("blocks", C.c_void_p), ("n_blocks", C.c_int32), ("pic", PredPicture), ("desc", C.c_void_p),
+    _fields_ = [("after_queue", C.c_int32), ("on_queue", C.c_int32), ("me", C.c_void_p), ("blocks", C.c_void_p), ("n_blocks", C.c_int32), ("pic", PredPicture), ("desc", C.c_void_p),
                 ("tx", C.POINTER(TxBatch)), ("n_tx", C.c_int32), ("qrows", C.c_void_p), ("n_qrows", C.c_int32), ("stream", C.c_void_p), ("capacity", C.c_uint32),
                 ("offsets", C.c_void_p), ("rate", C.POINTER(RateBatch)), ("n_rate", C.c_int32), ("reads", C.c_uint64 * 3), ("n_reads", C.c_int32)]
 

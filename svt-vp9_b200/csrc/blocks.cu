@@ -63,6 +63,11 @@ extern "C" int svtb200_inter_chain_dev(SvtB200Ctx *c, const SvtB200InterChain *c
     std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     int rc;
+    struct Restore { SvtB200Ctx *c; cudaStream_t s; ~Restore() { c->stream = s; } } restore{c, c->stream}; /* (the lock is held throughout) */
+    if (ch->on_queue >= 0) {
+        if (ch->on_queue != SVTB200_STREAM_COMPUTE && ch->on_queue != SVTB200_STREAM_COMPUTE2 && ch->on_queue != SVTB200_STREAM_COMPUTE3) return SVTB200_EINVAL;
+        c->stream = svtb200_pick_stream(c, ch->on_queue);
+    }
     if (ch->after_queue >= 0) {
         if (ch->after_queue > SVTB200_STREAM_COMPUTE3) return SVTB200_EINVAL;
         cudaStream_t from = svtb200_pick_stream(c, ch->after_queue);
