@@ -11,7 +11,9 @@
  *       by (EbPictureAnalysisProcess.c, end of the kernel loop): that is the moment a picture's padded / decimated planes are final, a whole
  *       mini-GOP of look-ahead before motion estimation asks for them, so the upload is queued there instead of inside the first
  *       motion_estimate_sb() call of the picture.  The results objects are recognised by their system resource, learnt from the wrapped
- *       eb_vp9_picture_analysis_context_ctor() (EbPictureAnalysisProcess.c:46).  SVT_VP9_GPU_PREFETCH=1 turns it on (off by default: measured slower).
+ *       eb_vp9_picture_analysis_context_ctor() (EbPictureAnalysisProcess.c:46).  Off by default: SVT_VP9_GPU_PREFETCH=lock page-locks the picture's buffers there (background thread), =1 also uploads there; on
+ *       the 128-thread box neither beat the on-demand upload inside the picture's first ME call (the short clips of the bench are
+ *       dominated by first-touch costs: cudaMalloc + page-locking per pool object).
  *   teardown: eb_vp9_deinit_encoder() (Source/Lib/Codec/EbEncHandle.c:1711) is exported from here; the reference's own
  *       definition is kept under the name svtb200_real_eb_vp9_deinit_encoder (objcopy --redefine-sym on a COPY of the
  *       compiled object, oracle/build_ref.sh) and called after the GPU state of that encoder instance has been dropped.
@@ -234,6 +236,7 @@ static ResEntry g_res[MAX_RESIDENT];
 static pthread_once_t g_res_once = PTHREAD_ONCE_INIT;
 static void res_init(void) { for (int i = 0; i < MAX_RESIDENT; i++) pthread_mutex_init(&g_res[i].mu, NULL); }
 
+/* dev < 0: page-lock the object's buffers only (the background pass at the end of picture analysis) */
 static int ensure_resident(int dev, const EbPaReferenceObject *o, uint64_t poc, const void *inst, int want_quarter) {
     int idx = -1, fresh = 0;
     pthread_once(&g_res_once, res_init);
@@ -248,7 +251,7 @@ static int ensure_resident(int dev, const EbPaReferenceObject *o, uint64_t poc, 
     ResEntry *e = &g_res[idx];
     pthread_mutex_lock(&e->mu); /* only callers that need THIS picture wait here */
     int rc = SVTB200_OK;
-    if (!(e->valid[dev] && e->poc[dev] == poc && (e->has_q[dev] || !want_quarter))) {
+    if (dev < 0 ? !e->locked : !(e->valid[dev] && e->poc[dev] == poc && (e->has_q[dev] || !want_quarter))) {
         SvtB200Plane pl[3];
         svtb200_glue_pa_planes(o, pl);
         static int pagelock = -1; /* SVT_VP9_GPU_PAGELOCK=0: leave the reference's buffers pageable (staged copies, no page-locking cost) */
@@ -259,8 +262,10 @@ static int ensure_resident(int dev, const EbPaReferenceObject *o, uint64_t poc, 
                     svtb200_host_register((void *)pl[k].buf, (size_t)pl[k].stride * pl[k].padded_height) == SVTB200_OK) e->reg[k] = (void *)pl[k].buf;
             e->locked = 1;
         }
-        rc = svtb200_picture_upload(g_ctxs[dev], (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
-        if (rc == SVTB200_OK) { e->poc[dev] = poc; e->valid[dev] = 1; e->has_q[dev] = want_quarter; } else e->valid[dev] = 0;
+        if (dev >= 0) {
+            rc = svtb200_picture_upload(g_ctxs[dev], (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
+            if (rc == SVTB200_OK) { e->poc[dev] = poc; e->valid[dev] = 1; e->has_q[dev] = want_quarter; } else e->valid[dev] = 0;
+        }
     }
     pthread_mutex_unlock(&e->mu);
     return rc;
@@ -426,7 +431,7 @@ typedef struct { const EbPaReferenceObject *obj; uint64_t poc; const void *inst;
 static PrefetchNote    g_pf_ring[PREFETCH_RING];
 static unsigned        g_pf_head, g_pf_tail; /* g_mu */
 static pthread_cond_t  g_pf_cv = PTHREAD_COND_INITIALIZER;
-static int             g_pf_thread_started;
+static int             g_pf_thread_started, g_pf_mode = -1;
 
 static void *prefetch_thread(void *arg) {
     (void)arg;
@@ -440,7 +445,7 @@ static void *prefetch_thread(void *arg) {
         if (!live) continue;
         const double t0 = now_s();
         /* to the device that will run this picture's motion estimation; as a reference on other devices it is uploaded on demand */
-        if (ensure_resident((int)(n.poc % (uint64_t)g_ndev), n.obj, n.poc, n.inst, n.want_q) == SVTB200_OK) __atomic_add_fetch(&g_prefetched, 1, __ATOMIC_RELAXED);
+        if (ensure_resident(g_pf_mode == 2 ? (int)(n.poc % (uint64_t)g_ndev) : -1, n.obj, n.poc, n.inst, n.want_q) == SVTB200_OK) __atomic_add_fetch(&g_prefetched, 1, __ATOMIC_RELAXED);
         pthread_mutex_lock(&g_mu);
         g_t_prefetch += now_s() - t0;
         pthread_mutex_unlock(&g_mu);
@@ -449,9 +454,11 @@ static void *prefetch_thread(void *arg) {
 }
 
 EbErrorType __wrap_eb_vp9_post_full_object(EbObjectWrapper *w) {
-    static int enabled = -1;
-    if (enabled < 0) { const char *e = getenv("SVT_VP9_GPU_PREFETCH"); enabled = e && e[0] == '1'; } /* off unless asked for: see DESIGN.md section 5 */
-    if (enabled && !g_replay && w && w->system_resource_ptr && w->object_ptr) {
+    if (g_pf_mode < 0) { /* default "0": off; "lock": page-lock the picture's buffers at the end of picture analysis (background thread); "1": upload there */
+        const char *e = getenv("SVT_VP9_GPU_PREFETCH");
+        g_pf_mode = (e && e[0] == '1') ? 2 : (e && e[0] == 'l') ? 1 : 0;
+    }
+    if (g_pf_mode && !g_replay && w && w->system_resource_ptr && w->object_ptr) {
         const void *q = (const void *)w->system_resource_ptr->empty_queue;
         int is_pa = 0;
         for (int i = 0; i < MAX_PA_QUEUES; i++) is_pa |= g_pa_queues[i] && g_pa_queues[i] == q; /* written once at start-up, before any picture */
