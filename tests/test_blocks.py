@@ -222,3 +222,121 @@ def test_cuda_open_loop_partition():
             L.svtb200_dev_free(hd, d_me); L.svtb200_dev_free(hd, d_b)
     finally:
         ctx.close()
+
+
+@pytest.mark.gpu
+def test_cuda_inter_chain_equals_single_calls():
+    """svtb200_inter_chain_dev (partition -> block walk -> prediction -> transform batches -> packing -> rate in ONE call, on a chosen
+    queue behind another) against the same stages through their own entry points: every output buffer identical."""
+    import test_rate as TR
+    w, h = 384, 256
+    rng = np.random.default_rng(41)
+    T = H.vp9_tables()
+    refs = [_planes(rng, w, h, "smooth"), _planes(rng, w, h, "smooth")]
+    src = [np.ascontiguousarray(r[PAD if p == 0 else PAD // 2:(PAD if p == 0 else PAD // 2) + (h if p == 0 else h // 2),
+                                  PAD if p == 0 else PAD // 2:(PAD if p == 0 else PAD // 2) + (w if p == 0 else w // 2)]) for p, r in enumerate(refs[0])]
+    src = [np.clip(s.astype(int) + rng.integers(-12, 13, size=s.shape), 0, 255).astype(np.uint8) for s in src]
+    me = _synthetic_me(rng, w, h)
+    for k in ("x_mv_l0", "y_mv_l0", "x_mv_l1", "y_mv_l1"):
+        me[k] = rng.integers(-40, 41, size=len(me))
+    n_blk = (w // 32) * (h // 32)
+    rows = H.quant_rows([100])
+    ctx = api.Context(0)
+    ctx.register_scans(T)
+    ctx.register_rate_tables(T)
+    api._bind_txq(ctx.L)
+    api._bind_rate(ctx.L)
+    L, hd = ctx.L, ctx.h
+    dev = []
+
+    def up(a):
+        a = np.ascontiguousarray(a)
+        d = L.svtb200_dev_alloc(hd, max(a.nbytes, 16))
+        ctx.check(L.svtb200_memcpy_h2d(hd, d, a.ctypes.data, a.nbytes), "h2d")
+        dev.append(d)
+        return d
+
+    def down(d, like):
+        out = np.zeros_like(like)
+        ctx.check(L.svtb200_memcpy_d2h(hd, out.ctypes.data, d, out.nbytes), "d2h")
+        return out
+    try:
+        d_ref = {id(a): up(a) for l in refs for a in l}
+        d_src = [up(s) for s in src]
+        d_me, d_rows = up(me), up(rows)
+        d_tc = [up(T["token_costs_default"][ts]) for ts in range(4)]
+        passes = [(3, 32, 0), (2, 16, 1), (2, 16, 2)]
+        jobs, rblk = [], []
+        for ts, N, p in passes:
+            pw, ph = src[p].shape[1], src[p].shape[0]
+            by, bx = np.meshgrid(np.arange(0, ph, N), np.arange(0, pw, N), indexing="ij")
+            j = np.zeros(by.size, dtype=api.TX_JOB_DTYPE)
+            j["src_offset"] = j["pred_offset"] = j["recon_offset"] = by.ravel() * pw + bx.ravel()
+            j["flags"] = 1
+            rb = np.zeros(by.size, dtype=api.RATE_BLOCK_DTYPE)
+            rb["plane_type"], rb["is_inter"] = (1 if p else 0), 1
+            jobs.append(j); rblk.append(rb)
+        d_jobs, d_rblk = [up(j) for j in jobs], [up(r) for r in rblk]
+        n_tu, n_coef = sum(len(j) for j in jobs), sum(len(j) * N * N for j, (_, N, _) in zip(jobs, passes))
+        results = []
+        for variant in ("single", "chain"):
+            bufs = {"pred": [up(np.zeros_like(s)) for s in src], "rec": [up(np.zeros_like(s)) for s in src],
+                    "q": [up(np.zeros(len(j) * N * N, np.int16)) for j, (_, N, _) in zip(jobs, passes)],
+                    "dq": [up(np.zeros(len(j) * N * N, np.int16)) for j, (_, N, _) in zip(jobs, passes)],
+                    "eob": [up(np.zeros(len(j), np.uint16)) for j in jobs], "rate": [up(np.zeros(len(j), np.int32)) for j in jobs],
+                    "blk": up(np.zeros(n_blk, api.INTER_BLOCK_DTYPE)), "desc": up(np.zeros(3 * n_blk * 64, np.uint8)),
+                    "stream": up(np.zeros(n_coef, np.int16)), "off": up(np.zeros(n_tu + 1, np.uint32))}
+            pic = api.PredPicture()
+            pic.width, pic.height, pic.use_subpel_flag = w, h, 1
+            for l in range(2):
+                for p in range(3):
+                    a = refs[l][p]
+                    pic.ref[l][p] = d_ref[id(a)] + _pad_of(p) * a.shape[1] + _pad_of(p)
+                    pic.ref_stride[l][p] = a.shape[1]
+            for p in range(3):
+                pic.dst[p], pic.dst_stride[p] = bufs["pred"][p], src[p].shape[1]
+            tx = (api.TxBatch * 3)()
+            rt = (api.RateBatch * 3)()
+            for k, (ts, N, p) in enumerate(passes):
+                b = tx[k]
+                b.tx_size, b.n, b.jobs = ts, len(jobs[k]), d_jobs[k]
+                b.planes.src, b.planes.src_stride, b.planes.src_bytes = d_src[p], src[p].shape[1], src[p].nbytes
+                b.planes.pred, b.planes.pred_stride, b.planes.pred_bytes = bufs["pred"][p], src[p].shape[1], src[p].nbytes
+                b.planes.recon, b.planes.recon_stride, b.planes.recon_bytes = bufs["rec"][p], src[p].shape[1], src[p].nbytes
+                b.coeff, b.qcoeff, b.dqcoeff, b.eob = None, bufs["q"][k], bufs["dq"][k], bufs["eob"][k]
+                r = rt[k]
+                r.tx_size, r.n, r.qcoeff, r.eob, r.blocks, r.token_costs, r.rate = ts, len(jobs[k]), bufs["q"][k], bufs["eob"][k], d_rblk[k], d_tc[ts], bufs["rate"][k]
+            if variant == "single":
+                assert L.svtb200_me_best_blocks_dev(hd, d_me, w, h, bufs["blk"]) == n_blk
+                ctx.check(L.svtb200_inter_blocks_expand_dev(hd, bufs["blk"], n_blk, C.byref(pic), bufs["desc"]), "expand")
+                ctx.check(L.svtb200_inter_predict_batch_dev(hd, bufs["desc"], 3 * n_blk), "predict")
+                ctx.check(L.svtb200_txq_multi_dev(hd, tx, 3, d_rows, 1), "txq")
+                ctx.check(L.svtb200_coeff_pack_dev(hd, tx, 3, bufs["stream"], n_coef, bufs["off"]), "pack")
+                ctx.check(L.svtb200_coeff_rate_multi_dev(hd, rt, 3), "rate")
+            else:
+                ch = api.InterChain()
+                ch.after_queue, ch.on_queue = api.COMPUTE, api.COMPUTE2   # the chain on the second queue, behind what the first holds
+                ch.me, ch.blocks, ch.n_blocks, ch.pic, ch.desc = d_me, bufs["blk"], n_blk, pic, bufs["desc"]
+                ch.tx, ch.n_tx, ch.qrows, ch.n_qrows = tx, 3, d_rows, 1
+                ch.stream, ch.capacity, ch.offsets = bufs["stream"], n_coef, bufs["off"]
+                ch.rate, ch.n_rate, ch.n_reads = rt, 3, 0
+                l0 = ctx.launches()
+                ctx.check(L.svtb200_inter_chain_dev(hd, C.addressof(ch)), "chain")
+                assert ctx.launches() - l0 == 7
+            ctx.sync()
+            out = [down(bufs["pred"][p], src[p]) for p in range(3)] + [down(bufs["rec"][p], src[p]) for p in range(3)]
+            out += [down(bufs["q"][k], np.zeros(len(jobs[k]) * N * N, np.int16)) for k, (_, N, _) in enumerate(passes)]
+            out += [down(bufs["eob"][k], np.zeros(len(jobs[k]), np.uint16)) for k in range(3)] + [down(bufs["rate"][k], np.zeros(len(jobs[k]), np.int32)) for k in range(3)]
+            out += [down(bufs["off"], np.zeros(n_tu + 1, np.uint32)), down(bufs["stream"], np.zeros(n_coef, np.int16))]
+            results.append(out)
+        for a, b in zip(*results):
+            assert (a == b).all()
+        assert results[0][0].any() and results[0][9].any() and results[0][12].any()
+        # ... and the rates are the oracle's
+        for k, (ts, N, p) in enumerate(passes):
+            q = results[0][6 + k].reshape(len(jobs[k]), N * N)
+            assert (results[0][12 + k] == TR._oracle_rate(ts, np.ascontiguousarray(q), results[0][9 + k], rblk[k], T["token_costs_default"])).all()
+    finally:
+        for d in dev:
+            L.svtb200_dev_free(hd, d)
+        ctx.close()
