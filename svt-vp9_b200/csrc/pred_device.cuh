@@ -48,21 +48,50 @@ __device__ __forceinline__ uint32_t pred_clip8(int v) { return (uint32_t)(v < 0 
 __device__ static void pred_one(const uint8_t *src /* at the block's integer position */, int stride, int sx, int sy, int w, int h,
                                 uint8_t *win, uint8_t *tmp, uint8_t *res) {
     const int t = threadIdx.x;
+    /* rows are fetched as aligned 32-bit words and re-aligned with a funnel shift when the geometry allows it (block width a
+     * multiple of 4, word-aligned plane): a quarter of the load instructions of a byte loop.  The word path starts a filtered row at
+     * sample -4 instead of -3 and may read up to 3 bytes past the last sample the reference functions read -- inside the plane's
+     * padding (the motion vector clamp keeps the block within VP9_INTERP_EXTEND + block size of the picture, the padding is larger) */
+    const bool words = (w & 3) == 0;
     if (!sx && !sy) { /* eb_vp9_convolve_copy_c */
-        const uint32_t rw = pred_rcp(w);
-        for (int i = t; i < w * h; i += PRED_THREADS) {
-            const int r = pred_div(i, rw), c = i - r * w;
-            res[r * 64 + c] = __ldg(src + (ptrdiff_t)r * stride + c);
+        if (words) {
+            const int wq = w >> 2;
+            const uint32_t rwq = pred_rcp(wq);
+            for (int i = t; i < wq * h; i += PRED_THREADS) {
+                const int r = pred_div(i, rwq), c = i - r * wq;
+                const uintptr_t a = (uintptr_t)(src + (ptrdiff_t)r * stride + 4 * c);
+                const uint32_t *g = (const uint32_t *)(a & ~(uintptr_t)3);
+                const uint32_t sh = (uint32_t)(a & 3) * 8, lo = __ldg(g), hi = sh ? __ldg(g + 1) : 0u;
+                *(uint32_t *)(res + r * 64 + 4 * c) = __funnelshift_r(lo, hi, sh);
+            }
+        } else {
+            const uint32_t rw = pred_rcp(w);
+            for (int i = t; i < w * h; i += PRED_THREADS) {
+                const int r = pred_div(i, rw), c = i - r * w;
+                res[r * 64 + c] = __ldg(src + (ptrdiff_t)r * stride + c);
+            }
         }
         __syncthreads();
         return;
     }
     const int x_lo = sx ? -3 : 0, nx = sx ? w + 7 : w;
     const int y_lo = sy ? -3 : 0, ny = sy ? h + 7 : h;
-    const uint32_t rnx = pred_rcp(nx);
-    for (int i = t; i < nx * ny; i += PRED_THREADS) { /* only the samples the reference functions read */
-        const int r = pred_div(i, rnx), c = i - r * nx;
-        win[r * PRED_WP + c + x_lo + 4] = __ldg(src + (ptrdiff_t)(r + y_lo) * stride + c + x_lo);
+    if (words) {
+        const int xa = sx ? -4 : 0, nwr = sx ? (w >> 2) + 2 : (w >> 2); /* samples xa .. xa + 4 * nwr - 1 of every staged row */
+        const uint32_t rnw = pred_rcp(nwr);
+        for (int i = t; i < nwr * ny; i += PRED_THREADS) {
+            const int r = pred_div(i, rnw), c = i - r * nwr;
+            const uintptr_t a = (uintptr_t)(src + (ptrdiff_t)(r + y_lo) * stride + xa + 4 * c);
+            const uint32_t *g = (const uint32_t *)(a & ~(uintptr_t)3);
+            const uint32_t sh = (uint32_t)(a & 3) * 8, lo = __ldg(g), hi = sh ? __ldg(g + 1) : 0u;
+            *(uint32_t *)(win + r * PRED_WP + xa + 4 + 4 * c) = __funnelshift_r(lo, hi, sh);
+        }
+    } else {
+        const uint32_t rnx = pred_rcp(nx);
+        for (int i = t; i < nx * ny; i += PRED_THREADS) { /* only the samples the reference functions read */
+            const int r = pred_div(i, rnx), c = i - r * nx;
+            win[r * PRED_WP + c + x_lo + 4] = __ldg(src + (ptrdiff_t)(r + y_lo) * stride + c + x_lo);
+        }
     }
     __syncthreads();
     const int wq = (w + 3) >> 2;
