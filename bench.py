@@ -475,7 +475,7 @@ def encoder_record(local_rank, world, clip4k, budget_s=120.0, sync=None):
 
 
 def encoder_all_gpus_record(world, clip4k):
-    """ONE encoder handle on all the GPUs of the launch (SVT_VP9_GPU=0,1,..: pictures dealt to the devices by picture number): configs[2]
+    """ONE encoder handle on all the GPUs of the launch (SVT_VP9_GPU=0,1,..: pictures dealt to the devices mini-GOP by mini-GOP): configs[2]
     through the application, reference build against drop-in build.  Runs on rank 0 while the other ranks wait."""
     if not (os.path.exists(APP_REF) and os.path.exists(APP_B200)):
         return {"unavailable": "oracle/_ref applications not built"}
@@ -489,7 +489,7 @@ def encoder_all_gpus_record(world, clip4k):
                           {"SVT_VP9_GPU": ",".join(str(i) for i in range(world)), "SVT_VP9_GPU_REPORT": rep})
         return {"frames": n_frames, "gpus": world, "reference": ref, "b200": gpu, "b200_gpu_report": gpu_report(rep),
                 "bitstream_identical": bool(ref["md5"]) and ref["md5"] == gpu["md5"], "speedup": (gpu["fps"] / ref["fps"]) if ref["fps"] and gpu["fps"] else None,
-                "note": "one EbEncHandle pipeline, motion estimation and deblocking of its pictures dealt to %d GPUs by picture number (no exchange between devices)" % world}
+                "note": "one EbEncHandle pipeline, motion estimation and deblocking of its pictures dealt to %d GPUs mini-GOP by mini-GOP (no exchange between devices)" % world}
     finally:
         shutil.rmtree(d, ignore_errors=True)
 

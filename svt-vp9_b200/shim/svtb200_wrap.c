@@ -27,7 +27,7 @@
  * through to the reference functions (__real_*), so the library still works on a CPU-only box.
  *
  * Environment: SVT_VP9_GPU=<device index> (default 0) or a comma-separated list of devices ("0,1,2,3": ONE encoder, its pictures
- * dealt to the devices by picture number -- motion estimation is open loop, a picture needs only its own and its references' SOURCE
+ * dealt to the devices mini-GOP by mini-GOP -- motion estimation is open loop, a picture needs only its own and its references' SOURCE
  * planes, which are uploaded to the device that runs it; filtered pictures are dealt round-robin; no exchange between devices),
  * SVT_VP9_GPU=off disables the GPU path; SVT_VP9_GPU_REPORT=<file> counters at exit.  Measurement aids (tools / bench.py): SVT_VP9_ME_RECORD=<file> writes every picture's ME results to a table at exit;
  * SVT_VP9_ME_REPLAY=<file> serves motion estimation from such a table (no ME work at all: the speed the pipeline around the
@@ -356,7 +356,10 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
             __atomic_store_n(&s->state, 1, __ATOMIC_RELEASE);
             svtb200_glue_me_params(pcs, me, &s->P);
             s->n_sb = ((s->P.luma_width + 63) / 64) * ((s->P.luma_height + 63) / 64);
-            s->dev = (int)(pcs->picture_number % (uint64_t)g_ndev); /* pictures dealt to the devices by display number */
+            /* pictures dealt to the devices mini-GOP by mini-GOP (display order): the pictures of a mini-GOP reference each other, so a
+             * device mostly finds its references already resident (dealing single pictures made every device upload ~3 pictures per
+             * picture it ran) */
+            s->dev = (int)(((pcs->picture_number + ((uint64_t)1 << pcs->hierarchical_levels) - 1) >> pcs->hierarchical_levels) % (uint64_t)g_ndev);
             if (s->cap_sb < (size_t)s->n_sb) {
                 if (s->res) svtb200_host_free(s->res);
                 if (s->rcme) svtb200_host_free(s->rcme);
