@@ -7,9 +7,10 @@
  * cpu_baseline leg); nothing in the product path may call it.
  *
  * Parity pinning: this file is validated against the UNMODIFIED reference (oracle/_ref, built
- * from /root/reference by oracle/build_ref.sh) by tests/test_me_oracle_vs_ref.py and through the
- * fixtures under tests/golden/ that were dumped from the reference encoder by
- * oracle/ref_seam_dump.c.
+ * from /root/reference by oracle/build_ref.sh): inside real encodes by the seam check (oracle/ref_seam_check.c,
+ * oracle/run_seam_check.py), on whole pictures through the path driver (oracle/ref_path_driver.c,
+ * tests/test_ref_path_driver.py), and through the fixtures under tests/golden/ that were dumped from the
+ * reference encoder by the seam check's dump mode (oracle/make_golden.py; tests/test_me_oracle.py).
  *
  * Reference functions followed (paths relative to Source/Lib):
  *   motion_estimate_sb                Codec/EbMotionEstimation.c:4524-5305
