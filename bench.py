@@ -405,7 +405,21 @@ def run_encoder(app, yuv, out, w, h, n_frames, n_buffered, mode, tune, env_extra
     m2 = re.search(r"Total Encoding Time:\s*([0-9.]+)\s*ms", txt)
     md5 = hashlib.md5(open(out, "rb").read()).hexdigest() if os.path.exists(out) and os.path.getsize(out) else None
     return {"fps": float(m.group(1)) if m else None, "encode_ms": float(m2.group(1)) if m2 else None, "wall_s": round(wall, 2), "rc": rc, "md5": md5,
-            "tail": None if m else txt[-300:]}
+            "bytes": os.path.getsize(out) if os.path.exists(out) else 0, "tail": None if m else txt[-300:]}
+
+
+def bitstream_difference(a, b):
+    """None when the two files hold the same bytes; otherwise their sizes and the offset of the first differing byte (a file cut short by
+    the application's abort in its own teardown -- 3840x2160, SURVEY.md section 5 -- is a prefix of the complete one)."""
+    try:
+        x, y = np.fromfile(a, dtype=np.uint8), np.fromfile(b, dtype=np.uint8)
+    except OSError:
+        return {"missing": True}
+    k = min(x.size, y.size)
+    nz = np.flatnonzero(x[:k] != y[:k])
+    if x.size == y.size and not nz.size:
+        return None
+    return {"bytes": [int(x.size), int(y.size)], "first_difference_at": int(nz[0]) if nz.size else int(k)}
 
 
 def gpu_report(path):
@@ -450,6 +464,8 @@ def encoder_record(local_rank, world, clip4k, budget_s=120.0, sync=None):
                 sync()
                 gpus.append(run_encoder(APP_B200, yuv, os.path.join(d, "b200.ivf"), cw, ch, n_frames, n_buf, 8, 1,
                                         {"SVT_VP9_GPU": str(local_rank), "SVT_VP9_GPU_REPORT": rep}))
+                if gpus[-1]["md5"] != refs[-1]["md5"]:
+                    gpus[-1]["difference"] = bitstream_difference(os.path.join(d, "ref.ivf"), os.path.join(d, "b200.ivf"))
             if name != "1080p_m8":   # one more reference run after the drop-in run, so that the reference is never the only cold one
                 refs.append(run_encoder(APP_REF, yuv, os.path.join(d, "ref.ivf"), cw, ch, n_frames, n_buf, 8, 1))
             best = lambda runs: max(runs, key=lambda r: r["fps"] or 0.0)

@@ -133,6 +133,12 @@ int svtb200_picture_upload(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane 
  * on it. */
 int svtb200_picture_upload_luma(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane *full,
                                 int32_t quarter_pad, int32_t sixteenth_pad, int make_quarter);
+/* svtb200_picture_upload_luma from PAGEABLE host memory (the reference's picture pool, EbPaReferenceObject::input_padded_picture_ptr, as the
+ * encoder allocated it): the calling thread copies the picture area into one of a small ring of page-locked slots the context owns and the
+ * transfer runs from there, instead of page-locking every pool object on first sight.  Thread safe; calls for different pictures stage in
+ * parallel. */
+int svtb200_picture_upload_luma_staged(SvtB200Ctx *ctx, uint64_t pic_id, const SvtB200Plane *full,
+                                       int32_t quarter_pad, int32_t sixteenth_pad, int make_quarter);
 int svtb200_picture_release(SvtB200Ctx *ctx, uint64_t pic_id);
 /* Device-side descriptor of an uploaded plane (which: 0 full, 1 quarter, 2 sixteenth): buf is a DEVICE pointer with the
  * same stride / origin as the uploaded host plane -- for chaining svtb200_txq_batch_dev / svtb200_deblock_picture_dev

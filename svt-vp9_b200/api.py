@@ -145,6 +145,7 @@ def lib():
         L.svtb200_memcpy_d2h.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
         L.svtb200_picture_upload.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Plane), C.POINTER(Plane), C.POINTER(Plane)]
         L.svtb200_picture_upload_luma.argtypes = [C.c_void_p, C.c_uint64, C.POINTER(Plane), C.c_int32, C.c_int32, C.c_int]
+        L.svtb200_picture_upload_luma_staged.argtypes = L.svtb200_picture_upload_luma.argtypes
         L.svtb200_picture_release.argtypes = [C.c_void_p, C.c_uint64]
         L.svtb200_picture_touch.argtypes = [C.c_void_p, C.c_uint64]
         L.svtb200_memcpy_h2d_async.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t]
@@ -217,10 +218,11 @@ class Context:
         s = C.byref(sixteenth) if sixteenth is not None else None
         self.check(self.L.svtb200_picture_upload(self.h, pic_id, C.byref(full), q, s), "picture_upload")
 
-    def picture_upload_luma(self, pic_id, full, quarter_pad=32, sixteenth_pad=16, make_quarter=True):
-        """Only the picture area of the padded luma crosses PCIe; padding and both decimations are made on the device."""
-        self.check(self.L.svtb200_picture_upload_luma(self.h, pic_id, C.byref(full), quarter_pad, sixteenth_pad, int(make_quarter)),
-                   "picture_upload_luma")
+    def picture_upload_luma(self, pic_id, full, quarter_pad=32, sixteenth_pad=16, make_quarter=True, staged=False):
+        """Only the picture area of the padded luma crosses PCIe; padding and both decimations are made on the device.
+        staged: through the context's ring of page-locked slots (pageable caller memory)."""
+        f = self.L.svtb200_picture_upload_luma_staged if staged else self.L.svtb200_picture_upload_luma
+        self.check(f(self.h, pic_id, C.byref(full), quarter_pad, sixteenth_pad, int(make_quarter)), "picture_upload_luma")
 
     def picture_plane(self, pic_id, which):
         """Download one resident plane (0 full, 1 quarter, 2 sixteenth) -> (array (rows, stride), Plane descriptor)."""

@@ -5,6 +5,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <atomic>
 #include <map>
 #include <mutex>
 #include <string>
@@ -29,6 +30,14 @@ struct DevPicture {
     DevPlane    pl[3];            /* full, quarter, sixteenth */
     cudaEvent_t ready = nullptr;  /* recorded on the upload stream after the picture's copies / front-end kernels */
     cudaEvent_t used[3] = {nullptr, nullptr, nullptr}; /* one per compute queue: recorded after the last kernel on that queue that reads the picture */
+};
+
+#define SVTB200_STAGE_SLOTS 8
+struct StageSlot { /* svtb200_picture_upload_luma_staged: one page-locked picture area */
+    uint8_t    *buf = nullptr;
+    size_t      cap = 0;
+    cudaEvent_t done = nullptr; /* the transfer out of the slot has finished */
+    std::mutex  mu;
 };
 
 struct ScanTable {
@@ -56,6 +65,7 @@ struct SvtB200Ctx {
     void    *me_trace = nullptr; size_t me_trace_bytes = 0; int me_trace_enabled = 0;
     /* pinned staging */
     uint8_t *pin = nullptr; size_t pin_bytes = 0;
+    StageSlot stage[SVTB200_STAGE_SLOTS]; std::atomic<unsigned> stage_next{0};
     /* transform / quant */
     ScanTable scans[4][4];
     int16_t  *scan_nb[4][4] = {};  /* neighbour tables of the scans (rate estimation) */

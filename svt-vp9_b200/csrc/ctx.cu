@@ -50,6 +50,7 @@ void svtb200_destroy(SvtB200Ctx *c) {
     if (c->pred_desc) cudaFree(c->pred_desc);
     if (c->pred_read) cudaEventDestroy(c->pred_read);
     if (c->pin) cudaFreeHost(c->pin);
+    for (StageSlot &st : c->stage) { if (st.buf) cudaFreeHost(st.buf); if (st.done) cudaEventDestroy(st.done); }
     for (int a = 0; a < 4; a++) for (int b = 0; b < 4; b++) { if (c->scans[a][b].scan) cudaFree(c->scans[a][b].scan); if (c->scans[a][b].iscan) cudaFree(c->scans[a][b].iscan); if (c->scan_nb[a][b]) cudaFree(c->scan_nb[a][b]); }
     if (c->rate_tables) cudaFree(c->rate_tables);
     if (c->chain_ev) cudaEventDestroy(c->chain_ev);
@@ -278,11 +279,14 @@ static int alloc_plane(SvtB200Ctx *c, DevPlane *dst, int stride, int rows) {
     return 0;
 }
 
-int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *full, int32_t quarter_pad, int32_t sixteenth_pad,
-                                int make_quarter) {
-    if (!c || !full || !full->buf || full->stride <= 0 || full->padded_height <= 0 || quarter_pad < 0 || sixteenth_pad < 0) return SVTB200_EINVAL;
-    if ((full->stride & 3) || full->width <= 0 || full->height <= 0) return SVTB200_EINVAL;
-    std::lock_guard<std::recursive_mutex> g(c->mu);
+static int upload_luma_args_ok(const SvtB200Ctx *c, const SvtB200Plane *full, int32_t quarter_pad, int32_t sixteenth_pad) {
+    if (!c || !full || !full->buf || full->stride <= 0 || full->padded_height <= 0 || quarter_pad < 0 || sixteenth_pad < 0) return 0;
+    return !((full->stride & 3) || full->width <= 0 || full->height <= 0);
+}
+/* area / area_pitch: where the picture area's first sample is read from (the caller's plane itself, or a page-locked staging copy of it);
+ * the geometry of the device plane always follows 'full'.  Called with c->mu held. */
+static int upload_luma_locked(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *full, const uint8_t *area, size_t area_pitch, int32_t quarter_pad,
+                              int32_t sixteenth_pad, int make_quarter) {
     cudaSetDevice(c->device);
     DevPicture &p = c->pics[pic_id];
     int rc;
@@ -297,9 +301,7 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
     if ((rc = alloc_plane(c, f, dpitch, full->padded_height))) return rc;
     f->ox = SVTB200_DEV_PAD_L; f->oy = full->origin_y; f->w = full->width; f->h = full->height;
     /* only the picture area crosses PCIe; the padding is regenerated on the device */
-    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(f->buf + (size_t)f->oy * f->stride + f->ox, f->stride,
-                                            full->buf + (size_t)full->origin_y * full->stride + full->origin_x, full->stride, f->w, f->h,
-                                            cudaMemcpyHostToDevice, c->up));
+    SVTB200_CUDA_CHECK(c, cudaMemcpy2DAsync(f->buf + (size_t)f->oy * f->stride + f->ox, f->stride, area, area_pitch, f->w, f->h, cudaMemcpyHostToDevice, c->up));
     dim3 blk(128);
     pa_pad_full_kernel<<<dim3((f->stride / 4 + 127) / 128, f->rows), blk, 0, c->up>>>(f->buf, f->stride, f->ox, f->oy, f->w, f->h, f->rows, f->stride,
                                                                                      full->origin_x);
@@ -318,6 +320,42 @@ int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Pla
     }
     SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return upload_end(c, p);
+}
+
+int svtb200_picture_upload_luma(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *full, int32_t quarter_pad, int32_t sixteenth_pad,
+                                int make_quarter) {
+    if (!upload_luma_args_ok(c, full, quarter_pad, sixteenth_pad)) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    return upload_luma_locked(c, pic_id, full, full->buf + (size_t)full->origin_y * full->stride + full->origin_x, (size_t)full->stride, quarter_pad,
+                              sixteenth_pad, make_quarter);
+}
+
+/* The same from PAGEABLE host memory (the reference's picture pool as it is): the picture area is first copied, by the calling thread, into a
+ * slot of a small ring of page-locked buffers the context owns, and the DMA transfer runs from there.  Page-locking the caller's buffers
+ * instead (svtb200_host_register) costs ~1 ms per MB the first time each pool object is seen -- at 3840x2160 that was 10 ms per picture on
+ * clips as short as the pool is deep -- while the staging copy is a plain memcpy of the picture area (no padding) whenever a picture is
+ * uploaded.  Several threads may stage different pictures at the same time (one slot each); the context lock is taken only to queue the work. */
+int svtb200_picture_upload_luma_staged(SvtB200Ctx *c, uint64_t pic_id, const SvtB200Plane *full, int32_t quarter_pad, int32_t sixteenth_pad,
+                                       int make_quarter) {
+    if (!upload_luma_args_ok(c, full, quarter_pad, sixteenth_pad)) return SVTB200_EINVAL;
+    StageSlot &s = c->stage[c->stage_next.fetch_add(1) % SVTB200_STAGE_SLOTS];
+    std::lock_guard<std::mutex> sl(s.mu);
+    cudaSetDevice(c->device);
+    if (s.done) SVTB200_CUDA_CHECK(c, cudaEventSynchronize(s.done)); /* the transfer that last read this slot */
+    const size_t w = (size_t)full->width, h = (size_t)full->height;
+    if (s.cap < w * h) {
+        if (s.buf) cudaFreeHost(s.buf);
+        s.buf = nullptr; s.cap = 0;
+        if (cudaMallocHost((void **)&s.buf, w * h) != cudaSuccess) { cudaGetLastError(); c->err = "cudaMallocHost(staging slot) failed"; return SVTB200_ENOMEM; }
+        s.cap = w * h;
+    }
+    const uint8_t *src = full->buf + (size_t)full->origin_y * full->stride + full->origin_x;
+    for (size_t y = 0; y < h; y++) memcpy(s.buf + y * w, src + y * (size_t)full->stride, w);
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    const int rc = upload_luma_locked(c, pic_id, full, s.buf, w, quarter_pad, sixteenth_pad, make_quarter);
+    if (!s.done) SVTB200_CUDA_CHECK(c, cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming | cudaEventBlockingSync));
+    SVTB200_CUDA_CHECK(c, cudaEventRecord(s.done, c->up));
+    return rc;
 }
 
 int svtb200_picture_plane_dev(SvtB200Ctx *c, uint64_t pic_id, int which, SvtB200Plane *out) {

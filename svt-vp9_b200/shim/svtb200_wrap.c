@@ -65,6 +65,8 @@ static unsigned        g_lf_next;
 #define g_ctx_lf g_ctxs_lf[0]
 static int             g_state; /* 0 untried, 1 ready, -1 unavailable */
 static unsigned long   g_me_pictures, g_me_sbs, g_lf_pictures, g_fallbacks, g_replayed, g_prefetched;
+static unsigned long   g_uploads;
+static double          g_t_register, g_t_upcall; /* of g_t_resident: page-locking / inside the upload calls */
 static double          g_t_resident, g_t_me, g_t_lf, g_t_prefetch; /* seconds spent in uploads / waiting for ME results / svtb200_deblock_picture */
 static double now_s(void) { struct timespec t; clock_gettime(CLOCK_MONOTONIC, &t); return t.tv_sec + 1e-9 * t.tv_nsec; }
 
@@ -164,6 +166,7 @@ static void report(void) {
     for (int d = 0; d < g_ndev; d++) fprintf(f, "me_pictures_dev%d %lu\n", d, g_dev_pictures[d]);
     fprintf(f, "ms_upload %d\nms_me %d\nms_lf %d\nprefetched %lu\nms_prefetch %d\n", (int)(1e3 * g_t_resident), (int)(1e3 * g_t_me), (int)(1e3 * g_t_lf),
             g_prefetched, (int)(1e3 * g_t_prefetch));
+    fprintf(f, "uploads %lu\nms_pagelock %d\nms_upload_calls %d\n", g_uploads, (int)(1e3 * g_t_register), (int)(1e3 * g_t_upcall));
     fclose(f);
 }
 
@@ -251,21 +254,38 @@ static int ensure_resident(int dev, const EbPaReferenceObject *o, uint64_t poc, 
     ResEntry *e = &g_res[idx];
     pthread_mutex_lock(&e->mu); /* only callers that need THIS picture wait here */
     int rc = SVTB200_OK;
-    if (dev < 0 ? !e->locked : !(e->valid[dev] && e->poc[dev] == poc && (e->has_q[dev] || !want_quarter))) {
+    /* how a picture reaches the device (SVT_VP9_GPU_UPLOAD): "pageable" (default) = the three planes as they are, through the driver's own
+     * staging of pageable memory; "pagelock" = the same with each pool object page-locked the first time it is seen (asynchronous uploads,
+     * but ~1 ms per MB the first time: 10 ms per 4K picture on clips as short as the pool is deep); "staged" = only the picture area, copied by
+     * this thread into a ring of page-locked slots the library owns, padding and decimations made on the device
+     * (svtb200_picture_upload_luma_staged; measured slower than the driver's staging inside the loaded encoder). */
+    static int upmode = -1;
+    if (upmode < 0) {
+        const char *ev = getenv("SVT_VP9_GPU_UPLOAD"), *pl0 = getenv("SVT_VP9_GPU_PAGELOCK");
+        upmode = (ev && !strcmp(ev, "pagelock")) ? 1 : (ev && !strcmp(ev, "staged")) ? 0 : (pl0 && pl0[0] == '1') ? 1 : 2;
+    }
+    if (dev < 0 ? (upmode == 1 && !e->locked) : !(e->valid[dev] && e->poc[dev] == poc && (e->has_q[dev] || !want_quarter))) {
         SvtB200Plane pl[3];
         svtb200_glue_pa_planes(o, pl);
-        static int pagelock = -1; /* SVT_VP9_GPU_PAGELOCK=0: leave the reference's buffers pageable (staged copies, no page-locking cost) */
-        if (pagelock < 0) { const char *ev = getenv("SVT_VP9_GPU_PAGELOCK"); pagelock = !(ev && ev[0] == '0'); }
-        if (pagelock && (fresh || !e->locked)) { /* a buffer of the reference's pool, first time seen: page-lock it */
+        const double tr0 = now_s();
+        if (upmode == 1 && (fresh || !e->locked)) { /* a buffer of the reference's pool, first time seen: page-lock it */
             for (int k = 0; k < 3; k++)
                 if (pl[k].buf && pl[k].stride > 0 && pl[k].padded_height > 0 &&
                     svtb200_host_register((void *)pl[k].buf, (size_t)pl[k].stride * pl[k].padded_height) == SVTB200_OK) e->reg[k] = (void *)pl[k].buf;
             e->locked = 1;
         }
+        const double tr1 = now_s();
         if (dev >= 0) {
-            rc = svtb200_picture_upload(g_ctxs[dev], (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
+            rc = SVTB200_EINVAL;
+            if (upmode == 0) rc = svtb200_picture_upload_luma_staged(g_ctxs[dev], (uint64_t)(uintptr_t)o, &pl[0], pl[1].origin_x, pl[2].origin_x, want_quarter);
+            if (rc == SVTB200_EINVAL) rc = svtb200_picture_upload(g_ctxs[dev], (uint64_t)(uintptr_t)o, &pl[0], want_quarter ? &pl[1] : NULL, &pl[2]);
             if (rc == SVTB200_OK) { e->poc[dev] = poc; e->valid[dev] = 1; e->has_q[dev] = want_quarter; } else e->valid[dev] = 0;
         }
+        pthread_mutex_lock(&g_mu);
+        g_t_register += tr1 - tr0;
+        g_t_upcall += now_s() - tr1;
+        g_uploads += dev >= 0;
+        pthread_mutex_unlock(&g_mu);
     }
     pthread_mutex_unlock(&e->mu);
     return rc;

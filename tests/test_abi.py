@@ -44,8 +44,9 @@ def test_create_fails_loudly_without_a_gpu():
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("staged", [False, True], ids=["direct", "staged"])
 @pytest.mark.parametrize("w,h,hme1", [(640, 384, True), (200, 136, True), (456, 248, False)])
-def test_device_decimation_and_padding_match_host_front_end(w, h, hme1):
+def test_device_decimation_and_padding_match_host_front_end(w, h, hme1, staged):
     frames = importlib.import_module("svt-vp9_b200.frames")
     rng = np.random.default_rng(w)
     luma = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
@@ -56,7 +57,12 @@ def test_device_decimation_and_padding_match_host_front_end(w, h, hme1):
     poisoned[:, :frames.FULL_PAD] = 0xAA
     st_p = frames.plane_structs({**pl, "full": poisoned})
     ctx = api.Context(0)
-    ctx.picture_upload_luma(7, st_p[0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, hme1)
+    if staged:  # more uploads than the ring has slots: every slot is reused while its last transfer may still be in flight
+        junk_full = np.ascontiguousarray(poisoned[::-1])
+        junk = frames.plane_structs({**pl, "full": junk_full})
+        for k in range(12):
+            ctx.picture_upload_luma(100 + k, junk[0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, hme1, staged=True)
+    ctx.picture_upload_luma(7, st_p[0], frames.QUARTER_PAD, frames.SIXTEENTH_PAD, hme1, staged=staged)
     for which, key in ((0, "full"), (1, "quarter"), (2, "sixteenth")):
         if which == 1 and not hme1:
             continue
