@@ -58,7 +58,7 @@ gcc $CF -fcommon $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/r
 gcc -shared -o $OUT/libSvtVp9Enc_refdrv.so $OUT/obj/*.o $OUT/ref_path_driver.o -lpthread -lm -Wl,--no-undefined
 echo "build_ref: path driver ok"
 
-# ---- drop-in flavour: the same reference objects with the two seam functions bound to libsvtvp9_b200.so
+# ---- drop-in flavour: the same reference objects with the seam functions bound to libsvtvp9_b200.so (S1 / S2 always, S3 with SVT_VP9_GPU_ENCODE_PASS=1)
 # (svt-vp9_b200/shim/svtb200_wrap.c); used by the encoder-level parity test on the GPU box.
 # Shape of the reference's own library (Source/Lib/CMakeLists.txt / CMakeLists.txt:61): SONAME libSvtVp9Enc.so.1, symbol map
 # Source/API/EbApi.version (SVT_VP9_0 { global: Eb*; eb*; local: *; }) -- read where it lies at link time, not copied.
@@ -73,9 +73,11 @@ if [ -f $HERE/../svt-vp9_b200/libsvtvp9_b200.so ]; then
     esac
   done
   gcc $CF $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/../svt-vp9_b200/shim/svtb200_wrap.c -o $OUT/svtb200_wrap.o
-  gcc -shared -o $D/libSvtVp9Enc.so.1 $D/obj/*.o $OUT/svtb200_wrap.o -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm \
+  gcc $CF $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/../svt-vp9_b200/shim/svtb200_wrap_tx.c -o $OUT/svtb200_wrap_tx.o
+  gcc -shared -o $D/libSvtVp9Enc.so.1 $D/obj/*.o $OUT/svtb200_wrap.o $OUT/svtb200_wrap_tx.o -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm \
       -Wl,-soname,libSvtVp9Enc.so.1 -Wl,--version-script=$REF/Source/API/EbApi.version \
       -Wl,--wrap=motion_estimate_sb -Wl,--wrap=eb_vp9_loop_filter_frame -Wl,--wrap=eb_vp9_post_full_object -Wl,--wrap=eb_vp9_picture_analysis_context_ctor \
+      -Wl,--wrap=eb_vp9_idct32x32_add -Wl,--wrap=eb_vp9_iht16x16_add -Wl,--wrap=eb_vp9_iht8x8_add -Wl,--wrap=eb_vp9_idct4x4_add \
       -Wl,-rpath,'$ORIGIN/../../../svt-vp9_b200'
   gcc -std=gnu99 -O2 -w -I$OUT/inc -I$REF/Source/API $REF/Source/App/*.c -o $OUT/SvtVp9EncApp_b200 \
       -L$D -l:libSvtVp9Enc.so.1 -L$HERE/../svt-vp9_b200 -lsvtvp9_b200 -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN/dropin' -Wl,-rpath,'$ORIGIN/../../svt-vp9_b200'

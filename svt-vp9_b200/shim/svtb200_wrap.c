@@ -149,6 +149,11 @@ static void table_read(const char *path) {
     fclose(f);
 }
 
+/* svtb200_wrap_tx.c: seam S3 bound call by call (SVT_VP9_GPU_ENCODE_PASS=1) */
+void svtb200_tx_install(int device);
+void svtb200_tx_uninstall(void);
+void svtb200_tx_report(FILE *f);
+
 static unsigned long long launches_total(void) {
     unsigned long long n = 0;
     for (int d = 0; d < g_ndev; d++) n += svtb200_launch_count(g_ctxs[d]) + svtb200_launch_count(g_ctxs_lf[d]);
@@ -167,6 +172,7 @@ static void report(void) {
     fprintf(f, "ms_upload %d\nms_me %d\nms_lf %d\nprefetched %lu\nms_prefetch %d\n", (int)(1e3 * g_t_resident), (int)(1e3 * g_t_me), (int)(1e3 * g_t_lf),
             g_prefetched, (int)(1e3 * g_t_prefetch));
     fprintf(f, "uploads %lu\nms_pagelock %d\nms_upload_calls %d\n", g_uploads, (int)(1e3 * g_t_register), (int)(1e3 * g_t_upcall));
+    svtb200_tx_report(f);
     fclose(f);
 }
 
@@ -445,6 +451,10 @@ EbErrorType __wrap_eb_vp9_picture_analysis_context_ctor(EbPictureBufferDescInitD
         if (!known && fr >= 0) g_pa_queues[fr] = (const void *)out_fifo->queue_ptr;
         pthread_mutex_unlock(&g_mu);
     }
+    {   /* this constructor runs inside eb_vp9_init_encoder after the run-time dispatch tables were filled: the place to bind seam S3 */
+        const char *e = getenv("SVT_VP9_GPU");
+        if (!(e && !strcmp(e, "off"))) svtb200_tx_install(e ? atoi(e) : 0);
+    }
     return __real_eb_vp9_picture_analysis_context_ctor(init, denoise_flag, ctx, in_fifo, out_fifo, sb_total_count);
 }
 
@@ -609,6 +619,7 @@ EbErrorType eb_vp9_deinit_encoder(EbComponentType *svt_enc_component) {
         pthread_mutex_unlock(&g_mu);
         pthread_setcancelstate(cs, NULL);
     }
+    svtb200_tx_uninstall();
     report(); /* counters / recorded table now: the reference's own teardown aborts at 3840x2160, which skips destructors */
     return svtb200_real_eb_vp9_deinit_encoder(svt_enc_component);
 }

@@ -95,6 +95,38 @@ def test_encoder_with_gpu_hot_path_writes_the_reference_bitstream(w, h, n, mode)
         assert a == b, "bitstreams differ (%s)" % r
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("w,h,n,mode", [(320, 192, 10, 8), (256, 128, 6, 3)], ids=["320x192-m8", "256x128-m3"])
+def test_encoder_with_every_transform_call_on_the_gpu_writes_the_reference_bitstream(w, h, n, mode):
+    """SVT_VP9_GPU_ENCODE_PASS=1: seam S3 bound call by call (svt-vp9_b200/shim/svtb200_wrap_tx.c) -- every forward transform, quantiser
+    and inverse transform + reconstruction call of mode decision and of the encode pass (perform_coding_loop / perform_inv_trans_add,
+    Source/Lib/Codec/EbEncDecProcess.c:365-655) is one device batch of one block: all sizes, the ADST types of intra blocks (enc-mode 3), the
+    partial 32x32 transform, every eob the encoder produces.  Slow by construction (a PCIe round trip per call); the bitstream must not change."""
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "clip.yuv")
+        _write_yuv(yuv, w, h, n, 23 + mode)
+        a = _encode(APP_REF, yuv, os.path.join(d, "ref.ivf"), w, h, n, mode)
+        rep = os.path.join(d, "rep.txt")
+        b = _encode(APP_B200, yuv, os.path.join(d, "b200.ivf"), w, h, n, mode,
+                    {"SVT_VP9_GPU": "0", "SVT_VP9_GPU_ENCODE_PASS": "1", "SVT_VP9_GPU_REPORT": rep, "SVT_VP9_GPU_VERBOSE": "1"})
+        r = _report(rep)
+        assert r["state"] == 1 and r["fallbacks"] == 0 and r["tx_fallbacks"] == 0, r
+        assert r["tx_forward"] > 1000 and r["tx_quantize"] > 1000 and r["tx_inverse"] > 100, r   # the device served the transform calls
+        assert a == b, "bitstreams differ (%s)" % r
+
+
+def test_encode_pass_binding_without_a_gpu_leaves_the_reference_kernels_in_place():
+    with tempfile.TemporaryDirectory() as d:
+        yuv = os.path.join(d, "clip.yuv")
+        _write_yuv(yuv, 192, 128, 6, 9)
+        a = _encode(APP_REF, yuv, os.path.join(d, "ref.ivf"), 192, 128, 6, 8)
+        rep = os.path.join(d, "rep.txt")
+        b = _encode(APP_B200, yuv, os.path.join(d, "b200.ivf"), 192, 128, 6, 8, {"SVT_VP9_GPU": "off", "SVT_VP9_GPU_ENCODE_PASS": "1", "SVT_VP9_GPU_REPORT": rep})
+        assert a == b
+        r = _report(rep)
+        assert r["tx_forward"] == 0 and r["tx_quantize"] == 0 and r["tx_inverse"] == 0
+
+
 def _n_gpus():
     try:
         import torch
