@@ -264,6 +264,39 @@ int svtb200_zz_sad_picture(SvtB200Ctx *ctx, uint64_t cur_id, uint64_t prev_id, i
 int svtb200_zz_sad_picture_dev(SvtB200Ctx *ctx, uint64_t cur_id, uint64_t prev_id, int32_t luma_width, int32_t luma_height,
                                int32_t th_shift, uint8_t *scores_dev, uint32_t *sads_dev);
 
+/* ---- rest of the picture-analysis front end (noise filters / detection, edge maps) ----------------------------------------------
+ * The noise filters of picture_pre_processing_operations (Source/Lib/Codec/EbPictureAnalysisProcess.c:4191): eb_vp9_noise_extract_luma_weak
+ * (:1653), _luma_strong (:1450), _chroma_weak (:1575), _chroma_strong (:1498) as detect_input_picture_noise / denoise_input_picture apply
+ * them to every super-block row of a plane: get_filtered_types (:1403) with the cross (/8), gaussian (/16), gaussian (/16) and box (/9)
+ * kernels on every sample that is not on the plane's border; border samples are copied.  in / den: DEVICE pointers to the sample at (0,0)
+ * of a w x h plane (for the chroma kinds the chroma plane's own size); noise (luma weak only, may be NULL, geometry of den) receives
+ * clip(in - den, 0, 255). */
+#define SVTB200_NOISE_LUMA_WEAK 0
+#define SVTB200_NOISE_LUMA_STRONG 1
+#define SVTB200_NOISE_CHROMA_WEAK 2
+#define SVTB200_NOISE_CHROMA_STRONG 3
+int svtb200_noise_filter_dev(SvtB200Ctx *ctx, int kind, const uint8_t *in_dev, int32_t in_stride, int32_t w, int32_t h, uint8_t *den_dev,
+                             int32_t den_stride, uint8_t *noise_dev);
+/* detect_input_picture_noise() (:3512-3575) up to its picture-level decision: the weak luma filter of the whole picture into den, and per
+ * COMPLETE 64x64 super-block compute_variance64x64 (:408) of the noise samples (noise_var, raw) and of the denoised samples (den_var,
+ * >> 16), the flat-noise flag (den_var < den_th && noise_var > noise_th: FLAT_MAX_VAR and NOISE_MIN_LEVEL_0 / _1 of the reference,
+ * sb_flat_noise_array), and totals[0] = sum of noise_var >> 16, totals[1] = number of complete super-blocks (pic_noise_variance =
+ * totals[0] / totals[1]; the class thresholds on it stay with the host).  Incomplete super-blocks: zeros.  All pointers DEVICE memory. */
+int svtb200_noise_detect_dev(SvtB200Ctx *ctx, const uint8_t *in_dev, int32_t in_stride, int32_t w, int32_t h, uint8_t *den_dev, int32_t den_stride,
+                             uint64_t noise_th, uint64_t den_th, uint64_t *noise_var_dev, uint64_t *den_var_dev, uint8_t *flat_dev, uint64_t *totals_dev);
+/* edge_detection() (:4545) on the block statistics svtb200_block_stats_picture_dev leaves ([n_sb][85]): per super-block edge_block_num
+ * (64x64 variance above 70 % of the picture's average), isolated_high_intensity_sb (the 9x9 neighbourhoods of bright super-blocks beside
+ * dark ones, with the reference's raster-order clear-then-mark semantics) and sharp_edge_sb_flag; pic_avg_variance
+ * (compute_picture_spatial_statistics, :4827) is produced on the way. */
+int svtb200_edge_detection_dev(SvtB200Ctx *ctx, const uint8_t *y_mean_dev, const uint16_t *variance_dev, int32_t luma_width, int32_t luma_height,
+                               uint8_t *edge_block_num_dev, uint8_t *isolated_dev, uint8_t *sharp_edge_dev, uint16_t *pic_avg_variance_dev);
+/* edge_detection_mean_luma_chroma16x16() (:4434): edge_cu of the sixteen 16x16 blocks of every super-block ([n_sb][16], raster order) from
+ * the 16x16 means of luma ([n_sb][85]) and chroma ([n_sb][21], svtb200_chroma_block_mean_dev); logo_flags[sb] = SbParams::potential_logo_sb
+ * (a function of the picture size, EbSequenceControlSet.c:332-400; completeness is derived here); zeros unless picture_number is a multiple
+ * of 4.  max_grad_dev: one uint32 of device scratch (holds the picture's largest gradient afterwards). */
+int svtb200_edge_cu_dev(SvtB200Ctx *ctx, const uint8_t *y_mean_dev, const uint8_t *cb_mean_dev, const uint8_t *cr_mean_dev, const uint8_t *logo_flags_dev,
+                        int32_t luma_width, int32_t luma_height, uint64_t picture_number, uint8_t *edge_cu_dev, uint32_t *max_grad_dev);
+
 /* The five 2-entry (DC, AC) rows quantize_b reads (Source/Lib/VPX/quantize.c:112):
  * zbin, round, quant, quant_shift, dequant -- produced by eb_vp9_init_quantizer
  * (Source/Lib/VPX/vp9_quantize.c:206) on the reference host. */

@@ -764,3 +764,103 @@ void refdrv_pool_free(void *h) {
     for (int i = 0; i < p->n_threads; i++) { refdrv_pred_free(p->pred[i]); free(p->rate[i]); }
     free(p->tasks); free(p->tu_left); free(p->me_left); free(p->pred_left); free(p->th); free(p->me); free(p->pred); free(p->rate); free(p);
 }
+
+/* ------------------------------------------------------------------------------------------------ picture analysis: noise filters, edge maps */
+#include "EbPictureAnalysisProcess.h" /* the reference's filter dispatch tables (static, one copy per includer) */
+
+/* The noise filters of the picture-analysis stage exactly as detect_input_picture_noise / denoise_input_picture call them
+ * (EbPictureAnalysisProcess.c:3538-3546, :3384-3440): per super-block row the dispatch-table entry at the row's first super-block, then the
+ * plain-C function on the last super-block column when that one is partial.  kind: 0 luma weak (+ noise), 1 luma strong, 2 chroma weak,
+ * 3 chroma strong; flavour: 0 = plain C entries, 1 = AVX2 entries.  plane / den: the sample at (0,0); w x h = the PLANE's size.
+ * noise (kind 0): h rows of den_stride bytes -- the reference's noise buffer is one super-block row tall, each row is copied out after it was made. */
+int refdrv_noise_filter(int kind, int flavour, uint8_t *plane, int stride, int w, int h, uint8_t *den, int den_stride, uint8_t *noise) {
+    EbPictureBufferDesc in, dn, nz;
+    memset(&in, 0, sizeof(in)); memset(&dn, 0, sizeof(dn)); memset(&nz, 0, sizeof(nz));
+    const int chroma = kind >= 2, lw = chroma ? 2 * w : w, lh = chroma ? 2 * h : h;
+    in.width = dn.width = nz.width = (uint16_t)lw; in.height = dn.height = nz.height = (uint16_t)lh;
+    in.buffer_y = in.buffer_cb = in.buffer_cr = plane; in.stride_y = in.stride_cb = in.stride_cr = (uint16_t)stride;
+    dn.buffer_y = dn.buffer_cb = dn.buffer_cr = den;   dn.stride_y = dn.stride_cb = dn.stride_cr = (uint16_t)den_stride;
+    uint8_t *nbuf = NULL;
+    if (kind == 0) { nbuf = (uint8_t *)calloc((size_t)den_stride * 66 + 64, 1); nz.buffer_y = nbuf; nz.stride_y = (uint16_t)den_stride; }
+    for (int sy = 0; sy < lh; sy += 64)
+        for (int sx = 0; sx < lw; sx += 64) {
+            const uint32_t oy = (uint32_t)(chroma ? sy / 2 : sy), ox = (uint32_t)(chroma ? sx / 2 : sx);
+            const int last_partial = sx + 64 > lw;
+            switch (kind) {
+            case 0:
+                if (sx == 0) weak_luma_filter_func_ptr_array[flavour](&in, &dn, &nz, oy, ox);
+                if (last_partial) eb_vp9_noise_extract_luma_weak(&in, &dn, &nz, oy, ox);
+                break;
+            case 1:
+                if (sx == 0) strong_luma_filter_func_ptr_array[flavour](&in, &dn, oy, ox);
+                if (last_partial) eb_vp9_noise_extract_luma_strong(&in, &dn, oy, ox);
+                break;
+            case 2:
+                if (sx == 0) weak_chroma_filter_func_ptr_array[flavour](&in, &dn, oy, ox);
+                if (last_partial) eb_vp9_noise_extract_chroma_weak(&in, &dn, oy, ox);
+                break;
+            default:
+                if (sx == 0) strong_chroma_filter_func_ptr_array[flavour](&in, &dn, oy, ox);
+                if (last_partial) eb_vp9_noise_extract_chroma_strong(&in, &dn, oy, ox);
+            }
+            if (kind == 0 && noise && sx + 64 >= lw) /* the row is complete */
+                for (int y = 0; y < 64 && sy + y < lh; y++) memcpy(noise + (size_t)(sy + y) * den_stride, nbuf + (size_t)y * den_stride, (size_t)lw);
+        }
+    free(nbuf);
+    return 0;
+}
+
+static SequenceControlSet *pa_scs(int w, int h, const uint8_t *logo_flags) {
+    SequenceControlSet *scs = (SequenceControlSet *)calloc(1, sizeof(SequenceControlSet));
+    const int sbs_w = (w + 63) / 64, sbs_h = (h + 63) / 64;
+    scs->luma_width = (uint16_t)w; scs->luma_height = (uint16_t)h; scs->sb_total_count = (uint16_t)(sbs_w * sbs_h);
+    scs->sb_params_array = (SbParams *)calloc((size_t)sbs_w * sbs_h, sizeof(SbParams));
+    for (int i = 0; i < sbs_w * sbs_h; i++) {
+        SbParams *p = &scs->sb_params_array[i];
+        p->horizontal_index = (uint8_t)(i % sbs_w); p->vertical_index = (uint8_t)(i / sbs_w);
+        p->origin_x = (uint16_t)((i % sbs_w) * 64); p->origin_y = (uint16_t)((i / sbs_w) * 64);
+        p->is_complete_sb = p->origin_x + 64 <= w && p->origin_y + 64 <= h;
+        p->potential_logo_sb = logo_flags ? logo_flags[i] : 0;
+    }
+    return scs;
+}
+
+/* edge_detection (EbPictureAnalysisProcess.c:4545) on given block statistics */
+int refdrv_edge_detection(const uint8_t *y_mean, const uint16_t *variance, int w, int h, int pic_avg_variance, uint8_t *edge_block_num, uint8_t *isolated,
+                          uint8_t *sharp_edge) {
+    SequenceControlSet *scs = pa_scs(w, h, NULL);
+    PictureParentControlSet *pcs = (PictureParentControlSet *)calloc(1, sizeof(PictureParentControlSet));
+    const int n = scs->sb_total_count;
+    pcs->sb_total_count = (uint16_t)n; pcs->pic_avg_variance = (uint16_t)pic_avg_variance;
+    pcs->variance = (uint16_t **)calloc(n, sizeof(void *)); pcs->y_mean = (uint8_t **)calloc(n, sizeof(void *));
+    for (int i = 0; i < n; i++) { pcs->variance[i] = (uint16_t *)variance + (size_t)i * 85; pcs->y_mean[i] = (uint8_t *)y_mean + (size_t)i * 85; }
+    pcs->edge_results_ptr = (EdgeSbResults *)calloc(n, sizeof(EdgeSbResults));
+    pcs->sharp_edge_sb_flag = (uint8_t *)calloc(n, 1);
+    edge_detection(scs, pcs);
+    for (int i = 0; i < n; i++) { edge_block_num[i] = pcs->edge_results_ptr[i].edge_block_num; isolated[i] = pcs->edge_results_ptr[i].isolated_high_intensity_sb; sharp_edge[i] = pcs->sharp_edge_sb_flag[i]; }
+    free(pcs->edge_results_ptr); free(pcs->sharp_edge_sb_flag); free(pcs->variance); free(pcs->y_mean); free(pcs); free(scs->sb_params_array); free(scs);
+    return 0;
+}
+
+/* edge_detection_mean_luma_chroma16x16 (:4434); logo_flags[sb] = SbParams::potential_logo_sb (is_complete_sb comes from the picture size) */
+int refdrv_edge_cu(const uint8_t *y_mean, const uint8_t *cb_mean, const uint8_t *cr_mean, const uint8_t *logo_flags, int w, int h, uint64_t picture_number,
+                   uint8_t *edge_cu) {
+    void edge_detection_mean_luma_chroma16x16(SequenceControlSet *, PictureParentControlSet *, PictureAnalysisContext *, uint32_t);
+    SequenceControlSet *scs = pa_scs(w, h, logo_flags);
+    PictureParentControlSet *pcs = (PictureParentControlSet *)calloc(1, sizeof(PictureParentControlSet));
+    PictureAnalysisContext *pa = (PictureAnalysisContext *)calloc(1, sizeof(PictureAnalysisContext));
+    const int n = scs->sb_total_count;
+    pcs->sb_total_count = (uint16_t)n; pcs->picture_number = picture_number;
+    pcs->y_mean = (uint8_t **)calloc(n, sizeof(void *)); pcs->cb_mean = (uint8_t **)calloc(n, sizeof(void *)); pcs->cr_mean = (uint8_t **)calloc(n, sizeof(void *));
+    pa->grad = (uint16_t **)calloc(n, sizeof(void *));
+    for (int i = 0; i < n; i++) {
+        pcs->y_mean[i] = (uint8_t *)y_mean + (size_t)i * 85; pcs->cb_mean[i] = (uint8_t *)cb_mean + (size_t)i * 21; pcs->cr_mean[i] = (uint8_t *)cr_mean + (size_t)i * 21;
+        pa->grad[i] = (uint16_t *)calloc(PA_BLOCK_MAX_COUNT, sizeof(uint16_t));
+    }
+    pcs->sb_stat_array = (SbStat *)calloc(n, sizeof(SbStat));
+    edge_detection_mean_luma_chroma16x16(scs, pcs, pa, (uint32_t)n);
+    for (int i = 0; i < n; i++) for (int b = 0; b < 16; b++) edge_cu[(size_t)i * 16 + b] = pcs->sb_stat_array[i].cu_stat_array[5 + b].edge_cu;
+    for (int i = 0; i < n; i++) free(pa->grad[i]);
+    free(pa->grad); free(pa); free(pcs->sb_stat_array); free(pcs->y_mean); free(pcs->cb_mean); free(pcs->cr_mean); free(pcs); free(scs->sb_params_array); free(scs);
+    return 0;
+}

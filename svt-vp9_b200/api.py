@@ -170,6 +170,11 @@ def lib():
         L.svtb200_inter_blocks_expand_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.POINTER(PredPicture), C.c_void_p]
         L.svtb200_me_best_blocks_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
         L.svtb200_inter_chain_dev.argtypes = [C.c_void_p, C.c_void_p]
+        L.svtb200_noise_filter_dev.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_void_p]
+        L.svtb200_noise_detect_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32, C.c_uint64, C.c_uint64,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.svtb200_edge_detection_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.svtb200_edge_cu_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint64, C.c_void_p, C.c_void_p]
         L.svtb200_chroma_block_mean_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         L.svtb200_chroma_histogram_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.svtb200_full_distortion_batch_dev.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]

@@ -1,0 +1,71 @@
+/* pa_noise.cu -- rest of the picture-analysis front end: the noise filters and noise-detection statistics of
+ * picture_pre_processing_operations (Source/Lib/Codec/EbPictureAnalysisProcess.c:1403-1760, :3512-3560) and the two edge maps of
+ * compute_picture_spatial_statistics (edge_detection :4545, edge_detection_mean_luma_chroma16x16 :4434).  See include/svtb200.h. */
+#include "common.cuh"
+
+#include "pa_noise_kernel.cuh"
+
+extern "C" {
+
+int svtb200_noise_filter_dev(SvtB200Ctx *c, int kind, const uint8_t *in, int32_t in_stride, int32_t w, int32_t h, uint8_t *den, int32_t den_stride, uint8_t *noise) {
+    if (!c || !in || !den || kind < 0 || kind > 3 || w < 3 || h < 3 || in_stride < w || den_stride < w || (noise && kind != SVTB200_NOISE_LUMA_WEAK)) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    const dim3 grid((w + 511) / 512, h), blk(128);
+    if (kind == SVTB200_NOISE_LUMA_WEAK) noise_filter_kernel<0><<<grid, blk, 0, c->stream>>>(in, in_stride, w, h, den, den_stride, noise);
+    else if (kind == SVTB200_NOISE_CHROMA_STRONG) noise_filter_kernel<6><<<grid, blk, 0, c->stream>>>(in, in_stride, w, h, den, den_stride, nullptr);
+    else noise_filter_kernel<4><<<grid, blk, 0, c->stream>>>(in, in_stride, w, h, den, den_stride, nullptr); /* luma strong, chroma weak */
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
+int svtb200_noise_detect_dev(SvtB200Ctx *c, const uint8_t *in, int32_t in_stride, int32_t w, int32_t h, uint8_t *den, int32_t den_stride, uint64_t noise_th,
+                             uint64_t den_th, uint64_t *noise_var, uint64_t *den_var, uint8_t *flat, uint64_t *totals) {
+    if (!c || !in || !den || !noise_var || !den_var || !flat || !totals || w < 3 || h < 3 || in_stride < w || den_stride < w) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    NoiseDetArgs A;
+    A.in = in; A.is = in_stride; A.w = w; A.h = h; A.den = den; A.ds = den_stride; A.sbs_w = (w + 63) / 64;
+    A.noise_th = noise_th; A.den_th = den_th;
+    A.noise_var = (unsigned long long *)noise_var; A.den_var = (unsigned long long *)den_var; A.totals = (unsigned long long *)totals; A.flat = flat;
+    SVTB200_CUDA_CHECK(c, cudaMemsetAsync(totals, 0, 16, c->stream));
+    noise_detect_kernel<<<A.sbs_w * ((h + 63) / 64), 256, 0, c->stream>>>(A);
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
+int svtb200_edge_detection_dev(SvtB200Ctx *c, const uint8_t *y_mean, const uint16_t *variance, int32_t w, int32_t h, uint8_t *edge_block_num, uint8_t *isolated,
+                               uint8_t *sharp_edge, uint16_t *pic_avg_variance) {
+    if (!c || !y_mean || !variance || !edge_block_num || !isolated || !sharp_edge || !pic_avg_variance || w <= 0 || h <= 0) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    const int sbs_w = (w + 63) / 64, sbs_h = (h + 63) / 64, n = sbs_w * sbs_h;
+    pa_avg_variance_kernel<<<1, 1024, 0, c->stream>>>(variance, n, pic_avg_variance);
+    edge_detection_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(y_mean, variance, sbs_w, sbs_h, pic_avg_variance, edge_block_num, isolated, sharp_edge);
+    c->launches += 2;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
+int svtb200_edge_cu_dev(SvtB200Ctx *c, const uint8_t *y_mean, const uint8_t *cb_mean, const uint8_t *cr_mean, const uint8_t *logo_flags, int32_t w, int32_t h,
+                        uint64_t picture_number, uint8_t *edge_cu, uint32_t *max_grad) {
+    if (!c || !y_mean || !cb_mean || !cr_mean || !logo_flags || !edge_cu || !max_grad || w <= 0 || h <= 0) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    const int sbs_w = (w + 63) / 64, n = sbs_w * ((h + 63) / 64);
+    if (picture_number & 3) { /* "the values are calculated for every 4th frame" (:4441); the others get zeros */
+        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(edge_cu, 0, (size_t)n * 16, c->stream));
+        return SVTB200_OK;
+    }
+    SVTB200_CUDA_CHECK(c, cudaMemsetAsync(max_grad, 0, 4, c->stream));
+    const int blocks = (n * 16 + 255) / 256;
+    edge_cu_kernel<0><<<blocks, 256, 0, c->stream>>>(y_mean, cb_mean, cr_mean, logo_flags, w, h, sbs_w, n, max_grad, edge_cu);
+    edge_cu_kernel<1><<<blocks, 256, 0, c->stream>>>(y_mean, cb_mean, cr_mean, logo_flags, w, h, sbs_w, n, max_grad, edge_cu);
+    c->launches += 2;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
+} /* extern "C" */

@@ -1,0 +1,168 @@
+/* pa_noise_kernel.cuh -- device code of pa_noise.cu (noise filters / noise detection statistics / edge maps of the picture-analysis
+ * stage); a header of its own so that tests/emu/pa_emu.cpp can run the same source on the CPU. */
+#ifndef SVTB200_PA_NOISE_KERNEL_CUH
+#define SVTB200_PA_NOISE_KERNEL_CUH
+#include <stdint.h>
+#include <stddef.h>
+
+/* get_filtered_types (:1403) on the sample at p: type 0 = cross (1 1 4 1 1) / 8, 4 = 3x3 gaussian / 16, 6 = 3x3 box (4 * sum / 36) */
+template <int TYPE>
+__device__ __forceinline__ uint32_t nz_filtered(const uint8_t *p, int s) {
+    const uint32_t c = __ldg(p), n = __ldg(p - s), so = __ldg(p + s), w = __ldg(p - 1), e = __ldg(p + 1);
+    if (TYPE == 0) return (n + w + 4 * c + e + so) >> 3;
+    const uint32_t nw = __ldg(p - s - 1), ne = __ldg(p - s + 1), sw = __ldg(p + s - 1), se = __ldg(p + s + 1);
+    if (TYPE == 4) return (nw + ne + sw + se + 2 * (n + w + e + so) + 4 * c) >> 4;
+    return (4 * (nw + n + ne + w + c + e + sw + so + se)) / 36; /* <= 255 */
+}
+
+/* one thread per four horizontally adjacent samples; border samples of the plane are copied, their noise is 0 */
+template <int TYPE>
+__global__ void __launch_bounds__(128) noise_filter_kernel(const uint8_t *in, int is, int w, int h, uint8_t *den, int ds, uint8_t *noise) {
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4, y = blockIdx.y;
+    if (x0 >= w) return;
+    const bool row_inner = y > 0 && y < h - 1;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int x = x0 + k;
+        if (x >= w) break;
+        const uint8_t *p = in + (size_t)y * is + x;
+        const uint32_t v = __ldg(p);
+        const bool inner = row_inner && x > 0 && x < w - 1;
+        const uint32_t d = inner ? nz_filtered<TYPE>(p, is) : v;
+        den[(size_t)y * ds + x] = (uint8_t)d;
+        if (noise) noise[(size_t)y * ds + x] = (uint8_t)(inner && v > d ? v - d : 0);
+    }
+}
+
+/* ---- detect_input_picture_noise: weak filter + the 64x64 variances of noise and denoised samples, one CTA per super-block ---- */
+struct NoiseDetArgs {
+    const uint8_t *in; int32_t is, w, h;
+    uint8_t *den; int32_t ds;
+    int32_t sbs_w;
+    unsigned long long noise_th, den_th;
+    unsigned long long *noise_var, *den_var, *totals;
+    uint8_t *flat;
+};
+__global__ void __launch_bounds__(256) noise_detect_kernel(const NoiseDetArgs A) {
+    __shared__ uint8_t den_s[64][64 + 4], nz_s[64][64 + 4];
+    __shared__ unsigned long long m_s[2][64], q_s[2][64]; /* [noise, denoised][8x8 block]: 8.8 means, 16.16 means of squares */
+    const int sb = blockIdx.x, sx = (sb % A.sbs_w) * 64, sy = (sb / A.sbs_w) * 64, t = threadIdx.x;
+    const bool complete = sx + 64 <= A.w && sy + 64 <= A.h;
+    for (int i = t; i < 4096; i += 256) {
+        const int y = i >> 6, x = i & 63, px = sx + x, py = sy + y;
+        if (px >= A.w || py >= A.h) continue;
+        const uint8_t *p = A.in + (size_t)py * A.is + px;
+        const uint32_t v = __ldg(p);
+        const bool inner = py > 0 && py < A.h - 1 && px > 0 && px < A.w - 1;
+        const uint32_t d = inner ? nz_filtered<0>(p, A.is) : v;
+        A.den[(size_t)py * A.ds + px] = (uint8_t)d;
+        den_s[y][x] = (uint8_t)d;
+        nz_s[y][x] = (uint8_t)(inner && v > d ? v - d : 0);
+    }
+    if (!complete) { /* "do it only for complete 64x64 blocks" (:3549) */
+        if (t == 0) { A.noise_var[sb] = 0; A.den_var[sb] = 0; A.flat[sb] = 0; }
+        return;
+    }
+    __syncthreads();
+    if (t < 128) { /* 8x8 sums of rows 0, 2, 4, 6 (eb_vp9_compute_sub_mean8x8 / subd_mean_of_squared_values8x8) */
+        const int which = t >> 6, b = t & 63, bx = (b & 7) * 8, by = (b >> 3) * 8;
+        uint32_t sum = 0, sq = 0;
+#pragma unroll
+        for (int r = 0; r < 8; r += 2)
+#pragma unroll
+            for (int k = 0; k < 8; k++) { const uint32_t v = which ? den_s[by + r][bx + k] : nz_s[by + r][bx + k]; sum += v; sq += v * v; }
+        m_s[which][b] = (unsigned long long)sum << 3;
+        q_s[which][b] = (unsigned long long)sq << 11;
+    }
+    __syncthreads();
+    if (t < 2) { /* quadrant averages up to 64x64 (compute_variance64x64, :408) */
+        unsigned long long m16[16], q16[16], m32[4], q32[4];
+        const unsigned long long *m = m_s[t], *q = q_s[t];
+        for (int i = 0; i < 16; i++) { const int a = (2 * (i >> 2)) * 8 + 2 * (i & 3); m16[i] = (m[a] + m[a + 1] + m[a + 8] + m[a + 9]) >> 2; q16[i] = (q[a] + q[a + 1] + q[a + 8] + q[a + 9]) >> 2; }
+        for (int i = 0; i < 4; i++) { const int a = (2 * (i >> 1)) * 4 + 2 * (i & 1); m32[i] = (m16[a] + m16[a + 1] + m16[a + 4] + m16[a + 5]) >> 2; q32[i] = (q16[a] + q16[a + 1] + q16[a + 4] + q16[a + 5]) >> 2; }
+        const unsigned long long m64 = (m32[0] + m32[1] + m32[2] + m32[3]) >> 2, q64 = (q32[0] + q32[1] + q32[2] + q32[3]) >> 2;
+        m_s[t][0] = q64 - m64 * m64;
+    }
+    __syncthreads();
+    if (t == 0) {
+        const unsigned long long nv = m_s[0][0], dv = m_s[1][0] >> 16;
+        A.noise_var[sb] = nv; A.den_var[sb] = dv;
+        A.flat[sb] = dv < A.den_th && nv > A.noise_th;
+        atomicAdd(&A.totals[0], nv >> 16);
+        atomicAdd(&A.totals[1], 1ull);
+    }
+}
+
+/* ---- edge_detection (:4545) ---- */
+__global__ void __launch_bounds__(1024) pa_avg_variance_kernel(const uint16_t *variance, int n_sb, uint16_t *avg) {
+    __shared__ unsigned long long part[32];
+    unsigned long long s = 0;
+    for (int i = threadIdx.x; i < n_sb; i += blockDim.x) s += variance[(size_t)i * 85];
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = s;
+    __syncthreads();
+    if (threadIdx.x == 0) { for (int i = 1; i < (int)(blockDim.x >> 5); i++) s += part[i]; *avg = (uint16_t)(s / (unsigned long long)n_sb); } /* compute_picture_spatial_statistics :4827 */
+}
+__device__ __forceinline__ bool edge_bright_beside_dark(const uint8_t *y_mean, int sb, int x, int y, int sbs_w, int sbs_h) {
+    if (!(x > 3 && x < sbs_w - 4 && y > 3 && y < sbs_h - 4)) return false;
+    if (!(y_mean[(size_t)sb * 85] > 180)) return false;
+    return y_mean[(size_t)(sb - 1) * 85] < 120 || y_mean[(size_t)(sb + 1) * 85] < 120 || y_mean[(size_t)(sb - sbs_w) * 85] < 120 || y_mean[(size_t)(sb + sbs_w) * 85] < 120;
+}
+__global__ void edge_detection_kernel(const uint8_t *y_mean, const uint16_t *variance, int sbs_w, int sbs_h, const uint16_t *avg, uint8_t *edge_block_num,
+                                      uint8_t *isolated, uint8_t *sharp) {
+    const int sb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sb >= sbs_w * sbs_h) return;
+    const int x = sb % sbs_w, y = sb / sbs_w;
+    uint8_t ebn = 0, sh = 0, iso = 0;
+    if (x > 0 && x < sbs_w - 1 && y > 0 && y < sbs_h - 1) {
+        const uint16_t *v = variance + (size_t)sb * 85;
+        const unsigned long long th0 = ((unsigned long long)*avg * 70) / 100;
+        ebn = v[0] > th0;
+        if (v[0] > 200) {
+            int n = 0;
+            for (int i = 5; i <= 20; i++) n += v[i] < 20;
+            sh = n > 4;
+        }
+    }
+    /* The reference walks the super-blocks in raster order, clears the flag of the one it is at and then marks the 9x9 neighbourhood of a
+     * bright super-block beside a dark one: what stays set on super-block n are the marks made from n itself or from a LATER super-block. */
+    for (int j = -4; j <= 4 && !iso; j++)
+        for (int i = -4; i <= 4; i++) {
+            const int mx = x + i, my = y + j, m = my * sbs_w + mx;
+            if (mx < 0 || mx >= sbs_w || my < 0 || my >= sbs_h || m < sb) continue;
+            if (edge_bright_beside_dark(y_mean, m, mx, my, sbs_w, sbs_h)) { iso = 1; break; }
+        }
+    edge_block_num[sb] = ebn; sharp[sb] = sh; isolated[sb] = iso;
+}
+
+/* ---- edge_detection_mean_luma_chroma16x16 (:4434): gradient of the 16x16 means, relative to the picture's largest ---- */
+__device__ __forceinline__ uint32_t edge_cu_grad(const uint8_t *ym, const uint8_t *cb, const uint8_t *cr, int b) {
+    const int k = 5 + b, x = b & 3, y = b >> 2;
+    int gx = 0, gy = 0, nx = 0, ny = 0;
+#define AD(a, i, j) abs((int)(a)[i] - (int)(a)[j])
+    if (x != 0) { gx += AD(ym, k, k - 1) + AD(cr, k, k - 1) + AD(cb, k, k - 1); nx++; }
+    if (x != 3) { gx += AD(ym, k + 1, k) + AD(cr, k + 1, k) + AD(cb, k + 1, k); nx++; }
+    if (y != 0) { gy += AD(ym, k, k - 4) + AD(cr, k, k - 4) + AD(cb, k, k - 4); ny++; }
+    if (y != 3) { gy += AD(ym, k + 4, k) + AD(cr, k + 4, k) + AD(cb, k + 4, k); ny++; }
+#undef AD
+    return (uint32_t)(gx / nx + gy / ny) & 0xffffu;
+}
+/* pass 0: the picture's largest gradient (at least 1); pass 1: the flags.  One thread per (super-block, 16x16 block). */
+template <int PASS>
+__global__ void edge_cu_kernel(const uint8_t *y_mean, const uint8_t *cb_mean, const uint8_t *cr_mean, const uint8_t *logo, int w, int h, int sbs_w, int n_sb,
+                               uint32_t *max_grad, uint8_t *edge_cu) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x, sb = i >> 4, b = i & 15;
+    const bool valid = sb < n_sb; /* (no early return: the warp reduction below needs every lane) */
+    const int sx = valid ? (sb % sbs_w) * 64 : 0, sy = valid ? (sb / sbs_w) * 64 : 0;
+    const bool on = valid && logo[sb] && sx + 64 <= w && sy + 64 <= h; /* potential_logo_sb && is_complete_sb */
+    const uint32_t g = on ? edge_cu_grad(y_mean + (size_t)sb * 85, cb_mean + (size_t)sb * 21, cr_mean + (size_t)sb * 21, b) : 0;
+    if (PASS == 0) {
+        uint32_t m = g;
+        for (int o = 16; o > 0; o >>= 1) m = max(m, __shfl_xor_sync(0xffffffffu, m, o));
+        if ((threadIdx.x & 31) == 0 && m > 1) atomicMax(max_grad, m);
+    } else if (valid) {
+        const uint32_t v = min((g * 765u) / max(*max_grad, 1u), 255u); /* max_grad starts at 1 in the reference */
+        edge_cu[i] = on && v >= 30;
+    }
+}
+#endif
