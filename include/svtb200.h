@@ -598,6 +598,25 @@ typedef struct SvtB200IntraBlock {
 /* blocks: HOST array (copied to the device by the call) */
 int svtb200_intra_predict_batch(SvtB200Ctx *ctx, const SvtB200IntraBlock *blocks, int n);
 
+/* generate_intra_reference_samples() (Source/Lib/Codec/EbEncDecProcess.c:1128-1315) for n transform blocks of one plane, on the device:
+ * the above row (above[-1] .. above[2 bs - 1]) and the left column (bs samples) the predictors read, taken from the plane the blocks'
+ * neighbours live in (the reconstruction, or the source for the open-loop intra search: the reference's neighbour arrays hold exactly
+ * these samples) with the reference's availability and frame-edge rules: 127 / 129 fills without a top / left neighbour, the above-right
+ * half replicated from above[bs - 1] except for the left 4x4 of an 8x8 block (have_right), rows / columns past the frame edge replicated
+ * from the last sample inside (extend_right / extend_bottom: the prediction block crosses the frame edge, xd->mb_to_right_edge < 0 /
+ * mb_to_bottom_edge < 0).  A job is filled from the block the way the reference derives its locals (:1131-1172):
+ *   x0, y0        position of the transform block in the plane: (-mb_to_left_edge >> (3 + ss_x)) + 4 * (bmi_index & 1), ... + 4 * (bmi_index >> 1)
+ *   have_top/left block origin (chroma: ROUND_UV(origin) >> 1) > 0;   have_right  (bmi_index & 1) + (1 << tx_size) < plane block width in 4-sample units
+ * edges_dev: 128 bytes per job: [15] = above[-1], [16 ..) = above, [80 ..) = left -- SvtB200IntraBlock::above = edges + 128 j + 16,
+ * ::left = edges + 128 j + 80 feed svtb200_intra_predict_batch without a host round trip.  plane_dev: the sample at (0,0). */
+typedef struct SvtB200IntraEdgeJob {
+    int32_t x0, y0;
+    uint8_t tx_size, have_left, have_top, have_right;
+    uint8_t extend_right, extend_bottom, pad[2];
+} SvtB200IntraEdgeJob;
+int svtb200_intra_edges_dev(SvtB200Ctx *ctx, const uint8_t *plane_dev, int32_t stride, int32_t frame_width, int32_t frame_height,
+                            const SvtB200IntraEdgeJob *jobs_dev, int n, uint8_t *edges_dev);
+
 /* full_distortion_intrinsic_func_ptr_array[..][eob != 0][0][..] (Source/Lib/Codec/EbPictureOperators.h:240, call site
  * Source/Lib/Codec/EbEncDecProcess.c:723): per transform block k of n (N x N coefficients each, block-major as svtb200_txq_batch
  * writes them) dist[2k] = sum (coeff - recon_coeff)^2, dist[2k+1] = sum coeff^2; with eob[k] == 0 both are sum coeff^2

@@ -37,6 +37,7 @@ void svtb200_oracle_luma_histogram(const SvtB200Plane *p16, int rw, int rh, uint
 /* prediction of the encode pass (host pointers in the descriptors) and full-loop distortion: pred_port.c */
 void svtb200_oracle_inter_predict(const SvtB200PredBlock *blocks, int n);
 void svtb200_oracle_intra_predict(const SvtB200IntraBlock *blocks, int n); /* host pointers */
+void svtb200_oracle_intra_edges(const uint8_t *plane, int stride, int frame_width, int frame_height, const SvtB200IntraEdgeJob *jobs, int n, uint8_t *out);
 void svtb200_oracle_full_distortion(int tx_size, int n, const int16_t *coeff, const int16_t *recon_coeff, const uint16_t *eob, uint64_t *dist);
 
 /* coefficient rate estimation (coeff_rate_estimate, use_fast_coef_costing == 0): rate_port.c */

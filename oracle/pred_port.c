@@ -181,3 +181,50 @@ void svtb200_oracle_intra_predict(const SvtB200IntraBlock *b, int n) {
         for (int r = 0; r < bs; r++) memcpy(b->dst + (ptrdiff_t)r * b->dst_stride, o + r * 32, (size_t)bs);
     }
 }
+
+/* generate_intra_reference_samples() (Source/Lib/Codec/EbEncDecProcess.c:1128-1315) for one transform block, with the neighbour samples
+ * read from the plane itself: the reference keeps them in its neighbour arrays (top_array[x] = the sample above the block at column x,
+ * left_array[y] = the sample left of it in row y, top_left_array = the corner; EbEncDecProcess.c:1179-1218), which hold the plane's
+ * samples at those positions whenever the block's neighbours have been written.  Sections NEED_LEFT (:1221), NEED_ABOVE (:1243) and
+ * NEED_ABOVERIGHT (:1269: it rewrites the whole above row) restated with their frame-edge extension rules.
+ * out: 128 bytes per job: [15] = above[-1], [16 .. 16 + 2 bs) = above, [80 .. 80 + bs) = left, everything else 0. */
+void svtb200_oracle_intra_edges(const uint8_t *plane, int stride, int frame_width, int frame_height, const SvtB200IntraEdgeJob *jobs, int n, uint8_t *out) {
+    for (int j = 0; j < n; j++) {
+        const SvtB200IntraEdgeJob *b = &jobs[j];
+        const int bs = 4 << b->tx_size, x0 = b->x0, y0 = b->y0;
+        uint8_t *rec = out + (size_t)j * 128, *row = rec + 16, *left = rec + 80;
+        const uint8_t *A = plane + (ptrdiff_t)(y0 - 1) * stride + x0; /* above_ref */
+        memset(rec, 0, 128);
+        if (b->have_left) {
+            if (b->extend_bottom && y0 + bs > frame_height) {
+                const int ext = frame_height - y0;
+                int i = 0;
+                for (; i < ext; i++) left[i] = plane[(ptrdiff_t)(y0 + i) * stride + x0 - 1];
+                for (; i < bs; i++) left[i] = plane[(ptrdiff_t)(y0 + ext - 1) * stride + x0 - 1];
+            } else
+                for (int i = 0; i < bs; i++) left[i] = plane[(ptrdiff_t)(y0 + i) * stride + x0 - 1];
+        } else
+            memset(left, 129, (size_t)bs);
+        if (!b->have_top) { memset(row - 1, 127, (size_t)(2 * bs + 1)); continue; }
+        const int four_right = bs == 4 && b->have_right;
+        if (b->extend_right) {
+            if (x0 + 2 * bs <= frame_width) {
+                if (four_right) memcpy(row, A, (size_t)(2 * bs));
+                else { memcpy(row, A, (size_t)bs); memset(row + bs, row[bs - 1], (size_t)bs); }
+            } else if (x0 + bs <= frame_width) {
+                const int r = frame_width - x0;
+                if (four_right) { memcpy(row, A, (size_t)r); memset(row + r, row[r - 1], (size_t)(x0 + 2 * bs - frame_width)); }
+                else { memcpy(row, A, (size_t)bs); memset(row + bs, row[bs - 1], (size_t)bs); }
+            } else {
+                const int r = frame_width - x0;
+                memcpy(row, A, (size_t)r);
+                memset(row + r, row[r - 1], (size_t)(x0 + 2 * bs - frame_width));
+            }
+        } else {
+            memcpy(row, A, (size_t)bs);
+            if (four_right) memcpy(row + bs, A + bs, (size_t)bs); /* (with have_left the reference aliases above_ref itself: same samples) */
+            else memset(row + bs, row[bs - 1], (size_t)bs);
+        }
+        row[-1] = b->have_left ? A[-1] : 129;
+    }
+}

@@ -864,3 +864,59 @@ int refdrv_edge_cu(const uint8_t *y_mean, const uint8_t *cb_mean, const uint8_t 
     free(pa->grad); free(pa); free(pcs->sb_stat_array); free(pcs->y_mean); free(pcs->cb_mean); free(pcs->cr_mean); free(pcs); free(scs->sb_params_array); free(scs);
     return 0;
 }
+
+/* ------------------------------------------------------------------------------------------------ intra reference samples
+ * The reference's own generate_intra_reference_samples() (EbEncDecProcess.c:1128) on an EncDecContext filled the way the encode pass fills
+ * it (block origin, ep block statistics, bmi_index, MACROBLOCKD edges) with neighbour arrays that hold the samples around the block
+ * (top_array / left_array / top_left_array, everything else poisoned -- including the context's own scratch rows, which keep whatever
+ * the previous block left there in the encoder).  out: the 128-byte records of svtb200_intra_edges_dev. */
+typedef struct { int32_t mi_row, mi_col; uint8_t bsize, tx_size, bmi_index, is_4x4; } RefdrvIntraBlk;
+void generate_intra_reference_samples(SequenceControlSet *sequence_control_set_ptr, EncDecContext *context_ptr, int plane);
+
+int refdrv_intra_edges(void *h, const uint8_t *plane_buf, int stride, int plane, int luma_w, int luma_h, const RefdrvIntraBlk *blks, int n, uint8_t *out) {
+    RefPredCtx *c = (RefPredCtx *)h;
+    if (!g_init || !c) return -1;
+    SequenceControlSet scs;
+    memset(&scs, 0, sizeof(scs));
+    scs.luma_width = (uint16_t)luma_w; scs.luma_height = (uint16_t)luma_h; scs.chroma_width = (uint16_t)(luma_w >> 1); scs.chroma_height = (uint16_t)(luma_h >> 1);
+    const int mi_cols = (luma_w + 7) >> 3, mi_rows = (luma_h + 7) >> 3, ss = plane ? 1 : 0;
+    NeighborArrayUnit na;
+    memset(&na, 0, sizeof(na));
+    const size_t top_n = (size_t)luma_w + 256, left_n = (size_t)luma_h + 256, tl_n = 2 * MAX_PICTURE_HEIGHT_SIZE + 256;
+    na.top_array = (uint8_t *)malloc(top_n); na.left_array = (uint8_t *)malloc(left_n); na.top_left_array = (uint8_t *)malloc(tl_n);
+    uint8_t *above_ref = (uint8_t *)malloc(256), *left_ref = (uint8_t *)malloc(256);
+    c->ctx.intra_above_ref = above_ref; c->ctx.intra_left_ref = left_ref;
+    c->ctx.luma_recon_neighbor_array = c->ctx.cb_recon_neighbor_array = c->ctx.cr_recon_neighbor_array = &na;
+    for (int i = 0; i < n; i++) {
+        const RefdrvIntraBlk *b = &blks[i];
+        const BLOCK_SIZE mi_bsize = (BLOCK_SIZE)b->bsize; /* the mode-info block (>= 8x8) */
+        const int sq = b->is_4x4 ? 4 : 4 * eb_vp9_num_4x4_blocks_wide_lookup[mi_bsize];
+        memset(na.top_array, 0xA5, top_n); memset(na.left_array, 0x5A, left_n); memset(na.top_left_array, 0xC3, tl_n);
+        memset(above_ref, 0x77, 256); memset(left_ref, 0x99, 256);
+        memset(c->ctx.above_data, 0xEE, sizeof(c->ctx.above_data)); memset(c->ctx.left_col, 0xDD, sizeof(c->ctx.left_col));
+        c->bs.bsize = b->is_4x4 ? BLOCK_4X4 : mi_bsize;
+        c->bs.tx_size = c->bs.tx_size_uv = (TX_SIZE)b->tx_size;
+        c->bs.sq_size = sq; c->bs.sq_size_uv = sq >> 1 < 4 ? 4 : sq >> 1;
+        c->ctx.bmi_index = b->bmi_index;
+        c->ctx.block_origin_x = (uint16_t)(b->mi_col * 8 + 4 * (b->bmi_index & 1)); c->ctx.block_origin_y = (uint16_t)(b->mi_row * 8 + 4 * (b->bmi_index >> 1));
+        c->xd.mb_to_top_edge = -((b->mi_row * MI_SIZE) * 8);
+        c->xd.mb_to_bottom_edge = ((mi_rows - eb_vp9_num_8x8_blocks_high_lookup[mi_bsize] - b->mi_row) * MI_SIZE) * 8;
+        c->xd.mb_to_left_edge = -((b->mi_col * MI_SIZE) * 8);
+        c->xd.mb_to_right_edge = ((mi_cols - eb_vp9_num_8x8_blocks_wide_lookup[mi_bsize] - b->mi_col) * MI_SIZE) * 8;
+        /* the neighbour arrays around the block, in the plane's coordinates */
+        const int ox = plane ? ROUND_UV(c->ctx.block_origin_x) >> 1 : c->ctx.block_origin_x, oy = plane ? ROUND_UV(c->ctx.block_origin_y) >> 1 : c->ctx.block_origin_y;
+        const int cnt = (plane ? c->bs.sq_size_uv : c->bs.sq_size) << 1;
+        if (oy > 0) for (int k = 0; k < cnt; k++) na.top_array[ox + k] = plane_buf[(ptrdiff_t)(oy - 1) * stride + ox + k];
+        if (ox > 0) for (int k = 0; k < cnt; k++) na.left_array[oy + k] = plane_buf[(ptrdiff_t)(oy + k) * stride + ox - 1];
+        if (ox > 0 && oy > 0) na.top_left_array[(plane ? MAX_PICTURE_HEIGHT_SIZE >> 1 : MAX_PICTURE_HEIGHT_SIZE) + ox - oy] = plane_buf[(ptrdiff_t)(oy - 1) * stride + ox - 1];
+        (void)ss;
+        generate_intra_reference_samples(&scs, &c->ctx, plane);
+        uint8_t *rec = out + (size_t)i * 128;
+        const int bs = 4 << b->tx_size;
+        memset(rec, 0, 128);
+        memcpy(rec + 15, c->ctx.const_above_row[plane] - 1, (size_t)(2 * bs + 1));
+        memcpy(rec + 80, c->ctx.left_col[plane], (size_t)bs);
+    }
+    free(na.top_array); free(na.left_array); free(na.top_left_array); free(above_ref); free(left_ref);
+    return 0;
+}

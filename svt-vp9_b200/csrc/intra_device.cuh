@@ -6,6 +6,7 @@
 #ifndef SVTB200_INTRA_DEVICE_CUH
 #define SVTB200_INTRA_DEVICE_CUH
 #include <stdint.h>
+#include <stddef.h>
 
 struct IntraEdge { const uint8_t *a, *l; };
 __device__ __forceinline__ int intra_e(const IntraEdge &E, int j) { return j >= -1 ? E.a[j] : E.l[-2 - j]; }
@@ -58,5 +59,42 @@ __device__ __forceinline__ int intra_sample(int mode, int bs, int dc, const Intr
     }
     }
     return 0;
+}
+/* ---- generate_intra_reference_samples (Source/Lib/Codec/EbEncDecProcess.c:1128-1315) in closed form: byte k of a job's 128-byte edge
+ * record straight from the plane (one thread per byte: every output sample is ONE plane sample or a constant, picked by the
+ * availability / frame-edge rules; the sequential form's copy-then-replicate steps become an index clamp). ---- */
+#ifdef SVTB200_CPU_EMU
+#include "../../include/svtb200.h"
+#endif
+__device__ __forceinline__ uint8_t intra_edge_byte(const uint8_t *plane, int stride, int fw, int fh, const SvtB200IntraEdgeJob &b, int k) {
+    const int bs = 4 << b.tx_size, x0 = b.x0, y0 = b.y0;
+    if (k >= 80) { /* left column */
+        const int i = k - 80;
+        if (i >= bs) return 0;
+        if (!b.have_left) return 129;
+        const int s = (b.extend_bottom && y0 + bs > fh) ? min(i, fh - y0 - 1) : i; /* rows past the frame: the last row inside */
+        return plane[(ptrdiff_t)(y0 + s) * stride + x0 - 1];
+    }
+    if (k < 15 || k >= 16 + 2 * bs) return 0;
+    if (!b.have_top) return 127;
+    const uint8_t *A = plane + (ptrdiff_t)(y0 - 1) * stride + x0;
+    if (k == 15) return b.have_left ? A[-1] : 129;
+    const int i = k - 16;
+    const bool four_right = bs == 4 && b.have_right; /* the left 4x4 of an 8x8 block: its above-right samples exist */
+    int last = four_right ? 2 * bs - 1 : bs - 1;       /* last sample taken from the plane; the rest replicates it */
+    if (b.extend_right) {
+        const int r = fw - x0;                         /* samples of the row inside the frame */
+        if (x0 + 2 * bs <= fw) {}
+        else if (x0 + bs <= fw) { if (four_right) last = r - 1; }
+        else last = r - 1;
+    }
+    return A[min(i, last)];
+}
+#define INTRA_EDGE_THREADS 256
+__global__ void __launch_bounds__(INTRA_EDGE_THREADS) intra_edges_kernel(const uint8_t *plane, int stride, int fw, int fh, const SvtB200IntraEdgeJob *jobs, int n,
+                                                                         uint8_t *out) {
+    const int j = blockIdx.x * 2 + (threadIdx.x >> 7), k = threadIdx.x & 127; /* two jobs per CTA, one thread per byte of the record */
+    if (j >= n) return;
+    out[(size_t)j * 128 + k] = intra_edge_byte(plane, stride, fw, fh, jobs[j], k);
 }
 #endif

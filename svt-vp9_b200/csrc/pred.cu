@@ -103,6 +103,18 @@ extern "C" int svtb200_intra_predict_batch(SvtB200Ctx *c, const SvtB200IntraBloc
     return SVTB200_OK;
 }
 
+extern "C" int svtb200_intra_edges_dev(SvtB200Ctx *c, const uint8_t *plane, int32_t stride, int32_t fw, int32_t fh, const SvtB200IntraEdgeJob *jobs, int n,
+                                       uint8_t *edges) {
+    if (!c || n < 0 || (n && (!plane || !jobs || !edges)) || fw <= 0 || fh <= 0 || stride < fw) return SVTB200_EINVAL;
+    if (!n) return SVTB200_OK;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    intra_edges_kernel<<<(n + 1) / 2, INTRA_EDGE_THREADS, 0, c->stream>>>(plane, stride, fw, fh, jobs, n, edges);
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
 /* ---- full-loop distortion: one warp per transform block ---- */
 __global__ void __launch_bounds__(256) full_dist_kernel(int nn, int n, const int16_t *coeff, const int16_t *rc, const uint16_t *eob, uint64_t *dist) {
     const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;

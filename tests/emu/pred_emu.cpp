@@ -21,3 +21,8 @@ extern "C" int pred_emu_run(const SvtB200PredBlock *blocks, int n, int grid) {
     emu_launch(dim3((unsigned)(n < grid ? n : grid)), dim3(PRED_THREADS), 0, [&] { pred_kernel(blocks, n); });
     return 0;
 }
+
+extern "C" int intra_edges_emu_run(const uint8_t *plane, int stride, int fw, int fh, const SvtB200IntraEdgeJob *jobs, int n, uint8_t *out) {
+    emu_launch(dim3((unsigned)((n + 1) / 2)), dim3(INTRA_EDGE_THREADS), 0, [&] { intra_edges_kernel(plane, stride, fw, fh, jobs, n, out); });
+    return 0;
+}
