@@ -661,7 +661,11 @@ def main():
     d_rows = to_dev(H.quant_rows([QINDEX]))
     d_lfm, d_thr = to_dev(lf_masks_32x32()), to_dev(H.lf_thresholds())
     # result buffers exist NSLOT times: the end-to-end leg downloads slot s while the kernels of the next pictures fill the others
-    NSLOT = 3
+    NSLOT = int(os.environ.get("SVTB200_BENCH_SLOTS", "4"))
+    # the end-to-end leg queues a picture's exact-size coefficient-stream copy STREAM_LAG steps after the picture itself (the host must have
+    # seen the stream's length by then): with a lag of one the host could never run more than one picture ahead of the download queue --
+    # picture i + 1's upload was not even queued before picture i - 1 had come down -- and the copies did not overlap the kernels
+    STREAM_LAG = max(1, min(NSLOT - 2, int(os.environ.get("SVTB200_E2E_STREAM_LAG", "2"))))
     # eob and rate arrays of the six passes are carved from one allocation per slot: one download each
     al = lambda v: (v + 255) & ~255
     eob_off = [sum(al(m * 2) for m in pass_n[:k]) for k in range(len(pass_n) + 1)]
@@ -901,12 +905,12 @@ def main():
             d2h(h_off[slot], d_off[slot], (n_tu + 1) * 4)                       # D2H block offsets + stream length
         downloaded[slot] = ctx.marker(api.DOWNLOAD)
         if PACK_MODE != "mapped" and "d2h" not in skip and "pack" not in skip:
-            finish_streams()                                                    # the previous picture's stream: its length has arrived by now
             pending_stream.append((slot, downloaded[slot]))
+            finish_streams(STREAM_LAG)                                          # the stream of picture i - STREAM_LAG: its length has arrived by now
 
-    def finish_streams():
-        """queue the exact-size stream copies of the pictures whose offsets are (being) downloaded"""
-        while pending_stream:
+    def finish_streams(keep=0):
+        """queue the exact-size stream copies of the pictures whose offsets are (being) downloaded, all but the newest `keep`"""
+        while len(pending_stream) > keep:
             sl, mk = pending_stream.pop(0)
             ctx.wait(mk)
             nbytes = 2 * int(h_off_np[sl][n_tu])

@@ -19,7 +19,10 @@ int svtb200_create(int device, SvtB200Ctx **out) {
     /* the upload queue also runs the (tiny) padding / decimation kernels: give it priority over the picture-sized compute kernels */
     int prio_lo = 0, prio_hi = 0;
     cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
-    if (cudaStreamCreateWithFlags(&c->compute[0], cudaStreamNonBlocking) != cudaSuccess || cudaStreamCreateWithFlags(&c->compute[1], cudaStreamNonBlocking) != cudaSuccess ||
+    /* SVTB200_COMPUTE2_PRIORITY=1: CTAs of the second compute queue are dispatched ahead of the first queue's whenever an SM has room */
+    const char *p2 = getenv("SVTB200_COMPUTE2_PRIORITY");
+    if (cudaStreamCreateWithFlags(&c->compute[0], cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithPriority(&c->compute[1], cudaStreamNonBlocking, (p2 && p2[0] == '1') ? prio_hi : prio_lo) != cudaSuccess ||
         cudaStreamCreateWithFlags(&c->compute[2], cudaStreamNonBlocking) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->up, cudaStreamNonBlocking, prio_hi) != cudaSuccess ||
         cudaStreamCreateWithPriority(&c->down, cudaStreamNonBlocking, prio_hi) != cudaSuccess) { delete c; cudaGetLastError(); return SVTB200_ENODEV; }

@@ -104,6 +104,10 @@ static int me_launch(SvtB200Ctx *c, const SvtB200MeParams *P, uint64_t cur_id, c
         if (c->me_counter) {
             int per_sm = 0;
             if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, me_sb_kernel, ME_THREADS, (size_t)L.total) != cudaSuccess || per_sm < 1) { cudaGetLastError(); per_sm = 1; }
+            /* SVTB200_ME_CTAS_PER_SM=n: leave room on every SM (registers, shared memory, warp slots) for the kernels of the OTHER compute queues --
+             * a persistent grid that fills the SMs keeps everything else out until it ends */
+            static const int cap_per_sm = getenv("SVTB200_ME_CTAS_PER_SM") ? atoi(getenv("SVTB200_ME_CTAS_PER_SM")) : 0;
+            if (cap_per_sm > 0 && cap_per_sm < per_sm) per_sm = cap_per_sm;
             A.sb_counter = c->me_counter + (c->me_counter_next++ & 63);
             SVTB200_CUDA_CHECK(c, cudaMemsetAsync(A.sb_counter, 0, sizeof(uint32_t), c->stream));
             grid = std::min(A.n_sb, per_sm * (c->sm_count > 0 ? c->sm_count : 148));

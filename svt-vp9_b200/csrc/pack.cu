@@ -21,7 +21,9 @@
 
 #define PACK_MAX_BATCHES 8
 #define PACK_THREADS 256
-#define PACK_CHUNK 64 /* blocks per CTA: 8 per warp, so that the dependent loads of a block (scan entry -> coefficient) overlap across many warps */
+#ifndef PACK_CHUNK
+#define PACK_CHUNK 32 /* blocks per CTA: 4 per warp, so that the dependent loads of a block (scan entry -> coefficient) overlap across many warps; 64 gave 389 CTAs at 4K: a third of the warp slots */
+#endif
 
 struct PackBatch {
     const SvtB200TxJob *jobs;

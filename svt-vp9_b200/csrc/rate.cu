@@ -68,7 +68,9 @@ __device__ __forceinline__ int rate_band(int c, int tx_size) { /* the band of sc
  * thread finds the block of its position by bisection over the running eob sums): no lane idles on a short block, and every
  * position is an independent chain of loads.  The terms of a block are summed in shared memory (one atomic per warp when the
  * warp's positions all belong to one block, which is the common case). */
-#define RATE_CHUNK 64
+#ifndef RATE_CHUNK
+#define RATE_CHUNK 32 /* 64 left two thirds of the warp slots empty at 4K (389 CTAs on 148 SMs): the kernel is a chain of dependent loads per position */
+#endif
 #define RATE_MAX_BATCHES 8
 struct RateMultiArgs {
     RateArgs b[RATE_MAX_BATCHES];
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(RATE_THREADS) rate_multi_kernel(const __grid_c
             }
             rate_s[tid] = r;
         }
-        /* exclusive scan of the eob values over the first RATE_CHUNK threads (two warps) */
+        /* exclusive scan of the eob values over the first RATE_CHUNK threads */
         uint32_t inc = len;
         for (int o = 1; o < 32; o <<= 1) { const uint32_t x = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += x; }
         if (lane == 31) wsum[tid >> 5] = inc;
