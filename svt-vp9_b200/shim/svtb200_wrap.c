@@ -260,21 +260,26 @@ static int ensure_resident(int dev, const EbPaReferenceObject *o, uint64_t poc, 
     ResEntry *e = &g_res[idx];
     pthread_mutex_lock(&e->mu); /* only callers that need THIS picture wait here */
     int rc = SVTB200_OK;
-    /* how a picture reaches the device (SVT_VP9_GPU_UPLOAD): "pageable" (default) = the three planes as they are, through the driver's own
-     * staging of pageable memory; "pagelock" = the same with each pool object page-locked the first time it is seen (asynchronous uploads,
-     * but ~1 ms per MB the first time: 10 ms per 4K picture on clips as short as the pool is deep); "staged" = only the picture area, copied by
-     * this thread into a ring of page-locked slots the library owns, padding and decimations made on the device
-     * (svtb200_picture_upload_luma_staged; measured slower than the driver's staging inside the loaded encoder). */
+    /* how a picture reaches the device (SVT_VP9_GPU_UPLOAD): "pagelock" = the three planes as they are, each pool object page-locked the
+     * first time it is seen (asynchronous DMA uploads afterwards; the first touch costs ~1 ms per MB and more on a cold host: up to 10 ms per
+     * 3840x2160 picture on clips as short as the pool is deep); "pageable" = the same planes through the driver's own staging of pageable memory
+     * (no first-touch cost, ~1 ms per 1080p picture more on every upload, with the context lock held meanwhile); "staged" = only the picture
+     * area, copied by this thread into a ring of page-locked slots the library owns, padding and decimations made on the device
+     * (svtb200_picture_upload_luma_staged).  Default "auto": page-lock objects of up to SVT_VP9_GPU_PAGELOCK_MAX_MB (6) megabytes, i.e. up to
+     * 1080p, pageable above -- what measured best on 300-frame 1080p and 100-frame 4K encodes (tools/encoder_fps.py). */
     static int upmode = -1;
+    static size_t lock_max_bytes;
     if (upmode < 0) {
-        const char *ev = getenv("SVT_VP9_GPU_UPLOAD"), *pl0 = getenv("SVT_VP9_GPU_PAGELOCK");
-        upmode = (ev && !strcmp(ev, "pagelock")) ? 1 : (ev && !strcmp(ev, "staged")) ? 0 : (pl0 && pl0[0] == '1') ? 1 : 2;
+        const char *ev = getenv("SVT_VP9_GPU_UPLOAD"), *pl0 = getenv("SVT_VP9_GPU_PAGELOCK"), *mb = getenv("SVT_VP9_GPU_PAGELOCK_MAX_MB");
+        lock_max_bytes = (size_t)(mb ? atoi(mb) : 6) << 20;
+        upmode = (ev && !strcmp(ev, "pagelock")) ? 1 : (ev && !strcmp(ev, "pageable")) ? 2 : (ev && !strcmp(ev, "staged")) ? 0 : (pl0 && pl0[0] == '1') ? 1 : (pl0 && pl0[0] == '0') ? 2 : 3;
     }
     if (dev < 0 ? (upmode == 1 && !e->locked) : !(e->valid[dev] && e->poc[dev] == poc && (e->has_q[dev] || !want_quarter))) {
         SvtB200Plane pl[3];
         svtb200_glue_pa_planes(o, pl);
         const double tr0 = now_s();
-        if (upmode == 1 && (fresh || !e->locked)) { /* a buffer of the reference's pool, first time seen: page-lock it */
+        const int lock_it = upmode == 1 || (upmode == 3 && (size_t)pl[0].stride * (size_t)pl[0].padded_height <= lock_max_bytes);
+        if (lock_it && (fresh || !e->locked)) { /* a buffer of the reference's pool, first time seen: page-lock it */
             for (int k = 0; k < 3; k++)
                 if (pl[k].buf && pl[k].stride > 0 && pl[k].padded_height > 0 &&
                     svtb200_host_register((void *)pl[k].buf, (size_t)pl[k].stride * pl[k].padded_height) == SVTB200_OK) e->reg[k] = (void *)pl[k].buf;
@@ -538,6 +543,8 @@ void __wrap_eb_vp9_loop_filter_frame(VP9_COMMON *cm, MACROBLOCKD *xd, int frame_
     {   /* the reconstruction buffers come from a small pool: page-lock each plane the first time it is filtered */
         int known = 0;
         for (int i = 0; i < g_lf_reg_n; i++) known |= g_lf_reg[i] == (void *)xd->plane[0].dst.buf;
+        /* (page-locked whatever their size: the pool is a handful of buffers, and a pageable 4K reconstruction measured 24 ms per filtered
+         * picture against 2 ms) */
         if (!known && g_lf_reg_n + 3 <= 192) {
             if (svtb200_host_register(xd->plane[0].dst.buf, (size_t)xd->plane[0].dst.stride * (P.height - 1) + P.width) == SVTB200_OK)
                 g_lf_reg[g_lf_reg_n++] = xd->plane[0].dst.buf;
