@@ -556,7 +556,8 @@ def main():
                         "behind the picture's motion estimation and beside the next picture's; value = "
                         "CUDA events around the K steps with both queues joined inside the timed region",
               "coefficients": "quantised coefficients leave the device as the scan-order prefix (eob entries) of every TU -- what the entropy coder reads "
-                              "(svtb200_coeff_pack_dev); in the end-to-end leg the pack kernel stores them straight into page-locked host memory",
+                              "(svtb200_coeff_pack_dev); in the end-to-end leg the block offsets (with the stream's length) come down with the other results and the exact-size copy "
+                              "of the stream is queued two steps later (SVTB200_E2E_PACK=mapped: stored by the kernel straight into page-locked host memory, measured slower)",
               "l2": "17 distinct pictures (165 MB of luma planes + 105 MB chroma) cycled: working set larger than the 126 MB L2",
               "parallelism": "pictures sharded across GPUs (independent mini-GOP streams per rank), no collective on the data path"}
 
@@ -856,7 +857,7 @@ def main():
 
     # ---- end-to-end leg: host buffers in, host buffers out, through the C ABI's three queues.  Picture i+1 uploads and
     # picture i-1 downloads while picture i computes; the host collects picture i-3's results (the previous user of the slot)
-    # before it queues picture i, i.e. three pictures are in flight (upload / kernels / download).
+    # before it queues picture i, i.e. NSLOT pictures are in flight (upload / kernels / download).
     downloaded = [0] * NSLOT   # marker after the last download out of each result slot
     stream_coefs = [0, 0]      # coefficients the pack kernel stored into host memory, pictures counted
     chroma_used = {}      # marker after the last kernel that read the chroma buffers of a picture
@@ -1025,7 +1026,7 @@ def main():
     alg["rate_kernel"] = int((stream_bytes + n_tu * 10) * n_me)         # coefficients up to eob read once; eob + descriptor in, rate out
 
     if args.verify:
-        # the pipelined leg (4 queues, 3 slots) must have produced exactly what a synchronous single-queue run produces
+        # the pipelined leg (4 queues, NSLOT slots) must have produced exactly what a synchronous single-queue run produces
         checked = 0
         for i in range(n_warm + n_timed - NSLOT, n_warm + n_timed):
             slot, n = i % NSLOT, ENCODE_ORDER[i % 16]

@@ -1,4 +1,4 @@
-"""The end-to-end leg of bench.py drives the C ABI's four queues with three result slots; `--verify` recomputes its last
+"""The end-to-end leg of bench.py drives the C ABI's four queues with several result slots; `--verify` recomputes its last
 pictures synchronously on one queue and compares every downloaded byte (ME results, quantised coefficients, eob, filtered
 planes).  35 steps so that the base-layer picture (deblocking + plane download) is among the verified ones."""
 import os
