@@ -284,6 +284,18 @@ int svtb200_noise_filter_dev(SvtB200Ctx *ctx, int kind, const uint8_t *in_dev, i
  * totals[0] / totals[1]; the class thresholds on it stay with the host).  Incomplete super-blocks: zeros.  All pointers DEVICE memory. */
 int svtb200_noise_detect_dev(SvtB200Ctx *ctx, const uint8_t *in_dev, int32_t in_stride, int32_t w, int32_t h, uint8_t *den_dev, int32_t den_stride,
                              uint64_t noise_th, uint64_t den_th, uint64_t *noise_var_dev, uint64_t *den_var_dev, uint8_t *flat_dev, uint64_t *totals_dev);
+/* The decimated twins of the same stage, which the reference selects by resolution / tune / enc-mode (eb_vp9_signal_derivation_pre_analysis_oq / _sq,
+ * Source/Lib/Codec/EbResourceCoordinationProcess.c:290-390; tune 1 at enc-mode > 3: 1080p -> quarter, 4K -> half precision): quarter_sample_detect_noise
+ * (:3809) on the 1/4 plane with block = 32 and sub_sample_detect_noise (:3930) on the 1/16 plane with block = 16 -- one block x block area is one
+ * full-resolution super-block, written at (by / block) * picture_width_in_sb + bx / block.  in_dev / w / h: the decimated plane's sample (0,0) and size
+ * (svtb200_picture_plane_dev, which 1 / 2).  The statistics follow the reference's routines to the letter, including where they differ from the
+ * full-resolution one (whole 64x64 areas of the plane only -- at 3840x2160 the complete super-block row 32 is never visited --, 8x8 means over all
+ * eight rows, compute_variance32x32's block pairing, the noise rows of a 64-row band's first block row for every block of the band): the flags
+ * are pinned against sb_flat_noise_array inside real encodes (oracle/ref_seam_check.c).  den_dev (w x h, pitch den_stride) is scratch: the areas walked
+ * receive the weak-filtered samples.  Unvisited super-blocks: zeros.  noise_th / den_th: NOISE_MIN_LEVEL_DECIM_0 / _1 and FLAT_MAX_VAR_DECIM. */
+int svtb200_noise_detect_decimated_dev(SvtB200Ctx *ctx, const uint8_t *in_dev, int32_t in_stride, int32_t w, int32_t h, int32_t block,
+                                       int32_t picture_width_in_sb, int32_t n_sb, uint8_t *den_dev, int32_t den_stride, uint64_t noise_th, uint64_t den_th,
+                                       uint64_t *noise_var_dev, uint64_t *den_var_dev, uint8_t *flat_dev, uint64_t *totals_dev);
 /* edge_detection() (:4545) on the block statistics svtb200_block_stats_picture_dev leaves ([n_sb][85]): per super-block edge_block_num
  * (64x64 variance above 70 % of the picture's average), isolated_high_intensity_sb (the 9x9 neighbourhoods of bright super-blocks beside
  * dark ones, with the reference's raster-order clear-then-mark semantics) and sharp_edge_sb_flag; pic_avg_variance

@@ -47,7 +47,8 @@ gcc $CF $INC -I$HERE/../include -I$HERE/../svt-vp9_b200/shim -c $HERE/ref_seam_c
 gcc -std=gnu99 -O2 -fPIC -I$HERE/../include -c $HERE/me_port.c -o $OUT/me_port.o
 gcc -std=gnu99 -O2 -fPIC -I$HERE/../include -c $HERE/lf_port.c -o $OUT/lf_port.o
 gcc -std=gnu99 -O2 -fPIC -I$HERE/../include -c $HERE/pa_port.c -o $OUT/pa_port.o
-gcc -shared -o $OUT/libSvtVp9Enc_seam.so $OUT/obj/*.o $OUT/seam_check.o $OUT/me_port.o $OUT/lf_port.o $OUT/pa_port.o -lpthread -lm \
+gcc -std=gnu99 -O2 -fPIC -I$HERE/../include -c $HERE/pa_noise_port.c -o $OUT/pa_noise_port.o
+gcc -shared -o $OUT/libSvtVp9Enc_seam.so $OUT/obj/*.o $OUT/seam_check.o $OUT/me_port.o $OUT/lf_port.o $OUT/pa_port.o $OUT/pa_noise_port.o -lpthread -lm \
     -Wl,--no-undefined -Wl,--wrap=motion_estimate_sb -Wl,--wrap=eb_vp9_loop_filter_frame
 gcc -std=gnu99 -O2 -w -I$OUT/inc -I$REF/Source/API $REF/Source/App/*.c -o $OUT/SvtVp9EncApp_seam \
     -L$OUT -lSvtVp9Enc_seam -lpthread -lm -lrt -Wl,-rpath,'$ORIGIN'

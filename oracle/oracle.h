@@ -50,6 +50,17 @@ void svtb200_oracle_chroma_block_mean(const uint8_t *cb, const uint8_t *cr, int 
 void svtb200_oracle_chroma_histogram(const uint8_t *cb, const uint8_t *cr, int stride, int luma_width, int luma_height, int rw, int rh,
                                      uint32_t *hist, uint8_t *avg, uint64_t sum16[2]);
 
+/* rest of the picture-analysis front end: pa_noise_port.c */
+void svtb200_oracle_noise_filter(int kind, const uint8_t *in, int in_stride, int w, int h, uint8_t *den, int den_stride, uint8_t *noise);
+void svtb200_oracle_noise_detect(const uint8_t *in, int in_stride, int w, int h, uint8_t *den, int den_stride, uint64_t noise_th, uint64_t den_th,
+                                 uint64_t *noise_var, uint64_t *den_var, uint8_t *flat, uint64_t totals[2]);
+void svtb200_oracle_noise_detect_decimated(const uint8_t *in, int in_stride, int w, int h, int block, int picture_width_in_sb, int n_sb, uint8_t *den, int den_stride,
+                                           uint64_t noise_th, uint64_t den_th, uint64_t *noise_var, uint64_t *den_var, uint8_t *flat, uint64_t totals[2]);
+void svtb200_oracle_edge_detection(const uint8_t *y_mean, const uint16_t *variance, int w, int h, uint64_t pic_avg_variance, uint8_t *edge_block_num,
+                                   uint8_t *isolated, uint8_t *sharp_edge);
+void svtb200_oracle_edge_cu(const uint8_t *y_mean, const uint8_t *cb_mean, const uint8_t *cr_mean, const uint8_t *sb_flags, int n_sb, uint64_t picture_number,
+                            uint8_t *edge_cu);
+
 /* block walk in front of the inter predictors, open-loop partition of the bench: blocks_port.c */
 void svtb200_oracle_inter_expand(const SvtB200InterBlock *blocks, int n, const SvtB200PredPicture *pic, SvtB200PredBlock *out);
 int  svtb200_oracle_me_best_blocks(const SvtB200MeCuResult *me, int width, int height, SvtB200InterBlock *out);

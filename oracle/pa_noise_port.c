@@ -7,12 +7,15 @@
  *                                   clip(in - denoised, 0, 255)
  *   svtb200_oracle_noise_detect     detect_input_picture_noise (:3512-3560): per COMPLETE super-block compute_variance64x64 (:408) of the
  *                                   noise and of the denoised samples, the flat-noise flag, the picture sums
+ *   svtb200_oracle_noise_detect_decimated   quarter_sample_detect_noise (:3809) / sub_sample_detect_noise (:3930): the same on the 1/4 / 1/16 plane with
+ *                                   32x32 / 16x16 blocks (the methods the reference picks at 1080p / 4K for tune 1 above enc-mode 3)
  *   svtb200_oracle_edge_detection   edge_detection (:4545)
  *   svtb200_oracle_edge_cu          edge_detection_mean_luma_chroma16x16 (:4434)
  * Pinned against the reference's own functions (plain C and the AVX2 entries of its dispatch tables) through the path driver
  * (oracle/ref_path_driver.c: refdrv_noise_filter, refdrv_edge_detection, refdrv_edge_cu; tests/test_pa_noise_edge.py).
  */
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
 #include "oracle.h"
 
@@ -80,6 +83,69 @@ void svtb200_oracle_noise_detect(const uint8_t *in, int in_stride, int w, int h,
             totals[0] += noise_var[sb] >> 16;
             totals[1]++;
         }
+}
+
+/* compute_variance32x32 (:152) / compute_variance16x16 (:345): the same hierarchy cut off at 32x32 / 16x16 */
+static uint64_t variance_n(const uint8_t *p, int stride, int n /* 16, 32 or 64 */) {
+    if (n == 64) return variance64(p, stride);
+    uint64_t m[16], q[16];
+    const int nb = n / 8;
+    for (int b = 0; b < nb * nb; b++) {
+        const uint8_t *s = p + (size_t)(b / nb) * 8 * stride + (b % nb) * 8;
+        uint64_t a = 0, a2 = 0;
+        /* compute_mean_func[0] / [1] (Codec/EbComputeMean.h:21; compute_mean, compute_mean_of_squared_values, C_DEFAULT/EbComputeMean_C.c:15-60): ALL
+         * eight rows of the 8x8 block here -- (sum << 8) / 64 and (sum of squares << 16) / 64 --, not the rows 0, 2, 4, 6 of the 64x64 routine */
+        for (int r = 0; r < 8; r++) for (int x = 0; x < 8; x++) { const uint64_t v = s[(size_t)r * stride + x]; a += v; a2 += v * v; }
+        m[b] = a << 2; q[b] = a2 << 10;
+    }
+    if (n == 32) {
+        uint64_t m16[4], q16[4];
+        /* the reference groups the sixteen 8x8 blocks (numbered row by row, four per row) as {2i, 2i+1, 2i+8, 2i+9} -- the pairing of its 64x64
+         * routine, whose rows hold eight blocks (:300-312): two blocks of block row 0 / 1 with the two below them two rows down, not one */
+        for (int i = 0; i < 4; i++) { const int a = 2 * i; m16[i] = (m[a] + m[a + 1] + m[a + 8] + m[a + 9]) >> 2; q16[i] = (q[a] + q[a + 1] + q[a + 8] + q[a + 9]) >> 2; }
+        const uint64_t mm = (m16[0] + m16[1] + m16[2] + m16[3]) >> 2, qq = (q16[0] + q16[1] + q16[2] + q16[3]) >> 2;
+        return qq - mm * mm;
+    }
+    const uint64_t mm = (m[0] + m[1] + m[2] + m[3]) >> 2, qq = (q[0] + q[1] + q[2] + q[3]) >> 2;
+    return qq - mm * mm;
+}
+
+/* quarter_sample_detect_noise (:3809, block 32 on the 1/4 plane) / sub_sample_detect_noise (:3930, block 16 on the 1/16 plane) up to their
+ * picture-level decision.  in: the decimated plane (w x h); one block x block area = one full-resolution super-block, sb index
+ * (by / block) * picture_width_in_sb + bx / block.  As the reference does it: the plane is walked in 64x64 areas, floor(w / 64) x
+ * floor(h / 64) of them -- blocks further right / down are never visited (at 3840x2160 the complete super-block row 32 is not) --, each
+ * 64-row band is weak-filtered into den (+ the band's noise rows), and the NOISE variance of every block of the band is taken from the
+ * band's FIRST `block` noise rows at the block's columns (noise_origin_index carries no row offset for the block inside the band, :3866 /
+ * :3988), the variance of the denoised samples from the block's own position.  Unvisited super-blocks: zeros. */
+void svtb200_oracle_noise_detect_decimated(const uint8_t *in, int in_stride, int w, int h, int block, int picture_width_in_sb, int n_sb, uint8_t *den, int den_stride,
+                                           uint64_t noise_th, uint64_t den_th, uint64_t *noise_var, uint64_t *den_var, uint8_t *flat, uint64_t totals[2]) {
+    uint8_t *noise = (uint8_t *)malloc((size_t)w * 64);
+    memset(noise_var, 0, (size_t)n_sb * 8); memset(den_var, 0, (size_t)n_sb * 8); memset(flat, 0, (size_t)n_sb);
+    totals[0] = totals[1] = 0;
+    svtb200_oracle_noise_filter(0, in, in_stride, w, h, den, den_stride, NULL);
+    for (int by64 = 0; by64 < h / 64; by64++) {
+        for (int y = 0; y < 64; y++) /* the band's noise rows */
+            for (int x = 0; x < w; x++) {
+                const int py = by64 * 64 + y;
+                const int inner = py > 0 && py < h - 1 && x > 0 && x < w - 1;
+                const int d = (int)in[(size_t)py * in_stride + x] - (int)den[(size_t)py * den_stride + x];
+                noise[(size_t)y * w + x] = (uint8_t)(inner && d > 0 ? d : 0);
+            }
+        for (int bx64 = 0; bx64 < w / 64; bx64++)
+            for (int vi = 0; vi < 64 / block; vi++)
+                for (int hi = 0; hi < 64 / block; hi++) {
+                    const int bx = bx64 * 64 + hi * block, by = by64 * 64 + vi * block;
+                    if (bx + block > w || by + block > h) continue;
+                    const int sb = (by / block) * picture_width_in_sb + bx / block;
+                    if (sb >= n_sb) continue;
+                    noise_var[sb] = variance_n(noise + bx, w, block); /* rows 0 .. block-1 of the band, whatever vi is */
+                    den_var[sb] = variance_n(den + (size_t)by * den_stride + bx, den_stride, block) >> 16;
+                    flat[sb] = den_var[sb] < den_th && noise_var[sb] > noise_th;
+                    totals[0] += noise_var[sb] >> 16;
+                    totals[1]++;
+                }
+    }
+    free(noise);
 }
 
 /* edge_detection (:4545).  y_mean / variance: [n_sb][85] as the block statistics leave them.  The reference walks the super-blocks in

@@ -24,6 +24,7 @@ static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static int   g_mode = -1; /* 0 off, 1 check, 2 dump */
 static char  g_dir[512];
 static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed, g_stats_bad, g_hist_pics, g_hist_bad, g_chroma_bad, g_chroma_hist_bad;
+static long  g_edge_bad, g_edge_cu_bad, g_edge_cu_set, g_noise_pics, g_noise_bad, g_noise_method = -1, g_noise_class_hist[12], g_noise_flat_set, g_dbg_row[4], g_dbg_col[4], g_dbg_ref1, g_dbg_mine1;
 static int   g_max_dump_pics = 4, g_dump_from = 0;
 
 #define MAX_TRACKED 64
@@ -39,6 +40,10 @@ static void write_summary(void) {
     FILE *f = fopen(path, "w");
     if (!f) return;
     fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\nstats_bad %ld\nhist_pics %ld\nhist_bad %ld\nchroma_bad %ld\nchroma_hist_bad %ld\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped, g_stats_bad, g_hist_pics, g_hist_bad, g_chroma_bad, g_chroma_hist_bad);
+    fprintf(f, "edge_bad %ld\nedge_cu_bad %ld\nedge_cu_set %ld\nnoise_pics %ld\nnoise_bad %ld\n", g_edge_bad, g_edge_cu_bad, g_edge_cu_set, g_noise_pics, g_noise_bad);
+    fprintf(f, "noise_flat_set %ld\nnoise_method %ld\n", g_noise_flat_set, g_noise_method);
+    if (g_dbg_mine1 + g_dbg_ref1) fprintf(f, "dbg_rows %ld,%ld,%ld,%ld\ndbg_cols %ld,%ld,%ld,%ld\ndbg_only_oracle %ld\ndbg_only_reference %ld\n", g_dbg_row[0], g_dbg_row[1], g_dbg_row[2], g_dbg_row[3], g_dbg_col[0], g_dbg_col[1], g_dbg_col[2], g_dbg_col[3], g_dbg_mine1, g_dbg_ref1); /* NOISE_DETECT_HALF / QUARTER / FULL_PRECISION = 0 / 1 / 2 */
+    for (int i = 0; i < 12; i++) if (g_noise_class_hist[i]) fprintf(f, "noise_class_%d %ld\n", i, g_noise_class_hist[i]);
     fclose(f);
 }
 
@@ -127,7 +132,71 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
                 if (cav[(iw * rh + ih) * 2 + p] != (uint8_t)pcs->average_intensity_per_region[iw][ih][1 + p]) chb++;
             }
             free(ch);
-            pthread_mutex_lock(&g_mu); g_hist_pics++; g_hist_bad += hb; g_chroma_bad += cbad; g_chroma_hist_bad += chb; pthread_mutex_unlock(&g_mu);
+            /* ... the two edge maps of compute_picture_spatial_statistics (edge_detection, edge_detection_mean_luma_chroma16x16) ... */
+            long ebad = 0, ecbad = 0, ecset = 0, nbad = 0, npics = 0, nflat = 0;
+            {
+                uint8_t *ym = (uint8_t *)malloc((size_t)n_sb * 85), *cbm = (uint8_t *)malloc((size_t)n_sb * 21), *crm = (uint8_t *)malloc((size_t)n_sb * 21);
+                uint16_t *vr = (uint16_t *)malloc((size_t)n_sb * 85 * 2);
+                uint8_t *o3 = (uint8_t *)malloc((size_t)n_sb * 3), *fl = (uint8_t *)malloc((size_t)n_sb), *ecu = (uint8_t *)malloc((size_t)n_sb * 16);
+                for (int s = 0; s < n_sb; s++) {
+                    memcpy(ym + (size_t)s * 85, pcs->y_mean[s], 85); memcpy(vr + (size_t)s * 85, pcs->variance[s], 85 * 2);
+                    memcpy(cbm + (size_t)s * 21, pcs->cb_mean[s], 21); memcpy(crm + (size_t)s * 21, pcs->cr_mean[s], 21);
+                    fl[s] = scs->sb_params_array[s].potential_logo_sb && scs->sb_params_array[s].is_complete_sb;
+                }
+                svtb200_oracle_edge_detection(ym, vr, scs->luma_width, scs->luma_height, pcs->pic_avg_variance, o3, o3 + n_sb, o3 + 2 * n_sb);
+                for (int s = 0; s < n_sb; s++)
+                    ebad += o3[s] != pcs->edge_results_ptr[s].edge_block_num || o3[n_sb + s] != pcs->edge_results_ptr[s].isolated_high_intensity_sb ||
+                            o3[2 * n_sb + s] != pcs->sharp_edge_sb_flag[s];
+                svtb200_oracle_edge_cu(ym, cbm, crm, fl, n_sb, pcs->picture_number, ecu);
+                for (int s = 0; s < n_sb; s++)
+                    for (int b = 0; b < 16; b++) { ecbad += ecu[s * 16 + b] != pcs->sb_stat_array[s].cu_stat_array[5 + b].edge_cu; ecset += ecu[s * 16 + b]; }
+                free(ym); free(cbm); free(crm); free(vr); free(o3); free(fl); free(ecu);
+            }
+            /* ... and the noise detection (detect_input_picture_noise, full-sample method) -- on pictures the denoiser left alone: what motion
+             * estimation sees is then still what picture analysis measured (classes from 3_1 up, and flat-noise super-blocks at 4K, are
+             * filtered in place, EbPictureAnalysisProcess.c:3358) */
+            if (pcs->noise_detection_method == NOISE_DETECT_FULL_PRECISION && pcs->pic_noise_class < PIC_NOISE_CLASS_3_1 && scs->input_resolution != INPUT_SIZE_4K_RANGE) {
+                const uint8_t *luma = ip->buffer_y + (size_t)ip->origin_y * ip->stride_y + ip->origin_x;
+                uint8_t *den = (uint8_t *)malloc((size_t)ip->width * ip->height), *fl = (uint8_t *)malloc((size_t)n_sb);
+                uint64_t *nv = (uint64_t *)malloc((size_t)n_sb * 8), *dv = (uint64_t *)malloc((size_t)n_sb * 8), tot[2];
+                svtb200_oracle_noise_detect(luma, ip->stride_y, ip->width, ip->height, den, ip->width, pcs->noise_detection_th == 1 ? 70000 : 120000 /* NOISE_MIN_LEVEL_0 / _1 */,
+                                            50 /* FLAT_MAX_VAR */, nv, dv, fl, tot);
+                for (int s = 0; s < n_sb; s++) { nbad += fl[s] != pcs->sb_flat_noise_array[s]; nflat += fl[s]; }
+                const uint64_t v = tot[1] ? tot[0] / tot[1] : 0, th = scs->luma_height <= 720 ? 25 : 0; /* the class thresholds of :3587-3615 */
+                int cls = v >= 80 + th ? 11 : v >= 70 + th ? 10 : v >= 60 + th ? 9 : v >= 50 + th ? 8 : v >= 40 + th ? 7 : v >= 30 + th ? 6 : v >= 20 + th ? 5 : v >= 17 + th ? 4 :
+                          v >= 10 + th ? 3 : v >= 5 + th ? 2 : 1;
+                if (cls >= PIC_NOISE_CLASS_4) cls = PIC_NOISE_CLASS_3_1;
+                nbad += cls != (int)pcs->pic_noise_class;
+                npics++;
+                free(den); free(fl); free(nv); free(dv);
+            }
+            /* the decimated methods (quarter_sample_detect_noise on the 1/4 plane, sub_sample_detect_noise on the 1/16 plane): comparable on
+             * pictures of class 1 and 3, which sub_sample_filter_noise leaves alone (:4089-4100) */
+            if (pcs->noise_detection_method != NOISE_DETECT_FULL_PRECISION && (pcs->pic_noise_class == PIC_NOISE_CLASS_1 || pcs->pic_noise_class == PIC_NOISE_CLASS_3)) {
+                const int quarter = pcs->noise_detection_method == NOISE_DETECT_QUARTER_PRECISION;
+                const SvtB200Plane *dp = quarter ? &cur[1] : &cur[2];
+                if (dp->buf) {
+                    const int pw = (scs->luma_width + 63) / 64;
+                    const uint8_t *d0 = dp->buf + (size_t)dp->origin_y * dp->stride + dp->origin_x;
+                    uint8_t *den = (uint8_t *)malloc((size_t)dp->width * dp->height), *fl = (uint8_t *)malloc((size_t)n_sb);
+                    uint64_t *nv = (uint64_t *)malloc((size_t)n_sb * 8), *dv = (uint64_t *)malloc((size_t)n_sb * 8), tot[2];
+                    svtb200_oracle_noise_detect_decimated(d0, dp->stride, dp->width, dp->height, quarter ? 32 : 16, pw, n_sb, den, dp->width,
+                                                          pcs->noise_detection_th == 1 ? 70000 : 120000 /* NOISE_MIN_LEVEL_DECIM_0 / _1 */, 50 /* FLAT_MAX_VAR_DECIM */, nv, dv, fl, tot);
+                    for (int s = 0; s < n_sb; s++) { nbad += fl[s] != pcs->sb_flat_noise_array[s]; nflat += fl[s];
+                        if (fl[s] != pcs->sb_flat_noise_array[s]) { g_dbg_row[(s / pw) & 3]++; g_dbg_col[(s % pw) & 3]++; if (fl[s]) g_dbg_mine1++; else g_dbg_ref1++; } }
+                    const uint64_t v = tot[1] ? tot[0] / tot[1] : 0;
+                    int cls;
+                    if (quarter) cls = v > 60 ? PIC_NOISE_CLASS_3_1 : v >= 10 ? PIC_NOISE_CLASS_3 : v >= 5 ? PIC_NOISE_CLASS_2 : PIC_NOISE_CLASS_1;
+                    else { const uint64_t th = scs->luma_height <= 720 ? 25 : scs->luma_height <= 1080 ? 10 : 0;
+                           cls = v >= 55 + th ? PIC_NOISE_CLASS_3_1 : v >= 10 + th ? PIC_NOISE_CLASS_3 : v >= 5 + th ? PIC_NOISE_CLASS_2 : PIC_NOISE_CLASS_1; }
+                    nbad += cls != (int)pcs->pic_noise_class;
+                    npics++;
+                    free(den); free(fl); free(nv); free(dv);
+                }
+            }
+            pthread_mutex_lock(&g_mu); g_noise_method = pcs->noise_detection_method; if ((unsigned)pcs->pic_noise_class < 12) g_noise_class_hist[pcs->pic_noise_class]++; pthread_mutex_unlock(&g_mu);
+            pthread_mutex_lock(&g_mu); g_hist_pics++; g_hist_bad += hb; g_chroma_bad += cbad; g_chroma_hist_bad += chb;
+            g_edge_bad += ebad; g_edge_cu_bad += ecbad; g_edge_cu_set += ecset; g_noise_pics += npics; g_noise_bad += nbad; g_noise_flat_set += nflat; pthread_mutex_unlock(&g_mu);
         }
         {   /* the picture-analysis statistics of this SB (compute_block_mean_compute_variance) against the oracle restatement */
             SvtB200Plane one = cur[0];

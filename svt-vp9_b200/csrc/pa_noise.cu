@@ -20,20 +20,43 @@ int svtb200_noise_filter_dev(SvtB200Ctx *c, int kind, const uint8_t *in, int32_t
     return SVTB200_OK;
 }
 
-int svtb200_noise_detect_dev(SvtB200Ctx *c, const uint8_t *in, int32_t in_stride, int32_t w, int32_t h, uint8_t *den, int32_t den_stride, uint64_t noise_th,
-                             uint64_t den_th, uint64_t *noise_var, uint64_t *den_var, uint8_t *flat, uint64_t *totals) {
+static int noise_detect_launch(SvtB200Ctx *c, const uint8_t *in, int32_t in_stride, int32_t w, int32_t h, int32_t block, int32_t pw, int32_t n_sb, uint8_t *den,
+                               int32_t den_stride, uint64_t noise_th, uint64_t den_th, uint64_t *noise_var, uint64_t *den_var, uint8_t *flat, uint64_t *totals) {
     if (!c || !in || !den || !noise_var || !den_var || !flat || !totals || w < 3 || h < 3 || in_stride < w || den_stride < w) return SVTB200_EINVAL;
     std::lock_guard<std::recursive_mutex> g(c->mu);
     cudaSetDevice(c->device);
     NoiseDetArgs A;
-    A.in = in; A.is = in_stride; A.w = w; A.h = h; A.den = den; A.ds = den_stride; A.sbs_w = (w + 63) / 64;
+    A.in = in; A.is = in_stride; A.w = w; A.h = h; A.den = den; A.ds = den_stride;
+    A.block = block; A.pw = pw; A.n_sb = n_sb;
     A.noise_th = noise_th; A.den_th = den_th;
     A.noise_var = (unsigned long long *)noise_var; A.den_var = (unsigned long long *)den_var; A.totals = (unsigned long long *)totals; A.flat = flat;
     SVTB200_CUDA_CHECK(c, cudaMemsetAsync(totals, 0, 16, c->stream));
-    noise_detect_kernel<<<A.sbs_w * ((h + 63) / 64), 256, 0, c->stream>>>(A);
-    c->launches++;
+    int areas;
+    if (block == 64) { A.sbs_w = (w + 63) / 64; areas = A.sbs_w * ((h + 63) / 64); }
+    else { /* the reference walks whole 64x64 areas of the decimated plane only; super-blocks it never visits keep zeros */
+        A.sbs_w = w / 64; areas = A.sbs_w * (h / 64);
+        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(noise_var, 0, (size_t)n_sb * 8, c->stream));
+        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(den_var, 0, (size_t)n_sb * 8, c->stream));
+        SVTB200_CUDA_CHECK(c, cudaMemsetAsync(flat, 0, (size_t)n_sb, c->stream));
+    }
+    if (areas > 0) {
+        noise_detect_kernel<<<areas, 256, 0, c->stream>>>(A);
+        c->launches++;
+    }
     SVTB200_CUDA_CHECK(c, cudaGetLastError());
     return SVTB200_OK;
+}
+
+int svtb200_noise_detect_dev(SvtB200Ctx *c, const uint8_t *in, int32_t in_stride, int32_t w, int32_t h, uint8_t *den, int32_t den_stride, uint64_t noise_th,
+                             uint64_t den_th, uint64_t *noise_var, uint64_t *den_var, uint8_t *flat, uint64_t *totals) {
+    return noise_detect_launch(c, in, in_stride, w, h, 64, (w + 63) / 64, ((w + 63) / 64) * ((h + 63) / 64), den, den_stride, noise_th, den_th, noise_var, den_var, flat, totals);
+}
+
+int svtb200_noise_detect_decimated_dev(SvtB200Ctx *c, const uint8_t *in, int32_t in_stride, int32_t w, int32_t h, int32_t block, int32_t picture_width_in_sb, int32_t n_sb,
+                                       uint8_t *den, int32_t den_stride, uint64_t noise_th, uint64_t den_th, uint64_t *noise_var, uint64_t *den_var, uint8_t *flat,
+                                       uint64_t *totals) {
+    if ((block != 32 && block != 16) || picture_width_in_sb <= 0 || n_sb <= 0) return SVTB200_EINVAL;
+    return noise_detect_launch(c, in, in_stride, w, h, block, picture_width_in_sb, n_sb, den, den_stride, noise_th, den_th, noise_var, den_var, flat, totals);
 }
 
 int svtb200_edge_detection_dev(SvtB200Ctx *c, const uint8_t *y_mean, const uint16_t *variance, int32_t w, int32_t h, uint8_t *edge_block_num, uint8_t *isolated,

@@ -34,19 +34,52 @@ __global__ void __launch_bounds__(128) noise_filter_kernel(const uint8_t *in, in
     }
 }
 
-/* ---- detect_input_picture_noise: weak filter + the 64x64 variances of noise and denoised samples, one CTA per super-block ---- */
+/* ---- detect_input_picture_noise (:3512) and its decimated twins quarter_sample_detect_noise (:3809, block 32 on the 1/4 plane) /
+ * sub_sample_detect_noise (:3930, block 16 on the 1/16 plane): weak filter + the variances of the noise and of the denoised samples of every
+ * block x block area (= one full-resolution super-block), one CTA per 64x64 area of the plane.  What the reference does differently for
+ * block < 64, reproduced because sb_flat_noise_array depends on it: (1) only floor(w / 64) x floor(h / 64) areas are walked (grid);
+ * (2) the 8x8 means take ALL eight rows (compute_mean_func, EbComputeMean.h:21) where the 64x64 routine takes rows 0, 2, 4, 6;
+ * (3) compute_variance32x32 pairs the 8x8 blocks {2i, 2i+1, 2i+8, 2i+9} of its 4-wide numbering (:300-312); (4) the NOISE variance of
+ * every block of a 64-row band is taken from the band's first `block` noise rows (noise_origin_index has no row offset inside the band). ---- */
 struct NoiseDetArgs {
     const uint8_t *in; int32_t is, w, h;
     uint8_t *den; int32_t ds;
-    int32_t sbs_w;
+    int32_t sbs_w;            /* 64x64 areas per row of the grid */
+    int32_t block, pw, n_sb;  /* block 64: sb = area index; block 32 / 16: sb = (by / block) * pw + bx / block */
     unsigned long long noise_th, den_th;
     unsigned long long *noise_var, *den_var, *totals;
     uint8_t *flat;
 };
+/* variance of sub-block (vi, hi) of the tile from the 8x8 tables (64 entries, 8 per row); noise_rows: take block row 0 of the band (quirk 4) */
+__device__ __forceinline__ unsigned long long nz_block_variance(const unsigned long long *m, const unsigned long long *q, int block, int vi, int hi) {
+    if (block == 64) {
+        unsigned long long m16[16], q16[16], m32[4], q32[4];
+        for (int i = 0; i < 16; i++) { const int a = (2 * (i >> 2)) * 8 + 2 * (i & 3); m16[i] = (m[a] + m[a + 1] + m[a + 8] + m[a + 9]) >> 2; q16[i] = (q[a] + q[a + 1] + q[a + 8] + q[a + 9]) >> 2; }
+        for (int i = 0; i < 4; i++) { const int a = (2 * (i >> 1)) * 4 + 2 * (i & 1); m32[i] = (m16[a] + m16[a + 1] + m16[a + 4] + m16[a + 5]) >> 2; q32[i] = (q16[a] + q16[a + 1] + q16[a + 4] + q16[a + 5]) >> 2; }
+        const unsigned long long mm = (m32[0] + m32[1] + m32[2] + m32[3]) >> 2, qq = (q32[0] + q32[1] + q32[2] + q32[3]) >> 2;
+        return qq - mm * mm;
+    }
+    if (block == 32) {
+        unsigned long long m16[4], q16[4];
+#define NZ_AT(k) (((vi) * 4 + ((k) >> 2)) * 8 + (hi) * 4 + ((k) & 3)) /* 8x8 block k (four per row) of the 32x32 block, in the tile's table */
+        for (int i = 0; i < 4; i++) {
+            const int a = 2 * i;
+            m16[i] = (m[NZ_AT(a)] + m[NZ_AT(a + 1)] + m[NZ_AT(a + 8)] + m[NZ_AT(a + 9)]) >> 2;
+            q16[i] = (q[NZ_AT(a)] + q[NZ_AT(a + 1)] + q[NZ_AT(a + 8)] + q[NZ_AT(a + 9)]) >> 2;
+        }
+#undef NZ_AT
+        const unsigned long long mm = (m16[0] + m16[1] + m16[2] + m16[3]) >> 2, qq = (q16[0] + q16[1] + q16[2] + q16[3]) >> 2;
+        return qq - mm * mm;
+    }
+    const int a = (vi * 2) * 8 + hi * 2;
+    const unsigned long long mm = (m[a] + m[a + 1] + m[a + 8] + m[a + 9]) >> 2, qq = (q[a] + q[a + 1] + q[a + 8] + q[a + 9]) >> 2;
+    return qq - mm * mm;
+}
 __global__ void __launch_bounds__(256) noise_detect_kernel(const NoiseDetArgs A) {
     __shared__ uint8_t den_s[64][64 + 4], nz_s[64][64 + 4];
     __shared__ unsigned long long m_s[2][64], q_s[2][64]; /* [noise, denoised][8x8 block]: 8.8 means, 16.16 means of squares */
-    const int sb = blockIdx.x, sx = (sb % A.sbs_w) * 64, sy = (sb / A.sbs_w) * 64, t = threadIdx.x;
+    __shared__ unsigned long long var_s[2][16];
+    const int tile = blockIdx.x, sx = (tile % A.sbs_w) * 64, sy = (tile / A.sbs_w) * 64, t = threadIdx.x;
     const bool complete = sx + 64 <= A.w && sy + 64 <= A.h;
     for (int i = t; i < 4096; i += 256) {
         const int y = i >> 6, x = i & 63, px = sx + x, py = sy + y;
@@ -59,37 +92,41 @@ __global__ void __launch_bounds__(256) noise_detect_kernel(const NoiseDetArgs A)
         den_s[y][x] = (uint8_t)d;
         nz_s[y][x] = (uint8_t)(inner && v > d ? v - d : 0);
     }
-    if (!complete) { /* "do it only for complete 64x64 blocks" (:3549) */
-        if (t == 0) { A.noise_var[sb] = 0; A.den_var[sb] = 0; A.flat[sb] = 0; }
+    if (!complete) { /* "do it only for complete 64x64 blocks" (:3549); the decimated walks never get here (their grid holds whole areas only) */
+        if (t == 0 && A.block == 64) { A.noise_var[tile] = 0; A.den_var[tile] = 0; A.flat[tile] = 0; }
         return;
     }
     __syncthreads();
-    if (t < 128) { /* 8x8 sums of rows 0, 2, 4, 6 (eb_vp9_compute_sub_mean8x8 / subd_mean_of_squared_values8x8) */
+    const bool all_rows = A.block != 64;
+    if (t < 128) { /* 8x8 sums: rows 0, 2, 4, 6 (eb_vp9_compute_sub_mean8x8 ...) for the 64x64 routine, every row (compute_mean ...) for the others */
         const int which = t >> 6, b = t & 63, bx = (b & 7) * 8, by = (b >> 3) * 8;
         uint32_t sum = 0, sq = 0;
 #pragma unroll
-        for (int r = 0; r < 8; r += 2)
+        for (int r = 0; r < 8; r++) {
+            if ((r & 1) && !all_rows) continue;
 #pragma unroll
             for (int k = 0; k < 8; k++) { const uint32_t v = which ? den_s[by + r][bx + k] : nz_s[by + r][bx + k]; sum += v; sq += v * v; }
-        m_s[which][b] = (unsigned long long)sum << 3;
-        q_s[which][b] = (unsigned long long)sq << 11;
+        }
+        m_s[which][b] = (unsigned long long)sum << (all_rows ? 2 : 3);
+        q_s[which][b] = (unsigned long long)sq << (all_rows ? 10 : 11);
     }
     __syncthreads();
-    if (t < 2) { /* quadrant averages up to 64x64 (compute_variance64x64, :408) */
-        unsigned long long m16[16], q16[16], m32[4], q32[4];
-        const unsigned long long *m = m_s[t], *q = q_s[t];
-        for (int i = 0; i < 16; i++) { const int a = (2 * (i >> 2)) * 8 + 2 * (i & 3); m16[i] = (m[a] + m[a + 1] + m[a + 8] + m[a + 9]) >> 2; q16[i] = (q[a] + q[a + 1] + q[a + 8] + q[a + 9]) >> 2; }
-        for (int i = 0; i < 4; i++) { const int a = (2 * (i >> 1)) * 4 + 2 * (i & 1); m32[i] = (m16[a] + m16[a + 1] + m16[a + 4] + m16[a + 5]) >> 2; q32[i] = (q16[a] + q16[a + 1] + q16[a + 4] + q16[a + 5]) >> 2; }
-        const unsigned long long m64 = (m32[0] + m32[1] + m32[2] + m32[3]) >> 2, q64 = (q32[0] + q32[1] + q32[2] + q32[3]) >> 2;
-        m_s[t][0] = q64 - m64 * m64;
+    const int nb = 64 / A.block, nsub = nb * nb; /* sub-blocks of the area */
+    if (t < 2 * nsub) {
+        const int which = t / nsub, k = t % nsub, vi = k / nb, hi = k % nb;
+        var_s[which][k] = nz_block_variance(m_s[which], q_s[which], A.block, which ? vi : 0, hi); /* noise: the band's first block row */
     }
     __syncthreads();
-    if (t == 0) {
-        const unsigned long long nv = m_s[0][0], dv = m_s[1][0] >> 16;
-        A.noise_var[sb] = nv; A.den_var[sb] = dv;
-        A.flat[sb] = dv < A.den_th && nv > A.noise_th;
-        atomicAdd(&A.totals[0], nv >> 16);
-        atomicAdd(&A.totals[1], 1ull);
+    if (t < nsub) {
+        const int vi = t / nb, hi = t % nb;
+        const int sb = A.block == 64 ? tile : ((sy / A.block) + vi) * A.pw + (sx / A.block) + hi;
+        if (sb < A.n_sb) {
+            const unsigned long long nv = var_s[0][t], dv = var_s[1][t] >> 16;
+            A.noise_var[sb] = nv; A.den_var[sb] = dv;
+            A.flat[sb] = dv < A.den_th && nv > A.noise_th;
+            atomicAdd(&A.totals[0], nv >> 16);
+            atomicAdd(&A.totals[1], 1ull);
+        }
     }
 }
 

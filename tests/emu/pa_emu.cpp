@@ -11,14 +11,17 @@ extern "C" int pa_emu_noise_filter(int kind, const uint8_t *in, int is, int w, i
     return 0;
 }
 
-extern "C" int pa_emu_noise_detect(const uint8_t *in, int is, int w, int h, uint8_t *den, int ds, uint64_t noise_th, uint64_t den_th, uint64_t *noise_var,
-                                   uint64_t *den_var, uint8_t *flat, uint64_t *totals) {
+extern "C" int pa_emu_noise_detect(const uint8_t *in, int is, int w, int h, int block, int pw, int n_sb, uint8_t *den, int ds, uint64_t noise_th, uint64_t den_th,
+                                   uint64_t *noise_var, uint64_t *den_var, uint8_t *flat, uint64_t *totals) {
     NoiseDetArgs A;
-    A.in = in; A.is = is; A.w = w; A.h = h; A.den = den; A.ds = ds; A.sbs_w = (w + 63) / 64;
+    A.in = in; A.is = is; A.w = w; A.h = h; A.den = den; A.ds = ds; A.block = block; A.pw = pw; A.n_sb = n_sb;
     A.noise_th = noise_th; A.den_th = den_th;
     A.noise_var = (unsigned long long *)noise_var; A.den_var = (unsigned long long *)den_var; A.totals = (unsigned long long *)totals; A.flat = flat;
     totals[0] = totals[1] = 0;
-    emu_launch(dim3((unsigned)(A.sbs_w * ((h + 63) / 64))), dim3(256), 0, [&] { noise_detect_kernel(A); });
+    int areas;
+    if (block == 64) { A.sbs_w = (w + 63) / 64; areas = A.sbs_w * ((h + 63) / 64); }
+    else { A.sbs_w = w / 64; areas = A.sbs_w * (h / 64); for (int i = 0; i < n_sb; i++) { noise_var[i] = den_var[i] = 0; flat[i] = 0; } }
+    if (areas > 0) emu_launch(dim3((unsigned)areas), dim3(256), 0, [&] { noise_detect_kernel(A); });
     return 0;
 }
 

@@ -4,6 +4,9 @@
 reference's own functions -- plain C and the AVX2 entries of its dispatch tables -- through the path driver; the CUDA kernels
 (csrc/pa_noise.cu) against the oracle."""
 import ctypes as C
+import os
+import subprocess
+import sys
 
 import numpy as np
 import pytest
@@ -11,6 +14,7 @@ import pytest
 import helpers as H
 
 api = H.api
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 NOISE_MIN_LEVEL_0, NOISE_MIN_LEVEL_1, FLAT_MAX_VAR = 70000, 120000, 50   # EbPictureAnalysisProcess.c:32-35
 KINDS = ["luma_weak", "luma_strong", "chroma_weak", "chroma_strong"]
 
@@ -19,6 +23,8 @@ def _O():
     O = H.oracle()
     O.svtb200_oracle_noise_filter.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
     O.svtb200_oracle_noise_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    O.svtb200_oracle_noise_detect_decimated.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
+                                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     O.svtb200_oracle_edge_detection.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     O.svtb200_oracle_edge_cu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
     return O
@@ -187,7 +193,8 @@ def test_oracle_noise_detect_is_consistent_with_the_pinned_restatements():
 def _E():
     E = H.emu()
     E.pa_emu_noise_filter.argtypes = [C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p]
-    E.pa_emu_noise_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    E.pa_emu_noise_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
+                                      C.c_void_p, C.c_void_p]
     E.pa_emu_edge_detection.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     E.pa_emu_edge_cu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return E
@@ -217,10 +224,59 @@ def test_kernel_source_noise_detect_on_the_cpu():
     n_sb = want[1].size
     den = np.full_like(a, 0x33)
     nv, dv, flat, tot = np.zeros(n_sb, np.uint64), np.zeros(n_sb, np.uint64), np.zeros(n_sb, np.uint8), np.zeros(2, np.uint64)
-    _E().pa_emu_noise_detect(a.ctypes.data + y0 * stride + x0, stride, w, h, den.ctypes.data + y0 * stride + x0, stride, NOISE_MIN_LEVEL_0, FLAT_MAX_VAR,
-                             nv.ctypes.data, dv.ctypes.data, flat.ctypes.data, tot.ctypes.data)
+    _E().pa_emu_noise_detect(a.ctypes.data + y0 * stride + x0, stride, w, h, 64, (w + 63) // 64, n_sb, den.ctypes.data + y0 * stride + x0, stride, NOISE_MIN_LEVEL_0,
+                             FLAT_MAX_VAR, nv.ctypes.data, dv.ctypes.data, flat.ctypes.data, tot.ctypes.data)
     for g, wv, name in zip((den[y0:y0 + h, x0:x0 + w], nv, dv, flat, tot), want, ("denoised", "noise_var", "den_var", "flat", "totals")):
         assert (g == wv).all(), name
+
+
+# ---- the decimated detection methods (quarter_sample_detect_noise: block 32 on the 1/4 plane, sub_sample_detect_noise: block 16 on the 1/16 plane).
+# The oracle restatement is pinned inside real encodes of the unmodified reference (oracle/ref_seam_check.c: sb_flat_noise_array and pic_noise_class
+# of every comparable picture, both methods, flags set: test_oracle_noise_detection_pinned_inside_real_encodes below).
+def _decimated_case(rng, luma_w, luma_h, block):
+    step = 64 // block                       # 2: quarter plane, 4: sixteenth plane
+    w, h = luma_w // step, luma_h // step
+    a, y0, x0, stride = _noisy_picture(rng, w, h)
+    pw, n_sb = (luma_w + 63) // 64, ((luma_w + 63) // 64) * ((luma_h + 63) // 64)
+    return a, y0, x0, stride, w, h, pw, n_sb
+
+
+def oracle_noise_detect_decimated(a, y0, x0, stride, w, h, block, pw, n_sb, noise_th, den_th=FLAT_MAX_VAR):
+    den = np.full_like(a, 0x5a)
+    nv, dv, flat, tot = np.zeros(n_sb, np.uint64), np.zeros(n_sb, np.uint64), np.zeros(n_sb, np.uint8), np.zeros(2, np.uint64)
+    _O().svtb200_oracle_noise_detect_decimated(a.ctypes.data + y0 * stride + x0, stride, w, h, block, pw, n_sb, den.ctypes.data + y0 * stride + x0, stride, noise_th, den_th,
+                                               nv.ctypes.data, dv.ctypes.data, flat.ctypes.data, tot.ctypes.data)
+    return nv, dv, flat, tot
+
+
+@pytest.mark.parametrize("luma_w,luma_h,block", [(704, 456, 32), (1088, 840, 16)])
+def test_kernel_source_decimated_noise_detect_on_the_cpu(luma_w, luma_h, block):
+    rng = np.random.default_rng(block)
+    a, y0, x0, stride, w, h, pw, n_sb = _decimated_case(rng, luma_w, luma_h, block)
+    want = oracle_noise_detect_decimated(a, y0, x0, stride, w, h, block, pw, n_sb, NOISE_MIN_LEVEL_0)
+    den = np.full_like(a, 0x33)
+    got = [np.full(n_sb, 7, np.uint64), np.full(n_sb, 7, np.uint64), np.full(n_sb, 7, np.uint8), np.zeros(2, np.uint64)]
+    _E().pa_emu_noise_detect(a.ctypes.data + y0 * stride + x0, stride, w, h, block, pw, n_sb, den.ctypes.data + y0 * stride + x0, stride, NOISE_MIN_LEVEL_0, FLAT_MAX_VAR,
+                             *[g.ctypes.data for g in got])
+    for g, wv, name in zip(got, want, ("noise_var", "den_var", "flat", "totals")):
+        assert (g == wv).all(), name
+    visited = (w // 64) * (h // 64) * (64 // block) ** 2
+    assert want[3][1] == visited and visited < (w // block) * (h // block)      # areas right of / below the last whole 64x64 area are not walked
+    assert want[2].any() and (want[0][want[1] > 0] > 0).any()
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "SvtVp9EncApp_seam")), reason="oracle/_ref seam-check flavour not built")
+@pytest.mark.parametrize("args,method", [("960 544 8 0 6 8 20 1", 2), ("1920 1080 8 1 5 6 16 1", 1), ("3840 2160 8 1 3 5 12 1", 0)], ids=["full", "quarter", "half"])
+def test_oracle_noise_detection_pinned_inside_real_encodes(args, method):
+    """the unmodified reference encodes a smooth, mildly noisy clip; the seam check recomputes the noise detection of every picture the denoiser left
+    alone with the oracle (the method the reference picked: full sample at 540p, quarter at 1080p, half = 1/16 plane at 4K) and compares the
+    flat-noise flags of all super-blocks and the picture's noise class; the edge maps are compared on every picture as well"""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "run_seam_check.py")] + args.split(), stdout=subprocess.PIPE, timeout=900)
+    out = dict(l.split() for l in r.stdout.decode().strip().splitlines() if len(l.split()) == 2)
+    assert int(out["noise_method"]) == method, out
+    assert int(out["noise_pics"]) >= 2 and int(out["noise_flat_set"]) > 0, out       # pictures were comparable and flags were set
+    for k in ("noise_bad", "edge_bad", "edge_cu_bad", "sb_bad", "stats_bad"):
+        assert int(out[k]) == 0, out
 
 
 @pytest.mark.parametrize("w,h", [(832, 704), (640, 480)])
@@ -302,6 +358,31 @@ def test_cuda_noise_filters_and_detection(w, h):
         for d, o, wv, name in zip(d_out, outs, want[1:], ("noise_var", "den_var", "flat", "totals")):
             assert (D.down(d, o) == wv).all(), name
         assert want[3].any() or w < 1000   # (a handful of super-blocks need not hold a flat noisy one)
+    finally:
+        D.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("luma_w,luma_h,block", [(1920, 1080, 32), (3840, 2160, 16), (704, 456, 32)], ids=["1080p-quarter", "4k-sixteenth", "704x456-quarter"])
+def test_cuda_decimated_noise_detection(luma_w, luma_h, block):
+    rng = np.random.default_rng(luma_w + block)
+    a, y0, x0, stride, w, h, pw, n_sb = _decimated_case(rng, luma_w, luma_h, block)
+    want = oracle_noise_detect_decimated(a, y0, x0, stride, w, h, block, pw, n_sb, NOISE_MIN_LEVEL_1)
+    D = _Dev()
+    L, hd = D.ctx.L, D.ctx.h
+    L.svtb200_noise_detect_decimated_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_int32,
+                                                     C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    try:
+        d_in, d_den = D.up(a), D.up(np.full_like(a, 0x33))
+        outs = [np.full(n_sb, 7, np.uint64), np.full(n_sb, 7, np.uint64), np.full(n_sb, 7, np.uint8), np.zeros(2, np.uint64)]
+        d_out = [D.up(o) for o in outs]
+        off = y0 * stride + x0
+        D.ctx.check(L.svtb200_noise_detect_decimated_dev(hd, d_in + off, stride, w, h, block, pw, n_sb, d_den + off, stride, NOISE_MIN_LEVEL_1, FLAT_MAX_VAR, *d_out),
+                    "noise_detect_decimated")
+        D.ctx.sync()
+        for d, o, wv, name in zip(d_out, outs, want, ("noise_var", "den_var", "flat", "totals")):
+            assert (D.down(d, o) == wv).all(), name
+        assert want[2].any()
     finally:
         D.close()
 
