@@ -302,6 +302,12 @@ int svtb200_noise_detect_decimated_dev(SvtB200Ctx *ctx, const uint8_t *in_dev, i
  * (compute_picture_spatial_statistics, :4827) is produced on the way. */
 int svtb200_edge_detection_dev(SvtB200Ctx *ctx, const uint8_t *y_mean_dev, const uint16_t *variance_dev, int32_t luma_width, int32_t luma_height,
                                uint8_t *edge_block_num_dev, uint8_t *isolated_dev, uint8_t *sharp_edge_dev, uint16_t *pic_avg_variance_dev);
+/* determine_homogeneous_region_in_picture() (:4660) on the same block statistics: var_of_var_32x32_based_sb_array ([n_sb][4]: the variance of
+ * the sixteen 8x8 variances of each 32x32 quadrant; all ones for incomplete super-blocks), sb_homogeneous_area_array (64x64 variance of
+ * variances <= detail_th = VAR_BASED_DETAIL_PRESERVATION_SELECTOR_THRSLHD), and counts[3] = {complete super-blocks, those with 64x64 variance
+ * < low_var_th = SB_LOW_VAR_TH, those with variance 0}: very_low_var_pic_flag / logo_pic_flag are counts[1] * 100 / counts[0] > 60 / > 80. */
+int svtb200_homogeneous_regions_dev(SvtB200Ctx *ctx, const uint16_t *variance_dev, int32_t luma_width, int32_t luma_height, uint32_t low_var_th,
+                                    uint64_t detail_th, uint64_t *var_of_var32_dev, uint8_t *homogeneous_dev, uint64_t *counts_dev);
 /* edge_detection_mean_luma_chroma16x16() (:4434): edge_cu of the sixteen 16x16 blocks of every super-block ([n_sb][16], raster order) from
  * the 16x16 means of luma ([n_sb][85]) and chroma ([n_sb][21], svtb200_chroma_block_mean_dev); logo_flags[sb] = SbParams::potential_logo_sb
  * (a function of the picture size, EbSequenceControlSet.c:332-400; completeness is derived here); zeros unless picture_number is a multiple

@@ -61,6 +61,9 @@ void svtb200_oracle_edge_detection(const uint8_t *y_mean, const uint16_t *varian
 void svtb200_oracle_edge_cu(const uint8_t *y_mean, const uint8_t *cb_mean, const uint8_t *cr_mean, const uint8_t *sb_flags, int n_sb, uint64_t picture_number,
                             uint8_t *edge_cu);
 
+void svtb200_oracle_homogeneous_regions(const uint16_t *variance, int w, int h, uint32_t low_var_th, uint64_t detail_th, uint64_t *var_of_var32, uint8_t *homogeneous,
+                                        uint64_t counts[3]);
+
 /* block walk in front of the inter predictors, open-loop partition of the bench: blocks_port.c */
 void svtb200_oracle_inter_expand(const SvtB200InterBlock *blocks, int n, const SvtB200PredPicture *pic, SvtB200PredBlock *out);
 int  svtb200_oracle_me_best_blocks(const SvtB200MeCuResult *me, int width, int height, SvtB200InterBlock *out);

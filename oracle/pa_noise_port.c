@@ -211,3 +211,30 @@ void svtb200_oracle_edge_cu(const uint8_t *y_mean, const uint8_t *cb_mean, const
                 edge_cu[(size_t)sb * 16 + b] = (uint16_t)(v < 255 ? v : 255) < 30 ? 0 : 1;
             }
 }
+
+/* determine_homogeneous_region_in_picture (:4660): the variance of the 8x8 variances inside each 32x32 quadrant and inside the 64x64 of every
+ * COMPLETE super-block (incomplete: all ones / homogeneous), the homogeneous-area flag (64x64 variance of variance <= detail_th,
+ * VAR_BASED_DETAIL_PRESERVATION_SELECTOR_THRSLHD), and the picture counts very_low_var_pic_flag / logo_pic_flag are thresholds of:
+ * counts[0] = complete super-blocks, counts[1] = those whose 64x64 variance is below low_var_th (SB_LOW_VAR_TH), counts[2] = those with variance 0.
+ * variance: [n_sb][85] as the block statistics leave them (8x8 entries 21..84, row-major 8 per row). */
+void svtb200_oracle_homogeneous_regions(const uint16_t *variance, int w, int h, uint32_t low_var_th, uint64_t detail_th, uint64_t *var_of_var32, uint8_t *homogeneous,
+                                        uint64_t counts[3]) {
+    const int sbs_w = (w + 63) / 64, sbs_h = (h + 63) / 64;
+    counts[0] = counts[1] = counts[2] = 0;
+    for (int sb = 0; sb < sbs_w * sbs_h; sb++) {
+        const uint16_t *v = variance + (size_t)sb * 85;
+        homogeneous[sb] = 1;
+        if ((sb % sbs_w) * 64 + 64 > w || (sb / sbs_w) * 64 + 64 > h) { for (int k = 0; k < 4; k++) var_of_var32[(size_t)sb * 4 + k] = ~(uint64_t)0; continue; }
+        counts[0]++; counts[1] += v[0] < low_var_th; counts[2] += v[0] == 0;
+        uint64_t s64 = 0, q64 = 0;
+        for (int k = 0; k < 4; k++) {
+            uint64_t s = 0, q = 0;
+            for (int r = 0; r < 4; r++) for (int c = 0; c < 4; c++) { const uint64_t x = v[21 + ((k >> 1) * 4 + r) * 8 + (k & 1) * 4 + c]; s += x; q += x * x; }
+            s >>= 4; q >>= 4;
+            var_of_var32[(size_t)sb * 4 + k] = q - s * s;
+        }
+        for (int i = 21; i < 85; i++) { s64 += v[i]; q64 += (uint64_t)v[i] * v[i]; }
+        s64 >>= 6; q64 >>= 6;
+        if (q64 - s64 * s64 > detail_th) homogeneous[sb] = 0;
+    }
+}

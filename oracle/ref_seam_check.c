@@ -24,7 +24,7 @@ static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static int   g_mode = -1; /* 0 off, 1 check, 2 dump */
 static char  g_dir[512];
 static long  g_sb_total, g_sb_bad, g_pu_bad, g_printed, g_stats_bad, g_hist_pics, g_hist_bad, g_chroma_bad, g_chroma_hist_bad;
-static long  g_edge_bad, g_edge_cu_bad, g_edge_cu_set, g_noise_pics, g_noise_bad, g_noise_method = -1, g_noise_class_hist[12], g_noise_flat_set, g_dbg_row[4], g_dbg_col[4], g_dbg_ref1, g_dbg_mine1;
+static long  g_edge_bad, g_edge_cu_bad, g_edge_cu_set, g_noise_pics, g_noise_bad, g_noise_method = -1, g_noise_class_hist[12], g_noise_flat_set, g_dbg_row[4], g_dbg_col[4], g_dbg_ref1, g_dbg_mine1, g_homog_bad, g_homog_nonflat;
 static int   g_max_dump_pics = 4, g_dump_from = 0;
 
 #define MAX_TRACKED 64
@@ -41,7 +41,7 @@ static void write_summary(void) {
     if (!f) return;
     fprintf(f, "sb_total %ld\nsb_bad %ld\npu_bad %ld\ndumped %d\nstats_bad %ld\nhist_pics %ld\nhist_bad %ld\nchroma_bad %ld\nchroma_hist_bad %ld\n", g_sb_total, g_sb_bad, g_pu_bad, g_dumped, g_stats_bad, g_hist_pics, g_hist_bad, g_chroma_bad, g_chroma_hist_bad);
     fprintf(f, "edge_bad %ld\nedge_cu_bad %ld\nedge_cu_set %ld\nnoise_pics %ld\nnoise_bad %ld\n", g_edge_bad, g_edge_cu_bad, g_edge_cu_set, g_noise_pics, g_noise_bad);
-    fprintf(f, "noise_flat_set %ld\nnoise_method %ld\n", g_noise_flat_set, g_noise_method);
+    fprintf(f, "noise_flat_set %ld\nnoise_method %ld\nhomog_bad %ld\nhomog_not_homogeneous %ld\n", g_noise_flat_set, g_noise_method, g_homog_bad, g_homog_nonflat);
     if (g_dbg_mine1 + g_dbg_ref1) fprintf(f, "dbg_rows %ld,%ld,%ld,%ld\ndbg_cols %ld,%ld,%ld,%ld\ndbg_only_oracle %ld\ndbg_only_reference %ld\n", g_dbg_row[0], g_dbg_row[1], g_dbg_row[2], g_dbg_row[3], g_dbg_col[0], g_dbg_col[1], g_dbg_col[2], g_dbg_col[3], g_dbg_mine1, g_dbg_ref1); /* NOISE_DETECT_HALF / QUARTER / FULL_PRECISION = 0 / 1 / 2 */
     for (int i = 0; i < 12; i++) if (g_noise_class_hist[i]) fprintf(f, "noise_class_%d %ld\n", i, g_noise_class_hist[i]);
     fclose(f);
@@ -147,6 +147,21 @@ EbErrorType __wrap_motion_estimate_sb(PictureParentControlSet *pcs, uint32_t sb_
                 for (int s = 0; s < n_sb; s++)
                     ebad += o3[s] != pcs->edge_results_ptr[s].edge_block_num || o3[n_sb + s] != pcs->edge_results_ptr[s].isolated_high_intensity_sb ||
                             o3[2 * n_sb + s] != pcs->sharp_edge_sb_flag[s];
+                {   /* determine_homogeneous_region_in_picture: variance of variances, homogeneous-area flags, the two picture flags */
+                    uint64_t *vv = (uint64_t *)malloc((size_t)n_sb * 32), cnt[3];
+                    uint8_t *hm = (uint8_t *)malloc((size_t)n_sb);
+                    long hbad = 0, hnf = 0;
+                    svtb200_oracle_homogeneous_regions(vr, scs->luma_width, scs->luma_height, 5 /* SB_LOW_VAR_TH */, 64 * 64 /* VAR_BASED_DETAIL_PRESERVATION_SELECTOR_THRSLHD */, vv, hm, cnt);
+                    for (int s = 0; s < n_sb; s++) {
+                        for (int k = 0; k < 4; k++) hbad += vv[(size_t)s * 4 + k] != pcs->var_of_var_32x32_based_sb_array[s][k];
+                        hbad += (hm[s] != 0) != (pcs->sb_homogeneous_area_array[s] != 0);
+                        hnf += !hm[s];
+                    }
+                    hbad += (cnt[0] > 0 && (cnt[1] * 100) / cnt[0] > 60 /* PIC_LOW_VAR_PERCENTAGE_TH */) != (pcs->very_low_var_pic_flag != 0);
+                    hbad += (cnt[0] > 0 && (cnt[1] * 100) / cnt[0] > 80) != (pcs->logo_pic_flag != 0);
+                    free(vv); free(hm);
+                    pthread_mutex_lock(&g_mu); g_homog_bad += hbad; g_homog_nonflat += hnf; pthread_mutex_unlock(&g_mu);
+                }
                 svtb200_oracle_edge_cu(ym, cbm, crm, fl, n_sb, pcs->picture_number, ecu);
                 for (int s = 0; s < n_sb; s++)
                     for (int b = 0; b < 16; b++) { ecbad += ecu[s * 16 + b] != pcs->sb_stat_array[s].cu_stat_array[5 + b].edge_cu; ecset += ecu[s * 16 + b]; }

@@ -72,6 +72,20 @@ int svtb200_edge_detection_dev(SvtB200Ctx *c, const uint8_t *y_mean, const uint1
     return SVTB200_OK;
 }
 
+int svtb200_homogeneous_regions_dev(SvtB200Ctx *c, const uint16_t *variance, int32_t w, int32_t h, uint32_t low_var_th, uint64_t detail_th, uint64_t *var_of_var32,
+                                    uint8_t *homogeneous, uint64_t *counts) {
+    if (!c || !variance || !var_of_var32 || !homogeneous || !counts || w <= 0 || h <= 0) return SVTB200_EINVAL;
+    std::lock_guard<std::recursive_mutex> g(c->mu);
+    cudaSetDevice(c->device);
+    const int sbs_w = (w + 63) / 64, n = sbs_w * ((h + 63) / 64);
+    SVTB200_CUDA_CHECK(c, cudaMemsetAsync(counts, 0, 24, c->stream));
+    homogeneous_regions_kernel<<<(n + 127) / 128, 128, 0, c->stream>>>(variance, w, h, sbs_w, n, low_var_th, detail_th, (unsigned long long *)var_of_var32, homogeneous,
+                                                                    (unsigned long long *)counts);
+    c->launches++;
+    SVTB200_CUDA_CHECK(c, cudaGetLastError());
+    return SVTB200_OK;
+}
+
 int svtb200_edge_cu_dev(SvtB200Ctx *c, const uint8_t *y_mean, const uint8_t *cb_mean, const uint8_t *cr_mean, const uint8_t *logo_flags, int32_t w, int32_t h,
                         uint64_t picture_number, uint8_t *edge_cu, uint32_t *max_grad) {
     if (!c || !y_mean || !cb_mean || !cr_mean || !logo_flags || !edge_cu || !max_grad || w <= 0 || h <= 0) return SVTB200_EINVAL;

@@ -202,4 +202,33 @@ __global__ void edge_cu_kernel(const uint8_t *y_mean, const uint8_t *cb_mean, co
         edge_cu[i] = on && v >= 30;
     }
 }
+/* ---- determine_homogeneous_region_in_picture (:4660): one thread per super-block on the 64 8x8 variances the block statistics left ---- */
+__global__ void homogeneous_regions_kernel(const uint16_t *variance, int w, int h, int sbs_w, int n_sb, uint32_t low_var_th, unsigned long long detail_th,
+                                           unsigned long long *var_of_var32, uint8_t *homogeneous, unsigned long long *counts) {
+    const int sb = blockIdx.x * blockDim.x + threadIdx.x;
+    if (sb >= n_sb) return;
+    const uint16_t *v = variance + (size_t)sb * 85;
+    uint8_t hom = 1;
+    if ((sb % sbs_w) * 64 + 64 > w || (sb / sbs_w) * 64 + 64 > h) { /* "should be re-calculated and scaled properly" (:4762): all ones */
+#pragma unroll
+        for (int k = 0; k < 4; k++) var_of_var32[(size_t)sb * 4 + k] = ~0ull;
+    } else {
+        unsigned long long s64 = 0, q64 = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            unsigned long long s = 0, q = 0;
+            for (int r = 0; r < 4; r++)
+                for (int c = 0; c < 4; c++) { const unsigned long long x = v[21 + ((k >> 1) * 4 + r) * 8 + (k & 1) * 4 + c]; s += x; q += x * x; }
+            s64 += s; q64 += q;
+            s >>= 4; q >>= 4;
+            var_of_var32[(size_t)sb * 4 + k] = q - s * s;
+        }
+        s64 >>= 6; q64 >>= 6;
+        hom = !(q64 - s64 * s64 > detail_th);
+        atomicAdd(&counts[0], 1ull);
+        if (v[0] < low_var_th) atomicAdd(&counts[1], 1ull);
+        if (v[0] == 0) atomicAdd(&counts[2], 1ull);
+    }
+    homogeneous[sb] = hom;
+}
 #endif

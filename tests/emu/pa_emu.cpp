@@ -39,3 +39,10 @@ extern "C" int pa_emu_edge_cu(const uint8_t *y_mean, const uint8_t *cb, const ui
     emu_launch(dim3((unsigned)blocks), dim3(256), 0, [&] { edge_cu_kernel<1>(y_mean, cb, cr, logo, w, h, sbs_w, n, max_grad, edge_cu); });
     return 0;
 }
+
+extern "C" int pa_emu_homogeneous(const uint16_t *variance, int w, int h, uint32_t low_var_th, uint64_t detail_th, uint64_t *vv, uint8_t *hom, uint64_t *counts) {
+    const int sbs_w = (w + 63) / 64, n = sbs_w * ((h + 63) / 64);
+    counts[0] = counts[1] = counts[2] = 0;
+    emu_launch(dim3((unsigned)((n + 127) / 128)), dim3(128), 0, [&] { homogeneous_regions_kernel(variance, w, h, sbs_w, n, low_var_th, detail_th, (unsigned long long *)vv, hom, (unsigned long long *)counts); });
+    return 0;
+}

@@ -26,6 +26,7 @@ def _O():
     O.svtb200_oracle_noise_detect_decimated.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64,
                                                         C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     O.svtb200_oracle_edge_detection.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+    O.svtb200_oracle_homogeneous_regions.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     O.svtb200_oracle_edge_cu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_uint64, C.c_void_p]
     return O
 
@@ -196,6 +197,7 @@ def _E():
     E.pa_emu_noise_detect.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_uint64, C.c_uint64, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p]
     E.pa_emu_edge_detection.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    E.pa_emu_homogeneous.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
     E.pa_emu_edge_cu.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
     return E
 
@@ -275,7 +277,7 @@ def test_oracle_noise_detection_pinned_inside_real_encodes(args, method):
     out = dict(l.split() for l in r.stdout.decode().strip().splitlines() if len(l.split()) == 2)
     assert int(out["noise_method"]) == method, out
     assert int(out["noise_pics"]) >= 2 and int(out["noise_flat_set"]) > 0, out       # pictures were comparable and flags were set
-    for k in ("noise_bad", "edge_bad", "edge_cu_bad", "sb_bad", "stats_bad"):
+    for k in ("noise_bad", "edge_bad", "edge_cu_bad", "homog_bad", "sb_bad", "stats_bad"):
         assert int(out[k]) == 0, out
 
 
@@ -298,6 +300,36 @@ def test_kernel_source_edge_maps_on_the_cpu(w, h):
     got_cu, mg = np.full_like(want_cu, 3), np.zeros(1, np.uint32)
     _E().pa_emu_edge_cu(y_mean.ctypes.data, cb.ctypes.data, cr.ctypes.data, logo.ctypes.data, w, h, got_cu.ctypes.data, mg.ctypes.data)
     assert (got_cu == want_cu).all() and want_cu.any()
+
+
+def _variances(rng, w, h):
+    """block statistics with flat and busy super-blocks (the homogeneous-area flag both ways), some 64x64 variances below SB_LOW_VAR_TH"""
+    n_sb = ((w + 63) // 64) * ((h + 63) // 64)
+    var = rng.integers(0, 40, size=(n_sb, 85)).astype(np.uint16)
+    busy = rng.integers(0, 2, size=n_sb).astype(bool)
+    var[busy, 21:] = rng.integers(0, 1500, size=(int(busy.sum()), 64))
+    var[:, 0] = rng.integers(0, 12, size=n_sb)
+    return var
+
+
+def oracle_homogeneous(var, w, h):
+    n_sb = var.shape[0]
+    vv, hom, cnt = np.zeros((n_sb, 4), np.uint64), np.full(n_sb, 7, np.uint8), np.zeros(3, np.uint64)
+    _O().svtb200_oracle_homogeneous_regions(var.ctypes.data, w, h, 5, 64 * 64, vv.ctypes.data, hom.ctypes.data, cnt.ctypes.data)
+    return vv, hom, cnt
+
+
+@pytest.mark.parametrize("w,h", [(832, 704), (456, 280)])
+def test_kernel_source_homogeneous_regions_on_the_cpu(w, h):
+    """(the oracle itself is pinned inside real encodes: homog_bad 0 in test_oracle_noise_detection_pinned_inside_real_encodes)"""
+    rng = np.random.default_rng(h)
+    var = _variances(rng, w, h)
+    want = oracle_homogeneous(var, w, h)
+    got = [np.zeros_like(want[0]), np.full_like(want[1], 9), np.zeros(3, np.uint64)]
+    _E().pa_emu_homogeneous(var.ctypes.data, w, h, 5, 64 * 64, *[g.ctypes.data for g in got])
+    for g, wv in zip(got, want):
+        assert (g == wv).all()
+    assert want[1].any() and not want[1].all() and want[2][1] > 0
 
 
 # ---------------------------------------------------------------------------------------------- CUDA
@@ -413,5 +445,15 @@ def test_cuda_edge_maps(w, h, pic):
             assert (D.down(d, o) == wv).all(), name
         assert (D.down(d_cu, want_cu) == want_cu).all()
         assert want_cu.any() == (pic % 4 == 0)
+        # determine_homogeneous_region_in_picture on a second set of statistics
+        L.svtb200_homogeneous_regions_dev.argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_uint32, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        var2 = _variances(rng, w, h)
+        want_h = oracle_homogeneous(var2, w, h)
+        outs_h = [np.zeros_like(want_h[0]), np.full_like(want_h[1], 9), np.zeros(3, np.uint64)]
+        d_h = [D.up(o) for o in outs_h]
+        D.ctx.check(L.svtb200_homogeneous_regions_dev(hd, D.up(var2), w, h, 5, 64 * 64, *d_h), "homogeneous_regions")
+        D.ctx.sync()
+        for d, o, wv in zip(d_h, outs_h, want_h):
+            assert (D.down(d, o) == wv).all()
     finally:
         D.close()
