@@ -503,6 +503,8 @@ def encoder_all_gpus_record(world, clip4k):
         ref = run_encoder(APP_REF, yuv, os.path.join(d, "ref.ivf"), 3840, 2160, n_frames, 16, 8, 1)
         gpu = run_encoder(APP_B200, yuv, os.path.join(d, "b200.ivf"), 3840, 2160, n_frames, 16, 8, 1,
                           {"SVT_VP9_GPU": ",".join(str(i) for i in range(world)), "SVT_VP9_GPU_REPORT": rep})
+        if gpu["md5"] != ref["md5"]:
+            gpu["difference"] = bitstream_difference(os.path.join(d, "ref.ivf"), os.path.join(d, "b200.ivf"))
         return {"frames": n_frames, "gpus": world, "reference": ref, "b200": gpu, "b200_gpu_report": gpu_report(rep),
                 "bitstream_identical": bool(ref["md5"]) and ref["md5"] == gpu["md5"], "speedup": (gpu["fps"] / ref["fps"]) if ref["fps"] and gpu["fps"] else None,
                 "note": "one EbEncHandle pipeline, motion estimation and deblocking of its pictures dealt to %d GPUs mini-GOP by mini-GOP (no exchange between devices)" % world}
