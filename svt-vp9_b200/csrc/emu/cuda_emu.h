@@ -109,6 +109,22 @@ template <class T> static inline T emu_shfl(T v, int src_lane) {
 template <class T> static inline T __shfl_xor_sync(unsigned, T v, int m) { return emu_shfl(v, (int)(threadIdx.x & 31) ^ m); }
 template <class T> static inline T __shfl_down_sync(unsigned, T v, int d) { int l = (threadIdx.x & 31) + d; return emu_shfl(v, l > 31 ? (int)(threadIdx.x & 31) : l); }
 template <class T> static inline T __shfl_sync(unsigned, T v, int l) { return emu_shfl(v, l); }
+template <class T> static inline T __shfl_up_sync(unsigned, T v, int d) { int l = (int)(threadIdx.x & 31) - d; return emu_shfl(v, l < 0 ? (int)(threadIdx.x & 31) : l); }
+/* full-mask votes (every lane of the warp participates; lanes past the block's last thread do not exist) */
+static inline unsigned __ballot_sync(unsigned, int pred) {
+    const unsigned lane = threadIdx.x & 31, first = threadIdx.x & ~31u;
+    const unsigned nthreads = blockDim.x * blockDim.y * blockDim.z, lanes = nthreads - first < 32 ? nthreads - first : 32;
+    emu_warp_xchg[lane] = pred ? 1 : 0;
+    emu_warp_barrier->arrive_and_wait();
+    unsigned m = 0;
+    for (unsigned i = 0; i < lanes; i++) m |= (unsigned)(emu_warp_xchg[i] & 1) << i;
+    emu_warp_barrier->arrive_and_wait();
+    return m;
+}
+static inline int __all_sync(unsigned mask, int pred) { return __ballot_sync(mask, !pred) == 0; }
+static inline int __any_sync(unsigned mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+static inline int __ffs(int x) { return __builtin_ffs(x); }
+static inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 
 template <class F> static void emu_launch(dim3 grid, dim3 block, size_t smem_bytes, F body) {
     const unsigned nthreads = block.x * block.y * block.z, nwarps = (nthreads + 31) / 32;

@@ -235,3 +235,83 @@ def test_cuda_rate_multi_launch():
         for d in dev:
             L.svtb200_dev_free(h, d)
         ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------- kernel sources on the CPU
+class _RateEmuBatch(C.Structure):
+    _fields_ = [("tx_size", C.c_int32), ("n", C.c_int32), ("qcoeff", C.c_void_p), ("eob", C.c_void_p), ("blocks", C.c_void_p), ("token_costs", C.c_void_p),
+                ("scan", C.c_void_p * 4), ("nb", C.c_void_p * 4), ("rate", C.c_void_p)]
+
+
+class _PackEmuBatch(C.Structure):
+    _fields_ = [("tx_size", C.c_int32), ("n", C.c_int32), ("jobs", C.c_void_p), ("qcoeff", C.c_void_p), ("eob", C.c_void_p), ("scan", C.c_void_p * 4)]
+
+
+def _tables(tx_size):
+    T = H.vp9_tables()
+    scans = [np.ascontiguousarray(T["scan_%d_%d" % (tx_size, 0 if tx_size == 3 else t)], dtype=np.int16) for t in range(4)]
+    nbs = [np.ascontiguousarray(T["nb_%d_%d" % (tx_size, 0 if tx_size == 3 else t)], dtype=np.int16) for t in range(4)]
+    return scans, nbs
+
+
+@pytest.mark.parametrize("costs", ["default", "random"])
+def test_kernel_source_rate_on_the_cpu(costs):
+    """rate_multi_kernel (csrc/rate_kernel.cuh) under the CPU emulation: all four transform sizes as the batches of ONE launch, every kind of
+    block, against the oracle (which the tests above pin against the reference's coeff_rate_estimate)"""
+    rng = np.random.default_rng(7)
+    tc = _token_costs(rng, costs)
+    T = H.vp9_tables()
+    tabs = [np.ascontiguousarray(T[k]) for k in ("rate_vtok", "rate_vcost", "rate_c6lo", "rate_c6hi")]
+    keep, batches, want = [], (_RateEmuBatch * 4)(), []
+    for ts in range(4):
+        parts = [_blocks(rng, ts, 40 if ts < 3 else 12, kind) for kind in KINDS]
+        q, eob, blk = (np.ascontiguousarray(np.concatenate([p[i] for p in parts])) for i in range(3))
+        scans, nbs = _tables(ts)
+        tcs, rate = np.ascontiguousarray(tc[ts]), np.full(len(eob), -7, np.int32)
+        keep += [q, eob, blk, scans, nbs, tcs, rate]
+        b = batches[ts]
+        b.tx_size, b.n, b.qcoeff, b.eob, b.blocks, b.token_costs, b.rate = ts, len(eob), q.ctypes.data, eob.ctypes.data, blk.ctypes.data, tcs.ctypes.data, rate.ctypes.data
+        for t in range(4):
+            b.scan[t], b.nb[t] = scans[t].ctypes.data, nbs[t].ctypes.data
+        want.append((_oracle_rate(ts, q, eob, blk, tc), rate))
+    E = H.emu()
+    E.rate_emu_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    assert E.rate_emu_run(C.addressof(batches), 4, *[t.ctypes.data for t in tabs]) == 0
+    for ts, (w, got) in enumerate(want):
+        assert (got == w).all(), (ts, np.flatnonzero(got != w)[:5])
+
+
+def test_kernel_source_pack_on_the_cpu():
+    """pack_sum_kernel + pack_kernel (csrc/pack_kernel.cuh) under the CPU emulation: the scan-order prefix (eob entries, padded with a zero to an
+    even count) of every block of three batches, back to back, against a direct restatement of what tokenize_b reads (vp9_tokenize.c:275)"""
+    rng = np.random.default_rng(9)
+    T = H.vp9_tables()
+    keep, batches, runs = [], (_PackEmuBatch * 3)(), []
+    for k, ts in enumerate((3, 1, 0)):
+        parts = [_blocks(rng, ts, 50 if ts < 3 else 20, kind) for kind in ("typical", "sparse", "empty", "full", "dc")]
+        q, eob, blk = (np.ascontiguousarray(np.concatenate([p[i] for p in parts])) for i in range(3))
+        jobs = np.zeros(len(eob), dtype=api.TX_JOB_DTYPE)
+        jobs["tx_type"] = blk["tx_type"]
+        scans, _ = _tables(ts)
+        keep += [q, eob, jobs, scans]
+        b = batches[k]
+        b.tx_size, b.n, b.jobs, b.qcoeff, b.eob = ts, len(eob), jobs.ctypes.data, q.ctypes.data, eob.ctypes.data
+        for t in range(4):
+            b.scan[t] = scans[t].ctypes.data
+        for j in range(len(eob)):
+            e = int(eob[j])
+            run = q[j][scans[int(jobs["tx_type"][j]) & 3][:e]].astype(np.int16)
+            runs.append(np.concatenate([run, np.zeros(e & 1, np.int16)]))
+    want_stream = np.concatenate(runs)
+    want_off = np.concatenate([[0], np.cumsum([len(r) for r in runs])]).astype(np.uint32)
+    stream, off = np.full(len(want_stream) + 64, 0x7777, np.int16), np.zeros(len(runs) + 1, np.uint32)
+    E = H.emu()
+    E.pack_emu_run.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint32, C.c_void_p]
+    assert E.pack_emu_run(C.addressof(batches), 3, stream.ctypes.data, len(stream), off.ctypes.data) == 0
+    assert (off == want_off).all()
+    assert (stream[:len(want_stream)] == want_stream).all() and (stream[len(want_stream):] == 0x7777).all()
+    # capacity smaller than the stream: the total is still reported, blocks that do not fit are left out, nothing is written past the capacity
+    cap = int(want_off[len(runs) // 2])
+    stream2, off2 = np.full(len(want_stream) + 64, 0x7777, np.int16), np.zeros(len(runs) + 1, np.uint32)
+    assert E.pack_emu_run(C.addressof(batches), 3, stream2.ctypes.data, cap, off2.ctypes.data) == 0
+    assert off2[-1] == want_off[-1] and (stream2[:cap] == want_stream[:cap]).all() and (stream2[cap:] == 0x7777).all()
