@@ -21,6 +21,9 @@
 #include <vector>
 
 struct uint2 { unsigned x, y; };
+struct alignas(16) uint4 { unsigned x, y, z, w; };
+static inline uint2 make_uint2(unsigned x, unsigned y) { uint2 r; r.x = x; r.y = y; return r; }
+static inline uint4 make_uint4(unsigned x, unsigned y, unsigned z, unsigned w) { uint4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
 struct uint3_emu { unsigned x, y, z; };
 struct dim3 { unsigned x, y, z; dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {} };
 extern thread_local uint3_emu threadIdx, blockIdx;
@@ -40,7 +43,14 @@ extern thread_local uint64_t *emu_warp_xchg; /* 32 slots per warp */
 #define __grid_constant__
 
 static inline void __syncthreads() { emu_block_barrier->arrive_and_wait(); }
-static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier->arrive_and_wait(); }
+/* __syncwarp(mask): the whole warp, or -- for the aligned groups of 4 / 8 / 16 lanes the transform kernels synchronise -- a barrier of that group
+ * alone (groups of one warp may run through different numbers of them, e.g. only the blocks that reconstruct) */
+extern thread_local std::barrier<> **emu_group_barriers; /* [3][8]: groups of 4, 8, 16 lanes of this thread's warp */
+static inline void __syncwarp(unsigned mask = 0xffffffffu) {
+    const int n = __builtin_popcount(mask);
+    if (n == 4 || n == 8 || n == 16) { emu_group_barriers[(n == 4 ? 0 : n == 8 ? 1 : 2) * 8 + __builtin_ctz(mask) / n]->arrive_and_wait(); return; }
+    emu_warp_barrier->arrive_and_wait();
+}
 /* named barrier over the upper half of the CTA's threads (bar.sync 1, blockDim/2 on the device) */
 static inline void emu_sync_upper_half() { emu_upper_half_barrier->arrive_and_wait(); }
 template <class T> static inline T __ldg(const T *p) { return *p; }
@@ -133,8 +143,13 @@ template <class F> static void emu_launch(dim3 grid, dim3 block, size_t smem_byt
     for (unsigned bz = 0; bz < grid.z; bz++) for (unsigned by = 0; by < grid.y; by++) for (unsigned bx = 0; bx < grid.x; bx++) {
         std::barrier<> bar(nthreads);
         std::barrier<> upper(nthreads >= 2 ? nthreads - nthreads / 2 : 1);
-        std::vector<std::unique_ptr<std::barrier<>>> wbars;
-        for (unsigned w = 0; w < nwarps; w++) wbars.emplace_back(new std::barrier<>(std::min(32u, nthreads - w * 32)));
+        std::vector<std::unique_ptr<std::barrier<>>> wbars, gbars;
+        std::vector<std::barrier<> *> gptr((size_t)nwarps * 24, nullptr);
+        for (unsigned w = 0; w < nwarps; w++) {
+            wbars.emplace_back(new std::barrier<>(std::min(32u, nthreads - w * 32)));
+            for (unsigned si = 0; si < 3; si++)
+                for (unsigned gi = 0; gi < 32u / (4u << si); gi++) { gbars.emplace_back(new std::barrier<>(4u << si)); gptr[(size_t)w * 24 + si * 8 + gi] = gbars.back().get(); }
+        }
         std::vector<std::thread> ts;
         for (unsigned t = 0; t < nthreads; t++)
             ts.emplace_back([&, t] {
@@ -142,6 +157,7 @@ template <class F> static void emu_launch(dim3 grid, dim3 block, size_t smem_byt
                 blockIdx = {bx, by, bz}; blockDim = block; gridDim = grid;
                 emu_dyn_smem = (uint8_t *)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
                 emu_block_barrier = &bar; emu_upper_half_barrier = &upper; emu_warp_barrier = wbars[t / 32].get(); emu_warp_xchg = xchg.data() + (size_t)(t / 32) * 32;
+                emu_group_barriers = gptr.data() + (size_t)(t / 32) * 24;
                 body();
             });
         for (auto &th : ts) th.join();
@@ -150,5 +166,5 @@ template <class F> static void emu_launch(dim3 grid, dim3 block, size_t smem_byt
 #define SVTB200_EMU_DEFINE_STATE                                              \
     thread_local uint3_emu threadIdx, blockIdx; thread_local dim3 blockDim, gridDim; \
     thread_local uint8_t *emu_dyn_smem; thread_local std::barrier<> *emu_block_barrier, *emu_warp_barrier, *emu_upper_half_barrier; \
-    thread_local uint64_t *emu_warp_xchg;
+    thread_local uint64_t *emu_warp_xchg; thread_local std::barrier<> **emu_group_barriers;
 #endif
