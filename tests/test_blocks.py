@@ -149,6 +149,35 @@ def test_oracle_open_loop_partition_geometry():
         assert int(b["mv"][0][1]) == 2 * int(r["x_mv_l1"] if d == 1 else r["x_mv_l0"])
 
 
+@pytest.mark.parametrize("subpel", [1, 0])
+@pytest.mark.parametrize("size", [(200, 136), (640, 384), (1920, 1080)])
+def test_kernel_source_block_walk_on_the_cpu(size, subpel):
+    """the per-block arithmetic the two kernels of csrc/blocks.cu evaluate (csrc/blocks_device.cuh), on the CPU: descriptors of every block and
+    plane -- every clamp side, both use_subpel_flag values, compound blocks -- and the open-loop partition, against the oracle"""
+    w, h = size
+    rng = np.random.default_rng(w + subpel)
+    refs = [_planes(rng, w, h), _planes(rng, w, h)]
+    dst = [np.zeros(((h + 63) & ~63, (w + 63) & ~63), np.uint8), np.zeros((((h + 63) & ~63) // 2, ((w + 63) & ~63) // 2), np.uint8),
+           np.zeros((((h + 63) & ~63) // 2, ((w + 63) & ~63) // 2), np.uint8)]
+    pic = _picture(w, h, refs, dst, lambda a: a.ctypes.data, subpel)
+    blocks = _random_blocks(rng, w, h, 400)
+    want = _oracle_expand(blocks, pic)
+    E = H.emu()
+    E.blocks_emu_expand.argtypes = [C.c_void_p, C.c_int, C.POINTER(api.PredPicture), C.c_void_p]
+    got = (api.PredBlock * (3 * len(blocks)))()
+    E.blocks_emu_expand(blocks.ctypes.data, len(blocks), C.byref(pic), C.addressof(got))
+    assert bytes(got) == bytes(want)
+    if w % 16 == 0 and h % 16 == 0:
+        O = H.oracle()
+        O.svtb200_oracle_me_best_blocks.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        E.blocks_emu_me_best.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+        me = _synthetic_me(rng, w, h)
+        a, b = np.zeros((w // 16) * (h // 16), dtype=api.INTER_BLOCK_DTYPE), np.zeros((w // 16) * (h // 16), dtype=api.INTER_BLOCK_DTYPE)
+        n = O.svtb200_oracle_me_best_blocks(me.ctypes.data, w, h, a.ctypes.data)
+        assert E.blocks_emu_me_best(me.ctypes.data, w, h, b.ctypes.data) == n and n > 0
+        assert a[:n].tobytes() == b[:n].tobytes()
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("subpel", [1, 0])
 def test_cuda_block_walk_descriptors_and_prediction(subpel):
