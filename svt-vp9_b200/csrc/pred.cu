@@ -115,21 +115,6 @@ extern "C" int svtb200_intra_edges_dev(SvtB200Ctx *c, const uint8_t *plane, int3
     return SVTB200_OK;
 }
 
-/* ---- full-loop distortion: one warp per transform block ---- */
-__global__ void __launch_bounds__(256) full_dist_kernel(int nn, int n, const int16_t *coeff, const int16_t *rc, const uint16_t *eob, uint64_t *dist) {
-    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
-    if (k >= n) return;
-    const int16_t *a = coeff + (size_t)k * nn, *b = rc + (size_t)k * nn;
-    uint32_t res = 0, pred = 0;
-    for (int i = lane; i < nn; i += 32) {
-        const int c = a[i], d = (int16_t)(c - b[i]); /* sq_r16to32 takes an int16_t (EbPictureOperators_C.c:264) */
-        res += (uint32_t)(d * d);
-        pred += (uint32_t)(c * c);
-    }
-    for (int o = 16; o > 0; o >>= 1) { res += __shfl_xor_sync(0xffffffffu, res, o); pred += __shfl_xor_sync(0xffffffffu, pred, o); }
-    if (lane == 0) { dist[2 * k] = eob[k] ? res : pred; dist[2 * k + 1] = pred; }
-}
-
 extern "C" int svtb200_full_distortion_batch_dev(SvtB200Ctx *c, int tx_size, int n, const int16_t *coeff, const int16_t *recon_coeff,
                                                  const uint16_t *eob, uint64_t *dist) {
     if (!c || tx_size < 0 || tx_size > 3 || n < 0 || (n && (!coeff || !recon_coeff || !eob || !dist))) return SVTB200_EINVAL;

@@ -173,4 +173,18 @@ __global__ void __launch_bounds__(PRED_THREADS) pred_kernel(const SvtB200PredBlo
         __syncthreads();
     }
 }
+/* ---- full-loop distortion: one warp per transform block ---- */
+__global__ void __launch_bounds__(256) full_dist_kernel(int nn, int n, const int16_t *coeff, const int16_t *rc, const uint16_t *eob, uint64_t *dist) {
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= n) return;
+    const int16_t *a = coeff + (size_t)k * nn, *b = rc + (size_t)k * nn;
+    uint32_t res = 0, pred = 0;
+    for (int i = lane; i < nn; i += 32) {
+        const int c = a[i], d = (int16_t)(c - b[i]); /* sq_r16to32 takes an int16_t (EbPictureOperators_C.c:264) */
+        res += (uint32_t)(d * d);
+        pred += (uint32_t)(c * c);
+    }
+    for (int o = 16; o > 0; o >>= 1) { res += __shfl_xor_sync(0xffffffffu, res, o); pred += __shfl_xor_sync(0xffffffffu, pred, o); }
+    if (lane == 0) { dist[2 * k] = eob[k] ? res : pred; dist[2 * k + 1] = pred; }
+}
 #endif

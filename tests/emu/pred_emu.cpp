@@ -26,3 +26,9 @@ extern "C" int intra_edges_emu_run(const uint8_t *plane, int stride, int fw, int
     emu_launch(dim3((unsigned)((n + 1) / 2)), dim3(INTRA_EDGE_THREADS), 0, [&] { intra_edges_kernel(plane, stride, fw, fh, jobs, n, out); });
     return 0;
 }
+
+extern "C" int full_dist_emu_run(int tx_size, int n, const int16_t *coeff, const int16_t *rc, const uint16_t *eob, uint64_t *dist) {
+    const int nn = (4 << tx_size) * (4 << tx_size);
+    emu_launch(dim3((unsigned)((n + 7) / 8)), dim3(256), 0, [&] { full_dist_kernel(nn, n, coeff, rc, eob, dist); });
+    return 0;
+}

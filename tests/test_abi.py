@@ -109,3 +109,35 @@ def test_device_padding_matches_reference_generate_padding(w, h, px, py):
     ctx.close()
     assert (got == want).all()
     assert (np.pad(buf[py:py + h, px:px + w], ((py, py), (px, px)), mode="edge") == got).all()
+
+
+@pytest.mark.parametrize("w,h", [(640, 384), (200, 136), (456, 248)])
+def test_kernel_sources_front_end_on_the_cpu(w, h):
+    """pa_pad_full_kernel and pa_decimate_kernel (csrc/pa_front_kernel.cuh) under the CPU emulation: what svtb200_picture_upload_luma runs on the device
+    after its 2-D copy of the picture area -- the device layout of the full plane (the host's padded row inside it, beyond it the bytes a read past the
+    end of the contiguous host row finds) and the 1/4, 1/16 planes with their padding -- against the reference layout (frames.pa_planes)"""
+    import ctypes as C
+    frames = importlib.import_module("svt-vp9_b200.frames")
+    rng = np.random.default_rng(h)
+    luma = rng.integers(0, 256, size=(h, w), dtype=np.uint8)
+    pl = frames.pa_planes(luma)
+    poisoned = pl["full"].copy()
+    poisoned[:frames.FULL_PAD] = 0x55            # the padding must be regenerated, not copied
+    poisoned[:, :frames.FULL_PAD] = 0xAA
+    dev_ox, dpitch = 80, (w + 80 + 96 + 15) & ~15           # SVTB200_DEV_PAD_L / _R of csrc/common.cuh
+    rows = h + 2 * frames.FULL_PAD
+    dev = np.full((rows, dpitch), 0x33, np.uint8)
+    qw, qh, sw, sh = (w + 1) // 2, (h + 1) // 2, (w + 3) // 4, (h + 3) // 4
+    qstride, sstride = (qw + 2 * frames.QUARTER_PAD + 15) & ~15, (sw + 2 * frames.SIXTEENTH_PAD + 15) & ~15
+    quarter = np.full((qh + 2 * frames.QUARTER_PAD, qstride), 0x33, np.uint8)
+    sixteenth = np.full((sh + 2 * frames.SIXTEENTH_PAD, sstride), 0x33, np.uint8)
+    E = H.emu()
+    E.pa_emu_front.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int]
+    E.pa_emu_front(poisoned.ctypes.data, poisoned.shape[1], frames.FULL_PAD, w, h, dev.ctypes.data, dpitch, dev_ox, quarter.ctypes.data, qstride, frames.QUARTER_PAD,
+                   sixteenth.ctypes.data, sstride, frames.SIXTEENTH_PAD)
+    want = pl["full"]
+    x0, hp = dev_ox - frames.FULL_PAD, want.shape[1]
+    assert (dev[:, x0:x0 + hp] == want).all()
+    right = dpitch - (x0 + hp)
+    assert right >= 24 and (dev[:-1, x0 + hp:] == want[1:, :right]).all() and (dev[1:, :x0] == want[:-1, hp - x0:]).all()
+    assert (quarter[:, :pl["quarter"].shape[1]] == pl["quarter"]).all() and (sixteenth[:, :pl["sixteenth"].shape[1]] == pl["sixteenth"]).all()

@@ -88,3 +88,24 @@ def test_cuda_chroma_statistics(size):
         for d in dev:
             L.svtb200_dev_free(hd, d)
         ctx.close()
+
+
+@pytest.mark.parametrize("size", [(640, 384), (456, 280)])
+def test_kernel_sources_chroma_statistics_on_the_cpu(size):
+    """chroma_mean_kernel and the two chroma histogram kernels (csrc/pa_chroma_kernel.cuh) under the CPU emulation, against the oracle"""
+    w, h = size
+    rng = np.random.default_rng(w + 1)
+    stride = ((w // 2 + 7) & ~7) + 16
+    cb = H.aligned_copy(rng.integers(0, 256, size=((h + 63) // 64 * 32 + 8, stride), dtype=np.uint8))
+    cr = H.aligned_copy((rng.integers(0, 64, size=cb.shape) + 100).astype(np.uint8))
+    rw = rh = 4
+    mb, mr, hist, avg, s16 = _oracle(cb, cr, w, h, rw, rh)
+    E = H.emu()
+    E.pa_emu_chroma_mean.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    E.pa_emu_chroma_histogram.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    gb, gr = np.full_like(mb, 9), np.full_like(mr, 9)
+    E.pa_emu_chroma_mean(cb.ctypes.data, cr.ctypes.data, stride, w, h, gb.ctypes.data, gr.ctypes.data)
+    assert (gb == mb).all() and (gr == mr).all() and mb.any()
+    gh, ga, gs = np.zeros_like(hist), np.zeros_like(avg), np.zeros_like(s16)
+    E.pa_emu_chroma_histogram(cb.ctypes.data, cr.ctypes.data, stride, w, h, rw, rh, gh.ctypes.data, ga.ctypes.data, gs.ctypes.data)
+    assert (gh == hist).all() and (ga == avg).all() and (gs == s16).all()

@@ -142,6 +142,22 @@ def _oracle_distortion(tx_size, coeff, rc, eob):
     return out
 
 
+@pytest.mark.parametrize("tx_size", [0, 1, 2, 3])
+def test_kernel_source_full_distortion_on_the_cpu(tx_size):
+    """full_dist_kernel (csrc/pred_device.cuh) under the CPU emulation against the oracle: 32-bit wrapping sums, the eob == 0 rule"""
+    rng = np.random.default_rng(40 + tx_size)
+    nn, n = (4 << tx_size) ** 2, 37
+    coeff = rng.integers(-32768, 32768, size=(n, nn), dtype=np.int16)
+    rc = (coeff.astype(np.int32) + rng.integers(-3000, 3001, size=coeff.shape)).clip(-32768, 32767).astype(np.int16)
+    eob = rng.integers(0, 3, size=n).astype(np.uint16)
+    want = _oracle_distortion(tx_size, coeff, rc, eob)
+    got = np.zeros_like(want)
+    E = H.emu()
+    E.full_dist_emu_run.argtypes = [C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    E.full_dist_emu_run(tx_size, n, coeff.ctypes.data, rc.ctypes.data, eob.ctypes.data, got.ctypes.data)
+    assert (got == want).all() and (eob == 0).any()
+
+
 @pytest.mark.skipif(not H.have_refdrv(), reason="oracle/_ref path driver not built")
 @pytest.mark.parametrize("simd", [0, 1])
 @pytest.mark.parametrize("tx_size", [0, 1, 2, 3])

@@ -131,3 +131,28 @@ def test_cuda_histogram_matches_oracle(w, h, rw, rh):
     ctx.close()
     eh, ea, es = _oracle_hist(st[1], rw, rh)
     assert (hist == eh).all() and (avg == ea).all() and s16 == es
+
+
+# ---------------------------------------------------------------------------------------------- kernel sources on the CPU
+@pytest.mark.parametrize("w,h,res,noise", [(640, 384, 2, 1), (456, 248, 1, 2), (200, 136, 2, 8)])
+def test_kernel_sources_zz_sad_block_stats_histogram_on_the_cpu(w, h, res, noise):
+    """zz_sad_kernel, block_stats_kernel and the two histogram kernels (csrc/zz_kernel.cuh) under the CPU emulation, against the oracle"""
+    pl, st = _pair(w, h, noise, 5)
+    E = H.emu()
+    E.pa_emu_zz_sad.argtypes = [C.POINTER(api.Plane), C.POINTER(api.Plane), C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    E.pa_emu_block_stats.argtypes = [C.POINTER(api.Plane), C.c_int, C.c_int, C.c_void_p, C.c_void_p]
+    E.pa_emu_luma_histogram.argtypes = [C.POINTER(api.Plane), C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64)]
+    want, want_sad = H.oracle_zz_sad(st[1], st[0], w, h, TH_SHIFT[res])
+    got, sad = np.full_like(want, 77), np.zeros_like(want_sad)
+    E.pa_emu_zz_sad(C.byref(st[1][2]), C.byref(st[0][0]), w, h, TH_SHIFT[res], got.ctypes.data, sad.ctypes.data)
+    assert (got == want).all() and (sad == want_sad).all()
+    eym, evar = _oracle_stats(st[1], w, h)
+    # (the statistics kernel reads whole super-blocks: the padded plane holds the samples right of / below a ragged picture)
+    ym, var = np.zeros_like(eym), np.zeros_like(evar)
+    E.pa_emu_block_stats(C.byref(st[1][0]), w, h, ym.ctypes.data, var.ctypes.data)
+    assert (ym == eym).all() and (var == evar).all() and var.max() > 0
+    for rw, rh in ((4, 4), (2, 3)):
+        eh, ea, es = _oracle_hist(st[1], rw, rh)
+        hist, avg, s16 = np.zeros_like(eh), np.zeros_like(ea), C.c_uint64()
+        E.pa_emu_luma_histogram(C.byref(st[1][2]), rw, rh, hist.ctypes.data, avg.ctypes.data, C.byref(s16))
+        assert (hist == eh).all() and (avg == ea).all() and s16.value == es
